@@ -1,0 +1,137 @@
+/*
+ * include/scpp_b200.h — C-ABI of libscpp_b200.so: the drop-in boundary of the B200-native batched
+ * successive-convexification engine.  Plain pointers and sizes only; all arrays are HOST memory owned by the
+ * caller, instance-major and C-contiguous; the opaque engine owns every device buffer.
+ *
+ * Each entry point names the reference interface (EmbersArc/SCpp, commit d45d2c8) it replaces.  The reference is a
+ * single-instance C++ API; here every call acts on a batch of N independent problem instances that share the
+ * model/algorithm parameter files and differ in their boundary states (the reference's own, commented-out,
+ * Monte-Carlo recipe: scpp_models/src/rocketQuat.cpp:203-227).
+ *
+ * There is no CPU execution path: every compute entry point returns SCPP_B200_ERR_CUDA if no CUDA device is usable.
+ */
+#ifndef SCPP_B200_H
+#define SCPP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCPP_B200_OK 0
+#define SCPP_B200_ERR_ARG 1
+#define SCPP_B200_ERR_CUDA 2
+#define SCPP_B200_ERR_IO 3
+#define SCPP_B200_ERR_NCCL 4
+#define SCPP_B200_ERR_UNSUPPORTED 5
+
+/* model selector: the reference picks the model at compile time, scpp_core/include/activeModel.hpp:6-10 */
+#define SCPP_B200_MODEL_ROCKETQUAT 0 /* scpp_models/src/rocketQuat.cpp, nx=14 nu=4 np=10 */
+#define SCPP_B200_MODEL_ROCKET2D 1   /* scpp_models/src/rocket2d.cpp,  nx=6  nu=2 np=6  */
+
+/* RocketQuat::Parameters (scpp_models/include/rocketQuat.hpp:50-85) and Rocket2d::Parameters
+ * (scpp_models/include/rocket2d.hpp:51-84) as loaded from model.info; angles in radians.
+ * Rocket2d uses g_I[0..1], J_B[0], r_T_B[0..1], m. */
+typedef struct {
+    double g_I[3];
+    double J_B[3];
+    double r_T_B[3];
+    double alpha_m;
+    double m;
+    double T_min, T_max, t_max;
+    double gimbal_max, theta_max, gamma_gs, w_B_max;
+    double final_time;
+    int exact_minimum_thrust;
+    int enable_roll_control;
+    int constrain_initial_final;
+    int pad_;
+} scpp_b200_model_params;
+
+typedef struct {
+    double feastol, abstol, reltol; /* ECOS defaults: 1e-8 */
+    int maxit;                      /* ECOS default: 100 */
+} scpp_b200_ipm_settings;
+
+/* SC.info as read by SCAlgorithm::loadParameters (scpp_core/src/SCAlgorithm.cpp:22-46) + engine knobs */
+typedef struct {
+    int K;
+    int free_final_time, interpolate_input, nondimensionalize;
+    double weight_time, weight_trust_region_time, weight_trust_region_trajectory, weight_virtual_control;
+    double nu_tol, delta_tol;
+    int max_iterations;
+    int nsub;         /* RK4 sub-steps per shooting interval (reference: RKF78 x 5, discretizationImplementation.hpp:154) */
+    int keep_history; /* keep every iterate for scpp_b200_get_iterate (SCAlgorithm::getAllSolutions) */
+    int pad_;
+    scpp_b200_ipm_settings ipm;
+} scpp_b200_sc_config;
+
+typedef struct scpp_b200_engine scpp_b200_engine;
+
+/* per (instance, iteration) record returned by scpp_b200_get_info: what SCAlgorithm::iterate prints
+ * (SCAlgorithm.cpp:117-128) plus the solver certificate */
+#define SCPP_B200_INFO_STRIDE 10 /* norm1_nu, sum_delta, delta_sigma, sigma, weight_tr_used, ipm_iterations, ipm_status, pres, dres, relgap */
+
+int scpp_b200_version(void);
+const char *scpp_b200_last_error(void);
+int scpp_b200_device_count(void); /* 0 if no usable CUDA device */
+int scpp_b200_model_dims(int model, int *nx, int *nu, int *np);
+void scpp_b200_default_config(int model, scpp_b200_sc_config *cfg); /* values of scpp_models/config/<Model>/SC.info */
+
+/* ---- parameter files (host logic; usable without a GPU) -------------------------------------------------------
+ * replaces ParameterServer (scpp_core/utils/include/parameterServer.hpp:34-127: Boost INFO files) and
+ * RocketQuat::Parameters::loadFromFile (rocketQuat.cpp:234-289) / Rocket2d::Parameters::loadFromFile (rocket2d.cpp:150-196).
+ * x_init / x_final receive the boundary states built there (nx doubles each). */
+int scpp_b200_load_model_info(const char *path, int model, scpp_b200_model_params *params, double *x_init, double *x_final);
+int scpp_b200_load_sc_info(const char *path, scpp_b200_sc_config *cfg); /* SCAlgorithm::loadParameters */
+
+/* ---- engine life cycle ------------------------------------------------------------------------------------------
+ * replaces SCAlgorithm::SCAlgorithm(Model::ptr_t) + SCAlgorithm::initialize() (SCAlgorithm.cpp:14-20,48-64):
+ * allocates all device state for n_instances problem instances on CUDA device `device`. */
+int scpp_b200_create(int model, const scpp_b200_model_params *params, const scpp_b200_sc_config *cfg,
+                     int n_instances, int device, scpp_b200_engine **out);
+void scpp_b200_destroy(scpp_b200_engine *e);
+
+/* boundary states of every instance, dimensional: x_init [N][nx], x_final [N][nx] (model->p.x_init / x_final,
+ * mutated by callers such as scpp/src/SC_sim.cpp:36).  Host -> device copy. */
+int scpp_b200_set_boundary_states(scpp_b200_engine *e, const double *x_init, const double *x_final);
+
+/* SCAlgorithm::solve(bool warm_start) (SCAlgorithm.cpp:134-189): the whole outer loop on the device —
+ * per iteration K1 multiple shooting (discretization::multipleShooting, discretization.cpp:42-55),
+ * K2 SOCP solve (ECOSSolver::solve, SCAlgorithm.cpp:78) fused with readSolution and the convergence logic
+ * (SCAlgorithm.cpp:100-131).  A failed instance is flagged, never aborts the batch (reference: std::terminate, :94-98). */
+int scpp_b200_solve(scpp_b200_engine *e, int warm_start);
+
+/* SCAlgorithm::getSolution (SCAlgorithm.cpp:212-215): final trajectories REDIMENSIONALISED (:182-187).
+ * X [N][K][nx], U [N][K][nu], t [N]; iterations [N]; flags [N]: 0 not converged, 1 converged, 2 solver failure.
+ * Any pointer may be NULL.  Device -> host copy. */
+int scpp_b200_get_solution(scpp_b200_engine *e, double *X, double *U, double *t, int *iterations, int *flags);
+
+/* SCAlgorithm::getAllSolutions (SCAlgorithm.cpp:217-232): iterate `it` (0 = initial guess) of every instance in the
+ * units the algorithm iterates on (nondimensional when cfg.nondimensionalize).  Needs cfg.keep_history. */
+int scpp_b200_get_iterate(scpp_b200_engine *e, int it, double *X, double *U, double *t);
+int scpp_b200_get_info(scpp_b200_engine *e, double *info /* [N][max_iterations][SCPP_B200_INFO_STRIDE] */);
+
+/* device timing of the last solve (CUDA events on the engine stream): ms in K1, ms in K2, ms total, kernel launches,
+ * outer iterations executed, sum over instances of iterations executed */
+int scpp_b200_last_timing(scpp_b200_engine *e, double *ms_discretize, double *ms_socp, double *ms_total,
+                          int *kernel_launches, int *outer_iterations, long long *instance_iterations);
+size_t scpp_b200_device_bytes(scpp_b200_engine *e);
+
+/* ---- test hooks on the two hot paths ----------------------------------------------------------------------------
+ * K1 alone: discretization::multipleShooting for n trajectories.  X [n][K][nx], U [n][K][nu], sigma [n], par [n][np];
+ * outputs in the reference's layout (column-major Eigen blocks per interval, DiscretizationData
+ * scpp_core/include/discretizationData.hpp:8-20): A [n][K-1][nx*nx], B,C [n][K-1][nx*nu], s,z [n][K-1][nx]. */
+int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const double *X, const double *U, const double *sigma,
+                         const double *par, double *A, double *B, double *C, double *s, double *z);
+
+/* ---- multi-GPU: one process (rank) per GPU, the batch is sharded by the caller ----------------------------------
+ * the only data-path collective is one ncclAllGather of the per-instance convergence flags per outer iteration. */
+int scpp_b200_comm_unique_id(char id[128]);
+int scpp_b200_comm_init(scpp_b200_engine *e, int nranks, int rank, const char id[128]);
+long long scpp_b200_global_active(scpp_b200_engine *e); /* instances still iterating over all ranks after the last solve */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

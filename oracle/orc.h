@@ -166,6 +166,12 @@ void orc_rq_perturb(const orc_rq_params *nominal, const double *rpy_init, unsign
 double orc_uniform_pm1(unsigned long long seed, unsigned long long instance, unsigned draw);
 
 int orc_num_threads(void);
+/* CPU-baseline driver: n_inst independent cold SC solves, one instance per OpenMP thread (the reference itself is
+ * single-threaded); params_array = n_inst parameter structs, params_stride bytes apart.  Returns the total number of
+ * SC iterations executed.  Output pointers may be NULL. */
+#include <stddef.h>
+int orc_sc_solve_batch(int model, int n_inst, const void *params_array, size_t params_stride, const orc_sc_config *cfg,
+                       int *iters_out, int *conv_out, double *X_out, double *U_out, double *t_out, int nthreads);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,588 @@
+// scpp_b200/csrc/engine.cu — CUDA kernels, the batched SC engine and the C-ABI (include/scpp_b200.h).
+// Built for sm_100a only; there is no CPU execution path in this library.
+#include "../../include/scpp_b200.h"
+#include "sc.cuh"
+#include "info_parser.hpp"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace scpp;
+
+static_assert(sizeof(scpp_b200_model_params) == sizeof(ModelParamsHost), "ABI struct mismatch");
+static_assert(sizeof(scpp_b200_sc_config) == sizeof(ScConfig), "ABI struct mismatch");
+static_assert(SCPP_B200_INFO_STRIDE == INFO_STRIDE, "ABI constant mismatch");
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call)                                                                                                  \
+    do {                                                                                                          \
+        cudaError_t e_ = (call);                                                                                  \
+        if (e_ != cudaSuccess) return fail(SCPP_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int WPB = 4;   // warps (= problem instances) per CTA of the SOCP kernel
+
+// ------------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void k_setup(ScArrays<M> a, ModelParamsHost P, ScConfig cfg)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < a.N) sc_setup_instance<M>(a, P, cfg, n);
+}
+
+// SCAlgorithm::solve(warm_start = true), SCAlgorithm.cpp:141-145,152: keep the trajectory (re-nondimensionalised with the
+// scales of the NEW x_init), keep the trust-region weight, refresh parameters and the minimum-thrust directions
+template <class M>
+__global__ void k_warm(ScArrays<M> a, ModelParamsHost P, ScConfig cfg)
+{
+    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.N) return;
+    const int K = a.K;
+    double *X = a.X + (size_t)n * K * NX, *U = a.U + (size_t)n * K * NU;
+    double old_scale[2] = {a.scale[2 * n], a.scale[2 * n + 1]};
+    for (int k = 0; k < K; k++) M::redim(old_scale, X + k * NX, U + k * NU);
+    double *xi = a.xi + (size_t)n * NX, *xf = a.xf + (size_t)n * NX;
+    for (int i = 0; i < NX; i++) { xi[i] = a.x_init[(size_t)n * NX + i]; xf[i] = a.x_final[(size_t)n * NX + i]; }
+    M::setup(P, cfg.nondimensionalize, xi, xf, a.par + (size_t)n * M::NP, a.cst + (size_t)n * MAX_CST, a.scale + (size_t)n * 2);
+    for (int k = 0; k < K; k++) {
+        M::nondim(a.scale + 2 * n, X + k * NX, U + k * NU);
+        a.fixm[(size_t)n * K + k] = M::fixed(P, xi, xf, K, k, a.fixv + ((size_t)n * K + k) * NB);
+        double *td = a.tdir + ((size_t)n * K + k) * 3;
+        if (P.exact_minimum_thrust) M::thrust_dir(U + k * NU, td); else { td[0] = 0.; td[1] = 0.; td[2] = 1.; }
+    }
+    a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
+    if (a.hist) {
+        double *h = a.hist + (size_t)n * (a.max_it + 1) * a.hist_stride();
+        for (int k = 0; k < K; k++) { for (int i = 0; i < NX; i++) h[k * NB + i] = X[k * NX + i]; for (int i = 0; i < NU; i++) h[k * NB + NX + i] = U[k * NU + i]; }
+        h[K * NB] = a.sigma[n];
+    }
+}
+
+// K1: one thread per (active instance, interval, column)
+template <class M>
+__global__ void __launch_bounds__(128) k_discretize(ScArrays<M> a, int nsub, int free_time, const int *__restrict__ active, int n_active)
+{
+    constexpr int NX = M::NX, NU = M::NU, NC = NX + 2 * NU + 2;
+    const int per = (a.K - 1) * NC;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_active * per) return;
+    const int ai = int(idx / per), rem = int(idx - (long long)ai * per);
+    const int k = rem / NC, c = rem - k * NC;
+    const int n = active ? active[ai] : ai;
+    discretize_column<M>(a.X + (size_t)n * a.K * NX, a.U + (size_t)n * a.K * NU, a.sigma[n], a.par + (size_t)n * M::NP,
+                         a.K, k, c, nsub, free_time, a.dd + ((size_t)n * (a.K - 1) + k) * NX * NC);
+}
+
+// K2 (+K3 epilogue): one warp per active instance
+template <class M>
+__global__ void __launch_bounds__(WPB * 32) k_solve(ScArrays<M> a, ScConfig cfg, const int *__restrict__ active, int n_active)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * WPB + warp;
+    if (gw >= n_active) return;
+    sc_solve_instance<M>(a, cfg, active[gw], smem + (size_t)warp * Ipm<M>::sm_doubles());
+}
+
+__global__ void k_iota(int *v, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) v[i] = i; }
+
+// next active list + convergence flag bytes (what the ranks exchange)
+__global__ void k_compact(const int *__restrict__ active, int n_active, const int *__restrict__ converged, int *__restrict__ next,
+                          int *__restrict__ counter, unsigned char *__restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_active) return;
+    const int n = active[i];
+    const int c = converged[n];
+    flags[n] = (unsigned char)c;
+    if (!c) next[atomicAdd(counter, 1)] = n;
+}
+__global__ void k_count_zero(const unsigned char *__restrict__ flags, long long n, unsigned long long *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = (i < n) && flags[i] == 0;
+    const unsigned b = __ballot_sync(0xffffffffu, z);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (unsigned long long)__popc(b));
+}
+
+template <class M>
+__global__ void k_export(ScArrays<M> a, double *Xo, double *Uo)
+{
+    constexpr int NX = M::NX, NU = M::NU;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)a.N * a.K) return;
+    const int n = int(idx / a.K);
+    double x[NX], u[NU];
+    for (int i = 0; i < NX; i++) x[i] = a.X[idx * NX + i];
+    for (int i = 0; i < NU; i++) u[i] = a.U[idx * NU + i];
+    M::redim(a.scale + 2 * n, x, u);
+    for (int i = 0; i < NX; i++) Xo[idx * NX + i] = x[i];
+    for (int i = 0; i < NU; i++) Uo[idx * NU + i] = u[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// NCCL through dlopen (only needed for multi-GPU runs)
+// ------------------------------------------------------------------------------------------------------------------
+struct NcclUid { char b[128]; };
+struct Nccl {
+    void *h = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUid /* ncclUniqueId by value */, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load()
+    {
+        if (h) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllGather && CommDestroy;
+    }
+};
+static Nccl g_nccl;
+
+// ------------------------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------------------------
+struct scpp_b200_engine {
+    virtual ~scpp_b200_engine() {}
+    virtual int init() = 0;
+    virtual int set_boundary(const double *xi, const double *xf) = 0;
+    virtual int solve(int warm) = 0;
+    virtual int get_solution(double *X, double *U, double *t, int *it, int *flags) = 0;
+    virtual int get_iterate(int it, double *X, double *U, double *t) = 0;
+    virtual int get_info(double *info) = 0;
+    int model = 0, N = 0, device = 0;
+    ModelParamsHost P;
+    ScConfig cfg;
+    double ms_disc = 0, ms_socp = 0, ms_total = 0;
+    int launches = 0, outer = 0;
+    long long inst_iters = 0, global_active = 0;
+    size_t bytes = 0;
+    void *comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+template <class M>
+struct EngineT : scpp_b200_engine {
+    static constexpr int NX = M::NX, NU = M::NU, NB = NX + NU, NC = NX + 2 * NU + 2;
+    ScArrays<M> a;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int *active[2] = {nullptr, nullptr};
+    int *counter = nullptr;
+    unsigned long long *gcount = nullptr;
+    unsigned char *flags = nullptr, *flags_all = nullptr;
+    double *Xo = nullptr, *Uo = nullptr;
+    int *h_counter = nullptr;             // pinned
+    unsigned long long *h_gcount = nullptr;
+    std::vector<void *> allocs;
+    bool have_states = false, solved_once = false;
+
+    template <class T>
+    int dalloc(T **p, size_t n)
+    {
+        CU(cudaMalloc((void **)p, n * sizeof(T)));
+        CU(cudaMemsetAsync(*p, 0, n * sizeof(T), stream));
+        allocs.push_back(*p);
+        bytes += n * sizeof(T);
+        return 0;
+    }
+    ~EngineT() override
+    {
+        cudaSetDevice(device);
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        for (void *p : allocs) cudaFree(p);
+        if (h_counter) cudaFreeHost(h_counter);
+        if (h_gcount) cudaFreeHost(h_gcount);
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    int init() override
+    {
+        CU(cudaSetDevice(device));
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto &e : ev) CU(cudaEventCreate(&e));
+        const int K = cfg.K;
+        a.N = N; a.K = K; a.max_it = cfg.max_iterations;
+        a.ws_stride = Ipm<M>::ws_doubles(K);
+        int rc;
+#define DA(ptr, n) if ((rc = dalloc(&(ptr), (size_t)(n)))) return rc
+        DA(a.x_init, (size_t)N * NX); DA(a.x_final, (size_t)N * NX); DA(a.xi, (size_t)N * NX); DA(a.xf, (size_t)N * NX);
+        DA(a.par, (size_t)N * M::NP); DA(a.cst, (size_t)N * MAX_CST); DA(a.scale, (size_t)N * 2);
+        DA(a.X, (size_t)N * K * NX); DA(a.U, (size_t)N * K * NU); DA(a.sigma, N);
+        DA(a.tdir, (size_t)N * K * 3); DA(a.fixm, (size_t)N * K); DA(a.fixv, (size_t)N * K * NB); DA(a.w_tr, N);
+        DA(a.iters, N); DA(a.status, N); DA(a.converged, N);
+        DA(a.dd, (size_t)N * (K - 1) * NX * NC);
+        DA(a.ws, (size_t)N * a.ws_stride);
+        DA(a.info, (size_t)N * cfg.max_iterations * INFO_STRIDE);
+        a.hist = nullptr;
+        if (cfg.keep_history) DA(a.hist, (size_t)N * (cfg.max_iterations + 1) * a.hist_stride());
+        DA(active[0], N); DA(active[1], N); DA(counter, 1); DA(gcount, 1); DA(flags, N);
+        DA(Xo, (size_t)N * K * NX); DA(Uo, (size_t)N * K * NU);
+#undef DA
+        CU(cudaMallocHost((void **)&h_counter, sizeof(int)));
+        CU(cudaMallocHost((void **)&h_gcount, sizeof(unsigned long long)));
+        CU(cudaFuncSetAttribute(k_solve<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WPB * Ipm<M>::sm_doubles() * sizeof(double))));
+        CU(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    int set_boundary(const double *xi, const double *xf) override
+    {
+        CU(cudaSetDevice(device));
+        CU(cudaMemcpyAsync(a.x_init, xi, (size_t)N * NX * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(a.x_final, xf, (size_t)N * NX * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        have_states = true;
+        return 0;
+    }
+    int solve(int warm) override
+    {
+        if (!have_states) return fail(SCPP_B200_ERR_ARG, "scpp_b200_solve: boundary states not set");
+        if (warm && !solved_once) return fail(SCPP_B200_ERR_ARG, "scpp_b200_solve: warm start requested before any solve");
+        CU(cudaSetDevice(device));
+        const int K = cfg.K, T = 128;
+        launches = 0; outer = 0; ms_disc = ms_socp = 0; inst_iters = 0;
+        CU(cudaEventRecord(ev[0], stream));
+        if (warm) k_warm<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg);
+        else k_setup<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg);
+        k_iota<<<(N + 255) / 256, 256, 0, stream>>>(active[0], N);
+        launches += 2;
+        CU(cudaMemsetAsync(flags, 0, N, stream));
+        int n_active = N, cur = 0;
+        global_active = (long long)N * nranks;
+        const size_t smem = WPB * Ipm<M>::sm_doubles() * sizeof(double);
+        for (int it = 0; it < cfg.max_iterations && global_active > 0; it++) {
+            outer++;
+            inst_iters += n_active;
+            CU(cudaEventRecord(ev[1], stream));
+            if (n_active > 0) {
+                const long long thr = (long long)n_active * (K - 1) * NC;
+                k_discretize<M><<<(unsigned)((thr + 127) / 128), 128, 0, stream>>>(a, cfg.nsub, cfg.free_final_time, active[cur], n_active);
+                launches++;
+            }
+            CU(cudaEventRecord(ev[2], stream));
+            if (n_active > 0) {
+                k_solve<M><<<(n_active + WPB - 1) / WPB, WPB * 32, smem, stream>>>(a, cfg, active[cur], n_active);
+                launches++;
+            }
+            CU(cudaEventRecord(ev[3], stream));
+            CU(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+            if (n_active > 0) {
+                k_compact<<<(n_active + 255) / 256, 256, 0, stream>>>(active[cur], n_active, a.converged, active[cur ^ 1], counter, flags);
+                launches++;
+            }
+            CU(cudaMemcpyAsync(h_counter, counter, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            if (comm) {
+                // the one data-path collective: every rank learns every instance's convergence flag
+                int rc = g_nccl.AllGather(flags, flags_all, (size_t)N, /*ncclUint8*/ 1, comm, stream);
+                if (rc != 0) return fail(SCPP_B200_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+                CU(cudaMemsetAsync(gcount, 0, sizeof(unsigned long long), stream));
+                const long long tot = (long long)N * nranks;
+                k_count_zero<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(flags_all, tot, gcount);
+                launches++;
+                CU(cudaMemcpyAsync(h_gcount, gcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+            }
+            CU(cudaStreamSynchronize(stream));
+            float m1 = 0, m2 = 0;
+            CU(cudaEventElapsedTime(&m1, ev[1], ev[2]));
+            CU(cudaEventElapsedTime(&m2, ev[2], ev[3]));
+            ms_disc += m1; ms_socp += m2;
+            n_active = *h_counter;
+            cur ^= 1;
+            global_active = comm ? (long long)*h_gcount : (long long)n_active;
+        }
+        CU(cudaEventRecord(ev[4], stream));
+        CU(cudaStreamSynchronize(stream));
+        float mt = 0;
+        CU(cudaEventElapsedTime(&mt, ev[0], ev[4]));
+        ms_total = mt;
+        CU(cudaGetLastError());
+        solved_once = true;
+        return 0;
+    }
+    int get_solution(double *X, double *U, double *t, int *it, int *flg) override
+    {
+        CU(cudaSetDevice(device));
+        const int K = cfg.K;
+        const long long tot = (long long)N * K;
+        k_export<M><<<(unsigned)((tot + 127) / 128), 128, 0, stream>>>(a, Xo, Uo);
+        if (X) CU(cudaMemcpyAsync(X, Xo, (size_t)N * K * NX * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (U) CU(cudaMemcpyAsync(U, Uo, (size_t)N * K * NU * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (t) CU(cudaMemcpyAsync(t, a.sigma, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (it) CU(cudaMemcpyAsync(it, a.iters, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (flg) CU(cudaMemcpyAsync(flg, a.converged, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        return 0;
+    }
+    int get_iterate(int it, double *X, double *U, double *t) override
+    {
+        if (!a.hist) return fail(SCPP_B200_ERR_ARG, "scpp_b200_get_iterate: engine created without keep_history");
+        if (it < 0 || it > cfg.max_iterations) return fail(SCPP_B200_ERR_ARG, "scpp_b200_get_iterate: iteration out of range");
+        CU(cudaSetDevice(device));
+        const int K = cfg.K;
+        const size_t hs = a.hist_stride();
+        std::vector<double> buf((size_t)N * hs);
+        CU(cudaMemcpy2DAsync(buf.data(), hs * sizeof(double), a.hist + (size_t)it * hs, (size_t)(cfg.max_iterations + 1) * hs * sizeof(double),
+                             hs * sizeof(double), N, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        for (int n = 0; n < N; n++) {
+            const double *h = buf.data() + (size_t)n * hs;
+            for (int k = 0; k < K; k++) {
+                if (X) for (int i = 0; i < NX; i++) X[((size_t)n * K + k) * NX + i] = h[k * NB + i];
+                if (U) for (int i = 0; i < NU; i++) U[((size_t)n * K + k) * NU + i] = h[k * NB + NX + i];
+            }
+            if (t) t[n] = h[K * NB];
+        }
+        return 0;
+    }
+    int get_info(double *info) override
+    {
+        CU(cudaSetDevice(device));
+        CU(cudaMemcpy(info, a.info, (size_t)N * cfg.max_iterations * INFO_STRIDE * sizeof(double), cudaMemcpyDeviceToHost));
+        return 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int scpp_b200_version(void) { return 100; }
+const char *scpp_b200_last_error(void) { return g_err.c_str(); }
+int scpp_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int scpp_b200_model_dims(int model, int *nx, int *nu, int *np)
+{
+    if (model == SCPP_B200_MODEL_ROCKETQUAT) { *nx = RocketQuat::NX; *nu = RocketQuat::NU; *np = RocketQuat::NP; return 0; }
+    if (model == SCPP_B200_MODEL_ROCKET2D) { *nx = Rocket2d::NX; *nu = Rocket2d::NU; *np = Rocket2d::NP; return 0; }
+    return fail(SCPP_B200_ERR_ARG, "unknown model");
+}
+// scpp_models/config/RocketQuat/SC.info:1-16, scpp_models/config/Rocket2D/SC.info:1-16
+void scpp_b200_default_config(int model, scpp_b200_sc_config *c)
+{
+    memset(c, 0, sizeof(*c));
+    c->free_final_time = 1; c->interpolate_input = 1; c->nondimensionalize = 1;
+    c->K = model == SCPP_B200_MODEL_ROCKETQUAT ? 15 : 25;
+    c->weight_time = 1.; c->weight_trust_region_time = 1.;
+    c->weight_trust_region_trajectory = model == SCPP_B200_MODEL_ROCKETQUAT ? 50. : 1.;
+    c->weight_virtual_control = 1000.;
+    c->nu_tol = 1e-5; c->delta_tol = 1e-3; c->max_iterations = 15;
+    c->nsub = 20; c->keep_history = 0;
+    c->ipm.feastol = 1e-8; c->ipm.abstol = 1e-8; c->ipm.reltol = 1e-8; c->ipm.maxit = 100;
+}
+
+static void deg2rad(double &v) { v *= M_PI / 180.; }
+static void quat_mul(const double *a, const double *b, double *o)
+{
+    o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    o[2] = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+    o[3] = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+}
+// eulerToQuaternionXYZ, scpp_models/include/common.hpp:29-38
+static void euler_xyz(const double *e, double *q)
+{
+    const double qx[4] = {cos(e[0] / 2), sin(e[0] / 2), 0, 0}, qy[4] = {cos(e[1] / 2), 0, sin(e[1] / 2), 0}, qz[4] = {cos(e[2] / 2), 0, 0, sin(e[2] / 2)};
+    double t[4];
+    quat_mul(qx, qy, t); quat_mul(t, qz, q);
+}
+
+int scpp_b200_load_model_info(const char *path, int model, scpp_b200_model_params *p, double *x_init, double *x_final)
+{
+    try {
+        ParameterServer ps(path);
+        memset(p, 0, sizeof(*p));
+        if (model == SCPP_B200_MODEL_ROCKETQUAT) {   // rocketQuat.cpp:234-289
+            bool random_initial_state, exact, roll;
+            double I_sp, m_init, m_dry, r_init[3], v_init[3], rpy_init[3], w_init[3], r_final[3], v_final[3], rpy_final[3], w_final[3];
+            ps.loadMatrix("g_I", p->g_I, 3); ps.loadMatrix("J_B", p->J_B, 3); ps.loadMatrix("r_T_B", p->r_T_B, 3);
+            ps.loadScalar("m_init", m_init); ps.loadMatrix("r_init", r_init, 3); ps.loadMatrix("v_init", v_init, 3);
+            ps.loadMatrix("rpy_init", rpy_init, 3); ps.loadMatrix("w_init", w_init, 3); ps.loadMatrix("w_final", w_final, 3);
+            ps.loadScalar("m_dry", m_dry); ps.loadMatrix("r_final", r_final, 3); ps.loadMatrix("v_final", v_final, 3);
+            ps.loadMatrix("rpy_final", rpy_final, 3);
+            ps.loadScalar("T_min", p->T_min); ps.loadScalar("T_max", p->T_max); ps.loadScalar("t_max", p->t_max);
+            ps.loadScalar("I_sp", I_sp);
+            ps.loadScalar("gimbal_max", p->gimbal_max); ps.loadScalar("theta_max", p->theta_max);
+            ps.loadScalar("gamma_gs", p->gamma_gs); ps.loadScalar("w_B_max", p->w_B_max);
+            ps.loadScalar("random_initial_state", random_initial_state);
+            ps.loadScalar("final_time", p->final_time);
+            ps.loadScalar("exact_minimum_thrust", exact); ps.loadScalar("enable_roll_control", roll);
+            deg2rad(p->gimbal_max); deg2rad(p->theta_max); deg2rad(p->gamma_gs); deg2rad(p->w_B_max);
+            for (int i = 0; i < 3; i++) { deg2rad(rpy_init[i]); deg2rad(rpy_final[i]); deg2rad(w_init[i]); deg2rad(w_final[i]); }
+            p->alpha_m = 1. / (I_sp * fabs(p->g_I[2]));
+            p->exact_minimum_thrust = exact; p->enable_roll_control = roll;
+            double q0[4], q1[4];
+            euler_xyz(rpy_init, q0); euler_xyz(rpy_final, q1);
+            x_init[0] = m_init; x_final[0] = m_dry;
+            for (int i = 0; i < 3; i++) { x_init[1 + i] = r_init[i]; x_init[4 + i] = v_init[i]; x_init[11 + i] = w_init[i];
+                                          x_final[1 + i] = r_final[i]; x_final[4 + i] = v_final[i]; x_final[11 + i] = w_final[i]; }
+            for (int i = 0; i < 4; i++) { x_init[7 + i] = q0[i]; x_final[7 + i] = q1[i]; }
+            // random_initial_state: randomizeInitialState() is commented out in the reference (rocketQuat.cpp:203-227); batches are
+            // perturbed by the caller instead
+            (void)random_initial_state;
+            if (roll) return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control = true is not built into this engine");
+        } else if (model == SCPP_B200_MODEL_ROCKET2D) {   // rocket2d.cpp:150-196
+            bool cif, slack;
+            double r_init[2], v_init[2], r_final[2], v_final[2], w_init, w_final, eta_init, eta_final;
+            ps.loadMatrix("g_I", p->g_I, 2); ps.loadScalar("J_B", p->J_B[0]); ps.loadMatrix("r_T_B", p->r_T_B, 2);
+            ps.loadMatrix("r_init", r_init, 2); ps.loadMatrix("v_init", v_init, 2); ps.loadScalar("eta_init", eta_init); ps.loadScalar("w_init", w_init);
+            ps.loadMatrix("r_final", r_final, 2); ps.loadMatrix("v_final", v_final, 2); ps.loadScalar("eta_final", eta_final); ps.loadScalar("w_final", w_final);
+            ps.loadScalar("final_time", p->final_time);
+            ps.loadScalar("m", p->m); ps.loadScalar("T_min", p->T_min); ps.loadScalar("T_max", p->T_max);
+            ps.loadScalar("gamma_gs", p->gamma_gs); ps.loadScalar("gimbal_max", p->gimbal_max);
+            ps.loadScalar("theta_max", p->theta_max); ps.loadScalar("w_B_max", p->w_B_max);
+            ps.loadScalar("constrain_initial_final", cif); ps.loadScalar("add_slack_variables", slack);
+            deg2rad(p->gimbal_max); deg2rad(p->theta_max); deg2rad(p->gamma_gs); deg2rad(p->w_B_max);
+            deg2rad(w_init); deg2rad(w_final); deg2rad(eta_init); deg2rad(eta_final);
+            p->constrain_initial_final = cif;
+            x_init[0] = r_init[0]; x_init[1] = r_init[1]; x_init[2] = v_init[0]; x_init[3] = v_init[1]; x_init[4] = eta_init; x_init[5] = w_init;
+            x_final[0] = r_final[0]; x_final[1] = r_final[1]; x_final[2] = v_final[0]; x_final[3] = v_final[1]; x_final[4] = eta_final; x_final[5] = w_final;
+        } else return fail(SCPP_B200_ERR_ARG, "unknown model");
+    } catch (const std::exception &ex) { return fail(SCPP_B200_ERR_IO, ex.what()); }
+    return 0;
+}
+
+int scpp_b200_load_sc_info(const char *path, scpp_b200_sc_config *c)
+{
+    try {   // SCAlgorithm::loadParameters, SCAlgorithm.cpp:22-46
+        ParameterServer ps(path);
+        bool fft, nd, ii;
+        ps.loadScalar("K", c->K);
+        ps.loadScalar("free_final_time", fft);
+        ps.loadScalar("nondimensionalize", nd);
+        ps.loadScalar("delta_tol", c->delta_tol); ps.loadScalar("max_iterations", c->max_iterations); ps.loadScalar("nu_tol", c->nu_tol);
+        ps.loadScalar("weight_time", c->weight_time); ps.loadScalar("weight_virtual_control", c->weight_virtual_control);
+        ps.loadScalar("weight_trust_region_trajectory", c->weight_trust_region_trajectory);
+        ps.loadScalar("interpolate_input", ii);
+        if (fft) ps.loadScalar("weight_trust_region_time", c->weight_trust_region_time);
+        c->free_final_time = fft; c->nondimensionalize = nd; c->interpolate_input = ii;
+    } catch (const std::exception &ex) { return fail(SCPP_B200_ERR_IO, ex.what()); }
+    return 0;
+}
+
+int scpp_b200_create(int model, const scpp_b200_model_params *params, const scpp_b200_sc_config *cfg, int n, int device, scpp_b200_engine **out)
+{
+    if (!params || !cfg || !out || n <= 0) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: bad argument");
+    if (cfg->K < 3 || cfg->max_iterations < 1 || cfg->nsub < 1) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: K >= 3, max_iterations >= 1, nsub >= 1 required");
+    if (!cfg->free_final_time || !cfg->interpolate_input)
+        return fail(SCPP_B200_ERR_UNSUPPORTED, "only free_final_time = true, interpolate_input = true (the shipped SC.info settings) are built");
+    if (params->enable_roll_control) return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control = true is not built into this engine");
+    if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");
+    scpp_b200_engine *e = nullptr;
+    if (model == SCPP_B200_MODEL_ROCKETQUAT) e = new EngineT<RocketQuat>();
+    else if (model == SCPP_B200_MODEL_ROCKET2D) e = new EngineT<Rocket2d>();
+    else return fail(SCPP_B200_ERR_ARG, "unknown model");
+    e->model = model; e->N = n; e->device = device;
+    memcpy(&e->P, params, sizeof(ModelParamsHost));
+    memcpy(&e->cfg, cfg, sizeof(ScConfig));
+    int rc = e->init();
+    if (rc) { delete e; return rc; }
+    *out = e;
+    return 0;
+}
+void scpp_b200_destroy(scpp_b200_engine *e) { delete e; }
+int scpp_b200_set_boundary_states(scpp_b200_engine *e, const double *xi, const double *xf) { return (e && xi && xf) ? e->set_boundary(xi, xf) : fail(SCPP_B200_ERR_ARG, "null argument"); }
+int scpp_b200_solve(scpp_b200_engine *e, int warm) { return e ? e->solve(warm) : fail(SCPP_B200_ERR_ARG, "null engine"); }
+int scpp_b200_get_solution(scpp_b200_engine *e, double *X, double *U, double *t, int *it, int *fl) { return e ? e->get_solution(X, U, t, it, fl) : fail(SCPP_B200_ERR_ARG, "null engine"); }
+int scpp_b200_get_iterate(scpp_b200_engine *e, int it, double *X, double *U, double *t) { return e ? e->get_iterate(it, X, U, t) : fail(SCPP_B200_ERR_ARG, "null engine"); }
+int scpp_b200_get_info(scpp_b200_engine *e, double *info) { return (e && info) ? e->get_info(info) : fail(SCPP_B200_ERR_ARG, "null argument"); }
+int scpp_b200_last_timing(scpp_b200_engine *e, double *a, double *b, double *c, int *l, int *o, long long *ii)
+{
+    if (!e) return fail(SCPP_B200_ERR_ARG, "null engine");
+    if (a) *a = e->ms_disc; if (b) *b = e->ms_socp; if (c) *c = e->ms_total; if (l) *l = e->launches; if (o) *o = e->outer; if (ii) *ii = e->inst_iters;
+    return 0;
+}
+size_t scpp_b200_device_bytes(scpp_b200_engine *e) { return e ? e->bytes : 0; }
+long long scpp_b200_global_active(scpp_b200_engine *e) { return e ? e->global_active : -1; }
+
+} // extern "C"
+
+template <class M>
+static int discretize_hook(int K, int n, int nsub, int device, const double *X, const double *U, const double *sigma, const double *par,
+                           double *A, double *B, double *C, double *s, double *z)
+{
+    constexpr int NX = M::NX, NU = M::NU, NC = NX + 2 * NU + 2;
+    CU(cudaSetDevice(device));
+    ScArrays<M> a;
+    memset(&a, 0, sizeof(a));
+    a.N = n; a.K = K;
+    const size_t nd = (size_t)n * (K - 1) * NX * NC;
+    CU(cudaMalloc((void **)&a.X, (size_t)n * K * NX * 8)); CU(cudaMalloc((void **)&a.U, (size_t)n * K * NU * 8));
+    CU(cudaMalloc((void **)&a.sigma, (size_t)n * 8)); CU(cudaMalloc((void **)&a.par, (size_t)n * M::NP * 8)); CU(cudaMalloc((void **)&a.dd, nd * 8));
+    CU(cudaMemcpy(a.X, X, (size_t)n * K * NX * 8, cudaMemcpyHostToDevice)); CU(cudaMemcpy(a.U, U, (size_t)n * K * NU * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(a.sigma, sigma, (size_t)n * 8, cudaMemcpyHostToDevice)); CU(cudaMemcpy(a.par, par, (size_t)n * M::NP * 8, cudaMemcpyHostToDevice));
+    const long long thr = (long long)n * (K - 1) * NC;
+    k_discretize<M><<<(unsigned)((thr + 127) / 128), 128>>>(a, nsub, 1, nullptr, n);
+    CU(cudaGetLastError());
+    std::vector<double> dd(nd);
+    CU(cudaMemcpy(dd.data(), a.dd, nd * 8, cudaMemcpyDeviceToHost));
+    cudaFree(a.X); cudaFree(a.U); cudaFree(a.sigma); cudaFree(a.par); cudaFree(a.dd);
+    for (size_t b = 0; b < (size_t)n * (K - 1); b++) {
+        const double *t = dd.data() + b * NX * NC;
+        for (int i = 0; i < NX; i++) {
+            for (int j = 0; j < NX; j++) A[b * NX * NX + i + NX * j] = t[i * NC + j];
+            for (int j = 0; j < NU; j++) { B[b * NX * NU + i + NX * j] = t[i * NC + NX + j]; C[b * NX * NU + i + NX * j] = t[i * NC + NX + NU + j]; }
+            s[b * NX + i] = t[i * NC + NX + 2 * NU]; z[b * NX + i] = t[i * NC + NX + 2 * NU + 1];
+        }
+    }
+    return 0;
+}
+extern "C" {
+
+int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const double *X, const double *U, const double *sigma, const double *par,
+                         double *A, double *B, double *C, double *s, double *z)
+{
+    if (K < 2 || n <= 0 || nsub < 1 || !X || !U || !sigma || !par || !A || !B || !C || !s || !z) return fail(SCPP_B200_ERR_ARG, "scpp_b200_discretize: bad argument");
+    if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");
+    if (model == SCPP_B200_MODEL_ROCKETQUAT) return discretize_hook<RocketQuat>(K, n, nsub, device, X, U, sigma, par, A, B, C, s, z);
+    if (model == SCPP_B200_MODEL_ROCKET2D) return discretize_hook<Rocket2d>(K, n, nsub, device, X, U, sigma, par, A, B, C, s, z);
+    return fail(SCPP_B200_ERR_ARG, "unknown model");
+}
+
+int scpp_b200_comm_unique_id(char id[128])
+{
+    if (!g_nccl.load()) return fail(SCPP_B200_ERR_NCCL, "libnccl.so.2 not found");
+    int rc = g_nccl.GetUniqueId(id);
+    return rc ? fail(SCPP_B200_ERR_NCCL, "ncclGetUniqueId failed") : 0;
+}
+int scpp_b200_comm_init(scpp_b200_engine *e, int nranks, int rank, const char id[128])
+{
+    if (!e || nranks < 1 || rank < 0 || rank >= nranks) return fail(SCPP_B200_ERR_ARG, "scpp_b200_comm_init: bad argument");
+    if (nranks == 1) return 0;
+    if (!g_nccl.load()) return fail(SCPP_B200_ERR_NCCL, "libnccl.so.2 not found");
+    CU(cudaSetDevice(e->device));
+    NcclUid uid;
+    memcpy(uid.b, id, 128);
+    int rc = g_nccl.CommInitRank(&e->comm, nranks, uid, rank);
+    if (rc) return fail(SCPP_B200_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    e->nranks = nranks; e->rank = rank;
+    // flags of all ranks
+    unsigned char *fa = nullptr;
+    CU(cudaMalloc((void **)&fa, (size_t)e->N * nranks));
+    if (e->model == SCPP_B200_MODEL_ROCKETQUAT) { auto *t = static_cast<EngineT<RocketQuat> *>(e); t->flags_all = fa; t->allocs.push_back(fa); }
+    else { auto *t = static_cast<EngineT<Rocket2d> *>(e); t->flags_all = fa; t->allocs.push_back(fa); }
+    return 0;
+}
+
+} // extern "C"

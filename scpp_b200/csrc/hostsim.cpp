@@ -1,0 +1,68 @@
+// scpp_b200/csrc/hostsim.cpp — TEST-ONLY host-simulation build of the kernel bodies (LANES == 1).
+// Built into tests/_hostsim/libhostsim.so by tests/hostsim.py; never part of libscpp_b200.so and never
+// loaded by the scpp_b200 package: the product has no CPU execution path.
+#include "sc.cuh"
+#include <vector>
+#include <cstring>
+#include <cstdlib>
+
+using namespace scpp;
+
+template <class M>
+static void run_discretize(int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd)
+{
+    constexpr int NC = M::NX + 2 * M::NU + 2;
+    for (int k = 0; k < K - 1; k++)
+        for (int c = 0; c < NC; c++)
+            discretize_column<M>(X, U, sigma, par, K, k, c, nsub, 1, dd + (size_t)k * M::NX * NC);
+}
+
+extern "C" void hs_discretize(int model, int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd)
+{
+    if (model == 0) run_discretize<RocketQuat>(K, X, U, sigma, par, nsub, dd);
+    else run_discretize<Rocket2d>(K, X, U, sigma, par, nsub, dd);
+}
+
+template <class M>
+static int run_sc(const ModelParamsHost *P, const ScConfig *cfg, int N, const double *x_init, const double *x_final,
+                  double *X, double *U, double *sigma, int *iters, int *status, int *converged, double *hist, double *info)
+{
+    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU, NC = NX + 2 * NU + 2;
+    const int K = cfg->K;
+    ScArrays<M> a;
+    a.N = N; a.K = K; a.max_it = cfg->max_iterations;
+    std::vector<double> xi(N * NX), xf(N * NX), par(N * M::NP), cst(N * MAX_CST), scale(N * 2), tdir((size_t)N * K * 3), fixv((size_t)N * K * NB), wtr(N);
+    std::vector<uint32_t> fixm((size_t)N * K);
+    std::vector<double> dd((size_t)N * (K - 1) * NX * NC);
+    a.ws_stride = Ipm<M>::ws_doubles(K);
+    std::vector<double> ws((size_t)N * a.ws_stride), smem(Ipm<M>::sm_doubles());
+    a.x_init = const_cast<double *>(x_init); a.x_final = const_cast<double *>(x_final);
+    a.xi = xi.data(); a.xf = xf.data(); a.par = par.data(); a.cst = cst.data(); a.scale = scale.data();
+    a.X = X; a.U = U; a.sigma = sigma; a.tdir = tdir.data(); a.fixm = fixm.data(); a.fixv = fixv.data(); a.w_tr = wtr.data();
+    a.iters = iters; a.status = status; a.converged = converged; a.dd = dd.data(); a.ws = ws.data(); a.hist = hist; a.info = info;
+    for (int n = 0; n < N; n++) sc_setup_instance<M>(a, *P, *cfg, n);
+    for (int it = 0; it < cfg->max_iterations; it++) {
+        int active = 0;
+        for (int n = 0; n < N; n++) {
+            if (converged[n]) continue;
+            active++;
+            run_discretize<M>(K, X + (size_t)n * K * NX, U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg->nsub,
+                              a.dd + (size_t)n * (K - 1) * NX * NC);
+            sc_solve_instance<M>(a, *cfg, n, smem.data());
+        }
+        if (!active) break;
+    }
+    // redimensionalise the final trajectories (SCAlgorithm.cpp:182-187)
+    for (int n = 0; n < N; n++)
+        for (int k = 0; k < K; k++) M::redim(a.scale + 2 * n, X + ((size_t)n * K + k) * NX, U + ((size_t)n * K + k) * NU);
+    return 0;
+}
+
+extern "C" int hs_sc_solve(int model, const ModelParamsHost *P, const ScConfig *cfg, int N, const double *x_init, const double *x_final,
+                           double *X, double *U, double *sigma, int *iters, int *status, int *converged, double *hist, double *info)
+{
+    if (model == 0) return run_sc<RocketQuat>(P, cfg, N, x_init, x_final, X, U, sigma, iters, status, converged, hist, info);
+    return run_sc<Rocket2d>(P, cfg, N, x_init, x_final, X, U, sigma, iters, status, converged, hist, info);
+}
+
+extern "C" int hs_sizes(int which) { return which == 0 ? (int)sizeof(ModelParamsHost) : (int)sizeof(ScConfig); }

@@ -1,0 +1,52 @@
+// scpp_b200/csrc/portable.cuh — lane abstraction shared by the CUDA kernels and the host-simulation build.
+//
+// The SOCP kernel is written "one warp per problem instance": 32 lanes cooperate on one instance and exchange
+// data through shared memory.  The same source is compiled by g++ with LANES == 1 into a TEST-ONLY library
+// (tests/_hostsim) so the algorithm can be unit-tested on a machine without a GPU; the product library
+// (libscpp_b200.so) contains only the CUDA build and has no CPU execution path.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SCPP_HD __host__ __device__ __forceinline__
+#define SCPP_D __device__ __forceinline__
+#else
+#define SCPP_HD inline
+#define SCPP_D inline
+#endif
+
+namespace scpp {
+
+#if defined(__CUDA_ARCH__)
+constexpr int LANES = 32;
+SCPP_D int lane_id() { return threadIdx.x & 31; }
+SCPP_D void warp_sync() { __syncwarp(); }
+SCPP_D double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+SCPP_D double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+SCPP_D int warp_or(int v) { return __any_sync(0xffffffffu, v); }
+SCPP_D double warp_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+#else
+constexpr int LANES = 1;
+inline int lane_id() { return 0; }
+inline void warp_sync() {}
+inline double warp_sum(double v) { return v; }
+inline double warp_max(double v) { return v; }
+inline int warp_or(int v) { return v; }
+inline double warp_bcast(double v, int) { return v; }
+#endif
+
+// lanes stride over [0,n)
+#define FOR_LANE(i, n) for (int i = lane_id(); i < (n); i += LANES)
+
+} // namespace scpp

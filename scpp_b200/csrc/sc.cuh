@@ -1,0 +1,137 @@
+// scpp_b200/csrc/sc.cuh — per-instance successive-convexification state and the glue around the two hot paths
+// (kernel K0 = setup / initial guess, K3 = read solution + convergence logic; K3 is fused into the K2 epilogue).
+//
+// Reference: scpp_core/src/SCAlgorithm.cpp:66-210 (iterate / solve / readSolution), scpp_models (setup).
+#pragma once
+#include "ipm.cuh"
+#include "discretize.cuh"
+
+namespace scpp {
+
+// SC.info, scpp_core/src/SCAlgorithm.cpp:22-46, plus engine knobs
+struct ScConfig {
+    int K;
+    int free_final_time, interpolate_input, nondimensionalize;
+    double weight_time, weight_trust_region_time, weight_trust_region_trajectory, weight_virtual_control;
+    double nu_tol, delta_tol;
+    int max_iterations;
+    int nsub;                 // RK4 sub-steps per shooting interval (K1)
+    int keep_history;         // store every iterate (getAllSolutions)
+    int pad_;
+    IpmSettings ipm;
+};
+
+constexpr int INFO_STRIDE = 10;   // per (instance, iteration): norm1_nu, sum_delta, delta_sigma, sigma, w_tr_used,
+                                  //                            ipm_iterations, ipm_status, pres, dres, relgap
+
+// batch-wide device arrays, instance-major
+template <class M>
+struct ScArrays {
+    static constexpr int NX = M::NX, NU = M::NU, NB = NX + NU, NC = NX + 2 * NU + 2;
+    int N, K, max_it;
+    double *x_init, *x_final;      // [N][NX] as uploaded (dimensional)
+    double *xi, *xf;               // [N][NX] scaled
+    double *par;                   // [N][NP]
+    double *cst;                   // [N][MAX_CST]
+    double *scale;                 // [N][2]
+    double *X, *U, *sigma;         // [N][K][NX], [N][K][NU], [N]
+    double *tdir;                  // [N][K][3]
+    uint32_t *fixm;                // [N][K]
+    double *fixv;                  // [N][K][NB]
+    double *w_tr;                  // [N] current trust-region weight
+    int *iters, *status, *converged;   // [N]
+    double *dd;                    // [N][K-1][NX][NC]
+    double *ws;                    // [N][ws_doubles]
+    double *hist;                  // [N][max_it+1][K*NB+1] or null
+    double *info;                  // [N][max_it][INFO_STRIDE]
+    size_t ws_stride;
+
+    SCPP_HD size_t hist_stride() const { return (size_t)K * NB + 1; }
+};
+
+// ---- K0: nondimensionalise, model parameters, constraint constants, pinned variables, initial guess -------------
+// SCAlgorithm::solve cold start, SCAlgorithm.cpp:138-159
+template <class M>
+SCPP_HD void sc_setup_instance(const ScArrays<M> &a, const ModelParamsHost &P, const ScConfig &cfg, int n)
+{
+    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU;
+    const int K = a.K;
+    double *xi = a.xi + (size_t)n * NX, *xf = a.xf + (size_t)n * NX;
+    for (int i = 0; i < NX; i++) { xi[i] = a.x_init[(size_t)n * NX + i]; xf[i] = a.x_final[(size_t)n * NX + i]; }
+    double *cst = a.cst + (size_t)n * MAX_CST;
+    M::setup(P, cfg.nondimensionalize, xi, xf, a.par + (size_t)n * M::NP, cst, a.scale + (size_t)n * 2);
+    double *X = a.X + (size_t)n * K * NX, *U = a.U + (size_t)n * K * NU;
+    for (int k = 0; k < K; k++) {
+        M::initial_guess(xi, xf, cst, K, k, X + k * NX, U + k * NU);
+        a.fixm[(size_t)n * K + k] = M::fixed(P, xi, xf, K, k, a.fixv + ((size_t)n * K + k) * NB);
+        double *td = a.tdir + ((size_t)n * K + k) * 3;
+        if (P.exact_minimum_thrust) M::thrust_dir(U + k * NU, td);            // rocketQuat.cpp:162-165
+        else { td[0] = 0.; td[1] = 0.; td[2] = 1.; }
+    }
+    a.sigma[n] = P.final_time;
+    a.w_tr[n] = cfg.weight_trust_region_trajectory;                            // loadParameters(), SCAlgorithm.cpp:148
+    a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
+    if (a.hist) {
+        double *h = a.hist + (size_t)n * (a.max_it + 1) * a.hist_stride();
+        for (int k = 0; k < K; k++) { for (int i = 0; i < NX; i++) h[k * NB + i] = X[k * NX + i]; for (int i = 0; i < NU; i++) h[k * NB + NX + i] = U[k * NU + i]; }
+        h[K * NB] = a.sigma[n];
+    }
+}
+
+// ---- K2 + K3: solve the sub-problem of instance n, then readSolution and the convergence logic ------------------
+// SCAlgorithm::iterate, SCAlgorithm.cpp:78-131 (the defect print :85-92 is diagnostic only and not computed)
+template <class M>
+SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n, double *smem)
+{
+    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU, NC = NX + 2 * NU + 2;
+    const int K = a.K;
+    Ipm<M> ipm;
+    ipm.K = K;
+    ipm.dd = a.dd + (size_t)n * (K - 1) * NX * NC;
+    double *X = a.X + (size_t)n * K * NX, *U = a.U + (size_t)n * K * NU;
+    ipm.Xbar = X; ipm.Ubar = U; ipm.sigbar = a.sigma[n];
+    ipm.cst = a.cst + (size_t)n * MAX_CST;
+    ipm.tdir = a.tdir + (size_t)n * K * 3;
+    ipm.fixm = a.fixm + (size_t)n * K;
+    ipm.fixv = a.fixv + (size_t)n * K * NB;
+    ipm.w_time = cfg.weight_time; ipm.w_trs = cfg.weight_trust_region_time; ipm.w_vc = cfg.weight_virtual_control;
+    const double w_tr = a.w_tr[n];
+    ipm.w_tr = w_tr;
+    ipm.bind(a.ws + (size_t)n * a.ws_stride, smem);
+    const IpmResult r = ipm.solve(cfg.ipm);
+    const int it = a.iters[n];
+    double *inf = a.info + ((size_t)n * a.max_it + it) * INFO_STRIDE;
+    const bool ok = (r.status == 0 || r.status == 3);
+    warp_sync();
+    double n1 = 0, sd = 0;
+    if (ok) {
+        // readSolution (SCAlgorithm.cpp:191-210): X, U, sigma <- solver variables
+        FOR_LANE(e, K * NB) { const int k = e / NB, i = e - k * NB; const double v = ipm.prim[ipm.pn(k) + i]; if (i < NX) X[k * NX + i] = v; else U[k * NU + (i - NX)] = v; }
+        FOR_LANE(e, (K - 1) * NX) n1 += ipm.prim[ipm.p_t(0) + e];            // norm1_nu  (:102-103)
+        FOR_LANE(k, K) sd += ipm.prim[ipm.pn(k) + NB];                       // delta.sum() (:105-107)
+    }
+    n1 = warp_sum(n1); sd = warp_sum(sd);
+    warp_sync();
+    if (lane_id() == 0) {
+        const double sg = ok ? ipm.prim[ipm.p_sigma()] : a.sigma[n];
+        const double dsg = ok ? ipm.prim[ipm.p_dsig()] : 0.;
+        inf[0] = n1; inf[1] = sd; inf[2] = dsg; inf[3] = sg; inf[4] = w_tr;
+        inf[5] = r.iterations; inf[6] = r.status; inf[7] = r.pres; inf[8] = r.dres; inf[9] = r.relgap;
+        a.iters[n] = it + 1;
+        if (!ok) { a.status[n] = r.status; a.converged[n] = 2; }             // reference: std::terminate (:94-98); here: flag the instance
+        else {
+            a.sigma[n] = sg;
+            if (n1 < cfg.nu_tol) a.w_tr[n] = w_tr * 2.;                      // :112-115
+            if (sd < cfg.delta_tol && n1 < cfg.nu_tol) a.converged[n] = 1;   // :131
+            if (r.status == 3) a.status[n] = 3;
+        }
+    }
+    if (a.hist && ok) {
+        double *h = a.hist + ((size_t)n * (a.max_it + 1) + it + 1) * a.hist_stride();
+        FOR_LANE(e, K * NB) { const int k = e / NB, i = e - k * NB; h[e] = ipm.prim[ipm.pn(k) + i]; }
+        if (lane_id() == 0) h[K * NB] = ipm.prim[ipm.p_sigma()];
+    }
+    warp_sync();
+}
+
+} // namespace scpp

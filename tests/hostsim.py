@@ -1,0 +1,103 @@
+"""TEST-ONLY: builds and binds the host-simulation library (kernel bodies compiled by g++ with LANES == 1).
+Never imported by the scpp_b200 package."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+class ModelParamsHost(C.Structure):
+    _fields_ = [("g_I", C.c_double * 3), ("J_B", C.c_double * 3), ("r_T_B", C.c_double * 3), ("alpha_m", C.c_double),
+                ("m", C.c_double), ("T_min", C.c_double), ("T_max", C.c_double), ("t_max", C.c_double),
+                ("gimbal_max", C.c_double), ("theta_max", C.c_double), ("gamma_gs", C.c_double), ("w_B_max", C.c_double),
+                ("final_time", C.c_double), ("exact_minimum_thrust", C.c_int), ("enable_roll_control", C.c_int),
+                ("constrain_initial_final", C.c_int), ("pad_", C.c_int)]
+
+
+class IpmSettings(C.Structure):
+    _fields_ = [("feastol", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("maxit", C.c_int)]
+
+
+class ScConfig(C.Structure):
+    _fields_ = [("K", C.c_int), ("free_final_time", C.c_int), ("interpolate_input", C.c_int), ("nondimensionalize", C.c_int),
+                ("weight_time", C.c_double), ("weight_trust_region_time", C.c_double),
+                ("weight_trust_region_trajectory", C.c_double), ("weight_virtual_control", C.c_double),
+                ("nu_tol", C.c_double), ("delta_tol", C.c_double), ("max_iterations", C.c_int), ("nsub", C.c_int),
+                ("keep_history", C.c_int), ("pad_", C.c_int), ("ipm", IpmSettings)]
+
+
+def build():
+    out = os.path.join(ROOT, "tests", "_hostsim")
+    os.makedirs(out, exist_ok=True)
+    src = os.path.join(ROOT, "scpp_b200", "csrc")
+    lib = os.path.join(out, "libhostsim.so")
+    deps = [os.path.join(src, f) for f in os.listdir(src) if f.endswith((".cuh", ".cpp", ".hpp"))]
+    if os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps):
+        return lib
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-w", "-I" + src,
+                           os.path.join(src, "hostsim.cpp"), "-o", lib])
+    return lib
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        assert _LIB.hs_sizes(0) == C.sizeof(ModelParamsHost) and _LIB.hs_sizes(1) == C.sizeof(ScConfig)
+    return _LIB
+
+
+def params_from_oracle(model, p):
+    """orc_py.RQParams / R2DParams -> (ModelParamsHost, x_init, x_final)"""
+    P = ModelParamsHost()
+    if model == 0:
+        P.g_I[:] = list(p.g_I); P.J_B[:] = list(p.J_B); P.r_T_B[:] = list(p.r_T_B)
+        P.alpha_m = p.alpha_m; P.T_min = p.T_min; P.T_max = p.T_max; P.t_max = p.t_max
+        P.gimbal_max = p.gimbal_max; P.theta_max = p.theta_max; P.gamma_gs = p.gamma_gs; P.w_B_max = p.w_B_max
+        P.final_time = p.final_time; P.exact_minimum_thrust = p.exact_minimum_thrust; P.enable_roll_control = p.enable_roll_control
+    else:
+        P.g_I[:] = [p.g_I[0], p.g_I[1], 0]; P.J_B[:] = [p.J_B, 0, 0]; P.r_T_B[:] = [p.r_T_B[0], p.r_T_B[1], 0]
+        P.m = p.m; P.T_min = p.T_min; P.T_max = p.T_max
+        P.gimbal_max = p.gimbal_max; P.theta_max = p.theta_max; P.gamma_gs = p.gamma_gs; P.w_B_max = p.w_B_max
+        P.final_time = p.final_time; P.constrain_initial_final = p.constrain_initial_final
+    return P, np.array(p.x_init, float), np.array(p.x_final, float)
+
+
+def sc_config(ocfg, nsub=20, tol=1e-9, maxit=100, history=True):
+    c = ScConfig()
+    for f in ("K", "free_final_time", "interpolate_input", "nondimensionalize", "weight_time", "weight_trust_region_time",
+              "weight_trust_region_trajectory", "weight_virtual_control", "nu_tol", "delta_tol", "max_iterations"):
+        setattr(c, f, getattr(ocfg, f))
+    c.nsub = nsub; c.keep_history = int(history)
+    c.ipm.feastol = tol; c.ipm.abstol = tol; c.ipm.reltol = tol; c.ipm.maxit = maxit
+    return c
+
+
+DIMS = {0: (14, 4), 1: (6, 2)}
+
+
+def sc_solve(model, P, cfg, x_init, x_final):
+    nx, nu = DIMS[model]
+    x_init = np.ascontiguousarray(np.atleast_2d(x_init), float); x_final = np.ascontiguousarray(np.atleast_2d(x_final), float)
+    N, K, M = x_init.shape[0], cfg.K, cfg.max_iterations
+    if x_final.shape[0] == 1 and N > 1:
+        x_final = np.ascontiguousarray(np.tile(x_final, (N, 1)))
+    X = np.zeros((N, K, nx)); U = np.zeros((N, K, nu)); sg = np.zeros(N)
+    iters = np.zeros(N, np.int32); status = np.zeros(N, np.int32); conv = np.zeros(N, np.int32)
+    hist = np.zeros((N, M + 1, K * (nx + nu) + 1)); info = np.zeros((N, M, 10))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().hs_sc_solve(model, C.byref(P), C.byref(cfg), N, p(x_init), p(x_final), p(X), p(U), p(sg), p(iters), p(status), p(conv), p(hist), p(info))
+    H = hist[:, :, :-1].reshape(N, M + 1, K, nx + nu)
+    return dict(X=X, U=U, t=sg, iters=iters, status=status, converged=conv, X_all=H[..., :nx], U_all=H[..., nx:], t_all=hist[:, :, -1], info=info)
+
+
+def discretize(model, X, U, sigma, par, nsub):
+    nx, nu = DIMS[model]
+    K = X.shape[0]
+    out = np.zeros((K - 1, nx, nx + 2 * nu + 2))
+    p = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(C.c_void_p)
+    lib().hs_discretize(model, K, p(X), p(U), C.c_double(sigma), p(par), nsub, out.ctypes.data_as(C.c_void_p))
+    return dict(A=out[:, :, :nx], B=out[:, :, nx:nx + nu], C=out[:, :, nx + nu:nx + 2 * nu], s=out[:, :, nx + 2 * nu], z=out[:, :, nx + 2 * nu + 1])

@@ -1,0 +1,177 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA engine, called through the C-ABI, against the CPU oracle.
+
+PARITY UNPINNED: the reference has no golden vectors; the oracle (oracle/*.c) is a literal restatement certified by KKT
+residuals (tests/test_oracle.py).  Tolerances are north_star's: 1e-5 on the state, 1e-4 on the control, in the units the
+algorithm iterates on (nondimensional; thrusts are ~1e-2 there, SURVEY §7 "parity definition")."""
+import ctypes as C
+import numpy as np
+import pytest
+
+import orc_py as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_X, TOL_U = 1e-5, 1e-4
+RPY_F9 = np.deg2rad([-20.0, 20.0, 0.0])
+
+
+@pytest.fixture(scope="module")
+def S():
+    import scpp_b200
+    assert scpp_b200.device_count() > 0, "no CUDA device"
+    return scpp_b200
+
+
+def _oracle_nondim_par(p):
+    pn = O.RQParams.from_buffer_copy(p); O.lib().orc_rq_nondimensionalize(C.byref(pn))
+    par = np.zeros(10); O.lib().orc_rq_model_par(C.byref(pn), par.ctypes.data_as(C.c_void_p))
+    return pn, par
+
+
+def test_discretize_matches_rkf78_oracle(S):
+    """hot path 1 alone: RK4 x nsub forward-sensitivity kernel vs the literal RKF78 x 5 Phi^-1-form oracle"""
+    p, rpy = O.falcon9()
+    r = O.sc_solve(O.ROCKETQUAT, p, O.sc_config(K=50, max_iterations=3))
+    pn, par = _oracle_nondim_par(p)
+    for it in (0, 3):
+        X, U, t = r["X_all"][it], r["U_all"][it], r["t_all"][it]
+        ref = O.discretize(O.ROCKETQUAT, X, U, t, par)
+        got = S.discretize(S.ROCKETQUAT, X, U, t, par, nsub=20)
+        for key in ("A", "B", "C", "s", "z"):
+            scale = np.abs(ref[key]).max()
+            assert np.abs(got[key][0] - ref[key]).max() <= 2e-10 * max(1.0, scale), key
+        # the identity the SOCP relies on: linear model == nonlinear propagation at the linearisation point
+        for k in (0, 17, 48):
+            lin = got["A"][0, k] @ X[k] + got["B"][0, k] @ U[k] + got["C"][0, k] @ U[k + 1] + got["s"][0, k] * t + got["z"][0, k]
+            assert np.allclose(lin, O.simulate(O.ROCKETQUAT, t / 49, U[k], U[k + 1], par, X[k]), atol=1e-9)
+
+
+def test_discretize_rocket2d_and_ragged_sizes(S):
+    p2 = O.rocket2d()
+    pn = O.R2DParams.from_buffer_copy(p2); O.lib().orc_r2d_nondimensionalize(C.byref(pn))
+    par = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(pn), par.ctypes.data_as(C.c_void_p))
+    for K in (3, 7, 30):      # K=3: smallest the engine accepts; odd sizes exercise partial warps / blocks
+        X = np.zeros((K, 6)); U = np.zeros((K, 2)); t = C.c_double()
+        O.lib().orc_r2d_initial_trajectory(C.byref(pn), K, X.ctypes.data_as(C.c_void_p), U.ctypes.data_as(C.c_void_p), C.byref(t))
+        ref = O.discretize(O.ROCKET2D, X, U, t.value, par)
+        got = S.discretize(S.ROCKET2D, X, U, t.value, par, nsub=20)
+        for key in ("A", "B", "C", "s", "z"):
+            assert np.abs(got[key][0] - ref[key]).max() <= 2e-10 * max(1.0, np.abs(ref[key]).max()), (K, key)
+
+
+def _compare_run(S, name, model_o, params_list, K, max_it, tol_x=TOL_X, tol_u=TOL_U, xi=None, cfg_over=None):
+    model, params, x_init, x_final, cfg = S.load_model(name, K=K, max_iterations=max_it, keep_history=1, **(cfg_over or {}))
+    N = len(params_list)
+    if xi is None:
+        xi = np.array([list(p.x_init) for p in params_list])
+    eng = S.SCAlgorithm(model, params, cfg, N)
+    eng.set_boundary_states(xi, x_final)
+    eng.solve()
+    sol = eng.get_solution(); info = eng.get_info()
+    Xh, Uh, th = eng.get_all_solutions()
+    ocfg = O.sc_config(K=K, model=model_o, max_iterations=max_it)
+    for k, v in (cfg_over or {}).items():
+        if hasattr(ocfg, k):
+            setattr(ocfg, k, v)
+    report = []
+    for i, p in enumerate(params_list):
+        ro = O.sc_solve(model_o, p, ocfg)
+        n = abs(ro["iterations"])
+        assert ro["iterations"] > 0, "oracle failed"
+        assert sol["iterations"][i] == n, f"instance {i}: iteration count {sol['iterations'][i]} vs oracle {n}"
+        assert (sol["flags"][i] == 1) == ro["converged"]
+        for it in range(n + 1):
+            dX = np.abs(Xh[i, it] - ro["X_all"][it]).max(); dU = np.abs(Uh[i, it] - ro["U_all"][it]).max()
+            assert dX < tol_x and dU < tol_u, f"instance {i} iterate {it}: dX {dX:.2e} dU {dU:.2e}"
+            report.append((dX, dU))
+        # same discrete decisions: weight doubling (SCAlgorithm.cpp:112-115) and convergence test (:131)
+        for it in range(n):
+            assert info[i, it, 4] == ro["info"][it].weight_tr_used
+            assert abs(info[i, it, 0] - ro["info"][it].norm1_nu) < 1e-6 and abs(info[i, it, 1] - ro["info"][it].sum_delta) < 1e-5
+        # final trajectory is redimensionalised (SCAlgorithm.cpp:182-187)
+        assert np.allclose(sol["X"][i], ro["X"], rtol=1e-6, atol=1e-4 * np.abs(ro["X"]).max())
+    eng.close()
+    return report
+
+
+def test_sc_rocket2d_config0(S):
+    """BASELINE.json configs[0]: Rocket2D SC K=30 single instance (the reference's CPU-runnable case)"""
+    rep = _compare_run(S, "Rocket2D", O.ROCKET2D, [O.rocket2d()], K=30, max_it=15)
+    assert len(rep) >= 3
+
+
+def test_sc_rocketquat_k50_batch(S):
+    """BASELINE.json configs[1] at oracle-checkable batch size: RocketQuat K=50, perturbed initial states"""
+    p, rpy = O.falcon9()
+    plist = [O.rq_perturb(p, rpy, 0x5C99, i) for i in range(6)] + [p]
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=6)
+
+
+def test_sc_rocketquat_starship_k100(S):
+    """BASELINE.json configs[4]: Starship parameters, K=100"""
+    p, rpy = O.starship()
+    _compare_run(S, "RocketQuatStarship", O.ROCKETQUAT, [p, O.rq_perturb(p, rpy, 0x5C99, 1)], K=100, max_it=4)
+
+
+def test_full_batch_properties(S):
+    """BASELINE.json configs[1] at full size (1024): size-independent properties instead of oracle comparison"""
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50)
+    N = 1024
+    xi = S.perturbed_initial_states(x_init, RPY_F9, N)
+    eng = S.SCAlgorithm(model, params, cfg, N)
+    eng.set_boundary_states(xi, x_final)
+    eng.solve()
+    a = eng.get_solution(); info = eng.get_info(); t1 = eng.last_timing()
+    eng.solve()
+    b = eng.get_solution()
+    # (1) determinism / idempotence of a cold solve
+    assert np.array_equal(a["X"], b["X"]) and np.array_equal(a["U"], b["U"]) and np.array_equal(a["iterations"], b["iterations"])
+    # (2) no instance failed, every instance iterated 1..max_iterations times, accounting adds up
+    assert (a["flags"] != 2).all()
+    assert a["iterations"].min() >= 1 and a["iterations"].max() <= cfg.max_iterations
+    assert t1["instance_iterations"] == int(a["iterations"].sum())
+    # (3) boundary conditions hold for every instance (pinned variables): x_0 = x_init, final rows, last input
+    assert np.allclose(a["X"][:, 0, :], xi, rtol=1e-12, atol=1e-9)
+    fin = [1, 2, 3, 4, 5, 6, 8, 9, 11, 12, 13]
+    assert np.abs(a["X"][:, -1, fin] - x_final[fin]).max() < 1e-6
+    assert np.abs(a["U"][:, -1, [0, 1, 3]]).max() < 1e-6 and np.abs(a["U"][:, :, 3]).max() < 1e-9
+    # (4) application constraints hold (dimensional): thrust bounds, gimbal, glide slope, dry mass
+    Tn = np.linalg.norm(a["U"][:, :, :3], axis=2)
+    assert Tn.max() <= params.T_max * (1 + 1e-6)
+    assert (a["U"][:, :, 2] >= params.T_min * (1 - 1e-6)).all()                      # n = (0,0,1) on a cold start
+    assert (np.linalg.norm(a["U"][:, :, :2], axis=2) <= np.tan(params.gimbal_max) * a["U"][:, :, 2] * (1 + 1e-6) + 1e-3).all()
+    assert (np.linalg.norm(a["X"][:, :, 1:3], axis=2) <= np.tan(params.gamma_gs) * a["X"][:, :, 3] * (1 + 1e-6) + 1e-3).all()
+    assert (a["X"][:, :, 0] >= x_final[0] * (1 - 1e-9)).all()
+    # (5) every sub-problem carries a certificate: status optimal / reduced accuracy, small residuals
+    for i in range(N):
+        n = a["iterations"][i]
+        assert set(info[i, :n, 6].astype(int)) <= {0, 3}
+        assert info[i, :n, 7].max() < 1e-6 and info[i, :n, 8].max() < 1e-6
+    # (6) batch independence: instance 777 solved alone gives the identical trajectory
+    eng1 = S.SCAlgorithm(model, params, cfg, 1)
+    eng1.set_boundary_states(xi[777:778], x_final)
+    eng1.solve()
+    c = eng1.get_solution()
+    assert np.array_equal(c["X"][0], a["X"][777]) and c["iterations"][0] == a["iterations"][777]
+    eng1.close(); eng.close()
+
+
+def test_warm_start_and_errors(S):
+    model, params, x_init, x_final, cfg = S.load_model("Rocket2D", K=30)
+    eng = S.SCAlgorithm(model, params, cfg, 3)
+    with pytest.raises(S.ScppError):
+        eng.solve()                                  # boundary states not set
+    eng.set_boundary_states(x_init, x_final)
+    with pytest.raises(S.ScppError):
+        eng.solve(warm_start=True)                   # nothing to warm-start from
+    eng.solve()
+    cold = eng.get_solution()
+    assert (cold["flags"] == 1).all()
+    eng.solve(warm_start=True)                       # SCAlgorithm::solve(true): starts from the converged trajectory
+    warm = eng.get_solution()
+    assert (warm["flags"] == 1).all() and (warm["iterations"] <= cold["iterations"]).all()
+    assert np.allclose(warm["X"], cold["X"], atol=1e-3 * np.abs(cold["X"]).max())
+    eng.close()
+    bad = S.default_config(model); bad.free_final_time = 0
+    with pytest.raises(S.ScppError):
+        S.SCAlgorithm(model, params, bad, 1)
