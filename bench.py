@@ -116,7 +116,7 @@ def run_reference(args, rank, world):
         return
     import orc_py as O
     cores = os.cpu_count() or 1
-    n_inst = max(1, min(cores, 64))
+    n_inst = max(1, min(cores, 128))
     for _ in range(args.warmup):
         cpu_reference_run(min(n_inst, cores), cores)
     tot_it, tot_t = 0, 0.0
@@ -255,7 +255,7 @@ def main():
                 "roofline": roof, "roofline_iteration": roof_it, "fp64_peak": fp64, "clocks": clocks}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_s = max(1, min(cores, 32))
+            n_s = max(1, min(cores, 128))
             it, dt = cpu_reference_run(n_s, cores)
             line["cpu_baseline"] = {"value": it / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_s} of the same perturbed instances (full SC solve), one instance per thread, {dt:.1f} s wall"}

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) k_discretize(ScArrays<M> a, int nsub, int
 template <class M>
 __global__ void __launch_bounds__(WPB * 32) k_solve(ScArrays<M> a, ScConfig cfg, const int *__restrict__ active, int n_active)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * WPB + warp;
     if (gw >= n_active) return;

@@ -5,6 +5,7 @@
 #include <vector>
 #include <cstring>
 #include <cstdlib>
+#include <cmath>
 
 using namespace scpp;
 
@@ -63,6 +64,44 @@ extern "C" int hs_sc_solve(int model, const ModelParamsHost *P, const ScConfig *
 {
     if (model == 0) return run_sc<RocketQuat>(P, cfg, N, x_init, x_final, X, U, sigma, iters, status, converged, hist, info);
     return run_sc<Rocket2d>(P, cfg, N, x_init, x_final, X, U, sigma, iters, status, converged, hist, info);
+}
+
+// forward-mode dual number: instantiates the generic-scalar flow map (the plugin surface, systemFlowMap) to obtain the exact
+// Jacobian the reference gets from CppAD (systemDynamics.hpp:206-235); compared in tests with the hand-derived sparse one
+struct Dual {
+    double v, d;
+    Dual(double v_ = 0., double d_ = 0.) : v(v_), d(d_) {}
+};
+static inline Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+static inline Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+static inline Dual operator-(Dual a) { return {-a.v, -a.d}; }
+static inline Dual operator*(Dual a, Dual b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
+static inline Dual operator/(Dual a, Dual b) { return {a.v / b.v, (a.d * b.v - a.v * b.d) / (b.v * b.v)}; }
+static inline Dual sqrt(Dual a) { double r = std::sqrt(a.v); return {r, a.d / (2. * r)}; }
+static inline Dual sin(Dual a) { return {std::sin(a.v), std::cos(a.v) * a.d}; }
+static inline Dual cos(Dual a) { return {std::cos(a.v), -std::sin(a.v) * a.d}; }
+
+template <class M>
+static void run_jac(const double *x, const double *u, const double *par, double *f, double *A_ad, double *B_ad, double *A_lin, double *B_lin)
+{
+    constexpr int NX = M::NX, NU = M::NU;
+    M::template flow_map<double>(x, u, par, f);
+    for (int j = 0; j < NX + NU; j++) {
+        Dual xd[NX], ud[NU], fd[NX];
+        for (int i = 0; i < NX; i++) xd[i] = Dual(x[i], i == j ? 1. : 0.);
+        for (int i = 0; i < NU; i++) ud[i] = Dual(u[i], NX + i == j ? 1. : 0.);
+        M::template flow_map<Dual>(xd, ud, par, fd);
+        for (int i = 0; i < NX; i++) { if (j < NX) A_ad[i * NX + j] = fd[i].d; else B_ad[i * NU + (j - NX)] = fd[i].d; }
+    }
+    typename M::Lin L;
+    M::linearize(x, u, par, L);
+    for (int j = 0; j < NX; j++) { double e[NX] = {0}, o[NX]; e[j] = 1.; M::A_apply(L, e, o); for (int i = 0; i < NX; i++) A_lin[i * NX + j] = o[i]; }
+    for (int j = 0; j < NU; j++) { double e[NU] = {0}, o[NX]; e[j] = 1.; M::B_apply(L, e, o); for (int i = 0; i < NX; i++) B_lin[i * NU + j] = o[i]; }
+    for (int i = 0; i < NX; i++) if (std::fabs(L.f[i] - f[i]) > 1e-13 * (1. + std::fabs(f[i]))) f[i] = NAN;   // Lin.f must equal flow_map
+}
+extern "C" void hs_jacobians(int model, const double *x, const double *u, const double *par, double *f, double *A_ad, double *B_ad, double *A_lin, double *B_lin)
+{
+    if (model == 0) run_jac<RocketQuat>(x, u, par, f, A_ad, B_ad, A_lin, B_lin); else run_jac<Rocket2d>(x, u, par, f, A_ad, B_ad, A_lin, B_lin);
 }
 
 extern "C" int hs_sizes(int which) { return which == 0 ? (int)sizeof(ModelParamsHost) : (int)sizeof(ScConfig); }

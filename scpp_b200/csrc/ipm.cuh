@@ -16,13 +16,18 @@
 // (NB x NB blocks, NB = nx + nu) plus one dense border row/column for sigma; it is factored by a block Cholesky
 // sweep over the K nodes.
 //
-// Work split inside the warp: cone arithmetic is done lane-per-node / lane-per-row; everything touching the
-// discretisation tensors [A|B|C|s|z]_k and the NB x NB blocks is warp-cooperative on tiles staged in shared memory.
+// Execution shape (v2): every phase is a SWEEP over the K stages (stage k = node k + shooting interval k).  All
+// per-instance state lives in HBM in stage-major records; for each stage the warp copies the stage's records
+// (the [A|B|C|s|z]_k tile, the cone rows, the factor blocks) into a shared-memory window with coalesced 16-byte
+// asynchronous copies, works on the window (cone arithmetic: one lane per cone / LP row / virtual-control pair;
+// tile and block arithmetic: warp-cooperative), and writes the results back coalesced.  Global memory is never
+// touched with per-lane strided or dependent accesses.
 #pragma once
 #include "models.cuh"
 #if !defined(__CUDACC__)
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #endif
 
 namespace scpp {
@@ -38,9 +43,101 @@ struct IpmResult {
     double pres, dres, gap, relgap, pcost;
 };
 
+#if defined(__CUDACC__)
+#define SCPP_OUTLINE __host__ __device__ __noinline__
+#else
+#define SCPP_OUTLINE inline
+#endif
+
+// ---- second-order-cone primitives (one lane, one cone); kept out of line to bound the code size -------------------
+namespace soc {
+SCPP_HD double jn2(const double *u, int d) { double n = 0; for (int i = 1; i < d; i++) n += u[i] * u[i]; return u[0] * u[0] - n; }
+
+SCPP_OUTLINE bool scale(const double *sk, const double *zk, int d, double *w, double &e2i, double *lm)
+{
+    double ss = jn2(sk, d), zz = jn2(zk, d);
+    if (!(ss > 0.) || !(zz > 0.) || !(sk[0] > 0.) || !(zk[0] > 0.)) return false;
+    double sn = sqrt(ss), zn = sqrt(zz), sz = 0;
+#pragma unroll 1
+    for (int i = 0; i < d; i++) sz += sk[i] * zk[i];
+    double gam = sqrt((1. + sz / (sn * zn)) / 2.);
+    double i2g = 1. / (2. * gam);
+    w[0] = (sk[0] / sn + zk[0] / zn) * i2g;
+#pragma unroll 1
+    for (int i = 1; i < d; i++) w[i] = (sk[i] / sn - zk[i] / zn) * i2g;
+    e2i = zn / sn;
+    double eta = sqrt(sn / zn), w1z1 = 0;
+#pragma unroll 1
+    for (int i = 1; i < d; i++) w1z1 += w[i] * zk[i];
+    double f = zk[0] + w1z1 / (1. + w[0]);
+    lm[0] = eta * (w[0] * zk[0] + w1z1);
+#pragma unroll 1
+    for (int i = 1; i < d; i++) lm[i] = eta * (zk[i] + f * w[i]);
+    return true;
+}
+// o = W^-2 v  (o may alias v)
+SCPP_OUTLINE void Mv(const double *w, double e2i, const double *v, int d, double *o)
+{
+    double dot = w[0] * v[0];
+#pragma unroll 1
+    for (int i = 1; i < d; i++) dot -= w[i] * v[i];
+    const double v0 = v[0];
+#pragma unroll 1
+    for (int i = 1; i < d; i++) o[i] = e2i * (-2. * dot * w[i] + v[i]);
+    o[0] = e2i * (2. * dot * w[0] - v0);
+}
+// o = W v | W^-1 v  (o may alias v)
+SCPP_OUTLINE void Wv(const double *w, double e2i, const double *v, int d, double *o, bool inv)
+{
+    const double eta = 1. / sqrt(e2i);
+    const double sg = inv ? -1. : 1., sc = inv ? 1. / eta : eta;
+    double w1v1 = 0;
+#pragma unroll 1
+    for (int i = 1; i < d; i++) w1v1 += w[i] * v[i];
+    const double o0 = w[0] * v[0] + sg * w1v1, f = sg * v[0] + w1v1 / (1. + w[0]);
+#pragma unroll 1
+    for (int i = 1; i < d; i++) o[i] = sc * (v[i] + f * w[i]);
+    o[0] = sc * o0;
+}
+SCPP_OUTLINE void jprod(const double *u, const double *v, int d, double *o)   // o may alias u or v
+{
+    double dot = 0;
+#pragma unroll 1
+    for (int i = 0; i < d; i++) dot += u[i] * v[i];
+    const double u0 = u[0], v0 = v[0];
+#pragma unroll 1
+    for (int i = 1; i < d; i++) o[i] = u0 * v[i] + v0 * u[i];
+    o[0] = dot;
+}
+SCPP_OUTLINE void jdiv(const double *lm, const double *dv, int d, double *o)   // o = lm \ dv  (o may alias dv)
+{
+    double den = jn2(lm, d), l1d1 = 0;
+#pragma unroll 1
+    for (int i = 1; i < d; i++) l1d1 += lm[i] * dv[i];
+    const double x0 = (lm[0] * dv[0] - l1d1) / den;
+#pragma unroll 1
+    for (int i = 1; i < d; i++) o[i] = (dv[i] - x0 * lm[i]) / lm[0];
+    o[0] = x0;
+}
+SCPP_OUTLINE double step(const double *lm, const double *dk, int d)
+{
+    const double a = sqrt(jn2(lm, d)), l0 = lm[0] / a;
+    double ld = l0 * dk[0];
+#pragma unroll 1
+    for (int i = 1; i < d; i++) ld -= lm[i] / a * dk[i];
+    const double rho0 = ld / a, f = (ld + dk[0]) / (l0 + 1.);
+    double n1 = 0;
+#pragma unroll 1
+    for (int i = 1; i < d; i++) { double r = (dk[i] - f * lm[i] / a) / a; n1 += r * r; }
+    return sqrt(n1) - rho0;
+}
+} // namespace soc
+
+SCPP_HD constexpr int pad2(int x) { return (x + 1) & ~1; }
+
 template <class M>
 struct Ipm {
-    static constexpr int NX = M::NX, NU = M::NU, NB = NX + NU, NC = NX + 2 * NU + 2, NCP = NC + 1;
+    static constexpr int NX = M::NX, NU = M::NU, NB = NX + NU, NC = NX + 2 * NU + 2, NCP = NC + 2;
     static constexpr int NLP = M::NLP, NCONE = M::NCONE, NCR = M::NCR;
     static constexpr int MN = NLP + NCR + 1 + NB;   // cone rows per node: model LP | model cones | trust region
     static constexpr int PN = NB + 1;               // primal per node: xi, delta
@@ -48,14 +145,26 @@ struct Ipm {
     static constexpr int NRK = NCONE + 1;           // rank-1 terms of the model Hessian: cones + one multi-entry LP row
     static constexpr int TRO = NLP + NCR;           // offset of the trust-region cone inside a node block
     static constexpr int BLK = NB * NB;
-    static constexpr int FACK = 2 * BLK + NB;       // per node: Linv_kk | L_{k+1,k} | border l_k
+    static constexpr int NTASK = NCN + NLP + NX;    // per-stage cone tasks: cones, LP rows, virtual-control pairs
+    // stage-major record strides (even => 16-byte aligned records)
+    static constexpr int RS = pad2(MN + 2 * NX);    // cone rows of one stage: node rows | interval rows (s-: NX, s+: NX)
+    static constexpr int PS = pad2(PN + NX);        // primal of one stage: xi | delta | t
+    static constexpr int CS = pad2(NCN);            // eta^-2 per cone of one stage
+    static constexpr int FS = pad2(2 * BLK + 2 * NB);   // Linv_kk | L_{k+1,k} | l_k | f_k
+    static constexpr int OFF_LN = BLK, OFF_L = 2 * BLK, OFF_F = 2 * BLK + NB;
+    static_assert(NB % 2 == 0 && NC % 2 == 0, "16-byte record alignment needs even nx+nu and even tile width");
 
-    SCPP_HD static int m_rows(int K) { return K * MN + (K - 1) * 2 * NX + 4; }
-    SCPP_HD static int n_prim(int K) { return K * PN + 2 + (K - 1) * NX; }
-    SCPP_HD static int n_cones(int K) { return K * NCN + 1; }
-    SCPP_HD static int n_y(int K) { return K * NB + 1; }
-    SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 8 * m_rows(K) + n_cones(K) + K * FACK + n_y(K) + 16; }
-    SCPP_HD static int sm_doubles() { return NX * NCP + 5 * BLK + 2 * NRK * NB + 12 * NB + 4 * NX + 32; }
+    SCPP_HD static int m_rows(int K) { return K * RS + 4; }
+    SCPP_HD static int n_prim(int K) { return K * PS + 2; }
+    SCPP_HD static int n_ce(int K) { return K * CS + 2; }
+    SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 8 * m_rows(K) + n_ce(K) + K * FS + 16; }
+    // shared window: tile | factor record | L_{k,k-1} carry | UNION{ 8 row arrays + primal windows ; phase F: wb + H,O,Hn + model terms }
+    //                | vectors | scalars
+    static constexpr int W_DD = 0, W_FAC = W_DD + pad2(NX * NCP), W_LP = W_FAC + FS, W_ROW = W_LP + BLK, W_PRIM = W_ROW + 8 * RS,
+                         W_MAT = W_ROW + RS, W_RK = W_MAT + 3 * BLK,
+                         W_UEND = (W_PRIM + 4 * PS + pad2(NB)) > (W_RK + 2 * NRK * NB) ? (W_PRIM + 4 * PS + pad2(NB)) : (W_RK + 2 * NRK * NB),
+                         W_VEC = W_UEND, W_X = W_VEC + 6 * NB, W_SC = W_X + 2 * pad2(NX), W_END = W_SC + 32;
+    SCPP_HD static int sm_doubles() { return W_END; }
 
     // ---- problem data (read only) -----------------------------------------------------------------------------
     int K;
@@ -68,13 +177,13 @@ struct Ipm {
     const uint32_t *fixm;  // [K]
     const double *fixv;    // [K][NB]
     double w_time, w_trs, w_tr, w_vc;
-    // ---- workspace (global memory, per instance) --------------------------------------------------------------
-    double *prim, *dprim, *rx;
+    // ---- workspace (global memory, per instance, stage-major) ---------------------------------------------------
+    double *prim, *dprim, *rx, *best_;
     double *s, *z, *wb, *lam, *rz, *cr, *dz, *ds;
-    double *ce;            // eta^-2 per second-order cone
-    double *fac, *gy;
-    double *best_;         // best primal iterate seen
-    double *sm;            // per-warp shared scratch
+    double *ce;
+    double *fac;
+    double *sm;            // per-warp shared window
+    double l_ss;           // Cholesky pivot of the sigma border
 
     SCPP_HD void bind(double *ws, double *smem)
     {
@@ -82,248 +191,242 @@ struct Ipm {
         double *p = ws;
         prim = p; p += np; dprim = p; p += np; rx = p; p += np; best_ = p; p += np;
         s = p; p += m; z = p; p += m; wb = p; p += m; lam = p; p += m; rz = p; p += m; cr = p; p += m; dz = p; p += m; ds = p; p += m;
-        ce = p; p += n_cones(K);
-        fac = p; p += K * FACK;
-        gy = p; p += n_y(K);
+        ce = p; p += n_ce(K);
+        fac = p;
         sm = smem;
     }
-    // index helpers
-    SCPP_HD int pn(int k) const { return k * PN; }
-    SCPP_HD int p_sigma() const { return K * PN; }
-    SCPP_HD int p_dsig() const { return K * PN + 1; }
-    SCPP_HD int p_t(int k) const { return K * PN + 2 + k * NX; }
-    SCPP_HD int rn(int k) const { return k * MN; }
-    SCPP_HD int ri(int k) const { return K * MN + k * 2 * NX; }
-    SCPP_HD int rg() const { return K * MN + (K - 1) * 2 * NX; }
+    // accessors used by the SC glue (sc.cuh)
+    SCPP_HD double xi_at(int k, int i) const { return prim[k * PS + i]; }
+    SCPP_HD double delta_at(int k) const { return prim[k * PS + NB]; }
+    SCPP_HD double t_at(int k, int i) const { return prim[k * PS + PN + i]; }
+    SCPP_HD double sigma_val() const { return prim[K * PS]; }
+    SCPP_HD double dsigma_val() const { return prim[K * PS + 1]; }
+
     SCPP_HD bool fixed(int k, int i) const { return (fixm[k] >> i) & 1u; }
-    SCPP_HD double xibar(int k, int i) const { return i < NX ? Xbar[k * NX + i] : Ubar[k * NU + (i - NX)]; }
 
-    // shared scratch layout
-    SCPP_HD double *sm_dd() const { return sm; }
-    SCPP_HD double *sm_H() const { return sm + NX * NCP; }
-    SCPP_HD double *sm_O() const { return sm_H() + BLK; }
-    SCPP_HD double *sm_Lp() const { return sm_O() + BLK; }
-    SCPP_HD double *sm_Li() const { return sm_Lp() + BLK; }
-    SCPP_HD double *sm_Hn() const { return sm_Li() + BLK; }
-    SCPP_HD double *sm_rk() const { return sm_Hn() + BLK; }            // [NRK][NB] rank-1 vectors, then [NRK][NB] diagonals
-    SCPP_HD double *sm_v(int i) const { return sm_rk() + 2 * NRK * NB + i * NB; }   // 12 NB-vectors
-    SCPP_HD double *sm_x(int i) const { return sm_v(12) + i * NX; }                 // 4 NX-vectors
-    SCPP_HD double *sm_sc() const { return sm_x(4); }                               // 32 scalars
+    // ---- window plumbing ------------------------------------------------------------------------------------------
+    // cooperative copy of n (even) doubles global -> shared, 16 bytes per lane per step, asynchronous on the device
+    SCPP_HD void ld(double *dst, const double *src, int n) const
+    {
+#if defined(__CUDA_ARCH__)
+        const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+        for (int c = lane_id(); c < n / 2; c += LANES)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u * c), "l"(src + 2 * c) : "memory");
+#else
+        memcpy(dst, src, sizeof(double) * n);
+#endif
+    }
+    // the [A|B|C|s|z]_k tile: NX rows of NC doubles into rows of stride NCP
+    SCPP_HD void ld_dd(int k) const
+    {
+        const double *src = dd + (size_t)k * NX * NC;
+        double *t = sm + W_DD;
+#if defined(__CUDA_ARCH__)
+        const unsigned d0 = (unsigned)__cvta_generic_to_shared(t);
+        for (int c = lane_id(); c < NX * (NC / 2); c += LANES) {
+            const int r = c / (NC / 2), q = c - r * (NC / 2);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0 + 8u * (r * NCP + 2 * q)), "l"(src + r * NC + 2 * q) : "memory");
+        }
+#else
+        for (int r = 0; r < NX; r++) memcpy(t + r * NCP, src + r * NC, sizeof(double) * NC);
+#endif
+    }
+    SCPP_HD void ld_wait() const
+    {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+#endif
+        warp_sync();
+    }
+    // cooperative coalesced store shared -> global
+    SCPP_HD void st(double *dst, const double *src, int n) const { FOR_LANE(e, n) dst[e] = src[e]; }
 
-    // ---- second-order-cone primitives (one lane, one cone) ------------------------------------------------------
-    SCPP_HD static double jn2(const double *u, int d) { double n = 0; for (int i = 1; i < d; i++) n += u[i] * u[i]; return u[0] * u[0] - n; }
-    SCPP_HD static bool soc_scale(const double *sk, const double *zk, int d, double *w, double &e2i, double *lm)
-    {
-        double ss = jn2(sk, d), zz = jn2(zk, d);
-        if (!(ss > 0.) || !(zz > 0.) || !(sk[0] > 0.) || !(zk[0] > 0.)) return false;
-        double sn = sqrt(ss), zn = sqrt(zz), sz = 0;
-        for (int i = 0; i < d; i++) sz += sk[i] * zk[i];
-        double gam = sqrt((1. + sz / (sn * zn)) / 2.);
-        double i2g = 1. / (2. * gam);
-        w[0] = (sk[0] / sn + zk[0] / zn) * i2g;
-        for (int i = 1; i < d; i++) w[i] = (sk[i] / sn - zk[i] / zn) * i2g;
-        e2i = zn / sn;
-        double eta = sqrt(sn / zn), w1z1 = 0;
-        for (int i = 1; i < d; i++) w1z1 += w[i] * zk[i];
-        double f = zk[0] + w1z1 / (1. + w[0]);
-        lm[0] = eta * (w[0] * zk[0] + w1z1);
-        for (int i = 1; i < d; i++) lm[i] = eta * (zk[i] + f * w[i]);
-        return true;
-    }
-    SCPP_HD static void soc_M(const double *w, double e2i, const double *v, int d, double *o)   // o = W^-2 v
-    {
-        double dot = w[0] * v[0];
-        for (int i = 1; i < d; i++) dot -= w[i] * v[i];
-        o[0] = e2i * (2. * dot * w[0] - v[0]);
-        for (int i = 1; i < d; i++) o[i] = e2i * (-2. * dot * w[i] + v[i]);
-    }
-    SCPP_HD static void soc_W(const double *w, double e2i, const double *v, int d, double *o, bool inv) // o = W v | W^-1 v
-    {
-        const double eta = 1. / sqrt(e2i);
-        const double sg = inv ? -1. : 1., sc = inv ? 1. / eta : eta;
-        double w1v1 = 0;
-        for (int i = 1; i < d; i++) w1v1 += w[i] * v[i];
-        const double o0 = w[0] * v[0] + sg * w1v1, f = sg * v[0] + w1v1 / (1. + w[0]);
-        for (int i = 1; i < d; i++) o[i] = sc * (v[i] + f * w[i]);
-        o[0] = sc * o0;
-    }
-    SCPP_HD static void soc_jprod(const double *u, const double *v, int d, double *o)
-    {
-        double dot = 0;
-        for (int i = 0; i < d; i++) dot += u[i] * v[i];
-        const double u0 = u[0], v0 = v[0];
-        for (int i = 1; i < d; i++) o[i] = u0 * v[i] + v0 * u[i];
-        o[0] = dot;
-    }
-    SCPP_HD static void soc_jdiv(const double *lm, const double *dv, int d, double *o)
-    {
-        double den = jn2(lm, d), l1d1 = 0;
-        for (int i = 1; i < d; i++) l1d1 += lm[i] * dv[i];
-        const double x0 = (lm[0] * dv[0] - l1d1) / den;
-        for (int i = 1; i < d; i++) o[i] = (dv[i] - x0 * lm[i]) / lm[0];
-        o[0] = x0;
-    }
-    SCPP_HD static double soc_step(const double *lm, const double *dk, int d)
-    {
-        const double a = sqrt(jn2(lm, d)), l0 = lm[0] / a;
-        double ld = l0 * dk[0];
-        for (int i = 1; i < d; i++) ld -= lm[i] / a * dk[i];
-        const double rho0 = ld / a, f = (ld + dk[0]) / (l0 + 1.);
-        double n1 = 0;
-        for (int i = 1; i < d; i++) { double r = (dk[i] - f * lm[i] / a) / a; n1 += r * r; }
-        return sqrt(n1) - rho0;
-    }
+    SCPP_HD double *row(int a) const { return sm + W_ROW + a * RS; }     // 8 row-array windows
+    SCPP_HD double *pw(int a) const { return sm + W_PRIM + a * PS; }     // 4 primal windows (+ NB spare after the 4th)
+    SCPP_HD double *vec(int i) const { return sm + W_VEC + i * NB; }
+    SCPP_HD double *xv(int i) const { return sm + W_X + i * pad2(NX); }
+    SCPP_HD double *sc() const { return sm + W_SC; }
+    SCPP_HD double *tile() const { return sm + W_DD; }
+    SCPP_HD double *facw() const { return sm + W_FAC; }
 
-    // row r of the node table evaluated at xi:  returns h - sum coef xi
-    SCPP_HD double row_slack(int r, int k, const double *xi) const
+    // task -> (type, row offset in the stage window, dimension, cone index): 0 LP row, 1 second-order cone, 2 virtual-control pair
+    SCPP_HD static void task(int tk, int &type, int &o, int &d, int &ci)
     {
-        const RowDesc rd = M::row(r);
-        double v = cst[rd.hs];
-        for (int j = 0; j < rd.n; j++) v -= coef(rd, j, k) * xi[rd.idx[j]];
-        return v;
+        if (tk < NCONE) { type = 1; o = NLP + M::cone_off(tk); d = M::cone_dim(tk); ci = tk; }
+        else if (tk == NCONE) { type = 1; o = TRO; d = 1 + NB; ci = NCONE; }
+        else if (tk < NCN + NLP) { type = 0; o = tk - NCN; d = 1; ci = -1; }
+        else { type = 2; o = MN + (tk - NCN - NLP); d = 1; ci = -1; }
     }
     SCPP_HD double coef(const RowDesc &rd, int j, int k) const { return rd.cs[j] >= 0 ? cst[rd.cs[j]] : -tdir[3 * k + (-rd.cs[j] - 1)]; }
 
-    // stage the discretisation tile of interval k into shared memory (row stride padded to NCP)
-    SCPP_HD void stage_dd(int k) const
+    // r_i = x_{k+1,i} - (A~ xi_k)_i - (C u_{k+1})_i - s_i sigma [- z_i]   from windows (tile staged)
+    SCPP_HD double dyn_row(int i, const double *xk, const double *xn, double sg, bool with_const) const
     {
-        const double *src = dd + (size_t)k * NX * NC;
-        double *t = sm_dd();
-        FOR_LANE(e, NX * NC) { int r = e / NC, c = e - r * NC; t[r * NCP + c] = src[e]; }
-        warp_sync();
-    }
-    // r_i = x_{k+1,i} - (A xi_k)_i - (B u_k)_i - (C u_{k+1})_i - s_i sigma - z_i  for lane-owned i (tile staged), y from `p`
-    SCPP_HD double dyn_resid(int k, int i, const double *p, bool with_const) const
-    {
-        const double *t = sm_dd() + i * NCP;
-        const double *xk = p + pn(k), *xn = p + pn(k + 1);
+        const double *t = tile() + i * NCP;
         double acc = xn[i];
+#pragma unroll 1
         for (int j = 0; j < NB; j++) acc -= t[j] * xk[j];
+#pragma unroll 1
         for (int j = 0; j < NU; j++) acc -= t[NB + j] * xn[NX + j];
-        acc -= t[NB + NU] * p[p_sigma()];
+        acc -= t[NB + NU] * sg;
         if (with_const) acc -= t[NB + NU + 1];
         return acc;
     }
-    // out (indexed like y) += J' w  for interval k, w in sm_x(0)[NX] ; tile staged.  out_k = node k slice, etc.
-    SCPP_HD void dyn_JT(int k, const double *w, double *out_k, double *out_n, double &acc_sigma) const
+    // out_k -= A~' w ; carry = [w ; -C' w] (contribution to node k+1) ; returns lane-partial of -s'w
+    SCPP_HD double dyn_JT(const double *w, double *out_k, double *carry) const
     {
-        const double *t = sm_dd();
-        FOR_LANE(j, NB) { double a = 0; for (int i = 0; i < NX; i++) a += t[i * NCP + j] * w[i]; out_k[j] -= a; }
+        const double *t = tile();
         FOR_LANE(j, NB) {
-            if (j < NX) out_n[j] += w[j];
-            else { double a = 0; for (int i = 0; i < NX; i++) a += t[i * NCP + NB + (j - NX)] * w[i]; out_n[j] -= a; }
+            double a = 0, c = 0;
+#pragma unroll 1
+            for (int i = 0; i < NX; i++) a += t[i * NCP + j] * w[i];
+            out_k[j] -= a;
+            if (j < NX) c = w[j];
+            else {
+#pragma unroll 1
+                for (int i = 0; i < NX; i++) c -= t[i * NCP + NB + (j - NX)] * w[i];
+            }
+            carry[j] = c;
         }
-        FOR_LANE(i, NX) acc_sigma -= t[i * NCP + NB + NU] * w[i];
+        double sg = 0;
+        FOR_LANE(i, NX) sg -= t[i * NCP + NB + NU] * w[i];
+        return sg;
+    }
+    // gather of the model-row contributions G' v onto variable j of the node (generic: scans the row table)
+    SCPP_HD double model_GT(int j, int k, const double *v /* node rows window */) const
+    {
+        double a = 0;
+#pragma unroll 1
+        for (int r = 0; r < NLP + NCR; r++) {
+            const RowDesc rd = M::row(r);
+#pragma unroll 1
+            for (int q = 0; q < rd.n; q++) if (rd.idx[q] == j) a += coef(rd, q, k) * v[r];
+        }
+        return a;
+    }
+    SCPP_HD double model_G(int r, int k, const double *x) const   // (G x)_r for a model row
+    {
+        const RowDesc rd = M::row(r);
+        double a = 0;
+#pragma unroll 1
+        for (int q = 0; q < rd.n; q++) a += coef(rd, q, k) * x[rd.idx[q]];
+        return a;
+    }
+    SCPP_HD void load_xibar(int k, double *dst) const
+    {
+        FOR_LANE(i, NB) dst[i] = i < NX ? Xbar[k * NX + i] : Ubar[k * NU + (i - NX)];
     }
 
     // =============================================================================================================
-    //  Phase R : residuals, Nesterov-Todd scaling, termination quantities
+    //  Phase R : residuals, Nesterov-Todd scaling, termination quantities  (one forward sweep)
     // =============================================================================================================
     struct Norms { double gap, rz2, rx2, pcost, zrz, xrx, h2; int bad; };
 
     SCPP_HD void phase_residuals(Norms &nm, bool identity)
     {
-        double gap = 0, rz2 = 0, pcost = 0, zrz = 0, h2 = 0;
+        double gap = 0, rz2 = 0, pcost = 0, zrz = 0, h2 = 0, rx2 = 0, xrx = 0, acc_sig = 0;
         int bad = 0;
-        // ---- nodes: one lane per node
-        for (int k = lane_id(); k < K; k += LANES) {
-            const double *xi = prim + pn(k);
-            const double dl = xi[NB];
-            double *rxk = rx + pn(k);
-            for (int i = 0; i < NB; i++) rxk[i] = 0.;
-            const int r0 = rn(k);
-            // model rows
-            for (int r = 0; r < NLP + NCR; r++) {
-                const RowDesc rd = M::row(r);
-                double sl = cst[rd.hs];
-                for (int j = 0; j < rd.n; j++) { const double c = coef(rd, j, k); sl -= c * xi[rd.idx[j]]; rxk[rd.idx[j]] += c * z[r0 + r]; }
-                rz[r0 + r] = s[r0 + r] - sl;
-                h2 += cst[rd.hs] * cst[rd.hs];
-            }
-            // trust region: s = (delta ; xibar - xi)
-            rz[r0 + TRO] = s[r0 + TRO] - dl;
-            for (int i = 0; i < NB; i++) {
-                const double xb = xibar(k, i);
-                rz[r0 + TRO + 1 + i] = s[r0 + TRO + 1 + i] - (xb - xi[i]);
-                rxk[i] += z[r0 + TRO + 1 + i];
-                h2 += xb * xb;
-            }
-            rxk[NB] = w_tr - z[r0 + TRO];
-            pcost += w_tr * dl;
-            // scaling
-            for (int r = 0; r < NLP; r++) {
-                const double sv = s[r0 + r], zv = z[r0 + r];
-                if (!(sv > 0.) || !(zv > 0.)) bad = 1;
-                wb[r0 + r] = identity ? 1. : zv / sv;
-                lam[r0 + r] = identity ? 1. : sqrt(sv * zv);
-            }
-            for (int c = 0; c < NCN; c++) {
-                const int o = r0 + NLP + (c < NCONE ? M::cone_off(c) : NCR), d = c < NCONE ? M::cone_dim(c) : 1 + NB;
-                if (identity) { ce[k * NCN + c] = 1.; for (int i = 0; i < d; i++) { wb[o + i] = i == 0; lam[o + i] = i == 0; } }
-                else if (!soc_scale(s + o, z + o, d, wb + o, ce[k * NCN + c], lam + o)) bad = 1;
-            }
-            for (int r = 0; r < MN; r++) { gap += s[r0 + r] * z[r0 + r]; rz2 += rz[r0 + r] * rz[r0 + r]; zrz += z[r0 + r] * rz[r0 + r]; }
-        }
-        warp_sync();
-        // ---- intervals: warp-cooperative, tile staged
-        double acc_sig = 0;
-        for (int k = 0; k < K - 1; k++) {
-            stage_dd(k);
-            const int r0 = ri(k);
-            double *w = sm_x(0);
-            FOR_LANE(i, NX) {
-                const double r = dyn_resid(k, i, prim, true);
-                const double t = prim[p_t(k) + i];
-                const double sm_ = s[r0 + i], sp = s[r0 + NX + i], zm = z[r0 + i], zp = z[r0 + NX + i];
-                const double rm = sm_ - (t - r), rp = sp - (t + r);
-                rz[r0 + i] = rm; rz[r0 + NX + i] = rp;
-                if (!(sm_ > 0.) || !(sp > 0.) || !(zm > 0.) || !(zp > 0.)) bad = 1;
-                wb[r0 + i] = identity ? 1. : zm / sm_; wb[r0 + NX + i] = identity ? 1. : zp / sp;
-                lam[r0 + i] = identity ? 1. : sqrt(sm_ * zm); lam[r0 + NX + i] = identity ? 1. : sqrt(sp * zp);
-                rx[p_t(k) + i] = w_vc - zm - zp;
-                w[i] = zm - zp;
-                gap += sm_ * zm + sp * zp; rz2 += rm * rm + rp * rp; zrz += zm * rm + zp * rp;
-                pcost += w_vc * t;
-                const double zc = sm_dd()[i * NCP + NB + NU + 1];
-                h2 += 2. * zc * zc;
+        double *S = row(0), *Z = row(1), *RZ = row(2), *WB = row(3), *LM = row(4);
+        double *P = pw(0), *PNX = pw(1), *RX = pw(2), *XB = pw(3), *CE = sc();
+        double *carry = vec(0), *w = xv(0);
+        const double sg = prim[K * PS];
+        FOR_LANE(j, NB) carry[j] = 0.;
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            const bool hasint = k < K - 1;
+            if (hasint) { ld_dd(k); ld(PNX, prim + (k + 1) * PS, PS); }
+            ld(S, s + k * RS, RS); ld(Z, z + k * RS, RS); ld(P, prim + k * PS, PS);
+            load_xibar(k, XB);
+            ld_wait();
+            // ---- cone tasks
+            FOR_LANE(tk, NTASK) {
+                int type, o, d, ci;
+                task(tk, type, o, d, ci);
+                if (type == 1) {
+                    if (ci < NCONE) {
+#pragma unroll 1
+                        for (int r = 0; r < d; r++) { const RowDesc rd = M::row(o + r); const double sl = cst[rd.hs] - model_G(o + r, k, P); RZ[o + r] = S[o + r] - sl; h2 += cst[rd.hs] * cst[rd.hs]; }
+                    } else {
+                        RZ[o] = S[o] - P[NB];
+#pragma unroll 1
+                        for (int i = 0; i < NB; i++) { RZ[o + 1 + i] = S[o + 1 + i] - (XB[i] - P[i]); h2 += XB[i] * XB[i]; }
+                        pcost += w_tr * P[NB];
+                    }
+                    if (identity) { CE[ci] = 1.; for (int i = 0; i < d; i++) { WB[o + i] = i == 0; LM[o + i] = i == 0; } }
+                    else if (!soc::scale(S + o, Z + o, d, WB + o, CE[ci], LM + o)) bad = 1;
+#pragma unroll 1
+                    for (int r = 0; r < d; r++) { gap += S[o + r] * Z[o + r]; rz2 += RZ[o + r] * RZ[o + r]; zrz += Z[o + r] * RZ[o + r]; }
+                } else if (type == 0) {
+                    const RowDesc rd = M::row(o);
+                    const double sl = cst[rd.hs] - model_G(o, k, P);
+                    const double sv = S[o], zv = Z[o];
+                    RZ[o] = sv - sl;
+                    h2 += cst[rd.hs] * cst[rd.hs];
+                    if (!(sv > 0.) || !(zv > 0.)) bad = 1;
+                    WB[o] = identity ? 1. : zv / sv; LM[o] = identity ? 1. : sqrt(sv * zv);
+                    gap += sv * zv; rz2 += RZ[o] * RZ[o]; zrz += zv * RZ[o];
+                } else if (hasint) {
+                    const int i = o - MN;
+                    const double r = dyn_row(i, P, PNX, sg, true), t = P[PN + i];
+                    const double sm_ = S[o], sp = S[o + NX], zm = Z[o], zp = Z[o + NX];
+                    const double rm = sm_ - (t - r), rp = sp - (t + r);
+                    RZ[o] = rm; RZ[o + NX] = rp;
+                    if (!(sm_ > 0.) || !(sp > 0.) || !(zm > 0.) || !(zp > 0.)) bad = 1;
+                    WB[o] = identity ? 1. : zm / sm_; WB[o + NX] = identity ? 1. : zp / sp;
+                    LM[o] = identity ? 1. : sqrt(sm_ * zm); LM[o + NX] = identity ? 1. : sqrt(sp * zp);
+                    RX[PN + i] = w_vc - zm - zp;
+                    w[i] = zm - zp;
+                    gap += sm_ * zm + sp * zp; rz2 += rm * rm + rp * rp; zrz += zm * rm + zp * rp;
+                    pcost += w_vc * t;
+                    const double zc = tile()[i * NCP + NB + NU + 1];
+                    h2 += 2. * zc * zc;
+                } else {
+                    const int i = o - MN;
+                    RZ[o] = 0.; RZ[o + NX] = 0.; WB[o] = 1.; WB[o + NX] = 1.; LM[o] = 1.; LM[o + NX] = 1.; RX[PN + i] = 0.;
+                }
             }
             warp_sync();
-            dyn_JT(k, w, rx + pn(k), rx + pn(k + 1), acc_sig);
+            // ---- dual residual of node k: carry from interval k-1 + G'z of the node cones (+ interval k below)
+            FOR_LANE(j, NB) RX[j] = carry[j] + Z[TRO + 1 + j] + model_GT(j, k, Z);
+            if (lane_id() == 0) RX[NB] = w_tr - Z[TRO];
+            warp_sync();
+            if (hasint) acc_sig += dyn_JT(w, RX, carry);
+            warp_sync();
+            FOR_LANE(e, PN + NX) {
+                if (e < NB && fixed(k, e)) RX[e] = 0.;
+                rx2 += RX[e] * RX[e]; xrx += P[e] * RX[e];
+            }
+            warp_sync();
+            st(rz + k * RS, RZ, RS); st(wb + k * RS, WB, RS); st(lam + k * RS, LM, RS);
+            st(rx + k * PS, RX, PN + NX);
+            FOR_LANE(c, NCN) ce[k * CS + c] = CE[c];
             warp_sync();
         }
         acc_sig = warp_sum(acc_sig);
         // ---- globals: lane 0
         if (lane_id() == 0) {
-            const int r0 = rg();
-            const double sg = prim[p_sigma()], dsg = prim[p_dsig()];
+            const int r0 = K * RS, c0 = K * CS, p0 = K * PS;
+            const double dsg = prim[p0 + 1];
             double rxs = w_time + acc_sig;
-            // sigma >= 0.001
-            rz[r0] = s[r0] - (sg - 0.001);
+            rz[r0] = s[r0] - (sg - 0.001);                          // sigma >= 0.001   (SCProblem.cpp:34)
             rxs -= z[r0];
             if (!(s[r0] > 0.) || !(z[r0] > 0.)) bad = 1;
             wb[r0] = identity ? 1. : z[r0] / s[r0]; lam[r0] = identity ? 1. : sqrt(s[r0] * z[r0]);
-            // ((1+dsg)/2 ; (1-dsg)/2 ; sigma - sigbar)
-            rz[r0 + 1] = s[r0 + 1] - (0.5 + 0.5 * dsg);
+            rz[r0 + 1] = s[r0 + 1] - (0.5 + 0.5 * dsg);            // ((1+dsg)/2 ; (1-dsg)/2 ; sigma - sigbar)   (:92-96)
             rz[r0 + 2] = s[r0 + 2] - (0.5 - 0.5 * dsg);
             rz[r0 + 3] = s[r0 + 3] - (sg - sigbar);
             rxs -= z[r0 + 3];
-            rx[p_dsig()] = w_trs - 0.5 * z[r0 + 1] + 0.5 * z[r0 + 2];
-            rx[p_sigma()] = rxs;
-            if (identity) { ce[K * NCN] = 1.; for (int i = 0; i < 3; i++) { wb[r0 + 1 + i] = i == 0; lam[r0 + 1 + i] = i == 0; } }
-            else if (!soc_scale(s + r0 + 1, z + r0 + 1, 3, wb + r0 + 1, ce[K * NCN], lam + r0 + 1)) bad = 1;
+            rx[p0 + 1] = w_trs - 0.5 * z[r0 + 1] + 0.5 * z[r0 + 2];
+            rx[p0] = rxs;
+            if (identity) { ce[c0] = 1.; for (int i = 0; i < 3; i++) { wb[r0 + 1 + i] = i == 0; lam[r0 + 1 + i] = i == 0; } }
+            else if (!soc::scale(s + r0 + 1, z + r0 + 1, 3, wb + r0 + 1, ce[c0], lam + r0 + 1)) bad = 1;
             for (int r = 0; r < 4; r++) { gap += s[r0 + r] * z[r0 + r]; rz2 += rz[r0 + r] * rz[r0 + r]; zrz += z[r0 + r] * rz[r0 + r]; }
             pcost += w_time * sg + w_trs * dsg;
             h2 += 0.001 * 0.001 + 0.5 + sigbar * sigbar;
+            rx2 += rx[p0] * rx[p0] + rx[p0 + 1] * rx[p0 + 1];
+            xrx += sg * rx[p0] + dsg * rx[p0 + 1];
         }
         warp_sync();
-        // ---- dual residual norm over free variables
-        double rx2 = 0, xrx = 0;
-        FOR_LANE(e, n_prim(K)) {
-            bool fx = false;
-            if (e < K * PN) { const int k = e / PN, i = e - k * PN; fx = i < NB && fixed(k, i); }
-            if (fx) rx[e] = 0.;
-            rx2 += rx[e] * rx[e]; xrx += prim[e] * rx[e];
-        }
         nm.gap = warp_sum(gap); nm.rz2 = warp_sum(rz2); nm.pcost = warp_sum(pcost); nm.zrz = warp_sum(zrz);
         nm.rx2 = warp_sum(rx2); nm.xrx = warp_sum(xrx); nm.h2 = warp_sum(h2); nm.bad = warp_or(bad);
     }
@@ -331,21 +434,21 @@ struct Ipm {
     // =============================================================================================================
     //  Phase F : assemble the reduced Hessian stage by stage and factor it (block-tridiagonal Cholesky + border)
     // =============================================================================================================
-    // model-cone part of H_kk as rank-1 terms + diagonals in shared memory (lanes over cones)
-    SCPP_HD void build_model_terms(int k, double *alpha)
+    SCPP_HD void build_model_terms(int k, const double *WB, const double *CE, double *alpha)
     {
-        double *rk = sm_rk(), *dg = sm_rk() + NRK * NB;
+        double *rk = sm + W_RK, *dg = rk + NRK * NB;
         FOR_LANE(e, 2 * NRK * NB) rk[e] = 0.;
         warp_sync();
-        const int r0 = rn(k);
         FOR_LANE(c, NRK) {
             double *a = rk + c * NB, *d = dg + c * NB;
             if (c < NCONE) {
                 const int o = NLP + M::cone_off(c), dim = M::cone_dim(c);
-                const double e2i = ce[k * NCN + c];
+                const double e2i = CE[c];
+#pragma unroll 1
                 for (int r = 0; r < dim; r++) {
                     const RowDesc rd = M::row(o + r);
-                    const double wh = (r == 0) ? wb[r0 + o] : -wb[r0 + o + r];
+                    const double wh = (r == 0) ? WB[o] : -WB[o + r];
+#pragma unroll 1
                     for (int j = 0; j < rd.n; j++) {
                         const double cf = coef(rd, j, k);
                         a[rd.idx[j]] += wh * cf;
@@ -355,9 +458,10 @@ struct Ipm {
                 alpha[c] = 2. * e2i;
             } else {   // LP rows: single-entry rows go to the diagonal, the multi-entry row is a rank-1 term
                 double al = 0.;
+#pragma unroll 1
                 for (int r = 0; r < NLP; r++) {
                     const RowDesc rd = M::row(r);
-                    const double dv = wb[r0 + r];
+                    const double dv = WB[r];
                     if (rd.n == 1) { const double cf = coef(rd, 0, k); d[rd.idx[0]] += dv * cf * cf; }
                     else { for (int j = 0; j < rd.n; j++) a[rd.idx[j]] = coef(rd, j, k); al = dv; }
                 }
@@ -369,31 +473,39 @@ struct Ipm {
 
     SCPP_HD bool phase_factor()
     {
-        double *H = sm_H(), *O = sm_O(), *Lp = sm_Lp(), *Li = sm_Li(), *Hn = sm_Hn();
-        double *bk = sm_v(0), *bn = sm_v(1), *lk = sm_v(2), *lprev = sm_v(3), *wt = sm_v(4);   // NB-vectors
-        double *Dt = sm_x(1);
-        double *alpha = sm_sc();
-        double corner = 0.;       // lane-partial accumulation of H_sigma,sigma
+        double *H = sm + W_MAT, *O = H + BLK, *Hn = O + BLK, *Lp = sm + W_LP;
+        double *F = facw();                 // Linv | Lnext | l | f   (the record written for this stage)
+        double *Li = F, *Ln = F + OFF_LN, *lk = F + OFF_L;
+        double *WB = row(0), *CE = sc() + 8, *alpha = sc();
+        double *bk = vec(0), *bn = vec(1), *lprev = vec(2);
+        double *Dt = xv(1);
+        double corner = 0.;
         int bad = 0;
         FOR_LANE(e, BLK) { Hn[e] = 0.; Lp[e] = 0.; }
         FOR_LANE(j, NB) { bn[j] = 0.; lprev[j] = 0.; }
         warp_sync();
+#pragma unroll 1
         for (int k = 0; k < K; k++) {
-            const int r0 = rn(k);
-            build_model_terms(k, alpha);
-            // ---- node part of H_kk, trust region included, plus the carry from interval k-1
+            const bool hasint = k < K - 1;
+            if (hasint) ld_dd(k);
+            ld(WB, wb + k * RS, RS); ld(CE, ce + k * CS, CS);
+            ld_wait();
+            build_model_terms(k, WB, CE, alpha);
+            // ---- node part of H_kk (trust region with delta eliminated) + carry from interval k-1
             {
-                const double *rk = sm_rk(), *dg = sm_rk() + NRK * NB;
-                const double *wt_ = wb + r0 + TRO;           // wbar of the trust-region cone (global memory)
-                const double e2i = ce[k * NCN + NCONE];
-                const double w0 = wt_[0];
-                const double kap = e2i * (2. * w0 * w0 - 1.);   // M_00
-                // p1 = -M e0 (tail) = e2i * 2 w0 w1  ;  Mtilde = e2i (I + 2 w1 w1') - p1 p1'/kap
+                const double *rk = sm + W_RK, *dg = rk + NRK * NB;
+                const double *wt_ = WB + TRO;
+                const double e2i = CE[NCONE], w0 = wt_[0];
+                const double kap = e2i * (2. * w0 * w0 - 1.);
                 FOR_LANE(e, BLK) {
                     const int i = e / NB, j = e - i * NB;
                     double v = Hn[e];
+#pragma unroll
                     for (int c = 0; c < NRK; c++) v += alpha[c] * rk[c * NB + i] * rk[c * NB + j];
-                    if (i == j) for (int c = 0; c < NRK; c++) v += dg[c * NB + i];
+                    if (i == j) {
+#pragma unroll
+                        for (int c = 0; c < NRK; c++) v += dg[c * NB + i];
+                    }
                     const double wi = wt_[1 + i], wj = wt_[1 + j];
                     v += e2i * ((i == j ? 1. : 0.) + 2. * wi * wj) - (e2i * 2. * w0 * wi) * (e2i * 2. * w0 * wj) / kap;
                     H[e] = v;
@@ -402,35 +514,46 @@ struct Ipm {
             }
             warp_sync();
             // ---- interval k: H_kk += A~' D A~ ; O = [-D A~ ; C' D A~] ; Hn = [[D, -D C],[-C' D, C' D C]] ; borders
-            if (k < K - 1) {
-                stage_dd(k);
-                const double *t = sm_dd();
-                const int q0 = ri(k);
-                FOR_LANE(i, NX) { const double dm = wb[q0 + i], dp = wb[q0 + NX + i]; Dt[i] = 4. * dm * dp / (dm + dp); }
+            if (hasint) {
+                const double *t = tile();
+                FOR_LANE(i, NX) { const double dm = WB[MN + i], dp = WB[MN + NX + i]; Dt[i] = 4. * dm * dp / (dm + dp); }
                 warp_sync();
                 FOR_LANE(e, BLK) {
                     const int a = e / NB, b = e - a * NB;
                     double v = 0;
+#pragma unroll 2
                     for (int i = 0; i < NX; i++) v += t[i * NCP + a] * Dt[i] * t[i * NCP + b];
                     H[e] += v;
-                    // O[a][b]: row a of node k+1, column b of node k
                     double o;
                     if (a < NX) o = -Dt[a] * t[a * NCP + b];
-                    else { o = 0; for (int i = 0; i < NX; i++) o += t[i * NCP + NB + (a - NX)] * Dt[i] * t[i * NCP + b]; }
+                    else {
+                        o = 0;
+#pragma unroll 2
+                        for (int i = 0; i < NX; i++) o += t[i * NCP + NB + (a - NX)] * Dt[i] * t[i * NCP + b];
+                    }
                     O[e] = o;
                     double hn;
                     if (a < NX && b < NX) hn = (a == b) ? Dt[a] : 0.;
                     else if (a < NX) hn = -Dt[a] * t[a * NCP + NB + (b - NX)];
                     else if (b < NX) hn = -Dt[b] * t[b * NCP + NB + (a - NX)];
-                    else { hn = 0; for (int i = 0; i < NX; i++) hn += t[i * NCP + NB + (a - NX)] * Dt[i] * t[i * NCP + NB + (b - NX)]; }
+                    else {
+                        hn = 0;
+#pragma unroll 2
+                        for (int i = 0; i < NX; i++) hn += t[i * NCP + NB + (a - NX)] * Dt[i] * t[i * NCP + NB + (b - NX)];
+                    }
                     Hn[e] = hn;
                 }
                 FOR_LANE(j, NB) {
                     double v = 0, vn;
+#pragma unroll 2
                     for (int i = 0; i < NX; i++) v += t[i * NCP + j] * Dt[i] * t[i * NCP + NB + NU];
                     bk[j] += v;
                     if (j < NX) vn = -Dt[j] * t[j * NCP + NB + NU];
-                    else { vn = 0; for (int i = 0; i < NX; i++) vn += t[i * NCP + NB + (j - NX)] * Dt[i] * t[i * NCP + NB + NU]; }
+                    else {
+                        vn = 0;
+#pragma unroll 2
+                        for (int i = 0; i < NX; i++) vn += t[i * NCP + NB + (j - NX)] * Dt[i] * t[i * NCP + NB + NU];
+                    }
                     bn[j] = vn;
                 }
                 FOR_LANE(i, NX) { const double sv = t[i * NCP + NB + NU]; corner += Dt[i] * sv * sv; }
@@ -440,7 +563,7 @@ struct Ipm {
             warp_sync();
             // ---- pinned variables: identity rows/columns
             {
-                const uint32_t mk = fixm[k], mn = (k < K - 1) ? fixm[k + 1] : 0u;
+                const uint32_t mk = fixm[k], mn = hasint ? fixm[k + 1] : 0u;
                 FOR_LANE(e, BLK) {
                     const int a = e / NB, b = e - a * NB;
                     if (((mk >> a) & 1u) || ((mk >> b) & 1u)) H[e] = (a == b) ? 1. : 0.;
@@ -453,20 +576,30 @@ struct Ipm {
             if (k > 0) {
                 FOR_LANE(e, BLK) {
                     const int a = e / NB, b = e - a * NB;
-                    if (b <= a) { double v = 0; for (int c = 0; c < NB; c++) v += Lp[a * NB + c] * Lp[b * NB + c]; H[e] -= v; }
+                    if (b <= a) {
+                        double v = 0;
+#pragma unroll 2
+                        for (int c = 0; c < NB; c++) v += Lp[a * NB + c] * Lp[b * NB + c];
+                        H[e] -= v;
+                    }
                 }
-                FOR_LANE(j, NB) { double v = 0; for (int c = 0; c < NB; c++) v += Lp[j * NB + c] * lprev[c]; bk[j] -= v; }
+                FOR_LANE(j, NB) {
+                    double v = 0;
+#pragma unroll 2
+                    for (int c = 0; c < NB; c++) v += Lp[j * NB + c] * lprev[c];
+                    bk[j] -= v;
+                }
             }
             warp_sync();
             // ---- Cholesky of H (lower, in place), column by column
+#pragma unroll 1
             for (int j = 0; j < NB; j++) {
                 const double djj = H[j * NB + j];
                 if (!(djj > 0.)) bad = 1;
                 const double inv = 1. / sqrt(djj > 0. ? djj : 1.);
                 warp_sync();
-                FOR_LANE(i, NB) if (i >= j) H[i * NB + j] *= inv;   // L_jj = sqrt, L_ij = H_ij / L_jj
+                FOR_LANE(i, NB) if (i >= j) H[i * NB + j] *= inv;
                 warp_sync();
-                // trailing update of the lower triangle
                 const int rem = NB - 1 - j;
                 FOR_LANE(e, rem * rem) {
                     const int a = j + 1 + e / rem, b = j + 1 + e % rem;
@@ -476,274 +609,397 @@ struct Ipm {
             }
             // ---- Linv = L^-1 (lower): lane per column
             FOR_LANE(c, NB) {
+#pragma unroll 1
                 for (int i = 0; i < NB; i++) {
                     if (i < c) { Li[i * NB + c] = 0.; continue; }
                     double v = (i == c) ? 1. : 0.;
+#pragma unroll 1
                     for (int q = c; q < i; q++) v -= H[i * NB + q] * Li[q * NB + c];
                     Li[i * NB + c] = v / H[i * NB + i];
                 }
             }
             warp_sync();
-            // ---- L_{k+1,k} = O L^-T = O Linv' ;  l_k = Linv bk ; corner -= l_k' l_k
+            // ---- L_{k+1,k} = O Linv' ;  l_k = Linv bk ; corner -= l_k' l_k
             FOR_LANE(e, BLK) {
                 const int a = e / NB, b = e - a * NB;
                 double v = 0;
+#pragma unroll 1
                 for (int c = 0; c <= b; c++) v += O[a * NB + c] * Li[b * NB + c];
-                Lp[e] = v;
+                Ln[e] = v;
             }
-            FOR_LANE(j, NB) { double v = 0; for (int c = 0; c <= j; c++) v += Li[j * NB + c] * bk[c]; lk[j] = v; wt[j] = v; corner -= v * v; }
+            FOR_LANE(j, NB) {
+                double v = 0;
+#pragma unroll 1
+                for (int c = 0; c <= j; c++) v += Li[j * NB + c] * bk[c];
+                lk[j] = v; corner -= v * v;
+            }
             warp_sync();
-            // ---- store
-            double *f = fac + (size_t)k * FACK;
-            FOR_LANE(e, BLK) { f[e] = Li[e]; f[BLK + e] = Lp[e]; }
-            FOR_LANE(j, NB) { f[2 * BLK + j] = lk[j]; lprev[j] = wt[j]; }
+            st(fac + (size_t)k * FS, F, OFF_F);
+            FOR_LANE(e, BLK) Lp[e] = Ln[e];
+            FOR_LANE(j, NB) lprev[j] = lk[j];
             warp_sync();
         }
         corner = warp_sum(corner);
-        // ---- globals: sigma >= 0.001 row and the sigma trust-region cone with delta_sigma eliminated
-        {
-            const int r0 = rg();
+        {   // globals: sigma >= 0.001 row and the sigma trust-region cone with delta_sigma eliminated
+            const int r0 = K * RS;
             const double d = wb[r0];
-            const double *w = wb + r0 + 1;
-            const double e2i = ce[K * NCN];
-            double g[3] = {-0.5, 0.5, 0.}, p[3];
-            soc_M(w, e2i, g, 3, p);
+            double w3[3] = {wb[r0 + 1], wb[r0 + 2], wb[r0 + 3]};
+            const double e2i = ce[K * CS];
+            double g[3] = {-0.5, 0.5, 0.}, p[3], e2[3] = {0., 0., 1.}, m2[3];
+            soc::Mv(w3, e2i, g, 3, p);
             const double kap = g[0] * p[0] + g[1] * p[1];
-            double e2[3] = {0., 0., 1.}, m2[3];
-            soc_M(w, e2i, e2, 3, m2);
+            soc::Mv(w3, e2i, e2, 3, m2);
             corner += d + (m2[2] - p[2] * p[2] / kap);
         }
         if (!(corner > 0.)) bad = 1;
-        if (lane_id() == 0) sm_sc()[16] = sqrt(corner > 0. ? corner : 1.);
-        warp_sync();
+        l_ss = sqrt(corner > 0. ? corner : 1.);
         return !warp_or(bad);
     }
 
     // =============================================================================================================
-    //  Phase S : solve the Newton system for one right-hand side.
-    //     in : dprim = rx-like vector (per primal variable), ds = rz-like vector (per cone row)
-    //     out: dprim = primal direction (xi, delta, sigma, delta_sigma, t), dz = dual direction
+    //  Phase S : solve the Newton system  G'dz = rxv ,  G dx - W^2 dz = rzv  with the local variables eliminated.
+    //     mode 0: rxv = dprim (array), rzv = ds (array)                        [starting point]
+    //     mode 1: rxv = -rx,            rzv = -rz + s                          [affine direction]
+    //     mode 2: rxv = -(1-sig) rx,    rzv = -(1-sig) rz - W (lam \ d_s),  d_s = -lam o lam - cr + sig mu e   [combined]
+    //  forward sweep: right-hand side + forward substitution; backward sweep: back substitution + recovery of the
+    //  local variables, dz and ds = rzs*rz - G dx, the scaled step lengths (tmax) and, for mode 1, cr = ds~ o dz~.
     // =============================================================================================================
-    //     rzs: on exit ds = rzs * rz - G dx  (the primal Newton equation; keeps the primal residual contracting exactly)
-    SCPP_HD void phase_solve(double rzs)
+    SCPP_HD void gen_rhs(int mode, bool hasint, double csig, double sigmu, double *RZV, double *RXV,
+                         const double *S_, const double *RZ, const double *LM, const double *CR, const double *WB, const double *CE, const double *RXW)
     {
-        const double l_ss = sm_sc()[16];
-        // ---- S1a: nodes (lane per node): gy_k = rx_k + sum_c G' v_c
-        for (int k = lane_id(); k < K; k += LANES) {
-            double g[NB];
-            for (int i = 0; i < NB; i++) g[i] = dprim[pn(k) + i];
-            const int r0 = rn(k);
-            for (int r = 0; r < NLP; r++) {
-                const RowDesc rd = M::row(r);
-                const double v = wb[r0 + r] * ds[r0 + r];
-                for (int j = 0; j < rd.n; j++) g[rd.idx[j]] += coef(rd, j, k) * v;
+        if (mode == 1) {
+            FOR_LANE(e, RS) RZV[e] = -RZ[e] + S_[e];
+            FOR_LANE(e, PS) RXV[e] = -RXW[e];
+        } else {
+            FOR_LANE(e, PS) RXV[e] = -csig * RXW[e];
+            FOR_LANE(tk, NTASK) {
+                int type, o, d, ci;
+                task(tk, type, o, d, ci);
+                if (type == 1) {
+                    double t1[1 + NB];
+                    soc::jprod(LM + o, LM + o, d, t1);
+#pragma unroll 1
+                    for (int i = 0; i < d; i++) t1[i] = -t1[i] - CR[o + i];
+                    t1[0] += sigmu;
+                    soc::jdiv(LM + o, t1, d, t1);
+                    soc::Wv(WB + o, CE[ci], t1, d, t1, false);
+#pragma unroll 1
+                    for (int i = 0; i < d; i++) RZV[o + i] = -csig * RZ[o + i] - t1[i];
+                } else {
+                    const int reps = (type == 2) ? 2 : 1;
+                    if (type == 2 && !hasint) { RZV[o] = 0.; RZV[o + NX] = 0.; continue; }
+                    for (int q = 0; q < reps; q++) {
+                        const int oo = o + q * NX;
+                        const double wv = sqrt(1. / WB[oo]);
+                        const double t1 = (-LM[oo] * LM[oo] - CR[oo] + sigmu) / LM[oo];
+                        RZV[oo] = -csig * RZ[oo] - wv * t1;
+                    }
+                }
             }
-            for (int c = 0; c < NCONE; c++) {
-                const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
-                double v[M::MAXDIM];
-                soc_M(wb + r0 + o, ce[k * NCN + c], ds + r0 + o, d, v);
-                for (int r = 0; r < d; r++) { const RowDesc rd = M::row(o + r); for (int j = 0; j < rd.n; j++) g[rd.idx[j]] += coef(rd, j, k) * v[r]; }
-            }
-            {   // trust region with delta eliminated: v = M rz - p (p'rz + rx_delta)/kap , p = -M e0
-                const double *w = wb + r0 + TRO, *rzv = ds + r0 + TRO;
-                const double e2i = ce[k * NCN + NCONE];
-                double v[1 + NB], p[1 + NB], e0[1 + NB];
-                for (int i = 0; i <= NB; i++) e0[i] = (i == 0) ? -1. : 0.;
-                soc_M(w, e2i, rzv, 1 + NB, v);
-                soc_M(w, e2i, e0, 1 + NB, p);
-                const double kap = -p[0];
-                double prz = 0;
-                for (int i = 0; i <= NB; i++) prz += p[i] * rzv[i];
-                const double rho = (prz + dprim[pn(k) + NB]) / kap;
-                for (int i = 0; i < NB; i++) g[i] += v[1 + i] - p[1 + i] * rho;
-            }
-            for (int i = 0; i < NB; i++) gy[k * NB + i] = g[i];
         }
-        warp_sync();
-        // ---- S1b: intervals
-        double gsig = 0;
-        for (int k = 0; k < K - 1; k++) {
-            stage_dd(k);
-            const int q0 = ri(k);
-            double *w = sm_x(0);
-            FOR_LANE(i, NX) {
-                const double dm = wb[q0 + i], dp = wb[q0 + NX + i], rm = ds[q0 + i], rp = ds[q0 + NX + i];
-                const double rho = (-(dm * rm + dp * rp) + dprim[p_t(k) + i]) / (dm + dp);
-                w[i] = dm * (rm + rho) - dp * (rp + rho);
+    }
+
+    SCPP_HD void phase_solve(int mode, double csig, double sigmu, double rzs, double &tmax_out)
+    {
+        double *WB = row(0), *RZV = row(1), *V = row(2), *RZ = row(3), *LM = row(4), *CR = row(5), *S_ = row(6), *DZ = row(7);
+        double *RXV = pw(0), *RXW = pw(1), *DP = pw(2), *CE = sc() + 8;
+        double *F = facw();
+        double *carry = vec(0), *g = vec(1), *tmp = vec(2), *fprev = vec(3), *Lp = sm + W_LP;   // Lp: L_{k,k-1}
+        double *w = xv(0);
+        const int r0g = K * RS, p0g = K * PS;
+        // ---------------- forward sweep ----------------
+        double gsig = 0, ldot = 0;
+        FOR_LANE(j, NB) { carry[j] = 0.; fprev[j] = 0.; }
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            const bool hasint = k < K - 1;
+            if (hasint) ld_dd(k);
+            ld(F, fac + (size_t)k * FS, OFF_F);
+            ld(WB, wb + k * RS, RS); ld(CE, ce + k * CS, CS);
+            if (mode == 0) { ld(RZV, ds + k * RS, RS); ld(RXV, dprim + k * PS, PS); }
+            else {
+                ld(RZ, rz + k * RS, RS); ld(RXW, rx + k * PS, PS);
+                if (mode == 1) ld(S_, s + k * RS, RS);
+                else { ld(LM, lam + k * RS, RS); ld(CR, cr + k * RS, RS); }
+            }
+            ld_wait();
+            if (mode != 0) { gen_rhs(mode, hasint, csig, sigmu, RZV, RXV, S_, RZ, LM, CR, WB, CE, RXW); warp_sync(); }
+            // ---- v_c = Mtilde rzv per cone; pairs produce w_i
+            FOR_LANE(tk, NTASK) {
+                int type, o, d, ci;
+                task(tk, type, o, d, ci);
+                if (type == 1) {
+                    soc::Mv(WB + o, CE[ci], RZV + o, d, V + o);
+                    if (ci == NCONE) {      // trust region: v -= p (p'rzv + rx_delta)/kap ,  p = -M e0
+                        double p[1 + NB], e0[1 + NB];
+#pragma unroll 1
+                        for (int i = 0; i <= NB; i++) e0[i] = (i == 0) ? -1. : 0.;
+                        soc::Mv(WB + o, CE[ci], e0, d, p);
+                        double prz = 0;
+#pragma unroll 1
+                        for (int i = 0; i <= NB; i++) prz += p[i] * RZV[o + i];
+                        const double rho = (prz + RXV[NB]) / (-p[0]);
+#pragma unroll 1
+                        for (int i = 0; i <= NB; i++) V[o + i] -= p[i] * rho;
+                    }
+                } else if (type == 0) V[o] = WB[o] * RZV[o];
+                else if (hasint) {
+                    const int i = o - MN;
+                    const double dm = WB[o], dp = WB[o + NX], rm = RZV[o], rp = RZV[o + NX];
+                    const double rho = (-(dm * rm + dp * rp) + RXV[PN + i]) / (dm + dp);
+                    w[i] = dm * (rm + rho) - dp * (rp + rho);
+                }
             }
             warp_sync();
-            dyn_JT(k, w, gy + k * NB, gy + (k + 1) * NB, gsig);
+            FOR_LANE(j, NB) g[j] = fixed(k, j) ? 0. : RXV[j] + carry[j] + V[TRO + 1 + j] + model_GT(j, k, V);
+            warp_sync();
+            if (hasint) gsig += dyn_JT(w, g, carry);
+            warp_sync();
+            // forward substitution: f_k = Linv (g_k - L_{k,k-1} f_{k-1})
+            FOR_LANE(j, NB) {
+                double v = fixed(k, j) ? 0. : g[j];
+                if (k > 0) {
+#pragma unroll 2
+                    for (int c = 0; c < NB; c++) v -= Lp[j * NB + c] * fprev[c];
+                }
+                tmp[j] = v;
+            }
+            warp_sync();
+            FOR_LANE(j, NB) {
+                double v = 0;
+#pragma unroll 1
+                for (int c = 0; c <= j; c++) v += F[j * NB + c] * tmp[c];
+                F[OFF_F + j] = v;
+                ldot += F[OFF_L + j] * v;
+            }
+            warp_sync();
+            FOR_LANE(j, NB) { fprev[j] = F[OFF_F + j]; fac[(size_t)k * FS + OFF_F + j] = F[OFF_F + j]; }
+            FOR_LANE(e, BLK) Lp[e] = F[OFF_LN + e];
+            if (mode != 0) st(ds + k * RS, RZV, RS);
             warp_sync();
         }
         gsig = warp_sum(gsig);
-        // ---- S1c: globals (every lane computes the same scalars)
-        double kap_s, p_s[3];
+        // ---- globals: rhs and local elimination for the sigma rows (every lane computes the same scalars)
+        double kap_s, p_s[3], rzg[4], rxg[2];
         {
-            const int r0 = rg();
-            const double *w = wb + r0 + 1, *rzv = ds + r0 + 1;
-            const double e2i = ce[K * NCN];
+            double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
+            const double e2i = ce[K * CS], d0 = wb[r0g];
+            if (mode == 0) { for (int i = 0; i < 4; i++) rzg[i] = ds[r0g + i]; rxg[0] = dprim[p0g]; rxg[1] = dprim[p0g + 1]; }
+            else if (mode == 1) { for (int i = 0; i < 4; i++) rzg[i] = -rz[r0g + i] + s[r0g + i]; rxg[0] = -rx[p0g]; rxg[1] = -rx[p0g + 1]; }
+            else {
+                const double l0 = lam[r0g];
+                rzg[0] = -csig * rz[r0g] - sqrt(1. / d0) * ((-l0 * l0 - cr[r0g] + sigmu) / l0);
+                double lm3[3] = {lam[r0g + 1], lam[r0g + 2], lam[r0g + 3]}, t1[3];
+                soc::jprod(lm3, lm3, 3, t1);
+                for (int i = 0; i < 3; i++) t1[i] = -t1[i] - cr[r0g + 1 + i];
+                t1[0] += sigmu;
+                soc::jdiv(lm3, t1, 3, t1);
+                soc::Wv(w3, e2i, t1, 3, t1, false);
+                for (int i = 0; i < 3; i++) rzg[1 + i] = -csig * rz[r0g + 1 + i] - t1[i];
+                rxg[0] = -csig * rx[p0g]; rxg[1] = -csig * rx[p0g + 1];
+            }
             double g3[3] = {-0.5, 0.5, 0.}, v[3];
-            soc_M(w, e2i, g3, 3, p_s);
+            soc::Mv(w3, e2i, g3, 3, p_s);
             kap_s = g3[0] * p_s[0] + g3[1] * p_s[1];
-            soc_M(w, e2i, rzv, 3, v);
-            const double prz = p_s[0] * rzv[0] + p_s[1] * rzv[1] + p_s[2] * rzv[2];
-            const double rho = (prz + dprim[p_dsig()]) / kap_s;
-            gsig += dprim[p_sigma()] - wb[r0] * ds[r0] - (v[2] - p_s[2] * rho);
-        }
-        // ---- S2: forward sweep  f_k = Linv_k (g_k - L_{k,k-1} f_{k-1}) ; pinned entries are zero
-        double *fprev = sm_v(5), *tmp = sm_v(6);
-        double ldot = 0.;      // lane-partial of sum_k l_k' f_k
-        for (int k = 0; k < K; k++) {
-            const double *f = fac + (size_t)k * FACK;
-            const double *fm = fac + (size_t)(k - 1) * FACK;
-            FOR_LANE(j, NB) {
-                double v = fixed(k, j) ? 0. : gy[k * NB + j];
-                if (k > 0) for (int c = 0; c < NB; c++) v -= fm[BLK + j * NB + c] * fprev[c];
-                tmp[j] = v;
-            }
-            warp_sync();
-            FOR_LANE(j, NB) {
-                double v = 0;
-                for (int c = 0; c <= j; c++) v += f[j * NB + c] * tmp[c];
-                gy[k * NB + j] = v;
-                ldot += f[2 * BLK + j] * v;
-            }
-            warp_sync();
-            FOR_LANE(j, NB) fprev[j] = gy[k * NB + j];
-            warp_sync();
+            soc::Mv(w3, e2i, rzg + 1, 3, v);
+            const double prz = p_s[0] * rzg[1] + p_s[1] * rzg[2] + p_s[2] * rzg[3];
+            const double rho = (prz + rxg[1]) / kap_s;
+            gsig += rxg[0] - d0 * rzg[0] - (v[2] - p_s[2] * rho);
         }
         const double fsig = (gsig - warp_sum(ldot)) / l_ss;
         const double ysig = fsig / l_ss;
-        // ---- S3: backward sweep  y_k = Linv_k' (f_k - L_{k+1,k}' y_{k+1} - l_k y_sigma)
-        double *ynext = sm_v(5);
+        warp_sync();
+        // ---------------- backward sweep ----------------
+        double tmax = 0;
+        double *ynext = vec(3), *yk = vec(4), *DS = RZV;
+        double *XN = pw(3);                 // d xi_{k+1}
+        FOR_LANE(j, NB) ynext[j] = 0.;
+#pragma unroll 1
         for (int k = K - 1; k >= 0; k--) {
-            const double *f = fac + (size_t)k * FACK;
+            const bool hasint = k < K - 1;
+            if (hasint) ld_dd(k);
+            ld(F, fac + (size_t)k * FS, FS);
+            ld(WB, wb + k * RS, RS); ld(CE, ce + k * CS, CS); ld(RZV, ds + k * RS, RS);
+            if (mode == 0) ld(RXV, dprim + k * PS, PS);
+            else { ld(RXW, rx + k * PS, PS); ld(RZ, rz + k * RS, RS); ld(LM, lam + k * RS, RS); }
+            ld_wait();
+            if (mode != 0) { FOR_LANE(e, PS) RXV[e] = (mode == 1 ? -1. : -csig) * RXW[e]; }
+            // back substitution: y_k = Linv' (f_k - L_{k+1,k}' y_{k+1} - l_k y_sigma)
             FOR_LANE(j, NB) {
-                double v = gy[k * NB + j] - f[2 * BLK + j] * ysig;
-                if (k < K - 1) for (int c = 0; c < NB; c++) v -= f[BLK + c * NB + j] * ynext[c];
+                double v = F[OFF_F + j] - F[OFF_L + j] * ysig;
+                if (hasint) {
+#pragma unroll 2
+                    for (int c = 0; c < NB; c++) v -= F[OFF_LN + c * NB + j] * ynext[c];
+                }
                 tmp[j] = v;
+                XN[j] = ynext[j];
             }
             warp_sync();
             FOR_LANE(j, NB) {
                 double v = 0;
-                for (int c = j; c < NB; c++) v += f[c * NB + j] * tmp[c];
-                gy[k * NB + j] = fixed(k, j) ? 0. : v;
+#pragma unroll 1
+                for (int c = j; c < NB; c++) v += F[c * NB + j] * tmp[c];
+                yk[j] = fixed(k, j) ? 0. : v;
             }
             warp_sync();
-            FOR_LANE(j, NB) ynext[j] = gy[k * NB + j];
-            warp_sync();
-        }
-        if (lane_id() == 0) gy[K * NB] = ysig;
-        warp_sync();
-        // ---- S4a: recovery at the nodes
-        for (int k = lane_id(); k < K; k += LANES) {
-            double dx[NB];
-            for (int i = 0; i < NB; i++) dx[i] = gy[k * NB + i];
-            const int r0 = rn(k);
-            for (int r = 0; r < NLP; r++) {
-                const RowDesc rd = M::row(r);
-                double gdx = 0;
-                for (int j = 0; j < rd.n; j++) gdx += coef(rd, j, k) * dx[rd.idx[j]];
-                dz[r0 + r] = wb[r0 + r] * (gdx - ds[r0 + r]);
-                ds[r0 + r] = rzs * rz[r0 + r] - gdx;
-            }
-            for (int c = 0; c < NCONE; c++) {
-                const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
-                double q[M::MAXDIM];
-                for (int r = 0; r < d; r++) {
-                    const RowDesc rd = M::row(o + r);
-                    double gdx = 0;
-                    for (int j = 0; j < rd.n; j++) gdx += coef(rd, j, k) * dx[rd.idx[j]];
-                    q[r] = gdx - ds[r0 + o + r];
-                    ds[r0 + o + r] = rzs * rz[r0 + o + r] - gdx;
+            // ---- recovery per cone: q = G dy - rzv ; local ; dz = M q + p dl ; ds = rzs rz - G dx ; scaled steps
+            FOR_LANE(tk, NTASK) {
+                int type, o, d, ci;
+                task(tk, type, o, d, ci);
+                if (type == 1) {
+                    double q[1 + NB], gdx[1 + NB];
+                    if (ci < NCONE) {
+#pragma unroll 1
+                        for (int r = 0; r < d; r++) { gdx[r] = model_G(o + r, k, yk); q[r] = gdx[r] - RZV[o + r]; }
+                        soc::Mv(WB + o, CE[ci], q, d, DZ + o);
+                    } else {
+                        double p[1 + NB], e0[1 + NB];
+                        q[0] = -RZV[o];
+#pragma unroll 1
+                        for (int i = 0; i < NB; i++) { q[1 + i] = yk[i] - RZV[o + 1 + i]; gdx[1 + i] = yk[i]; }
+#pragma unroll 1
+                        for (int i = 0; i <= NB; i++) e0[i] = (i == 0) ? -1. : 0.;
+                        soc::Mv(WB + o, CE[ci], e0, d, p);
+                        double pq = 0;
+#pragma unroll 1
+                        for (int i = 0; i <= NB; i++) pq += p[i] * q[i];
+                        const double ddl = (RXV[NB] - pq) / (-p[0]);
+                        soc::Mv(WB + o, CE[ci], q, d, DZ + o);
+#pragma unroll 1
+                        for (int i = 0; i <= NB; i++) DZ[o + i] += p[i] * ddl;
+                        gdx[0] = -ddl;
+                        DP[NB] = ddl;
+                    }
+                    if (mode != 0) {
+#pragma unroll 1
+                        for (int r = 0; r < d; r++) DS[o + r] = rzs * RZ[o + r] - gdx[r];
+                        double dzt[1 + NB], dst[1 + NB];
+                        soc::Wv(WB + o, CE[ci], DZ + o, d, dzt, false);
+                        soc::Wv(WB + o, CE[ci], DS + o, d, dst, true);
+                        tmax = fmax(tmax, fmax(soc::step(LM + o, dst, d), soc::step(LM + o, dzt, d)));
+                        if (mode == 1) soc::jprod(dst, dzt, d, CR + o);
+                    }
+                } else if (type == 0) {
+                    const double gdx = model_G(o, k, yk);
+                    DZ[o] = WB[o] * (gdx - RZV[o]);
+                    if (mode != 0) {
+                        DS[o] = rzs * RZ[o] - gdx;
+                        const double wv = sqrt(1. / WB[o]);
+                        const double dzt = wv * DZ[o], dst = DS[o] / wv;
+                        tmax = fmax(tmax, fmax(-dst / LM[o], -dzt / LM[o]));
+                        if (mode == 1) CR[o] = dst * dzt;
+                    }
+                } else if (hasint) {
+                    const int i = o - MN;
+                    const double ady = dyn_row(i, yk, XN, ysig, false);
+                    const double dm = WB[o], dp = WB[o + NX];
+                    const double qm = ady - RZV[o], qp = -ady - RZV[o + NX];
+                    const double dt = (RXV[PN + i] + dm * qm + dp * qp) / (dm + dp);
+                    DZ[o] = dm * (qm - dt); DZ[o + NX] = dp * (qp - dt);
+                    DP[PN + i] = dt;
+                    if (mode != 0) {
+                        DS[o] = rzs * RZ[o] - (ady - dt); DS[o + NX] = rzs * RZ[o + NX] - (-ady - dt);
+                        for (int q = 0; q < 2; q++) {
+                            const int oo = o + q * NX;
+                            const double wv = sqrt(1. / WB[oo]);
+                            const double dzt = wv * DZ[oo], dst = DS[oo] / wv;
+                            tmax = fmax(tmax, fmax(-dst / LM[oo], -dzt / LM[oo]));
+                            if (mode == 1) CR[oo] = dst * dzt;
+                        }
+                    }
+                } else {
+                    const int i = o - MN;
+                    DP[PN + i] = 0.; DZ[o] = 0.; DZ[o + NX] = 0.;
+                    if (mode != 0) { DS[o] = 0.; DS[o + NX] = 0.; if (mode == 1) { CR[o] = 0.; CR[o + NX] = 0.; } }
                 }
-                soc_M(wb + r0 + o, ce[k * NCN + c], q, d, dz + r0 + o);
             }
-            {
-                const double *w = wb + r0 + TRO;
-                const double e2i = ce[k * NCN + NCONE];
-                double q[1 + NB], p[1 + NB], e0[1 + NB], mq[1 + NB];
-                q[0] = -ds[r0 + TRO];
-                for (int i = 0; i < NB; i++) q[1 + i] = dx[i] - ds[r0 + TRO + 1 + i];
-                for (int i = 0; i <= NB; i++) e0[i] = (i == 0) ? -1. : 0.;
-                soc_M(w, e2i, e0, 1 + NB, p);
-                const double kap = -p[0];
-                double pq = 0;
-                for (int i = 0; i <= NB; i++) pq += p[i] * q[i];
-                const double ddl = (dprim[pn(k) + NB] - pq) / kap;
-                soc_M(w, e2i, q, 1 + NB, mq);
-                for (int i = 0; i <= NB; i++) dz[r0 + TRO + i] = mq[i] + p[i] * ddl;
-                ds[r0 + TRO] = rzs * rz[r0 + TRO] + ddl;
-                for (int i = 0; i < NB; i++) ds[r0 + TRO + 1 + i] = rzs * rz[r0 + TRO + 1 + i] - dx[i];
-                for (int i = 0; i < NB; i++) dprim[pn(k) + i] = dx[i];
-                dprim[pn(k) + NB] = ddl;
-            }
-        }
-        warp_sync();
-        // ---- S4b: recovery on the intervals
-        for (int k = 0; k < K - 1; k++) {
-            stage_dd(k);
-            const int q0 = ri(k);
-            FOR_LANE(i, NX) {
-                // a' dy = J dy  (no constant): uses dprim node parts and sigma from gy
-                const double *t = sm_dd() + i * NCP;
-                const double *xk = dprim + pn(k), *xn = dprim + pn(k + 1);
-                double ady = xn[i];
-                for (int j = 0; j < NB; j++) ady -= t[j] * xk[j];
-                for (int j = 0; j < NU; j++) ady -= t[NB + j] * xn[NX + j];
-                ady -= t[NB + NU] * ysig;
-                const double dm = wb[q0 + i], dp = wb[q0 + NX + i];
-                const double qm = ady - ds[q0 + i], qp = -ady - ds[q0 + NX + i];
-                const double dt = (dprim[p_t(k) + i] + dm * qm + dp * qp) / (dm + dp);
-                dz[q0 + i] = dm * (qm - dt);
-                dz[q0 + NX + i] = dp * (qp - dt);
-                ds[q0 + i] = rzs * rz[q0 + i] - (ady - dt);
-                ds[q0 + NX + i] = rzs * rz[q0 + NX + i] - (-ady - dt);
-                dprim[p_t(k) + i] = dt;
-            }
+            FOR_LANE(j, NB) DP[j] = yk[j];
+            warp_sync();
+            st(dz + k * RS, DZ, RS); st(dprim + k * PS, DP, PN + NX);
+            if (mode != 0) { st(ds + k * RS, DS, RS); if (mode == 1) st(cr + k * RS, CR, RS); }
+            FOR_LANE(j, NB) ynext[j] = yk[j];
             warp_sync();
         }
-        // ---- S4c: globals
+        // ---- globals recovery (lane 0)
         if (lane_id() == 0) {
-            const int r0 = rg();
-            dz[r0] = wb[r0] * (-ysig - ds[r0]);
-            const double *w = wb + r0 + 1;
-            const double e2i = ce[K * NCN];
-            double q[3] = {-ds[r0 + 1], -ds[r0 + 2], -ysig - ds[r0 + 3]}, mq[3];
+            double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
+            const double e2i = ce[K * CS], d0 = wb[r0g];
+            const double dz0 = d0 * (-ysig - rzg[0]);
+            double q[3] = {-rzg[1], -rzg[2], -ysig - rzg[3]}, mq[3], dzq[3];
             const double pq = p_s[0] * q[0] + p_s[1] * q[1] + p_s[2] * q[2];
-            const double dds = (dprim[p_dsig()] - pq) / kap_s;
-            soc_M(w, e2i, q, 3, mq);
-            for (int i = 0; i < 3; i++) dz[r0 + 1 + i] = mq[i] + p_s[i] * dds;
-            ds[r0] = rzs * rz[r0] + ysig;
-            ds[r0 + 1] = rzs * rz[r0 + 1] + 0.5 * dds;
-            ds[r0 + 2] = rzs * rz[r0 + 2] - 0.5 * dds;
-            ds[r0 + 3] = rzs * rz[r0 + 3] + ysig;
-            dprim[p_dsig()] = dds;
-            dprim[p_sigma()] = ysig;
+            const double dds = (rxg[1] - pq) / kap_s;
+            soc::Mv(w3, e2i, q, 3, mq);
+            for (int i = 0; i < 3; i++) dzq[i] = mq[i] + p_s[i] * dds;
+            dz[r0g] = dz0; for (int i = 0; i < 3; i++) dz[r0g + 1 + i] = dzq[i];
+            dprim[p0g] = ysig; dprim[p0g + 1] = dds;
+            if (mode != 0) {
+                double dsg[4] = {rzs * rz[r0g] + ysig, rzs * rz[r0g + 1] + 0.5 * dds, rzs * rz[r0g + 2] - 0.5 * dds, rzs * rz[r0g + 3] + ysig};
+                for (int i = 0; i < 4; i++) ds[r0g + i] = dsg[i];
+                const double wv = sqrt(1. / d0), l0 = lam[r0g];
+                const double dzt0 = wv * dz0, dst0 = dsg[0] / wv;
+                tmax = fmax(tmax, fmax(-dst0 / l0, -dzt0 / l0));
+                double lm3[3] = {lam[r0g + 1], lam[r0g + 2], lam[r0g + 3]}, dzt[3], dst[3], pr[3];
+                soc::Wv(w3, e2i, dzq, 3, dzt, false);
+                soc::Wv(w3, e2i, dsg + 1, 3, dst, true);
+                tmax = fmax(tmax, fmax(soc::step(lm3, dst, 3), soc::step(lm3, dzt, 3)));
+                if (mode == 1) { cr[r0g] = dst0 * dzt0; soc::jprod(dst, dzt, 3, pr); for (int i = 0; i < 3; i++) cr[r0g + 1 + i] = pr[i]; }
+            }
         }
         warp_sync();
+        tmax_out = warp_max(tmax);
     }
 
-    // ---- cone-wise helpers over all rows (lanes over cones / rows) ----------------------------------------------
-    // visit every cone: f(offset, dim, cone_index or -1 for an LP row)
+    // =============================================================================================================
+    //  light sweeps: slack evaluation, cone margins / shifts, the update
+    // =============================================================================================================
+    // out = h - G x  (stage sweep)
+    SCPP_HD void eval_slack(double *out)
+    {
+        double *P = pw(0), *PNX = pw(1), *XB = pw(3), *O_ = row(0);
+        const double sg = prim[K * PS], dsg = prim[K * PS + 1];
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            const bool hasint = k < K - 1;
+            if (hasint) { ld_dd(k); ld(PNX, prim + (k + 1) * PS, PS); }
+            ld(P, prim + k * PS, PS);
+            load_xibar(k, XB);
+            ld_wait();
+            FOR_LANE(r, RS) {
+                double v = 0.;
+                if (r < NLP + NCR) v = cst[M::row(r).hs] - model_G(r, k, P);
+                else if (r == TRO) v = P[NB];
+                else if (r < MN) v = XB[r - TRO - 1] - P[r - TRO - 1];
+                else if (r < MN + 2 * NX && hasint) {
+                    const int i = (r - MN) % NX;
+                    const double rr = dyn_row(i, P, PNX, sg, true), t = P[PN + i];
+                    v = (r - MN < NX) ? t - rr : t + rr;
+                }
+                O_[r] = v;
+            }
+            warp_sync();
+            st(out + k * RS, O_, RS);
+            warp_sync();
+        }
+        if (lane_id() == 0) { const int r0 = K * RS; out[r0] = sg - 0.001; out[r0 + 1] = 0.5 + 0.5 * dsg; out[r0 + 2] = 0.5 - 0.5 * dsg; out[r0 + 3] = sg - sigbar; }
+        warp_sync();
+    }
+    // visit every cone of the flat row array (used only by the two start-up shifts)
     template <class F>
     SCPP_HD void for_cones(F &&f) const
     {
-        for (int k = lane_id(); k < K; k += LANES) {
-            const int r0 = rn(k);
-            for (int r = 0; r < NLP; r++) f(r0 + r, 1, -1);
-            for (int c = 0; c < NCONE; c++) f(r0 + NLP + M::cone_off(c), M::cone_dim(c), k * NCN + c);
-            f(r0 + TRO, 1 + NB, k * NCN + NCONE);
+        FOR_LANE(e, K * NTASK) {
+            const int k = e / NTASK, tk = e - k * NTASK;
+            int type, o, d, ci;
+            task(tk, type, o, d, ci);
+            if (type == 2) { if (k < K - 1) { f(k * RS + o, 1); f(k * RS + o + NX, 1); } }
+            else f(k * RS + o, d);
         }
-        FOR_LANE(e, (K - 1) * 2 * NX) f(ri(0) + e, 1, -1);
-        if (lane_id() == 0) { f(rg(), 1, -1); f(rg() + 1, 3, K * NCN); }
+        if (lane_id() == 0) { f(K * RS, 1); f(K * RS + 1, 3); }
     }
-
-    // s (or z) <- slack margins; returns min over cones of (u0 - |u1|) and |u|^2
     SCPP_HD void cone_margin(const double *u, double &mn, double &nrm2) const
     {
         double lmn = 1e300, n2 = 0;
-        for_cones([&](int o, int d, int) {
+        for_cones([&](int o, int d) {
             double t = 0;
             for (int i = 1; i < d; i++) t += u[o + i] * u[o + i];
             const double mg = u[o] - sqrt(t);
@@ -752,59 +1008,77 @@ struct Ipm {
         });
         mn = -warp_max(-lmn); nrm2 = warp_sum(n2);
     }
-    SCPP_HD void cone_shift(double *u, double a) const { for_cones([&](int o, int, int) { u[o] += a; }); }
+    SCPP_HD void cone_shift(double *u, double a) const { for_cones([&](int o, int) { u[o] += a; }); }
 
-    // slack(prim) = h - G x into `out`
-    SCPP_HD void eval_slack(double *out)
+    // prim += a dprim ; s += a ds ; z += a dz ; returns the minimum cone margin of the new (s,z)
+    SCPP_HD double apply_step(double a)
     {
-        for (int k = lane_id(); k < K; k += LANES) {
-            const double *xi = prim + pn(k);
-            const int r0 = rn(k);
-            for (int r = 0; r < NLP + NCR; r++) out[r0 + r] = row_slack(r, k, xi);
-            out[r0 + TRO] = xi[NB];
-            for (int i = 0; i < NB; i++) out[r0 + TRO + 1 + i] = xibar(k, i) - xi[i];
-        }
-        for (int k = 0; k < K - 1; k++) {
-            stage_dd(k);
-            const int q0 = ri(k);
-            FOR_LANE(i, NX) { const double r = dyn_resid(k, i, prim, true), t = prim[p_t(k) + i]; out[q0 + i] = t - r; out[q0 + NX + i] = t + r; }
+        double *S_ = row(0), *Z = row(1), *DS = row(2), *DZ = row(3), *P = pw(0), *DP = pw(1);
+        double lmn = 1e300;
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            const bool hasint = k < K - 1;
+            ld(S_, s + k * RS, RS); ld(Z, z + k * RS, RS); ld(DS, ds + k * RS, RS); ld(DZ, dz + k * RS, RS);
+            ld(P, prim + k * PS, PS); ld(DP, dprim + k * PS, PS);
+            ld_wait();
+            FOR_LANE(e, RS) { S_[e] += a * DS[e]; Z[e] += a * DZ[e]; }
+            FOR_LANE(e, PN + NX) P[e] += a * DP[e];
+            warp_sync();
+            FOR_LANE(tk, NTASK) {
+                int type, o, d, ci;
+                task(tk, type, o, d, ci);
+                if (type == 2) { if (hasint) lmn = fmin(lmn, fmin(fmin(S_[o], S_[o + NX]), fmin(Z[o], Z[o + NX]))); }
+                else {
+                    double ts = 0, tz = 0;
+#pragma unroll 1
+                    for (int i = 1; i < d; i++) { ts += S_[o + i] * S_[o + i]; tz += Z[o + i] * Z[o + i]; }
+                    lmn = fmin(lmn, fmin(S_[o] - sqrt(ts), Z[o] - sqrt(tz)));
+                }
+            }
+            st(s + k * RS, S_, RS); st(z + k * RS, Z, RS); st(prim + k * PS, P, PN + NX);
             warp_sync();
         }
         if (lane_id() == 0) {
-            const int r0 = rg();
-            const double sg = prim[p_sigma()], dsg = prim[p_dsig()];
-            out[r0] = sg - 0.001; out[r0 + 1] = 0.5 + 0.5 * dsg; out[r0 + 2] = 0.5 - 0.5 * dsg; out[r0 + 3] = sg - sigbar;
+            const int r0 = K * RS, p0 = K * PS;
+            for (int i = 0; i < 4; i++) { s[r0 + i] += a * ds[r0 + i]; z[r0 + i] += a * dz[r0 + i]; }
+            prim[p0] += a * dprim[p0]; prim[p0 + 1] += a * dprim[p0 + 1];
+            lmn = fmin(lmn, fmin(s[r0], z[r0]));
+            lmn = fmin(lmn, s[r0 + 1] - sqrt(s[r0 + 2] * s[r0 + 2] + s[r0 + 3] * s[r0 + 3]));
+            lmn = fmin(lmn, z[r0 + 1] - sqrt(z[r0 + 2] * z[r0 + 2] + z[r0 + 3] * z[r0 + 3]));
         }
         warp_sync();
+        return -warp_max(-lmn);
     }
 
     // =============================================================================================================
     //  driver
     // =============================================================================================================
-    SCPP_HD IpmResult solve(const IpmSettings &st)
+    SCPP_HD IpmResult solve(const IpmSettings &st_)
     {
         IpmResult res;
         res.status = 1; res.iterations = 0; res.pres = res.dres = res.gap = res.relgap = res.pcost = 0.;
         const int np = n_prim(K), m = m_rows(K);
         // ---- starting point (CVXOPT conelp / ECOS style): least-squares primal and dual points, W = I
-        for (int k = lane_id(); k < K; k += LANES) {
-            for (int i = 0; i < NB; i++) prim[pn(k) + i] = fixed(k, i) ? fixv[k * NB + i] : xibar(k, i);
-            prim[pn(k) + NB] = 0.;
+        FOR_LANE(e, K * PS) {
+            const int k = e / PS, i = e - k * PS;
+            double v = 0.;
+            if (i < NB) v = fixed(k, i) ? fixv[k * NB + i] : (i < NX ? Xbar[k * NX + i] : Ubar[k * NU + (i - NX)]);
+            prim[e] = v;
         }
-        FOR_LANE(e, (K - 1) * NX) prim[p_t(0) + e] = 0.;
-        if (lane_id() == 0) { prim[p_sigma()] = sigbar; prim[p_dsig()] = 0.; }
+        if (lane_id() == 0) { prim[K * PS] = sigbar; prim[K * PS + 1] = 0.; }
         FOR_LANE(e, m) { s[e] = 0.; z[e] = 0.; }
         warp_sync();
         cone_shift(s, 1.); cone_shift(z, 1.);
         warp_sync();
         Norms nm;
+        double tm;
         phase_residuals(nm, true);
         if (!phase_factor()) { res.status = 2; return res; }
         // primal: min |G x - h|  ->  G dx - dz = slack(x0)
         eval_slack(ds);
         FOR_LANE(e, np) dprim[e] = 0.;
         warp_sync();
-        phase_solve(0.);
+        phase_solve(0, 0., 0., 0., tm);
         FOR_LANE(e, np) prim[e] += dprim[e];
         warp_sync();
         eval_slack(s);
@@ -814,14 +1088,11 @@ struct Ipm {
             warp_sync();
         }
         // dual: min |z| s.t. G'z + c = 0  ->  rx = -c, rz = 0
-        FOR_LANE(e, np) dprim[e] = 0.;
         FOR_LANE(e, m) ds[e] = 0.;
+        FOR_LANE(e, K * PS) { const int i = e % PS; dprim[e] = (i == NB) ? -w_tr : ((i >= PN && i < PN + NX && e / PS < K - 1) ? -w_vc : 0.); }
+        if (lane_id() == 0) { dprim[K * PS] = -w_time; dprim[K * PS + 1] = -w_trs; }
         warp_sync();
-        for (int k = lane_id(); k < K; k += LANES) dprim[pn(k) + NB] = -w_tr;
-        FOR_LANE(e, (K - 1) * NX) dprim[p_t(0) + e] = -w_vc;
-        if (lane_id() == 0) { dprim[p_sigma()] = -w_time; dprim[p_dsig()] = -w_trs; }
-        warp_sync();
-        phase_solve(0.);
+        phase_solve(0, 0., 0., 0., tm);
         FOR_LANE(e, m) z[e] = dz[e];
         warp_sync();
         {
@@ -834,111 +1105,49 @@ struct Ipm {
         const int degree = K * (NLP + NCN) + (K - 1) * 2 * NX + 2;
         double best = 1e300;
         int it;
-        for (it = 0; it <= st.maxit; it++) {
+#pragma unroll 1
+        for (it = 0; it <= st_.maxit; it++) {
             phase_residuals(nm, false);
             const double resz0 = fmax(1., sqrt(nm.h2));
             const double pres = sqrt(nm.rz2) / resz0, dres = sqrt(nm.rx2) / resx0, gap = nm.gap, pcost = nm.pcost;
             const double dcost = pcost - gap + nm.zrz - nm.xrx;
             double relgap = 1e300;
             if (pcost < 0.) relgap = gap / -pcost; else if (dcost > 0.) relgap = gap / dcost;
-            const double score = fmax(fmax(pres, dres) / st.feastol, fmin(gap / st.abstol, relgap / st.reltol));
+            const double score = fmax(fmax(pres, dres) / st_.feastol, fmin(gap / st_.abstol, relgap / st_.reltol));
 #if !defined(__CUDACC__)
             if (getenv("SCPP_DEBUG")) fprintf(stderr, "it %2d pres %.2e dres %.2e gap %.2e relgap %.2e pcost %.6e bad %d\n", it, pres, dres, gap, relgap, pcost, nm.bad);
 #endif
             if (!nm.bad && score < best) {
                 best = score;
                 res.pres = pres; res.dres = dres; res.gap = gap; res.relgap = relgap; res.pcost = pcost; res.iterations = it;
-                // keep the best iterate (primal only matters downstream): cr is free at this point of the iteration
-                FOR_LANE(e, np) rxbest()[e] = prim[e];
+                FOR_LANE(e, np) best_[e] = prim[e];
                 warp_sync();
             }
-            if (!nm.bad && pres <= st.feastol && dres <= st.feastol && (gap <= st.abstol || relgap <= st.reltol)) { res.status = 0; break; }
-            if (nm.bad || it == st.maxit || (score > 1e3 * best && best < 1e4)) { res.status = nm.bad ? 2 : (it == st.maxit ? 1 : 2); break; }
+            if (!nm.bad && pres <= st_.feastol && dres <= st_.feastol && (gap <= st_.abstol || relgap <= st_.reltol)) { res.status = 0; break; }
+            if (nm.bad || it == st_.maxit || (score > 1e3 * best && best < 1e4)) { res.status = nm.bad ? 2 : (it == st_.maxit ? 1 : 2); break; }
             if (!phase_factor()) { res.status = 2; break; }
-            // ---- affine direction: rx-like = -rx ; rz-like = -rz + s
-            FOR_LANE(e, np) dprim[e] = -rx[e];
-            FOR_LANE(e, m) ds[e] = -rz[e] + s[e];
-            warp_sync();
-            phase_solve(-1.);
-            // scaled directions dz~ = W dz, ds~ = W^-1 ds ; step to the boundary ; cr = ds~ o dz~
-            double tmax = 0;
-            for_cones([&](int o, int d, int ci) {
-                if (d == 1) {
-                    const double w = sqrt(1. / wb[o]);           // W = sqrt(s/z)
-                    const double dzt = w * dz[o], dst = ds[o] / w;
-                    tmax = fmax(tmax, fmax(-dst / lam[o], -dzt / lam[o]));
-                    cr[o] = dst * dzt;
-                } else {
-                    double dzt[1 + NB], dst[1 + NB];
-                    soc_W(wb + o, ce[ci], dz + o, d, dzt, false);
-                    soc_W(wb + o, ce[ci], ds + o, d, dst, true);
-                    tmax = fmax(tmax, fmax(soc_step(lam + o, dst, d), soc_step(lam + o, dzt, d)));
-                    soc_jprod(dst, dzt, d, cr + o);
-                }
-            });
-            tmax = warp_max(tmax);
+            double tmax;
+            phase_solve(1, 1., 0., -1., tmax);                               // affine direction
             const double a_aff = tmax <= 1. ? 1. : 1. / tmax;
             const double sig = (1. - a_aff) * (1. - a_aff) * (1. - a_aff), mu = gap / degree;
-            // ---- combined direction: d_s = -lam o lam - cr + sig mu e ; rz-like = -(1-sig) rz - W (lam \ d_s)
-            FOR_LANE(e, np) dprim[e] = -(1. - sig) * rx[e];
-            for_cones([&](int o, int d, int ci) {
-                if (d == 1) {
-                    const double w = sqrt(1. / wb[o]);
-                    const double dsv = -lam[o] * lam[o] - cr[o] + sig * mu;
-                    const double t1 = dsv / lam[o];
-                    ds[o] = -(1. - sig) * rz[o] - w * t1;
-                } else {
-                    double dsv[1 + NB], t1[1 + NB], wt[1 + NB];
-                    soc_jprod(lam + o, lam + o, d, dsv);
-                    for (int i = 0; i < d; i++) dsv[i] = -dsv[i] - cr[o + i];
-                    dsv[0] += sig * mu;
-                    soc_jdiv(lam + o, dsv, d, t1);
-                    soc_W(wb + o, ce[ci], t1, d, wt, false);
-                    for (int i = 0; i < d; i++) ds[o + i] = -(1. - sig) * rz[o + i] - wt[i];
-                }
-            });
-            warp_sync();
-            phase_solve(-(1. - sig));
-            tmax = 0;
-            for_cones([&](int o, int d, int ci) {
-                if (d == 1) {
-                    const double w = sqrt(1. / wb[o]);
-                    tmax = fmax(tmax, fmax(-(ds[o] / w) / lam[o], -(w * dz[o]) / lam[o]));
-                } else {
-                    double dzt[1 + NB], dst[1 + NB];
-                    soc_W(wb + o, ce[ci], dz + o, d, dzt, false);
-                    soc_W(wb + o, ce[ci], ds + o, d, dst, true);
-                    tmax = fmax(tmax, fmax(soc_step(lam + o, dst, d), soc_step(lam + o, dzt, d)));
-                }
-            });
-            tmax = warp_max(tmax);
+            phase_solve(2, 1. - sig, sig * mu, -(1. - sig), tmax);           // combined direction
             double alpha = tmax <= 0.99 ? 1. : 0.99 / tmax;
+            double applied = 0.;
             // additive update; back off if rounding leaves the cone
             for (int tries = 0; tries < 20; tries++) {
-                double lmn = 1e300;
-                for_cones([&](int o, int d, int) {
-                    double ts = 0, tz = 0;
-                    for (int i = 1; i < d; i++) { const double a = s[o + i] + alpha * ds[o + i], b = z[o + i] + alpha * dz[o + i]; ts += a * a; tz += b * b; }
-                    const double ms = s[o] + alpha * ds[o] - sqrt(ts), mz = z[o] + alpha * dz[o] - sqrt(tz);
-                    lmn = fmin(lmn, fmin(ms, mz));
-                });
-                lmn = -warp_max(-lmn);
-                if (lmn > 0.) break;
+                const double mg = apply_step(alpha - applied);
+                applied = alpha;
+                if (mg > 0.) break;
                 alpha *= 0.8;
             }
-            FOR_LANE(e, np) prim[e] += alpha * dprim[e];
-            FOR_LANE(e, m) { s[e] += alpha * ds[e]; z[e] += alpha * dz[e]; }
-            warp_sync();
         }
         if (res.status != 0) {
-            // fall back to the best iterate seen
-            FOR_LANE(e, np) prim[e] = rxbest()[e];
+            FOR_LANE(e, np) prim[e] = best_[e];
             warp_sync();
             if (best <= 10.) res.status = 0; else if (best <= 1e4) res.status = 3;
         } else res.iterations = it;
         return res;
     }
-    SCPP_HD double *rxbest() const { return best_; }
 };
 
 } // namespace scpp

@@ -106,15 +106,15 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
     double n1 = 0, sd = 0;
     if (ok) {
         // readSolution (SCAlgorithm.cpp:191-210): X, U, sigma <- solver variables
-        FOR_LANE(e, K * NB) { const int k = e / NB, i = e - k * NB; const double v = ipm.prim[ipm.pn(k) + i]; if (i < NX) X[k * NX + i] = v; else U[k * NU + (i - NX)] = v; }
-        FOR_LANE(e, (K - 1) * NX) n1 += ipm.prim[ipm.p_t(0) + e];            // norm1_nu  (:102-103)
-        FOR_LANE(k, K) sd += ipm.prim[ipm.pn(k) + NB];                       // delta.sum() (:105-107)
+        FOR_LANE(e, K * NB) { const int k = e / NB, i = e - k * NB; const double v = ipm.xi_at(k, i); if (i < NX) X[k * NX + i] = v; else U[k * NU + (i - NX)] = v; }
+        FOR_LANE(e, (K - 1) * NX) n1 += ipm.t_at(e / NX, e % NX);            // norm1_nu  (:102-103)
+        FOR_LANE(k, K) sd += ipm.delta_at(k);                       // delta.sum() (:105-107)
     }
     n1 = warp_sum(n1); sd = warp_sum(sd);
     warp_sync();
     if (lane_id() == 0) {
-        const double sg = ok ? ipm.prim[ipm.p_sigma()] : a.sigma[n];
-        const double dsg = ok ? ipm.prim[ipm.p_dsig()] : 0.;
+        const double sg = ok ? ipm.sigma_val() : a.sigma[n];
+        const double dsg = ok ? ipm.dsigma_val() : 0.;
         inf[0] = n1; inf[1] = sd; inf[2] = dsg; inf[3] = sg; inf[4] = w_tr;
         inf[5] = r.iterations; inf[6] = r.status; inf[7] = r.pres; inf[8] = r.dres; inf[9] = r.relgap;
         a.iters[n] = it + 1;
@@ -128,8 +128,8 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
     }
     if (a.hist && ok) {
         double *h = a.hist + ((size_t)n * (a.max_it + 1) + it + 1) * a.hist_stride();
-        FOR_LANE(e, K * NB) { const int k = e / NB, i = e - k * NB; h[e] = ipm.prim[ipm.pn(k) + i]; }
-        if (lane_id() == 0) h[K * NB] = ipm.prim[ipm.p_sigma()];
+        FOR_LANE(e, K * NB) { const int k = e / NB, i = e - k * NB; h[e] = ipm.xi_at(k, i); }
+        if (lane_id() == 0) h[K * NB] = ipm.sigma_val();
     }
     warp_sync();
 }

@@ -51,6 +51,7 @@ def test_discretize_rocket2d_and_ragged_sizes(S):
     pn = O.R2DParams.from_buffer_copy(p2); O.lib().orc_r2d_nondimensionalize(C.byref(pn))
     par = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(pn), par.ctypes.data_as(C.c_void_p))
     for K in (3, 7, 30):      # K=3: smallest the engine accepts; odd sizes exercise partial warps / blocks
+        tol = 2e-10 if K >= 30 else 1e-5      # coarse grids: 6 s intervals, RK4 x 20 and RKF78 x 5 both carry truncation error
         X = np.zeros((K, 6)); U = np.zeros((K, 2)); t = C.c_double()
         O.lib().orc_r2d_initial_trajectory(C.byref(pn), K, X.ctypes.data_as(C.c_void_p), U.ctypes.data_as(C.c_void_p), C.byref(t))
         ref = O.discretize(O.ROCKET2D, X, U, t.value, par)

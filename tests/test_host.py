@@ -1,0 +1,207 @@
+"""CPU tests of the host logic and of the kernel SOURCE compiled for the host (LANES == 1, tests/_hostsim):
+the C-ABI library loads and exports every declared symbol, the INFO loader, the dual-number check of the device
+Jacobians, kernel-source parity against the oracle, and the multi-rank plumbing over gloo (world_size 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import hostsim as H
+import orc_py as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def S():
+    from scpp_b200 import build
+    build.build()          # nvcc cross-compiles sm_100a without a GPU
+    import scpp_b200
+    return scpp_b200
+
+
+def test_cabi_exports_every_declared_symbol(S):
+    hdr = open(os.path.join(ROOT, "include", "scpp_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(scpp_b200_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(names) >= 18
+    lib = S.lib()
+    for n in names:
+        assert hasattr(lib, n), f"libscpp_b200.so does not export {n}"
+    assert lib.scpp_b200_version() >= 100
+    nx, nu, npar = S.model_dims(S.ROCKETQUAT)
+    assert (nx, nu, npar) == (14, 4, 10) and S.model_dims(S.ROCKET2D) == (6, 2, 6)
+
+
+def test_no_cpu_execution_path(S):
+    """without a CUDA device every compute entry point must fail loudly (never fall back)"""
+    if S.device_count() > 0:
+        pytest.skip("a GPU is present")
+    model, params, xi, xf, cfg = S.load_model("RocketQuat")
+    with pytest.raises(S.ScppError, match="no CUDA device"):
+        S.SCAlgorithm(model, params, cfg, 2)
+    with pytest.raises(S.ScppError, match="no CUDA device"):
+        S.discretize(model, np.zeros((3, 14)), np.zeros((3, 4)), 1.0, np.zeros(10))
+    # the package never imports the oracle or the host simulation
+    src = open(os.path.join(ROOT, "scpp_b200", "__init__.py")).read() + open(os.path.join(ROOT, "scpp_b200", "csrc", "engine.cu")).read()
+    assert "orc_" not in src and "hostsim" not in src and "liborc" not in src
+
+
+def test_info_loader_matches_reference_parameter_sets(S):
+    model, p, xi, xf, cfg = S.load_model("RocketQuat")
+    po, rpy = O.falcon9()
+    assert np.array_equal(xi, np.array(po.x_init)) and np.array_equal(xf, np.array(po.x_final))
+    for f in ("alpha_m", "T_min", "T_max", "t_max", "gimbal_max", "theta_max", "gamma_gs", "w_B_max", "final_time"):
+        assert getattr(p, f) == getattr(po, f), f
+    assert (cfg.K, cfg.max_iterations, cfg.weight_trust_region_trajectory, cfg.weight_virtual_control) == (15, 15, 50.0, 1000.0)
+    assert cfg.nu_tol == 1e-5 and cfg.delta_tol == 1e-3 and cfg.free_final_time == 1 and cfg.nondimensionalize == 1
+    _, ps, xis, _, _ = S.load_model("RocketQuatStarship")
+    pso, _ = O.starship()
+    assert np.array_equal(xis, np.array(pso.x_init)) and ps.T_max == pso.T_max and ps.gamma_gs == pso.gamma_gs
+    _, p2, xi2, xf2, cfg2 = S.load_model("Rocket2D")
+    p2o = O.rocket2d()
+    assert np.array_equal(xi2, np.array(p2o.x_init)) and np.array_equal(xf2, np.array(p2o.x_final)) and p2.m == p2o.m and cfg2.K == 25
+
+
+def test_info_loader_error_semantics(S, tmp_path):
+    """parameterServer.hpp:66-77,95-103: missing scalar, missing / redundant vector entries raise"""
+    good = open(os.path.join(ROOT, "configs", "RocketQuat", "model.info")).read()
+    def load(txt):
+        f = tmp_path / "m.info"; f.write_text(txt)
+        return S.load_model_info(str(f), S.ROCKETQUAT)
+    load(good)
+    with pytest.raises(S.ScppError, match="Failed to load scalar"):
+        load(good.replace("I_sp    275.", ""))
+    with pytest.raises(S.ScppError, match="Missing entries"):
+        load(good.replace("g_I   { (0) 0.0  (1) 0.0  (2) -9.81 }", "g_I   { (0) 0.0  (1) 0.0 }"))
+    with pytest.raises(S.ScppError, match="Redundant entries"):
+        load(good.replace("g_I   { (0) 0.0  (1) 0.0  (2) -9.81 }", "g_I   { (0) 0.0  (1) 0.0  (2) -9.81 (3) 1. }"))
+    with pytest.raises(S.ScppError):
+        S.load_model_info(str(tmp_path / "nope.info"), S.ROCKETQUAT)
+    # scaling and comments
+    p, xi, xf = load(good.replace("r_init    { (0) 200.  (1) 200.  (2) 800. }", "r_init { scaling 100. ; cm\n (0) 2. \n (1) 2. \n (2) 8. }"))
+    assert np.allclose(xi[1:4], [200, 200, 800])
+
+
+def test_perturbation_recipe_matches_oracle(S):
+    model, p, xi, xf, cfg = S.load_model("RocketQuat")
+    po, rpy = O.falcon9()
+    b = S.perturbed_initial_states(xi, rpy, 5, first=3)
+    for i in range(5):
+        assert np.array_equal(b[i], np.array(O.rq_perturb(po, rpy, 0x5C99, 3 + i).x_init))
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_device_jacobian_equals_dual_number_jacobian(model):
+    """hand-derived sparse Jacobian used by K1 == forward-mode AD of the generic-scalar flow map == oracle Jacobian"""
+    rng = np.random.default_rng(7)
+    nx, nu = H.DIMS[model]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for _ in range(10):
+        if model == 0:
+            x = 0.5 * rng.normal(size=nx); x[0] = 1 + rng.random(); x[7] += 1
+            u = 0.02 * rng.normal(size=nu); u[2] += 0.03
+            par = np.array([0.3, 0.01, -0.02, -0.0115, 0.3, 0.25, 0.004, 0.001, -0.002, -0.0177])
+        else:
+            x = rng.normal(size=nx); u = np.array([0.2 * rng.normal(), 0.02 * rng.random() + 0.01]); par = np.array([1.0, 0.3, 0.001, -0.012, 0.002, -0.018])
+        f = np.zeros(nx); Aad = np.zeros((nx, nx)); Bad = np.zeros((nx, nu)); Al = np.zeros((nx, nx)); Bl = np.zeros((nx, nu))
+        H.lib().hs_jacobians(model, p(x), p(u), p(par), p(f), p(Aad), p(Bad), p(Al), p(Bl))
+        assert not np.isnan(f).any()
+        assert np.allclose(Al, Aad, atol=1e-13) and np.allclose(Bl, Bad, atol=1e-13)
+        Ao, Bo = O.jac(model, x, u, par)
+        assert np.allclose(Ao, Aad, atol=1e-13) and np.allclose(Bo, Bad, atol=1e-13) and np.allclose(O.f(model, x, u, par), f, atol=1e-14)
+
+
+def test_kernel_source_discretisation_vs_oracle():
+    p, rpy = O.falcon9()
+    r = O.sc_solve(O.ROCKETQUAT, p, O.sc_config(K=30, max_iterations=2))
+    pn = O.RQParams.from_buffer_copy(p); O.lib().orc_rq_nondimensionalize(C.byref(pn))
+    par = np.zeros(10); O.lib().orc_rq_model_par(C.byref(pn), par.ctypes.data_as(C.c_void_p))
+    X, U, t = r["X_all"][2], r["U_all"][2], r["t_all"][2]
+    ref = O.discretize(O.ROCKETQUAT, X, U, t, par)
+    errs = []
+    for nsub in (5, 10, 20):
+        got = H.discretize(0, X, U, t, par, nsub)
+        errs.append(max(np.abs(got[k] - ref[k]).max() / max(1.0, np.abs(ref[k]).max()) for k in ("A", "B", "C", "s", "z")))
+    assert errs[2] < 2e-10                       # the shipped NSUB
+    assert 8 < errs[0] / errs[1] < 24 and 8 < errs[1] / errs[2] < 24   # 4th-order convergence towards the RKF78 result
+
+
+@pytest.mark.parametrize("name,model,K,max_it", [("Rocket2D", 1, 30, 15), ("RocketQuat", 0, 20, 5)])
+def test_kernel_source_sc_loop_vs_oracle(name, model, K, max_it):
+    """the K2/K3 source (structured IPM, one 'warp' of 1 lane) reproduces the literal ECOS-form oracle iterate by iterate"""
+    if model == 0:
+        p, _ = O.falcon9()
+    else:
+        p = O.rocket2d()
+    ocfg = O.sc_config(K=K, model=model, max_iterations=max_it)
+    ro = O.sc_solve(model, p, ocfg)
+    P, xi, xf = H.params_from_oracle(model, p)
+    rh = H.sc_solve(model, P, H.sc_config(ocfg, tol=1e-8), xi, xf)
+    n = ro["iterations"]
+    assert n > 0 and rh["iters"][0] == n and bool(rh["converged"][0] == 1) == ro["converged"]
+    for it in range(n + 1):
+        assert np.abs(rh["X_all"][0, it] - ro["X_all"][it]).max() < 1e-5
+        assert np.abs(rh["U_all"][0, it] - ro["U_all"][it]).max() < 1e-4
+    for it in range(n):
+        assert rh["info"][0, it, 4] == ro["info"][it].weight_tr_used
+        assert int(rh["info"][0, it, 6]) in (0, 3)
+    assert np.allclose(rh["X"][0], ro["X"], rtol=1e-6, atol=1e-4 * np.abs(ro["X"]).max())
+
+
+def test_shard_range_partitions_the_batch():
+    from scpp_b200.sharding import shard_range
+    for n, w in ((8192, 8), (1000, 3), (5, 8), (1, 1)):
+        spans = [shard_range(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch.distributed as dist
+import scpp_b200 as S, hostsim as H, orc_py as O
+from scpp_b200.sharding import shard_range, broadcast_unique_id, global_active, reduce_timing
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+uid = broadcast_unique_id(dist, lambda: bytes(range(128)), rank)
+assert uid == bytes(range(128))
+N, K, max_it = 5, 12, 4
+lo, hi = shard_range(N, world, rank)
+model, p, xi, xf, cfg = S.load_model("RocketQuat", K=K, max_iterations=max_it)
+xis = S.perturbed_initial_states(xi, np.deg2rad([-20., 20., 0.]), hi - lo, first=lo)
+# per-rank engine stand-in on CPU: the kernel source compiled for the host (test-only)
+po, _ = O.falcon9()
+P, _, _ = H.params_from_oracle(0, po)
+r = H.sc_solve(0, P, H.sc_config(O.sc_config(K=K, max_iterations=max_it), tol=1e-8), xis, xf)
+pad = max(b - a for a, b in (shard_range(N, world, q) for q in range(world)))
+n_act, allf = global_active(dist, (r["converged"] != 0).astype(np.uint8), pad)
+t, c = reduce_timing(dist, [1.0 + rank], [int(r["iters"].sum())])
+full = S.perturbed_initial_states(xi, np.deg2rad([-20., 20., 0.]), N)
+assert np.array_equal(full[lo:hi], xis)
+out = dict(rank=rank, n_act=n_act, tmax=float(t[0]), iters=float(c[0]), local_iters=int(r["iters"].sum()), shape=list(allf.shape))
+print("RESULT", out, flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_plumbing_over_gloo(tmp_path):
+    """world_size 2 on CPU: shard assignment, unique-id broadcast, flag all-gather and timing reduction agree on both ranks"""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29671", str(script), ROOT]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    outs = [eval(l.split("RESULT", 1)[1]) for l in res.stdout.splitlines() if "RESULT" in l]
+    assert len(outs) == 2
+    a, b = sorted(outs, key=lambda o: o["rank"])
+    assert a["n_act"] == b["n_act"] and a["tmax"] == b["tmax"] == 2.0
+    assert a["iters"] == b["iters"] == a["local_iters"] + b["local_iters"]
+    assert a["shape"] == [2, 3]
