@@ -44,7 +44,7 @@ struct IpmResult {
 };
 
 #if defined(__CUDACC__)
-#define SCPP_OUTLINE __host__ __device__ __noinline__
+#define SCPP_OUTLINE __host__ __device__ __forceinline__
 #else
 #define SCPP_OUTLINE inline
 #endif
@@ -317,6 +317,77 @@ struct Ipm {
         FOR_LANE(i, NB) dst[i] = i < NX ? Xbar[k * NX + i] : Ubar[k * NU + (i - NX)];
     }
 
+    // ---- trust-region cone (dimension D = 1 + NB): WARP-COOPERATIVE primitives, lane i owns element i, vectors in the
+    //      shared window, reductions by shuffles.  Every lane of the warp must call them (uniform control flow).
+    //      Outputs may alias inputs.
+    static constexpr int D = 1 + NB;
+    SCPP_HD bool tr_scale(const double *sk, const double *zk, double *w, double &e2i, double *lm) const
+    {
+        double a = 0, b = 0, c = 0;
+        FOR_LANE(i, D) { if (i > 0) { a += sk[i] * sk[i]; b += zk[i] * zk[i]; } c += sk[i] * zk[i]; }
+        warp_sum3(a, b, c);
+        const double s0 = sk[0], z0 = zk[0];
+        const double ss = s0 * s0 - a, zz = z0 * z0 - b;
+        if (!(ss > 0.) || !(zz > 0.) || !(s0 > 0.) || !(z0 > 0.)) return false;
+        const double sn = sqrt(ss), zn = sqrt(zz);
+        const double i2g = 1. / (2. * sqrt((1. + c / (sn * zn)) / 2.));
+        const double w0 = (s0 / sn + z0 / zn) * i2g;
+        double w1z1 = 0;
+        warp_sync();
+        FOR_LANE(i, D) { const double wi = (i == 0) ? w0 : (sk[i] / sn - zk[i] / zn) * i2g; if (i > 0) w1z1 += wi * zk[i]; w[i] = wi; }
+        w1z1 = warp_sum(w1z1);
+        e2i = zn / sn;
+        const double eta = sqrt(sn / zn), f = z0 + w1z1 / (1. + w0);
+        FOR_LANE(i, D) lm[i] = (i == 0) ? eta * (w0 * z0 + w1z1) : eta * (zk[i] + f * w[i]);
+        warp_sync();
+        return true;
+    }
+    SCPP_HD void tr_Mv(const double *w, double e2i, const double *v, double *o) const   // o = W^-2 v
+    {
+        double dot = 0;
+        FOR_LANE(i, D) dot += (i == 0 ? w[0] * v[0] : -w[i] * v[i]);
+        dot = warp_sum(dot);
+        warp_sync();
+        FOR_LANE(i, D) o[i] = (i == 0) ? e2i * (2. * dot * w[0] - v[0]) : e2i * (-2. * dot * w[i] + v[i]);
+        warp_sync();
+    }
+    SCPP_HD void tr_Wv(const double *w, double e2i, const double *v, double *o, bool inv) const   // o = W v | W^-1 v
+    {
+        const double eta = 1. / sqrt(e2i), sg = inv ? -1. : 1., scl = inv ? 1. / eta : eta;
+        double w1v1 = 0;
+        FOR_LANE(i, D) if (i > 0) w1v1 += w[i] * v[i];
+        w1v1 = warp_sum(w1v1);
+        const double v0 = v[0], w0 = w[0];
+        const double f = sg * v0 + w1v1 / (1. + w0);
+        warp_sync();
+        FOR_LANE(i, D) o[i] = (i == 0) ? scl * (w0 * v0 + sg * w1v1) : scl * (v[i] + f * w[i]);
+        warp_sync();
+    }
+    // scaled step-to-boundary measures of two directions at once: returns max(t(d1), t(d2))
+    SCPP_HD double tr_step2(const double *lm, const double *d1, const double *d2) const
+    {
+        double l1 = 0, a1 = 0, a2 = 0;
+        FOR_LANE(i, D) if (i > 0) { l1 += lm[i] * lm[i]; a1 += lm[i] * d1[i]; a2 += lm[i] * d2[i]; }
+        warp_sum3(l1, a1, a2);
+        const double a = sqrt(lm[0] * lm[0] - l1), l0 = lm[0] / a;
+        const double ld1 = l0 * d1[0] - a1 / a, ld2 = l0 * d2[0] - a2 / a;
+        const double f1 = (ld1 + d1[0]) / (l0 + 1.), f2 = (ld2 + d2[0]) / (l0 + 1.);
+        double n1 = 0, n2 = 0, dummy = 0;
+        FOR_LANE(i, D) if (i > 0) { const double r1 = (d1[i] - f1 * lm[i] / a) / a, r2 = (d2[i] - f2 * lm[i] / a) / a; n1 += r1 * r1; n2 += r2 * r2; }
+        warp_sum3(n1, n2, dummy);
+        return fmax(sqrt(n1) - ld1 / a, sqrt(n2) - ld2 / a);
+    }
+    SCPP_HD void tr_jprod(const double *u, const double *v, double *o) const
+    {
+        double dot = 0;
+        FOR_LANE(i, D) dot += u[i] * v[i];
+        dot = warp_sum(dot);
+        const double u0 = u[0], v0 = v[0];
+        warp_sync();
+        FOR_LANE(i, D) o[i] = (i == 0) ? dot : u0 * v[i] + v0 * u[i];
+        warp_sync();
+    }
+
     // =============================================================================================================
     //  Phase R : residuals, Nesterov-Todd scaling, termination quantities  (one forward sweep)
     // =============================================================================================================
@@ -338,20 +409,31 @@ struct Ipm {
             ld(S, s + k * RS, RS); ld(Z, z + k * RS, RS); ld(P, prim + k * PS, PS);
             load_xibar(k, XB);
             ld_wait();
-            // ---- cone tasks
+            // ---- trust-region cone: warp-cooperative
+            {
+                const int o = TRO;
+                FOR_LANE(i, D) {
+                    const double sl = (i == 0) ? P[NB] : XB[i - 1] - P[i - 1];
+                    RZ[o + i] = S[o + i] - sl;
+                    if (i > 0) h2 += XB[i - 1] * XB[i - 1];
+                }
+                if (lane_id() == 0) pcost += w_tr * P[NB];
+                if (identity) { FOR_LANE(i, D) { WB[o + i] = i == 0; LM[o + i] = i == 0; } if (lane_id() == 0) CE[NCONE] = 1.; }
+                else {
+                    double e2i;
+                    if (!tr_scale(S + o, Z + o, WB + o, e2i, LM + o)) bad = 1;
+                    else if (lane_id() == 0) CE[NCONE] = e2i;
+                }
+                FOR_LANE(i, D) { gap += S[o + i] * Z[o + i]; rz2 += RZ[o + i] * RZ[o + i]; zrz += Z[o + i] * RZ[o + i]; }
+            }
+            // ---- small cone tasks: one lane each
             FOR_LANE(tk, NTASK) {
+                if (tk == NCONE) continue;
                 int type, o, d, ci;
                 task(tk, type, o, d, ci);
                 if (type == 1) {
-                    if (ci < NCONE) {
 #pragma unroll 1
-                        for (int r = 0; r < d; r++) { const RowDesc rd = M::row(o + r); const double sl = cst[rd.hs] - model_G(o + r, k, P); RZ[o + r] = S[o + r] - sl; h2 += cst[rd.hs] * cst[rd.hs]; }
-                    } else {
-                        RZ[o] = S[o] - P[NB];
-#pragma unroll 1
-                        for (int i = 0; i < NB; i++) { RZ[o + 1 + i] = S[o + 1 + i] - (XB[i] - P[i]); h2 += XB[i] * XB[i]; }
-                        pcost += w_tr * P[NB];
-                    }
+                    for (int r = 0; r < d; r++) { const RowDesc rd = M::row(o + r); const double sl = cst[rd.hs] - model_G(o + r, k, P); RZ[o + r] = S[o + r] - sl; h2 += cst[rd.hs] * cst[rd.hs]; }
                     if (identity) { CE[ci] = 1.; for (int i = 0; i < d; i++) { WB[o + i] = i == 0; LM[o + i] = i == 0; } }
                     else if (!soc::scale(S + o, Z + o, d, WB + o, CE[ci], LM + o)) bad = 1;
 #pragma unroll 1
@@ -664,7 +746,7 @@ struct Ipm {
     //  forward sweep: right-hand side + forward substitution; backward sweep: back substitution + recovery of the
     //  local variables, dz and ds = rzs*rz - G dx, the scaled step lengths (tmax) and, for mode 1, cr = ds~ o dz~.
     // =============================================================================================================
-    SCPP_HD void gen_rhs(int mode, bool hasint, double csig, double sigmu, double *RZV, double *RXV,
+    SCPP_HD void gen_rhs(int mode, bool hasint, double csig, double sigmu, double *RZV, double *RXV, double *T1,
                          const double *S_, const double *RZ, const double *LM, const double *CR, const double *WB, const double *CE, const double *RXW)
     {
         if (mode == 1) {
@@ -672,11 +754,34 @@ struct Ipm {
             FOR_LANE(e, PS) RXV[e] = -RXW[e];
         } else {
             FOR_LANE(e, PS) RXV[e] = -csig * RXW[e];
+            {   // trust-region cone (warp-cooperative): rzv = -csig rz - W (lam \ (-lam o lam - cr + sigmu e))
+                const int o = TRO;
+                const double *lm = LM + o, *w = WB + o;
+                double ll = 0;
+                FOR_LANE(i, D) ll += lm[i] * lm[i];
+                ll = warp_sum(ll);
+                const double l0 = lm[0], den = 2. * l0 * l0 - ll;
+                double l1d1 = 0;
+                FOR_LANE(i, D) {
+                    const double dv = (i == 0) ? -ll - CR[o] + sigmu : -2. * l0 * lm[i] - CR[o + i];
+                    T1[o + i] = dv;
+                    if (i > 0) l1d1 += lm[i] * dv;
+                }
+                l1d1 = warp_sum(l1d1);
+                warp_sync();
+                const double x0 = (l0 * T1[o] - l1d1) / den;
+                warp_sync();
+                FOR_LANE(i, D) T1[o + i] = (i == 0) ? x0 : (T1[o + i] - x0 * lm[i]) / l0;
+                warp_sync();
+                tr_Wv(w, CE[NCONE], T1 + o, T1 + o, false);
+                FOR_LANE(i, D) RZV[o + i] = -csig * RZ[o + i] - T1[o + i];
+            }
             FOR_LANE(tk, NTASK) {
+                if (tk == NCONE) continue;
                 int type, o, d, ci;
                 task(tk, type, o, d, ci);
                 if (type == 1) {
-                    double t1[1 + NB];
+                    double *t1 = T1 + o;
                     soc::jprod(LM + o, LM + o, d, t1);
 #pragma unroll 1
                     for (int i = 0; i < d; i++) t1[i] = -t1[i] - CR[o + i];
@@ -723,26 +828,25 @@ struct Ipm {
                 else { ld(LM, lam + k * RS, RS); ld(CR, cr + k * RS, RS); }
             }
             ld_wait();
-            if (mode != 0) { gen_rhs(mode, hasint, csig, sigmu, RZV, RXV, S_, RZ, LM, CR, WB, CE, RXW); warp_sync(); }
+            if (mode != 0) { gen_rhs(mode, hasint, csig, sigmu, RZV, RXV, V, S_, RZ, LM, CR, WB, CE, RXW); warp_sync(); }
             // ---- v_c = Mtilde rzv per cone; pairs produce w_i
+            {   // trust region (warp-cooperative): v = M rzv - p (p'rzv + rx_delta)/kap ,  p = M(-e0)
+                const int o = TRO;
+                const double *w = WB + o;
+                const double e2i = CE[NCONE], w0 = w[0];
+                tr_Mv(w, e2i, RZV + o, V + o);
+                double prz = 0;
+                FOR_LANE(i, D) { const double p = (i == 0) ? -e2i * (2. * w0 * w0 - 1.) : 2. * e2i * w0 * w[i]; prz += p * RZV[o + i]; }
+                prz = warp_sum(prz);
+                const double rho = (prz + RXV[NB]) / (e2i * (2. * w0 * w0 - 1.));
+                FOR_LANE(i, D) { const double p = (i == 0) ? -e2i * (2. * w0 * w0 - 1.) : 2. * e2i * w0 * w[i]; V[o + i] -= p * rho; }
+            }
             FOR_LANE(tk, NTASK) {
+                if (tk == NCONE) continue;
                 int type, o, d, ci;
                 task(tk, type, o, d, ci);
-                if (type == 1) {
-                    soc::Mv(WB + o, CE[ci], RZV + o, d, V + o);
-                    if (ci == NCONE) {      // trust region: v -= p (p'rzv + rx_delta)/kap ,  p = -M e0
-                        double p[1 + NB], e0[1 + NB];
-#pragma unroll 1
-                        for (int i = 0; i <= NB; i++) e0[i] = (i == 0) ? -1. : 0.;
-                        soc::Mv(WB + o, CE[ci], e0, d, p);
-                        double prz = 0;
-#pragma unroll 1
-                        for (int i = 0; i <= NB; i++) prz += p[i] * RZV[o + i];
-                        const double rho = (prz + RXV[NB]) / (-p[0]);
-#pragma unroll 1
-                        for (int i = 0; i <= NB; i++) V[o + i] -= p[i] * rho;
-                    }
-                } else if (type == 0) V[o] = WB[o] * RZV[o];
+                if (type == 1) soc::Mv(WB + o, CE[ci], RZV + o, d, V + o);
+                else if (type == 0) V[o] = WB[o] * RZV[o];
                 else if (hasint) {
                     const int i = o - MN;
                     const double dm = WB[o], dp = WB[o + NX], rm = RZV[o], rp = RZV[o + NX];
@@ -843,41 +947,51 @@ struct Ipm {
             }
             warp_sync();
             // ---- recovery per cone: q = G dy - rzv ; local ; dz = M q + p dl ; ds = rzs rz - G dx ; scaled steps
+            //      scratch: Q = V window, GDX = S_ window (both free in the backward sweep)
+            double *Q = V, *GDX = S_;
+            {   // trust region (warp-cooperative)
+                const int o = TRO;
+                const double *w = WB + o;
+                const double e2i = CE[NCONE], w0 = w[0], kap = e2i * (2. * w0 * w0 - 1.);
+                double pq = 0;
+                FOR_LANE(i, D) {
+                    const double q = (i == 0) ? -RZV[o] : yk[i - 1] - RZV[o + i];
+                    const double p = (i == 0) ? -kap : 2. * e2i * w0 * w[i];
+                    Q[o + i] = q; pq += p * q;
+                }
+                pq = warp_sum(pq);
+                const double ddl = (RXV[NB] - pq) / kap;
+                warp_sync();
+                tr_Mv(w, e2i, Q + o, DZ + o);
+                FOR_LANE(i, D) {
+                    const double p = (i == 0) ? -kap : 2. * e2i * w0 * w[i];
+                    DZ[o + i] += p * ddl;
+                    if (mode != 0) DS[o + i] = rzs * RZ[o + i] - ((i == 0) ? -ddl : yk[i - 1]);
+                }
+                if (lane_id() == 0) DP[NB] = ddl;
+                warp_sync();
+                if (mode != 0) {
+                    tr_Wv(w, e2i, DZ + o, Q + o, false);          // dz~
+                    tr_Wv(w, e2i, DS + o, GDX + o, true);         // ds~
+                    tmax = fmax(tmax, tr_step2(LM + o, GDX + o, Q + o));
+                    if (mode == 1) tr_jprod(GDX + o, Q + o, CR + o);
+                }
+            }
             FOR_LANE(tk, NTASK) {
+                if (tk == NCONE) continue;
                 int type, o, d, ci;
                 task(tk, type, o, d, ci);
                 if (type == 1) {
-                    double q[1 + NB], gdx[1 + NB];
-                    if (ci < NCONE) {
 #pragma unroll 1
-                        for (int r = 0; r < d; r++) { gdx[r] = model_G(o + r, k, yk); q[r] = gdx[r] - RZV[o + r]; }
-                        soc::Mv(WB + o, CE[ci], q, d, DZ + o);
-                    } else {
-                        double p[1 + NB], e0[1 + NB];
-                        q[0] = -RZV[o];
-#pragma unroll 1
-                        for (int i = 0; i < NB; i++) { q[1 + i] = yk[i] - RZV[o + 1 + i]; gdx[1 + i] = yk[i]; }
-#pragma unroll 1
-                        for (int i = 0; i <= NB; i++) e0[i] = (i == 0) ? -1. : 0.;
-                        soc::Mv(WB + o, CE[ci], e0, d, p);
-                        double pq = 0;
-#pragma unroll 1
-                        for (int i = 0; i <= NB; i++) pq += p[i] * q[i];
-                        const double ddl = (RXV[NB] - pq) / (-p[0]);
-                        soc::Mv(WB + o, CE[ci], q, d, DZ + o);
-#pragma unroll 1
-                        for (int i = 0; i <= NB; i++) DZ[o + i] += p[i] * ddl;
-                        gdx[0] = -ddl;
-                        DP[NB] = ddl;
-                    }
+                    for (int r = 0; r < d; r++) { const double gdx = model_G(o + r, k, yk); GDX[o + r] = gdx; Q[o + r] = gdx - RZV[o + r]; }
+                    soc::Mv(WB + o, CE[ci], Q + o, d, DZ + o);
                     if (mode != 0) {
 #pragma unroll 1
-                        for (int r = 0; r < d; r++) DS[o + r] = rzs * RZ[o + r] - gdx[r];
-                        double dzt[1 + NB], dst[1 + NB];
-                        soc::Wv(WB + o, CE[ci], DZ + o, d, dzt, false);
-                        soc::Wv(WB + o, CE[ci], DS + o, d, dst, true);
-                        tmax = fmax(tmax, fmax(soc::step(LM + o, dst, d), soc::step(LM + o, dzt, d)));
-                        if (mode == 1) soc::jprod(dst, dzt, d, CR + o);
+                        for (int r = 0; r < d; r++) DS[o + r] = rzs * RZ[o + r] - GDX[o + r];
+                        soc::Wv(WB + o, CE[ci], DZ + o, d, Q + o, false);
+                        soc::Wv(WB + o, CE[ci], DS + o, d, GDX + o, true);
+                        tmax = fmax(tmax, fmax(soc::step(LM + o, GDX + o, d), soc::step(LM + o, Q + o, d)));
+                        if (mode == 1) soc::jprod(GDX + o, Q + o, d, CR + o);
                     }
                 } else if (type == 0) {
                     const double gdx = model_G(o, k, yk);
@@ -1024,7 +1138,14 @@ struct Ipm {
             FOR_LANE(e, RS) { S_[e] += a * DS[e]; Z[e] += a * DZ[e]; }
             FOR_LANE(e, PN + NX) P[e] += a * DP[e];
             warp_sync();
+            {   // trust region margins (warp-cooperative)
+                double ts = 0, tz = 0, dummy = 0;
+                FOR_LANE(i, D) if (i > 0) { ts += S_[TRO + i] * S_[TRO + i]; tz += Z[TRO + i] * Z[TRO + i]; }
+                warp_sum3(ts, tz, dummy);
+                lmn = fmin(lmn, fmin(S_[TRO] - sqrt(ts), Z[TRO] - sqrt(tz)));
+            }
             FOR_LANE(tk, NTASK) {
+                if (tk == NCONE) continue;
                 int type, o, d, ci;
                 task(tk, type, o, d, ci);
                 if (type == 2) { if (hasint) lmn = fmin(lmn, fmin(fmin(S_[o], S_[o + NX]), fmin(Z[o], Z[o + NX]))); }

@@ -51,36 +51,12 @@ struct RocketQuat {
     static constexpr int MAXDIM = 4;
     static constexpr const char *name = "RocketQuat";
 
-    SCPP_HD static int cone_dim(int c) { const int d[NCONE] = {3, 3, 4, 4, 3}; return d[c]; }
-    SCPP_HD static int cone_off(int c) { const int o[NCONE] = {0, 3, 6, 10, 14}; return o[c]; }
+    SCPP_HD static int cone_dim(int c) { return (c == 2 || c == 3) ? 4 : 3; }                       // {3,3,4,4,3}
+    SCPP_HD static int cone_off(int c) { return 3 * c + (c > 2 ? 1 : 0) + (c > 3 ? 1 : 0); }         // {0,3,6,10,14}
 
     // rocketQuat.cpp:70-144 (exact_minimum_thrust handled through tdir: (0,0,1) reproduces T_z >= T_min, :125;
     // enable_roll_control == false: X.row(13)==0 and U.row(3)==0 become fixed variables, :141-142)
-    SCPP_HD static RowDesc row(int r)
-    {
-        const RowDesc t[NLP + NCR] = {
-            {1, {0, 0, 0}, {2, 0, 0}, 3},          // m_k - m_dry >= 0                          :93
-            {3, {14, 15, 16}, {-1, -2, -3}, 4},    // n_k' T_k - T_min >= 0                     :113-121
-            {1, {3, 0, 0}, {5, 0, 0}, 0},          // glide slope: tan(gamma) r_z               :96-97
-            {1, {1, 0, 0}, {2, 0, 0}, 0},
-            {1, {2, 0, 0}, {2, 0, 0}, 0},
-            {0, {0, 0, 0}, {0, 0, 0}, 6},          // tilt: sqrt((1-cos theta_max)/2)           :100-101
-            {1, {8, 0, 0}, {2, 0, 0}, 0},
-            {1, {9, 0, 0}, {2, 0, 0}, 0},
-            {0, {0, 0, 0}, {0, 0, 0}, 7},          // |w| <= w_B_max                            :104-105
-            {1, {11, 0, 0}, {2, 0, 0}, 0},
-            {1, {12, 0, 0}, {2, 0, 0}, 0},
-            {1, {13, 0, 0}, {2, 0, 0}, 0},
-            {0, {0, 0, 0}, {0, 0, 0}, 8},          // |T| <= T_max                              :129
-            {1, {14, 0, 0}, {2, 0, 0}, 0},
-            {1, {15, 0, 0}, {2, 0, 0}, 0},
-            {1, {16, 0, 0}, {2, 0, 0}, 0},
-            {1, {16, 0, 0}, {9, 0, 0}, 0},         // gimbal: tan(gimbal_max) T_z               :132-133
-            {1, {14, 0, 0}, {2, 0, 0}, 0},
-            {1, {15, 0, 0}, {2, 0, 0}, 0},
-        };
-        return t[r];
-    }
+    SCPP_HD static RowDesc row(int r);
 
     // ---- systemFlowMap for a generic scalar (rocketQuat.cpp:7-37); par = [alpha_m, g_I, J_B, r_T_B]
     template <class T>
@@ -277,17 +253,7 @@ struct Rocket2d {
     SCPP_HD static int cone_dim(int) { return 2; }
     SCPP_HD static int cone_off(int) { return 0; }
     // rocket2d.cpp:46-84
-    SCPP_HD static RowDesc row(int r)
-    {
-        const RowDesc t[NLP + NCR] = {
-            {1, {4, 0, 0}, {1, 0, 0}, 3}, {1, {4, 0, 0}, {2, 0, 0}, 3},    // |eta| <= theta_max          :66-68
-            {1, {5, 0, 0}, {1, 0, 0}, 4}, {1, {5, 0, 0}, {2, 0, 0}, 4},    // |w| <= w_B_max              :70-72
-            {1, {6, 0, 0}, {1, 0, 0}, 5}, {1, {6, 0, 0}, {2, 0, 0}, 5},    // |gimbal| <= gimbal_max      :76-78
-            {1, {7, 0, 0}, {2, 0, 0}, 6}, {1, {7, 0, 0}, {1, 0, 0}, 7},    // T_min <= T <= T_max         :80-82
-            {1, {1, 0, 0}, {8, 0, 0}, 0}, {1, {0, 0, 0}, {2, 0, 0}, 0},    // |r_x| <= tan(gamma) r_y     :63-64
-        };
-        return t[r];
-    }
+    SCPP_HD static RowDesc row(int r);
     // rocket2d.cpp:7-40 ; par = [m, J_B, g_I(2), r_T_B(2)]
     template <class T>
     SCPP_HD static void flow_map(const T *x, const T *u, const double *par, T *f)
@@ -375,5 +341,57 @@ struct Rocket2d {
     }
     SCPP_HD static void thrust_dir(const double *, double *d) { d[0] = 0.; d[1] = 0.; d[2] = 1.; }
 };
+
+// ---- constraint row tables (real constant data: a function-local table would be rebuilt on the stack at every call) ----
+#define SCPP_RQ_ROWS {                                                                                          \
+        {1, {0, 0, 0}, {2, 0, 0}, 3},          /* m_k - m_dry >= 0                          rocketQuat.cpp:93      */ \
+        {3, {14, 15, 16}, {-1, -2, -3}, 4},    /* n_k' T_k - T_min >= 0                     :113-121               */ \
+        {1, {3, 0, 0}, {5, 0, 0}, 0},          /* glide slope: tan(gamma) r_z               :96-97                 */ \
+        {1, {1, 0, 0}, {2, 0, 0}, 0},                                                                             \
+        {1, {2, 0, 0}, {2, 0, 0}, 0},                                                                             \
+        {0, {0, 0, 0}, {0, 0, 0}, 6},          /* tilt: sqrt((1-cos theta_max)/2)           :100-101               */ \
+        {1, {8, 0, 0}, {2, 0, 0}, 0},                                                                             \
+        {1, {9, 0, 0}, {2, 0, 0}, 0},                                                                             \
+        {0, {0, 0, 0}, {0, 0, 0}, 7},          /* |w| <= w_B_max                            :104-105               */ \
+        {1, {11, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {12, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {13, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {0, {0, 0, 0}, {0, 0, 0}, 8},          /* |T| <= T_max                              :129                   */ \
+        {1, {14, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {15, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {16, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {16, 0, 0}, {9, 0, 0}, 0},         /* gimbal: tan(gimbal_max) T_z               :132-133               */ \
+        {1, {14, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {15, 0, 0}, {2, 0, 0}, 0},                                                                            \
+    }
+#define SCPP_R2D_ROWS {                                                                                         \
+        {1, {4, 0, 0}, {1, 0, 0}, 3}, {1, {4, 0, 0}, {2, 0, 0}, 3},    /* |eta| <= theta_max          rocket2d.cpp:66-68 */ \
+        {1, {5, 0, 0}, {1, 0, 0}, 4}, {1, {5, 0, 0}, {2, 0, 0}, 4},    /* |w| <= w_B_max              :70-72 */ \
+        {1, {6, 0, 0}, {1, 0, 0}, 5}, {1, {6, 0, 0}, {2, 0, 0}, 5},    /* |gimbal| <= gimbal_max      :76-78 */ \
+        {1, {7, 0, 0}, {2, 0, 0}, 6}, {1, {7, 0, 0}, {1, 0, 0}, 7},    /* T_min <= T <= T_max         :80-82 */ \
+        {1, {1, 0, 0}, {8, 0, 0}, 0}, {1, {0, 0, 0}, {2, 0, 0}, 0},    /* |r_x| <= tan(gamma) r_y     :63-64 */ \
+    }
+static const RowDesc rq_rows_host[RocketQuat::NLP + RocketQuat::NCR] = SCPP_RQ_ROWS;
+static const RowDesc r2d_rows_host[Rocket2d::NLP + Rocket2d::NCR] = SCPP_R2D_ROWS;
+#if defined(__CUDACC__)
+static __constant__ RowDesc rq_rows_dev[RocketQuat::NLP + RocketQuat::NCR] = SCPP_RQ_ROWS;
+static __constant__ RowDesc r2d_rows_dev[Rocket2d::NLP + Rocket2d::NCR] = SCPP_R2D_ROWS;
+#endif
+SCPP_HD RowDesc RocketQuat::row(int r)
+{
+#if defined(__CUDA_ARCH__)
+    return rq_rows_dev[r];
+#else
+    return rq_rows_host[r];
+#endif
+}
+SCPP_HD RowDesc Rocket2d::row(int r)
+{
+#if defined(__CUDA_ARCH__)
+    return r2d_rows_dev[r];
+#else
+    return r2d_rows_host[r];
+#endif
+}
 
 } // namespace scpp

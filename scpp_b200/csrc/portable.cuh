@@ -34,6 +34,14 @@ SCPP_D double warp_max(double v)
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+SCPP_D void warp_sum3(double &a, double &b, double &c)   // three interleaved butterfly reductions (one latency chain)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o), tc = __shfl_xor_sync(0xffffffffu, c, o);
+        a += ta; b += tb; c += tc;
+    }
+}
 SCPP_D int warp_or(int v) { return __any_sync(0xffffffffu, v); }
 SCPP_D double warp_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 #else
@@ -42,6 +50,7 @@ inline int lane_id() { return 0; }
 inline void warp_sync() {}
 inline double warp_sum(double v) { return v; }
 inline double warp_max(double v) { return v; }
+inline void warp_sum3(double &, double &, double &) {}
 inline int warp_or(int v) { return v; }
 inline double warp_bcast(double v, int) { return v; }
 #endif
