@@ -162,6 +162,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU path)")
 
     model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=args.K)
+    if os.environ.get("SCPP_WARM"):
+        cfg.ipm.warm = float(os.environ["SCPP_WARM"])      # experimental: blended interior-point warm start
     rpy = np.deg2rad([-20.0, 20.0, 0.0])      # rpy_init of configs/RocketQuat/model.info
     n_local = args.batch
     xi = S.perturbed_initial_states(x_init, rpy, n_local, first=rank * n_local)
@@ -245,7 +247,7 @@ def main():
                                        f"(reference Monte-Carlo recipe, seed 0x5C99), max_iterations={cfg.max_iterations}",
                            "batch_per_gpu": n_local, "global_batch": n_local * world, "K": args.K, "parallelism": f"instances sharded x{world}",
                            "l2": f"working set {eng.device_bytes() / 1e6:.0f} MB per GPU >> 126 MB L2 (no flush needed)",
-                           "integrator": f"RK4 x {cfg.nsub} (reference RKF78 x 5)", "ipm_tol": cfg.ipm.feastol},
+                           "integrator": f"RK4 x {cfg.nsub} (reference RKF78 x 5)", "ipm_tol": cfg.ipm.feastol, "ipm_warm": cfg.ipm.warm},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "ms_per_step": 1e3 * stats[1] / args.steps},
                 "gpu_launches": int(sums[2]),

@@ -25,7 +25,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) return fail(SCPP_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-constexpr int WPB = 4;   // warps (= problem instances) per CTA of the SOCP kernel
+constexpr int WPB = 5;   // warps (= problem instances) per CTA of the SOCP kernel
 
 // ------------------------------------------------------------------------------------------------------------------
 // kernels

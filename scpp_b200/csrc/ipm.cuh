@@ -35,6 +35,9 @@ namespace scpp {
 struct IpmSettings {
     double feastol, abstol, reltol;
     int maxit;
+    int pad_;
+    double warm;     // 0: cold start every solve (ECOS behaviour); 0 < warm < 1: blend the cold starting point with the previous
+                     // sub-problem's final interior point (weight `warm` on the previous point)
 };
 
 struct IpmResult {
@@ -62,9 +65,10 @@ SCPP_OUTLINE bool scale(const double *sk, const double *zk, int d, double *w, do
     for (int i = 0; i < d; i++) sz += sk[i] * zk[i];
     double gam = sqrt((1. + sz / (sn * zn)) / 2.);
     double i2g = 1. / (2. * gam);
-    w[0] = (sk[0] / sn + zk[0] / zn) * i2g;
+    const double isn = i2g / sn, izn = i2g / zn;
+    w[0] = sk[0] * isn + zk[0] * izn;
 #pragma unroll 1
-    for (int i = 1; i < d; i++) w[i] = (sk[i] / sn - zk[i] / zn) * i2g;
+    for (int i = 1; i < d; i++) w[i] = sk[i] * isn - zk[i] * izn;
     e2i = zn / sn;
     double eta = sqrt(sn / zn), w1z1 = 0;
 #pragma unroll 1
@@ -114,22 +118,22 @@ SCPP_OUTLINE void jdiv(const double *lm, const double *dv, int d, double *o)   /
     double den = jn2(lm, d), l1d1 = 0;
 #pragma unroll 1
     for (int i = 1; i < d; i++) l1d1 += lm[i] * dv[i];
-    const double x0 = (lm[0] * dv[0] - l1d1) / den;
+    const double x0 = (lm[0] * dv[0] - l1d1) / den, il0 = 1. / lm[0];
 #pragma unroll 1
-    for (int i = 1; i < d; i++) o[i] = (dv[i] - x0 * lm[i]) / lm[0];
+    for (int i = 1; i < d; i++) o[i] = (dv[i] - x0 * lm[i]) * il0;
     o[0] = x0;
 }
 SCPP_OUTLINE double step(const double *lm, const double *dk, int d)
 {
-    const double a = sqrt(jn2(lm, d)), l0 = lm[0] / a;
+    const double ia = 1. / sqrt(jn2(lm, d)), l0 = lm[0] * ia;
     double ld = l0 * dk[0];
 #pragma unroll 1
-    for (int i = 1; i < d; i++) ld -= lm[i] / a * dk[i];
-    const double rho0 = ld / a, f = (ld + dk[0]) / (l0 + 1.);
+    for (int i = 1; i < d; i++) ld -= lm[i] * ia * dk[i];
+    const double rho0 = ld * ia, f = (ld + dk[0]) / (l0 + 1.) * ia;
     double n1 = 0;
 #pragma unroll 1
-    for (int i = 1; i < d; i++) { double r = (dk[i] - f * lm[i] / a) / a; n1 += r * r; }
-    return sqrt(n1) - rho0;
+    for (int i = 1; i < d; i++) { const double r = dk[i] - f * lm[i]; n1 += r * r; }
+    return sqrt(n1) * ia - rho0;
 }
 } // namespace soc
 
@@ -152,18 +156,22 @@ struct Ipm {
     static constexpr int CS = pad2(NCN);            // eta^-2 per cone of one stage
     static constexpr int FS = pad2(2 * BLK + 2 * NB);   // Linv_kk | L_{k+1,k} | l_k | f_k
     static constexpr int OFF_LN = BLK, OFF_L = 2 * BLK, OFF_F = 2 * BLK + NB;
-    static_assert(NB % 2 == 0 && NC % 2 == 0, "16-byte record alignment needs even nx+nu and even tile width");
+    static_assert(NB % 2 == 0 && NC % 2 == 0 && NX % 2 == 0, "16-byte record alignment needs even nx, nx+nu and tile width");
 
     SCPP_HD static int m_rows(int K) { return K * RS + 4; }
     SCPP_HD static int n_prim(int K) { return K * PS + 2; }
     SCPP_HD static int n_ce(int K) { return K * CS + 2; }
-    SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 8 * m_rows(K) + n_ce(K) + K * FS + 16; }
-    // shared window: tile | factor record | L_{k,k-1} carry | UNION{ 8 row arrays + primal windows ; phase F: wb + H,O,Hn + model terms }
-    //                | vectors | scalars
+    SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 9 * m_rows(K) + n_ce(K) + K * FS + 16; }
+    // shared window: tile | factor record | L_{k,k-1} carry | UNION{ 8 row arrays + primal windows ; phase F: wb + H,O + model terms }
+    //                | compact carry of interval k-1 | vectors | scalars | per-stage row coefficients, reverse map, constants
+    static constexpr int NROW = NLP + NCR;
+    static constexpr int HNC = pad2(NX + NX * NU + NU * NU);      // D | D C | C' D C  of the previous interval
     static constexpr int W_DD = 0, W_FAC = W_DD + pad2(NX * NCP), W_LP = W_FAC + FS, W_ROW = W_LP + BLK, W_PRIM = W_ROW + 8 * RS,
-                         W_MAT = W_ROW + RS, W_RK = W_MAT + 3 * BLK,
+                         W_MAT = W_ROW + RS, W_RK = W_MAT + 2 * BLK,
                          W_UEND = (W_PRIM + 4 * PS + pad2(NB)) > (W_RK + 2 * NRK * NB) ? (W_PRIM + 4 * PS + pad2(NB)) : (W_RK + 2 * NRK * NB),
-                         W_VEC = W_UEND, W_X = W_VEC + 6 * NB, W_SC = W_X + 2 * pad2(NX), W_END = W_SC + 32;
+                         W_HN = W_UEND, W_VEC = W_HN + HNC, W_X = W_VEC + 6 * NB, W_SC = W_X + 2 * pad2(NX),
+                         W_RCQ = W_SC + 32, W_RIDX = W_RCQ + 4 * NROW, W_REV = W_RIDX + pad2(2 * NROW), W_CST = W_REV + pad2(2 * NB),
+                         W_END = W_CST + pad2(MAX_CST + 4);
     SCPP_HD static int sm_doubles() { return W_END; }
 
     // ---- problem data (read only) -----------------------------------------------------------------------------
@@ -179,7 +187,7 @@ struct Ipm {
     double w_time, w_trs, w_tr, w_vc;
     // ---- workspace (global memory, per instance, stage-major) ---------------------------------------------------
     double *prim, *dprim, *rx, *best_;
-    double *s, *z, *wb, *lam, *rz, *cr, *dz, *ds;
+    double *s, *z, *wb, *lam, *rz, *cr, *dz, *ds, *zprev;
     double *ce;
     double *fac;
     double *sm;            // per-warp shared window
@@ -190,7 +198,7 @@ struct Ipm {
         const int np = n_prim(K), m = m_rows(K);
         double *p = ws;
         prim = p; p += np; dprim = p; p += np; rx = p; p += np; best_ = p; p += np;
-        s = p; p += m; z = p; p += m; wb = p; p += m; lam = p; p += m; rz = p; p += m; cr = p; p += m; dz = p; p += m; ds = p; p += m;
+        s = p; p += m; z = p; p += m; wb = p; p += m; lam = p; p += m; rz = p; p += m; cr = p; p += m; dz = p; p += m; ds = p; p += m; zprev = p; p += m;
         ce = p; p += n_ce(K);
         fac = p;
         sm = smem;
@@ -257,15 +265,63 @@ struct Ipm {
         else if (tk < NCN + NLP) { type = 0; o = tk - NCN; d = 1; ci = -1; }
         else { type = 2; o = MN + (tk - NCN - NLP); d = 1; ci = -1; }
     }
-    SCPP_HD double coef(const RowDesc &rd, int j, int k) const { return rd.cs[j] >= 0 ? cst[rd.cs[j]] : -tdir[3 * k + (-rd.cs[j] - 1)]; }
-
+    // per-stage row coefficients in shared memory: RCQ[r][0..2] = coefficients, RCQ[r][3] = h ; RIDX[r][q] = variable index
+    // (or -1); REV[j][t] = (row*4+q) of the up-to-3 entries that touch variable j (or -1).  CST = per-instance constants.
+    SCPP_HD double *rcq() const { return sm + W_RCQ; }
+    SCPP_HD int *ridx() const { return reinterpret_cast<int *>(sm + W_RIDX); }
+    SCPP_HD int *rev() const { return reinterpret_cast<int *>(sm + W_REV); }
+    SCPP_HD double *cstw() const { return sm + W_CST; }
+    // once per solve: constants, index table, reverse map and the k-independent coefficients
+    SCPP_HD void tables_init() const
+    {
+        FOR_LANE(i, MAX_CST) cstw()[i] = cst[i];
+        warp_sync();
+        FOR_LANE(r, NROW) {
+            const RowDesc rd = M::row(r);
+            for (int q = 0; q < 4; q++) ridx()[r * 4 + q] = (q < rd.n) ? rd.idx[q] : -1;
+            for (int q = 0; q < 3; q++) rcq()[r * 4 + q] = (q < rd.n && rd.cs[q] >= 0) ? cstw()[rd.cs[q]] : 0.;
+            rcq()[r * 4 + 3] = cstw()[rd.hs];
+        }
+        FOR_LANE(j, NB) {
+            int n = 0;
+            for (int t = 0; t < 4; t++) rev()[j * 4 + t] = -1;
+            for (int r = 0; r < NROW; r++) { const RowDesc rd = M::row(r); for (int q = 0; q < rd.n; q++) if (rd.idx[q] == j && n < 4) rev()[j * 4 + n++] = r * 4 + q; }
+        }
+        warp_sync();
+    }
+    // once per stage: only the linearised minimum-thrust row depends on k (coefficient slots < 0 take -tdir[k])
+    SCPP_HD void tables_stage(int k) const
+    {
+        FOR_LANE(e, NROW * 3) {
+            const int r = e / 3, q = e - 3 * r;
+            const RowDesc rd = M::row(r);
+            if (q < rd.n && rd.cs[q] < 0) rcq()[r * 4 + q] = -tdir[3 * k + (-rd.cs[q] - 1)];
+        }
+    }
+    SCPP_HD double row_h(int r) const { return rcq()[r * 4 + 3]; }
+    // gather of the model-row contributions G' v onto variable j of the node
+    SCPP_HD double model_GT(int j, int, const double *v /* node rows window */) const
+    {
+        double a = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) { const int e = rev()[j * 4 + t]; if (e >= 0) a += rcq()[e] * v[e >> 2]; }
+        return a;
+    }
+    SCPP_HD double model_G(int r, int, const double *x) const   // (G x)_r for a model row
+    {
+        double a = 0;
+#pragma unroll
+        for (int q = 0; q < 3; q++) { const int i = ridx()[r * 4 + q]; if (i >= 0) a += rcq()[r * 4 + q] * x[i]; }
+        return a;
+    }
     // r_i = x_{k+1,i} - (A~ xi_k)_i - (C u_{k+1})_i - s_i sigma [- z_i]   from windows (tile staged)
     SCPP_HD double dyn_row(int i, const double *xk, const double *xn, double sg, bool with_const) const
     {
         const double *t = tile() + i * NCP;
-        double acc = xn[i];
-#pragma unroll 1
-        for (int j = 0; j < NB; j++) acc -= t[j] * xk[j];
+        double acc = xn[i], acc2 = 0;
+#pragma unroll 3
+        for (int j = 0; j < NB; j += 2) { acc -= t[j] * xk[j]; acc2 -= t[j + 1] * xk[j + 1]; }
+        acc += acc2;
 #pragma unroll 1
         for (int j = 0; j < NU; j++) acc -= t[NB + j] * xn[NX + j];
         acc -= t[NB + NU] * sg;
@@ -277,13 +333,13 @@ struct Ipm {
     {
         const double *t = tile();
         FOR_LANE(j, NB) {
-            double a = 0, c = 0;
-#pragma unroll 1
-            for (int i = 0; i < NX; i++) a += t[i * NCP + j] * w[i];
-            out_k[j] -= a;
+            double a = 0, a2 = 0, c = 0;
+#pragma unroll 7
+            for (int i = 0; i < NX; i += 2) { a += t[i * NCP + j] * w[i]; a2 += t[(i + 1) * NCP + j] * w[i + 1]; }
+            out_k[j] -= a + a2;
             if (j < NX) c = w[j];
             else {
-#pragma unroll 1
+#pragma unroll 7
                 for (int i = 0; i < NX; i++) c -= t[i * NCP + NB + (j - NX)] * w[i];
             }
             carry[j] = c;
@@ -291,26 +347,6 @@ struct Ipm {
         double sg = 0;
         FOR_LANE(i, NX) sg -= t[i * NCP + NB + NU] * w[i];
         return sg;
-    }
-    // gather of the model-row contributions G' v onto variable j of the node (generic: scans the row table)
-    SCPP_HD double model_GT(int j, int k, const double *v /* node rows window */) const
-    {
-        double a = 0;
-#pragma unroll 1
-        for (int r = 0; r < NLP + NCR; r++) {
-            const RowDesc rd = M::row(r);
-#pragma unroll 1
-            for (int q = 0; q < rd.n; q++) if (rd.idx[q] == j) a += coef(rd, q, k) * v[r];
-        }
-        return a;
-    }
-    SCPP_HD double model_G(int r, int k, const double *x) const   // (G x)_r for a model row
-    {
-        const RowDesc rd = M::row(r);
-        double a = 0;
-#pragma unroll 1
-        for (int q = 0; q < rd.n; q++) a += coef(rd, q, k) * x[rd.idx[q]];
-        return a;
     }
     SCPP_HD void load_xibar(int k, double *dst) const
     {
@@ -331,10 +367,11 @@ struct Ipm {
         if (!(ss > 0.) || !(zz > 0.) || !(s0 > 0.) || !(z0 > 0.)) return false;
         const double sn = sqrt(ss), zn = sqrt(zz);
         const double i2g = 1. / (2. * sqrt((1. + c / (sn * zn)) / 2.));
-        const double w0 = (s0 / sn + z0 / zn) * i2g;
+        const double isn = i2g / sn, izn = i2g / zn;
+        const double w0 = s0 * isn + z0 * izn;
         double w1z1 = 0;
         warp_sync();
-        FOR_LANE(i, D) { const double wi = (i == 0) ? w0 : (sk[i] / sn - zk[i] / zn) * i2g; if (i > 0) w1z1 += wi * zk[i]; w[i] = wi; }
+        FOR_LANE(i, D) { const double wi = (i == 0) ? w0 : sk[i] * isn - zk[i] * izn; if (i > 0) w1z1 += wi * zk[i]; w[i] = wi; }
         w1z1 = warp_sum(w1z1);
         e2i = zn / sn;
         const double eta = sqrt(sn / zn), f = z0 + w1z1 / (1. + w0);
@@ -369,13 +406,14 @@ struct Ipm {
         double l1 = 0, a1 = 0, a2 = 0;
         FOR_LANE(i, D) if (i > 0) { l1 += lm[i] * lm[i]; a1 += lm[i] * d1[i]; a2 += lm[i] * d2[i]; }
         warp_sum3(l1, a1, a2);
-        const double a = sqrt(lm[0] * lm[0] - l1), l0 = lm[0] / a;
-        const double ld1 = l0 * d1[0] - a1 / a, ld2 = l0 * d2[0] - a2 / a;
-        const double f1 = (ld1 + d1[0]) / (l0 + 1.), f2 = (ld2 + d2[0]) / (l0 + 1.);
+        const double ia = 1. / sqrt(lm[0] * lm[0] - l1), l0 = lm[0] * ia;
+        const double ld1 = l0 * d1[0] - a1 * ia, ld2 = l0 * d2[0] - a2 * ia;
+        const double il = ia / (l0 + 1.);
+        const double f1 = (ld1 + d1[0]) * il, f2 = (ld2 + d2[0]) * il;
         double n1 = 0, n2 = 0, dummy = 0;
-        FOR_LANE(i, D) if (i > 0) { const double r1 = (d1[i] - f1 * lm[i] / a) / a, r2 = (d2[i] - f2 * lm[i] / a) / a; n1 += r1 * r1; n2 += r2 * r2; }
+        FOR_LANE(i, D) if (i > 0) { const double r1 = d1[i] - f1 * lm[i], r2 = d2[i] - f2 * lm[i]; n1 += r1 * r1; n2 += r2 * r2; }
         warp_sum3(n1, n2, dummy);
-        return fmax(sqrt(n1) - ld1 / a, sqrt(n2) - ld2 / a);
+        return fmax((sqrt(n1) - ld1) * ia, (sqrt(n2) - ld2) * ia);
     }
     SCPP_HD void tr_jprod(const double *u, const double *v, double *o) const
     {
@@ -408,6 +446,7 @@ struct Ipm {
             if (hasint) { ld_dd(k); ld(PNX, prim + (k + 1) * PS, PS); }
             ld(S, s + k * RS, RS); ld(Z, z + k * RS, RS); ld(P, prim + k * PS, PS);
             load_xibar(k, XB);
+            tables_stage(k);
             ld_wait();
             // ---- trust-region cone: warp-cooperative
             {
@@ -433,17 +472,17 @@ struct Ipm {
                 task(tk, type, o, d, ci);
                 if (type == 1) {
 #pragma unroll 1
-                    for (int r = 0; r < d; r++) { const RowDesc rd = M::row(o + r); const double sl = cst[rd.hs] - model_G(o + r, k, P); RZ[o + r] = S[o + r] - sl; h2 += cst[rd.hs] * cst[rd.hs]; }
+                    for (int r = 0; r < d; r++) { const double hh = row_h(o + r); const double sl = hh - model_G(o + r, k, P); RZ[o + r] = S[o + r] - sl; h2 += hh * hh; }
                     if (identity) { CE[ci] = 1.; for (int i = 0; i < d; i++) { WB[o + i] = i == 0; LM[o + i] = i == 0; } }
                     else if (!soc::scale(S + o, Z + o, d, WB + o, CE[ci], LM + o)) bad = 1;
 #pragma unroll 1
                     for (int r = 0; r < d; r++) { gap += S[o + r] * Z[o + r]; rz2 += RZ[o + r] * RZ[o + r]; zrz += Z[o + r] * RZ[o + r]; }
                 } else if (type == 0) {
-                    const RowDesc rd = M::row(o);
-                    const double sl = cst[rd.hs] - model_G(o, k, P);
+                    const double hh = row_h(o);
+                    const double sl = hh - model_G(o, k, P);
                     const double sv = S[o], zv = Z[o];
                     RZ[o] = sv - sl;
-                    h2 += cst[rd.hs] * cst[rd.hs];
+                    h2 += hh * hh;
                     if (!(sv > 0.) || !(zv > 0.)) bad = 1;
                     WB[o] = identity ? 1. : zv / sv; LM[o] = identity ? 1. : sqrt(sv * zv);
                     gap += sv * zv; rz2 += RZ[o] * RZ[o]; zrz += zv * RZ[o];
@@ -528,13 +567,11 @@ struct Ipm {
                 const double e2i = CE[c];
 #pragma unroll 1
                 for (int r = 0; r < dim; r++) {
-                    const RowDesc rd = M::row(o + r);
                     const double wh = (r == 0) ? WB[o] : -WB[o + r];
-#pragma unroll 1
-                    for (int j = 0; j < rd.n; j++) {
-                        const double cf = coef(rd, j, k);
-                        a[rd.idx[j]] += wh * cf;
-                        d[rd.idx[j]] += (r == 0 ? -e2i : e2i) * cf * cf;    // -J_rr g g' (single-entry rows)
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        const int i = ridx()[(o + r) * 4 + q];
+                        if (i >= 0) { const double cf = rcq()[(o + r) * 4 + q]; a[i] += wh * cf; d[i] += (r == 0 ? -e2i : e2i) * cf * cf; }   // -J_rr g g' (single-entry rows)
                     }
                 }
                 alpha[c] = 2. * e2i;
@@ -542,10 +579,9 @@ struct Ipm {
                 double al = 0.;
 #pragma unroll 1
                 for (int r = 0; r < NLP; r++) {
-                    const RowDesc rd = M::row(r);
                     const double dv = WB[r];
-                    if (rd.n == 1) { const double cf = coef(rd, 0, k); d[rd.idx[0]] += dv * cf * cf; }
-                    else { for (int j = 0; j < rd.n; j++) a[rd.idx[j]] = coef(rd, j, k); al = dv; }
+                    if (ridx()[r * 4 + 1] < 0) { const double cf = rcq()[r * 4]; d[ridx()[r * 4]] += dv * cf * cf; }
+                    else { for (int q = 0; q < 3; q++) { const int i = ridx()[r * 4 + q]; if (i >= 0) a[i] = rcq()[r * 4 + q]; } al = dv; }
                 }
                 alpha[c] = al;
             }
@@ -555,7 +591,8 @@ struct Ipm {
 
     SCPP_HD bool phase_factor()
     {
-        double *H = sm + W_MAT, *O = H + BLK, *Hn = O + BLK, *Lp = sm + W_LP;
+        double *H = sm + W_MAT, *O = H + BLK, *Lp = sm + W_LP;
+        double *Dp = sm + W_HN, *DCp = Dp + NX, *CDCp = DCp + NX * NU;   // carry of interval k-1: D | D C | C' D C
         double *F = facw();                 // Linv | Lnext | l | f   (the record written for this stage)
         double *Li = F, *Ln = F + OFF_LN, *lk = F + OFF_L;
         double *WB = row(0), *CE = sc() + 8, *alpha = sc();
@@ -563,7 +600,8 @@ struct Ipm {
         double *Dt = xv(1);
         double corner = 0.;
         int bad = 0;
-        FOR_LANE(e, BLK) { Hn[e] = 0.; Lp[e] = 0.; }
+        FOR_LANE(e, BLK) Lp[e] = 0.;
+        FOR_LANE(e, HNC) Dp[e] = 0.;
         FOR_LANE(j, NB) { bn[j] = 0.; lprev[j] = 0.; }
         warp_sync();
 #pragma unroll 1
@@ -571,6 +609,7 @@ struct Ipm {
             const bool hasint = k < K - 1;
             if (hasint) ld_dd(k);
             ld(WB, wb + k * RS, RS); ld(CE, ce + k * CS, CS);
+            tables_stage(k);
             ld_wait();
             build_model_terms(k, WB, CE, alpha);
             // ---- node part of H_kk (trust region with delta eliminated) + carry from interval k-1
@@ -578,52 +617,59 @@ struct Ipm {
                 const double *rk = sm + W_RK, *dg = rk + NRK * NB;
                 const double *wt_ = WB + TRO;
                 const double e2i = CE[NCONE], w0 = wt_[0];
-                const double kap = e2i * (2. * w0 * w0 - 1.);
+                const double kap = e2i * (2. * w0 * w0 - 1.), c2 = 4. * e2i * e2i * w0 * w0 / kap;
+#pragma unroll 2
                 FOR_LANE(e, BLK) {
                     const int i = e / NB, j = e - i * NB;
-                    double v = Hn[e];
+                    double v;
+                    if (i < NX && j < NX) v = (i == j) ? Dp[i] : 0.;
+                    else if (i < NX) v = -DCp[i * NU + (j - NX)];
+                    else if (j < NX) v = -DCp[j * NU + (i - NX)];
+                    else v = CDCp[(i - NX) * NU + (j - NX)];
 #pragma unroll
                     for (int c = 0; c < NRK; c++) v += alpha[c] * rk[c * NB + i] * rk[c * NB + j];
                     if (i == j) {
 #pragma unroll
                         for (int c = 0; c < NRK; c++) v += dg[c * NB + i];
+                        v += e2i;
                     }
-                    const double wi = wt_[1 + i], wj = wt_[1 + j];
-                    v += e2i * ((i == j ? 1. : 0.) + 2. * wi * wj) - (e2i * 2. * w0 * wi) * (e2i * 2. * w0 * wj) / kap;
+                    v += (2. * e2i - c2) * wt_[1 + i] * wt_[1 + j];
                     H[e] = v;
                 }
                 FOR_LANE(j, NB) bk[j] = bn[j];
             }
             warp_sync();
-            // ---- interval k: H_kk += A~' D A~ ; O = [-D A~ ; C' D A~] ; Hn = [[D, -D C],[-C' D, C' D C]] ; borders
+            // ---- interval k: H_kk += A~' D A~ ; O = [-D A~ ; C' D A~] ; carry = (D, D C, C' D C) ; borders
             if (hasint) {
-                const double *t = tile();
+                double *t = tile();
                 FOR_LANE(i, NX) { const double dm = WB[MN + i], dp = WB[MN + NX + i]; Dt[i] = 4. * dm * dp / (dm + dp); }
                 warp_sync();
-                FOR_LANE(e, BLK) {
+                // O rows of the x_{k+1} block are -D A~ ; keep D A~ for the products: O[a][b], a < NX
+                FOR_LANE(e, NX * NB) { const int a = e / NB, b = e - a * NB; O[a * NB + b] = -Dt[a] * t[a * NCP + b]; }
+                FOR_LANE(e, NX * NU) { const int i = e / NU, j = e - i * NU; DCp[e] = Dt[i] * t[i * NCP + NB + j]; }
+                FOR_LANE(i, NX) Dp[i] = Dt[i];
+                warp_sync();
+#pragma unroll 2
+                FOR_LANE(e, BLK) {       // H += A~' (D A~) = -A~' O_x
                     const int a = e / NB, b = e - a * NB;
                     double v = 0;
 #pragma unroll 2
-                    for (int i = 0; i < NX; i++) v += t[i * NCP + a] * Dt[i] * t[i * NCP + b];
+                    for (int i = 0; i < NX; i++) v -= t[i * NCP + a] * O[i * NB + b];
                     H[e] += v;
-                    double o;
-                    if (a < NX) o = -Dt[a] * t[a * NCP + b];
-                    else {
-                        o = 0;
+                }
+                FOR_LANE(e, NU * NB) {   // O rows of the u_{k+1} block: C' D A~ = -C' O_x
+                    const int a = e / NB, b = e - a * NB;
+                    double v = 0;
 #pragma unroll 2
-                        for (int i = 0; i < NX; i++) o += t[i * NCP + NB + (a - NX)] * Dt[i] * t[i * NCP + b];
-                    }
-                    O[e] = o;
-                    double hn;
-                    if (a < NX && b < NX) hn = (a == b) ? Dt[a] : 0.;
-                    else if (a < NX) hn = -Dt[a] * t[a * NCP + NB + (b - NX)];
-                    else if (b < NX) hn = -Dt[b] * t[b * NCP + NB + (a - NX)];
-                    else {
-                        hn = 0;
+                    for (int i = 0; i < NX; i++) v -= t[i * NCP + NB + a] * O[i * NB + b];
+                    O[(NX + a) * NB + b] = v;
+                }
+                FOR_LANE(e, NU * NU) {
+                    const int a = e / NU, b = e - a * NU;
+                    double v = 0;
 #pragma unroll 2
-                        for (int i = 0; i < NX; i++) hn += t[i * NCP + NB + (a - NX)] * Dt[i] * t[i * NCP + NB + (b - NX)];
-                    }
-                    Hn[e] = hn;
+                    for (int i = 0; i < NX; i++) v += t[i * NCP + NB + a] * DCp[i * NU + b];
+                    CDCp[e] = v;
                 }
                 FOR_LANE(j, NB) {
                     double v = 0, vn;
@@ -656,13 +702,14 @@ struct Ipm {
             warp_sync();
             // ---- Schur update with the previous off-diagonal factor: H -= Lp Lp' ; bk -= Lp lprev
             if (k > 0) {
+#pragma unroll 2
                 FOR_LANE(e, BLK) {
                     const int a = e / NB, b = e - a * NB;
                     if (b <= a) {
-                        double v = 0;
+                        double v0 = 0, v1 = 0;
 #pragma unroll 2
-                        for (int c = 0; c < NB; c++) v += Lp[a * NB + c] * Lp[b * NB + c];
-                        H[e] -= v;
+                        for (int c = 0; c < NB; c += 2) { v0 += Lp[a * NB + c] * Lp[b * NB + c]; v1 += Lp[a * NB + c + 1] * Lp[b * NB + c + 1]; }
+                        H[e] -= v0 + v1;
                     }
                 }
                 FOR_LANE(j, NB) {
@@ -673,20 +720,23 @@ struct Ipm {
                 }
             }
             warp_sync();
-            // ---- Cholesky of H (lower, in place), column by column
+            // ---- Cholesky of H (lower, in place), left-looking by columns: lane i owns row i
 #pragma unroll 1
             for (int j = 0; j < NB; j++) {
+                FOR_LANE(i, NB) if (i >= j) {
+                    double v0 = H[i * NB + j], v1 = 0;
+                    int c = 0;
+#pragma unroll 1
+                    for (; c + 1 < j; c += 2) { v0 -= H[i * NB + c] * H[j * NB + c]; v1 -= H[i * NB + c + 1] * H[j * NB + c + 1]; }
+                    if (c < j) v0 -= H[i * NB + c] * H[j * NB + c];
+                    H[i * NB + j] = v0 + v1;         // unscaled column j (row j reads only columns < j of itself)
+                }
+                warp_sync();
                 const double djj = H[j * NB + j];
                 if (!(djj > 0.)) bad = 1;
                 const double inv = 1. / sqrt(djj > 0. ? djj : 1.);
                 warp_sync();
                 FOR_LANE(i, NB) if (i >= j) H[i * NB + j] *= inv;
-                warp_sync();
-                const int rem = NB - 1 - j;
-                FOR_LANE(e, rem * rem) {
-                    const int a = j + 1 + e / rem, b = j + 1 + e % rem;
-                    if (b <= a) H[a * NB + b] -= H[a * NB + j] * H[b * NB + j];
-                }
                 warp_sync();
             }
             // ---- Linv = L^-1 (lower): lane per column
@@ -702,12 +752,15 @@ struct Ipm {
             }
             warp_sync();
             // ---- L_{k+1,k} = O Linv' ;  l_k = Linv bk ; corner -= l_k' l_k
+#pragma unroll 2
             FOR_LANE(e, BLK) {
                 const int a = e / NB, b = e - a * NB;
-                double v = 0;
+                double v0 = 0, v1 = 0;
+                int c = 0;
 #pragma unroll 1
-                for (int c = 0; c <= b; c++) v += O[a * NB + c] * Li[b * NB + c];
-                Ln[e] = v;
+                for (; c + 1 <= b; c += 2) { v0 += O[a * NB + c] * Li[b * NB + c]; v1 += O[a * NB + c + 1] * Li[b * NB + c + 1]; }
+                if (c <= b) v0 += O[a * NB + c] * Li[b * NB + c];
+                Ln[e] = v0 + v1;
             }
             FOR_LANE(j, NB) {
                 double v = 0;
@@ -827,6 +880,7 @@ struct Ipm {
                 if (mode == 1) ld(S_, s + k * RS, RS);
                 else { ld(LM, lam + k * RS, RS); ld(CR, cr + k * RS, RS); }
             }
+            tables_stage(k);
             ld_wait();
             if (mode != 0) { gen_rhs(mode, hasint, csig, sigmu, RZV, RXV, V, S_, RZ, LM, CR, WB, CE, RXW); warp_sync(); }
             // ---- v_c = Mtilde rzv per cone; pairs produce w_i
@@ -926,6 +980,7 @@ struct Ipm {
             ld(WB, wb + k * RS, RS); ld(CE, ce + k * CS, CS); ld(RZV, ds + k * RS, RS);
             if (mode == 0) ld(RXV, dprim + k * PS, PS);
             else { ld(RXW, rx + k * PS, PS); ld(RZ, rz + k * RS, RS); ld(LM, lam + k * RS, RS); }
+            tables_stage(k);
             ld_wait();
             if (mode != 0) { FOR_LANE(e, PS) RXV[e] = (mode == 1 ? -1. : -csig) * RXW[e]; }
             // back substitution: y_k = Linv' (f_k - L_{k+1,k}' y_{k+1} - l_k y_sigma)
@@ -998,9 +1053,9 @@ struct Ipm {
                     DZ[o] = WB[o] * (gdx - RZV[o]);
                     if (mode != 0) {
                         DS[o] = rzs * RZ[o] - gdx;
-                        const double wv = sqrt(1. / WB[o]);
-                        const double dzt = wv * DZ[o], dst = DS[o] / wv;
-                        tmax = fmax(tmax, fmax(-dst / LM[o], -dzt / LM[o]));
+                        const double iw = sqrt(WB[o]), il = 1. / LM[o];      // W = 1/sqrt(wb)
+                        const double dzt = DZ[o] / iw, dst = DS[o] * iw;
+                        tmax = fmax(tmax, fmax(-dst, -dzt) * il);
                         if (mode == 1) CR[o] = dst * dzt;
                     }
                 } else if (hasint) {
@@ -1015,9 +1070,9 @@ struct Ipm {
                         DS[o] = rzs * RZ[o] - (ady - dt); DS[o + NX] = rzs * RZ[o + NX] - (-ady - dt);
                         for (int q = 0; q < 2; q++) {
                             const int oo = o + q * NX;
-                            const double wv = sqrt(1. / WB[oo]);
-                            const double dzt = wv * DZ[oo], dst = DS[oo] / wv;
-                            tmax = fmax(tmax, fmax(-dst / LM[oo], -dzt / LM[oo]));
+                            const double iw = sqrt(WB[oo]), il = 1. / LM[oo];
+                            const double dzt = DZ[oo] / iw, dst = DS[oo] * iw;
+                            tmax = fmax(tmax, fmax(-dst, -dzt) * il);
                             if (mode == 1) CR[oo] = dst * dzt;
                         }
                     }
@@ -1077,10 +1132,11 @@ struct Ipm {
             if (hasint) { ld_dd(k); ld(PNX, prim + (k + 1) * PS, PS); }
             ld(P, prim + k * PS, PS);
             load_xibar(k, XB);
+            tables_stage(k);
             ld_wait();
             FOR_LANE(r, RS) {
                 double v = 0.;
-                if (r < NLP + NCR) v = cst[M::row(r).hs] - model_G(r, k, P);
+                if (r < NLP + NCR) v = row_h(r) - model_G(r, k, P);
                 else if (r == TRO) v = P[NB];
                 else if (r < MN) v = XB[r - TRO - 1] - P[r - TRO - 1];
                 else if (r < MN + 2 * NX && hasint) {
@@ -1124,11 +1180,13 @@ struct Ipm {
     }
     SCPP_HD void cone_shift(double *u, double a) const { for_cones([&](int o, int) { u[o] += a; }); }
 
-    // prim += a dprim ; s += a ds ; z += a dz ; returns the minimum cone margin of the new (s,z)
-    SCPP_HD double apply_step(double a)
+    // prim += a dprim ; s += a ds ; z += a dz.  The step length keeps every cone 1 % inside in exact arithmetic; a cone whose
+    // margin u0 - |u1| is lost to rounding (active to ~1e-16 relative) is nudged back inside by a few ulps of u0 so the next
+    // Nesterov-Todd scaling stays defined (perturbation << the 1e-8 tolerances).
+    SCPP_HD static double nudge(double u0, double n1) { const double thr = 4e-16 * (fabs(u0) + n1) + 1e-300; return (u0 - n1 > thr) ? u0 : n1 + thr; }
+    SCPP_HD void apply_step(double a)
     {
         double *S_ = row(0), *Z = row(1), *DS = row(2), *DZ = row(3), *P = pw(0), *DP = pw(1);
-        double lmn = 1e300;
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
             const bool hasint = k < K - 1;
@@ -1138,24 +1196,26 @@ struct Ipm {
             FOR_LANE(e, RS) { S_[e] += a * DS[e]; Z[e] += a * DZ[e]; }
             FOR_LANE(e, PN + NX) P[e] += a * DP[e];
             warp_sync();
-            {   // trust region margins (warp-cooperative)
+            {   // trust region (warp-cooperative)
                 double ts = 0, tz = 0, dummy = 0;
                 FOR_LANE(i, D) if (i > 0) { ts += S_[TRO + i] * S_[TRO + i]; tz += Z[TRO + i] * Z[TRO + i]; }
                 warp_sum3(ts, tz, dummy);
-                lmn = fmin(lmn, fmin(S_[TRO] - sqrt(ts), Z[TRO] - sqrt(tz)));
+                if (lane_id() == 0) { S_[TRO] = nudge(S_[TRO], sqrt(ts)); Z[TRO] = nudge(Z[TRO], sqrt(tz)); }
             }
             FOR_LANE(tk, NTASK) {
                 if (tk == NCONE) continue;
                 int type, o, d, ci;
                 task(tk, type, o, d, ci);
-                if (type == 2) { if (hasint) lmn = fmin(lmn, fmin(fmin(S_[o], S_[o + NX]), fmin(Z[o], Z[o + NX]))); }
-                else {
+                if (type == 2) {
+                    if (hasint) { S_[o] = nudge(S_[o], 0.); S_[o + NX] = nudge(S_[o + NX], 0.); Z[o] = nudge(Z[o], 0.); Z[o + NX] = nudge(Z[o + NX], 0.); }
+                } else {
                     double ts = 0, tz = 0;
 #pragma unroll 1
                     for (int i = 1; i < d; i++) { ts += S_[o + i] * S_[o + i]; tz += Z[o + i] * Z[o + i]; }
-                    lmn = fmin(lmn, fmin(S_[o] - sqrt(ts), Z[o] - sqrt(tz)));
+                    S_[o] = nudge(S_[o], sqrt(ts)); Z[o] = nudge(Z[o], sqrt(tz));
                 }
             }
+            warp_sync();
             st(s + k * RS, S_, RS); st(z + k * RS, Z, RS); st(prim + k * PS, P, PN + NX);
             warp_sync();
         }
@@ -1163,22 +1223,28 @@ struct Ipm {
             const int r0 = K * RS, p0 = K * PS;
             for (int i = 0; i < 4; i++) { s[r0 + i] += a * ds[r0 + i]; z[r0 + i] += a * dz[r0 + i]; }
             prim[p0] += a * dprim[p0]; prim[p0 + 1] += a * dprim[p0 + 1];
-            lmn = fmin(lmn, fmin(s[r0], z[r0]));
-            lmn = fmin(lmn, s[r0 + 1] - sqrt(s[r0 + 2] * s[r0 + 2] + s[r0 + 3] * s[r0 + 3]));
-            lmn = fmin(lmn, z[r0 + 1] - sqrt(z[r0 + 2] * z[r0 + 2] + z[r0 + 3] * z[r0 + 3]));
+            s[r0] = nudge(s[r0], 0.); z[r0] = nudge(z[r0], 0.);
+            s[r0 + 1] = nudge(s[r0 + 1], sqrt(s[r0 + 2] * s[r0 + 2] + s[r0 + 3] * s[r0 + 3]));
+            z[r0 + 1] = nudge(z[r0 + 1], sqrt(z[r0 + 2] * z[r0 + 2] + z[r0 + 3] * z[r0 + 3]));
         }
         warp_sync();
-        return -warp_max(-lmn);
     }
 
     // =============================================================================================================
     //  driver
     // =============================================================================================================
-    SCPP_HD IpmResult solve(const IpmSettings &st_)
+    SCPP_HD IpmResult solve(const IpmSettings &st_, bool have_prev = false)
     {
         IpmResult res;
         res.status = 1; res.iterations = 0; res.pres = res.dres = res.gap = res.relgap = res.pcost = 0.;
         const int np = n_prim(K), m = m_rows(K);
+        tables_init();
+        const bool warm = have_prev && st_.warm > 0.;
+        if (warm) {   // keep the previous final interior point: primal in best_, s in cr, z in zprev (all untouched by the start-up)
+            FOR_LANE(e, np) best_[e] = prim[e];
+            FOR_LANE(e, m) { cr[e] = s[e]; zprev[e] = z[e]; }
+            warp_sync();
+        }
         // ---- starting point (CVXOPT conelp / ECOS style): least-squares primal and dual points, W = I
         FOR_LANE(e, K * PS) {
             const int k = e / PS, i = e - k * PS;
@@ -1221,6 +1287,13 @@ struct Ipm {
             if (mg <= 1e-8 * fmax(1., sqrt(n2))) { cone_shift(z, 1. - mg); }
             warp_sync();
         }
+        if (warm) {
+            const double lw = st_.warm, lc = 1. - st_.warm;
+            FOR_LANE(e, K * PS) { const int k = e / PS, i = e - k * PS; if (!(i < NB && fixed(k, i))) prim[e] = lw * best_[e] + lc * prim[e]; }
+            if (lane_id() == 0) { prim[K * PS] = lw * best_[K * PS] + lc * prim[K * PS]; prim[K * PS + 1] = lw * best_[K * PS + 1] + lc * prim[K * PS + 1]; }
+            FOR_LANE(e, m) { s[e] = lw * cr[e] + lc * s[e]; z[e] = lw * zprev[e] + lc * z[e]; }
+            warp_sync();
+        }
         const double cnorm = sqrt(w_time * w_time + w_trs * w_trs + K * w_tr * w_tr + (K - 1) * NX * w_vc * w_vc);
         const double resx0 = fmax(1., cnorm);
         const int degree = K * (NLP + NCN) + (K - 1) * 2 * NX + 2;
@@ -1241,7 +1314,7 @@ struct Ipm {
             if (!nm.bad && score < best) {
                 best = score;
                 res.pres = pres; res.dres = dres; res.gap = gap; res.relgap = relgap; res.pcost = pcost; res.iterations = it;
-                FOR_LANE(e, np) best_[e] = prim[e];
+                if (score <= 1e4) { FOR_LANE(e, np) best_[e] = prim[e]; }      // a fallback iterate only matters inside the accuracy band
                 warp_sync();
             }
             if (!nm.bad && pres <= st_.feastol && dres <= st_.feastol && (gap <= st_.abstol || relgap <= st_.reltol)) { res.status = 0; break; }
@@ -1252,18 +1325,11 @@ struct Ipm {
             const double a_aff = tmax <= 1. ? 1. : 1. / tmax;
             const double sig = (1. - a_aff) * (1. - a_aff) * (1. - a_aff), mu = gap / degree;
             phase_solve(2, 1. - sig, sig * mu, -(1. - sig), tmax);           // combined direction
-            double alpha = tmax <= 0.99 ? 1. : 0.99 / tmax;
-            double applied = 0.;
-            // additive update; back off if rounding leaves the cone
-            for (int tries = 0; tries < 20; tries++) {
-                const double mg = apply_step(alpha - applied);
-                applied = alpha;
-                if (mg > 0.) break;
-                alpha *= 0.8;
-            }
+            const double alpha = tmax <= 0.99 ? 1. : 0.99 / tmax;
+            apply_step(alpha);
         }
         if (res.status != 0) {
-            FOR_LANE(e, np) prim[e] = best_[e];
+            if (best <= 1e4) { FOR_LANE(e, np) prim[e] = best_[e]; }
             warp_sync();
             if (best <= 10.) res.status = 0; else if (best <= 1e4) res.status = 3;
         } else res.iterations = it;

@@ -98,8 +98,8 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
     const double w_tr = a.w_tr[n];
     ipm.w_tr = w_tr;
     ipm.bind(a.ws + (size_t)n * a.ws_stride, smem);
-    const IpmResult r = ipm.solve(cfg.ipm);
     const int it = a.iters[n];
+    const IpmResult r = ipm.solve(cfg.ipm, it > 0 && a.status[n] != 2);
     double *inf = a.info + ((size_t)n * a.max_it + it) * INFO_STRIDE;
     const bool ok = (r.status == 0 || r.status == 3);
     warp_sync();

@@ -18,7 +18,7 @@ class ModelParamsHost(C.Structure):
 
 
 class IpmSettings(C.Structure):
-    _fields_ = [("feastol", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("maxit", C.c_int)]
+    _fields_ = [("feastol", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("maxit", C.c_int), ("pad_", C.c_int), ("warm", C.c_double)]
 
 
 class ScConfig(C.Structure):
@@ -66,13 +66,13 @@ def params_from_oracle(model, p):
     return P, np.array(p.x_init, float), np.array(p.x_final, float)
 
 
-def sc_config(ocfg, nsub=20, tol=1e-9, maxit=100, history=True):
+def sc_config(ocfg, nsub=20, tol=1e-9, maxit=100, history=True, warm=0.0):
     c = ScConfig()
     for f in ("K", "free_final_time", "interpolate_input", "nondimensionalize", "weight_time", "weight_trust_region_time",
               "weight_trust_region_trajectory", "weight_virtual_control", "nu_tol", "delta_tol", "max_iterations"):
         setattr(c, f, getattr(ocfg, f))
     c.nsub = nsub; c.keep_history = int(history)
-    c.ipm.feastol = tol; c.ipm.abstol = tol; c.ipm.reltol = tol; c.ipm.maxit = maxit
+    c.ipm.feastol = tol; c.ipm.abstol = tol; c.ipm.reltol = tol; c.ipm.maxit = maxit; c.ipm.warm = warm
     return c
 
 
