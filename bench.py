@@ -162,8 +162,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU path)")
 
     model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=args.K)
-    if os.environ.get("SCPP_WARM"):
-        cfg.ipm.warm = float(os.environ["SCPP_WARM"])      # experimental: blended interior-point warm start
+    # blended interior-point start (engine knob, same optimum; parity-tested in tests/test_gpu_parity.py); SCPP_WARM=0 gives ECOS-style cold starts
+    cfg.ipm.warm = float(os.environ.get("SCPP_WARM", "0.9"))
     rpy = np.deg2rad([-20.0, 20.0, 0.0])      # rpy_init of configs/RocketQuat/model.info
     n_local = args.batch
     xi = S.perturbed_initial_states(x_init, rpy, n_local, first=rank * n_local)

@@ -54,40 +54,47 @@ struct IpmResult {
 
 // ---- second-order-cone primitives (one lane, one cone); kept out of line to bound the code size -------------------
 namespace soc {
-SCPP_HD double jn2(const double *u, int d) { double n = 0; for (int i = 1; i < d; i++) n += u[i] * u[i]; return u[0] * u[0] - n; }
+constexpr int SOC_MAXD = 4;   // the single-lane primitives serve the small model cones (dimension <= 4); the trust region is warp-cooperative
+SCPP_HD double jn2(const double *u, int d)
+{
+    double n = 0;
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) n += u[i] * u[i];
+    return u[0] * u[0] - n;
+}
 
 SCPP_OUTLINE bool scale(const double *sk, const double *zk, int d, double *w, double &e2i, double *lm)
 {
     double ss = jn2(sk, d), zz = jn2(zk, d);
     if (!(ss > 0.) || !(zz > 0.) || !(sk[0] > 0.) || !(zk[0] > 0.)) return false;
     double sn = sqrt(ss), zn = sqrt(zz), sz = 0;
-#pragma unroll 1
-    for (int i = 0; i < d; i++) sz += sk[i] * zk[i];
+#pragma unroll
+    for (int i = 0; i < SOC_MAXD; i++) if (i < d) sz += sk[i] * zk[i];
     double gam = sqrt((1. + sz / (sn * zn)) / 2.);
     double i2g = 1. / (2. * gam);
     const double isn = i2g / sn, izn = i2g / zn;
     w[0] = sk[0] * isn + zk[0] * izn;
-#pragma unroll 1
-    for (int i = 1; i < d; i++) w[i] = sk[i] * isn - zk[i] * izn;
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) w[i] = sk[i] * isn - zk[i] * izn;
     e2i = zn / sn;
     double eta = sqrt(sn / zn), w1z1 = 0;
-#pragma unroll 1
-    for (int i = 1; i < d; i++) w1z1 += w[i] * zk[i];
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) w1z1 += w[i] * zk[i];
     double f = zk[0] + w1z1 / (1. + w[0]);
     lm[0] = eta * (w[0] * zk[0] + w1z1);
-#pragma unroll 1
-    for (int i = 1; i < d; i++) lm[i] = eta * (zk[i] + f * w[i]);
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) lm[i] = eta * (zk[i] + f * w[i]);
     return true;
 }
 // o = W^-2 v  (o may alias v)
 SCPP_OUTLINE void Mv(const double *w, double e2i, const double *v, int d, double *o)
 {
     double dot = w[0] * v[0];
-#pragma unroll 1
-    for (int i = 1; i < d; i++) dot -= w[i] * v[i];
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) dot -= w[i] * v[i];
     const double v0 = v[0];
-#pragma unroll 1
-    for (int i = 1; i < d; i++) o[i] = e2i * (-2. * dot * w[i] + v[i]);
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) o[i] = e2i * (-2. * dot * w[i] + v[i]);
     o[0] = e2i * (2. * dot * w[0] - v0);
 }
 // o = W v | W^-1 v  (o may alias v)
@@ -96,43 +103,43 @@ SCPP_OUTLINE void Wv(const double *w, double e2i, const double *v, int d, double
     const double eta = 1. / sqrt(e2i);
     const double sg = inv ? -1. : 1., sc = inv ? 1. / eta : eta;
     double w1v1 = 0;
-#pragma unroll 1
-    for (int i = 1; i < d; i++) w1v1 += w[i] * v[i];
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) w1v1 += w[i] * v[i];
     const double o0 = w[0] * v[0] + sg * w1v1, f = sg * v[0] + w1v1 / (1. + w[0]);
-#pragma unroll 1
-    for (int i = 1; i < d; i++) o[i] = sc * (v[i] + f * w[i]);
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) o[i] = sc * (v[i] + f * w[i]);
     o[0] = sc * o0;
 }
 SCPP_OUTLINE void jprod(const double *u, const double *v, int d, double *o)   // o may alias u or v
 {
     double dot = 0;
-#pragma unroll 1
-    for (int i = 0; i < d; i++) dot += u[i] * v[i];
+#pragma unroll
+    for (int i = 0; i < SOC_MAXD; i++) if (i < d) dot += u[i] * v[i];
     const double u0 = u[0], v0 = v[0];
-#pragma unroll 1
-    for (int i = 1; i < d; i++) o[i] = u0 * v[i] + v0 * u[i];
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) o[i] = u0 * v[i] + v0 * u[i];
     o[0] = dot;
 }
 SCPP_OUTLINE void jdiv(const double *lm, const double *dv, int d, double *o)   // o = lm \ dv  (o may alias dv)
 {
     double den = jn2(lm, d), l1d1 = 0;
-#pragma unroll 1
-    for (int i = 1; i < d; i++) l1d1 += lm[i] * dv[i];
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) l1d1 += lm[i] * dv[i];
     const double x0 = (lm[0] * dv[0] - l1d1) / den, il0 = 1. / lm[0];
-#pragma unroll 1
-    for (int i = 1; i < d; i++) o[i] = (dv[i] - x0 * lm[i]) * il0;
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) o[i] = (dv[i] - x0 * lm[i]) * il0;
     o[0] = x0;
 }
 SCPP_OUTLINE double step(const double *lm, const double *dk, int d)
 {
     const double ia = 1. / sqrt(jn2(lm, d)), l0 = lm[0] * ia;
     double ld = l0 * dk[0];
-#pragma unroll 1
-    for (int i = 1; i < d; i++) ld -= lm[i] * ia * dk[i];
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) ld -= lm[i] * ia * dk[i];
     const double rho0 = ld * ia, f = (ld + dk[0]) / (l0 + 1.) * ia;
     double n1 = 0;
-#pragma unroll 1
-    for (int i = 1; i < d; i++) { const double r = dk[i] - f * lm[i]; n1 += r * r; }
+#pragma unroll
+    for (int i = 1; i < SOC_MAXD; i++) if (i < d) { const double r = dk[i] - f * lm[i]; n1 += r * r; }
     return sqrt(n1) * ia - rho0;
 }
 } // namespace soc
@@ -156,6 +163,7 @@ struct Ipm {
     static constexpr int CS = pad2(NCN);            // eta^-2 per cone of one stage
     static constexpr int FS = pad2(2 * BLK + 2 * NB);   // Linv_kk | L_{k+1,k} | l_k | f_k
     static constexpr int OFF_LN = BLK, OFF_L = 2 * BLK, OFF_F = 2 * BLK + NB;
+    static_assert(M::MAXDIM <= soc::SOC_MAXD, "single-lane cone primitives are unrolled for dimension <= 4");
     static_assert(NB % 2 == 0 && NC % 2 == 0 && NX % 2 == 0, "16-byte record alignment needs even nx, nx+nu and tile width");
 
     SCPP_HD static int m_rows(int K) { return K * RS + 4; }
@@ -322,7 +330,7 @@ struct Ipm {
 #pragma unroll 3
         for (int j = 0; j < NB; j += 2) { acc -= t[j] * xk[j]; acc2 -= t[j + 1] * xk[j + 1]; }
         acc += acc2;
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < NU; j++) acc -= t[NB + j] * xn[NX + j];
         acc -= t[NB + NU] * sg;
         if (with_const) acc -= t[NB + NU + 1];
@@ -744,10 +752,12 @@ struct Ipm {
 #pragma unroll 1
                 for (int i = 0; i < NB; i++) {
                     if (i < c) { Li[i * NB + c] = 0.; continue; }
-                    double v = (i == c) ? 1. : 0.;
+                    double v = (i == c) ? 1. : 0., v2 = 0.;
+                    int q = c;
 #pragma unroll 1
-                    for (int q = c; q < i; q++) v -= H[i * NB + q] * Li[q * NB + c];
-                    Li[i * NB + c] = v / H[i * NB + i];
+                    for (; q + 1 < i; q += 2) { v -= H[i * NB + q] * Li[q * NB + c]; v2 -= H[i * NB + q + 1] * Li[(q + 1) * NB + c]; }
+                    if (q < i) v -= H[i * NB + q] * Li[q * NB + c];
+                    Li[i * NB + c] = (v + v2) / H[i * NB + i];
                 }
             }
             warp_sync();
@@ -756,16 +766,15 @@ struct Ipm {
             FOR_LANE(e, BLK) {
                 const int a = e / NB, b = e - a * NB;
                 double v0 = 0, v1 = 0;
-                int c = 0;
-#pragma unroll 1
-                for (; c + 1 <= b; c += 2) { v0 += O[a * NB + c] * Li[b * NB + c]; v1 += O[a * NB + c + 1] * Li[b * NB + c + 1]; }
-                if (c <= b) v0 += O[a * NB + c] * Li[b * NB + c];
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) { v0 += O[a * NB + c] * Li[b * NB + c]; v1 += O[a * NB + c + 1] * Li[b * NB + c + 1]; }
                 Ln[e] = v0 + v1;
             }
             FOR_LANE(j, NB) {
-                double v = 0;
-#pragma unroll 1
-                for (int c = 0; c <= j; c++) v += Li[j * NB + c] * bk[c];
+                double v = 0, v2 = 0;
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) { v += Li[j * NB + c] * bk[c]; v2 += Li[j * NB + c + 1] * bk[c + 1]; }
+                v += v2;
                 lk[j] = v; corner -= v * v;
             }
             warp_sync();
@@ -917,16 +926,17 @@ struct Ipm {
             FOR_LANE(j, NB) {
                 double v = fixed(k, j) ? 0. : g[j];
                 if (k > 0) {
-#pragma unroll 2
+#pragma unroll
                     for (int c = 0; c < NB; c++) v -= Lp[j * NB + c] * fprev[c];
                 }
                 tmp[j] = v;
             }
             warp_sync();
             FOR_LANE(j, NB) {
-                double v = 0;
-#pragma unroll 1
-                for (int c = 0; c <= j; c++) v += F[j * NB + c] * tmp[c];
+                double v = 0, v2 = 0;
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) { v += F[j * NB + c] * tmp[c]; v2 += F[j * NB + c + 1] * tmp[c + 1]; }
+                v += v2;
                 F[OFF_F + j] = v;
                 ldot += F[OFF_L + j] * v;
             }
@@ -987,7 +997,7 @@ struct Ipm {
             FOR_LANE(j, NB) {
                 double v = F[OFF_F + j] - F[OFF_L + j] * ysig;
                 if (hasint) {
-#pragma unroll 2
+#pragma unroll
                     for (int c = 0; c < NB; c++) v -= F[OFF_LN + c * NB + j] * ynext[c];
                 }
                 tmp[j] = v;
@@ -995,9 +1005,10 @@ struct Ipm {
             }
             warp_sync();
             FOR_LANE(j, NB) {
-                double v = 0;
-#pragma unroll 1
-                for (int c = j; c < NB; c++) v += F[c * NB + j] * tmp[c];
+                double v = 0, v2 = 0;
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) { v += F[c * NB + j] * tmp[c]; v2 += F[(c + 1) * NB + j] * tmp[c + 1]; }
+                v += v2;
                 yk[j] = fixed(k, j) ? 0. : v;
             }
             warp_sync();

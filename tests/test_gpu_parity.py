@@ -60,8 +60,9 @@ def test_discretize_rocket2d_and_ragged_sizes(S):
             assert np.abs(got[key][0] - ref[key]).max() <= tol * max(1.0, np.abs(ref[key]).max()), (K, key)
 
 
-def _compare_run(S, name, model_o, params_list, K, max_it, tol_x=TOL_X, tol_u=TOL_U, xi=None, cfg_over=None):
+def _compare_run(S, name, model_o, params_list, K, max_it, tol_x=TOL_X, tol_u=TOL_U, xi=None, cfg_over=None, warm=0.0):
     model, params, x_init, x_final, cfg = S.load_model(name, K=K, max_iterations=max_it, keep_history=1, **(cfg_over or {}))
+    cfg.ipm.warm = warm
     N = len(params_list)
     if xi is None:
         xi = np.array([list(p.x_init) for p in params_list])
@@ -106,6 +107,13 @@ def test_sc_rocketquat_k50_batch(S):
     p, rpy = O.falcon9()
     plist = [O.rq_perturb(p, rpy, 0x5C99, i) for i in range(6)] + [p]
     _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=6)
+
+
+def test_sc_rocketquat_k50_blended_start(S):
+    """the opt-in blended interior-point start (ipm.warm, what bench.py uses) reaches the same optimum: same parity bar"""
+    p, rpy = O.falcon9()
+    plist = [O.rq_perturb(p, rpy, 0x5C99, i) for i in range(40, 44)]
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=8, warm=0.9)
 
 
 def test_sc_rocketquat_starship_k100(S):
