@@ -25,7 +25,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) return fail(SCPP_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-constexpr int WPB = 5;   // warps (= problem instances) per CTA of the SOCP kernel
+constexpr int WPB_MAX = 7;   // warps (= problem instances) per CTA of the SOCP kernel (chosen per launch, see solve())
 
 // ------------------------------------------------------------------------------------------------------------------
 // kernels
@@ -82,12 +82,12 @@ __global__ void __launch_bounds__(128) k_discretize(ScArrays<M> a, int nsub, int
 }
 
 // K2 (+K3 epilogue): one warp per active instance
-template <class M>
-__global__ void __launch_bounds__(WPB * 32) k_solve(ScArrays<M> a, ScConfig cfg, const int *__restrict__ active, int n_active)
+template <class M, int MAXW, int MINB>
+__global__ void __launch_bounds__(MAXW * 32, MINB) k_solve(ScArrays<M> a, ScConfig cfg, const int *__restrict__ active, int n_active)
 {
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * WPB + warp;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
     if (gw >= n_active) return;
     sc_solve_instance<M>(a, cfg, active[gw], smem + (size_t)warp * Ipm<M>::sm_doubles());
 }
@@ -192,6 +192,7 @@ struct EngineT : scpp_b200_engine {
     unsigned long long *h_gcount = nullptr;
     std::vector<void *> allocs;
     bool have_states = false, solved_once = false;
+    int n_sm = 148;
 
     template <class T>
     int dalloc(T **p, size_t n)
@@ -237,7 +238,9 @@ struct EngineT : scpp_b200_engine {
 #undef DA
         CU(cudaMallocHost((void **)&h_counter, sizeof(int)));
         CU(cudaMallocHost((void **)&h_gcount, sizeof(unsigned long long)));
-        CU(cudaFuncSetAttribute(k_solve<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WPB * Ipm<M>::sm_doubles() * sizeof(double))));
+        CU(cudaFuncSetAttribute(k_solve<M, WPB_MAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WPB_MAX * Ipm<M>::sm_doubles() * sizeof(double))));
+        CU(cudaFuncSetAttribute(k_solve<M, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(4 * Ipm<M>::sm_doubles() * sizeof(double))));
+        CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
         CU(cudaStreamSynchronize(stream));
         return 0;
     }
@@ -265,7 +268,6 @@ struct EngineT : scpp_b200_engine {
         CU(cudaMemsetAsync(flags, 0, N, stream));
         int n_active = N, cur = 0;
         global_active = (long long)N * nranks;
-        const size_t smem = WPB * Ipm<M>::sm_doubles() * sizeof(double);
         for (int it = 0; it < cfg.max_iterations && global_active > 0; it++) {
             outer++;
             inst_iters += n_active;
@@ -277,7 +279,17 @@ struct EngineT : scpp_b200_engine {
             }
             CU(cudaEventRecord(ev[2], stream));
             if (n_active > 0) {
-                k_solve<M><<<(n_active + WPB - 1) / WPB, WPB * 32, smem, stream>>>(a, cfg, active[cur], n_active);
+                // one warp per instance.  Small batches: spread the warps evenly, one CTA per SM (a batch of 1024 on 148 SMs is
+                // 7 warps per SM); large batches: 4-warp CTAs, two resident per SM (8 warps/SM at 232 registers, no spills).
+                int wpb = (n_active + n_sm - 1) / n_sm;
+                if (wpb < 1) wpb = 1;
+                if (wpb <= WPB_MAX) {
+                    const size_t smem = (size_t)wpb * Ipm<M>::sm_doubles() * sizeof(double);
+                    k_solve<M, WPB_MAX, 1><<<(n_active + wpb - 1) / wpb, wpb * 32, smem, stream>>>(a, cfg, active[cur], n_active);
+                } else {
+                    const size_t smem = (size_t)4 * Ipm<M>::sm_doubles() * sizeof(double);
+                    k_solve<M, 4, 2><<<(n_active + 3) / 4, 4 * 32, smem, stream>>>(a, cfg, active[cur], n_active);
+                }
                 launches++;
             }
             CU(cudaEventRecord(ev[3], stream));

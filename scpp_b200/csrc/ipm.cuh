@@ -438,24 +438,46 @@ struct Ipm {
     //  Phase R : residuals, Nesterov-Todd scaling, termination quantities  (one forward sweep)
     // =============================================================================================================
     struct Norms { double gap, rz2, rx2, pcost, zrz, xrx, h2; int bad; };
+    SCPP_HD static double nudge(double u0, double n1) { const double thr = 4e-16 * (fabs(u0) + n1) + 1e-300; return (u0 - n1 > thr) ? u0 : n1 + thr; }
 
-    SCPP_HD void phase_residuals(Norms &nm, bool identity)
+    //  `step` != 0 fuses the update of the previous iteration into this sweep:  (prim, s, z) += step * (dprim, ds, dz)
+    //  is applied to each stage window as it is loaded (and written back) before the residuals are taken.
+    SCPP_HD void phase_residuals(Norms &nm, bool identity, double step = 0.)
     {
         double gap = 0, rz2 = 0, pcost = 0, zrz = 0, h2 = 0, rx2 = 0, xrx = 0, acc_sig = 0;
         int bad = 0;
-        double *S = row(0), *Z = row(1), *RZ = row(2), *WB = row(3), *LM = row(4);
+        double *S = row(0), *Z = row(1), *RZ = row(2), *WB = row(3), *LM = row(4), *DSW = row(5), *DZW = row(6), *DPW = row(7);
         double *P = pw(0), *PNX = pw(1), *RX = pw(2), *XB = pw(3), *CE = sc();
-        double *carry = vec(0), *w = xv(0);
+        double *carry = vec(0), *w = xv(0), *DPN = vec(2);
+        const bool upd = step != 0.;
+        if (upd) {
+            if (lane_id() == 0) {
+                const int r0 = K * RS, p0 = K * PS;
+                for (int i = 0; i < 4; i++) { s[r0 + i] += step * ds[r0 + i]; z[r0 + i] += step * dz[r0 + i]; }
+                prim[p0] += step * dprim[p0]; prim[p0 + 1] += step * dprim[p0 + 1];
+                s[r0] = nudge(s[r0], 0.); z[r0] = nudge(z[r0], 0.);
+                s[r0 + 1] = nudge(s[r0 + 1], sqrt(s[r0 + 2] * s[r0 + 2] + s[r0 + 3] * s[r0 + 3]));
+                z[r0 + 1] = nudge(z[r0 + 1], sqrt(z[r0 + 2] * z[r0 + 2] + z[r0 + 3] * z[r0 + 3]));
+            }
+            warp_sync();
+        }
         const double sg = prim[K * PS];
         FOR_LANE(j, NB) carry[j] = 0.;
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
             const bool hasint = k < K - 1;
-            if (hasint) { ld_dd(k); ld(PNX, prim + (k + 1) * PS, PS); }
+            if (hasint) { ld_dd(k); ld(PNX, prim + (k + 1) * PS, PS); if (upd) ld(DPN, dprim + (k + 1) * PS, PS); }
             ld(S, s + k * RS, RS); ld(Z, z + k * RS, RS); ld(P, prim + k * PS, PS);
+            if (upd) { ld(DSW, ds + k * RS, RS); ld(DZW, dz + k * RS, RS); ld(DPW, dprim + k * PS, PS); }
             load_xibar(k, XB);
             tables_stage(k);
             ld_wait();
+            if (upd) {
+                update_window(step, S, Z, DSW, DZW, P, DPW, hasint);
+                if (hasint) { FOR_LANE(e, PN + NX) PNX[e] += step * DPN[e]; }
+                warp_sync();
+                st(s + k * RS, S, RS); st(z + k * RS, Z, RS); st(prim + k * PS, P, PN + NX);
+            }
             // ---- trust-region cone: warp-cooperative
             {
                 const int o = TRO;
@@ -1194,7 +1216,33 @@ struct Ipm {
     // prim += a dprim ; s += a ds ; z += a dz.  The step length keeps every cone 1 % inside in exact arithmetic; a cone whose
     // margin u0 - |u1| is lost to rounding (active to ~1e-16 relative) is nudged back inside by a few ulps of u0 so the next
     // Nesterov-Todd scaling stays defined (perturbation << the 1e-8 tolerances).
-    SCPP_HD static double nudge(double u0, double n1) { const double thr = 4e-16 * (fabs(u0) + n1) + 1e-300; return (u0 - n1 > thr) ? u0 : n1 + thr; }
+    // window update shared by apply_step (stand-alone) and phase_residuals (fused): S += a DS, Z += a DZ, P += a DP, then nudge
+    SCPP_HD void update_window(double a, double *S_, double *Z, const double *DS, const double *DZ, double *P, const double *DP, bool hasint)
+    {
+        FOR_LANE(e, RS) { S_[e] += a * DS[e]; Z[e] += a * DZ[e]; }
+        FOR_LANE(e, PN + NX) P[e] += a * DP[e];
+        warp_sync();
+        {   // trust region (warp-cooperative)
+            double ts = 0, tz = 0, dummy = 0;
+            FOR_LANE(i, D) if (i > 0) { ts += S_[TRO + i] * S_[TRO + i]; tz += Z[TRO + i] * Z[TRO + i]; }
+            warp_sum3(ts, tz, dummy);
+            if (lane_id() == 0) { S_[TRO] = nudge(S_[TRO], sqrt(ts)); Z[TRO] = nudge(Z[TRO], sqrt(tz)); }
+        }
+        FOR_LANE(tk, NTASK) {
+            if (tk == NCONE) continue;
+            int type, o, d, ci;
+            task(tk, type, o, d, ci);
+            if (type == 2) {
+                if (hasint) { S_[o] = nudge(S_[o], 0.); S_[o + NX] = nudge(S_[o + NX], 0.); Z[o] = nudge(Z[o], 0.); Z[o + NX] = nudge(Z[o + NX], 0.); }
+            } else {
+                double ts = 0, tz = 0;
+#pragma unroll
+                for (int i = 1; i < soc::SOC_MAXD; i++) if (i < d) { ts += S_[o + i] * S_[o + i]; tz += Z[o + i] * Z[o + i]; }
+                S_[o] = nudge(S_[o], sqrt(ts)); Z[o] = nudge(Z[o], sqrt(tz));
+            }
+        }
+        warp_sync();
+    }
     SCPP_HD void apply_step(double a)
     {
         double *S_ = row(0), *Z = row(1), *DS = row(2), *DZ = row(3), *P = pw(0), *DP = pw(1);
@@ -1204,29 +1252,7 @@ struct Ipm {
             ld(S_, s + k * RS, RS); ld(Z, z + k * RS, RS); ld(DS, ds + k * RS, RS); ld(DZ, dz + k * RS, RS);
             ld(P, prim + k * PS, PS); ld(DP, dprim + k * PS, PS);
             ld_wait();
-            FOR_LANE(e, RS) { S_[e] += a * DS[e]; Z[e] += a * DZ[e]; }
-            FOR_LANE(e, PN + NX) P[e] += a * DP[e];
-            warp_sync();
-            {   // trust region (warp-cooperative)
-                double ts = 0, tz = 0, dummy = 0;
-                FOR_LANE(i, D) if (i > 0) { ts += S_[TRO + i] * S_[TRO + i]; tz += Z[TRO + i] * Z[TRO + i]; }
-                warp_sum3(ts, tz, dummy);
-                if (lane_id() == 0) { S_[TRO] = nudge(S_[TRO], sqrt(ts)); Z[TRO] = nudge(Z[TRO], sqrt(tz)); }
-            }
-            FOR_LANE(tk, NTASK) {
-                if (tk == NCONE) continue;
-                int type, o, d, ci;
-                task(tk, type, o, d, ci);
-                if (type == 2) {
-                    if (hasint) { S_[o] = nudge(S_[o], 0.); S_[o + NX] = nudge(S_[o + NX], 0.); Z[o] = nudge(Z[o], 0.); Z[o + NX] = nudge(Z[o + NX], 0.); }
-                } else {
-                    double ts = 0, tz = 0;
-#pragma unroll 1
-                    for (int i = 1; i < d; i++) { ts += S_[o + i] * S_[o + i]; tz += Z[o + i] * Z[o + i]; }
-                    S_[o] = nudge(S_[o], sqrt(ts)); Z[o] = nudge(Z[o], sqrt(tz));
-                }
-            }
-            warp_sync();
+            update_window(a, S_, Z, DS, DZ, P, DP, hasint);
             st(s + k * RS, S_, RS); st(z + k * RS, Z, RS); st(prim + k * PS, P, PN + NX);
             warp_sync();
         }
@@ -1311,8 +1337,9 @@ struct Ipm {
         double best = 1e300;
         int it;
 #pragma unroll 1
+        double pending = 0.;       // step of the previous iteration, applied inside the next residual sweep
         for (it = 0; it <= st_.maxit; it++) {
-            phase_residuals(nm, false);
+            phase_residuals(nm, false, pending);
             const double resz0 = fmax(1., sqrt(nm.h2));
             const double pres = sqrt(nm.rz2) / resz0, dres = sqrt(nm.rx2) / resx0, gap = nm.gap, pcost = nm.pcost;
             const double dcost = pcost - gap + nm.zrz - nm.xrx;
@@ -1336,8 +1363,7 @@ struct Ipm {
             const double a_aff = tmax <= 1. ? 1. : 1. / tmax;
             const double sig = (1. - a_aff) * (1. - a_aff) * (1. - a_aff), mu = gap / degree;
             phase_solve(2, 1. - sig, sig * mu, -(1. - sig), tmax);           // combined direction
-            const double alpha = tmax <= 0.99 ? 1. : 0.99 / tmax;
-            apply_step(alpha);
+            pending = tmax <= 0.99 ? 1. : 0.99 / tmax;
         }
         if (res.status != 0) {
             if (best <= 1e4) { FOR_LANE(e, np) prim[e] = best_[e]; }
