@@ -195,8 +195,12 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     """world_size 2 on CPU: shard assignment, unique-id broadcast, flag all-gather and timing reduction agree on both ranks"""
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
+    import socket
+    with socket.socket() as sk:          # a free port, so parallel test sessions do not collide
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29671", str(script), ROOT]
+           "--master-port", str(port), str(script), ROOT]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     outs = [eval(l.split("RESULT", 1)[1]) for l in res.stdout.splitlines() if "RESULT" in l]
