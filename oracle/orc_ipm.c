@@ -83,6 +83,8 @@ typedef struct {
     double *wbar;  /* per cone row (normalised NT point, w0^2-|w1|^2=1) */
     double *lambda;
     double kkt_resid;
+    /* work arrays allocated once per solve (the CPU baseline runs many solves in parallel: no malloc in the hot loop) */
+    double *w_rhs, *w_sol, *w_wrk, *w_res, *w_t1, *w_t2, *w_ex, *w_ey, *w_ez, *w_cx, *w_cy, *w_cz, *w_w1, *w_w2;
 } ipm_t;
 
 /* ---------- cone helpers ---------- */
@@ -418,9 +420,8 @@ static void kkt_solve_inner(ipm_t *S, const double *rx, const double *ry, const 
                       double *dx, double *dy, double *dz, int identity_scaling)
 {
     const int n = S->n, p = S->p, m = S->m, N = S->N;
-    double *rhs = (double *)xcalloc(N, sizeof(double)), *sol = (double *)xcalloc(N, sizeof(double));
-    double *wrk = (double *)xcalloc(N, sizeof(double)), *res = (double *)xcalloc(N, sizeof(double));
-    double *t1 = (double *)xcalloc(m, sizeof(double)), *t2 = (double *)xcalloc(m, sizeof(double));
+    double *rhs = S->w_rhs, *sol = S->w_sol, *wrk = S->w_wrk, *res = S->w_res, *t1 = S->w_t1, *t2 = S->w_t2;
+    memset(rhs, 0, sizeof(double) * N);
     /* rhs_x = rx + G_ne' W^-2 rz_ne */
     if (identity_scaling) memcpy(t1, rz, sizeof(double) * m); else apply_Winv2(S, rz, t1);
     for (int j = 0; j < n; j++) rhs[j] = rx[j];
@@ -453,7 +454,6 @@ static void kkt_solve_inner(ipm_t *S, const double *rx, const double *ry, const 
     for (int i = 0; i < m; i++) { double acc = -rz[i]; for (int e = S->Gp[i]; e < S->Gp[i + 1]; e++) acc += S->Gv[e] * dx[S->Gj[e]]; t1[i] = acc; }
     if (identity_scaling) memcpy(dz, t1, sizeof(double) * m); else apply_Winv2(S, t1, dz);
     for (int e = 0; e < S->ne; e++) dz[S->exp_rows[e]] = sol[n + p + e];
-    free(rhs); free(sol); free(wrk); free(res); free(t1); free(t2);
 }
 
 /* outer refinement against the unreduced system [0 A' G'; A 0 0; G 0 -W^2] (the reduced normal-equation
@@ -463,9 +463,7 @@ static void kkt_solve(ipm_t *S, const double *rx, const double *ry, const double
 {
     const int n = S->n, p = S->p, m = S->m;
     kkt_solve_inner(S, rx, ry, rz, dx, dy, dz, identity_scaling);
-    double *ex = (double *)xcalloc(n, sizeof(double)), *ey = (double *)xcalloc(p, sizeof(double)), *ez = (double *)xcalloc(m, sizeof(double));
-    double *cx = (double *)xcalloc(n, sizeof(double)), *cy = (double *)xcalloc(p, sizeof(double)), *cz = (double *)xcalloc(m, sizeof(double));
-    double *w1 = (double *)xcalloc(m, sizeof(double)), *w2 = (double *)xcalloc(m, sizeof(double));
+    double *ex = S->w_ex, *ey = S->w_ey, *ez = S->w_ez, *cx = S->w_cx, *cy = S->w_cy, *cz = S->w_cz, *w1 = S->w_w1, *w2 = S->w_w2;
     double prev = 1e300;
     for (int it = 0; it < 3; it++) {
         for (int j = 0; j < n; j++) ex[j] = rx[j];
@@ -484,7 +482,6 @@ static void kkt_solve(ipm_t *S, const double *rx, const double *ry, const double
         for (int i = 0; i < p; i++) dy[i] += cy[i];
         for (int i = 0; i < m; i++) dz[i] += cz[i];
     }
-    free(ex); free(ey); free(ez); free(cx); free(cy); free(cz); free(w1); free(w2);
 }
 
 static double nrm2(const double *v, int n) { double a = 0; for (int i = 0; i < n; i++) a += v[i] * v[i]; return sqrt(a); }
@@ -528,6 +525,12 @@ int orc_conic_solve_keys(int n, int p, int m, int l, int ncones, const int *q,
     S.eta = (double *)xcalloc(ncones, sizeof(double));
     S.wbar = (double *)xcalloc(m, sizeof(double));
     S.lambda = (double *)xcalloc(m, sizeof(double));
+    S.w_rhs = (double *)xcalloc(S.N, sizeof(double)); S.w_sol = (double *)xcalloc(S.N, sizeof(double));
+    S.w_wrk = (double *)xcalloc(S.N, sizeof(double)); S.w_res = (double *)xcalloc(S.N, sizeof(double));
+    S.w_t1 = (double *)xcalloc(m, sizeof(double)); S.w_t2 = (double *)xcalloc(m, sizeof(double));
+    S.w_ex = (double *)xcalloc(n, sizeof(double)); S.w_ey = (double *)xcalloc(p, sizeof(double)); S.w_ez = (double *)xcalloc(m, sizeof(double));
+    S.w_cx = (double *)xcalloc(n, sizeof(double)); S.w_cy = (double *)xcalloc(p, sizeof(double)); S.w_cz = (double *)xcalloc(m, sizeof(double));
+    S.w_w1 = (double *)xcalloc(m, sizeof(double)); S.w_w2 = (double *)xcalloc(m, sizeof(double));
 
     double *rx = (double *)xcalloc(n, sizeof(double)), *ry = (double *)xcalloc(p, sizeof(double)), *rz = (double *)xcalloc(m, sizeof(double));
     double *dx = (double *)xcalloc(n, sizeof(double)), *dy = (double *)xcalloc(p, sizeof(double)), *dz = (double *)xcalloc(m, sizeof(double)), *ds = (double *)xcalloc(m, sizeof(double));
@@ -635,6 +638,8 @@ int orc_conic_solve_keys(int n, int p, int m, int l, int ncones, const int *q,
     free(S.coff); free(S.Ap); free(S.Aj); free(S.Av); free(S.Gp); free(S.Gj); free(S.Gv);
     free(S.exp_rows); free(S.exp_of_row); free(S.pos); free(S.first); free(S.rowptr); free(S.L); free(S.D); free(S.Kenv); free(S.sign);
     free(S.wl); free(S.eta); free(S.wbar); free(S.lambda);
+    free(S.w_rhs); free(S.w_sol); free(S.w_wrk); free(S.w_res); free(S.w_t1); free(S.w_t2);
+    free(S.w_ex); free(S.w_ey); free(S.w_ez); free(S.w_cx); free(S.w_cy); free(S.w_cz); free(S.w_w1); free(S.w_w2);
     free(rx); free(ry); free(rz); free(dx); free(dy); free(dz); free(ds); free(dxa); free(dya); free(dza); free(dsa);
     free(bb); free(t1); free(t2); free(t3); free(zero_n); free(zero_p); free(zero_m); free(negc);
     return status;

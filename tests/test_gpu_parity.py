@@ -122,6 +122,28 @@ def test_sc_rocketquat_starship_k100(S):
     _compare_run(S, "RocketQuatStarship", O.ROCKETQUAT, [p, O.rq_perturb(p, rpy, 0x5C99, 1)], K=100, max_it=4)
 
 
+def test_committed_fixtures(S):
+    """the committed (oracle-generated) fixtures in tests/golden/, compared on the box without running the oracle"""
+    import os
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    p, rpy = O.falcon9()
+    cases = [("rocket2d_K30", "Rocket2D", 30, 15, np.array(O.rocket2d().x_init)),
+             ("rocketquat_K20_nominal", "RocketQuat", 20, 5, np.array(p.x_init)),
+             ("rocketquat_K50_inst7", "RocketQuat", 50, 4, np.array(O.rq_perturb(p, rpy, 0x5C99, 7).x_init))]
+    for name, cfgname, K, max_it, xi in cases:
+        g = np.load(os.path.join(gdir, name + ".npz"))
+        model, params, x_init, x_final, cfg = S.load_model(cfgname, K=K, max_iterations=max_it, keep_history=1)
+        eng = S.SCAlgorithm(model, params, cfg, 1)
+        eng.set_boundary_states(xi, x_final)
+        eng.solve()
+        sol = eng.get_solution(); Xh, Uh, th = eng.get_all_solutions()
+        n = int(g["iterations"])
+        assert sol["iterations"][0] == n and int(sol["flags"][0] == 1) == int(g["converged"])
+        assert np.abs(Xh[0, :n + 1] - g["X_all"]).max() < TOL_X and np.abs(Uh[0, :n + 1] - g["U_all"]).max() < TOL_U
+        assert np.allclose(sol["X"][0], g["X"], rtol=1e-6, atol=1e-4 * np.abs(g["X"]).max())
+        eng.close()
+
+
 def test_full_batch_properties(S):
     """BASELINE.json configs[1] at full size (1024): size-independent properties instead of oracle comparison"""
     model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50)

@@ -244,3 +244,21 @@ def test_perturbation_recipe_is_reproducible():
     assert a.x_init[0] == p.x_init[0] and a.x_init[3] == p.x_init[3]          # mass and r_z unchanged
     assert abs(a.x_init[1]) <= abs(p.x_init[1]) and abs(a.x_init[6]) <= 1.2 * abs(p.x_init[6])
     assert np.isclose(np.linalg.norm(np.array(a.x_init)[7:11]), 1.0)
+
+
+@pytest.mark.parametrize("name,model,K,max_it,inst", [("rocket2d_K30", O.ROCKET2D, 30, 15, None), ("rocketquat_K20_nominal", O.ROCKETQUAT, 20, 5, None),
+                                                      ("rocketquat_K50_inst7", O.ROCKETQUAT, 50, 4, 7)])
+def test_oracle_reproduces_committed_fixtures(name, model, K, max_it, inst):
+    """tests/golden/*.npz are ORACLE-generated (the reference has no golden vectors): they pin the oracle against drift"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    if model == O.ROCKET2D:
+        p = O.rocket2d()
+    else:
+        p, rpy = O.falcon9()
+        if inst is not None:
+            p = O.rq_perturb(p, rpy, 0x5C99, inst)
+    r = O.sc_solve(model, p, O.sc_config(K=K, model=model, max_iterations=max_it))
+    assert r["iterations"] == int(g["iterations"]) and int(r["converged"]) == int(g["converged"])
+    assert np.allclose(r["X_all"], g["X_all"], atol=1e-9) and np.allclose(r["U_all"], g["U_all"], atol=1e-9)
+    assert np.allclose(r["t_all"], g["t_all"], atol=1e-9)
