@@ -170,8 +170,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU path)")
 
     model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=args.K)
-    # blended interior-point start (engine knob, same optimum; parity-tested in tests/test_gpu_parity.py); SCPP_WARM=0 gives ECOS-style cold starts
-    cfg.ipm.warm = float(os.environ.get("SCPP_WARM", "0.9"))
+    # interior warm start of the sub-problems (engine knob, same optimum; parity-tested in tests/test_gpu_parity.py);
+    # SCPP_WARM=0 gives ECOS-style cold starts
+    cfg.ipm.warm = float(os.environ.get("SCPP_WARM", "0.995"))
     rpy = np.deg2rad([-20.0, 20.0, 0.0])      # rpy_init of configs/RocketQuat/model.info
     n_local = args.batch
     xi = S.perturbed_initial_states(x_init, rpy, n_local, first=rank * n_local)

@@ -109,11 +109,12 @@ def test_sc_rocketquat_k50_batch(S):
     _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=6)
 
 
-def test_sc_rocketquat_k50_blended_start(S):
-    """the opt-in blended interior-point start (ipm.warm, what bench.py uses) reaches the same optimum: same parity bar"""
+def test_sc_rocketquat_k50_interior_warm_start(S):
+    """the opt-in interior warm start of the sub-problems (ipm.warm, what bench.py uses) reaches the same optimum: same parity bar"""
     p, rpy = O.falcon9()
-    plist = [O.rq_perturb(p, rpy, 0x5C99, i) for i in range(40, 44)]
-    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=8, warm=0.9)
+    plist = [O.rq_perturb(p, rpy, 0x5C99, i) for i in range(40, 46)] + [p]
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=15, warm=0.995)
+    _compare_run(S, "Rocket2D", O.ROCKET2D, [O.rocket2d()], K=30, max_it=15, warm=0.995)
 
 
 def test_sc_rocketquat_starship_k100(S):
