@@ -244,6 +244,13 @@ def main():
         whole = algorithmic_bytes(args.K, "all") * inst_iters / (float(np.sum(dev_ms)) * 1e-3) / 1e9
         roof_it = {"bound": "hbm", "scope": "k_discretize + k_solve (whole iteration, SURVEY §8d: 285024 B at K=50)", "achieved": whole,
                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": whole / peaks["hbm_gbs"]}
+        tpath = os.path.join(ROOT, "profiles", "k_solve_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("K") == args.K:      # ncu dram bytes per instance-iteration x instances of one launch (capture named in the file)
+                roof["traffic"] = tj["dram_bytes_per_instance_iteration"] * (inst_iters / socp_launches)
+                roof["traffic_source"] = "profiles/k_solve_traffic.json (ncu dram__bytes, per launch)"
         prof = os.path.join(ROOT, "profiles", "fp64_peak.json")
         fp64 = None
         if os.path.exists(prof):
