@@ -129,6 +129,10 @@ size_t scpp_b200_device_bytes(scpp_b200_engine *e);
 int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const double *X, const double *U, const double *sigma,
                          const double *par, double *A, double *B, double *C, double *s, double *z);
 
+/* the tensor-core block products of K2 (mma.sync.m8n8k4.f64, scpp_b200/csrc/blockops.cuh) checked on the device against scalar
+ * loops for the shapes the factorisation uses; returns the largest absolute deviation (no reference counterpart) */
+int scpp_b200_selftest_blockops(int device, double *max_abs_err);
+
 /* ---- multi-GPU: one process (rank) per GPU, the batch is sharded by the caller ----------------------------------
  * the only data-path collective is one ncclAllGather of the per-instance convergence flags per outer iteration. */
 int scpp_b200_comm_unique_id(char id[128]);

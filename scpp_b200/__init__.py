@@ -239,6 +239,13 @@ def comm_unique_id():
     return buf.raw
 
 
+def selftest_blockops(device=0):
+    """largest |DMMA block product - scalar loops| over the shapes K2 uses (device self-test)"""
+    err = C.c_double()
+    _check(lib().scpp_b200_selftest_blockops(device, C.byref(err)))
+    return err.value
+
+
 def discretize(model, X, U, sigma, par, nsub=20, device=0):
     """test hook on hot path 1 (discretization::multipleShooting): returns dict of [n][K-1][row][col] arrays"""
     nx, nu, npar = model_dims(model)

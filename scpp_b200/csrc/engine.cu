@@ -128,6 +128,42 @@ __global__ void k_export(ScArrays<M> a, double *Xo, double *Uo)
     for (int i = 0; i < NU; i++) Uo[idx * NU + i] = u[i];
 }
 
+// self-test of the tensor-core block products (blockops.cuh) against scalar loops: one warp, the shapes used by the factorisation
+__global__ void k_selftest_blockops(double *err)
+{
+    constexpr int NB = 18, NX = 14, NU = 4, NCP = 26;
+    __shared__ double A[NB * NB], B[NB * NB], T[NX * NCP], C1[NB * NB], C2[NB * NB];
+    const int lane = threadIdx.x;
+    for (int e = lane; e < NB * NB; e += 32) { A[e] = sin(0.37 * e + 0.1); B[e] = cos(0.11 * e) * ((e / NB >= e % NB) ? 1. : 0.); C1[e] = 0.01 * e; C2[e] = 0.01 * e; }
+    for (int e = lane; e < NX * NCP; e += 32) T[e] = sin(0.05 * e) + 0.3;
+    __syncwarp();
+    double worst = 0.;
+    // (1) C -= A A'  (lower tiles)   (2) C = A B' with B lower triangular   (3) C += T' (A_x) with a 14-row contraction   (4) 4 x 18 output
+    blk::mm<NB, NB, NB, true>([&](int m, int k) { return (m < NB && k < NB) ? A[m * NB + k] : 0.; }, [&](int k, int n) { return (k < NB && n < NB) ? A[n * NB + k] : 0.; },
+                              [&](int m, int n, double v) { if (m < NB && n < NB) C1[m * NB + n] -= v; });
+    __syncwarp();
+    for (int e = lane; e < NB * NB; e += 32) { const int a = e / NB, b = e % NB; if (b / 8 <= a / 8) { double v = 0; for (int c = 0; c < NB; c++) v += A[a * NB + c] * A[b * NB + c]; worst = fmax(worst, fabs(C1[e] - (C2[e] - v))); } }
+    __syncwarp();
+    blk::mm<NB, NB, NB, false>([&](int m, int k) { return (m < NB && k < NB) ? A[m * NB + k] : 0.; }, [&](int k, int n) { return (k < NB && n < NB) ? B[n * NB + k] : 0.; },
+                               [&](int m, int n, double v) { if (m < NB && n < NB) C1[m * NB + n] = v; });
+    __syncwarp();
+    for (int e = lane; e < NB * NB; e += 32) { const int a = e / NB, b = e % NB; double v = 0; for (int c = 0; c < NB; c++) v += A[a * NB + c] * B[b * NB + c]; worst = fmax(worst, fabs(C1[e] - v)); }
+    __syncwarp();
+    for (int e = lane; e < NB * NB; e += 32) C1[e] = C2[e];
+    __syncwarp();
+    blk::mm<NB, NB, NX, true>([&](int m, int k) { return (m < NB && k < NX) ? T[k * NCP + m] : 0.; }, [&](int k, int n) { return (k < NX && n < NB) ? -A[k * NB + n] : 0.; },
+                              [&](int m, int n, double v) { if (m < NB && n < NB) C1[m * NB + n] += v; });
+    __syncwarp();
+    for (int e = lane; e < NB * NB; e += 32) { const int a = e / NB, b = e % NB; if (b / 8 <= a / 8) { double v = 0; for (int i = 0; i < NX; i++) v -= T[i * NCP + a] * A[i * NB + b]; worst = fmax(worst, fabs(C1[e] - (C2[e] + v))); } }
+    __syncwarp();
+    blk::mm<NU, NB, NX, false>([&](int m, int k) { return (m < NU && k < NX) ? T[k * NCP + NB + m] : 0.; }, [&](int k, int n) { return (k < NX && n < NB) ? -A[k * NB + n] : 0.; },
+                               [&](int m, int n, double v) { if (m < NU && n < NB) C1[m * NB + n] = v; });
+    __syncwarp();
+    for (int e = lane; e < NU * NB; e += 32) { const int a = e / NB, b = e % NB; double v = 0; for (int i = 0; i < NX; i++) v -= T[i * NCP + NB + a] * A[i * NB + b]; worst = fmax(worst, fabs(C1[a * NB + b] - v)); }
+    for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if (lane == 0) *err = worst;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // NCCL through dlopen (only needed for multi-GPU runs)
 // ------------------------------------------------------------------------------------------------------------------
@@ -570,6 +606,20 @@ int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const do
     if (model == SCPP_B200_MODEL_ROCKETQUAT) return discretize_hook<RocketQuat>(K, n, nsub, device, X, U, sigma, par, A, B, C, s, z);
     if (model == SCPP_B200_MODEL_ROCKET2D) return discretize_hook<Rocket2d>(K, n, nsub, device, X, U, sigma, par, A, B, C, s, z);
     return fail(SCPP_B200_ERR_ARG, "unknown model");
+}
+
+int scpp_b200_selftest_blockops(int device, double *max_abs_err)
+{
+    if (!max_abs_err) return fail(SCPP_B200_ERR_ARG, "null argument");
+    if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");
+    CU(cudaSetDevice(device));
+    double *d = nullptr;
+    CU(cudaMalloc((void **)&d, sizeof(double)));
+    k_selftest_blockops<<<1, 32>>>(d);
+    CU(cudaMemcpy(max_abs_err, d, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    CU(cudaGetLastError());
+    return 0;
 }
 
 int scpp_b200_comm_unique_id(char id[128])

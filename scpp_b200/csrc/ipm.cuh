@@ -24,6 +24,7 @@
 // touched with per-lane strided or dependent accesses.
 #pragma once
 #include "models.cuh"
+#include "blockops.cuh"
 #if !defined(__CUDACC__)
 #include <cstdio>
 #include <cstdlib>
@@ -680,21 +681,13 @@ struct Ipm {
                 FOR_LANE(e, NX * NU) { const int i = e / NU, j = e - i * NU; DCp[e] = Dt[i] * t[i * NCP + NB + j]; }
                 FOR_LANE(i, NX) Dp[i] = Dt[i];
                 warp_sync();
-#pragma unroll 2
-                FOR_LANE(e, BLK) {       // H += A~' (D A~) = -A~' O_x
-                    const int a = e / NB, b = e - a * NB;
-                    double v = 0;
-#pragma unroll 2
-                    for (int i = 0; i < NX; i++) v -= t[i * NCP + a] * O[i * NB + b];
-                    H[e] += v;
-                }
-                FOR_LANE(e, NU * NB) {   // O rows of the u_{k+1} block: C' D A~ = -C' O_x
-                    const int a = e / NB, b = e - a * NB;
-                    double v = 0;
-#pragma unroll 2
-                    for (int i = 0; i < NX; i++) v -= t[i * NCP + NB + a] * O[i * NB + b];
-                    O[(NX + a) * NB + b] = v;
-                }
+                // H += A~' (D A~) = -A~' O_x   and   O_u = C' D A~ = -C' O_x   on the FP64 tensor cores (lower tiles of H suffice)
+                blk::mm<NB, NB, NX, true>([&](int m, int k) { return (m < NB && k < NX) ? t[k * NCP + m] : 0.; },
+                                          [&](int k, int n) { return (k < NX && n < NB) ? -O[k * NB + n] : 0.; },
+                                          [&](int m, int n, double v) { if (m < NB && n < NB) H[m * NB + n] += v; });
+                blk::mm<NU, NB, NX, false>([&](int m, int k) { return (m < NU && k < NX) ? t[k * NCP + NB + m] : 0.; },
+                                           [&](int k, int n) { return (k < NX && n < NB) ? -O[k * NB + n] : 0.; },
+                                           [&](int m, int n, double v) { if (m < NU && n < NB) O[(NX + m) * NB + n] = v; });
                 FOR_LANE(e, NU * NU) {
                     const int a = e / NU, b = e - a * NU;
                     double v = 0;
@@ -733,16 +726,9 @@ struct Ipm {
             warp_sync();
             // ---- Schur update with the previous off-diagonal factor: H -= Lp Lp' ; bk -= Lp lprev
             if (k > 0) {
-#pragma unroll 2
-                FOR_LANE(e, BLK) {
-                    const int a = e / NB, b = e - a * NB;
-                    if (b <= a) {
-                        double v0 = 0, v1 = 0;
-#pragma unroll 2
-                        for (int c = 0; c < NB; c += 2) { v0 += Lp[a * NB + c] * Lp[b * NB + c]; v1 += Lp[a * NB + c + 1] * Lp[b * NB + c + 1]; }
-                        H[e] -= v0 + v1;
-                    }
-                }
+                blk::mm<NB, NB, NB, true>([&](int m, int k) { return (m < NB && k < NB) ? Lp[m * NB + k] : 0.; },
+                                          [&](int k, int n) { return (k < NB && n < NB) ? Lp[n * NB + k] : 0.; },
+                                          [&](int m, int n, double v) { if (m < NB && n < NB) H[m * NB + n] -= v; });
                 FOR_LANE(j, NB) {
                     double v = 0;
 #pragma unroll 2
@@ -785,14 +771,9 @@ struct Ipm {
             }
             warp_sync();
             // ---- L_{k+1,k} = O Linv' ;  l_k = Linv bk ; corner -= l_k' l_k
-#pragma unroll 2
-            FOR_LANE(e, BLK) {
-                const int a = e / NB, b = e - a * NB;
-                double v0 = 0, v1 = 0;
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) { v0 += O[a * NB + c] * Li[b * NB + c]; v1 += O[a * NB + c + 1] * Li[b * NB + c + 1]; }
-                Ln[e] = v0 + v1;
-            }
+            blk::mm<NB, NB, NB, false>([&](int m, int k) { return (m < NB && k < NB) ? O[m * NB + k] : 0.; },
+                                       [&](int k, int n) { return (k < NB && n < NB) ? Li[n * NB + k] : 0.; },
+                                       [&](int m, int n, double v) { if (m < NB && n < NB) Ln[m * NB + n] = v; });
             FOR_LANE(j, NB) {
                 double v = 0, v2 = 0;
 #pragma unroll

@@ -28,6 +28,11 @@ def _oracle_nondim_par(p):
     return pn, par
 
 
+def test_tensor_core_block_products(S):
+    """mma.sync.m8n8k4.f64 block products (predicated 18-wide operands, lower-tile mode, 14-row contraction) == scalar loops"""
+    assert S.selftest_blockops() < 1e-12
+
+
 def test_discretize_matches_rkf78_oracle(S):
     """hot path 1 alone: RK4 x nsub forward-sensitivity kernel vs the literal RKF78 x 5 Phi^-1-form oracle"""
     p, rpy = O.falcon9()
