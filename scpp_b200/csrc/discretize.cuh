@@ -13,6 +13,8 @@
 //
 // Output layout per interval, row-major [NX][NC], NC = NX + 2 NU + 2:  row r = [A(r,:) | B(r,:) | C(r,:) | s(r) | z(r)]
 // => the NC threads of one interval store to consecutive addresses (coalesced).
+// K2's stage-parallel passes read the tiles with one lane per stage; for them the tile is stored a second time
+// stage-minor ([NX*NC][KS], KS = K rounded up to 4) so that 32 lanes load 32 consecutive doubles.
 #pragma once
 #include "models.cuh"
 
@@ -53,7 +55,7 @@ SCPP_HD void discretize_rhs(const double *x, const double *col, const double *u,
 // X:[K][NX] U:[K][NU] of one instance; writes column `c` of interval `k` into dd_k (row-major [NX][NC])
 template <class M>
 SCPP_HD void discretize_column(const double *X, const double *U, double sigma, const double *par, int K, int k, int c,
-                               int nsub, int free_time, double *ddk)
+                               int nsub, int free_time, double *ddk, double *ddT = nullptr, int KS = 0)
 {
     constexpr int NX = M::NX, NU = M::NU, NC = NX + 2 * NU + 2;
     int ctype, cidx;
@@ -96,6 +98,10 @@ SCPP_HD void discretize_column(const double *X, const double *U, double sigma, c
     (void)free_time;
 #pragma unroll
     for (int i = 0; i < NX; i++) ddk[i * NC + c] = col[i];
+    if (ddT) {   // the same tile, stage-minor: element (i, c) of interval k at (i*NC + c)*KS + k   (stage-parallel passes of K2)
+#pragma unroll
+        for (int i = 0; i < NX; i++) ddT[(size_t)(i * NC + c) * KS + k] = col[i];
+    }
 }
 
 } // namespace scpp

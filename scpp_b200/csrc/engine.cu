@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(128) k_discretize(ScArrays<M> a, int nsub, int
     const int k = rem / NC, c = rem - k * NC;
     const int n = active ? active[ai] : ai;
     discretize_column<M>(a.X + (size_t)n * a.K * NX, a.U + (size_t)n * a.K * NU, a.sigma[n], a.par + (size_t)n * M::NP,
-                         a.K, k, c, nsub, free_time, a.dd + ((size_t)n * (a.K - 1) + k) * NX * NC);
+                         a.K, k, c, nsub, free_time, a.dd + ((size_t)n * (a.K - 1) + k) * NX * NC,
+                         a.ddT ? a.ddT + (size_t)n * Ipm<M>::ddt_doubles(a.K) : nullptr, Ipm<M>::ks(a.K));
 }
 
 // K2 (+K3 epilogue): one warp per active instance
@@ -265,6 +266,7 @@ struct EngineT : scpp_b200_engine {
         DA(a.tdir, (size_t)N * K * 3); DA(a.fixm, (size_t)N * K); DA(a.fixv, (size_t)N * K * NB); DA(a.w_tr, N);
         DA(a.iters, N); DA(a.status, N); DA(a.converged, N);
         DA(a.dd, (size_t)N * (K - 1) * NX * NC);
+        DA(a.ddT, (size_t)N * Ipm<M>::ddt_doubles(K));
         DA(a.ws, (size_t)N * a.ws_stride);
         DA(a.info, (size_t)N * cfg.max_iterations * INFO_STRIDE);
         a.hist = nullptr;

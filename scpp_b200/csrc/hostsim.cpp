@@ -10,12 +10,12 @@
 using namespace scpp;
 
 template <class M>
-static void run_discretize(int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd)
+static void run_discretize(int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd, double *ddT = nullptr)
 {
     constexpr int NC = M::NX + 2 * M::NU + 2;
     for (int k = 0; k < K - 1; k++)
         for (int c = 0; c < NC; c++)
-            discretize_column<M>(X, U, sigma, par, K, k, c, nsub, 1, dd + (size_t)k * M::NX * NC);
+            discretize_column<M>(X, U, sigma, par, K, k, c, nsub, 1, dd + (size_t)k * M::NX * NC, ddT, Ipm<M>::ks(K));
 }
 
 extern "C" void hs_discretize(int model, int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd)
@@ -34,13 +34,13 @@ static int run_sc(const ModelParamsHost *P, const ScConfig *cfg, int N, const do
     a.N = N; a.K = K; a.max_it = cfg->max_iterations;
     std::vector<double> xi(N * NX), xf(N * NX), par(N * M::NP), cst(N * MAX_CST), scale(N * 2), tdir((size_t)N * K * 3), fixv((size_t)N * K * NB), wtr(N);
     std::vector<uint32_t> fixm((size_t)N * K);
-    std::vector<double> dd((size_t)N * (K - 1) * NX * NC);
+    std::vector<double> dd((size_t)N * (K - 1) * NX * NC), ddT((size_t)N * Ipm<M>::ddt_doubles(K));
     a.ws_stride = Ipm<M>::ws_doubles(K);
     std::vector<double> ws((size_t)N * a.ws_stride), smem(Ipm<M>::sm_doubles());
     a.x_init = const_cast<double *>(x_init); a.x_final = const_cast<double *>(x_final);
     a.xi = xi.data(); a.xf = xf.data(); a.par = par.data(); a.cst = cst.data(); a.scale = scale.data();
     a.X = X; a.U = U; a.sigma = sigma; a.tdir = tdir.data(); a.fixm = fixm.data(); a.fixv = fixv.data(); a.w_tr = wtr.data();
-    a.iters = iters; a.status = status; a.converged = converged; a.dd = dd.data(); a.ws = ws.data(); a.hist = hist; a.info = info;
+    a.iters = iters; a.status = status; a.converged = converged; a.dd = dd.data(); a.ddT = ddT.data(); a.ws = ws.data(); a.hist = hist; a.info = info;
     for (int n = 0; n < N; n++) sc_setup_instance<M>(a, *P, *cfg, n);
     for (int it = 0; it < cfg->max_iterations; it++) {
         int active = 0;
@@ -48,7 +48,7 @@ static int run_sc(const ModelParamsHost *P, const ScConfig *cfg, int N, const do
             if (converged[n]) continue;
             active++;
             run_discretize<M>(K, X + (size_t)n * K * NX, U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg->nsub,
-                              a.dd + (size_t)n * (K - 1) * NX * NC);
+                              a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K));
             sc_solve_instance<M>(a, *cfg, n, smem.data());
         }
         if (!active) break;

@@ -16,12 +16,17 @@
 // (NB x NB blocks, NB = nx + nu) plus one dense border row/column for sigma; it is factored by a block Cholesky
 // sweep over the K nodes.
 //
-// Execution shape (v2): every phase is a SWEEP over the K stages (stage k = node k + shooting interval k).  All
-// per-instance state lives in HBM in stage-major records; for each stage the warp copies the stage's records
-// (the [A|B|C|s|z]_k tile, the cone rows, the factor blocks) into a shared-memory window with coalesced 16-byte
-// asynchronous copies, works on the window (cone arithmetic: one lane per cone / LP row / virtual-control pair;
-// tile and block arithmetic: warp-cooperative), and writes the results back coalesced.  Global memory is never
-// touched with per-lane strided or dependent accesses.
+// Execution shape (v3).  The work of one interior-point iteration is of two kinds and each gets its own mapping:
+//   * STAGE-PARALLEL passes (residuals + Nesterov-Todd scaling, right-hand sides, recovery of dz/ds and the step
+//     lengths, the update):  nothing couples the K stages (stage k = node k + shooting interval k) except two
+//     nearest-neighbour reads, so ONE LANE runs the scalar cone arithmetic of ONE STAGE (K = 50: two rounds of the
+//     warp).  All per-stage state lives in HBM in STAGE-MINOR arrays  a[row * KS + k]  so that the 32 lanes of a
+//     load/store touch 32 consecutive doubles (fully coalesced), there are no shuffles, no divergence between the
+//     cone types and no shared-memory staging in these passes.
+//   * the CHAIN (block-tridiagonal Cholesky, forward and backward substitution) is sequential in k; there the warp
+//     cooperates on one stage at a time: per-stage records are staged in shared memory with 16-byte asynchronous
+//     copies (prefetched one stage ahead), block products run on the FP64 tensor cores (blockops.cuh), the 18x18
+//     Cholesky and the triangular inverse keep one matrix row / column per lane.
 #pragma once
 #include "models.cuh"
 #include "blockops.cuh"
@@ -48,15 +53,9 @@ struct IpmResult {
     double pres, dres, gap, relgap, pcost;
 };
 
-#if defined(__CUDACC__)
-#define SCPP_OUTLINE __host__ __device__ __forceinline__
-#else
-#define SCPP_OUTLINE inline
-#endif
-
-// ---- second-order-cone primitives (one lane, one cone); kept out of line to bound the code size -------------------
+// ---- second-order-cone primitives on small local arrays (dimension <= 4: the model cones) ------------------------------
 namespace soc {
-constexpr int SOC_MAXD = 4;   // the single-lane primitives serve the small model cones (dimension <= 4); the trust region is warp-cooperative
+constexpr int SOC_MAXD = 4;
 SCPP_HD double jn2(const double *u, int d)
 {
     double n = 0;
@@ -64,8 +63,7 @@ SCPP_HD double jn2(const double *u, int d)
     for (int i = 1; i < SOC_MAXD; i++) if (i < d) n += u[i] * u[i];
     return u[0] * u[0] - n;
 }
-
-SCPP_OUTLINE bool scale(const double *sk, const double *zk, int d, double *w, double &e2i, double *lm)
+SCPP_HD bool scale(const double *sk, const double *zk, int d, double *w, double &e2i, double *lm)
 {
     double ss = jn2(sk, d), zz = jn2(zk, d);
     if (!(ss > 0.) || !(zz > 0.) || !(sk[0] > 0.) || !(zk[0] > 0.)) return false;
@@ -89,7 +87,7 @@ SCPP_OUTLINE bool scale(const double *sk, const double *zk, int d, double *w, do
     return true;
 }
 // o = W^-2 v  (o may alias v)
-SCPP_OUTLINE void Mv(const double *w, double e2i, const double *v, int d, double *o)
+SCPP_HD void Mv(const double *w, double e2i, const double *v, int d, double *o)
 {
     double dot = w[0] * v[0];
 #pragma unroll
@@ -100,7 +98,7 @@ SCPP_OUTLINE void Mv(const double *w, double e2i, const double *v, int d, double
     o[0] = e2i * (2. * dot * w[0] - v0);
 }
 // o = W v | W^-1 v  (o may alias v)
-SCPP_OUTLINE void Wv(const double *w, double e2i, const double *v, int d, double *o, bool inv)
+SCPP_HD void Wv(const double *w, double e2i, const double *v, int d, double *o, bool inv)
 {
     const double eta = 1. / sqrt(e2i);
     const double sg = inv ? -1. : 1., sc = inv ? 1. / eta : eta;
@@ -112,7 +110,7 @@ SCPP_OUTLINE void Wv(const double *w, double e2i, const double *v, int d, double
     for (int i = 1; i < SOC_MAXD; i++) if (i < d) o[i] = sc * (v[i] + f * w[i]);
     o[0] = sc * o0;
 }
-SCPP_OUTLINE void jprod(const double *u, const double *v, int d, double *o)   // o may alias u or v
+SCPP_HD void jprod(const double *u, const double *v, int d, double *o)   // o may alias u or v
 {
     double dot = 0;
 #pragma unroll
@@ -122,7 +120,7 @@ SCPP_OUTLINE void jprod(const double *u, const double *v, int d, double *o)   //
     for (int i = 1; i < SOC_MAXD; i++) if (i < d) o[i] = u0 * v[i] + v0 * u[i];
     o[0] = dot;
 }
-SCPP_OUTLINE void jdiv(const double *lm, const double *dv, int d, double *o)   // o = lm \ dv  (o may alias dv)
+SCPP_HD void jdiv(const double *lm, const double *dv, int d, double *o)   // o = lm \ dv  (o may alias dv)
 {
     double den = jn2(lm, d), l1d1 = 0;
 #pragma unroll
@@ -132,7 +130,7 @@ SCPP_OUTLINE void jdiv(const double *lm, const double *dv, int d, double *o)   /
     for (int i = 1; i < SOC_MAXD; i++) if (i < d) o[i] = (dv[i] - x0 * lm[i]) * il0;
     o[0] = x0;
 }
-SCPP_OUTLINE double step(const double *lm, const double *dk, int d)
+SCPP_HD double step(const double *lm, const double *dk, int d)
 {
     const double ia = 1. / sqrt(jn2(lm, d)), l0 = lm[0] * ia;
     double ld = l0 * dk[0];
@@ -158,35 +156,37 @@ struct Ipm {
     static constexpr int NRK = NCONE + 1;           // rank-1 terms of the model Hessian: cones + one multi-entry LP row
     static constexpr int TRO = NLP + NCR;           // offset of the trust-region cone inside a node block
     static constexpr int BLK = NB * NB;
-    static constexpr int NTASK = NCN + NLP + NX;    // per-stage cone tasks: cones, LP rows, virtual-control pairs
-    // stage-major record strides (even => 16-byte aligned records)
-    static constexpr int RS = pad2(MN + 2 * NX);    // cone rows of one stage: node rows | interval rows (s-: NX, s+: NX)
-    static constexpr int PS = pad2(PN + NX);        // primal of one stage: xi | delta | t
-    static constexpr int CS = pad2(NCN);            // eta^-2 per cone of one stage
-    static constexpr int FS = pad2(2 * BLK + 2 * NB);   // Linv_kk | L_{k+1,k} | l_k | f_k
-    static constexpr int OFF_LN = BLK, OFF_L = 2 * BLK, OFF_F = 2 * BLK + NB;
+    static constexpr int D = 1 + NB;                // dimension of the trust-region cone
+    static constexpr int RS = MN + 2 * NX;          // cone rows of one stage: node rows | interval rows (s-: NX, s+: NX)
+    static constexpr int PSN = PN + NX;             // primal rows of one stage: xi | delta | t
+    static constexpr int NROW = NLP + NCR;          // model rows of one node
+    static constexpr int FS = pad2(2 * BLK + NB);   // factor record of one stage (stage-major): Linv_kk | L_{k+1,k} | l_k
+    static constexpr int OFF_LN = BLK, OFF_L = 2 * BLK;
     static_assert(M::MAXDIM <= soc::SOC_MAXD, "single-lane cone primitives are unrolled for dimension <= 4");
     static_assert(NB % 2 == 0 && NC % 2 == 0 && NX % 2 == 0, "16-byte record alignment needs even nx, nx+nu and tile width");
 
-    SCPP_HD static int m_rows(int K) { return K * RS + 4; }
-    SCPP_HD static int n_prim(int K) { return K * PS + 2; }
-    SCPP_HD static int n_ce(int K) { return K * CS + 2; }
-    SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 8 * m_rows(K) + n_ce(K) + K * FS + 16; }
-    // shared window: tile | factor record | L_{k,k-1} carry | UNION{ 8 row arrays + primal windows ; phase F: wb + H,O + model terms }
-    //                | compact carry of interval k-1 | vectors | scalars | per-stage row coefficients, reverse map, constants
-    static constexpr int NROW = NLP + NCR;
+    // stage-minor arrays:  element (row r, stage k) at  r * KS + k ;  the 4 global rows / 2 global primals follow the stage part
+    SCPP_HD static int ks(int K) { return (K + 3) & ~3; }
+    SCPP_HD static int m_rows(int K) { return RS * ks(K) + 4; }
+    SCPP_HD static int n_prim(int K) { return PSN * ks(K) + 2; }
+    SCPP_HD static int n_ce(int K) { return NCN * ks(K) + 2; }
+    SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 8 * m_rows(K) + n_ce(K) + (NB + NX) * ks(K) + K * FS + 16; }
+    SCPP_HD static int ddt_doubles(int K) { return NX * NC * ks(K); }
+    // shared window of the warp (chain phases only):
+    //   factorisation:  tile | record out | L_{k,k-1} | H | O | model terms          substitution: three record buffers
     static constexpr int HNC = pad2(NX + NX * NU + NU * NU);      // D | D C | C' D C  of the previous interval
-    static constexpr int W_DD = 0, W_FAC = W_DD + pad2(NX * NCP), W_LP = W_FAC + FS, W_ROW = W_LP + BLK, W_PRIM = W_ROW + 8 * RS,
-                         W_MAT = W_ROW + RS, W_RK = W_MAT + 2 * BLK,
-                         W_UEND = (W_PRIM + 4 * PS + pad2(NB)) > (W_RK + 2 * NRK * NB) ? (W_PRIM + 4 * PS + pad2(NB)) : (W_RK + 2 * NRK * NB),
-                         W_HN = W_UEND, W_VEC = W_HN + HNC, W_X = W_VEC + 6 * NB, W_SC = W_X + 2 * pad2(NX),
+    static constexpr int W_DD = 0, W_FAC = W_DD + pad2(NX * NCP), W_LP = W_FAC + FS, W_MAT = W_LP + BLK, W_RK = W_MAT + 2 * BLK,
+                         W_F_END = W_RK + 2 * NRK * NB, W_S_END = 3 * FS,
+                         W_UEND = W_F_END > W_S_END ? W_F_END : W_S_END,
+                         W_WB = W_UEND, W_HN = W_WB + pad2(RS), W_VEC = W_HN + HNC, W_X = W_VEC + 6 * NB, W_SC = W_X + 2 * pad2(NX),
                          W_RCQ = W_SC + 32, W_RIDX = W_RCQ + 4 * NROW, W_REV = W_RIDX + pad2(2 * NROW), W_CST = W_REV + pad2(2 * NB),
                          W_END = W_CST + pad2(MAX_CST + 4);
     SCPP_HD static int sm_doubles() { return W_END; }
 
     // ---- problem data (read only) -----------------------------------------------------------------------------
-    int K;
-    const double *dd;      // [K-1][NX][NC]
+    int K, KS;
+    const double *dd;      // [K-1][NX][NC]   stage-major tiles (chain)
+    const double *ddT;     // [NX*NC][KS]     the same tiles, stage-minor (stage-parallel passes)
     const double *Xbar;    // [K][NX]
     const double *Ubar;    // [K][NU]
     double sigbar;
@@ -195,36 +195,42 @@ struct Ipm {
     const uint32_t *fixm;  // [K]
     const double *fixv;    // [K][NB]
     double w_time, w_trs, w_tr, w_vc;
-    // ---- workspace (global memory, per instance, stage-major) ---------------------------------------------------
+    // ---- workspace (global memory, per instance) -------------------------------------------------------------------
     double *prim, *dprim, *rx, *best_;
     double *s, *z, *wb, *lam, *rz, *cr, *dz, *ds;
     double *ce;
-    double *fac;
+    double *gv;            // [NB][KS]  right-hand side g -> forward solution f -> solution y
+    double *wv;            // [NX][KS]  w of interval k (coupling to node k+1)
+    double *fac;           // [K][FS]
     double *sm;            // per-warp shared window
     double l_ss;           // Cholesky pivot of the sigma border
 
     SCPP_HD void bind(double *ws, double *smem)
     {
+        KS = ks(K);
         const int np = n_prim(K), m = m_rows(K);
         double *p = ws;
         prim = p; p += np; dprim = p; p += np; rx = p; p += np; best_ = p; p += np;
         s = p; p += m; z = p; p += m; wb = p; p += m; lam = p; p += m; rz = p; p += m; cr = p; p += m; dz = p; p += m; ds = p; p += m;
         ce = p; p += n_ce(K);
+        gv = p; p += NB * KS;
+        wv = p; p += NX * KS;
         fac = p;
         sm = smem;
     }
     // accessors used by the SC glue (sc.cuh)
-    SCPP_HD double xi_at(int k, int i) const { return prim[k * PS + i]; }
-    SCPP_HD double delta_at(int k) const { return prim[k * PS + NB]; }
-    SCPP_HD double t_at(int k, int i) const { return prim[k * PS + PN + i]; }
-    SCPP_HD double sigma_val() const { return prim[K * PS]; }
-    SCPP_HD double dsigma_val() const { return prim[K * PS + 1]; }
+    SCPP_HD double xi_at(int k, int i) const { return prim[i * KS + k]; }
+    SCPP_HD double delta_at(int k) const { return prim[NB * KS + k]; }
+    SCPP_HD double t_at(int k, int i) const { return prim[(PN + i) * KS + k]; }
+    SCPP_HD double sigma_val() const { return prim[PSN * KS]; }
+    SCPP_HD double dsigma_val() const { return prim[PSN * KS + 1]; }
 
     SCPP_HD bool fixed(int k, int i) const { return (fixm[k] >> i) & 1u; }
+    SCPP_HD double xibar(int k, int i) const { return i < NX ? Xbar[k * NX + i] : Ubar[k * NU + (i - NX)]; }
+    SCPP_HD double T(int i, int j, int k) const { return ddT[(i * NC + j) * KS + k]; }     // tile element, stage-minor
 
-    // ---- window plumbing ------------------------------------------------------------------------------------------
-    // cooperative copy of n (even) doubles global -> shared, 16 bytes per lane per step, asynchronous on the device
-    SCPP_HD void ld(double *dst, const double *src, int n) const
+    // ---- shared-window plumbing (chain phases) ----------------------------------------------------------------------
+    SCPP_HD void ld(double *dst, const double *src, int n) const   // n even, 16 bytes per lane per step, asynchronous on the device
     {
 #if defined(__CUDA_ARCH__)
         const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
@@ -234,8 +240,7 @@ struct Ipm {
         memcpy(dst, src, sizeof(double) * n);
 #endif
     }
-    // the [A|B|C|s|z]_k tile: NX rows of NC doubles into rows of stride NCP
-    SCPP_HD void ld_dd(int k) const
+    SCPP_HD void ld_dd(int k) const   // the [A|B|C|s|z]_k tile: NX rows of NC doubles into rows of stride NCP
     {
         const double *src = dd + (size_t)k * NX * NC;
         double *t = sm + W_DD;
@@ -249,39 +254,34 @@ struct Ipm {
         for (int r = 0; r < NX; r++) memcpy(t + r * NCP, src + r * NC, sizeof(double) * NC);
 #endif
     }
-    SCPP_HD void ld_wait() const
+    SCPP_HD void ld_commit() const
     {
 #if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+    }
+    SCPP_HD void ld_wait(int pending = 0) const   // all but the `pending` most recent groups have landed
+    {
+#if defined(__CUDA_ARCH__)
+        if (pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
         warp_sync();
     }
-    // cooperative coalesced store shared -> global
     SCPP_HD void st(double *dst, const double *src, int n) const { FOR_LANE(e, n) dst[e] = src[e]; }
 
-    SCPP_HD double *row(int a) const { return sm + W_ROW + a * RS; }     // 8 row-array windows
-    SCPP_HD double *pw(int a) const { return sm + W_PRIM + a * PS; }     // 4 primal windows (+ NB spare after the 4th)
     SCPP_HD double *vec(int i) const { return sm + W_VEC + i * NB; }
     SCPP_HD double *xv(int i) const { return sm + W_X + i * pad2(NX); }
     SCPP_HD double *sc() const { return sm + W_SC; }
     SCPP_HD double *tile() const { return sm + W_DD; }
     SCPP_HD double *facw() const { return sm + W_FAC; }
+    SCPP_HD double *fbuf(int b) const { return sm + b * FS; }
 
-    // task -> (type, row offset in the stage window, dimension, cone index): 0 LP row, 1 second-order cone, 2 virtual-control pair
-    SCPP_HD static void task(int tk, int &type, int &o, int &d, int &ci)
-    {
-        if (tk < NCONE) { type = 1; o = NLP + M::cone_off(tk); d = M::cone_dim(tk); ci = tk; }
-        else if (tk == NCONE) { type = 1; o = TRO; d = 1 + NB; ci = NCONE; }
-        else if (tk < NCN + NLP) { type = 0; o = tk - NCN; d = 1; ci = -1; }
-        else { type = 2; o = MN + (tk - NCN - NLP); d = 1; ci = -1; }
-    }
-    // per-stage row coefficients in shared memory: RCQ[r][0..2] = coefficients, RCQ[r][3] = h ; RIDX[r][q] = variable index
-    // (or -1); REV[j][t] = (row*4+q) of the up-to-3 entries that touch variable j (or -1).  CST = per-instance constants.
+    // per-stage row coefficients in shared memory (chain: assembly of the node Hessian):  RCQ[r][0..2] = coefficients,
+    // RCQ[r][3] = h ; RIDX[r][q] = variable index (or -1).  CST = per-instance constants (all phases).
     SCPP_HD double *rcq() const { return sm + W_RCQ; }
     SCPP_HD int *ridx() const { return reinterpret_cast<int *>(sm + W_RIDX); }
-    SCPP_HD int *rev() const { return reinterpret_cast<int *>(sm + W_REV); }
     SCPP_HD double *cstw() const { return sm + W_CST; }
-    // once per solve: constants, index table, reverse map and the k-independent coefficients
     SCPP_HD void tables_init() const
     {
         FOR_LANE(i, MAX_CST) cstw()[i] = cst[i];
@@ -292,14 +292,9 @@ struct Ipm {
             for (int q = 0; q < 3; q++) rcq()[r * 4 + q] = (q < rd.n && rd.cs[q] >= 0) ? cstw()[rd.cs[q]] : 0.;
             rcq()[r * 4 + 3] = cstw()[rd.hs];
         }
-        FOR_LANE(j, NB) {
-            int n = 0;
-            for (int t = 0; t < 4; t++) rev()[j * 4 + t] = -1;
-            for (int r = 0; r < NROW; r++) { const RowDesc rd = M::row(r); for (int q = 0; q < rd.n; q++) if (rd.idx[q] == j && n < 4) rev()[j * 4 + n++] = r * 4 + q; }
-        }
         warp_sync();
     }
-    // once per stage: only the linearised minimum-thrust row depends on k (coefficient slots < 0 take -tdir[k])
+    // once per stage of the chain: only the linearised minimum-thrust row depends on k (coefficient slots < 0 take -tdir[k])
     SCPP_HD void tables_stage(int k) const
     {
         FOR_LANE(e, NROW * 3) {
@@ -308,257 +303,244 @@ struct Ipm {
             if (q < rd.n && rd.cs[q] < 0) rcq()[r * 4 + q] = -tdir[3 * k + (-rd.cs[q] - 1)];
         }
     }
-    SCPP_HD double row_h(int r) const { return rcq()[r * 4 + 3]; }
-    // gather of the model-row contributions G' v onto variable j of the node
-    SCPP_HD double model_GT(int j, int, const double *v /* node rows window */) const
+    // ---- model rows in the stage-parallel passes: the row index is a compile-time constant after unrolling, so the row table
+    //      folds into immediates and the scatter targets are registers
+    SCPP_HD double coef(const RowDesc &rd, int q, int k) const { return rd.cs[q] >= 0 ? cstw()[rd.cs[q]] : -tdir[3 * k + (-rd.cs[q] - 1)]; }
+    SCPP_HD double row_h(const RowDesc &rd) const { return cstw()[rd.hs]; }
+    // (G x)_r with x read from a stage-minor array (rows 0..NB-1 = xi)
+    SCPP_HD double row_dot(int r, int k, const double *x) const
     {
+        const RowDesc rd = M::crow(r);
         double a = 0;
 #pragma unroll
-        for (int t = 0; t < 4; t++) { const int e = rev()[j * 4 + t]; if (e >= 0) a += rcq()[e] * v[e >> 2]; }
+        for (int q = 0; q < 3; q++) if (q < rd.n) a += coef(rd, q, k) * x[rd.idx[q] * KS + k];
         return a;
     }
-    SCPP_HD double model_G(int r, int, const double *x) const   // (G x)_r for a model row
+    // acc[idx] += coef * v  for the entries of row r
+    SCPP_HD void row_scatter(int r, int k, double v, double *acc) const
     {
-        double a = 0;
+        const RowDesc rd = M::crow(r);
 #pragma unroll
-        for (int q = 0; q < 3; q++) { const int i = ridx()[r * 4 + q]; if (i >= 0) a += rcq()[r * 4 + q] * x[i]; }
-        return a;
-    }
-    // r_i = x_{k+1,i} - (A~ xi_k)_i - (C u_{k+1})_i - s_i sigma [- z_i]   from windows (tile staged)
-    SCPP_HD double dyn_row(int i, const double *xk, const double *xn, double sg, bool with_const) const
-    {
-        const double *t = tile() + i * NCP;
-        double acc = xn[i], acc2 = 0;
-#pragma unroll 3
-        for (int j = 0; j < NB; j += 2) { acc -= t[j] * xk[j]; acc2 -= t[j + 1] * xk[j + 1]; }
-        acc += acc2;
-#pragma unroll
-        for (int j = 0; j < NU; j++) acc -= t[NB + j] * xn[NX + j];
-        acc -= t[NB + NU] * sg;
-        if (with_const) acc -= t[NB + NU + 1];
-        return acc;
-    }
-    // out_k -= A~' w ; carry = [w ; -C' w] (contribution to node k+1) ; returns lane-partial of -s'w
-    SCPP_HD double dyn_JT(const double *w, double *out_k, double *carry) const
-    {
-        const double *t = tile();
-        FOR_LANE(j, NB) {
-            double a = 0, a2 = 0, c = 0;
-#pragma unroll 7
-            for (int i = 0; i < NX; i += 2) { a += t[i * NCP + j] * w[i]; a2 += t[(i + 1) * NCP + j] * w[i + 1]; }
-            out_k[j] -= a + a2;
-            if (j < NX) c = w[j];
-            else {
-#pragma unroll 7
-                for (int i = 0; i < NX; i++) c -= t[i * NCP + NB + (j - NX)] * w[i];
-            }
-            carry[j] = c;
-        }
-        double sg = 0;
-        FOR_LANE(i, NX) sg -= t[i * NCP + NB + NU] * w[i];
-        return sg;
-    }
-    SCPP_HD void load_xibar(int k, double *dst) const
-    {
-        FOR_LANE(i, NB) dst[i] = i < NX ? Xbar[k * NX + i] : Ubar[k * NU + (i - NX)];
+        for (int q = 0; q < 3; q++) if (q < rd.n) acc[rd.idx[q]] += coef(rd, q, k) * v;
     }
 
-    // ---- trust-region cone (dimension D = 1 + NB): WARP-COOPERATIVE primitives, lane i owns element i, vectors in the
-    //      shared window, reductions by shuffles.  Every lane of the warp must call them (uniform control flow).
-    //      Outputs may alias inputs.
-    static constexpr int D = 1 + NB;
-    SCPP_HD bool tr_scale(const double *sk, const double *zk, double *w, double &e2i, double *lm) const
-    {
-        double a = 0, b = 0, c = 0;
-        FOR_LANE(i, D) { if (i > 0) { a += sk[i] * sk[i]; b += zk[i] * zk[i]; } c += sk[i] * zk[i]; }
-        warp_sum3(a, b, c);
-        const double s0 = sk[0], z0 = zk[0];
-        const double ss = s0 * s0 - a, zz = z0 * z0 - b;
-        if (!(ss > 0.) || !(zz > 0.) || !(s0 > 0.) || !(z0 > 0.)) return false;
-        const double sn = sqrt(ss), zn = sqrt(zz);
-        const double i2g = 1. / (2. * sqrt((1. + c / (sn * zn)) / 2.));
-        const double isn = i2g / sn, izn = i2g / zn;
-        const double w0 = s0 * isn + z0 * izn;
-        double w1z1 = 0;
-        warp_sync();
-        FOR_LANE(i, D) { const double wi = (i == 0) ? w0 : sk[i] * isn - zk[i] * izn; if (i > 0) w1z1 += wi * zk[i]; w[i] = wi; }
-        w1z1 = warp_sum(w1z1);
-        e2i = zn / sn;
-        const double eta = sqrt(sn / zn), f = z0 + w1z1 / (1. + w0);
-        FOR_LANE(i, D) lm[i] = (i == 0) ? eta * (w0 * z0 + w1z1) : eta * (zk[i] + f * w[i]);
-        warp_sync();
-        return true;
-    }
-    SCPP_HD void tr_Mv(const double *w, double e2i, const double *v, double *o) const   // o = W^-2 v
-    {
-        double dot = 0;
-        FOR_LANE(i, D) dot += (i == 0 ? w[0] * v[0] : -w[i] * v[i]);
-        dot = warp_sum(dot);
-        warp_sync();
-        FOR_LANE(i, D) o[i] = (i == 0) ? e2i * (2. * dot * w[0] - v[0]) : e2i * (-2. * dot * w[i] + v[i]);
-        warp_sync();
-    }
-    SCPP_HD void tr_Wv(const double *w, double e2i, const double *v, double *o, bool inv) const   // o = W v | W^-1 v
-    {
-        const double eta = 1. / sqrt(e2i), sg = inv ? -1. : 1., scl = inv ? 1. / eta : eta;
-        double w1v1 = 0;
-        FOR_LANE(i, D) if (i > 0) w1v1 += w[i] * v[i];
-        w1v1 = warp_sum(w1v1);
-        const double v0 = v[0], w0 = w[0];
-        const double f = sg * v0 + w1v1 / (1. + w0);
-        warp_sync();
-        FOR_LANE(i, D) o[i] = (i == 0) ? scl * (w0 * v0 + sg * w1v1) : scl * (v[i] + f * w[i]);
-        warp_sync();
-    }
-    // scaled step-to-boundary measures of two directions at once: returns max(t(d1), t(d2))
-    SCPP_HD double tr_step2(const double *lm, const double *d1, const double *d2) const
-    {
-        double l1 = 0, a1 = 0, a2 = 0;
-        FOR_LANE(i, D) if (i > 0) { l1 += lm[i] * lm[i]; a1 += lm[i] * d1[i]; a2 += lm[i] * d2[i]; }
-        warp_sum3(l1, a1, a2);
-        const double ia = 1. / sqrt(lm[0] * lm[0] - l1), l0 = lm[0] * ia;
-        const double ld1 = l0 * d1[0] - a1 * ia, ld2 = l0 * d2[0] - a2 * ia;
-        const double il = ia / (l0 + 1.);
-        const double f1 = (ld1 + d1[0]) * il, f2 = (ld2 + d2[0]) * il;
-        double n1 = 0, n2 = 0, dummy = 0;
-        FOR_LANE(i, D) if (i > 0) { const double r1 = d1[i] - f1 * lm[i], r2 = d2[i] - f2 * lm[i]; n1 += r1 * r1; n2 += r2 * r2; }
-        warp_sum3(n1, n2, dummy);
-        return fmax((sqrt(n1) - ld1) * ia, (sqrt(n2) - ld2) * ia);
-    }
-    SCPP_HD void tr_jprod(const double *u, const double *v, double *o) const
-    {
-        double dot = 0;
-        FOR_LANE(i, D) dot += u[i] * v[i];
-        dot = warp_sum(dot);
-        const double u0 = u[0], v0 = v[0];
-        warp_sync();
-        FOR_LANE(i, D) o[i] = (i == 0) ? dot : u0 * v[i] + v0 * u[i];
-        warp_sync();
-    }
-
-    // =============================================================================================================
-    //  Phase R : residuals, Nesterov-Todd scaling, termination quantities  (one forward sweep)
-    // =============================================================================================================
     struct Norms { double gap, rz2, rx2, pcost, zrz, xrx, h2; int bad; };
     SCPP_HD static double nudge(double u0, double n1) { const double thr = 4e-16 * (fabs(u0) + n1) + 1e-300; return (u0 - n1 > thr) ? u0 : n1 + thr; }
 
-    //  `step` != 0 fuses the update of the previous iteration into this sweep:  (prim, s, z) += step * (dprim, ds, dz)
-    //  is applied to each stage window as it is loaded (and written back) before the residuals are taken.
-    SCPP_HD void phase_residuals(Norms &nm, bool identity, double step = 0.)
+    // =============================================================================================================
+    //  stage-parallel pass U : (prim, s, z) += a (dprim, ds, dz).  The step length keeps every cone 1 % inside in exact
+    //  arithmetic; a cone whose margin u0 - |u1| is lost to rounding (active to ~1e-16 relative) is nudged back inside by a
+    //  few ulps of u0 so the next Nesterov-Todd scaling stays defined (perturbation << the 1e-8 tolerances).
+    // =============================================================================================================
+    SCPP_HD void pass_update(double a)
+    {
+        FOR_LANE(k, K) {
+            const bool hasint = k < K - 1;
+#pragma unroll 4
+            for (int e = 0; e < PSN; e++) prim[e * KS + k] += a * dprim[e * KS + k];
+#pragma unroll
+            for (int r = 0; r < NLP; r++) {
+                s[r * KS + k] = nudge(s[r * KS + k] + a * ds[r * KS + k], 0.);
+                z[r * KS + k] = nudge(z[r * KS + k] + a * dz[r * KS + k], 0.);
+            }
+#pragma unroll
+            for (int c = 0; c < NCN; c++) {
+                const int o = (c < NCONE) ? NLP + M::cone_off(c) : TRO, d = (c < NCONE) ? M::cone_dim(c) : D;
+                double ts = 0, tz = 0;
+#pragma unroll 6
+                for (int i = 1; i < d; i++) {
+                    const double sv = s[(o + i) * KS + k] + a * ds[(o + i) * KS + k], zv = z[(o + i) * KS + k] + a * dz[(o + i) * KS + k];
+                    s[(o + i) * KS + k] = sv; z[(o + i) * KS + k] = zv;
+                    ts += sv * sv; tz += zv * zv;
+                }
+                s[o * KS + k] = nudge(s[o * KS + k] + a * ds[o * KS + k], sqrt(ts));
+                z[o * KS + k] = nudge(z[o * KS + k] + a * dz[o * KS + k], sqrt(tz));
+            }
+            if (hasint) {
+#pragma unroll 4
+                for (int r = MN; r < RS; r++) {
+                    s[r * KS + k] = nudge(s[r * KS + k] + a * ds[r * KS + k], 0.);
+                    z[r * KS + k] = nudge(z[r * KS + k] + a * dz[r * KS + k], 0.);
+                }
+            }
+        }
+        if (lane_id() == 0) {
+            const int r0 = RS * KS, p0 = PSN * KS;
+            for (int i = 0; i < 4; i++) { s[r0 + i] += a * ds[r0 + i]; z[r0 + i] += a * dz[r0 + i]; }
+            prim[p0] += a * dprim[p0]; prim[p0 + 1] += a * dprim[p0 + 1];
+            s[r0] = nudge(s[r0], 0.); z[r0] = nudge(z[r0], 0.);
+            s[r0 + 1] = nudge(s[r0 + 1], sqrt(s[r0 + 2] * s[r0 + 2] + s[r0 + 3] * s[r0 + 3]));
+            z[r0 + 1] = nudge(z[r0 + 1], sqrt(z[r0 + 2] * z[r0 + 2] + z[r0 + 3] * z[r0 + 3]));
+        }
+        warp_sync();
+    }
+
+    // =============================================================================================================
+    //  stage-parallel pass R : residuals, Nesterov-Todd scaling, termination quantities
+    // =============================================================================================================
+    SCPP_HD void pass_residuals(Norms &nm, bool identity)
     {
         double gap = 0, rz2 = 0, pcost = 0, zrz = 0, h2 = 0, rx2 = 0, xrx = 0, acc_sig = 0;
         int bad = 0;
-        double *S = row(0), *Z = row(1), *RZ = row(2), *WB = row(3), *LM = row(4), *DSW = row(5), *DZW = row(6), *DPW = row(7);
-        double *P = pw(0), *PNX = pw(1), *RX = pw(2), *XB = pw(3), *CE = sc();
-        double *carry = vec(0), *w = xv(0), *DPN = vec(2);
-        const bool upd = step != 0.;
-        if (upd) {
-            if (lane_id() == 0) {
-                const int r0 = K * RS, p0 = K * PS;
-                for (int i = 0; i < 4; i++) { s[r0 + i] += step * ds[r0 + i]; z[r0 + i] += step * dz[r0 + i]; }
-                prim[p0] += step * dprim[p0]; prim[p0 + 1] += step * dprim[p0 + 1];
-                s[r0] = nudge(s[r0], 0.); z[r0] = nudge(z[r0], 0.);
-                s[r0 + 1] = nudge(s[r0 + 1], sqrt(s[r0 + 2] * s[r0 + 2] + s[r0 + 3] * s[r0 + 3]));
-                z[r0 + 1] = nudge(z[r0 + 1], sqrt(z[r0 + 2] * z[r0 + 2] + z[r0 + 3] * z[r0 + 3]));
-            }
-            warp_sync();
-        }
-        const double sg = prim[K * PS];
-        FOR_LANE(j, NB) carry[j] = 0.;
-#pragma unroll 1
-        for (int k = 0; k < K; k++) {
+        const double sg = prim[PSN * KS];
+        FOR_LANE(k, K) {
             const bool hasint = k < K - 1;
-            if (hasint) { ld_dd(k); ld(PNX, prim + (k + 1) * PS, PS); if (upd) ld(DPN, dprim + (k + 1) * PS, PS); }
-            ld(S, s + k * RS, RS); ld(Z, z + k * RS, RS); ld(P, prim + k * PS, PS);
-            if (upd) { ld(DSW, ds + k * RS, RS); ld(DZW, dz + k * RS, RS); ld(DPW, dprim + k * PS, PS); }
-            load_xibar(k, XB);
-            tables_stage(k);
-            ld_wait();
-            if (upd) {
-                update_window(step, S, Z, DSW, DZW, P, DPW, hasint);
-                if (hasint) { FOR_LANE(e, PN + NX) PNX[e] += step * DPN[e]; }
-                warp_sync();
-                st(s + k * RS, S, RS); st(z + k * RS, Z, RS); st(prim + k * PS, P, PN + NX);
-            }
-            // ---- trust-region cone: warp-cooperative
+            double P[NB], RXa[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++) { P[j] = prim[j * KS + k]; RXa[j] = 0.; }
+            const double delta = prim[NB * KS + k];
+            // ---- trust-region cone  (delta ; xibar - xi) in Q^{1+NB}
             {
-                const int o = TRO;
-                FOR_LANE(i, D) {
-                    const double sl = (i == 0) ? P[NB] : XB[i - 1] - P[i - 1];
-                    RZ[o + i] = S[o + i] - sl;
-                    if (i > 0) h2 += XB[i - 1] * XB[i - 1];
+                double S[D], Z[D];
+#pragma unroll
+                for (int i = 0; i < D; i++) { S[i] = s[(TRO + i) * KS + k]; Z[i] = z[(TRO + i) * KS + k]; }
+                double a = 0, b = 0, c = S[0] * Z[0];
+                {
+                    const double r0 = S[0] - delta;
+                    rz[TRO * KS + k] = r0; rz2 += r0 * r0; zrz += Z[0] * r0;
                 }
-                if (lane_id() == 0) pcost += w_tr * P[NB];
-                if (identity) { FOR_LANE(i, D) { WB[o + i] = i == 0; LM[o + i] = i == 0; } if (lane_id() == 0) CE[NCONE] = 1.; }
-                else {
-                    double e2i;
-                    if (!tr_scale(S + o, Z + o, WB + o, e2i, LM + o)) bad = 1;
-                    else if (lane_id() == 0) CE[NCONE] = e2i;
+#pragma unroll
+                for (int i = 1; i < D; i++) {
+                    const double xb = xibar(k, i - 1);
+                    const double rv = S[i] - (xb - P[i - 1]);
+                    rz[(TRO + i) * KS + k] = rv;
+                    h2 += xb * xb; rz2 += rv * rv; zrz += Z[i] * rv;
+                    a += S[i] * S[i]; b += Z[i] * Z[i]; c += S[i] * Z[i];
+                    RXa[i - 1] += Z[i];                                    // G'z of the trust-region rows
                 }
-                FOR_LANE(i, D) { gap += S[o + i] * Z[o + i]; rz2 += RZ[o + i] * RZ[o + i]; zrz += Z[o + i] * RZ[o + i]; }
+                gap += c; pcost += w_tr * delta;
+                if (identity) {
+#pragma unroll
+                    for (int i = 0; i < D; i++) { wb[(TRO + i) * KS + k] = i == 0; lam[(TRO + i) * KS + k] = i == 0; }
+                    ce[NCONE * KS + k] = 1.;
+                } else {
+                    const double ss = S[0] * S[0] - a, zz = Z[0] * Z[0] - b;
+                    if (!(ss > 0.) || !(zz > 0.) || !(S[0] > 0.) || !(Z[0] > 0.)) bad = 1;
+                    else {
+                        const double sn = sqrt(ss), zn = sqrt(zz);
+                        const double i2g = 1. / (2. * sqrt((1. + c / (sn * zn)) / 2.));
+                        const double isn = i2g / sn, izn = i2g / zn;
+                        const double w0 = S[0] * isn + Z[0] * izn;
+                        double w1z1 = 0;
+#pragma unroll
+                        for (int i = 1; i < D; i++) { const double wi = S[i] * isn - Z[i] * izn; w1z1 += wi * Z[i]; S[i] = wi; }
+                        const double eta = sqrt(sn / zn), f = Z[0] + w1z1 / (1. + w0);
+                        wb[TRO * KS + k] = w0; lam[TRO * KS + k] = eta * (w0 * Z[0] + w1z1);
+#pragma unroll
+                        for (int i = 1; i < D; i++) { wb[(TRO + i) * KS + k] = S[i]; lam[(TRO + i) * KS + k] = eta * (Z[i] + f * S[i]); }
+                        ce[NCONE * KS + k] = zn / sn;
+                    }
+                }
+                rx[NB * KS + k] = w_tr - Z[0];
+                rx2 += (w_tr - Z[0]) * (w_tr - Z[0]); xrx += delta * (w_tr - Z[0]);
             }
-            // ---- small cone tasks: one lane each
-            FOR_LANE(tk, NTASK) {
-                if (tk == NCONE) continue;
-                int type, o, d, ci;
-                task(tk, type, o, d, ci);
-                if (type == 1) {
-#pragma unroll 1
-                    for (int r = 0; r < d; r++) { const double hh = row_h(o + r); const double sl = hh - model_G(o + r, k, P); RZ[o + r] = S[o + r] - sl; h2 += hh * hh; }
-                    if (identity) { CE[ci] = 1.; for (int i = 0; i < d; i++) { WB[o + i] = i == 0; LM[o + i] = i == 0; } }
-                    else if (!soc::scale(S + o, Z + o, d, WB + o, CE[ci], LM + o)) bad = 1;
-#pragma unroll 1
-                    for (int r = 0; r < d; r++) { gap += S[o + r] * Z[o + r]; rz2 += RZ[o + r] * RZ[o + r]; zrz += Z[o + r] * RZ[o + r]; }
-                } else if (type == 0) {
-                    const double hh = row_h(o);
-                    const double sl = hh - model_G(o, k, P);
-                    const double sv = S[o], zv = Z[o];
-                    RZ[o] = sv - sl;
-                    h2 += hh * hh;
-                    if (!(sv > 0.) || !(zv > 0.)) bad = 1;
-                    WB[o] = identity ? 1. : zv / sv; LM[o] = identity ? 1. : sqrt(sv * zv);
-                    gap += sv * zv; rz2 += RZ[o] * RZ[o]; zrz += zv * RZ[o];
-                } else if (hasint) {
-                    const int i = o - MN;
-                    const double r = dyn_row(i, P, PNX, sg, true), t = P[PN + i];
-                    const double sm_ = S[o], sp = S[o + NX], zm = Z[o], zp = Z[o + NX];
+            // ---- model cones
+#pragma unroll
+            for (int c = 0; c < NCONE; c++) {
+                const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
+                double sk[soc::SOC_MAXD], zk[soc::SOC_MAXD], w[soc::SOC_MAXD], lm[soc::SOC_MAXD];
+#pragma unroll
+                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) {
+                    const RowDesc rd = M::crow(o + r);
+                    const double hh = row_h(rd), sl = hh - row_dot(o + r, k, prim);
+                    sk[r] = s[(o + r) * KS + k]; zk[r] = z[(o + r) * KS + k];
+                    const double rv = sk[r] - sl;
+                    rz[(o + r) * KS + k] = rv;
+                    h2 += hh * hh; gap += sk[r] * zk[r]; rz2 += rv * rv; zrz += zk[r] * rv;
+                    row_scatter(o + r, k, zk[r], RXa);
+                }
+                double e2i = 1.;
+                if (identity) {
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) { w[r] = r == 0; lm[r] = r == 0; }
+                } else if (!soc::scale(sk, zk, d, w, e2i, lm)) {
+                    bad = 1;
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) { w[r] = r == 0; lm[r] = r == 0; }
+                }
+#pragma unroll
+                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) { wb[(o + r) * KS + k] = w[r]; lam[(o + r) * KS + k] = lm[r]; }
+                ce[c * KS + k] = e2i;
+            }
+            // ---- model LP rows
+#pragma unroll
+            for (int r = 0; r < NLP; r++) {
+                const RowDesc rd = M::crow(r);
+                const double hh = row_h(rd), sl = hh - row_dot(r, k, prim);
+                const double sv = s[r * KS + k], zv = z[r * KS + k];
+                const double rv = sv - sl;
+                rz[r * KS + k] = rv;
+                h2 += hh * hh;
+                if (!(sv > 0.) || !(zv > 0.)) bad = 1;
+                wb[r * KS + k] = identity ? 1. : zv / sv; lam[r * KS + k] = identity ? 1. : sqrt(sv * zv);
+                gap += sv * zv; rz2 += rv * rv; zrz += zv * rv;
+                row_scatter(r, k, zv, RXa);
+            }
+            // ---- interval k: virtual-control pairs  t_i >= |r_i| ,  r = x_{k+1} - A~ xi_k - C u_{k+1} - s sigma - z
+            if (hasint) {
+                double UN[NU];
+#pragma unroll
+                for (int a = 0; a < NU; a++) UN[a] = prim[(NX + a) * KS + k + 1];
+#pragma unroll 2
+                for (int i = 0; i < NX; i++) {
+                    const int o = MN + i;
+                    const double sm_ = s[o * KS + k], sp = s[(o + NX) * KS + k], zm = z[o * KS + k], zp = z[(o + NX) * KS + k];
+                    const double wi = zm - zp;
+                    double acc = prim[i * KS + k + 1], acc2 = 0;
+#pragma unroll
+                    for (int j = 0; j < NB; j += 2) {
+                        const double t0 = T(i, j, k), t1 = T(i, j + 1, k);
+                        acc -= t0 * P[j]; acc2 -= t1 * P[j + 1];
+                        RXa[j] -= t0 * wi; RXa[j + 1] -= t1 * wi;
+                    }
+#pragma unroll
+                    for (int a = 0; a < NU; a++) acc2 -= T(i, NB + a, k) * UN[a];
+                    const double tsg = T(i, NB + NU, k), zc = T(i, NB + NU + 1, k);
+                    const double r = acc + acc2 - tsg * sg - zc;
+                    acc_sig -= tsg * wi;
+                    const double t = prim[(PN + i) * KS + k];
                     const double rm = sm_ - (t - r), rp = sp - (t + r);
-                    RZ[o] = rm; RZ[o + NX] = rp;
+                    rz[o * KS + k] = rm; rz[(o + NX) * KS + k] = rp;
                     if (!(sm_ > 0.) || !(sp > 0.) || !(zm > 0.) || !(zp > 0.)) bad = 1;
-                    WB[o] = identity ? 1. : zm / sm_; WB[o + NX] = identity ? 1. : zp / sp;
-                    LM[o] = identity ? 1. : sqrt(sm_ * zm); LM[o + NX] = identity ? 1. : sqrt(sp * zp);
-                    RX[PN + i] = w_vc - zm - zp;
-                    w[i] = zm - zp;
+                    wb[o * KS + k] = identity ? 1. : zm / sm_; wb[(o + NX) * KS + k] = identity ? 1. : zp / sp;
+                    lam[o * KS + k] = identity ? 1. : sqrt(sm_ * zm); lam[(o + NX) * KS + k] = identity ? 1. : sqrt(sp * zp);
+                    const double rxt = w_vc - zm - zp;
+                    rx[(PN + i) * KS + k] = rxt;
+                    rx2 += rxt * rxt; xrx += t * rxt;
                     gap += sm_ * zm + sp * zp; rz2 += rm * rm + rp * rp; zrz += zm * rm + zp * rp;
                     pcost += w_vc * t;
-                    const double zc = tile()[i * NCP + NB + NU + 1];
                     h2 += 2. * zc * zc;
-                } else {
-                    const int i = o - MN;
-                    RZ[o] = 0.; RZ[o + NX] = 0.; WB[o] = 1.; WB[o + NX] = 1.; LM[o] = 1.; LM[o + NX] = 1.; RX[PN + i] = 0.;
+                }
+            } else {
+#pragma unroll 2
+                for (int i = 0; i < NX; i++) {
+                    const int o = MN + i;
+                    rz[o * KS + k] = 0.; rz[(o + NX) * KS + k] = 0.; wb[o * KS + k] = 1.; wb[(o + NX) * KS + k] = 1.;
+                    lam[o * KS + k] = 1.; lam[(o + NX) * KS + k] = 1.; rx[(PN + i) * KS + k] = 0.;
                 }
             }
-            warp_sync();
-            // ---- dual residual of node k: carry from interval k-1 + G'z of the node cones (+ interval k below)
-            FOR_LANE(j, NB) RX[j] = carry[j] + Z[TRO + 1 + j] + model_GT(j, k, Z);
-            if (lane_id() == 0) RX[NB] = w_tr - Z[TRO];
-            warp_sync();
-            if (hasint) acc_sig += dyn_JT(w, RX, carry);
-            warp_sync();
-            FOR_LANE(e, PN + NX) {
-                if (e < NB && fixed(k, e)) RX[e] = 0.;
-                rx2 += RX[e] * RX[e]; xrx += P[e] * RX[e];
+            // ---- coupling from interval k-1:  [w ; -C' w],  w = z- - z+ of that interval
+            if (k > 0) {
+#pragma unroll
+                for (int i = 0; i < NX; i++) {
+                    const double wp = z[(MN + i) * KS + k - 1] - z[(MN + NX + i) * KS + k - 1];
+                    RXa[i] += wp;
+#pragma unroll
+                    for (int a = 0; a < NU; a++) RXa[NX + a] -= T(i, NB + a, k - 1) * wp;
+                }
             }
-            warp_sync();
-            st(rz + k * RS, RZ, RS); st(wb + k * RS, WB, RS); st(lam + k * RS, LM, RS);
-            st(rx + k * PS, RX, PN + NX);
-            FOR_LANE(c, NCN) ce[k * CS + c] = CE[c];
-            warp_sync();
+            const uint32_t mk = fixm[k];
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                const double v = ((mk >> j) & 1u) ? 0. : RXa[j];
+                rx[j * KS + k] = v;
+                rx2 += v * v; xrx += P[j] * v;
+            }
         }
         acc_sig = warp_sum(acc_sig);
         // ---- globals: lane 0
         if (lane_id() == 0) {
-            const int r0 = K * RS, c0 = K * CS, p0 = K * PS;
+            const int r0 = RS * KS, c0 = NCN * KS, p0 = PSN * KS;
             const double dsg = prim[p0 + 1];
             double rxs = w_time + acc_sig;
             rz[r0] = s[r0] - (sg - 0.001);                          // sigma >= 0.001   (SCProblem.cpp:34)
@@ -585,9 +567,9 @@ struct Ipm {
     }
 
     // =============================================================================================================
-    //  Phase F : assemble the reduced Hessian stage by stage and factor it (block-tridiagonal Cholesky + border)
+    //  chain phase F : assemble the reduced Hessian stage by stage and factor it (block-tridiagonal Cholesky + border)
     // =============================================================================================================
-    SCPP_HD void build_model_terms(int k, const double *WB, const double *CE, double *alpha)
+    SCPP_HD void build_model_terms(const double *WB, const double *CE, double *alpha)
     {
         double *rk = sm + W_RK, *dg = rk + NRK * NB;
         FOR_LANE(e, 2 * NRK * NB) rk[e] = 0.;
@@ -625,9 +607,9 @@ struct Ipm {
     {
         double *H = sm + W_MAT, *O = H + BLK, *Lp = sm + W_LP;
         double *Dp = sm + W_HN, *DCp = Dp + NX, *CDCp = DCp + NX * NU;   // carry of interval k-1: D | D C | C' D C
-        double *F = facw();                 // Linv | Lnext | l | f   (the record written for this stage)
+        double *F = facw();                 // Linv | Lnext | l   (the record written for this stage)
         double *Li = F, *Ln = F + OFF_LN, *lk = F + OFF_L;
-        double *WB = row(0), *CE = sc() + 8, *alpha = sc();
+        double *WB = sm + W_WB, *CE = sc() + 8, *alpha = sc();
         double *bk = vec(0), *bn = vec(1), *lprev = vec(2);
         double *Dt = xv(1);
         double corner = 0.;
@@ -640,10 +622,12 @@ struct Ipm {
         for (int k = 0; k < K; k++) {
             const bool hasint = k < K - 1;
             if (hasint) ld_dd(k);
-            ld(WB, wb + k * RS, RS); ld(CE, ce + k * CS, CS);
+            ld_commit();
+            FOR_LANE(r, RS) WB[r] = wb[r * KS + k];
+            FOR_LANE(c, NCN) CE[c] = ce[c * KS + k];
             tables_stage(k);
             ld_wait();
-            build_model_terms(k, WB, CE, alpha);
+            build_model_terms(WB, CE, alpha);
             // ---- node part of H_kk (trust region with delta eliminated) + carry from interval k-1
             {
                 const double *rk = sm + W_RK, *dg = rk + NRK * NB;
@@ -782,17 +766,17 @@ struct Ipm {
                 lk[j] = v; corner -= v * v;
             }
             warp_sync();
-            st(fac + (size_t)k * FS, F, OFF_F);
+            st(fac + (size_t)k * FS, F, FS);
             FOR_LANE(e, BLK) Lp[e] = Ln[e];
             FOR_LANE(j, NB) lprev[j] = lk[j];
             warp_sync();
         }
         corner = warp_sum(corner);
         {   // globals: sigma >= 0.001 row and the sigma trust-region cone with delta_sigma eliminated
-            const int r0 = K * RS;
+            const int r0 = RS * KS;
             const double d = wb[r0];
             double w3[3] = {wb[r0 + 1], wb[r0 + 2], wb[r0 + 3]};
-            const double e2i = ce[K * CS];
+            const double e2i = ce[NCN * KS];
             double g[3] = {-0.5, 0.5, 0.}, p[3], e2[3] = {0., 0., 1.}, m2[3];
             soc::Mv(w3, e2i, g, 3, p);
             const double kap = g[0] * p[0] + g[1] * p[1];
@@ -809,153 +793,419 @@ struct Ipm {
     //     mode 0: rxv = dprim (array), rzv = ds (array)                        [starting point]
     //     mode 1: rxv = -rx,            rzv = -rz + s                          [affine direction]
     //     mode 2: rxv = -(1-sig) rx,    rzv = -(1-sig) rz - W (lam \ d_s),  d_s = -lam o lam - cr + sig mu e   [combined]
-    //  forward sweep: right-hand side + forward substitution; backward sweep: back substitution + recovery of the
-    //  local variables, dz and ds = rzs*rz - G dx, the scaled step lengths (tmax) and, for mode 1, cr = ds~ o dz~.
+    //  pass A (stage-parallel): right-hand sides rzv (kept in ds) and g ; chain: forward and backward substitution ;
+    //  pass B (stage-parallel): recovery of the local variables, dz and ds = rzs*rz - G dx, the scaled step lengths (tmax)
+    //  and, for mode 1, cr = ds~ o dz~.
     // =============================================================================================================
-    SCPP_HD void gen_rhs(int mode, bool hasint, double csig, double sigmu, double *RZV, double *RXV, double *T1,
-                         const double *S_, const double *RZ, const double *LM, const double *CR, const double *WB, const double *CE, const double *RXW)
+    SCPP_HD double rxv_of(int mode, double csig, int e, int k) const
     {
-        if (mode == 1) {
-            FOR_LANE(e, RS) RZV[e] = -RZ[e] + S_[e];
-            FOR_LANE(e, PS) RXV[e] = -RXW[e];
-        } else {
-            FOR_LANE(e, PS) RXV[e] = -csig * RXW[e];
-            {   // trust-region cone (warp-cooperative): rzv = -csig rz - W (lam \ (-lam o lam - cr + sigmu e))
-                const int o = TRO;
-                const double *lm = LM + o, *w = WB + o;
-                double ll = 0;
-                FOR_LANE(i, D) ll += lm[i] * lm[i];
-                ll = warp_sum(ll);
-                const double l0 = lm[0], den = 2. * l0 * l0 - ll;
-                double l1d1 = 0;
-                FOR_LANE(i, D) {
-                    const double dv = (i == 0) ? -ll - CR[o] + sigmu : -2. * l0 * lm[i] - CR[o + i];
-                    T1[o + i] = dv;
-                    if (i > 0) l1d1 += lm[i] * dv;
-                }
-                l1d1 = warp_sum(l1d1);
-                warp_sync();
-                const double x0 = (l0 * T1[o] - l1d1) / den;
-                warp_sync();
-                FOR_LANE(i, D) T1[o + i] = (i == 0) ? x0 : (T1[o + i] - x0 * lm[i]) / l0;
-                warp_sync();
-                tr_Wv(w, CE[NCONE], T1 + o, T1 + o, false);
-                FOR_LANE(i, D) RZV[o + i] = -csig * RZ[o + i] - T1[o + i];
-            }
-            FOR_LANE(tk, NTASK) {
-                if (tk == NCONE) continue;
-                int type, o, d, ci;
-                task(tk, type, o, d, ci);
-                if (type == 1) {
-                    double *t1 = T1 + o;
-                    soc::jprod(LM + o, LM + o, d, t1);
-#pragma unroll 1
-                    for (int i = 0; i < d; i++) t1[i] = -t1[i] - CR[o + i];
-                    t1[0] += sigmu;
-                    soc::jdiv(LM + o, t1, d, t1);
-                    soc::Wv(WB + o, CE[ci], t1, d, t1, false);
-#pragma unroll 1
-                    for (int i = 0; i < d; i++) RZV[o + i] = -csig * RZ[o + i] - t1[i];
+        return mode == 0 ? dprim[e * KS + k] : (mode == 1 ? -rx[e * KS + k] : -csig * rx[e * KS + k]);
+    }
+
+    SCPP_HD double pass_rhs(int mode, double csig, double sigmu)   // returns the lane-partial of the sigma right-hand side
+    {
+        double gsig = 0;
+        FOR_LANE(k, K) {
+            const bool hasint = k < K - 1;
+            double G[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++) G[j] = rxv_of(mode, csig, j, k);
+            // ---- trust region: rzv, then v = M rzv - p (p'rzv + rx_delta)/kap ,  p = M(-e0)
+            {
+                double w[D], q[D];
+                const double e2i = ce[NCONE * KS + k];
+#pragma unroll
+                for (int i = 0; i < D; i++) w[i] = wb[(TRO + i) * KS + k];
+                if (mode == 0) {
+#pragma unroll
+                    for (int i = 0; i < D; i++) q[i] = ds[(TRO + i) * KS + k];
+                } else if (mode == 1) {
+#pragma unroll
+                    for (int i = 0; i < D; i++) q[i] = -rz[(TRO + i) * KS + k] + s[(TRO + i) * KS + k];
                 } else {
-                    const int reps = (type == 2) ? 2 : 1;
-                    if (type == 2 && !hasint) { RZV[o] = 0.; RZV[o + NX] = 0.; continue; }
-                    for (int q = 0; q < reps; q++) {
-                        const int oo = o + q * NX;
-                        const double wv = sqrt(1. / WB[oo]);
-                        const double t1 = (-LM[oo] * LM[oo] - CR[oo] + sigmu) / LM[oo];
-                        RZV[oo] = -csig * RZ[oo] - wv * t1;
+                    double lm[D];
+                    double ll = 0;
+#pragma unroll
+                    for (int i = 0; i < D; i++) { lm[i] = lam[(TRO + i) * KS + k]; ll += lm[i] * lm[i]; }
+                    const double l0 = lm[0], den = 2. * l0 * l0 - ll;
+                    double l1d1 = 0;
+#pragma unroll
+                    for (int i = 1; i < D; i++) { const double dv = -2. * l0 * lm[i] - cr[(TRO + i) * KS + k]; q[i] = dv; l1d1 += lm[i] * dv; }
+                    const double dv0 = -ll - cr[TRO * KS + k] + sigmu;
+                    const double x0 = (l0 * dv0 - l1d1) / den, il0 = 1. / l0;
+                    double w1v1 = 0;
+#pragma unroll
+                    for (int i = 1; i < D; i++) { q[i] = (q[i] - x0 * lm[i]) * il0; w1v1 += w[i] * q[i]; }
+                    // W (lam \ d_s)
+                    const double eta = 1. / sqrt(e2i), f = x0 + w1v1 / (1. + w[0]);
+                    q[0] = -csig * rz[TRO * KS + k] - eta * (w[0] * x0 + w1v1);
+#pragma unroll
+                    for (int i = 1; i < D; i++) q[i] = -csig * rz[(TRO + i) * KS + k] - eta * (q[i] + f * w[i]);
+                }
+                if (mode != 0) {
+#pragma unroll
+                    for (int i = 0; i < D; i++) ds[(TRO + i) * KS + k] = q[i];
+                }
+                const double w0 = w[0], kap = e2i * (2. * w0 * w0 - 1.);
+                double dot = w0 * q[0], prz = -kap * q[0];
+#pragma unroll
+                for (int i = 1; i < D; i++) { dot -= w[i] * q[i]; prz += 2. * e2i * w0 * w[i] * q[i]; }
+                const double rho = (prz + rxv_of(mode, csig, NB, k)) / kap;
+#pragma unroll
+                for (int i = 1; i < D; i++) G[i - 1] += e2i * (-2. * dot * w[i] + q[i]) - 2. * e2i * w0 * w[i] * rho;
+            }
+            // ---- model cones
+#pragma unroll
+            for (int c = 0; c < NCONE; c++) {
+                const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
+                double w[soc::SOC_MAXD], t1[soc::SOC_MAXD];
+                const double e2i = ce[c * KS + k];
+#pragma unroll
+                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) w[r] = wb[(o + r) * KS + k];
+                if (mode == 0) {
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = ds[(o + r) * KS + k];
+                } else if (mode == 1) {
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = -rz[(o + r) * KS + k] + s[(o + r) * KS + k];
+                } else {
+                    double lm[soc::SOC_MAXD];
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) lm[r] = lam[(o + r) * KS + k];
+                    soc::jprod(lm, lm, d, t1);
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = -t1[r] - cr[(o + r) * KS + k];
+                    t1[0] += sigmu;
+                    soc::jdiv(lm, t1, d, t1);
+                    soc::Wv(w, e2i, t1, d, t1, false);
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = -csig * rz[(o + r) * KS + k] - t1[r];
+                }
+                if (mode != 0) {
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) ds[(o + r) * KS + k] = t1[r];
+                }
+                soc::Mv(w, e2i, t1, d, t1);
+#pragma unroll
+                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) row_scatter(o + r, k, t1[r], G);
+            }
+            // ---- LP rows
+#pragma unroll
+            for (int r = 0; r < NLP; r++) {
+                const double dv = wb[r * KS + k];
+                double rzv;
+                if (mode == 0) rzv = ds[r * KS + k];
+                else if (mode == 1) rzv = -rz[r * KS + k] + s[r * KS + k];
+                else { const double lm = lam[r * KS + k]; rzv = -csig * rz[r * KS + k] - sqrt(1. / dv) * ((-lm * lm - cr[r * KS + k] + sigmu) / lm); }
+                if (mode != 0) ds[r * KS + k] = rzv;
+                row_scatter(r, k, dv * rzv, G);
+            }
+            // ---- interval pairs: t eliminated, w_i couples to nodes k and k+1
+            if (hasint) {
+#pragma unroll 2
+                for (int i = 0; i < NX; i++) {
+                    const int o = MN + i;
+                    const double dm = wb[o * KS + k], dp = wb[(o + NX) * KS + k];
+                    double rm, rp;
+                    if (mode == 0) { rm = ds[o * KS + k]; rp = ds[(o + NX) * KS + k]; }
+                    else if (mode == 1) { rm = -rz[o * KS + k] + s[o * KS + k]; rp = -rz[(o + NX) * KS + k] + s[(o + NX) * KS + k]; }
+                    else {
+                        const double lmm = lam[o * KS + k], lmp = lam[(o + NX) * KS + k];
+                        rm = -csig * rz[o * KS + k] - sqrt(1. / dm) * ((-lmm * lmm - cr[o * KS + k] + sigmu) / lmm);
+                        rp = -csig * rz[(o + NX) * KS + k] - sqrt(1. / dp) * ((-lmp * lmp - cr[(o + NX) * KS + k] + sigmu) / lmp);
+                    }
+                    if (mode != 0) { ds[o * KS + k] = rm; ds[(o + NX) * KS + k] = rp; }
+                    const double rho = (-(dm * rm + dp * rp) + rxv_of(mode, csig, PN + i, k)) / (dm + dp);
+                    const double wi = dm * (rm + rho) - dp * (rp + rho);
+                    wv[i * KS + k] = wi;
+#pragma unroll
+                    for (int j = 0; j < NB; j++) G[j] -= T(i, j, k) * wi;
+                    gsig -= T(i, NB + NU, k) * wi;
+                }
+            } else if (mode != 0) {
+#pragma unroll 2
+                for (int i = 0; i < NX; i++) { ds[(MN + i) * KS + k] = 0.; ds[(MN + NX + i) * KS + k] = 0.; }
+            }
+#pragma unroll
+            for (int j = 0; j < NB; j++) gv[j * KS + k] = G[j];
+        }
+        warp_sync();
+        // ---- coupling from interval k-1 and the pinned variables
+        FOR_LANE(k, K) {
+            const uint32_t mk = fixm[k];
+            double C[NU];
+#pragma unroll
+            for (int a = 0; a < NU; a++) C[a] = 0.;
+            if (k > 0) {
+#pragma unroll
+                for (int i = 0; i < NX; i++) {
+                    const double wp = wv[i * KS + k - 1];
+                    gv[i * KS + k] = ((mk >> i) & 1u) ? 0. : gv[i * KS + k] + wp;
+#pragma unroll
+                    for (int a = 0; a < NU; a++) C[a] -= T(i, NB + a, k - 1) * wp;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NX; i++) if ((mk >> i) & 1u) gv[i * KS + k] = 0.;
+            }
+#pragma unroll
+            for (int a = 0; a < NU; a++) gv[(NX + a) * KS + k] = ((mk >> (NX + a)) & 1u) ? 0. : gv[(NX + a) * KS + k] + C[a];
+        }
+        warp_sync();
+        return gsig;
+    }
+
+    // forward substitution  f_k = Linv_k (g_k - L_{k,k-1} f_{k-1})  in place in gv ; returns the lane-partial of  sum_k l_k' f_k
+    SCPP_HD double chain_forward()
+    {
+        double *fprev = vec(0), *tmp = vec(1);
+        double ldot = 0;
+        ld(fbuf(0), fac, FS); ld_commit();
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            if (k + 1 < K) ld(fbuf((k + 1) % 3), fac + (size_t)(k + 1) * FS, FS);
+            ld_commit();
+            const int j = lane_id();
+            double g = 0.;
+            if (LANES > 1 && j < NB) g = gv[j * KS + k];
+            ld_wait(1);
+            const double *F = fbuf(k % 3), *Lp = fbuf((k + 2) % 3) + OFF_LN;     // L_{k,k-1} sits in the record of stage k-1
+            FOR_LANE(jj, NB) {
+                double v = (LANES > 1) ? g : gv[jj * KS + k];
+                if (k > 0) {
+                    double v2 = 0;
+#pragma unroll
+                    for (int c = 0; c < NB; c += 2) { v -= Lp[jj * NB + c] * fprev[c]; v2 -= Lp[jj * NB + c + 1] * fprev[c + 1]; }
+                    v += v2;
+                }
+                tmp[jj] = v;
+            }
+            warp_sync();
+            FOR_LANE(jj, NB) {
+                double v = 0, v2 = 0;
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) { v += F[jj * NB + c] * tmp[c]; v2 += F[jj * NB + c + 1] * tmp[c + 1]; }
+                v += v2;
+                fprev[jj] = v;
+                gv[jj * KS + k] = v;
+                ldot += F[OFF_L + jj] * v;
+            }
+            warp_sync();
+        }
+        ld_wait();
+        return ldot;
+    }
+    // back substitution  y_k = Linv_k' (f_k - L_{k+1,k}' y_{k+1} - l_k y_sigma)  in place in gv
+    SCPP_HD void chain_backward(double ysig)
+    {
+        double *ynext = vec(0), *tmp = vec(1);
+        ld(fbuf((K - 1) % 3), fac + (size_t)(K - 1) * FS, FS); ld_commit();
+#pragma unroll 1
+        for (int k = K - 1; k >= 0; k--) {
+            const bool hasint = k < K - 1;
+            if (k > 0) ld(fbuf((k - 1) % 3), fac + (size_t)(k - 1) * FS, FS);
+            ld_commit();
+            const int j = lane_id();
+            double f = 0.;
+            if (LANES > 1 && j < NB) f = gv[j * KS + k];
+            const uint32_t mk = fixm[k];
+            ld_wait(1);
+            const double *F = fbuf(k % 3);
+            FOR_LANE(jj, NB) {
+                double v = ((LANES > 1) ? f : gv[jj * KS + k]) - F[OFF_L + jj] * ysig;
+                if (hasint) {
+                    double v2 = 0;
+#pragma unroll
+                    for (int c = 0; c < NB; c += 2) { v -= F[OFF_LN + c * NB + jj] * ynext[c]; v2 -= F[OFF_LN + (c + 1) * NB + jj] * ynext[c + 1]; }
+                    v += v2;
+                }
+                tmp[jj] = v;
+            }
+            warp_sync();
+            FOR_LANE(jj, NB) {
+                double v = 0, v2 = 0;
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) { v += F[c * NB + jj] * tmp[c]; v2 += F[(c + 1) * NB + jj] * tmp[c + 1]; }
+                v += v2;
+                if ((mk >> jj) & 1u) v = 0.;
+                ynext[jj] = v;
+                gv[jj * KS + k] = v;
+            }
+            warp_sync();
+        }
+        ld_wait();
+    }
+
+    SCPP_HD double pass_recover(int mode, double csig, double rzs, double ysig)   // returns the lane-partial of tmax
+    {
+        double tmax = 0;
+        FOR_LANE(k, K) {
+            const bool hasint = k < K - 1;
+            double yk[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++) { yk[j] = gv[j * KS + k]; dprim[j * KS + k] = yk[j]; }
+            // ---- trust region
+            {
+                double w[D], q[D];
+                const double e2i = ce[NCONE * KS + k];
+#pragma unroll
+                for (int i = 0; i < D; i++) w[i] = wb[(TRO + i) * KS + k];
+                const double w0 = w[0], kap = e2i * (2. * w0 * w0 - 1.);
+                q[0] = -ds[TRO * KS + k];
+                double pq = -kap * q[0], dot = w0 * q[0];
+#pragma unroll
+                for (int i = 1; i < D; i++) { q[i] = yk[i - 1] - ds[(TRO + i) * KS + k]; pq += 2. * e2i * w0 * w[i] * q[i]; dot -= w[i] * q[i]; }
+                const double ddl = (rxv_of(mode, csig, NB, k) - pq) / kap;
+                dprim[NB * KS + k] = ddl;
+                // dz = M q + p ddl   (in q)
+                q[0] = e2i * (2. * dot * w0 - q[0]) - kap * ddl;
+#pragma unroll
+                for (int i = 1; i < D; i++) q[i] = e2i * (-2. * dot * w[i] + q[i]) + 2. * e2i * w0 * w[i] * ddl;
+#pragma unroll
+                for (int i = 0; i < D; i++) dz[(TRO + i) * KS + k] = q[i];
+                if (mode != 0) {
+                    double dsv[D];
+                    dsv[0] = rzs * rz[TRO * KS + k] + ddl;
+                    double w1z = 0, w1s = 0;
+#pragma unroll
+                    for (int i = 1; i < D; i++) { dsv[i] = rzs * rz[(TRO + i) * KS + k] - yk[i - 1]; w1z += w[i] * q[i]; w1s += w[i] * dsv[i]; }
+#pragma unroll
+                    for (int i = 0; i < D; i++) ds[(TRO + i) * KS + k] = dsv[i];
+                    // scaled directions  dz~ = W dz (in q),  ds~ = W^-1 ds (in dsv)
+                    const double eta = 1. / sqrt(e2i), ieta = 1. / eta;
+                    const double fz = q[0] + w1z / (1. + w0), fs = -dsv[0] + w1s / (1. + w0);
+                    const double z0 = eta * (w0 * q[0] + w1z), s0 = ieta * (w0 * dsv[0] - w1s);
+                    double l1 = 0, a1 = 0, a2 = 0, cr0 = s0 * z0;
+                    const double lm0 = lam[TRO * KS + k];
+#pragma unroll
+                    for (int i = 1; i < D; i++) {
+                        const double lmi = lam[(TRO + i) * KS + k];
+                        q[i] = eta * (q[i] + fz * w[i]); dsv[i] = ieta * (dsv[i] + fs * w[i]);
+                        l1 += lmi * lmi; a1 += lmi * dsv[i]; a2 += lmi * q[i];
+                        cr0 += dsv[i] * q[i];
+                        w[i] = lmi;                                         // w is free from here on: keep lam
+                    }
+                    const double ia = 1. / sqrt(lm0 * lm0 - l1), l0 = lm0 * ia;
+                    const double ld1 = l0 * s0 - a1 * ia, ld2 = l0 * z0 - a2 * ia;
+                    const double il = ia / (l0 + 1.);
+                    const double f1 = (ld1 + s0) * il, f2 = (ld2 + z0) * il;
+                    double n1 = 0, n2 = 0;
+#pragma unroll
+                    for (int i = 1; i < D; i++) { const double r1 = dsv[i] - f1 * w[i], r2 = q[i] - f2 * w[i]; n1 += r1 * r1; n2 += r2 * r2; }
+                    tmax = fmax(tmax, fmax((sqrt(n1) - ld1) * ia, (sqrt(n2) - ld2) * ia));
+                    if (mode == 1) {
+                        cr[TRO * KS + k] = cr0;
+#pragma unroll
+                        for (int i = 1; i < D; i++) cr[(TRO + i) * KS + k] = s0 * q[i] + z0 * dsv[i];
                     }
                 }
             }
+            // ---- model cones
+#pragma unroll
+            for (int c = 0; c < NCONE; c++) {
+                const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
+                double w[soc::SOC_MAXD], q[soc::SOC_MAXD], gdx[soc::SOC_MAXD], lm[soc::SOC_MAXD];
+                const double e2i = ce[c * KS + k];
+#pragma unroll
+                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) {
+                    w[r] = wb[(o + r) * KS + k];
+                    gdx[r] = row_dot(o + r, k, gv);
+                    q[r] = gdx[r] - ds[(o + r) * KS + k];
+                }
+                soc::Mv(w, e2i, q, d, q);                                   // dz
+#pragma unroll
+                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) dz[(o + r) * KS + k] = q[r];
+                if (mode != 0) {
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) {
+                        gdx[r] = rzs * rz[(o + r) * KS + k] - gdx[r];       // ds
+                        ds[(o + r) * KS + k] = gdx[r];
+                        lm[r] = lam[(o + r) * KS + k];
+                    }
+                    soc::Wv(w, e2i, q, d, q, false);                        // dz~
+                    soc::Wv(w, e2i, gdx, d, gdx, true);                     // ds~
+                    tmax = fmax(tmax, fmax(soc::step(lm, gdx, d), soc::step(lm, q, d)));
+                    if (mode == 1) {
+                        soc::jprod(gdx, q, d, q);
+#pragma unroll
+                        for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) cr[(o + r) * KS + k] = q[r];
+                    }
+                }
+            }
+            // ---- LP rows
+#pragma unroll
+            for (int r = 0; r < NLP; r++) {
+                const double gdx = row_dot(r, k, gv), dv = wb[r * KS + k];
+                const double dzv = dv * (gdx - ds[r * KS + k]);
+                dz[r * KS + k] = dzv;
+                if (mode != 0) {
+                    const double dsv = rzs * rz[r * KS + k] - gdx;
+                    ds[r * KS + k] = dsv;
+                    const double iw = sqrt(dv), il = 1. / lam[r * KS + k];       // W = 1/sqrt(wb)
+                    const double dzt = dzv / iw, dst = dsv * iw;
+                    tmax = fmax(tmax, fmax(-dst, -dzt) * il);
+                    if (mode == 1) cr[r * KS + k] = dst * dzt;
+                }
+            }
+            // ---- interval pairs
+            if (hasint) {
+                double XNu[NU];
+#pragma unroll
+                for (int a = 0; a < NU; a++) XNu[a] = gv[(NX + a) * KS + k + 1];
+#pragma unroll 2
+                for (int i = 0; i < NX; i++) {
+                    const int o = MN + i;
+                    double acc = gv[i * KS + k + 1], acc2 = 0;
+#pragma unroll
+                    for (int j = 0; j < NB; j += 2) { acc -= T(i, j, k) * yk[j]; acc2 -= T(i, j + 1, k) * yk[j + 1]; }
+#pragma unroll
+                    for (int a = 0; a < NU; a++) acc2 -= T(i, NB + a, k) * XNu[a];
+                    const double ady = acc + acc2 - T(i, NB + NU, k) * ysig;
+                    const double dm = wb[o * KS + k], dp = wb[(o + NX) * KS + k];
+                    const double qm = ady - ds[o * KS + k], qp = -ady - ds[(o + NX) * KS + k];
+                    const double dt = (rxv_of(mode, csig, PN + i, k) + dm * qm + dp * qp) / (dm + dp);
+                    const double dzm = dm * (qm - dt), dzp = dp * (qp - dt);
+                    dz[o * KS + k] = dzm; dz[(o + NX) * KS + k] = dzp;
+                    dprim[(PN + i) * KS + k] = dt;
+                    if (mode != 0) {
+                        const double dsm = rzs * rz[o * KS + k] - (ady - dt), dsp = rzs * rz[(o + NX) * KS + k] - (-ady - dt);
+                        ds[o * KS + k] = dsm; ds[(o + NX) * KS + k] = dsp;
+                        {
+                            const double iw = sqrt(dm), il = 1. / lam[o * KS + k];
+                            const double dzt = dzm / iw, dst = dsm * iw;
+                            tmax = fmax(tmax, fmax(-dst, -dzt) * il);
+                            if (mode == 1) cr[o * KS + k] = dst * dzt;
+                        }
+                        {
+                            const double iw = sqrt(dp), il = 1. / lam[(o + NX) * KS + k];
+                            const double dzt = dzp / iw, dst = dsp * iw;
+                            tmax = fmax(tmax, fmax(-dst, -dzt) * il);
+                            if (mode == 1) cr[(o + NX) * KS + k] = dst * dzt;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 2
+                for (int i = 0; i < NX; i++) {
+                    const int o = MN + i;
+                    dprim[(PN + i) * KS + k] = 0.; dz[o * KS + k] = 0.; dz[(o + NX) * KS + k] = 0.;
+                    if (mode != 0) { ds[o * KS + k] = 0.; ds[(o + NX) * KS + k] = 0.; if (mode == 1) { cr[o * KS + k] = 0.; cr[(o + NX) * KS + k] = 0.; } }
+                }
+            }
         }
+        return tmax;
     }
 
     SCPP_HD void phase_solve(int mode, double csig, double sigmu, double rzs, double &tmax_out)
     {
-        double *WB = row(0), *RZV = row(1), *V = row(2), *RZ = row(3), *LM = row(4), *CR = row(5), *S_ = row(6), *DZ = row(7);
-        double *RXV = pw(0), *RXW = pw(1), *DP = pw(2), *CE = sc() + 8;
-        double *F = facw();
-        double *carry = vec(0), *g = vec(1), *tmp = vec(2), *fprev = vec(3), *Lp = sm + W_LP;   // Lp: L_{k,k-1}
-        double *w = xv(0);
-        const int r0g = K * RS, p0g = K * PS;
-        // ---------------- forward sweep ----------------
-        double gsig = 0, ldot = 0;
-        FOR_LANE(j, NB) { carry[j] = 0.; fprev[j] = 0.; }
-#pragma unroll 1
-        for (int k = 0; k < K; k++) {
-            const bool hasint = k < K - 1;
-            if (hasint) ld_dd(k);
-            ld(F, fac + (size_t)k * FS, OFF_F);
-            ld(WB, wb + k * RS, RS); ld(CE, ce + k * CS, CS);
-            if (mode == 0) { ld(RZV, ds + k * RS, RS); ld(RXV, dprim + k * PS, PS); }
-            else {
-                ld(RZ, rz + k * RS, RS); ld(RXW, rx + k * PS, PS);
-                if (mode == 1) ld(S_, s + k * RS, RS);
-                else { ld(LM, lam + k * RS, RS); ld(CR, cr + k * RS, RS); }
-            }
-            tables_stage(k);
-            ld_wait();
-            if (mode != 0) { gen_rhs(mode, hasint, csig, sigmu, RZV, RXV, V, S_, RZ, LM, CR, WB, CE, RXW); warp_sync(); }
-            // ---- v_c = Mtilde rzv per cone; pairs produce w_i
-            {   // trust region (warp-cooperative): v = M rzv - p (p'rzv + rx_delta)/kap ,  p = M(-e0)
-                const int o = TRO;
-                const double *w = WB + o;
-                const double e2i = CE[NCONE], w0 = w[0];
-                tr_Mv(w, e2i, RZV + o, V + o);
-                double prz = 0;
-                FOR_LANE(i, D) { const double p = (i == 0) ? -e2i * (2. * w0 * w0 - 1.) : 2. * e2i * w0 * w[i]; prz += p * RZV[o + i]; }
-                prz = warp_sum(prz);
-                const double rho = (prz + RXV[NB]) / (e2i * (2. * w0 * w0 - 1.));
-                FOR_LANE(i, D) { const double p = (i == 0) ? -e2i * (2. * w0 * w0 - 1.) : 2. * e2i * w0 * w[i]; V[o + i] -= p * rho; }
-            }
-            FOR_LANE(tk, NTASK) {
-                if (tk == NCONE) continue;
-                int type, o, d, ci;
-                task(tk, type, o, d, ci);
-                if (type == 1) soc::Mv(WB + o, CE[ci], RZV + o, d, V + o);
-                else if (type == 0) V[o] = WB[o] * RZV[o];
-                else if (hasint) {
-                    const int i = o - MN;
-                    const double dm = WB[o], dp = WB[o + NX], rm = RZV[o], rp = RZV[o + NX];
-                    const double rho = (-(dm * rm + dp * rp) + RXV[PN + i]) / (dm + dp);
-                    w[i] = dm * (rm + rho) - dp * (rp + rho);
-                }
-            }
-            warp_sync();
-            FOR_LANE(j, NB) g[j] = fixed(k, j) ? 0. : RXV[j] + carry[j] + V[TRO + 1 + j] + model_GT(j, k, V);
-            warp_sync();
-            if (hasint) gsig += dyn_JT(w, g, carry);
-            warp_sync();
-            // forward substitution: f_k = Linv (g_k - L_{k,k-1} f_{k-1})
-            FOR_LANE(j, NB) {
-                double v = fixed(k, j) ? 0. : g[j];
-                if (k > 0) {
-#pragma unroll
-                    for (int c = 0; c < NB; c++) v -= Lp[j * NB + c] * fprev[c];
-                }
-                tmp[j] = v;
-            }
-            warp_sync();
-            FOR_LANE(j, NB) {
-                double v = 0, v2 = 0;
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) { v += F[j * NB + c] * tmp[c]; v2 += F[j * NB + c + 1] * tmp[c + 1]; }
-                v += v2;
-                F[OFF_F + j] = v;
-                ldot += F[OFF_L + j] * v;
-            }
-            warp_sync();
-            FOR_LANE(j, NB) { fprev[j] = F[OFF_F + j]; fac[(size_t)k * FS + OFF_F + j] = F[OFF_F + j]; }
-            FOR_LANE(e, BLK) Lp[e] = F[OFF_LN + e];
-            if (mode != 0) st(ds + k * RS, RZV, RS);
-            warp_sync();
-        }
-        gsig = warp_sum(gsig);
+        const int r0g = RS * KS, p0g = PSN * KS;
+        double gsig = warp_sum(pass_rhs(mode, csig, sigmu));
+        const double ldot = warp_sum(chain_forward());
         // ---- globals: rhs and local elimination for the sigma rows (every lane computes the same scalars)
         double kap_s, p_s[3], rzg[4], rxg[2];
         {
             double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
-            const double e2i = ce[K * CS], d0 = wb[r0g];
+            const double e2i = ce[NCN * KS], d0 = wb[r0g];
             if (mode == 0) { for (int i = 0; i < 4; i++) rzg[i] = ds[r0g + i]; rxg[0] = dprim[p0g]; rxg[1] = dprim[p0g + 1]; }
             else if (mode == 1) { for (int i = 0; i < 4; i++) rzg[i] = -rz[r0g + i] + s[r0g + i]; rxg[0] = -rx[p0g]; rxg[1] = -rx[p0g + 1]; }
             else {
@@ -978,136 +1228,15 @@ struct Ipm {
             const double rho = (prz + rxg[1]) / kap_s;
             gsig += rxg[0] - d0 * rzg[0] - (v[2] - p_s[2] * rho);
         }
-        const double fsig = (gsig - warp_sum(ldot)) / l_ss;
+        const double fsig = (gsig - ldot) / l_ss;
         const double ysig = fsig / l_ss;
         warp_sync();
-        // ---------------- backward sweep ----------------
-        double tmax = 0;
-        double *ynext = vec(3), *yk = vec(4), *DS = RZV;
-        double *XN = pw(3);                 // d xi_{k+1}
-        FOR_LANE(j, NB) ynext[j] = 0.;
-#pragma unroll 1
-        for (int k = K - 1; k >= 0; k--) {
-            const bool hasint = k < K - 1;
-            if (hasint) ld_dd(k);
-            ld(F, fac + (size_t)k * FS, FS);
-            ld(WB, wb + k * RS, RS); ld(CE, ce + k * CS, CS); ld(RZV, ds + k * RS, RS);
-            if (mode == 0) ld(RXV, dprim + k * PS, PS);
-            else { ld(RXW, rx + k * PS, PS); ld(RZ, rz + k * RS, RS); ld(LM, lam + k * RS, RS); }
-            tables_stage(k);
-            ld_wait();
-            if (mode != 0) { FOR_LANE(e, PS) RXV[e] = (mode == 1 ? -1. : -csig) * RXW[e]; }
-            // back substitution: y_k = Linv' (f_k - L_{k+1,k}' y_{k+1} - l_k y_sigma)
-            FOR_LANE(j, NB) {
-                double v = F[OFF_F + j] - F[OFF_L + j] * ysig;
-                if (hasint) {
-#pragma unroll
-                    for (int c = 0; c < NB; c++) v -= F[OFF_LN + c * NB + j] * ynext[c];
-                }
-                tmp[j] = v;
-                XN[j] = ynext[j];
-            }
-            warp_sync();
-            FOR_LANE(j, NB) {
-                double v = 0, v2 = 0;
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) { v += F[c * NB + j] * tmp[c]; v2 += F[(c + 1) * NB + j] * tmp[c + 1]; }
-                v += v2;
-                yk[j] = fixed(k, j) ? 0. : v;
-            }
-            warp_sync();
-            // ---- recovery per cone: q = G dy - rzv ; local ; dz = M q + p dl ; ds = rzs rz - G dx ; scaled steps
-            //      scratch: Q = V window, GDX = S_ window (both free in the backward sweep)
-            double *Q = V, *GDX = S_;
-            {   // trust region (warp-cooperative)
-                const int o = TRO;
-                const double *w = WB + o;
-                const double e2i = CE[NCONE], w0 = w[0], kap = e2i * (2. * w0 * w0 - 1.);
-                double pq = 0;
-                FOR_LANE(i, D) {
-                    const double q = (i == 0) ? -RZV[o] : yk[i - 1] - RZV[o + i];
-                    const double p = (i == 0) ? -kap : 2. * e2i * w0 * w[i];
-                    Q[o + i] = q; pq += p * q;
-                }
-                pq = warp_sum(pq);
-                const double ddl = (RXV[NB] - pq) / kap;
-                warp_sync();
-                tr_Mv(w, e2i, Q + o, DZ + o);
-                FOR_LANE(i, D) {
-                    const double p = (i == 0) ? -kap : 2. * e2i * w0 * w[i];
-                    DZ[o + i] += p * ddl;
-                    if (mode != 0) DS[o + i] = rzs * RZ[o + i] - ((i == 0) ? -ddl : yk[i - 1]);
-                }
-                if (lane_id() == 0) DP[NB] = ddl;
-                warp_sync();
-                if (mode != 0) {
-                    tr_Wv(w, e2i, DZ + o, Q + o, false);          // dz~
-                    tr_Wv(w, e2i, DS + o, GDX + o, true);         // ds~
-                    tmax = fmax(tmax, tr_step2(LM + o, GDX + o, Q + o));
-                    if (mode == 1) tr_jprod(GDX + o, Q + o, CR + o);
-                }
-            }
-            FOR_LANE(tk, NTASK) {
-                if (tk == NCONE) continue;
-                int type, o, d, ci;
-                task(tk, type, o, d, ci);
-                if (type == 1) {
-#pragma unroll 1
-                    for (int r = 0; r < d; r++) { const double gdx = model_G(o + r, k, yk); GDX[o + r] = gdx; Q[o + r] = gdx - RZV[o + r]; }
-                    soc::Mv(WB + o, CE[ci], Q + o, d, DZ + o);
-                    if (mode != 0) {
-#pragma unroll 1
-                        for (int r = 0; r < d; r++) DS[o + r] = rzs * RZ[o + r] - GDX[o + r];
-                        soc::Wv(WB + o, CE[ci], DZ + o, d, Q + o, false);
-                        soc::Wv(WB + o, CE[ci], DS + o, d, GDX + o, true);
-                        tmax = fmax(tmax, fmax(soc::step(LM + o, GDX + o, d), soc::step(LM + o, Q + o, d)));
-                        if (mode == 1) soc::jprod(GDX + o, Q + o, d, CR + o);
-                    }
-                } else if (type == 0) {
-                    const double gdx = model_G(o, k, yk);
-                    DZ[o] = WB[o] * (gdx - RZV[o]);
-                    if (mode != 0) {
-                        DS[o] = rzs * RZ[o] - gdx;
-                        const double iw = sqrt(WB[o]), il = 1. / LM[o];      // W = 1/sqrt(wb)
-                        const double dzt = DZ[o] / iw, dst = DS[o] * iw;
-                        tmax = fmax(tmax, fmax(-dst, -dzt) * il);
-                        if (mode == 1) CR[o] = dst * dzt;
-                    }
-                } else if (hasint) {
-                    const int i = o - MN;
-                    const double ady = dyn_row(i, yk, XN, ysig, false);
-                    const double dm = WB[o], dp = WB[o + NX];
-                    const double qm = ady - RZV[o], qp = -ady - RZV[o + NX];
-                    const double dt = (RXV[PN + i] + dm * qm + dp * qp) / (dm + dp);
-                    DZ[o] = dm * (qm - dt); DZ[o + NX] = dp * (qp - dt);
-                    DP[PN + i] = dt;
-                    if (mode != 0) {
-                        DS[o] = rzs * RZ[o] - (ady - dt); DS[o + NX] = rzs * RZ[o + NX] - (-ady - dt);
-                        for (int q = 0; q < 2; q++) {
-                            const int oo = o + q * NX;
-                            const double iw = sqrt(WB[oo]), il = 1. / LM[oo];
-                            const double dzt = DZ[oo] / iw, dst = DS[oo] * iw;
-                            tmax = fmax(tmax, fmax(-dst, -dzt) * il);
-                            if (mode == 1) CR[oo] = dst * dzt;
-                        }
-                    }
-                } else {
-                    const int i = o - MN;
-                    DP[PN + i] = 0.; DZ[o] = 0.; DZ[o + NX] = 0.;
-                    if (mode != 0) { DS[o] = 0.; DS[o + NX] = 0.; if (mode == 1) { CR[o] = 0.; CR[o + NX] = 0.; } }
-                }
-            }
-            FOR_LANE(j, NB) DP[j] = yk[j];
-            warp_sync();
-            st(dz + k * RS, DZ, RS); st(dprim + k * PS, DP, PN + NX);
-            if (mode != 0) { st(ds + k * RS, DS, RS); if (mode == 1) st(cr + k * RS, CR, RS); }
-            FOR_LANE(j, NB) ynext[j] = yk[j];
-            warp_sync();
-        }
+        chain_backward(ysig);
+        double tmax = pass_recover(mode, csig, rzs, ysig);
         // ---- globals recovery (lane 0)
         if (lane_id() == 0) {
             double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
-            const double e2i = ce[K * CS], d0 = wb[r0g];
+            const double e2i = ce[NCN * KS], d0 = wb[r0g];
             const double dz0 = d0 * (-ysig - rzg[0]);
             double q[3] = {-rzg[1], -rzg[2], -ysig - rzg[3]}, mq[3], dzq[3];
             const double pq = p_s[0] * q[0] + p_s[1] * q[1] + p_s[2] * q[2];
@@ -1119,8 +1248,8 @@ struct Ipm {
             if (mode != 0) {
                 double dsg[4] = {rzs * rz[r0g] + ysig, rzs * rz[r0g + 1] + 0.5 * dds, rzs * rz[r0g + 2] - 0.5 * dds, rzs * rz[r0g + 3] + ysig};
                 for (int i = 0; i < 4; i++) ds[r0g + i] = dsg[i];
-                const double wv = sqrt(1. / d0), l0 = lam[r0g];
-                const double dzt0 = wv * dz0, dst0 = dsg[0] / wv;
+                const double wv_ = sqrt(1. / d0), l0 = lam[r0g];
+                const double dzt0 = wv_ * dz0, dst0 = dsg[0] / wv_;
                 tmax = fmax(tmax, fmax(-dst0 / l0, -dzt0 / l0));
                 double lm3[3] = {lam[r0g + 1], lam[r0g + 2], lam[r0g + 3]}, dzt[3], dst[3], pr[3];
                 soc::Wv(w3, e2i, dzq, 3, dzt, false);
@@ -1134,120 +1263,62 @@ struct Ipm {
     }
 
     // =============================================================================================================
-    //  light sweeps: slack evaluation, cone margins / shifts, the update
+    //  light stage-parallel passes used by the cold start: slack evaluation, cone margins / shifts
     // =============================================================================================================
-    // out = h - G x  (stage sweep)
-    SCPP_HD void eval_slack(double *out)
+    SCPP_HD void eval_slack(double *out)   // out = h - G x
     {
-        double *P = pw(0), *PNX = pw(1), *XB = pw(3), *O_ = row(0);
-        const double sg = prim[K * PS], dsg = prim[K * PS + 1];
-#pragma unroll 1
-        for (int k = 0; k < K; k++) {
+        const double sg = prim[PSN * KS], dsg = prim[PSN * KS + 1];
+        FOR_LANE(k, K) {
             const bool hasint = k < K - 1;
-            if (hasint) { ld_dd(k); ld(PNX, prim + (k + 1) * PS, PS); }
-            ld(P, prim + k * PS, PS);
-            load_xibar(k, XB);
-            tables_stage(k);
-            ld_wait();
-            FOR_LANE(r, RS) {
-                double v = 0.;
-                if (r < NLP + NCR) v = row_h(r) - model_G(r, k, P);
-                else if (r == TRO) v = P[NB];
-                else if (r < MN) v = XB[r - TRO - 1] - P[r - TRO - 1];
-                else if (r < MN + 2 * NX && hasint) {
-                    const int i = (r - MN) % NX;
-                    const double rr = dyn_row(i, P, PNX, sg, true), t = P[PN + i];
-                    v = (r - MN < NX) ? t - rr : t + rr;
+#pragma unroll
+            for (int r = 0; r < NROW; r++) { const RowDesc rd = M::crow(r); out[r * KS + k] = row_h(rd) - row_dot(r, k, prim); }
+            out[TRO * KS + k] = prim[NB * KS + k];
+#pragma unroll
+            for (int j = 0; j < NB; j++) out[(TRO + 1 + j) * KS + k] = xibar(k, j) - prim[j * KS + k];
+#pragma unroll 2
+            for (int i = 0; i < NX; i++) {
+                double tm = 0., tp = 0.;
+                if (hasint) {
+                    double acc = prim[i * KS + k + 1];
+#pragma unroll
+                    for (int j = 0; j < NB; j++) acc -= T(i, j, k) * prim[j * KS + k];
+#pragma unroll
+                    for (int a = 0; a < NU; a++) acc -= T(i, NB + a, k) * prim[(NX + a) * KS + k + 1];
+                    acc -= T(i, NB + NU, k) * sg + T(i, NB + NU + 1, k);
+                    const double t = prim[(PN + i) * KS + k];
+                    tm = t - acc; tp = t + acc;
                 }
-                O_[r] = v;
+                out[(MN + i) * KS + k] = tm; out[(MN + NX + i) * KS + k] = tp;
             }
-            warp_sync();
-            st(out + k * RS, O_, RS);
-            warp_sync();
         }
-        if (lane_id() == 0) { const int r0 = K * RS; out[r0] = sg - 0.001; out[r0 + 1] = 0.5 + 0.5 * dsg; out[r0 + 2] = 0.5 - 0.5 * dsg; out[r0 + 3] = sg - sigbar; }
+        if (lane_id() == 0) { const int r0 = RS * KS; out[r0] = sg - 0.001; out[r0 + 1] = 0.5 + 0.5 * dsg; out[r0 + 2] = 0.5 - 0.5 * dsg; out[r0 + 3] = sg - sigbar; }
         warp_sync();
     }
-    // visit every cone of the flat row array (used only by the two start-up shifts)
+    // visit every cone of a row array: f(first index, stride, dimension)
     template <class F>
     SCPP_HD void for_cones(F &&f) const
     {
-        FOR_LANE(e, K * NTASK) {
-            const int k = e / NTASK, tk = e - k * NTASK;
-            int type, o, d, ci;
-            task(tk, type, o, d, ci);
-            if (type == 2) { if (k < K - 1) { f(k * RS + o, 1); f(k * RS + o + NX, 1); } }
-            else f(k * RS + o, d);
+        FOR_LANE(k, K) {
+            for (int r = 0; r < NLP; r++) f(r * KS + k, KS, 1);
+            for (int c = 0; c < NCONE; c++) f((NLP + M::cone_off(c)) * KS + k, KS, M::cone_dim(c));
+            f(TRO * KS + k, KS, D);
+            if (k < K - 1) for (int r = MN; r < RS; r++) f(r * KS + k, KS, 1);
         }
-        if (lane_id() == 0) { f(K * RS, 1); f(K * RS + 1, 3); }
+        if (lane_id() == 0) { f(RS * KS, 1, 1); f(RS * KS + 1, 1, 3); }
     }
     SCPP_HD void cone_margin(const double *u, double &mn, double &nrm2) const
     {
         double lmn = 1e300, n2 = 0;
-        for_cones([&](int o, int d) {
+        for_cones([&](int o, int st_, int d) {
             double t = 0;
-            for (int i = 1; i < d; i++) t += u[o + i] * u[o + i];
+            for (int i = 1; i < d; i++) t += u[o + i * st_] * u[o + i * st_];
             const double mg = u[o] - sqrt(t);
             if (mg < lmn) lmn = mg;
             n2 += t + u[o] * u[o];
         });
         mn = -warp_max(-lmn); nrm2 = warp_sum(n2);
     }
-    SCPP_HD void cone_shift(double *u, double a) const { for_cones([&](int o, int) { u[o] += a; }); }
-
-    // prim += a dprim ; s += a ds ; z += a dz.  The step length keeps every cone 1 % inside in exact arithmetic; a cone whose
-    // margin u0 - |u1| is lost to rounding (active to ~1e-16 relative) is nudged back inside by a few ulps of u0 so the next
-    // Nesterov-Todd scaling stays defined (perturbation << the 1e-8 tolerances).
-    // window update shared by apply_step (stand-alone) and phase_residuals (fused): S += a DS, Z += a DZ, P += a DP, then nudge
-    SCPP_HD void update_window(double a, double *S_, double *Z, const double *DS, const double *DZ, double *P, const double *DP, bool hasint)
-    {
-        FOR_LANE(e, RS) { S_[e] += a * DS[e]; Z[e] += a * DZ[e]; }
-        FOR_LANE(e, PN + NX) P[e] += a * DP[e];
-        warp_sync();
-        {   // trust region (warp-cooperative)
-            double ts = 0, tz = 0, dummy = 0;
-            FOR_LANE(i, D) if (i > 0) { ts += S_[TRO + i] * S_[TRO + i]; tz += Z[TRO + i] * Z[TRO + i]; }
-            warp_sum3(ts, tz, dummy);
-            if (lane_id() == 0) { S_[TRO] = nudge(S_[TRO], sqrt(ts)); Z[TRO] = nudge(Z[TRO], sqrt(tz)); }
-        }
-        FOR_LANE(tk, NTASK) {
-            if (tk == NCONE) continue;
-            int type, o, d, ci;
-            task(tk, type, o, d, ci);
-            if (type == 2) {
-                if (hasint) { S_[o] = nudge(S_[o], 0.); S_[o + NX] = nudge(S_[o + NX], 0.); Z[o] = nudge(Z[o], 0.); Z[o + NX] = nudge(Z[o + NX], 0.); }
-            } else {
-                double ts = 0, tz = 0;
-#pragma unroll
-                for (int i = 1; i < soc::SOC_MAXD; i++) if (i < d) { ts += S_[o + i] * S_[o + i]; tz += Z[o + i] * Z[o + i]; }
-                S_[o] = nudge(S_[o], sqrt(ts)); Z[o] = nudge(Z[o], sqrt(tz));
-            }
-        }
-        warp_sync();
-    }
-    SCPP_HD void apply_step(double a)
-    {
-        double *S_ = row(0), *Z = row(1), *DS = row(2), *DZ = row(3), *P = pw(0), *DP = pw(1);
-#pragma unroll 1
-        for (int k = 0; k < K; k++) {
-            const bool hasint = k < K - 1;
-            ld(S_, s + k * RS, RS); ld(Z, z + k * RS, RS); ld(DS, ds + k * RS, RS); ld(DZ, dz + k * RS, RS);
-            ld(P, prim + k * PS, PS); ld(DP, dprim + k * PS, PS);
-            ld_wait();
-            update_window(a, S_, Z, DS, DZ, P, DP, hasint);
-            st(s + k * RS, S_, RS); st(z + k * RS, Z, RS); st(prim + k * PS, P, PN + NX);
-            warp_sync();
-        }
-        if (lane_id() == 0) {
-            const int r0 = K * RS, p0 = K * PS;
-            for (int i = 0; i < 4; i++) { s[r0 + i] += a * ds[r0 + i]; z[r0 + i] += a * dz[r0 + i]; }
-            prim[p0] += a * dprim[p0]; prim[p0 + 1] += a * dprim[p0 + 1];
-            s[r0] = nudge(s[r0], 0.); z[r0] = nudge(z[r0], 0.);
-            s[r0 + 1] = nudge(s[r0 + 1], sqrt(s[r0 + 2] * s[r0 + 2] + s[r0 + 3] * s[r0 + 3]));
-            z[r0 + 1] = nudge(z[r0 + 1], sqrt(z[r0 + 2] * z[r0 + 2] + z[r0 + 3] * z[r0 + 3]));
-        }
-        warp_sync();
-    }
+    SCPP_HD void cone_shift(double *u, double a) const { for_cones([&](int o, int, int) { u[o] += a; }); }
 
     // =============================================================================================================
     //  driver
@@ -1264,62 +1335,62 @@ struct Ipm {
         if (warm) {
             // previous interior point of this instance, pulled back from the boundary; pinned variables keep their values
             const double lw = st_.warm, lc = 1. - st_.warm;
-            FOR_LANE(e, K * PS) { const int k = e / PS, i = e - k * PS; if (i < NB && fixed(k, i)) prim[e] = fixv[k * NB + i]; }
+            FOR_LANE(k, K) { for (int i = 0; i < NB; i++) if (fixed(k, i)) prim[i * KS + k] = fixv[k * NB + i]; }
             FOR_LANE(e, m) { s[e] *= lw; z[e] *= lw; }
             warp_sync();
             cone_shift(s, lc); cone_shift(z, lc);
             warp_sync();
         } else {
-        // ---- starting point (CVXOPT conelp / ECOS style): least-squares primal and dual points, W = I
-        FOR_LANE(e, K * PS) {
-            const int k = e / PS, i = e - k * PS;
-            double v = 0.;
-            if (i < NB) v = fixed(k, i) ? fixv[k * NB + i] : (i < NX ? Xbar[k * NX + i] : Ubar[k * NU + (i - NX)]);
-            prim[e] = v;
-        }
-        if (lane_id() == 0) { prim[K * PS] = sigbar; prim[K * PS + 1] = 0.; }
-        FOR_LANE(e, m) { s[e] = 0.; z[e] = 0.; }
-        warp_sync();
-        cone_shift(s, 1.); cone_shift(z, 1.);
-        warp_sync();
-        phase_residuals(nm, true);
-        if (!phase_factor()) { res.status = 2; return res; }
-        // primal: min |G x - h|  ->  G dx - dz = slack(x0)
-        eval_slack(ds);
-        FOR_LANE(e, np) dprim[e] = 0.;
-        warp_sync();
-        phase_solve(0, 0., 0., 0., tm);
-        FOR_LANE(e, np) prim[e] += dprim[e];
-        warp_sync();
-        eval_slack(s);
-        {
-            double mg, n2; cone_margin(s, mg, n2);
-            if (mg <= 1e-8 * fmax(1., sqrt(n2))) { cone_shift(s, 1. - mg); }
+            // ---- starting point (CVXOPT conelp / ECOS style): least-squares primal and dual points, W = I
+            FOR_LANE(e, np) prim[e] = 0.;
+            FOR_LANE(e, m) { s[e] = 0.; z[e] = 0.; }
             warp_sync();
-        }
-        // dual: min |z| s.t. G'z + c = 0  ->  rx = -c, rz = 0
-        FOR_LANE(e, m) ds[e] = 0.;
-        FOR_LANE(e, K * PS) { const int i = e % PS; dprim[e] = (i == NB) ? -w_tr : ((i >= PN && i < PN + NX && e / PS < K - 1) ? -w_vc : 0.); }
-        if (lane_id() == 0) { dprim[K * PS] = -w_time; dprim[K * PS + 1] = -w_trs; }
-        warp_sync();
-        phase_solve(0, 0., 0., 0., tm);
-        FOR_LANE(e, m) z[e] = dz[e];
-        warp_sync();
-        {
-            double mg, n2; cone_margin(z, mg, n2);
-            if (mg <= 1e-8 * fmax(1., sqrt(n2))) { cone_shift(z, 1. - mg); }
+            FOR_LANE(k, K) { for (int i = 0; i < NB; i++) prim[i * KS + k] = fixed(k, i) ? fixv[k * NB + i] : xibar(k, i); }
+            if (lane_id() == 0) { prim[PSN * KS] = sigbar; prim[PSN * KS + 1] = 0.; }
             warp_sync();
-        }
+            cone_shift(s, 1.); cone_shift(z, 1.);
+            warp_sync();
+            pass_residuals(nm, true);
+            if (!phase_factor()) { res.status = 2; return res; }
+            // primal: min |G x - h|  ->  G dx - dz = slack(x0)
+            eval_slack(ds);
+            FOR_LANE(e, np) dprim[e] = 0.;
+            warp_sync();
+            phase_solve(0, 0., 0., 0., tm);
+            FOR_LANE(e, np) prim[e] += dprim[e];
+            warp_sync();
+            eval_slack(s);
+            {
+                double mg, n2; cone_margin(s, mg, n2);
+                if (mg <= 1e-8 * fmax(1., sqrt(n2))) { cone_shift(s, 1. - mg); }
+                warp_sync();
+            }
+            // dual: min |z| s.t. G'z + c = 0  ->  rx = -c, rz = 0
+            FOR_LANE(e, m) ds[e] = 0.;
+            FOR_LANE(e, np) dprim[e] = 0.;
+            warp_sync();
+            FOR_LANE(k, K) { dprim[NB * KS + k] = -w_tr; if (k < K - 1) for (int i = 0; i < NX; i++) dprim[(PN + i) * KS + k] = -w_vc; }
+            if (lane_id() == 0) { dprim[PSN * KS] = -w_time; dprim[PSN * KS + 1] = -w_trs; }
+            warp_sync();
+            phase_solve(0, 0., 0., 0., tm);
+            FOR_LANE(e, m) z[e] = dz[e];
+            warp_sync();
+            {
+                double mg, n2; cone_margin(z, mg, n2);
+                if (mg <= 1e-8 * fmax(1., sqrt(n2))) { cone_shift(z, 1. - mg); }
+                warp_sync();
+            }
         }
         const double cnorm = sqrt(w_time * w_time + w_trs * w_trs + K * w_tr * w_tr + (K - 1) * NX * w_vc * w_vc);
         const double resx0 = fmax(1., cnorm);
         const int degree = K * (NLP + NCN) + (K - 1) * 2 * NX + 2;
         double best = 1e300;
         int it;
+        double pending = 0.;       // step of the previous iteration, applied before the next residual pass
 #pragma unroll 1
-        double pending = 0.;       // step of the previous iteration, applied inside the next residual sweep
         for (it = 0; it <= st_.maxit; it++) {
-            phase_residuals(nm, false, pending);
+            if (pending != 0.) pass_update(pending);
+            pass_residuals(nm, false);
             const double resz0 = fmax(1., sqrt(nm.h2));
             const double pres = sqrt(nm.rz2) / resz0, dres = sqrt(nm.rx2) / resx0, gap = nm.gap, pcost = nm.pcost;
             const double dcost = pcost - gap + nm.zrz - nm.xrx;

@@ -42,6 +42,36 @@ struct RowDesc {
     signed char hs;
 };
 
+// ---- constraint row tables (real constant data: a function-local table would be rebuilt on the stack at every call) ----
+#define SCPP_RQ_ROWS {                                                                                          \
+        {1, {0, 0, 0}, {2, 0, 0}, 3},          /* m_k - m_dry >= 0                          rocketQuat.cpp:93      */ \
+        {3, {14, 15, 16}, {-1, -2, -3}, 4},    /* n_k' T_k - T_min >= 0                     :113-121               */ \
+        {1, {3, 0, 0}, {5, 0, 0}, 0},          /* glide slope: tan(gamma) r_z               :96-97                 */ \
+        {1, {1, 0, 0}, {2, 0, 0}, 0},                                                                             \
+        {1, {2, 0, 0}, {2, 0, 0}, 0},                                                                             \
+        {0, {0, 0, 0}, {0, 0, 0}, 6},          /* tilt: sqrt((1-cos theta_max)/2)           :100-101               */ \
+        {1, {8, 0, 0}, {2, 0, 0}, 0},                                                                             \
+        {1, {9, 0, 0}, {2, 0, 0}, 0},                                                                             \
+        {0, {0, 0, 0}, {0, 0, 0}, 7},          /* |w| <= w_B_max                            :104-105               */ \
+        {1, {11, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {12, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {13, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {0, {0, 0, 0}, {0, 0, 0}, 8},          /* |T| <= T_max                              :129                   */ \
+        {1, {14, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {15, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {16, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {16, 0, 0}, {9, 0, 0}, 0},         /* gimbal: tan(gimbal_max) T_z               :132-133               */ \
+        {1, {14, 0, 0}, {2, 0, 0}, 0},                                                                            \
+        {1, {15, 0, 0}, {2, 0, 0}, 0},                                                                            \
+    }
+#define SCPP_R2D_ROWS {                                                                                         \
+        {1, {4, 0, 0}, {1, 0, 0}, 3}, {1, {4, 0, 0}, {2, 0, 0}, 3},    /* |eta| <= theta_max          rocket2d.cpp:66-68 */ \
+        {1, {5, 0, 0}, {1, 0, 0}, 4}, {1, {5, 0, 0}, {2, 0, 0}, 4},    /* |w| <= w_B_max              :70-72 */ \
+        {1, {6, 0, 0}, {1, 0, 0}, 5}, {1, {6, 0, 0}, {2, 0, 0}, 5},    /* |gimbal| <= gimbal_max      :76-78 */ \
+        {1, {7, 0, 0}, {2, 0, 0}, 6}, {1, {7, 0, 0}, {1, 0, 0}, 7},    /* T_min <= T <= T_max         :80-82 */ \
+        {1, {1, 0, 0}, {8, 0, 0}, 0}, {1, {0, 0, 0}, {2, 0, 0}, 0},    /* |r_x| <= tan(gamma) r_y     :63-64 */ \
+    }
+
 // ================================= RocketQuat =====================================================
 struct RocketQuat {
     static constexpr int NX = 14, NU = 4, NP = 10;
@@ -57,6 +87,8 @@ struct RocketQuat {
     // rocketQuat.cpp:70-144 (exact_minimum_thrust handled through tdir: (0,0,1) reproduces T_z >= T_min, :125;
     // enable_roll_control == false: X.row(13)==0 and U.row(3)==0 become fixed variables, :141-142)
     SCPP_HD static RowDesc row(int r);
+    // the same table as a constant expression: with a compile-time row index (unrolled loops) it folds into immediates
+    SCPP_HD static constexpr RowDesc crow(int r) { constexpr RowDesc t[NLP + NCR] = SCPP_RQ_ROWS; return t[r]; }
 
     // ---- systemFlowMap for a generic scalar (rocketQuat.cpp:7-37); par = [alpha_m, g_I, J_B, r_T_B]
     template <class T>
@@ -254,6 +286,8 @@ struct Rocket2d {
     SCPP_HD static int cone_off(int) { return 0; }
     // rocket2d.cpp:46-84
     SCPP_HD static RowDesc row(int r);
+    // the same table as a constant expression: with a compile-time row index (unrolled loops) it folds into immediates
+    SCPP_HD static constexpr RowDesc crow(int r) { constexpr RowDesc t[NLP + NCR] = SCPP_R2D_ROWS; return t[r]; }
     // rocket2d.cpp:7-40 ; par = [m, J_B, g_I(2), r_T_B(2)]
     template <class T>
     SCPP_HD static void flow_map(const T *x, const T *u, const double *par, T *f)
@@ -342,35 +376,6 @@ struct Rocket2d {
     SCPP_HD static void thrust_dir(const double *, double *d) { d[0] = 0.; d[1] = 0.; d[2] = 1.; }
 };
 
-// ---- constraint row tables (real constant data: a function-local table would be rebuilt on the stack at every call) ----
-#define SCPP_RQ_ROWS {                                                                                          \
-        {1, {0, 0, 0}, {2, 0, 0}, 3},          /* m_k - m_dry >= 0                          rocketQuat.cpp:93      */ \
-        {3, {14, 15, 16}, {-1, -2, -3}, 4},    /* n_k' T_k - T_min >= 0                     :113-121               */ \
-        {1, {3, 0, 0}, {5, 0, 0}, 0},          /* glide slope: tan(gamma) r_z               :96-97                 */ \
-        {1, {1, 0, 0}, {2, 0, 0}, 0},                                                                             \
-        {1, {2, 0, 0}, {2, 0, 0}, 0},                                                                             \
-        {0, {0, 0, 0}, {0, 0, 0}, 6},          /* tilt: sqrt((1-cos theta_max)/2)           :100-101               */ \
-        {1, {8, 0, 0}, {2, 0, 0}, 0},                                                                             \
-        {1, {9, 0, 0}, {2, 0, 0}, 0},                                                                             \
-        {0, {0, 0, 0}, {0, 0, 0}, 7},          /* |w| <= w_B_max                            :104-105               */ \
-        {1, {11, 0, 0}, {2, 0, 0}, 0},                                                                            \
-        {1, {12, 0, 0}, {2, 0, 0}, 0},                                                                            \
-        {1, {13, 0, 0}, {2, 0, 0}, 0},                                                                            \
-        {0, {0, 0, 0}, {0, 0, 0}, 8},          /* |T| <= T_max                              :129                   */ \
-        {1, {14, 0, 0}, {2, 0, 0}, 0},                                                                            \
-        {1, {15, 0, 0}, {2, 0, 0}, 0},                                                                            \
-        {1, {16, 0, 0}, {2, 0, 0}, 0},                                                                            \
-        {1, {16, 0, 0}, {9, 0, 0}, 0},         /* gimbal: tan(gimbal_max) T_z               :132-133               */ \
-        {1, {14, 0, 0}, {2, 0, 0}, 0},                                                                            \
-        {1, {15, 0, 0}, {2, 0, 0}, 0},                                                                            \
-    }
-#define SCPP_R2D_ROWS {                                                                                         \
-        {1, {4, 0, 0}, {1, 0, 0}, 3}, {1, {4, 0, 0}, {2, 0, 0}, 3},    /* |eta| <= theta_max          rocket2d.cpp:66-68 */ \
-        {1, {5, 0, 0}, {1, 0, 0}, 4}, {1, {5, 0, 0}, {2, 0, 0}, 4},    /* |w| <= w_B_max              :70-72 */ \
-        {1, {6, 0, 0}, {1, 0, 0}, 5}, {1, {6, 0, 0}, {2, 0, 0}, 5},    /* |gimbal| <= gimbal_max      :76-78 */ \
-        {1, {7, 0, 0}, {2, 0, 0}, 6}, {1, {7, 0, 0}, {1, 0, 0}, 7},    /* T_min <= T <= T_max         :80-82 */ \
-        {1, {1, 0, 0}, {8, 0, 0}, 0}, {1, {0, 0, 0}, {2, 0, 0}, 0},    /* |r_x| <= tan(gamma) r_y     :63-64 */ \
-    }
 static const RowDesc rq_rows_host[RocketQuat::NLP + RocketQuat::NCR] = SCPP_RQ_ROWS;
 static const RowDesc r2d_rows_host[Rocket2d::NLP + Rocket2d::NCR] = SCPP_R2D_ROWS;
 #if defined(__CUDACC__)

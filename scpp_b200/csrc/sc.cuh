@@ -41,6 +41,7 @@ struct ScArrays {
     double *w_tr;                  // [N] current trust-region weight
     int *iters, *status, *converged;   // [N]
     double *dd;                    // [N][K-1][NX][NC]
+    double *ddT;                   // [N][NX*NC][KS]  the same tiles, stage-minor
     double *ws;                    // [N][ws_doubles]
     double *hist;                  // [N][max_it+1][K*NB+1] or null
     double *info;                  // [N][max_it][INFO_STRIDE]
@@ -88,6 +89,7 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
     Ipm<M> ipm;
     ipm.K = K;
     ipm.dd = a.dd + (size_t)n * (K - 1) * NX * NC;
+    ipm.ddT = a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K);
     double *X = a.X + (size_t)n * K * NX, *U = a.U + (size_t)n * K * NU;
     ipm.Xbar = X; ipm.Ubar = U; ipm.sigbar = a.sigma[n];
     ipm.cst = a.cst + (size_t)n * MAX_CST;
