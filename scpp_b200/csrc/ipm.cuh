@@ -281,6 +281,7 @@ struct Ipm {
     // RCQ[r][3] = h ; RIDX[r][q] = variable index (or -1).  CST = per-instance constants (all phases).
     SCPP_HD double *rcq() const { return sm + W_RCQ; }
     SCPP_HD int *ridx() const { return reinterpret_cast<int *>(sm + W_RIDX); }
+    SCPP_HD int *sup() const { return reinterpret_cast<int *>(sm + W_REV); }
     SCPP_HD double *cstw() const { return sm + W_CST; }
     SCPP_HD void tables_init() const
     {
@@ -291,6 +292,22 @@ struct Ipm {
             for (int q = 0; q < 4; q++) ridx()[r * 4 + q] = (q < rd.n) ? rd.idx[q] : -1;
             for (int q = 0; q < 3; q++) rcq()[r * 4 + q] = (q < rd.n && rd.cs[q] >= 0) ? cstw()[rd.cs[q]] : 0.;
             rcq()[r * 4 + 3] = cstw()[rd.hs];
+        }
+        warp_sync();
+        // support (variable indices, at most 4) of each rank-1 term of the model Hessian: cones, then the multi-entry LP row
+        FOR_LANE(c, NRK) {
+            int n = 0, *sp = sup() + 4 * c;
+            for (int q = 0; q < 4; q++) sp[q] = -1;
+            const int r0 = c < NCONE ? NLP + M::cone_off(c) : 0, r1 = c < NCONE ? r0 + M::cone_dim(c) : NLP;
+            for (int r = r0; r < r1; r++) {
+                if (c == NCONE && ridx()[r * 4 + 1] < 0) continue;      // single-entry LP rows are diagonal terms
+                for (int q = 0; q < 3; q++) {
+                    const int i = ridx()[r * 4 + q];
+                    bool seen = i < 0;
+                    for (int t = 0; t < n; t++) seen = seen || sp[t] == i;
+                    if (!seen && n < 4) sp[n++] = i;
+                }
+            }
         }
         warp_sync();
     }
@@ -603,6 +620,68 @@ struct Ipm {
         warp_sync();
     }
 
+    // Cholesky factor of the NB x NB block H (lower triangle valid, row-major in the shared window) and its inverse Li = L^-1.
+    // Device: lane i keeps row i of H in registers; column j is scaled by rsqrt of the pivot (broadcast by shuffle) and the
+    // trailing update takes L[c][j] from lane c by shuffle, fully unrolled (153 DFMA).  L goes back to the window, then lane c
+    // forward-substitutes column c of the inverse with uniform (broadcast) reads of L.  Host: the same arithmetic as plain loops.
+    SCPP_HD bool chol_inv(double *H, double *Li)
+    {
+#if defined(__CUDA_ARCH__)
+        const int lane = lane_id();
+        const bool own = lane < NB;
+        double h[NB], invd[NB];
+#pragma unroll
+        for (int c = 0; c < NB; c++) h[c] = own ? H[lane * NB + c] : 0.;
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const double d = __shfl_sync(0xffffffffu, h[j], j);
+            ok = ok && (d > 0.);
+            const double inv = rsqrt(d > 0. ? d : 1.);
+            invd[j] = inv;
+            const double l = h[j] * inv;
+            h[j] = l;
+#pragma unroll
+            for (int c = j + 1; c < NB; c++) { const double lc = __shfl_sync(0xffffffffu, l, c); h[c] = fma(-l, lc, h[c]); }
+        }
+        if (own) {
+#pragma unroll
+            for (int c = 0; c < NB; c++) H[lane * NB + c] = h[c];
+        }
+        __syncwarp();
+        double x[NB];
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            double a0 = (i == lane) ? 1. : 0., a1 = 0.;
+#pragma unroll
+            for (int q = 0; q < i; q += 2) { a0 = fma(-H[i * NB + q], x[q], a0); if (q + 1 < i) a1 = fma(-H[i * NB + q + 1], x[q + 1], a1); }
+            x[i] = (a0 + a1) * invd[i];
+        }
+        if (own) {
+#pragma unroll
+            for (int i = 0; i < NB; i++) Li[i * NB + lane] = x[i];
+        }
+        return ok;
+#else
+        bool ok = true;
+        for (int j = 0; j < NB; j++) {
+            for (int i = j; i < NB; i++) { double v = H[i * NB + j]; for (int c = 0; c < j; c++) v -= H[i * NB + c] * H[j * NB + c]; H[i * NB + j] = v; }
+            const double djj = H[j * NB + j];
+            if (!(djj > 0.)) ok = false;
+            const double inv = 1. / sqrt(djj > 0. ? djj : 1.);
+            for (int i = j; i < NB; i++) H[i * NB + j] *= inv;
+        }
+        for (int c = 0; c < NB; c++)
+            for (int i = 0; i < NB; i++) {
+                if (i < c) { Li[i * NB + c] = 0.; continue; }
+                double v = (i == c) ? 1. : 0.;
+                for (int q = c; q < i; q++) v -= H[i * NB + q] * Li[q * NB + c];
+                Li[i * NB + c] = v / H[i * NB + i];
+            }
+        return ok;
+#endif
+    }
+
     SCPP_HD bool phase_factor()
     {
         double *H = sm + W_MAT, *O = H + BLK, *Lp = sm + W_LP;
@@ -628,12 +707,21 @@ struct Ipm {
             tables_stage(k);
             ld_wait();
             build_model_terms(WB, CE, alpha);
-            // ---- node part of H_kk (trust region with delta eliminated) + carry from interval k-1
+            // ---- node part of H_kk (trust region with delta eliminated) + carry from interval k-1: dense part, then the
+            //      model cones / rows, each of which touches at most 4 variables (sparse rank-1 terms, one cone at a time)
             {
                 const double *rk = sm + W_RK, *dg = rk + NRK * NB;
                 const double *wt_ = WB + TRO;
                 const double e2i = CE[NCONE], w0 = wt_[0];
-                const double kap = e2i * (2. * w0 * w0 - 1.), c2 = 4. * e2i * e2i * w0 * w0 / kap;
+                const double kap = e2i * (2. * w0 * w0 - 1.), c2 = 4. * e2i * e2i * w0 * w0 / kap, beta = 2. * e2i - c2;
+                double *dsum = vec(3);
+                FOR_LANE(i, NB) {
+                    double v = e2i;
+#pragma unroll
+                    for (int c = 0; c < NRK; c++) v += dg[c * NB + i];
+                    dsum[i] = v;
+                }
+                warp_sync();
 #pragma unroll 2
                 FOR_LANE(e, BLK) {
                     const int i = e / NB, j = e - i * NB;
@@ -642,17 +730,19 @@ struct Ipm {
                     else if (i < NX) v = -DCp[i * NU + (j - NX)];
                     else if (j < NX) v = -DCp[j * NU + (i - NX)];
                     else v = CDCp[(i - NX) * NU + (j - NX)];
-#pragma unroll
-                    for (int c = 0; c < NRK; c++) v += alpha[c] * rk[c * NB + i] * rk[c * NB + j];
-                    if (i == j) {
-#pragma unroll
-                        for (int c = 0; c < NRK; c++) v += dg[c * NB + i];
-                        v += e2i;
-                    }
-                    v += (2. * e2i - c2) * wt_[1 + i] * wt_[1 + j];
-                    H[e] = v;
+                    if (i == j) v += dsum[i];
+                    H[e] = v + beta * wt_[1 + i] * wt_[1 + j];
                 }
                 FOR_LANE(j, NB) bk[j] = bn[j];
+                warp_sync();
+#pragma unroll 1
+                for (int c = 0; c < NRK; c++) {
+                    FOR_LANE(t, 16) {
+                        const int i = sup()[4 * c + (t >> 2)], j = sup()[4 * c + (t & 3)];
+                        if (i >= 0 && j >= 0) H[i * NB + j] += alpha[c] * rk[c * NB + i] * rk[c * NB + j];
+                    }
+                    warp_sync();
+                }
             }
             warp_sync();
             // ---- interval k: H_kk += A~' D A~ ; O = [-D A~ ; C' D A~] ; carry = (D, D C, C' D C) ; borders
@@ -721,38 +811,8 @@ struct Ipm {
                 }
             }
             warp_sync();
-            // ---- Cholesky of H (lower, in place), left-looking by columns: lane i owns row i
-#pragma unroll 1
-            for (int j = 0; j < NB; j++) {
-                FOR_LANE(i, NB) if (i >= j) {
-                    double v0 = H[i * NB + j], v1 = 0;
-                    int c = 0;
-#pragma unroll 1
-                    for (; c + 1 < j; c += 2) { v0 -= H[i * NB + c] * H[j * NB + c]; v1 -= H[i * NB + c + 1] * H[j * NB + c + 1]; }
-                    if (c < j) v0 -= H[i * NB + c] * H[j * NB + c];
-                    H[i * NB + j] = v0 + v1;         // unscaled column j (row j reads only columns < j of itself)
-                }
-                warp_sync();
-                const double djj = H[j * NB + j];
-                if (!(djj > 0.)) bad = 1;
-                const double inv = 1. / sqrt(djj > 0. ? djj : 1.);
-                warp_sync();
-                FOR_LANE(i, NB) if (i >= j) H[i * NB + j] *= inv;
-                warp_sync();
-            }
-            // ---- Linv = L^-1 (lower): lane per column
-            FOR_LANE(c, NB) {
-#pragma unroll 1
-                for (int i = 0; i < NB; i++) {
-                    if (i < c) { Li[i * NB + c] = 0.; continue; }
-                    double v = (i == c) ? 1. : 0., v2 = 0.;
-                    int q = c;
-#pragma unroll 1
-                    for (; q + 1 < i; q += 2) { v -= H[i * NB + q] * Li[q * NB + c]; v2 -= H[i * NB + q + 1] * Li[(q + 1) * NB + c]; }
-                    if (q < i) v -= H[i * NB + q] * Li[q * NB + c];
-                    Li[i * NB + c] = (v + v2) / H[i * NB + i];
-                }
-            }
+            // ---- Cholesky of H and Linv = L^-1
+            if (!chol_inv(H, Li)) bad = 1;
             warp_sync();
             // ---- L_{k+1,k} = O Linv' ;  l_k = Linv bk ; corner -= l_k' l_k
             blk::mm<NB, NB, NB, false>([&](int m, int k) { return (m < NB && k < NB) ? O[m * NB + k] : 0.; },

@@ -1,0 +1,22 @@
+#!/usr/bin/env python
+"""per-outer-iteration statistics of the interior-point iteration counts over a batch (GPU): mean / max / histogram"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, scpp_b200 as S
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50)
+cfg.ipm.warm = float(os.environ.get("SCPP_WARM", "0.995"))
+rpy = np.deg2rad([-20.0, 20.0, 0.0])
+xi = S.perturbed_initial_states(x_init, rpy, batch)
+eng = S.SCAlgorithm(model, params, cfg, batch)
+eng.set_boundary_states(xi, x_final)
+eng.solve()
+info = eng.get_info()
+it = info[:, :, 5]; st = info[:, :, 6]
+tot_mean = 0; tot_max = 0
+for o in range(info.shape[1]):
+    v = it[:, o]
+    tot_mean += v.mean(); tot_max += v.max()
+    print(f"outer {o:2d}: ipm its mean {v.mean():5.1f} p50 {np.percentile(v,50):4.0f} p90 {np.percentile(v,90):4.0f} p99 {np.percentile(v,99):4.0f} max {v.max():4.0f}  status!=0: {(st[:,o]!=0).sum()}")
+print(f"sum of means {tot_mean:.1f}  sum of maxima {tot_max:.1f}  (kernel time follows the maxima: ratio {tot_max/tot_mean:.2f})")
+print(eng.last_timing())
