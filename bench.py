@@ -173,6 +173,7 @@ def main():
     # interior warm start of the sub-problems (engine knob, same optimum; parity-tested in tests/test_gpu_parity.py);
     # SCPP_WARM=0 gives ECOS-style cold starts
     cfg.ipm.warm = float(os.environ.get("SCPP_WARM", "0.995"))
+    cfg.ipm_slice = int(os.environ.get("SCPP_SLICE", "1"))    # interior-point iterations per K2 launch (0: lock-step outer iterations)
     rpy = np.deg2rad([-20.0, 20.0, 0.0])      # rpy_init of configs/RocketQuat/model.info
     n_local = args.batch
     xi = S.perturbed_initial_states(x_init, rpy, n_local, first=rank * n_local)
@@ -262,7 +263,7 @@ def main():
                 "config": {"workload": workload_name(args.K, n_local),
                            "batch_per_gpu": n_local, "global_batch": n_local * world, "K": args.K, "parallelism": f"instances sharded x{world}",
                            "l2": f"working set {eng.device_bytes() / 1e6:.0f} MB per GPU >> 126 MB L2 (no flush needed)",
-                           "integrator": f"RK4 x {cfg.nsub} (reference RKF78 x 5)", "ipm_tol": cfg.ipm.feastol, "ipm_warm": cfg.ipm.warm},
+                           "integrator": f"RK4 x {cfg.nsub} (reference RKF78 x 5)", "ipm_tol": cfg.ipm.feastol, "ipm_warm": cfg.ipm.warm, "ipm_slice": cfg.ipm_slice},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "ms_per_step": 1e3 * stats[1] / args.steps},
                 "gpu_launches": int(sums[2]),

@@ -66,7 +66,9 @@ typedef struct {
     int max_iterations;
     int nsub;         /* RK4 sub-steps per shooting interval (reference: RKF78 x 5, discretizationImplementation.hpp:154) */
     int keep_history; /* keep every iterate for scpp_b200_get_iterate (SCAlgorithm::getAllSolutions) */
-    int pad_;
+    int ipm_slice;    /* engine knob: interior-point iterations per K2 launch (default 1).  Between launches the engine re-forms
+                         the batch, so an instance that needs 20 iterations does not hold back one that needs 5; 0 = run each
+                         sub-problem to the end in one launch (lock-step outer iterations).  Same arithmetic either way. */
     scpp_b200_ipm_settings ipm;
 } scpp_b200_sc_config;
 

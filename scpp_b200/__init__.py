@@ -38,7 +38,7 @@ class SCConfig(C.Structure):
                 ("weight_time", C.c_double), ("weight_trust_region_time", C.c_double),
                 ("weight_trust_region_trajectory", C.c_double), ("weight_virtual_control", C.c_double),
                 ("nu_tol", C.c_double), ("delta_tol", C.c_double), ("max_iterations", C.c_int), ("nsub", C.c_int),
-                ("keep_history", C.c_int), ("pad_", C.c_int), ("ipm", IpmSettings)]
+                ("keep_history", C.c_int), ("ipm_slice", C.c_int), ("ipm", IpmSettings)]
 
 
 class ScppError(RuntimeError):

@@ -59,6 +59,7 @@ __global__ void k_warm(ScArrays<M> a, ModelParamsHost P, ScConfig cfg)
         if (P.exact_minimum_thrust) M::thrust_dir(U + k * NU, td); else { td[0] = 0.; td[1] = 0.; td[2] = 1.; }
     }
     a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
+    a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.;
     if (a.hist) {
         double *h = a.hist + (size_t)n * (a.max_it + 1) * a.hist_stride();
         for (int k = 0; k < K; k++) { for (int i = 0; i < NX; i++) h[k * NB + i] = X[k * NX + i]; for (int i = 0; i < NU; i++) h[k * NB + NX + i] = U[k * NU + i]; }
@@ -95,16 +96,22 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) k_solve(ScArrays<M> a, ScConf
 
 __global__ void k_iota(int *v, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) v[i] = i; }
 
-// next active list + convergence flag bytes (what the ranks exchange)
-__global__ void k_compact(const int *__restrict__ active, int n_active, const int *__restrict__ converged, int *__restrict__ next,
-                          int *__restrict__ counter, unsigned char *__restrict__ flags)
+// after a round: the next active list, the instances among them that start a new sub-problem (to be discretised) and the
+// per-instance flag bytes the ranks exchange (0 running, 1 converged, 2 failed, 4 iteration limit reached)
+__global__ void k_compact(const int *__restrict__ active, int n_active, const int *__restrict__ converged, const int *__restrict__ iters, int max_it,
+                          const double *__restrict__ ipm_state, int state_stride, int *__restrict__ next, int *__restrict__ disc,
+                          int *__restrict__ counters, unsigned char *__restrict__ flags)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_active) return;
     const int n = active[i];
     const int c = converged[n];
-    flags[n] = (unsigned char)c;
-    if (!c) next[atomicAdd(counter, 1)] = n;
+    const int f = c ? c : (iters[n] >= max_it ? 4 : 0);
+    flags[n] = (unsigned char)f;
+    if (!f) {
+        next[atomicAdd(counters, 1)] = n;
+        if (ipm_state[(size_t)n * state_stride] == 0.) disc[atomicAdd(counters + 1, 1)] = n;
+    }
 }
 __global__ void k_count_zero(const unsigned char *__restrict__ flags, long long n, unsigned long long *__restrict__ out)
 {
@@ -207,7 +214,7 @@ struct scpp_b200_engine {
     ModelParamsHost P;
     ScConfig cfg;
     double ms_disc = 0, ms_socp = 0, ms_total = 0;
-    int launches = 0, outer = 0;
+    int launches = 0, outer = 0, rounds = 0;
     long long inst_iters = 0, global_active = 0;
     size_t bytes = 0;
     void *comm = nullptr;
@@ -220,8 +227,9 @@ struct EngineT : scpp_b200_engine {
     ScArrays<M> a;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    int *active[2] = {nullptr, nullptr};
-    int *counter = nullptr;
+    int *active[2] = {nullptr, nullptr}, *disc = nullptr;
+    int *counter = nullptr;               // [0] next active count, [1] instances starting a new sub-problem
+    std::vector<int> h_iters;
     unsigned long long *gcount = nullptr;
     unsigned char *flags = nullptr, *flags_all = nullptr;
     double *Xo = nullptr, *Uo = nullptr;
@@ -271,10 +279,10 @@ struct EngineT : scpp_b200_engine {
         DA(a.info, (size_t)N * cfg.max_iterations * INFO_STRIDE);
         a.hist = nullptr;
         if (cfg.keep_history) DA(a.hist, (size_t)N * (cfg.max_iterations + 1) * a.hist_stride());
-        DA(active[0], N); DA(active[1], N); DA(counter, 1); DA(gcount, 1); DA(flags, N);
+        DA(active[0], N); DA(active[1], N); DA(disc, N); DA(counter, 2); DA(a.ipm_state, (size_t)N * Ipm<M>::IPM_STATE); DA(gcount, 1); DA(flags, N);
         DA(Xo, (size_t)N * K * NX); DA(Uo, (size_t)N * K * NU);
 #undef DA
-        CU(cudaMallocHost((void **)&h_counter, sizeof(int)));
+        CU(cudaMallocHost((void **)&h_counter, 2 * sizeof(int)));
         CU(cudaMallocHost((void **)&h_gcount, sizeof(unsigned long long)));
         CU(cudaFuncSetAttribute(k_solve<M, WPB_MAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WPB_MAX * Ipm<M>::sm_doubles() * sizeof(double))));
         CU(cudaFuncSetAttribute(k_solve<M, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(4 * Ipm<M>::sm_doubles() * sizeof(double))));
@@ -297,28 +305,32 @@ struct EngineT : scpp_b200_engine {
         if (warm && !solved_once) return fail(SCPP_B200_ERR_ARG, "scpp_b200_solve: warm start requested before any solve");
         CU(cudaSetDevice(device));
         const int K = cfg.K, T = 128;
-        launches = 0; outer = 0; ms_disc = ms_socp = 0; inst_iters = 0;
+        launches = 0; outer = 0; ms_disc = ms_socp = 0; inst_iters = 0; rounds = 0;
         CU(cudaEventRecord(ev[0], stream));
         if (warm) k_warm<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg);
         else k_setup<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg);
         k_iota<<<(N + 255) / 256, 256, 0, stream>>>(active[0], N);
         launches += 2;
         CU(cudaMemsetAsync(flags, 0, N, stream));
-        int n_active = N, cur = 0;
+        int n_active = N, n_disc = N, cur = 0;
+        const int *disc_list = active[0];                         // first round: every instance starts its first sub-problem
         global_active = (long long)N * nranks;
-        for (int it = 0; it < cfg.max_iterations && global_active > 0; it++) {
-            outer++;
-            inst_iters += n_active;
+        // Rounds.  A round (1) discretises the instances that start a new sub-problem (K1), (2) advances EVERY unfinished
+        // instance by one slice of cfg.ipm_slice interior-point iterations (K2; K3 runs in its epilogue when a sub-problem is
+        // solved), (3) re-forms the lists and exchanges the flag bytes.  With ipm_slice == 0 a slice is a whole sub-problem and
+        // the rounds are the reference's outer iterations in lock-step.
+        const long long max_rounds = (long long)cfg.max_iterations * (cfg.ipm_slice > 0 ? (cfg.ipm.maxit + 3) / cfg.ipm_slice + 2 : 1) + 1;
+        for (long long round = 0; round < max_rounds && global_active > 0; round++) {
             CU(cudaEventRecord(ev[1], stream));
-            if (n_active > 0) {
-                const long long thr = (long long)n_active * (K - 1) * NC;
-                k_discretize<M><<<(unsigned)((thr + 127) / 128), 128, 0, stream>>>(a, cfg.nsub, cfg.free_final_time, active[cur], n_active);
+            if (n_disc > 0) {
+                const long long thr = (long long)n_disc * (K - 1) * NC;
+                k_discretize<M><<<(unsigned)((thr + 127) / 128), 128, 0, stream>>>(a, cfg.nsub, cfg.free_final_time, disc_list, n_disc);
                 launches++;
             }
             CU(cudaEventRecord(ev[2], stream));
             if (n_active > 0) {
                 // one warp per instance.  Small batches: spread the warps evenly, one CTA per SM (a batch of 1024 on 148 SMs is
-                // 7 warps per SM); large batches: 4-warp CTAs, two resident per SM (8 warps/SM at 232 registers, no spills).
+                // 7 warps per SM); large batches: 4-warp CTAs, two resident per SM.
                 int wpb = (n_active + n_sm - 1) / n_sm;
                 if (wpb < 1) wpb = 1;
                 if (wpb <= WPB_MAX) {
@@ -331,14 +343,15 @@ struct EngineT : scpp_b200_engine {
                 launches++;
             }
             CU(cudaEventRecord(ev[3], stream));
-            CU(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+            CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), stream));
             if (n_active > 0) {
-                k_compact<<<(n_active + 255) / 256, 256, 0, stream>>>(active[cur], n_active, a.converged, active[cur ^ 1], counter, flags);
+                k_compact<<<(n_active + 255) / 256, 256, 0, stream>>>(active[cur], n_active, a.converged, a.iters, cfg.max_iterations, a.ipm_state,
+                                                                     Ipm<M>::IPM_STATE, active[cur ^ 1], disc, counter, flags);
                 launches++;
             }
-            CU(cudaMemcpyAsync(h_counter, counter, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CU(cudaMemcpyAsync(h_counter, counter, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             if (comm) {
-                // the one data-path collective: every rank learns every instance's convergence flag
+                // the one data-path collective: every rank learns every instance's flag
                 int rc = g_nccl.AllGather(flags, flags_all, (size_t)N, /*ncclUint8*/ 1, comm, stream);
                 if (rc != 0) return fail(SCPP_B200_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
                 CU(cudaMemsetAsync(gcount, 0, sizeof(unsigned long long), stream));
@@ -352,10 +365,17 @@ struct EngineT : scpp_b200_engine {
             CU(cudaEventElapsedTime(&m1, ev[1], ev[2]));
             CU(cudaEventElapsedTime(&m2, ev[2], ev[3]));
             ms_disc += m1; ms_socp += m2;
-            n_active = *h_counter;
+            n_active = h_counter[0]; n_disc = h_counter[1];
+            disc_list = disc;
             cur ^= 1;
+            rounds++;
             global_active = comm ? (long long)*h_gcount : (long long)n_active;
         }
+        // SC iterations done: per instance (reported as instance-iterations) and the largest count (outer iterations)
+        h_iters.resize(N);
+        CU(cudaMemcpyAsync(h_iters.data(), a.iters, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        for (int n = 0; n < N; n++) { inst_iters += h_iters[n]; if (h_iters[n] > outer) outer = h_iters[n]; }
         CU(cudaEventRecord(ev[4], stream));
         CU(cudaStreamSynchronize(stream));
         float mt = 0;
@@ -438,7 +458,7 @@ void scpp_b200_default_config(int model, scpp_b200_sc_config *c)
     c->weight_trust_region_trajectory = model == SCPP_B200_MODEL_ROCKETQUAT ? 50. : 1.;
     c->weight_virtual_control = 1000.;
     c->nu_tol = 1e-5; c->delta_tol = 1e-3; c->max_iterations = 15;
-    c->nsub = 20; c->keep_history = 0;
+    c->nsub = 20; c->keep_history = 0; c->ipm_slice = 1;
     c->ipm.feastol = 1e-8; c->ipm.abstol = 1e-8; c->ipm.reltol = 1e-8; c->ipm.maxit = 100;
 }
 

@@ -36,23 +36,29 @@ static int run_sc(const ModelParamsHost *P, const ScConfig *cfg, int N, const do
     std::vector<uint32_t> fixm((size_t)N * K);
     std::vector<double> dd((size_t)N * (K - 1) * NX * NC), ddT((size_t)N * Ipm<M>::ddt_doubles(K));
     a.ws_stride = Ipm<M>::ws_doubles(K);
-    std::vector<double> ws((size_t)N * a.ws_stride), smem(Ipm<M>::sm_doubles());
+    std::vector<double> ws((size_t)N * a.ws_stride), smem(Ipm<M>::sm_doubles()), ist((size_t)N * Ipm<M>::IPM_STATE);
+    a.ipm_state = ist.data();
     a.x_init = const_cast<double *>(x_init); a.x_final = const_cast<double *>(x_final);
     a.xi = xi.data(); a.xf = xf.data(); a.par = par.data(); a.cst = cst.data(); a.scale = scale.data();
     a.X = X; a.U = U; a.sigma = sigma; a.tdir = tdir.data(); a.fixm = fixm.data(); a.fixv = fixv.data(); a.w_tr = wtr.data();
     a.iters = iters; a.status = status; a.converged = converged; a.dd = dd.data(); a.ddT = ddT.data(); a.ws = ws.data(); a.hist = hist; a.info = info;
     for (int n = 0; n < N; n++) sc_setup_instance<M>(a, *P, *cfg, n);
-    for (int it = 0; it < cfg->max_iterations; it++) {
-        int active = 0;
+    // the engine's round structure: every round discretises the instances that start a new sub-problem and advances every
+    // unfinished instance by one slice of interior-point iterations
+    long rounds = 0;
+    for (;;) {
+        int active = 0; rounds++;
         for (int n = 0; n < N; n++) {
-            if (converged[n]) continue;
+            if (converged[n] || iters[n] >= cfg->max_iterations) continue;
             active++;
-            run_discretize<M>(K, X + (size_t)n * K * NX, U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg->nsub,
-                              a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K));
+            if (a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] == 0.)
+                run_discretize<M>(K, X + (size_t)n * K * NX, U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg->nsub,
+                                  a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K));
             sc_solve_instance<M>(a, *cfg, n, smem.data());
         }
         if (!active) break;
     }
+    if (getenv("SCPP_DEBUG_ROUNDS")) fprintf(stderr, "rounds %ld\n", rounds);
     // redimensionalise the final trajectories (SCAlgorithm.cpp:182-187)
     for (int n = 0; n < N; n++)
         for (int k = 0; k < K; k++) M::redim(a.scale + 2 * n, X + ((size_t)n * K + k) * NX, U + ((size_t)n * K + k) * NU);

@@ -1383,16 +1383,27 @@ struct Ipm {
     // =============================================================================================================
     //  driver
     // =============================================================================================================
-    SCPP_HD IpmResult solve(const IpmSettings &st_, bool have_prev = false)
+    // Sliced driver.  `state` (IPM_STATE doubles, per instance, global memory) carries the solver across kernel launches:
+    // the engine runs at most `budget` interior-point iterations per launch and re-balances the batch between launches
+    // (instances need very different iteration counts).  state[0] == 0: begin a new sub-problem.
+    // Returns with finished == false when the budget ran out; everything else lives in the workspace already.
+    static constexpr int IPM_STATE = 12;
+    SCPP_HD IpmResult solve(const IpmSettings &st_, bool have_prev, int budget, double *state, bool &finished)
     {
         IpmResult res;
         res.status = 1; res.iterations = 0; res.pres = res.dres = res.gap = res.relgap = res.pcost = 0.;
         const int np = n_prim(K), m = m_rows(K);
+        finished = true;
         tables_init();
-        const bool warm = have_prev && st_.warm > 0. && st_.warm < 1.;
+        const bool resume = state[0] != 0.;
         Norms nm;
         double tm;
-        if (warm) {
+        double best = 1e300, pending = 0.;
+        int it = 0;
+        if (resume) {
+            it = (int)state[1]; pending = state[2]; best = state[3];
+            res.pres = state[4]; res.dres = state[5]; res.gap = state[6]; res.relgap = state[7]; res.pcost = state[8]; res.iterations = (int)state[9];
+        } else if (have_prev && st_.warm > 0. && st_.warm < 1.) {
             // previous interior point of this instance, pulled back from the boundary; pinned variables keep their values
             const double lw = st_.warm, lc = 1. - st_.warm;
             FOR_LANE(k, K) { for (int i = 0; i < NB; i++) if (fixed(k, i)) prim[i * KS + k] = fixv[k * NB + i]; }
@@ -1411,7 +1422,7 @@ struct Ipm {
             cone_shift(s, 1.); cone_shift(z, 1.);
             warp_sync();
             pass_residuals(nm, true);
-            if (!phase_factor()) { res.status = 2; return res; }
+            if (!phase_factor()) { res.status = 2; if (lane_id() == 0) state[0] = 0.; warp_sync(); return res; }
             // primal: min |G x - h|  ->  G dx - dz = slack(x0)
             eval_slack(ds);
             FOR_LANE(e, np) dprim[e] = 0.;
@@ -1440,39 +1451,59 @@ struct Ipm {
                 if (mg <= 1e-8 * fmax(1., sqrt(n2))) { cone_shift(z, 1. - mg); }
                 warp_sync();
             }
+            budget -= 1;                     // the least-squares start costs about one iteration
         }
         const double cnorm = sqrt(w_time * w_time + w_trs * w_trs + K * w_tr * w_tr + (K - 1) * NX * w_vc * w_vc);
         const double resx0 = fmax(1., cnorm);
         const int degree = K * (NLP + NCN) + (K - 1) * 2 * NX + 2;
-        double best = 1e300;
-        int it;
-        double pending = 0.;       // step of the previous iteration, applied before the next residual pass
+        // One slice = factorisation + the two solves of iteration `it`, then update + residuals + termination test of `it+1`,
+        // so that the cheap final test never occupies a launch of its own.  A resumed solver re-enters after the test.
+        bool past_test = resume;
+        double gap_cur = resume ? state[10] : 0.;
 #pragma unroll 1
-        for (it = 0; it <= st_.maxit; it++) {
-            if (pending != 0.) pass_update(pending);
-            pass_residuals(nm, false);
-            const double resz0 = fmax(1., sqrt(nm.h2));
-            const double pres = sqrt(nm.rz2) / resz0, dres = sqrt(nm.rx2) / resx0, gap = nm.gap, pcost = nm.pcost;
-            const double dcost = pcost - gap + nm.zrz - nm.xrx;
-            double relgap = 1e300;
-            if (pcost < 0.) relgap = gap / -pcost; else if (dcost > 0.) relgap = gap / dcost;
-            const double score = fmax(fmax(pres, dres) / st_.feastol, fmin(gap / st_.abstol, relgap / st_.reltol));
+        for (; it <= st_.maxit; it++) {
+            if (!past_test) {
+                if (pending != 0.) pass_update(pending);
+                pass_residuals(nm, false);
+                const double resz0 = fmax(1., sqrt(nm.h2));
+                const double pres = sqrt(nm.rz2) / resz0, dres = sqrt(nm.rx2) / resx0, gap = nm.gap, pcost = nm.pcost;
+                const double dcost = pcost - gap + nm.zrz - nm.xrx;
+                double relgap = 1e300;
+                if (pcost < 0.) relgap = gap / -pcost; else if (dcost > 0.) relgap = gap / dcost;
+                const double score = fmax(fmax(pres, dres) / st_.feastol, fmin(gap / st_.abstol, relgap / st_.reltol));
 #if !defined(__CUDACC__)
-            if (getenv("SCPP_DEBUG")) fprintf(stderr, "it %2d pres %.2e dres %.2e gap %.2e relgap %.2e pcost %.6e bad %d\n", it, pres, dres, gap, relgap, pcost, nm.bad);
+                if (getenv("SCPP_DEBUG")) fprintf(stderr, "it %2d pres %.2e dres %.2e gap %.2e relgap %.2e pcost %.6e bad %d\n", it, pres, dres, gap, relgap, pcost, nm.bad);
 #endif
-            if (!nm.bad && score < best) {
-                best = score;
-                res.pres = pres; res.dres = dres; res.gap = gap; res.relgap = relgap; res.pcost = pcost; res.iterations = it;
-                if (score <= 1e4) { FOR_LANE(e, np) best_[e] = prim[e]; }      // a fallback iterate only matters inside the accuracy band
-                warp_sync();
+                if (!nm.bad && score < best) {
+                    best = score;
+                    res.pres = pres; res.dres = dres; res.gap = gap; res.relgap = relgap; res.pcost = pcost; res.iterations = it;
+                    if (score <= 1e4) { FOR_LANE(e, np) best_[e] = prim[e]; }      // a fallback iterate only matters inside the accuracy band
+                    warp_sync();
+                }
+                if (!nm.bad && pres <= st_.feastol && dres <= st_.feastol && (gap <= st_.abstol || relgap <= st_.reltol)) { res.status = 0; break; }
+                // stop on failure, on the iteration limit, on divergence, or at the accuracy floor of the condensed system: once an
+                // iterate within 10x of the tolerances exists and the next one is worse (the dual residual grows with the
+                // conditioning as the gap closes), later iterates only get worse; the best iterate is returned below
+                if (nm.bad || it == st_.maxit || (score > 1e3 * best && best < 1e4) || (best <= 10. && score > best)) { res.status = nm.bad ? 2 : (it == st_.maxit ? 1 : 2); break; }
+                gap_cur = gap;
+                if (budget <= 0) {                       // out of budget: park the solver state, continue in the next launch
+                    if (lane_id() == 0) {
+                        state[0] = 1.; state[1] = it; state[2] = pending; state[3] = best;
+                        state[4] = res.pres; state[5] = res.dres; state[6] = res.gap; state[7] = res.relgap; state[8] = res.pcost; state[9] = res.iterations;
+                        state[10] = gap_cur;
+                    }
+                    warp_sync();
+                    finished = false;
+                    return res;
+                }
             }
-            if (!nm.bad && pres <= st_.feastol && dres <= st_.feastol && (gap <= st_.abstol || relgap <= st_.reltol)) { res.status = 0; break; }
-            if (nm.bad || it == st_.maxit || (score > 1e3 * best && best < 1e4)) { res.status = nm.bad ? 2 : (it == st_.maxit ? 1 : 2); break; }
+            past_test = false;
+            budget--;
             if (!phase_factor()) { res.status = 2; break; }
             double tmax;
             phase_solve(1, 1., 0., -1., tmax);                               // affine direction
             const double a_aff = tmax <= 1. ? 1. : 1. / tmax;
-            const double sig = (1. - a_aff) * (1. - a_aff) * (1. - a_aff), mu = gap / degree;
+            const double sig = (1. - a_aff) * (1. - a_aff) * (1. - a_aff), mu = gap_cur / degree;
             phase_solve(2, 1. - sig, sig * mu, -(1. - sig), tmax);           // combined direction
             pending = tmax <= 0.99 ? 1. : 0.99 / tmax;
         }
@@ -1481,6 +1512,8 @@ struct Ipm {
             warp_sync();
             if (best <= 10.) res.status = 0; else if (best <= 1e4) res.status = 3;
         } else res.iterations = it;
+        if (lane_id() == 0) state[0] = 0.;
+        warp_sync();
         return res;
     }
 };

@@ -17,7 +17,7 @@ struct ScConfig {
     int max_iterations;
     int nsub;                 // RK4 sub-steps per shooting interval (K1)
     int keep_history;         // store every iterate (getAllSolutions)
-    int pad_;
+    int ipm_slice;            // interior-point iterations per K2 launch (0: run every sub-problem to the end in one launch)
     IpmSettings ipm;
 };
 
@@ -43,6 +43,7 @@ struct ScArrays {
     double *dd;                    // [N][K-1][NX][NC]
     double *ddT;                   // [N][NX*NC][KS]  the same tiles, stage-minor
     double *ws;                    // [N][ws_doubles]
+    double *ipm_state;             // [N][Ipm::IPM_STATE]  solver state parked between K2 launches ([0] != 0: mid-solve)
     double *hist;                  // [N][max_it+1][K*NB+1] or null
     double *info;                  // [N][max_it][INFO_STRIDE]
     size_t ws_stride;
@@ -72,6 +73,7 @@ SCPP_HD void sc_setup_instance(const ScArrays<M> &a, const ModelParamsHost &P, c
     a.sigma[n] = P.final_time;
     a.w_tr[n] = cfg.weight_trust_region_trajectory;                            // loadParameters(), SCAlgorithm.cpp:148
     a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
+    a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.;
     if (a.hist) {
         double *h = a.hist + (size_t)n * (a.max_it + 1) * a.hist_stride();
         for (int k = 0; k < K; k++) { for (int i = 0; i < NX; i++) h[k * NB + i] = X[k * NX + i]; for (int i = 0; i < NU; i++) h[k * NB + NX + i] = U[k * NU + i]; }
@@ -79,7 +81,7 @@ SCPP_HD void sc_setup_instance(const ScArrays<M> &a, const ModelParamsHost &P, c
     }
 }
 
-// ---- K2 + K3: solve the sub-problem of instance n, then readSolution and the convergence logic ------------------
+// ---- K2 + K3: advance the sub-problem of instance n by one slice; when it is solved: readSolution and the convergence logic ----
 // SCAlgorithm::iterate, SCAlgorithm.cpp:78-131 (the defect print :85-92 is diagnostic only and not computed)
 template <class M>
 SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n, double *smem)
@@ -101,7 +103,10 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
     ipm.w_tr = w_tr;
     ipm.bind(a.ws + (size_t)n * a.ws_stride, smem);
     const int it = a.iters[n];
-    const IpmResult r = ipm.solve(cfg.ipm, it > 0 && a.status[n] != 2);
+    bool finished;
+    const IpmResult r = ipm.solve(cfg.ipm, it > 0 && a.status[n] != 2, cfg.ipm_slice > 0 ? cfg.ipm_slice : (1 << 30),
+                                  a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE, finished);
+    if (!finished) return;                                                   // continues in the next launch
     double *inf = a.info + ((size_t)n * a.max_it + it) * INFO_STRIDE;
     const bool ok = (r.status == 0 || r.status == 3);
     warp_sync();

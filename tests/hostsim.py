@@ -26,7 +26,7 @@ class ScConfig(C.Structure):
                 ("weight_time", C.c_double), ("weight_trust_region_time", C.c_double),
                 ("weight_trust_region_trajectory", C.c_double), ("weight_virtual_control", C.c_double),
                 ("nu_tol", C.c_double), ("delta_tol", C.c_double), ("max_iterations", C.c_int), ("nsub", C.c_int),
-                ("keep_history", C.c_int), ("pad_", C.c_int), ("ipm", IpmSettings)]
+                ("keep_history", C.c_int), ("ipm_slice", C.c_int), ("ipm", IpmSettings)]
 
 
 def build():
@@ -66,12 +66,12 @@ def params_from_oracle(model, p):
     return P, np.array(p.x_init, float), np.array(p.x_final, float)
 
 
-def sc_config(ocfg, nsub=20, tol=1e-9, maxit=100, history=True, warm=0.0):
+def sc_config(ocfg, nsub=20, tol=1e-9, maxit=100, history=True, warm=0.0, ipm_slice=1):
     c = ScConfig()
     for f in ("K", "free_final_time", "interpolate_input", "nondimensionalize", "weight_time", "weight_trust_region_time",
               "weight_trust_region_trajectory", "weight_virtual_control", "nu_tol", "delta_tol", "max_iterations"):
         setattr(c, f, getattr(ocfg, f))
-    c.nsub = nsub; c.keep_history = int(history)
+    c.nsub = nsub; c.keep_history = int(history); c.ipm_slice = ipm_slice
     c.ipm.feastol = tol; c.ipm.abstol = tol; c.ipm.reltol = tol; c.ipm.maxit = maxit; c.ipm.warm = warm
     return c
 

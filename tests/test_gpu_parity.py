@@ -122,6 +122,27 @@ def test_sc_rocketquat_k50_interior_warm_start(S):
     _compare_run(S, "Rocket2D", O.ROCKET2D, [O.rocket2d()], K=30, max_it=15, warm=0.995)
 
 
+def test_round_slicing_is_bit_identical(S):
+    """the engine's rounds (one interior-point iteration per K2 launch, batch re-formed in between) and the lock-step mode
+    (whole sub-problem per launch) run the same arithmetic: identical bits, instance by instance"""
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50, max_iterations=6, keep_history=1)
+    cfg.ipm.warm = 0.995
+    xi = S.perturbed_initial_states(x_init, np.deg2rad([-20.0, 20.0, 0.0]), 96)
+    out = []
+    for sl in (0, 1, 3):
+        cfg.ipm_slice = sl
+        eng = S.SCAlgorithm(model, params, cfg, 96)
+        eng.set_boundary_states(xi, x_final)
+        eng.solve()
+        out.append((eng.get_all_solutions(), eng.get_info(), eng.get_solution()))
+        eng.close()
+    for o in out[1:]:
+        for a, b in zip(o[0], out[0][0]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(o[1], out[0][1])
+        assert np.array_equal(o[2]["iterations"], out[0][2]["iterations"]) and np.array_equal(o[2]["flags"], out[0][2]["flags"])
+
+
 def test_sc_rocketquat_starship_k100(S):
     """BASELINE.json configs[4]: Starship parameters, K=100"""
     p, rpy = O.starship()

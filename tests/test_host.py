@@ -130,9 +130,9 @@ def test_kernel_source_discretisation_vs_oracle():
     assert 8 < errs[0] / errs[1] < 24 and 8 < errs[1] / errs[2] < 24   # 4th-order convergence towards the RKF78 result
 
 
-@pytest.mark.parametrize("warm", [0.0, 0.995])
+@pytest.mark.parametrize("warm,ipm_slice", [(0.0, 1), (0.995, 1), (0.0, 0), (0.995, 3)])
 @pytest.mark.parametrize("name,model,K,max_it", [("Rocket2D", 1, 30, 15), ("RocketQuat", 0, 20, 5)])
-def test_kernel_source_sc_loop_vs_oracle(name, model, K, max_it, warm):
+def test_kernel_source_sc_loop_vs_oracle(name, model, K, max_it, warm, ipm_slice):
     """the K2/K3 source (structured IPM, one 'warp' of 1 lane) reproduces the literal ECOS-form oracle iterate by iterate"""
     if model == 0:
         p, _ = O.falcon9()
@@ -141,7 +141,7 @@ def test_kernel_source_sc_loop_vs_oracle(name, model, K, max_it, warm):
     ocfg = O.sc_config(K=K, model=model, max_iterations=max_it)
     ro = O.sc_solve(model, p, ocfg)
     P, xi, xf = H.params_from_oracle(model, p)
-    rh = H.sc_solve(model, P, H.sc_config(ocfg, tol=1e-8, warm=warm), xi, xf)
+    rh = H.sc_solve(model, P, H.sc_config(ocfg, tol=1e-8, warm=warm, ipm_slice=ipm_slice), xi, xf)
     n = ro["iterations"]
     assert n > 0 and rh["iters"][0] == n and bool(rh["converged"][0] == 1) == ro["converged"]
     for it in range(n + 1):
@@ -151,6 +151,17 @@ def test_kernel_source_sc_loop_vs_oracle(name, model, K, max_it, warm):
         assert rh["info"][0, it, 4] == ro["info"][it].weight_tr_used
         assert int(rh["info"][0, it, 6]) in (0, 3)
     assert np.allclose(rh["X"][0], ro["X"], rtol=1e-6, atol=1e-4 * np.abs(ro["X"]).max())
+
+
+def test_sliced_solver_is_bit_identical_to_unsliced():
+    """parking the interior-point state between launches (cfg.ipm_slice) must not change a single bit of the iterates"""
+    p, _ = O.falcon9()
+    ocfg = O.sc_config(K=20, model=0, max_iterations=4)
+    P, xi, xf = H.params_from_oracle(0, p)
+    ref = H.sc_solve(0, P, H.sc_config(ocfg, tol=1e-8, warm=0.995, ipm_slice=0), xi, xf)
+    for sl in (1, 2, 5):
+        r = H.sc_solve(0, P, H.sc_config(ocfg, tol=1e-8, warm=0.995, ipm_slice=sl), xi, xf)
+        assert np.array_equal(r["X_all"], ref["X_all"]) and np.array_equal(r["U_all"], ref["U_all"]) and np.array_equal(r["info"], ref["info"])
 
 
 def test_shard_range_partitions_the_batch():

@@ -20,3 +20,14 @@ for o in range(info.shape[1]):
     print(f"outer {o:2d}: ipm its mean {v.mean():5.1f} p50 {np.percentile(v,50):4.0f} p90 {np.percentile(v,90):4.0f} p99 {np.percentile(v,99):4.0f} max {v.max():4.0f}  status!=0: {(st[:,o]!=0).sum()}")
 print(f"sum of means {tot_mean:.1f}  sum of maxima {tot_max:.1f}  (kernel time follows the maxima: ratio {tot_max/tot_mean:.2f})")
 print(eng.last_timing())
+tot = it.sum(axis=1)
+print("per-instance total ipm iterations: mean %.1f p50 %.0f p90 %.0f p99 %.0f max %.0f" % (tot.mean(), np.percentile(tot, 50), np.percentile(tot, 90), np.percentile(tot, 99), tot.max()))
+order = np.argsort(-tot)[:6]
+for i in order:
+    print(f"instance {i}: total {tot[i]:.0f} per outer {it[i].astype(int).tolist()} n1 {info[i,-1,0]:.2e} sd {info[i,-1,1]:.2e} wtr {info[i,-1,4]:.0f}")
+i = np.argsort(tot)[len(tot)//2]
+print(f"median instance {i}: total {tot[i]:.0f} per outer {it[i].astype(int).tolist()} n1 {info[i,-1,0]:.2e} sd {info[i,-1,1]:.2e} wtr {info[i,-1,4]:.0f}")
+rounds = int(tot.max()) + 2
+act = [(tot > r).sum() for r in range(0, rounds, 10)]
+print("active instances every 10 rounds:", act)
+print("work conserving bound: sum/1024 = %.1f rounds of a full batch; actual rounds ~ %d" % (tot.sum() / len(tot), rounds))
