@@ -173,9 +173,9 @@ struct Ipm {
     SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 8 * m_rows(K) + n_ce(K) + (NB + NX) * ks(K) + K * FS + 16; }
     SCPP_HD static int ddt_doubles(int K) { return NX * NC * ks(K); }
     // shared window of the warp (chain phases only):
-    //   factorisation:  tile | record out | L_{k,k-1} | H | O | model terms          substitution: three record buffers
+    //   factorisation:  two tile buffers | record out | L_{k,k-1} | H | O | model terms          substitution: three record buffers
     static constexpr int HNC = pad2(NX + NX * NU + NU * NU);      // D | D C | C' D C  of the previous interval
-    static constexpr int W_DD = 0, W_FAC = W_DD + pad2(NX * NCP), W_LP = W_FAC + FS, W_MAT = W_LP + BLK, W_RK = W_MAT + 2 * BLK,
+    static constexpr int W_DD = 0, W_FAC = W_DD + 2 * pad2(NX * NCP), W_LP = W_FAC + FS, W_MAT = W_LP + BLK, W_RK = W_MAT + 2 * BLK,
                          W_F_END = W_RK + 2 * NRK * NB, W_S_END = 3 * FS,
                          W_UEND = W_F_END > W_S_END ? W_F_END : W_S_END,
                          W_WB = W_UEND, W_HN = W_WB + pad2(RS), W_VEC = W_HN + HNC, W_X = W_VEC + 6 * NB, W_SC = W_X + 2 * pad2(NX),
@@ -240,10 +240,10 @@ struct Ipm {
         memcpy(dst, src, sizeof(double) * n);
 #endif
     }
-    SCPP_HD void ld_dd(int k) const   // the [A|B|C|s|z]_k tile: NX rows of NC doubles into rows of stride NCP
+    SCPP_HD void ld_dd(int k) const   // the [A|B|C|s|z]_k tile: NX rows of NC doubles into rows of stride NCP (buffer k & 1)
     {
         const double *src = dd + (size_t)k * NX * NC;
-        double *t = sm + W_DD;
+        double *t = tile(k);
 #if defined(__CUDA_ARCH__)
         const unsigned d0 = (unsigned)__cvta_generic_to_shared(t);
         for (int c = lane_id(); c < NX * (NC / 2); c += LANES) {
@@ -263,7 +263,8 @@ struct Ipm {
     SCPP_HD void ld_wait(int pending = 0) const   // all but the `pending` most recent groups have landed
     {
 #if defined(__CUDA_ARCH__)
-        if (pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
         warp_sync();
@@ -273,7 +274,7 @@ struct Ipm {
     SCPP_HD double *vec(int i) const { return sm + W_VEC + i * NB; }
     SCPP_HD double *xv(int i) const { return sm + W_X + i * pad2(NX); }
     SCPP_HD double *sc() const { return sm + W_SC; }
-    SCPP_HD double *tile() const { return sm + W_DD; }
+    SCPP_HD double *tile(int k) const { return sm + W_DD + (k & 1) * pad2(NX * NCP); }
     SCPP_HD double *facw() const { return sm + W_FAC; }
     SCPP_HD double *fbuf(int b) const { return sm + b * FS; }
 
@@ -312,12 +313,12 @@ struct Ipm {
         warp_sync();
     }
     // once per stage of the chain: only the linearised minimum-thrust row depends on k (coefficient slots < 0 take -tdir[k])
-    SCPP_HD void tables_stage(int k) const
+    SCPP_HD void tables_stage(const double *td) const   // td: the stage's direction in the shared window
     {
         FOR_LANE(e, NROW * 3) {
             const int r = e / 3, q = e - 3 * r;
             const RowDesc rd = M::row(r);
-            if (q < rd.n && rd.cs[q] < 0) rcq()[r * 4 + q] = -tdir[3 * k + (-rd.cs[q] - 1)];
+            if (q < rd.n && rd.cs[q] < 0) rcq()[r * 4 + q] = -td[-rd.cs[q] - 1];
         }
     }
     // ---- model rows in the stage-parallel passes: the row index is a compile-time constant after unrolling, so the row table
@@ -349,45 +350,91 @@ struct Ipm {
     //  arithmetic; a cone whose margin u0 - |u1| is lost to rounding (active to ~1e-16 relative) is nudged back inside by a
     //  few ulps of u0 so the next Nesterov-Todd scaling stays defined (perturbation << the 1e-8 tolerances).
     // =============================================================================================================
+    // Memory-level parallelism: the compiler may not move a load above a store to another workspace array (the arrays are
+    // not provably disjoint to it), so every block of a stage-parallel pass is written  LOAD everything -> compute -> STORE:
+    // dozens of independent, coalesced loads are in flight per lane instead of two, and a stage costs a handful of DRAM
+    // round trips instead of a hundred (ncu: these passes were 80-96 % long-scoreboard stalls).
+    template <int R0, int NR>
+    SCPP_HD void upd_rows(double a, int k, double (&S)[NR], double (&Z)[NR]) const      // S,Z <- (s,z) + a (ds,dz) for rows R0..R0+NR-1
+    {
+        double dS[NR], dZ[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) { S[r] = s[(R0 + r) * KS + k]; dS[r] = ds[(R0 + r) * KS + k]; Z[r] = z[(R0 + r) * KS + k]; dZ[r] = dz[(R0 + r) * KS + k]; }
+#pragma unroll
+        for (int r = 0; r < NR; r++) { S[r] += a * dS[r]; Z[r] += a * dZ[r]; }
+    }
+    template <int R0, int NR>
+    SCPP_HD void put_rows(int k, const double (&S)[NR], const double (&Z)[NR])
+    {
+#pragma unroll
+        for (int r = 0; r < NR; r++) { s[(R0 + r) * KS + k] = S[r]; z[(R0 + r) * KS + k] = Z[r]; }
+    }
     SCPP_HD void pass_update(double a)
     {
         FOR_LANE(k, K) {
             const bool hasint = k < K - 1;
-#pragma unroll 4
-            for (int e = 0; e < PSN; e++) prim[e * KS + k] += a * dprim[e * KS + k];
+            {
+                double p[PSN], d[PSN];
 #pragma unroll
-            for (int r = 0; r < NLP; r++) {
-                s[r * KS + k] = nudge(s[r * KS + k] + a * ds[r * KS + k], 0.);
-                z[r * KS + k] = nudge(z[r * KS + k] + a * dz[r * KS + k], 0.);
+                for (int e = 0; e < PSN; e++) { p[e] = prim[e * KS + k]; d[e] = dprim[e * KS + k]; }
+#pragma unroll
+                for (int e = 0; e < PSN; e++) prim[e * KS + k] = p[e] + a * d[e];
             }
+            {   // model rows: LP rows, then the model cones
+                double S[NROW], Z[NROW];
+                upd_rows<0, NROW>(a, k, S, Z);
 #pragma unroll
-            for (int c = 0; c < NCN; c++) {
-                const int o = (c < NCONE) ? NLP + M::cone_off(c) : TRO, d = (c < NCONE) ? M::cone_dim(c) : D;
-                double ts = 0, tz = 0;
-#pragma unroll 6
-                for (int i = 1; i < d; i++) {
-                    const double sv = s[(o + i) * KS + k] + a * ds[(o + i) * KS + k], zv = z[(o + i) * KS + k] + a * dz[(o + i) * KS + k];
-                    s[(o + i) * KS + k] = sv; z[(o + i) * KS + k] = zv;
-                    ts += sv * sv; tz += zv * zv;
+                for (int r = 0; r < NLP; r++) { S[r] = nudge(S[r], 0.); Z[r] = nudge(Z[r], 0.); }
+#pragma unroll
+                for (int c = 0; c < NCONE; c++) {
+                    const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
+                    double ts = 0, tz = 0;
+#pragma unroll
+                    for (int i = 1; i < soc::SOC_MAXD; i++) if (i < d) { ts += S[o + i] * S[o + i]; tz += Z[o + i] * Z[o + i]; }
+                    S[o] = nudge(S[o], sqrt(ts)); Z[o] = nudge(Z[o], sqrt(tz));
                 }
-                s[o * KS + k] = nudge(s[o * KS + k] + a * ds[o * KS + k], sqrt(ts));
-                z[o * KS + k] = nudge(z[o * KS + k] + a * dz[o * KS + k], sqrt(tz));
+                put_rows<0, NROW>(k, S, Z);
             }
-            if (hasint) {
-#pragma unroll 4
-                for (int r = MN; r < RS; r++) {
-                    s[r * KS + k] = nudge(s[r * KS + k] + a * ds[r * KS + k], 0.);
-                    z[r * KS + k] = nudge(z[r * KS + k] + a * dz[r * KS + k], 0.);
+            {   // trust-region cone
+                double S[D], Z[D];
+                upd_rows<TRO, D>(a, k, S, Z);
+                double ts = 0, tz = 0;
+#pragma unroll
+                for (int i = 1; i < D; i++) { ts += S[i] * S[i]; tz += Z[i] * Z[i]; }
+                S[0] = nudge(S[0], sqrt(ts)); Z[0] = nudge(Z[0], sqrt(tz));
+                put_rows<TRO, D>(k, S, Z);
+            }
+            if (hasint) {   // virtual-control pairs: s- rows, then s+ rows of the interval
+                {
+                    double S[NX], Z[NX];
+                    upd_rows<MN, NX>(a, k, S, Z);
+#pragma unroll
+                    for (int r = 0; r < NX; r++) { S[r] = nudge(S[r], 0.); Z[r] = nudge(Z[r], 0.); }
+                    put_rows<MN, NX>(k, S, Z);
+                }
+                {
+                    double S[NX], Z[NX];
+                    upd_rows<MN + NX, NX>(a, k, S, Z);
+#pragma unroll
+                    for (int r = 0; r < NX; r++) { S[r] = nudge(S[r], 0.); Z[r] = nudge(Z[r], 0.); }
+                    put_rows<MN + NX, NX>(k, S, Z);
                 }
             }
         }
         if (lane_id() == 0) {
             const int r0 = RS * KS, p0 = PSN * KS;
-            for (int i = 0; i < 4; i++) { s[r0 + i] += a * ds[r0 + i]; z[r0 + i] += a * dz[r0 + i]; }
-            prim[p0] += a * dprim[p0]; prim[p0 + 1] += a * dprim[p0 + 1];
-            s[r0] = nudge(s[r0], 0.); z[r0] = nudge(z[r0], 0.);
-            s[r0 + 1] = nudge(s[r0 + 1], sqrt(s[r0 + 2] * s[r0 + 2] + s[r0 + 3] * s[r0 + 3]));
-            z[r0 + 1] = nudge(z[r0 + 1], sqrt(z[r0 + 2] * z[r0 + 2] + z[r0 + 3] * z[r0 + 3]));
+            double s4[4], z4[4], d4[4], e4[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { s4[i] = s[r0 + i]; d4[i] = ds[r0 + i]; z4[i] = z[r0 + i]; e4[i] = dz[r0 + i]; }
+            const double p0v = prim[p0], p1v = prim[p0 + 1], d0v = dprim[p0], d1v = dprim[p0 + 1];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { s4[i] += a * d4[i]; z4[i] += a * e4[i]; }
+            s4[0] = nudge(s4[0], 0.); z4[0] = nudge(z4[0], 0.);
+            s4[1] = nudge(s4[1], sqrt(s4[2] * s4[2] + s4[3] * s4[3]));
+            z4[1] = nudge(z4[1], sqrt(z4[2] * z4[2] + z4[3] * z4[3]));
+#pragma unroll
+            for (int i = 0; i < 4; i++) { s[r0 + i] = s4[i]; z[r0 + i] = z4[i]; }
+            prim[p0] = p0v + a * d0v; prim[p0 + 1] = p1v + a * d1v;
         }
         warp_sync();
     }
@@ -395,6 +442,31 @@ struct Ipm {
     // =============================================================================================================
     //  stage-parallel pass R : residuals, Nesterov-Todd scaling, termination quantities
     // =============================================================================================================
+    // model rows on register copies of xi (the row index is a compile-time constant after unrolling: immediates and registers);
+    // td = linearised minimum-thrust direction of the stage
+    SCPP_HD double coef_reg(const RowDesc &rd, int q, const double *td) const { return rd.cs[q] >= 0 ? cstw()[rd.cs[q]] : -td[-rd.cs[q] - 1]; }
+    SCPP_HD double row_dot_reg(int r, const double *td, const double *P) const
+    {
+        const RowDesc rd = M::crow(r);
+        double a = 0;
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (q < rd.n) a += coef_reg(rd, q, td) * P[rd.idx[q]];
+        return a;
+    }
+    SCPP_HD void row_scatter_reg(int r, const double *td, double v, double *acc) const
+    {
+        const RowDesc rd = M::crow(r);
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (q < rd.n) acc[rd.idx[q]] += coef_reg(rd, q, td) * v;
+    }
+    // one row of interval k for the stage-parallel passes: the tile row [A~ | C | s | z] (NC) followed by `NA` per-row scalars
+    static constexpr int IR_SM = NC, IR_SP = NC + 1, IR_ZM = NC + 2, IR_ZP = NC + 3;
+    SCPP_HD void ld_tile_row(int i, int k, double *row) const
+    {
+#pragma unroll
+        for (int j = 0; j < NC; j++) row[j] = T(i, j, k);
+    }
+
     SCPP_HD void pass_residuals(Norms &nm, bool identity)
     {
         double gap = 0, rz2 = 0, pcost = 0, zrz = 0, h2 = 0, rx2 = 0, xrx = 0, acc_sig = 0;
@@ -402,148 +474,189 @@ struct Ipm {
         const double sg = prim[PSN * KS];
         FOR_LANE(k, K) {
             const bool hasint = k < K - 1;
-            double P[NB], RXa[NB];
+            double P[NB], RXa[NB], td[3];
+            // ---- block 1 (loads): xi, delta, the trust-region cone, the linearisation point
+            double S[D], Z[D], XB[NB];
 #pragma unroll
             for (int j = 0; j < NB; j++) { P[j] = prim[j * KS + k]; RXa[j] = 0.; }
             const double delta = prim[NB * KS + k];
-            // ---- trust-region cone  (delta ; xibar - xi) in Q^{1+NB}
-            {
-                double S[D], Z[D];
 #pragma unroll
-                for (int i = 0; i < D; i++) { S[i] = s[(TRO + i) * KS + k]; Z[i] = z[(TRO + i) * KS + k]; }
+            for (int i = 0; i < D; i++) { S[i] = s[(TRO + i) * KS + k]; Z[i] = z[(TRO + i) * KS + k]; }
+#pragma unroll
+            for (int j = 0; j < NB; j++) XB[j] = xibar(k, j);
+#pragma unroll
+            for (int q = 0; q < 3; q++) td[q] = tdir[3 * k + q];
+            // ---- trust-region cone  (delta ; xibar - xi) in Q^{1+NB}:  S <- wb, Z <- lam, RZ
+            {
+                double RZ[D];
                 double a = 0, b = 0, c = S[0] * Z[0];
-                {
-                    const double r0 = S[0] - delta;
-                    rz[TRO * KS + k] = r0; rz2 += r0 * r0; zrz += Z[0] * r0;
-                }
+                const double z0 = Z[0];
+                RZ[0] = S[0] - delta; rz2 += RZ[0] * RZ[0]; zrz += Z[0] * RZ[0];
 #pragma unroll
                 for (int i = 1; i < D; i++) {
-                    const double xb = xibar(k, i - 1);
+                    const double xb = XB[i - 1];
                     const double rv = S[i] - (xb - P[i - 1]);
-                    rz[(TRO + i) * KS + k] = rv;
+                    RZ[i] = rv;
                     h2 += xb * xb; rz2 += rv * rv; zrz += Z[i] * rv;
                     a += S[i] * S[i]; b += Z[i] * Z[i]; c += S[i] * Z[i];
                     RXa[i - 1] += Z[i];                                    // G'z of the trust-region rows
                 }
                 gap += c; pcost += w_tr * delta;
-                if (identity) {
+                double cev = 1.;
+                const double ss = S[0] * S[0] - a, zz = Z[0] * Z[0] - b;
+                const bool okc = (ss > 0.) && (zz > 0.) && (S[0] > 0.) && (Z[0] > 0.);
+                if (identity || !okc) {
+                    if (!identity) bad = 1;
 #pragma unroll
-                    for (int i = 0; i < D; i++) { wb[(TRO + i) * KS + k] = i == 0; lam[(TRO + i) * KS + k] = i == 0; }
-                    ce[NCONE * KS + k] = 1.;
+                    for (int i = 0; i < D; i++) { S[i] = i == 0; Z[i] = i == 0; }
                 } else {
-                    const double ss = S[0] * S[0] - a, zz = Z[0] * Z[0] - b;
-                    if (!(ss > 0.) || !(zz > 0.) || !(S[0] > 0.) || !(Z[0] > 0.)) bad = 1;
-                    else {
-                        const double sn = sqrt(ss), zn = sqrt(zz);
-                        const double i2g = 1. / (2. * sqrt((1. + c / (sn * zn)) / 2.));
-                        const double isn = i2g / sn, izn = i2g / zn;
-                        const double w0 = S[0] * isn + Z[0] * izn;
-                        double w1z1 = 0;
+                    const double sn = sqrt(ss), zn = sqrt(zz);
+                    const double i2g = 1. / (2. * sqrt((1. + c / (sn * zn)) / 2.));
+                    const double isn = i2g / sn, izn = i2g / zn;
+                    const double w0 = S[0] * isn + Z[0] * izn;
+                    double w1z1 = 0;
 #pragma unroll
-                        for (int i = 1; i < D; i++) { const double wi = S[i] * isn - Z[i] * izn; w1z1 += wi * Z[i]; S[i] = wi; }
-                        const double eta = sqrt(sn / zn), f = Z[0] + w1z1 / (1. + w0);
-                        wb[TRO * KS + k] = w0; lam[TRO * KS + k] = eta * (w0 * Z[0] + w1z1);
+                    for (int i = 1; i < D; i++) { const double wi = S[i] * isn - Z[i] * izn; w1z1 += wi * Z[i]; S[i] = wi; }
+                    const double eta = sqrt(sn / zn), f = Z[0] + w1z1 / (1. + w0);
+                    S[0] = w0; Z[0] = eta * (w0 * Z[0] + w1z1);
 #pragma unroll
-                        for (int i = 1; i < D; i++) { wb[(TRO + i) * KS + k] = S[i]; lam[(TRO + i) * KS + k] = eta * (Z[i] + f * S[i]); }
-                        ce[NCONE * KS + k] = zn / sn;
+                    for (int i = 1; i < D; i++) Z[i] = eta * (Z[i] + f * S[i]);
+                    cev = zn / sn;
+                }
+#pragma unroll
+                for (int i = 0; i < D; i++) { rz[(TRO + i) * KS + k] = RZ[i]; wb[(TRO + i) * KS + k] = S[i]; lam[(TRO + i) * KS + k] = Z[i]; }
+                ce[NCONE * KS + k] = cev;
+                rx[NB * KS + k] = w_tr - z0;
+                rx2 += (w_tr - z0) * (w_tr - z0); xrx += delta * (w_tr - z0);
+            }
+            // ---- block 2: model rows (LP rows, model cones):  S2 <- wb, Z2 <- lam, RZ2
+            {
+                double S2[NROW], Z2[NROW], RZ2[NROW], CEv[NCONE];
+#pragma unroll
+                for (int r = 0; r < NROW; r++) { S2[r] = s[r * KS + k]; Z2[r] = z[r * KS + k]; }
+#pragma unroll
+                for (int c = 0; c < NCONE; c++) {
+                    const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
+                    double sk[soc::SOC_MAXD], zk[soc::SOC_MAXD], w[soc::SOC_MAXD], lm[soc::SOC_MAXD];
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) {
+                        const RowDesc rd = M::crow(o + r);
+                        const double hh = row_h(rd), sl = hh - row_dot_reg(o + r, td, P);
+                        sk[r] = S2[o + r]; zk[r] = Z2[o + r];
+                        const double rv = sk[r] - sl;
+                        RZ2[o + r] = rv;
+                        h2 += hh * hh; gap += sk[r] * zk[r]; rz2 += rv * rv; zrz += zk[r] * rv;
+                        row_scatter_reg(o + r, td, zk[r], RXa);
                     }
-                }
-                rx[NB * KS + k] = w_tr - Z[0];
-                rx2 += (w_tr - Z[0]) * (w_tr - Z[0]); xrx += delta * (w_tr - Z[0]);
-            }
-            // ---- model cones
+                    double e2i = 1.;
+                    if (identity) {
 #pragma unroll
-            for (int c = 0; c < NCONE; c++) {
-                const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
-                double sk[soc::SOC_MAXD], zk[soc::SOC_MAXD], w[soc::SOC_MAXD], lm[soc::SOC_MAXD];
+                        for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) { w[r] = r == 0; lm[r] = r == 0; }
+                    } else if (!soc::scale(sk, zk, d, w, e2i, lm)) {
+                        bad = 1;
 #pragma unroll
-                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) {
-                    const RowDesc rd = M::crow(o + r);
-                    const double hh = row_h(rd), sl = hh - row_dot(o + r, k, prim);
-                    sk[r] = s[(o + r) * KS + k]; zk[r] = z[(o + r) * KS + k];
-                    const double rv = sk[r] - sl;
-                    rz[(o + r) * KS + k] = rv;
-                    h2 += hh * hh; gap += sk[r] * zk[r]; rz2 += rv * rv; zrz += zk[r] * rv;
-                    row_scatter(o + r, k, zk[r], RXa);
-                }
-                double e2i = 1.;
-                if (identity) {
+                        for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) { w[r] = r == 0; lm[r] = r == 0; }
+                    }
 #pragma unroll
-                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) { w[r] = r == 0; lm[r] = r == 0; }
-                } else if (!soc::scale(sk, zk, d, w, e2i, lm)) {
-                    bad = 1;
-#pragma unroll
-                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) { w[r] = r == 0; lm[r] = r == 0; }
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) { S2[o + r] = w[r]; Z2[o + r] = lm[r]; }
+                    CEv[c] = e2i;
                 }
 #pragma unroll
-                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) { wb[(o + r) * KS + k] = w[r]; lam[(o + r) * KS + k] = lm[r]; }
-                ce[c * KS + k] = e2i;
-            }
-            // ---- model LP rows
+                for (int r = 0; r < NLP; r++) {
+                    const RowDesc rd = M::crow(r);
+                    const double hh = row_h(rd), sl = hh - row_dot_reg(r, td, P);
+                    const double sv = S2[r], zv = Z2[r];
+                    const double rv = sv - sl;
+                    RZ2[r] = rv;
+                    h2 += hh * hh;
+                    if (!(sv > 0.) || !(zv > 0.)) bad = 1;
+                    S2[r] = identity ? 1. : zv / sv; Z2[r] = identity ? 1. : sqrt(sv * zv);
+                    gap += sv * zv; rz2 += rv * rv; zrz += zv * rv;
+                    row_scatter_reg(r, td, zv, RXa);
+                }
 #pragma unroll
-            for (int r = 0; r < NLP; r++) {
-                const RowDesc rd = M::crow(r);
-                const double hh = row_h(rd), sl = hh - row_dot(r, k, prim);
-                const double sv = s[r * KS + k], zv = z[r * KS + k];
-                const double rv = sv - sl;
-                rz[r * KS + k] = rv;
-                h2 += hh * hh;
-                if (!(sv > 0.) || !(zv > 0.)) bad = 1;
-                wb[r * KS + k] = identity ? 1. : zv / sv; lam[r * KS + k] = identity ? 1. : sqrt(sv * zv);
-                gap += sv * zv; rz2 += rv * rv; zrz += zv * rv;
-                row_scatter(r, k, zv, RXa);
+                for (int r = 0; r < NROW; r++) { rz[r * KS + k] = RZ2[r]; wb[r * KS + k] = S2[r]; lam[r * KS + k] = Z2[r]; }
+#pragma unroll
+                for (int c = 0; c < NCONE; c++) ce[c * KS + k] = CEv[c];
             }
-            // ---- interval k: virtual-control pairs  t_i >= |r_i| ,  r = x_{k+1} - A~ xi_k - C u_{k+1} - s sigma - z
+            // ---- block 3: interval k: virtual-control pairs  t_i >= |r_i| ,  r = x_{k+1} - A~ xi_k - C u_{k+1} - s sigma - z ;
+            //      the loads of row i+1 are issued before the stores of row i
             if (hasint) {
-                double UN[NU];
+                constexpr int NR = NC + 6;
+                double UN[NU], cur[NR], nxt[NR];
 #pragma unroll
                 for (int a = 0; a < NU; a++) UN[a] = prim[(NX + a) * KS + k + 1];
-#pragma unroll 2
-                for (int i = 0; i < NX; i++) {
+                auto ld_row = [&](int i, double *row) {
+                    ld_tile_row(i, k, row);
                     const int o = MN + i;
-                    const double sm_ = s[o * KS + k], sp = s[(o + NX) * KS + k], zm = z[o * KS + k], zp = z[(o + NX) * KS + k];
+                    row[IR_SM] = s[o * KS + k]; row[IR_SP] = s[(o + NX) * KS + k]; row[IR_ZM] = z[o * KS + k]; row[IR_ZP] = z[(o + NX) * KS + k];
+                    row[NC + 4] = prim[(PN + i) * KS + k]; row[NC + 5] = prim[i * KS + k + 1];
+                };
+                auto do_row = [&](int i, const double *cur) {
+                    const int o = MN + i;
+                    const double sm_ = cur[IR_SM], sp = cur[IR_SP], zm = cur[IR_ZM], zp = cur[IR_ZP];
                     const double wi = zm - zp;
-                    double acc = prim[i * KS + k + 1], acc2 = 0;
+                    double acc = cur[NC + 5], acc2 = 0;
 #pragma unroll
                     for (int j = 0; j < NB; j += 2) {
-                        const double t0 = T(i, j, k), t1 = T(i, j + 1, k);
+                        const double t0 = cur[j], t1 = cur[j + 1];
                         acc -= t0 * P[j]; acc2 -= t1 * P[j + 1];
                         RXa[j] -= t0 * wi; RXa[j + 1] -= t1 * wi;
                     }
 #pragma unroll
-                    for (int a = 0; a < NU; a++) acc2 -= T(i, NB + a, k) * UN[a];
-                    const double tsg = T(i, NB + NU, k), zc = T(i, NB + NU + 1, k);
+                    for (int a = 0; a < NU; a++) acc2 -= cur[NB + a] * UN[a];
+                    const double tsg = cur[NB + NU], zc = cur[NB + NU + 1];
                     const double r = acc + acc2 - tsg * sg - zc;
                     acc_sig -= tsg * wi;
-                    const double t = prim[(PN + i) * KS + k];
+                    const double t = cur[NC + 4];
                     const double rm = sm_ - (t - r), rp = sp - (t + r);
-                    rz[o * KS + k] = rm; rz[(o + NX) * KS + k] = rp;
                     if (!(sm_ > 0.) || !(sp > 0.) || !(zm > 0.) || !(zp > 0.)) bad = 1;
+                    const double rxt = w_vc - zm - zp;
+                    rz[o * KS + k] = rm; rz[(o + NX) * KS + k] = rp;
                     wb[o * KS + k] = identity ? 1. : zm / sm_; wb[(o + NX) * KS + k] = identity ? 1. : zp / sp;
                     lam[o * KS + k] = identity ? 1. : sqrt(sm_ * zm); lam[(o + NX) * KS + k] = identity ? 1. : sqrt(sp * zp);
-                    const double rxt = w_vc - zm - zp;
                     rx[(PN + i) * KS + k] = rxt;
                     rx2 += rxt * rxt; xrx += t * rxt;
                     gap += sm_ * zm + sp * zp; rz2 += rm * rm + rp * rp; zrz += zm * rm + zp * rp;
                     pcost += w_vc * t;
                     h2 += 2. * zc * zc;
+                };
+                // two-row software pipeline (rolled: the fully unrolled form thrashes the instruction cache): the loads of the
+                // next row are issued before the stores of the current one; the two buffers alternate by code position
+                ld_row(0, cur);
+#pragma unroll 1
+                for (int i = 0; i < NX; i += 2) {
+                    ld_row(i + 1, nxt);
+                    do_row(i, cur);
+                    if (i + 2 < NX) ld_row(i + 2, cur);
+                    do_row(i + 1, nxt);
                 }
             } else {
-#pragma unroll 2
+#pragma unroll
                 for (int i = 0; i < NX; i++) {
                     const int o = MN + i;
                     rz[o * KS + k] = 0.; rz[(o + NX) * KS + k] = 0.; wb[o * KS + k] = 1.; wb[(o + NX) * KS + k] = 1.;
                     lam[o * KS + k] = 1.; lam[(o + NX) * KS + k] = 1.; rx[(PN + i) * KS + k] = 0.;
                 }
             }
-            // ---- coupling from interval k-1:  [w ; -C' w],  w = z- - z+ of that interval
+            // ---- block 4: coupling from interval k-1:  [w ; -C' w],  w = z- - z+ of that interval (two load groups)
             if (k > 0) {
+                constexpr int HX = NX / 2;
 #pragma unroll
-                for (int i = 0; i < NX; i++) {
-                    const double wp = z[(MN + i) * KS + k - 1] - z[(MN + NX + i) * KS + k - 1];
-                    RXa[i] += wp;
+                for (int h = 0; h < 2; h++) {
+                    double wp[HX], Cc[HX][NU];
 #pragma unroll
-                    for (int a = 0; a < NU; a++) RXa[NX + a] -= T(i, NB + a, k - 1) * wp;
+                    for (int i = 0; i < HX; i++) {
+                        wp[i] = z[(MN + h * HX + i) * KS + k - 1] - z[(MN + NX + h * HX + i) * KS + k - 1];
+#pragma unroll
+                        for (int a = 0; a < NU; a++) Cc[i][a] = T(h * HX + i, NB + a, k - 1);
+                    }
+#pragma unroll
+                    for (int i = 0; i < HX; i++) {
+                        RXa[h * HX + i] += wp[i];
+#pragma unroll
+                        for (int a = 0; a < NU; a++) RXa[NX + a] -= Cc[i][a] * wp[i];
+                    }
                 }
             }
             const uint32_t mk = fixm[k];
@@ -558,25 +671,31 @@ struct Ipm {
         // ---- globals: lane 0
         if (lane_id() == 0) {
             const int r0 = RS * KS, c0 = NCN * KS, p0 = PSN * KS;
+            double s4[4], z4[4], w4[4], l4[4], r4[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { s4[i] = s[r0 + i]; z4[i] = z[r0 + i]; }
             const double dsg = prim[p0 + 1];
-            double rxs = w_time + acc_sig;
-            rz[r0] = s[r0] - (sg - 0.001);                          // sigma >= 0.001   (SCProblem.cpp:34)
-            rxs -= z[r0];
-            if (!(s[r0] > 0.) || !(z[r0] > 0.)) bad = 1;
-            wb[r0] = identity ? 1. : z[r0] / s[r0]; lam[r0] = identity ? 1. : sqrt(s[r0] * z[r0]);
-            rz[r0 + 1] = s[r0 + 1] - (0.5 + 0.5 * dsg);            // ((1+dsg)/2 ; (1-dsg)/2 ; sigma - sigbar)   (:92-96)
-            rz[r0 + 2] = s[r0 + 2] - (0.5 - 0.5 * dsg);
-            rz[r0 + 3] = s[r0 + 3] - (sg - sigbar);
-            rxs -= z[r0 + 3];
-            rx[p0 + 1] = w_trs - 0.5 * z[r0 + 1] + 0.5 * z[r0 + 2];
-            rx[p0] = rxs;
-            if (identity) { ce[c0] = 1.; for (int i = 0; i < 3; i++) { wb[r0 + 1 + i] = i == 0; lam[r0 + 1 + i] = i == 0; } }
-            else if (!soc::scale(s + r0 + 1, z + r0 + 1, 3, wb + r0 + 1, ce[c0], lam + r0 + 1)) bad = 1;
-            for (int r = 0; r < 4; r++) { gap += s[r0 + r] * z[r0 + r]; rz2 += rz[r0 + r] * rz[r0 + r]; zrz += z[r0 + r] * rz[r0 + r]; }
+            double rxs = w_time + acc_sig, cev = 1.;
+            r4[0] = s4[0] - (sg - 0.001);                           // sigma >= 0.001   (SCProblem.cpp:34)
+            rxs -= z4[0];
+            if (!(s4[0] > 0.) || !(z4[0] > 0.)) bad = 1;
+            w4[0] = identity ? 1. : z4[0] / s4[0]; l4[0] = identity ? 1. : sqrt(s4[0] * z4[0]);
+            r4[1] = s4[1] - (0.5 + 0.5 * dsg);                      // ((1+dsg)/2 ; (1-dsg)/2 ; sigma - sigbar)   (:92-96)
+            r4[2] = s4[2] - (0.5 - 0.5 * dsg);
+            r4[3] = s4[3] - (sg - sigbar);
+            rxs -= z4[3];
+            const double rxd = w_trs - 0.5 * z4[1] + 0.5 * z4[2];
+            if (identity) { for (int i = 0; i < 3; i++) { w4[1 + i] = i == 0; l4[1 + i] = i == 0; } }
+            else if (!soc::scale(s4 + 1, z4 + 1, 3, w4 + 1, cev, l4 + 1)) { bad = 1; for (int i = 0; i < 3; i++) { w4[1 + i] = i == 0; l4[1 + i] = i == 0; } }
+#pragma unroll
+            for (int i = 0; i < 4; i++) { rz[r0 + i] = r4[i]; wb[r0 + i] = w4[i]; lam[r0 + i] = l4[i]; }
+            ce[c0] = cev;
+            rx[p0 + 1] = rxd; rx[p0] = rxs;
+            for (int r = 0; r < 4; r++) { gap += s4[r] * z4[r]; rz2 += r4[r] * r4[r]; zrz += z4[r] * r4[r]; }
             pcost += w_time * sg + w_trs * dsg;
             h2 += 0.001 * 0.001 + 0.5 + sigbar * sigbar;
-            rx2 += rx[p0] * rx[p0] + rx[p0 + 1] * rx[p0 + 1];
-            xrx += sg * rx[p0] + dsg * rx[p0 + 1];
+            rx2 += rxs * rxs + rxd * rxd;
+            xrx += sg * rxs + dsg * rxd;
         }
         warp_sync();
         nm.gap = warp_sum(gap); nm.rz2 = warp_sum(rz2); nm.pcost = warp_sum(pcost); nm.zrz = warp_sum(zrz);
@@ -697,15 +816,49 @@ struct Ipm {
         FOR_LANE(e, HNC) Dp[e] = 0.;
         FOR_LANE(j, NB) { bn[j] = 0.; lprev[j] = 0.; }
         warp_sync();
+        // prefetch: the tile of interval k+1 is copied while stage k is factored; the scaling rows, cone scalars and the
+        // minimum-thrust direction of stage k+1 wait in registers (strided global loads issued one stage ahead)
+        double *TD = sc() + 16;
+        if (K > 1) ld_dd(0);
+        ld_commit();
+#if defined(__CUDA_ARCH__)
+        constexpr int WBN = (RS + LANES - 1) / LANES;
+        double wbn[WBN], cen = 0., tdn = 0.;
+        {
+            const int l = lane_id();
+#pragma unroll
+            for (int i = 0; i < WBN; i++) wbn[i] = (l + LANES * i < RS) ? wb[(l + LANES * i) * KS] : 0.;
+            if (l < NCN) cen = ce[l * KS];
+            if (l < 3) tdn = tdir[l];
+        }
+#endif
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
             const bool hasint = k < K - 1;
-            if (hasint) ld_dd(k);
+            if (k + 1 < K - 1) ld_dd(k + 1);
             ld_commit();
+#if defined(__CUDA_ARCH__)
+            {
+                const int l = lane_id();
+#pragma unroll
+                for (int i = 0; i < WBN; i++) if (l + LANES * i < RS) WB[l + LANES * i] = wbn[i];
+                if (l < NCN) CE[l] = cen;
+                if (l < 3) TD[l] = tdn;
+                if (k + 1 < K) {
+#pragma unroll
+                    for (int i = 0; i < WBN; i++) wbn[i] = (l + LANES * i < RS) ? wb[(l + LANES * i) * KS + k + 1] : 0.;
+                    if (l < NCN) cen = ce[l * KS + k + 1];
+                    if (l < 3) tdn = tdir[3 * (k + 1) + l];
+                }
+            }
+#else
             FOR_LANE(r, RS) WB[r] = wb[r * KS + k];
             FOR_LANE(c, NCN) CE[c] = ce[c * KS + k];
-            tables_stage(k);
-            ld_wait();
+            FOR_LANE(q, 3) TD[q] = tdir[3 * k + q];
+#endif
+            warp_sync();
+            tables_stage(TD);
+            ld_wait(1);
             build_model_terms(WB, CE, alpha);
             // ---- node part of H_kk (trust region with delta eliminated) + carry from interval k-1: dense part, then the
             //      model cones / rows, each of which touches at most 4 variables (sparse rank-1 terms, one cone at a time)
@@ -747,7 +900,7 @@ struct Ipm {
             warp_sync();
             // ---- interval k: H_kk += A~' D A~ ; O = [-D A~ ; C' D A~] ; carry = (D, D C, C' D C) ; borders
             if (hasint) {
-                double *t = tile();
+                double *t = tile(k);
                 FOR_LANE(i, NX) { const double dm = WB[MN + i], dp = WB[MN + NX + i]; Dt[i] = 4. * dm * dp / (dm + dp); }
                 warp_sync();
                 // O rows of the x_{k+1} block are -D A~ ; keep D A~ for the products: O[a][b], a < NX
@@ -862,45 +1015,69 @@ struct Ipm {
         return mode == 0 ? dprim[e * KS + k] : (mode == 1 ? -rx[e * KS + k] : -csig * rx[e * KS + k]);
     }
 
+    // rzv of rows R0..R0+NR-1 in scaled-residual form needs, per mode:  0: ds   1: rz, s   2: lam, cr, rz  -> in0, in1, in2
+    template <int NR>
+    SCPP_HD void ld_rhs_rows(int mode, int r0, int k, double *in0, double *in1, double *in2) const
+    {
+        if (mode == 0) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) in0[r] = ds[(r0 + r) * KS + k];
+        } else if (mode == 1) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) { in0[r] = rz[(r0 + r) * KS + k]; in1[r] = s[(r0 + r) * KS + k]; }
+        } else {
+#pragma unroll
+            for (int r = 0; r < NR; r++) { in0[r] = lam[(r0 + r) * KS + k]; in1[r] = cr[(r0 + r) * KS + k]; in2[r] = rz[(r0 + r) * KS + k]; }
+        }
+    }
+    // LP row: rzv from the loaded inputs (dv = W^-2 of the row)
+    SCPP_HD static double lp_rzv(int mode, double csig, double sigmu, double dv, double i0, double i1, double i2)
+    {
+        if (mode == 0) return i0;
+        if (mode == 1) return -i0 + i1;
+        return -csig * i2 - sqrt(1. / dv) * ((-i0 * i0 - i1 + sigmu) / i0);
+    }
+
     SCPP_HD double pass_rhs(int mode, double csig, double sigmu)   // returns the lane-partial of the sigma right-hand side
     {
         double gsig = 0;
         FOR_LANE(k, K) {
             const bool hasint = k < K - 1;
-            double G[NB];
+            double G[NB], td[3];
+            // ---- block 1 (loads): rxv of xi and delta, the trust-region cone
+            double w[D], q[D], i1[D], i2[D];
 #pragma unroll
             for (int j = 0; j < NB; j++) G[j] = rxv_of(mode, csig, j, k);
+            const double rxd = rxv_of(mode, csig, NB, k);
+            const double e2i = ce[NCONE * KS + k];
+#pragma unroll
+            for (int i = 0; i < D; i++) w[i] = wb[(TRO + i) * KS + k];
+            ld_rhs_rows<D>(mode, TRO, k, q, i1, i2);
+#pragma unroll
+            for (int t = 0; t < 3; t++) td[t] = tdir[3 * k + t];
             // ---- trust region: rzv, then v = M rzv - p (p'rzv + rx_delta)/kap ,  p = M(-e0)
             {
-                double w[D], q[D];
-                const double e2i = ce[NCONE * KS + k];
+                if (mode == 1) {
 #pragma unroll
-                for (int i = 0; i < D; i++) w[i] = wb[(TRO + i) * KS + k];
-                if (mode == 0) {
-#pragma unroll
-                    for (int i = 0; i < D; i++) q[i] = ds[(TRO + i) * KS + k];
-                } else if (mode == 1) {
-#pragma unroll
-                    for (int i = 0; i < D; i++) q[i] = -rz[(TRO + i) * KS + k] + s[(TRO + i) * KS + k];
-                } else {
-                    double lm[D];
+                    for (int i = 0; i < D; i++) q[i] = -q[i] + i1[i];
+                } else if (mode == 2) {      // q = lam, i1 = cr, i2 = rz
                     double ll = 0;
 #pragma unroll
-                    for (int i = 0; i < D; i++) { lm[i] = lam[(TRO + i) * KS + k]; ll += lm[i] * lm[i]; }
-                    const double l0 = lm[0], den = 2. * l0 * l0 - ll;
+                    for (int i = 0; i < D; i++) ll += q[i] * q[i];
+                    const double l0 = q[0], den = 2. * l0 * l0 - ll;
                     double l1d1 = 0;
 #pragma unroll
-                    for (int i = 1; i < D; i++) { const double dv = -2. * l0 * lm[i] - cr[(TRO + i) * KS + k]; q[i] = dv; l1d1 += lm[i] * dv; }
-                    const double dv0 = -ll - cr[TRO * KS + k] + sigmu;
+                    for (int i = 1; i < D; i++) { const double dv = -2. * l0 * q[i] - i1[i]; i1[i] = dv; l1d1 += q[i] * dv; }
+                    const double dv0 = -ll - i1[0] + sigmu;
                     const double x0 = (l0 * dv0 - l1d1) / den, il0 = 1. / l0;
                     double w1v1 = 0;
 #pragma unroll
-                    for (int i = 1; i < D; i++) { q[i] = (q[i] - x0 * lm[i]) * il0; w1v1 += w[i] * q[i]; }
+                    for (int i = 1; i < D; i++) { i1[i] = (i1[i] - x0 * q[i]) * il0; w1v1 += w[i] * i1[i]; }
                     // W (lam \ d_s)
                     const double eta = 1. / sqrt(e2i), f = x0 + w1v1 / (1. + w[0]);
-                    q[0] = -csig * rz[TRO * KS + k] - eta * (w[0] * x0 + w1v1);
+                    q[0] = -csig * i2[0] - eta * (w[0] * x0 + w1v1);
 #pragma unroll
-                    for (int i = 1; i < D; i++) q[i] = -csig * rz[(TRO + i) * KS + k] - eta * (q[i] + f * w[i]);
+                    for (int i = 1; i < D; i++) q[i] = -csig * i2[i] - eta * (i1[i] + f * w[i]);
                 }
                 if (mode != 0) {
 #pragma unroll
@@ -910,80 +1087,103 @@ struct Ipm {
                 double dot = w0 * q[0], prz = -kap * q[0];
 #pragma unroll
                 for (int i = 1; i < D; i++) { dot -= w[i] * q[i]; prz += 2. * e2i * w0 * w[i] * q[i]; }
-                const double rho = (prz + rxv_of(mode, csig, NB, k)) / kap;
+                const double rho = (prz + rxd) / kap;
 #pragma unroll
                 for (int i = 1; i < D; i++) G[i - 1] += e2i * (-2. * dot * w[i] + q[i]) - 2. * e2i * w0 * w[i] * rho;
             }
-            // ---- model cones
+            // ---- block 2: model rows (cones, LP rows)
+            {
+                double W2[NROW], a0[NROW], a1[NROW], a2[NROW], CEv[NCONE];
 #pragma unroll
-            for (int c = 0; c < NCONE; c++) {
-                const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
-                double w[soc::SOC_MAXD], t1[soc::SOC_MAXD];
-                const double e2i = ce[c * KS + k];
+                for (int r = 0; r < NROW; r++) W2[r] = wb[r * KS + k];
 #pragma unroll
-                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) w[r] = wb[(o + r) * KS + k];
-                if (mode == 0) {
+                for (int c = 0; c < NCONE; c++) CEv[c] = ce[c * KS + k];
+                ld_rhs_rows<NROW>(mode, 0, k, a0, a1, a2);
 #pragma unroll
-                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = ds[(o + r) * KS + k];
-                } else if (mode == 1) {
+                for (int c = 0; c < NCONE; c++) {
+                    const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
+                    double wc[soc::SOC_MAXD], t1[soc::SOC_MAXD];
+                    const double e2c = CEv[c];
 #pragma unroll
-                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = -rz[(o + r) * KS + k] + s[(o + r) * KS + k];
-                } else {
-                    double lm[soc::SOC_MAXD];
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) wc[r] = W2[o + r];
+                    if (mode == 0) {
 #pragma unroll
-                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) lm[r] = lam[(o + r) * KS + k];
-                    soc::jprod(lm, lm, d, t1);
+                        for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = a0[o + r];
+                    } else if (mode == 1) {
 #pragma unroll
-                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = -t1[r] - cr[(o + r) * KS + k];
-                    t1[0] += sigmu;
-                    soc::jdiv(lm, t1, d, t1);
-                    soc::Wv(w, e2i, t1, d, t1, false);
+                        for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = -a0[o + r] + a1[o + r];
+                    } else {
+                        double lm[soc::SOC_MAXD];
 #pragma unroll
-                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = -csig * rz[(o + r) * KS + k] - t1[r];
+                        for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) lm[r] = a0[o + r];
+                        soc::jprod(lm, lm, d, t1);
+#pragma unroll
+                        for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = -t1[r] - a1[o + r];
+                        t1[0] += sigmu;
+                        soc::jdiv(lm, t1, d, t1);
+                        soc::Wv(wc, e2c, t1, d, t1, false);
+#pragma unroll
+                        for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) t1[r] = -csig * a2[o + r] - t1[r];
+                    }
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) a0[o + r] = t1[r];          // rzv (kept for the store below)
+                    soc::Mv(wc, e2c, t1, d, t1);
+#pragma unroll
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) row_scatter_reg(o + r, td, t1[r], G);
+                }
+#pragma unroll
+                for (int r = 0; r < NLP; r++) {
+                    const double dv = W2[r];
+                    const double rzv = lp_rzv(mode, csig, sigmu, dv, a0[r], a1[r], a2[r]);
+                    a0[r] = rzv;
+                    row_scatter_reg(r, td, dv * rzv, G);
                 }
                 if (mode != 0) {
 #pragma unroll
-                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) ds[(o + r) * KS + k] = t1[r];
+                    for (int r = 0; r < NROW; r++) ds[r * KS + k] = a0[r];
                 }
-                soc::Mv(w, e2i, t1, d, t1);
-#pragma unroll
-                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) row_scatter(o + r, k, t1[r], G);
             }
-            // ---- LP rows
-#pragma unroll
-            for (int r = 0; r < NLP; r++) {
-                const double dv = wb[r * KS + k];
-                double rzv;
-                if (mode == 0) rzv = ds[r * KS + k];
-                else if (mode == 1) rzv = -rz[r * KS + k] + s[r * KS + k];
-                else { const double lm = lam[r * KS + k]; rzv = -csig * rz[r * KS + k] - sqrt(1. / dv) * ((-lm * lm - cr[r * KS + k] + sigmu) / lm); }
-                if (mode != 0) ds[r * KS + k] = rzv;
-                row_scatter(r, k, dv * rzv, G);
-            }
-            // ---- interval pairs: t eliminated, w_i couples to nodes k and k+1
+            // ---- block 3: interval pairs: t eliminated, w_i couples to nodes k and k+1 (row i+1 is loaded before row i is stored)
             if (hasint) {
-#pragma unroll 2
-                for (int i = 0; i < NX; i++) {
+                constexpr int NR = NB + 1 + 9;       // A~ row | s column | dm dp | rxv | six mode inputs
+                double cur[NR], nxt[NR];
+                auto ld_row = [&](int i, double *row) {
                     const int o = MN + i;
-                    const double dm = wb[o * KS + k], dp = wb[(o + NX) * KS + k];
-                    double rm, rp;
-                    if (mode == 0) { rm = ds[o * KS + k]; rp = ds[(o + NX) * KS + k]; }
-                    else if (mode == 1) { rm = -rz[o * KS + k] + s[o * KS + k]; rp = -rz[(o + NX) * KS + k] + s[(o + NX) * KS + k]; }
+#pragma unroll
+                    for (int j = 0; j < NB; j++) row[j] = T(i, j, k);
+                    row[NB] = T(i, NB + NU, k);
+                    row[NB + 1] = wb[o * KS + k]; row[NB + 2] = wb[(o + NX) * KS + k];
+                    row[NB + 3] = rxv_of(mode, csig, PN + i, k);
+                    if (mode == 0) { row[NB + 4] = ds[o * KS + k]; row[NB + 5] = ds[(o + NX) * KS + k]; }
+                    else if (mode == 1) { row[NB + 4] = rz[o * KS + k]; row[NB + 5] = rz[(o + NX) * KS + k]; row[NB + 6] = s[o * KS + k]; row[NB + 7] = s[(o + NX) * KS + k]; }
                     else {
-                        const double lmm = lam[o * KS + k], lmp = lam[(o + NX) * KS + k];
-                        rm = -csig * rz[o * KS + k] - sqrt(1. / dm) * ((-lmm * lmm - cr[o * KS + k] + sigmu) / lmm);
-                        rp = -csig * rz[(o + NX) * KS + k] - sqrt(1. / dp) * ((-lmp * lmp - cr[(o + NX) * KS + k] + sigmu) / lmp);
+                        row[NB + 4] = lam[o * KS + k]; row[NB + 5] = lam[(o + NX) * KS + k]; row[NB + 6] = cr[o * KS + k]; row[NB + 7] = cr[(o + NX) * KS + k];
+                        row[NB + 8] = rz[o * KS + k]; row[NB + 9] = rz[(o + NX) * KS + k];
                     }
+                };
+                auto do_row = [&](int i, const double *cur) {
+                    const int o = MN + i;
+                    const double dm = cur[NB + 1], dp = cur[NB + 2];
+                    const double rm = lp_rzv(mode, csig, sigmu, dm, cur[NB + 4], cur[NB + 6], cur[NB + 8]);
+                    const double rp = lp_rzv(mode, csig, sigmu, dp, cur[NB + 5], cur[NB + 7], cur[NB + 9]);
                     if (mode != 0) { ds[o * KS + k] = rm; ds[(o + NX) * KS + k] = rp; }
-                    const double rho = (-(dm * rm + dp * rp) + rxv_of(mode, csig, PN + i, k)) / (dm + dp);
+                    const double rho = (-(dm * rm + dp * rp) + cur[NB + 3]) / (dm + dp);
                     const double wi = dm * (rm + rho) - dp * (rp + rho);
                     wv[i * KS + k] = wi;
 #pragma unroll
-                    for (int j = 0; j < NB; j++) G[j] -= T(i, j, k) * wi;
-                    gsig -= T(i, NB + NU, k) * wi;
+                    for (int j = 0; j < NB; j++) G[j] -= cur[j] * wi;
+                    gsig -= cur[NB] * wi;
+                };
+                ld_row(0, cur);
+#pragma unroll 1
+                for (int i = 0; i < NX; i += 2) {
+                    ld_row(i + 1, nxt);
+                    do_row(i, cur);
+                    if (i + 2 < NX) ld_row(i + 2, cur);
+                    do_row(i + 1, nxt);
                 }
             } else if (mode != 0) {
-#pragma unroll 2
+#pragma unroll
                 for (int i = 0; i < NX; i++) { ds[(MN + i) * KS + k] = 0.; ds[(MN + NX + i) * KS + k] = 0.; }
             }
 #pragma unroll
@@ -993,62 +1193,77 @@ struct Ipm {
         // ---- coupling from interval k-1 and the pinned variables
         FOR_LANE(k, K) {
             const uint32_t mk = fixm[k];
-            double C[NU];
+            double g[NB];
 #pragma unroll
-            for (int a = 0; a < NU; a++) C[a] = 0.;
+            for (int j = 0; j < NB; j++) g[j] = gv[j * KS + k];
             if (k > 0) {
+                double wp[NX], Cc[NX][NU];
 #pragma unroll
                 for (int i = 0; i < NX; i++) {
-                    const double wp = wv[i * KS + k - 1];
-                    gv[i * KS + k] = ((mk >> i) & 1u) ? 0. : gv[i * KS + k] + wp;
+                    wp[i] = wv[i * KS + k - 1];
 #pragma unroll
-                    for (int a = 0; a < NU; a++) C[a] -= T(i, NB + a, k - 1) * wp;
+                    for (int a = 0; a < NU; a++) Cc[i][a] = T(i, NB + a, k - 1);
                 }
-            } else {
 #pragma unroll
-                for (int i = 0; i < NX; i++) if ((mk >> i) & 1u) gv[i * KS + k] = 0.;
+                for (int i = 0; i < NX; i++) {
+                    g[i] += wp[i];
+#pragma unroll
+                    for (int a = 0; a < NU; a++) g[NX + a] -= Cc[i][a] * wp[i];
+                }
             }
 #pragma unroll
-            for (int a = 0; a < NU; a++) gv[(NX + a) * KS + k] = ((mk >> (NX + a)) & 1u) ? 0. : gv[(NX + a) * KS + k] + C[a];
+            for (int j = 0; j < NB; j++) gv[j * KS + k] = ((mk >> j) & 1u) ? 0. : g[j];
         }
         warp_sync();
         return gsig;
     }
 
     // forward substitution  f_k = Linv_k (g_k - L_{k,k-1} f_{k-1})  in place in gv ; returns the lane-partial of  sum_k l_k' f_k
+    // Both substitutions keep THREE factor records in flight (prefetch distance 2: a stage is ~300 cycles of dependent
+    // arithmetic, a DRAM round trip ~800) and read the right-hand side two stages ahead into registers.
+    // Forward: stage k needs only its own record because the coupling term L_{k+1,k} f_k is formed at the end of stage k.
+    SCPP_HD void ld_col(double *dst, const double *src) const   // one stage column of a stage-minor [NB][KS] array: NB 8-byte asynchronous copies
+    {
+#if defined(__CUDA_ARCH__)
+        const int j = lane_id();
+        if (j < NB) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + j)), "l"(src + (size_t)j * KS) : "memory");
+#else
+        for (int j = 0; j < NB; j++) dst[j] = src[(size_t)j * KS];
+#endif
+    }
     SCPP_HD double chain_forward()
     {
-        double *fprev = vec(0), *tmp = vec(1);
+        double *fcur = vec(0), *tmp = vec(1);
         double ldot = 0;
-        ld(fbuf(0), fac, FS); ld_commit();
+        // group of record r carries the right-hand side of stage r+1 (needed at the end of stage r)
+        ld(fbuf(0), fac, FS); if (K > 1) ld_col(vec(2 + 1 % 3), gv + 1); ld_commit();
+        if (K > 1) { ld(fbuf(1), fac + FS, FS); if (K > 2) ld_col(vec(2 + 2 % 3), gv + 2); }
+        ld_commit();
+        FOR_LANE(jj, NB) tmp[jj] = gv[jj * KS];
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
-            if (k + 1 < K) ld(fbuf((k + 1) % 3), fac + (size_t)(k + 1) * FS, FS);
+            if (k + 2 < K) { ld(fbuf((k + 2) % 3), fac + (size_t)(k + 2) * FS, FS); if (k + 3 < K) ld_col(vec(2 + (k + 3) % 3), gv + k + 3); }
             ld_commit();
-            const int j = lane_id();
-            double g = 0.;
-            if (LANES > 1 && j < NB) g = gv[j * KS + k];
-            ld_wait(1);
-            const double *F = fbuf(k % 3), *Lp = fbuf((k + 2) % 3) + OFF_LN;     // L_{k,k-1} sits in the record of stage k-1
-            FOR_LANE(jj, NB) {
-                double v = (LANES > 1) ? g : gv[jj * KS + k];
-                if (k > 0) {
-                    double v2 = 0;
-#pragma unroll
-                    for (int c = 0; c < NB; c += 2) { v -= Lp[jj * NB + c] * fprev[c]; v2 -= Lp[jj * NB + c + 1] * fprev[c + 1]; }
-                    v += v2;
-                }
-                tmp[jj] = v;
-            }
-            warp_sync();
+            ld_wait(2);
+            const double *F = fbuf(k % 3), *Ln = F + OFF_LN, *gn = vec(2 + (k + 1) % 3);
             FOR_LANE(jj, NB) {
                 double v = 0, v2 = 0;
 #pragma unroll
                 for (int c = 0; c < NB; c += 2) { v += F[jj * NB + c] * tmp[c]; v2 += F[jj * NB + c + 1] * tmp[c + 1]; }
                 v += v2;
-                fprev[jj] = v;
+                fcur[jj] = v;
                 gv[jj * KS + k] = v;
                 ldot += F[OFF_L + jj] * v;
+            }
+            warp_sync();
+            if (k + 1 < K) {
+                FOR_LANE(jj, NB) {
+                    double v = gn[jj], v2 = 0;
+#pragma unroll
+                    for (int c = 0; c < NB; c += 2) { v -= Ln[jj * NB + c] * fcur[c]; v2 -= Ln[jj * NB + c + 1] * fcur[c + 1]; }
+                    v += v2;
+                    tmp[jj] = v;
+                }
             }
             warp_sync();
         }
@@ -1059,20 +1274,19 @@ struct Ipm {
     SCPP_HD void chain_backward(double ysig)
     {
         double *ynext = vec(0), *tmp = vec(1);
-        ld(fbuf((K - 1) % 3), fac + (size_t)(K - 1) * FS, FS); ld_commit();
+        ld(fbuf((K - 1) % 3), fac + (size_t)(K - 1) * FS, FS); ld_col(vec(2 + (K - 1) % 3), gv + K - 1); ld_commit();
+        if (K > 1) { ld(fbuf((K - 2) % 3), fac + (size_t)(K - 2) * FS, FS); ld_col(vec(2 + (K - 2) % 3), gv + K - 2); }
+        ld_commit();
 #pragma unroll 1
         for (int k = K - 1; k >= 0; k--) {
             const bool hasint = k < K - 1;
-            if (k > 0) ld(fbuf((k - 1) % 3), fac + (size_t)(k - 1) * FS, FS);
+            if (k >= 2) { ld(fbuf((k - 2) % 3), fac + (size_t)(k - 2) * FS, FS); ld_col(vec(2 + (k - 2) % 3), gv + k - 2); }
             ld_commit();
-            const int j = lane_id();
-            double f = 0.;
-            if (LANES > 1 && j < NB) f = gv[j * KS + k];
             const uint32_t mk = fixm[k];
-            ld_wait(1);
-            const double *F = fbuf(k % 3);
+            ld_wait(2);
+            const double *F = fbuf(k % 3), *fk = vec(2 + k % 3);
             FOR_LANE(jj, NB) {
-                double v = ((LANES > 1) ? f : gv[jj * KS + k]) - F[OFF_L + jj] * ysig;
+                double v = fk[jj] - F[OFF_L + jj] * ysig;
                 if (hasint) {
                     double v2 = 0;
 #pragma unroll
@@ -1101,21 +1315,31 @@ struct Ipm {
         double tmax = 0;
         FOR_LANE(k, K) {
             const bool hasint = k < K - 1;
-            double yk[NB];
+            double yk[NB], td[3];
+            // ---- block 1 (loads): the solution of the stage, the trust-region cone
+            double w[D], q[D], RZ[D], LM[D];
 #pragma unroll
-            for (int j = 0; j < NB; j++) { yk[j] = gv[j * KS + k]; dprim[j * KS + k] = yk[j]; }
+            for (int j = 0; j < NB; j++) yk[j] = gv[j * KS + k];
+            const double e2i = ce[NCONE * KS + k];
+            const double rxd = rxv_of(mode, csig, NB, k);
+#pragma unroll
+            for (int i = 0; i < D; i++) { w[i] = wb[(TRO + i) * KS + k]; q[i] = ds[(TRO + i) * KS + k]; }
+            if (mode != 0) {
+#pragma unroll
+                for (int i = 0; i < D; i++) { RZ[i] = rz[(TRO + i) * KS + k]; LM[i] = lam[(TRO + i) * KS + k]; }
+            }
+#pragma unroll
+            for (int t = 0; t < 3; t++) td[t] = tdir[3 * k + t];
+#pragma unroll
+            for (int j = 0; j < NB; j++) dprim[j * KS + k] = yk[j];
             // ---- trust region
             {
-                double w[D], q[D];
-                const double e2i = ce[NCONE * KS + k];
-#pragma unroll
-                for (int i = 0; i < D; i++) w[i] = wb[(TRO + i) * KS + k];
                 const double w0 = w[0], kap = e2i * (2. * w0 * w0 - 1.);
-                q[0] = -ds[TRO * KS + k];
+                q[0] = -q[0];
                 double pq = -kap * q[0], dot = w0 * q[0];
 #pragma unroll
-                for (int i = 1; i < D; i++) { q[i] = yk[i - 1] - ds[(TRO + i) * KS + k]; pq += 2. * e2i * w0 * w[i] * q[i]; dot -= w[i] * q[i]; }
-                const double ddl = (rxv_of(mode, csig, NB, k) - pq) / kap;
+                for (int i = 1; i < D; i++) { q[i] = yk[i - 1] - q[i]; pq += 2. * e2i * w0 * w[i] * q[i]; dot -= w[i] * q[i]; }
+                const double ddl = (rxd - pq) / kap;
                 dprim[NB * KS + k] = ddl;
                 // dz = M q + p ddl   (in q)
                 q[0] = e2i * (2. * dot * w0 - q[0]) - kap * ddl;
@@ -1125,10 +1349,10 @@ struct Ipm {
                 for (int i = 0; i < D; i++) dz[(TRO + i) * KS + k] = q[i];
                 if (mode != 0) {
                     double dsv[D];
-                    dsv[0] = rzs * rz[TRO * KS + k] + ddl;
+                    dsv[0] = rzs * RZ[0] + ddl;
                     double w1z = 0, w1s = 0;
 #pragma unroll
-                    for (int i = 1; i < D; i++) { dsv[i] = rzs * rz[(TRO + i) * KS + k] - yk[i - 1]; w1z += w[i] * q[i]; w1s += w[i] * dsv[i]; }
+                    for (int i = 1; i < D; i++) { dsv[i] = rzs * RZ[i] - yk[i - 1]; w1z += w[i] * q[i]; w1s += w[i] * dsv[i]; }
 #pragma unroll
                     for (int i = 0; i < D; i++) ds[(TRO + i) * KS + k] = dsv[i];
                     // scaled directions  dz~ = W dz (in q),  ds~ = W^-1 ds (in dsv)
@@ -1136,14 +1360,13 @@ struct Ipm {
                     const double fz = q[0] + w1z / (1. + w0), fs = -dsv[0] + w1s / (1. + w0);
                     const double z0 = eta * (w0 * q[0] + w1z), s0 = ieta * (w0 * dsv[0] - w1s);
                     double l1 = 0, a1 = 0, a2 = 0, cr0 = s0 * z0;
-                    const double lm0 = lam[TRO * KS + k];
+                    const double lm0 = LM[0];
 #pragma unroll
                     for (int i = 1; i < D; i++) {
-                        const double lmi = lam[(TRO + i) * KS + k];
+                        const double lmi = LM[i];
                         q[i] = eta * (q[i] + fz * w[i]); dsv[i] = ieta * (dsv[i] + fs * w[i]);
                         l1 += lmi * lmi; a1 += lmi * dsv[i]; a2 += lmi * q[i];
                         cr0 += dsv[i] * q[i];
-                        w[i] = lmi;                                         // w is free from here on: keep lam
                     }
                     const double ia = 1. / sqrt(lm0 * lm0 - l1), l0 = lm0 * ia;
                     const double ld1 = l0 * s0 - a1 * ia, ld2 = l0 * z0 - a2 * ia;
@@ -1151,7 +1374,7 @@ struct Ipm {
                     const double f1 = (ld1 + s0) * il, f2 = (ld2 + z0) * il;
                     double n1 = 0, n2 = 0;
 #pragma unroll
-                    for (int i = 1; i < D; i++) { const double r1 = dsv[i] - f1 * w[i], r2 = q[i] - f2 * w[i]; n1 += r1 * r1; n2 += r2 * r2; }
+                    for (int i = 1; i < D; i++) { const double r1 = dsv[i] - f1 * LM[i], r2 = q[i] - f2 * LM[i]; n1 += r1 * r1; n2 += r2 * r2; }
                     tmax = fmax(tmax, fmax((sqrt(n1) - ld1) * ia, (sqrt(n2) - ld2) * ia));
                     if (mode == 1) {
                         cr[TRO * KS + k] = cr0;
@@ -1160,92 +1383,133 @@ struct Ipm {
                     }
                 }
             }
-            // ---- model cones
+            // ---- block 2: model rows (cones, LP rows): DZ, DS, CR are stored at the end of the block
+            {
+                double W2[NROW], D2[NROW], R2[NROW], L2[NROW], CEv[NCONE], DZ[NROW], CRv[NROW];
 #pragma unroll
-            for (int c = 0; c < NCONE; c++) {
-                const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
-                double w[soc::SOC_MAXD], q[soc::SOC_MAXD], gdx[soc::SOC_MAXD], lm[soc::SOC_MAXD];
-                const double e2i = ce[c * KS + k];
+                for (int r = 0; r < NROW; r++) { W2[r] = wb[r * KS + k]; D2[r] = ds[r * KS + k]; }
 #pragma unroll
-                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) {
-                    w[r] = wb[(o + r) * KS + k];
-                    gdx[r] = row_dot(o + r, k, gv);
-                    q[r] = gdx[r] - ds[(o + r) * KS + k];
-                }
-                soc::Mv(w, e2i, q, d, q);                                   // dz
-#pragma unroll
-                for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) dz[(o + r) * KS + k] = q[r];
+                for (int c = 0; c < NCONE; c++) CEv[c] = ce[c * KS + k];
                 if (mode != 0) {
+#pragma unroll
+                    for (int r = 0; r < NROW; r++) { R2[r] = rz[r * KS + k]; L2[r] = lam[r * KS + k]; }
+                }
+#pragma unroll
+                for (int c = 0; c < NCONE; c++) {
+                    const int o = NLP + M::cone_off(c), d = M::cone_dim(c);
+                    double wc[soc::SOC_MAXD], qc[soc::SOC_MAXD], gdx[soc::SOC_MAXD], lm[soc::SOC_MAXD];
+                    const double e2c = CEv[c];
 #pragma unroll
                     for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) {
-                        gdx[r] = rzs * rz[(o + r) * KS + k] - gdx[r];       // ds
-                        ds[(o + r) * KS + k] = gdx[r];
-                        lm[r] = lam[(o + r) * KS + k];
+                        wc[r] = W2[o + r];
+                        gdx[r] = row_dot_reg(o + r, td, yk);
+                        qc[r] = gdx[r] - D2[o + r];
                     }
-                    soc::Wv(w, e2i, q, d, q, false);                        // dz~
-                    soc::Wv(w, e2i, gdx, d, gdx, true);                     // ds~
-                    tmax = fmax(tmax, fmax(soc::step(lm, gdx, d), soc::step(lm, q, d)));
-                    if (mode == 1) {
-                        soc::jprod(gdx, q, d, q);
+                    soc::Mv(wc, e2c, qc, d, qc);                                   // dz
 #pragma unroll
-                        for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) cr[(o + r) * KS + k] = q[r];
+                    for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) DZ[o + r] = qc[r];
+                    if (mode != 0) {
+#pragma unroll
+                        for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) {
+                            gdx[r] = rzs * R2[o + r] - gdx[r];                     // ds
+                            D2[o + r] = gdx[r];
+                            lm[r] = L2[o + r];
+                        }
+                        soc::Wv(wc, e2c, qc, d, qc, false);                        // dz~
+                        soc::Wv(wc, e2c, gdx, d, gdx, true);                       // ds~
+                        tmax = fmax(tmax, fmax(soc::step(lm, gdx, d), soc::step(lm, qc, d)));
+                        if (mode == 1) {
+                            soc::jprod(gdx, qc, d, qc);
+#pragma unroll
+                            for (int r = 0; r < soc::SOC_MAXD; r++) if (r < d) CRv[o + r] = qc[r];
+                        }
                     }
                 }
-            }
-            // ---- LP rows
 #pragma unroll
-            for (int r = 0; r < NLP; r++) {
-                const double gdx = row_dot(r, k, gv), dv = wb[r * KS + k];
-                const double dzv = dv * (gdx - ds[r * KS + k]);
-                dz[r * KS + k] = dzv;
+                for (int r = 0; r < NLP; r++) {
+                    const double gdx = row_dot_reg(r, td, yk), dv = W2[r];
+                    const double dzv = dv * (gdx - D2[r]);
+                    DZ[r] = dzv;
+                    if (mode != 0) {
+                        const double dsv = rzs * R2[r] - gdx;
+                        D2[r] = dsv;
+                        const double iw = sqrt(dv), il = 1. / L2[r];                // W = 1/sqrt(wb)
+                        const double dzt = dzv / iw, dst = dsv * iw;
+                        tmax = fmax(tmax, fmax(-dst, -dzt) * il);
+                        if (mode == 1) CRv[r] = dst * dzt;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < NROW; r++) dz[r * KS + k] = DZ[r];
                 if (mode != 0) {
-                    const double dsv = rzs * rz[r * KS + k] - gdx;
-                    ds[r * KS + k] = dsv;
-                    const double iw = sqrt(dv), il = 1. / lam[r * KS + k];       // W = 1/sqrt(wb)
-                    const double dzt = dzv / iw, dst = dsv * iw;
-                    tmax = fmax(tmax, fmax(-dst, -dzt) * il);
-                    if (mode == 1) cr[r * KS + k] = dst * dzt;
+#pragma unroll
+                    for (int r = 0; r < NROW; r++) ds[r * KS + k] = D2[r];
+                    if (mode == 1) {
+#pragma unroll
+                        for (int r = 0; r < NROW; r++) cr[r * KS + k] = CRv[r];
+                    }
                 }
             }
-            // ---- interval pairs
+            // ---- block 3: interval pairs (row i+1 is loaded before row i is stored)
             if (hasint) {
-                double XNu[NU];
+                constexpr int NT = NB + NU + 1, NR = NT + 10;   // A~ | C | s column ; x_{k+1,i} dm dp dsm dsp rxv | rz- rz+ lam- lam+
+                double XNu[NU], cur[NR], nxt[NR];
 #pragma unroll
                 for (int a = 0; a < NU; a++) XNu[a] = gv[(NX + a) * KS + k + 1];
-#pragma unroll 2
-                for (int i = 0; i < NX; i++) {
+                auto ld_row = [&](int i, double *row) {
                     const int o = MN + i;
-                    double acc = gv[i * KS + k + 1], acc2 = 0;
 #pragma unroll
-                    for (int j = 0; j < NB; j += 2) { acc -= T(i, j, k) * yk[j]; acc2 -= T(i, j + 1, k) * yk[j + 1]; }
+                    for (int j = 0; j < NT; j++) row[j] = T(i, j, k);
+                    row[NT] = gv[i * KS + k + 1];
+                    row[NT + 1] = wb[o * KS + k]; row[NT + 2] = wb[(o + NX) * KS + k];
+                    row[NT + 3] = ds[o * KS + k]; row[NT + 4] = ds[(o + NX) * KS + k];
+                    row[NT + 5] = rxv_of(mode, csig, PN + i, k);
+                    if (mode != 0) {
+                        row[NT + 6] = rz[o * KS + k]; row[NT + 7] = rz[(o + NX) * KS + k];
+                        row[NT + 8] = lam[o * KS + k]; row[NT + 9] = lam[(o + NX) * KS + k];
+                    }
+                };
+                auto do_row = [&](int i, const double *cur) {
+                    const int o = MN + i;
+                    double acc = cur[NT], acc2 = 0;
 #pragma unroll
-                    for (int a = 0; a < NU; a++) acc2 -= T(i, NB + a, k) * XNu[a];
-                    const double ady = acc + acc2 - T(i, NB + NU, k) * ysig;
-                    const double dm = wb[o * KS + k], dp = wb[(o + NX) * KS + k];
-                    const double qm = ady - ds[o * KS + k], qp = -ady - ds[(o + NX) * KS + k];
-                    const double dt = (rxv_of(mode, csig, PN + i, k) + dm * qm + dp * qp) / (dm + dp);
+                    for (int j = 0; j < NB; j += 2) { acc -= cur[j] * yk[j]; acc2 -= cur[j + 1] * yk[j + 1]; }
+#pragma unroll
+                    for (int a = 0; a < NU; a++) acc2 -= cur[NB + a] * XNu[a];
+                    const double ady = acc + acc2 - cur[NB + NU] * ysig;
+                    const double dm = cur[NT + 1], dp = cur[NT + 2];
+                    const double qm = ady - cur[NT + 3], qp = -ady - cur[NT + 4];
+                    const double dt = (cur[NT + 5] + dm * qm + dp * qp) / (dm + dp);
                     const double dzm = dm * (qm - dt), dzp = dp * (qp - dt);
                     dz[o * KS + k] = dzm; dz[(o + NX) * KS + k] = dzp;
                     dprim[(PN + i) * KS + k] = dt;
                     if (mode != 0) {
-                        const double dsm = rzs * rz[o * KS + k] - (ady - dt), dsp = rzs * rz[(o + NX) * KS + k] - (-ady - dt);
+                        const double dsm = rzs * cur[NT + 6] - (ady - dt), dsp = rzs * cur[NT + 7] - (-ady - dt);
                         ds[o * KS + k] = dsm; ds[(o + NX) * KS + k] = dsp;
                         {
-                            const double iw = sqrt(dm), il = 1. / lam[o * KS + k];
+                            const double iw = sqrt(dm), il = 1. / cur[NT + 8];
                             const double dzt = dzm / iw, dst = dsm * iw;
                             tmax = fmax(tmax, fmax(-dst, -dzt) * il);
                             if (mode == 1) cr[o * KS + k] = dst * dzt;
                         }
                         {
-                            const double iw = sqrt(dp), il = 1. / lam[(o + NX) * KS + k];
+                            const double iw = sqrt(dp), il = 1. / cur[NT + 9];
                             const double dzt = dzp / iw, dst = dsp * iw;
                             tmax = fmax(tmax, fmax(-dst, -dzt) * il);
                             if (mode == 1) cr[(o + NX) * KS + k] = dst * dzt;
                         }
                     }
+                };
+                ld_row(0, cur);
+#pragma unroll 1
+                for (int i = 0; i < NX; i += 2) {
+                    ld_row(i + 1, nxt);
+                    do_row(i, cur);
+                    if (i + 2 < NX) ld_row(i + 2, cur);
+                    do_row(i + 1, nxt);
                 }
             } else {
-#pragma unroll 2
+#pragma unroll
                 for (int i = 0; i < NX; i++) {
                     const int o = MN + i;
                     dprim[(PN + i) * KS + k] = 0.; dz[o * KS + k] = 0.; dz[(o + NX) * KS + k] = 0.;
