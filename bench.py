@@ -198,13 +198,14 @@ def main():
     if rank == 0:
         sampler.start()
     sync_all()
-    dev_ms, disc_ms, socp_ms, launches, inst_iters, outer = [], 0.0, 0.0, 0, 0, 0
+    dev_ms, disc_ms, socp_ms, launches, inst_iters, outer, rounds, inst_rounds = [], 0.0, 0.0, 0, 0, 0, 0, 0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         eng.solve()
         t = eng.last_timing()
         dev_ms.append(t["ms_total"]); disc_ms += t["ms_discretize"]; socp_ms += t["ms_socp"]
         launches += t["kernel_launches"]; inst_iters += t["instance_iterations"]; outer += t["outer_iterations"]
+        r = eng.last_rounds(); rounds += r["rounds"]; inst_rounds += r["instance_rounds"]
     sync_all()
     wall_dev = time.perf_counter() - t_wall0
     # ---- end-to-end through the public API with host buffers
@@ -234,13 +235,16 @@ def main():
         peaks, peak_kind = measured_peaks()
         value = sums[0] / (stats[0] * 1e-3)
         e2e_value = sums[1] / stats[1]
-        # roofline of the dominant kernel (k_solve): algorithmic bytes per launch / mean launch duration (rank 0's launches)
-        socp_launches = max(1, outer)
+        # roofline of the dominant kernel (k_solve; one launch = one ROUND = one interior-point iteration of every unfinished
+        # instance): algorithmic bytes of the instance-iterations finished in the timed region, spread over its launches, divided
+        # by the mean launch duration (CUDA events on the engine stream, rank 0's launches)
+        socp_launches = max(1, rounds)
         bytes_per_launch = algorithmic_bytes(args.K, "k_solve") * (inst_iters / socp_launches)
         ach = bytes_per_launch / (socp_ms / socp_launches * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "k_solve", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                 "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "algorithmic_bytes_per_instance_iteration": algorithmic_bytes(args.K, "k_solve"),
+                "launches_per_step": socp_launches / args.steps, "ms_per_launch": socp_ms / socp_launches,
                 "share_of_step": socp_ms / max(1e-9, float(np.sum(dev_ms)))}
         whole = algorithmic_bytes(args.K, "all") * inst_iters / (float(np.sum(dev_ms)) * 1e-3) / 1e9
         roof_it = {"bound": "hbm", "scope": "k_discretize + k_solve (whole iteration, SURVEY §8d: 285024 B at K=50)", "achieved": whole,
@@ -249,9 +253,11 @@ def main():
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            if tj.get("K") == args.K:      # ncu dram bytes per instance-iteration x instances of one launch (capture named in the file)
-                roof["traffic"] = tj["dram_bytes_per_instance_iteration"] * (inst_iters / socp_launches)
-                roof["traffic_source"] = "profiles/k_solve_traffic.json (ncu dram__bytes, per launch)"
+            if tj.get("K") == args.K:      # ncu dram bytes of one launch per instance it advanced x mean instances per launch here
+                roof["traffic"] = tj["dram_bytes_per_instance_round"] * (inst_rounds / socp_launches)
+                roof["traffic_gbs"] = roof["traffic"] / (socp_ms / socp_launches * 1e-3) / 1e9
+                roof["traffic_frac_of_peak"] = roof["traffic_gbs"] / peaks["hbm_gbs"]
+                roof["traffic_source"] = "profiles/k_solve_traffic.json (ncu dram__bytes_read+write of one full-batch launch)"
         prof = os.path.join(ROOT, "profiles", "fp64_peak.json")
         fp64 = None
         if os.path.exists(prof):

@@ -122,6 +122,9 @@ int scpp_b200_get_info(scpp_b200_engine *e, double *info /* [N][max_iterations][
  * outer iterations executed, sum over instances of iterations executed */
 int scpp_b200_last_timing(scpp_b200_engine *e, double *ms_discretize, double *ms_socp, double *ms_total,
                           int *kernel_launches, int *outer_iterations, long long *instance_iterations);
+/* rounds of the last solve (one K2 launch, or one split-pipeline kernel sequence, each) and the sum over the rounds of the
+ * instances they advanced */
+int scpp_b200_last_rounds(scpp_b200_engine *e, int *rounds, long long *instance_rounds);
 size_t scpp_b200_device_bytes(scpp_b200_engine *e);
 
 /* ---- test hooks on the two hot paths ----------------------------------------------------------------------------

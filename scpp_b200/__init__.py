@@ -222,6 +222,11 @@ class SCAlgorithm:
         return dict(ms_discretize=a.value, ms_socp=b.value, ms_total=c.value, kernel_launches=l.value, outer_iterations=o.value,
                     instance_iterations=ii.value)
 
+    def last_rounds(self):
+        r, ir = C.c_int(), C.c_longlong()
+        _check(lib().scpp_b200_last_rounds(self._h, C.byref(r), C.byref(ir)))
+        return dict(rounds=r.value, instance_rounds=ir.value)
+
     def device_bytes(self):
         return lib().scpp_b200_device_bytes(self._h)
 

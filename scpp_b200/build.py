@@ -1,11 +1,16 @@
-"""Builds scpp_b200/libscpp_b200.so (CUDA, sm_100a) in-tree with nvcc.  No JIT cache: the .so travels with the repo snapshot."""
+"""Builds scpp_b200/libscpp_b200.so (CUDA, sm_100a) in-tree with nvcc.  No JIT cache: the .so travels with the repo snapshot.
+The heavy kernels are explicit instantiations compiled as separate translation units in parallel (csrc/kernels_inst.cu)."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "libscpp_b200.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+GROUPS = [(m, g) for m in (0, 1) for g in range(5)]
 
 
 def needs_build():
@@ -20,11 +25,25 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", OUT, os.path.join(SRC, "engine.cu"), "-ldl"]
-    if verbose:
-        cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    jobs = [([nvcc] + ARCH + extra + ["-c", os.path.join(SRC, "engine.cu"), "-o", os.path.join(OBJ, "engine.o")], "engine")]
+    for m, g in GROUPS:
+        jobs.append(([nvcc] + ARCH + extra + [f"-DSCPP_KERNEL_MODEL={m}", f"-DSCPP_KERNEL_GROUP={g}", "-c", os.path.join(SRC, "kernels_inst.cu"),
+                                              "-o", os.path.join(OBJ, f"k_{m}_{g}.o")], f"kernels model {m} group {g}"))
+
+    def run(job):
+        cmd, name = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(f"== {name}\n{r.stdout}{r.stderr}")
+        if r.returncode:
+            raise RuntimeError(f"nvcc failed: {name}")
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        list(ex.map(run, jobs))
+    objs = [os.path.join(OBJ, "engine.o")] + [os.path.join(OBJ, f"k_{m}_{g}.o") for m, g in GROUPS]
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + ["-ldl"])
     return OUT
 
 

@@ -25,7 +25,6 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) return fail(SCPP_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-constexpr int WPB_MAX = 7;   // warps (= problem instances) per CTA of the SOCP kernel (chosen per launch, see solve())
 
 // ------------------------------------------------------------------------------------------------------------------
 // kernels
@@ -67,32 +66,7 @@ __global__ void k_warm(ScArrays<M> a, ModelParamsHost P, ScConfig cfg)
     }
 }
 
-// K1: one thread per (active instance, interval, column)
-template <class M>
-__global__ void __launch_bounds__(128) k_discretize(ScArrays<M> a, int nsub, int free_time, const int *__restrict__ active, int n_active)
-{
-    constexpr int NX = M::NX, NU = M::NU, NC = NX + 2 * NU + 2;
-    const int per = (a.K - 1) * NC;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)n_active * per) return;
-    const int ai = int(idx / per), rem = int(idx - (long long)ai * per);
-    const int k = rem / NC, c = rem - k * NC;
-    const int n = active ? active[ai] : ai;
-    discretize_column<M>(a.X + (size_t)n * a.K * NX, a.U + (size_t)n * a.K * NU, a.sigma[n], a.par + (size_t)n * M::NP,
-                         a.K, k, c, nsub, free_time, a.dd + ((size_t)n * (a.K - 1) + k) * NX * NC,
-                         a.ddT ? a.ddT + (size_t)n * Ipm<M>::ddt_doubles(a.K) : nullptr, Ipm<M>::ks(a.K));
-}
-
-// K2 (+K3 epilogue): one warp per active instance
-template <class M, int MAXW, int MINB>
-__global__ void __launch_bounds__(MAXW * 32, MINB) k_solve(ScArrays<M> a, ScConfig cfg, const int *__restrict__ active, int n_active)
-{
-    extern __shared__ __align__(16) double smem[];
-    const int warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (gw >= n_active) return;
-    sc_solve_instance<M>(a, cfg, active[gw], smem + (size_t)warp * Ipm<M>::sm_doubles());
-}
+#include "kernels.cuh"
 
 __global__ void k_iota(int *v, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) v[i] = i; }
 
@@ -215,7 +189,7 @@ struct scpp_b200_engine {
     ScConfig cfg;
     double ms_disc = 0, ms_socp = 0, ms_total = 0;
     int launches = 0, outer = 0, rounds = 0;
-    long long inst_iters = 0, global_active = 0;
+    long long inst_iters = 0, global_active = 0, inst_rounds = 0;
     size_t bytes = 0;
     void *comm = nullptr;
     int nranks = 1, rank = 0;
@@ -286,6 +260,13 @@ struct EngineT : scpp_b200_engine {
         CU(cudaMallocHost((void **)&h_gcount, sizeof(unsigned long long)));
         CU(cudaFuncSetAttribute(k_solve<M, WPB_MAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WPB_MAX * Ipm<M>::sm_doubles() * sizeof(double))));
         CU(cudaFuncSetAttribute(k_solve<M, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(4 * Ipm<M>::sm_doubles() * sizeof(double))));
+        {
+            const int wsm = int(WPB_MAX * Ipm<M>::sm_doubles() * sizeof(double));
+            CU(cudaFuncSetAttribute(k_sp_warp<M, SP_START, WPB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsm));
+            CU(cudaFuncSetAttribute(k_sp_warp<M, SP_FACTOR, WPB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsm));
+            CU(cudaFuncSetAttribute(k_sp_warp<M, SP_CHAIN, WPB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsm));
+            CU(cudaFuncSetAttribute(k_sp_assemble<M, WPB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WPB_MAX * Ipm<M>::asm_doubles() * sizeof(double))));
+        }
         CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
         CU(cudaStreamSynchronize(stream));
         return 0;
@@ -305,7 +286,7 @@ struct EngineT : scpp_b200_engine {
         if (warm && !solved_once) return fail(SCPP_B200_ERR_ARG, "scpp_b200_solve: warm start requested before any solve");
         CU(cudaSetDevice(device));
         const int K = cfg.K, T = 128;
-        launches = 0; outer = 0; ms_disc = ms_socp = 0; inst_iters = 0; rounds = 0;
+        launches = 0; outer = 0; ms_disc = ms_socp = 0; inst_iters = 0; rounds = 0; inst_rounds = 0;
         CU(cudaEventRecord(ev[0], stream));
         if (warm) k_warm<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg);
         else k_setup<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg);
@@ -319,7 +300,8 @@ struct EngineT : scpp_b200_engine {
         // instance by one slice of cfg.ipm_slice interior-point iterations (K2; K3 runs in its epilogue when a sub-problem is
         // solved), (3) re-forms the lists and exchanges the flag bytes.  With ipm_slice == 0 a slice is a whole sub-problem and
         // the rounds are the reference's outer iterations in lock-step.
-        const long long max_rounds = (long long)cfg.max_iterations * (cfg.ipm_slice > 0 ? (cfg.ipm.maxit + 3) / cfg.ipm_slice + 2 : 1) + 1;
+        const int slice_eff = cfg.ipm_slice < 0 ? 1 : cfg.ipm_slice;
+        const long long max_rounds = (long long)cfg.max_iterations * (slice_eff > 0 ? (cfg.ipm.maxit + 3) / slice_eff + 2 : 1) + 1;
         for (long long round = 0; round < max_rounds && global_active > 0; round++) {
             CU(cudaEventRecord(ev[1], stream));
             if (n_disc > 0) {
@@ -328,6 +310,38 @@ struct EngineT : scpp_b200_engine {
                 launches++;
             }
             CU(cudaEventRecord(ev[2], stream));
+            const int n_active_round = n_active;
+            const int parts = (K + 31) / 32;
+            const bool split = cfg.ipm_slice < 0 && parts <= 4;
+            if (split) {
+                // split pipeline: one interior-point iteration of every unfinished instance as a sequence of kernels (sc.cuh)
+                auto warp_launch = [&](auto kern, const int *list, int n, int mode) {
+                    int wpb = (n + n_sm - 1) / n_sm;
+                    if (wpb < 1) wpb = 1;
+                    if (wpb > WPB_MAX) wpb = WPB_MAX;
+                    kern<<<(n + wpb - 1) / wpb, wpb * 32, (size_t)wpb * Ipm<M>::sm_doubles() * sizeof(double), stream>>>(a, cfg, list, nullptr, n, mode);
+                    launches++;
+                };
+                if (n_disc > 0) warp_launch(k_sp_warp<M, SP_START, WPB_MAX>, disc_list, n_disc, 0);
+                if (n_active > 0) {
+                    const int *lst = active[cur];
+                    const long long aw = (long long)n_active * K;
+                    k_sp_assemble<M, WPB_MAX><<<(unsigned)((aw + WPB_MAX - 1) / WPB_MAX), WPB_MAX * 32,
+                                                (size_t)WPB_MAX * Ipm<M>::asm_doubles() * sizeof(double), stream>>>(a, cfg, lst, n_active);
+                    launches++;
+                    warp_launch(k_sp_warp<M, SP_FACTOR, WPB_MAX>, lst, n_active, 0);
+                    const int ipb = parts >= 4 ? 1 : 4 / parts, sthreads = 32 * parts * ipb, sgrid = (n_active + ipb - 1) / ipb;
+                    for (int mode = 1; mode <= 2; mode++) {
+                        k_sp_stage<M, SP_RHS><<<sgrid, sthreads, 0, stream>>>(a, cfg, lst, n_active, parts, ipb, mode);
+                        warp_launch(k_sp_warp<M, SP_CHAIN, WPB_MAX>, lst, n_active, mode);
+                        k_sp_stage<M, SP_RECOVER><<<sgrid, sthreads, 0, stream>>>(a, cfg, lst, n_active, parts, ipb, mode);
+                        launches += 2;
+                    }
+                    k_sp_stage<M, SP_UPDATE><<<sgrid, sthreads, 0, stream>>>(a, cfg, lst, n_active, parts, ipb, 0);
+                    k_sp_test<M><<<(n_active + 3) / 4, 128, 0, stream>>>(a, cfg, lst, n_active);
+                    launches += 2;
+                }
+            } else
             if (n_active > 0) {
                 // one warp per instance.  Small batches: spread the warps evenly, one CTA per SM (a batch of 1024 on 148 SMs is
                 // 7 warps per SM); large batches: 4-warp CTAs, two resident per SM.
@@ -368,7 +382,7 @@ struct EngineT : scpp_b200_engine {
             n_active = h_counter[0]; n_disc = h_counter[1];
             disc_list = disc;
             cur ^= 1;
-            rounds++;
+            rounds++; inst_rounds += n_active_round;
             global_active = comm ? (long long)*h_gcount : (long long)n_active;
         }
         // SC iterations done: per instance (reported as instance-iterations) and the largest count (outer iterations)
@@ -581,6 +595,12 @@ int scpp_b200_last_timing(scpp_b200_engine *e, double *a, double *b, double *c, 
 {
     if (!e) return fail(SCPP_B200_ERR_ARG, "null engine");
     if (a) *a = e->ms_disc; if (b) *b = e->ms_socp; if (c) *c = e->ms_total; if (l) *l = e->launches; if (o) *o = e->outer; if (ii) *ii = e->inst_iters;
+    return 0;
+}
+int scpp_b200_last_rounds(scpp_b200_engine *e, int *r, long long *ir)
+{
+    if (!e) return fail(SCPP_B200_ERR_ARG, "null engine");
+    if (r) *r = e->rounds; if (ir) *ir = e->inst_rounds;
     return 0;
 }
 size_t scpp_b200_device_bytes(scpp_b200_engine *e) { return e ? e->bytes : 0; }

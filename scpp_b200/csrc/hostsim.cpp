@@ -54,7 +54,21 @@ static int run_sc(const ModelParamsHost *P, const ScConfig *cfg, int N, const do
             if (a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] == 0.)
                 run_discretize<M>(K, X + (size_t)n * K * NX, U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg->nsub,
                                   a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K));
-            sc_solve_instance<M>(a, *cfg, n, smem.data());
+            if (cfg->ipm_slice >= 0) { sc_solve_instance<M>(a, *cfg, n, smem.data()); continue; }
+            // split pipeline: the kernel sequence of one round, run here for one instance after the other
+            double *w = smem.data();
+            const int P = (K + 31) / 32;
+            sc_split_step<M, SP_START>(a, *cfg, n, w, 0, 0);
+            for (int k = 0; k < K; k++) sc_split_step<M, SP_ASSEMBLE>(a, *cfg, n, w, 0, k);
+            sc_split_step<M, SP_FACTOR>(a, *cfg, n, w, 0, 0);
+            for (int mode = 1; mode <= 2; mode++) {
+                for (int p = 0; p < P; p++) sc_split_step<M, SP_RHS>(a, *cfg, n, w, mode, p);
+                sc_split_step<M, SP_CHAIN>(a, *cfg, n, w, mode, 0);
+                for (int p = 0; p < P; p++) sc_split_step<M, SP_RECOVER>(a, *cfg, n, w, mode, p);
+            }
+            for (int p = 0; p < P; p++) sc_split_step<M, SP_UPDATE>(a, *cfg, n, w, 0, p);
+            for (int p = 0; p < P; p++) sc_split_step<M, SP_RESIDUALS>(a, *cfg, n, w, 0, p);
+            sc_split_step<M, SP_TEST>(a, *cfg, n, w, 0, 0);
         }
         if (!active) break;
     }

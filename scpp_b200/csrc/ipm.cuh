@@ -38,6 +38,9 @@
 
 namespace scpp {
 
+// lanes stride over the warp's stage range (members k_lo, k_hi of Ipm)
+#define FOR_STAGE(k) for (int k = k_lo + lane_id(); k < k_hi; k += LANES)
+
 struct IpmSettings {
     double feastol, abstol, reltol;
     int maxit;
@@ -170,21 +173,30 @@ struct Ipm {
     SCPP_HD static int m_rows(int K) { return RS * ks(K) + 4; }
     SCPP_HD static int n_prim(int K) { return PSN * ks(K) + 2; }
     SCPP_HD static int n_ce(int K) { return NCN * ks(K) + 2; }
-    SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 8 * m_rows(K) + n_ce(K) + (NB + NX) * ks(K) + K * FS + 16; }
+    static constexpr int PARTS = 8, PSTR = 16;   // split pipeline: per-warp partial sums of the stage-parallel passes (K <= 32 * PARTS)
+    SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 8 * m_rows(K) + n_ce(K) + (NB + NX + 1) * ks(K) + PARTS * PSTR + K * FS + 16; }
     SCPP_HD static int ddt_doubles(int K) { return NX * NC * ks(K); }
-    // shared window of the warp (chain phases only):
-    //   factorisation:  two tile buffers | record out | L_{k,k-1} | H | O | model terms          substitution: three record buffers
+    // Shared window of a warp.  Front: per-solve tables and small vectors (every kernel).  Then a union:
+    //   inline factorisation (monolithic kernel):  two tile buffers | record out | L_{k,k-1} | H | O | model terms
+    //   substitutions / chain factorisation:       ring of three records | L_{k,k-1} | Linv scratch
+    //   assembly kernel (one warp per stage):      tile | carry data of interval k-1 | H | O | model terms
     static constexpr int HNC = pad2(NX + NX * NU + NU * NU);      // D | D C | C' D C  of the previous interval
-    static constexpr int W_DD = 0, W_FAC = W_DD + 2 * pad2(NX * NCP), W_LP = W_FAC + FS, W_MAT = W_LP + BLK, W_RK = W_MAT + 2 * BLK,
-                         W_F_END = W_RK + 2 * NRK * NB, W_S_END = 3 * FS,
-                         W_UEND = W_F_END > W_S_END ? W_F_END : W_S_END,
-                         W_WB = W_UEND, W_HN = W_WB + pad2(RS), W_VEC = W_HN + HNC, W_X = W_VEC + 6 * NB, W_SC = W_X + 2 * pad2(NX),
-                         W_RCQ = W_SC + 32, W_RIDX = W_RCQ + 4 * NROW, W_REV = W_RIDX + pad2(2 * NROW), W_CST = W_REV + pad2(2 * NB),
-                         W_END = W_CST + pad2(MAX_CST + 4);
+    static constexpr int cmax(int a, int b) { return a > b ? a : b; }
+    static constexpr int W_CST = 0, W_RCQ = W_CST + pad2(MAX_CST + 4), W_RIDX = W_RCQ + 4 * NROW, W_REV = W_RIDX + pad2(2 * NROW),
+                         W_SC = W_REV + pad2(2 * NB), W_VEC = W_SC + 32, W_X = W_VEC + 6 * NB, W_WB = W_X + 2 * pad2(NX), W_HN = W_WB + pad2(RS),
+                         W_U = W_HN + HNC,
+                         W_DD = W_U, W_FAC = W_DD + 2 * pad2(NX * NCP), W_LP = W_FAC + FS, W_MAT = W_LP + BLK, W_RK = W_MAT + 2 * BLK,
+                         W_F_END = W_RK + 2 * NRK * NB,
+                         W_RING = W_U, W_CLP = W_RING + 3 * FS, W_CLI = W_CLP + BLK, W_C_END = W_CLI + BLK,
+                         AW_DD = W_U, AW_PC = AW_DD + pad2(NX * NCP), AW_MAT = AW_PC + pad2(NX * NU + 3 * NX), AW_RK = AW_MAT + 2 * BLK,
+                         AW_END = AW_RK + 2 * NRK * NB,
+                         W_END = cmax(W_F_END, W_C_END);
+    SCPP_HD static int asm_doubles() { return AW_END; }
     SCPP_HD static int sm_doubles() { return W_END; }
 
     // ---- problem data (read only) -----------------------------------------------------------------------------
     int K, KS;
+    int k_lo, k_hi;        // stage range of the stage-parallel passes run by this warp ([0,K) unless the pass is split over warps)
     const double *dd;      // [K-1][NX][NC]   stage-major tiles (chain)
     const double *ddT;     // [NX*NC][KS]     the same tiles, stage-minor (stage-parallel passes)
     const double *Xbar;    // [K][NX]
@@ -201,13 +213,15 @@ struct Ipm {
     double *ce;
     double *gv;            // [NB][KS]  right-hand side g -> forward solution f -> solution y
     double *wv;            // [NX][KS]  w of interval k (coupling to node k+1)
+    double *cpart;         // [KS]      corner contribution of interval k (assembly kernel)
+    double *part;          // [PARTS][PSTR] partial sums of the split stage-parallel passes
     double *fac;           // [K][FS]
     double *sm;            // per-warp shared window
     double l_ss;           // Cholesky pivot of the sigma border
 
     SCPP_HD void bind(double *ws, double *smem)
     {
-        KS = ks(K);
+        KS = ks(K); k_lo = 0; k_hi = K;
         const int np = n_prim(K), m = m_rows(K);
         double *p = ws;
         prim = p; p += np; dprim = p; p += np; rx = p; p += np; best_ = p; p += np;
@@ -215,6 +229,8 @@ struct Ipm {
         ce = p; p += n_ce(K);
         gv = p; p += NB * KS;
         wv = p; p += NX * KS;
+        cpart = p; p += KS;
+        part = p; p += PARTS * PSTR;
         fac = p;
         sm = smem;
     }
@@ -276,7 +292,7 @@ struct Ipm {
     SCPP_HD double *sc() const { return sm + W_SC; }
     SCPP_HD double *tile(int k) const { return sm + W_DD + (k & 1) * pad2(NX * NCP); }
     SCPP_HD double *facw() const { return sm + W_FAC; }
-    SCPP_HD double *fbuf(int b) const { return sm + b * FS; }
+    SCPP_HD double *fbuf(int b) const { return sm + W_RING + b * FS; }
 
     // per-stage row coefficients in shared memory (chain: assembly of the node Hessian):  RCQ[r][0..2] = coefficients,
     // RCQ[r][3] = h ; RIDX[r][q] = variable index (or -1).  CST = per-instance constants (all phases).
@@ -284,6 +300,7 @@ struct Ipm {
     SCPP_HD int *ridx() const { return reinterpret_cast<int *>(sm + W_RIDX); }
     SCPP_HD int *sup() const { return reinterpret_cast<int *>(sm + W_REV); }
     SCPP_HD double *cstw() const { return sm + W_CST; }
+    SCPP_HD void cst_init() const { FOR_LANE(i, MAX_CST) cstw()[i] = cst[i]; warp_sync(); }   // all a stage-parallel pass needs of the tables
     SCPP_HD void tables_init() const
     {
         FOR_LANE(i, MAX_CST) cstw()[i] = cst[i];
@@ -342,7 +359,7 @@ struct Ipm {
         for (int q = 0; q < 3; q++) if (q < rd.n) acc[rd.idx[q]] += coef(rd, q, k) * v;
     }
 
-    struct Norms { double gap, rz2, rx2, pcost, zrz, xrx, h2; int bad; };
+    struct Norms { double gap, rz2, rx2, pcost, zrz, xrx, h2, acc_sig; int bad; };
     SCPP_HD static double nudge(double u0, double n1) { const double thr = 4e-16 * (fabs(u0) + n1) + 1e-300; return (u0 - n1 > thr) ? u0 : n1 + thr; }
 
     // =============================================================================================================
@@ -371,7 +388,7 @@ struct Ipm {
     }
     SCPP_HD void pass_update(double a)
     {
-        FOR_LANE(k, K) {
+        FOR_STAGE(k) {
             const bool hasint = k < K - 1;
             {
                 double p[PSN], d[PSN];
@@ -421,7 +438,7 @@ struct Ipm {
                 }
             }
         }
-        if (lane_id() == 0) {
+        if (lane_id() == 0 && k_lo == 0) {
             const int r0 = RS * KS, p0 = PSN * KS;
             double s4[4], z4[4], d4[4], e4[4];
 #pragma unroll
@@ -467,12 +484,14 @@ struct Ipm {
         for (int j = 0; j < NC; j++) row[j] = T(i, j, k);
     }
 
-    SCPP_HD void pass_residuals(Norms &nm, bool identity)
+    // split == true (split pipeline): no coupling from stage k-1 and no global rows here; residual_couple / residual_globals
+    // run in the next kernel; nm then holds the warp's partial sums
+    SCPP_HD void pass_residuals(Norms &nm, bool identity, bool split = false)
     {
         double gap = 0, rz2 = 0, pcost = 0, zrz = 0, h2 = 0, rx2 = 0, xrx = 0, acc_sig = 0;
         int bad = 0;
         const double sg = prim[PSN * KS];
-        FOR_LANE(k, K) {
+        FOR_STAGE(k) {
             const bool hasint = k < K - 1;
             double P[NB], RXa[NB], td[3];
             // ---- block 1 (loads): xi, delta, the trust-region cone, the linearisation point
@@ -640,74 +659,104 @@ struct Ipm {
                 }
             }
             // ---- block 4: coupling from interval k-1:  [w ; -C' w],  w = z- - z+ of that interval (two load groups)
-            if (k > 0) {
-                constexpr int HX = NX / 2;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    double wp[HX], Cc[HX][NU];
-#pragma unroll
-                    for (int i = 0; i < HX; i++) {
-                        wp[i] = z[(MN + h * HX + i) * KS + k - 1] - z[(MN + NX + h * HX + i) * KS + k - 1];
-#pragma unroll
-                        for (int a = 0; a < NU; a++) Cc[i][a] = T(h * HX + i, NB + a, k - 1);
-                    }
-#pragma unroll
-                    for (int i = 0; i < HX; i++) {
-                        RXa[h * HX + i] += wp[i];
-#pragma unroll
-                        for (int a = 0; a < NU; a++) RXa[NX + a] -= Cc[i][a] * wp[i];
-                    }
-                }
-            }
+            if (k > 0 && !split) couple_prev(k, RXa);
             const uint32_t mk = fixm[k];
 #pragma unroll
             for (int j = 0; j < NB; j++) {
-                const double v = ((mk >> j) & 1u) ? 0. : RXa[j];
+                const double v = (((mk >> j) & 1u) && !split) ? 0. : RXa[j];
+                rx[j * KS + k] = v;
+                if (!split) { rx2 += v * v; xrx += P[j] * v; }
+            }
+        }
+        nm.gap = warp_sum(gap); nm.rz2 = warp_sum(rz2); nm.pcost = warp_sum(pcost); nm.zrz = warp_sum(zrz);
+        nm.rx2 = warp_sum(rx2); nm.xrx = warp_sum(xrx); nm.h2 = warp_sum(h2); nm.bad = warp_or(bad);
+        nm.acc_sig = warp_sum(acc_sig);
+        if (!split) residual_globals(nm, identity);
+    }
+    // RXa += [w ; -C' w] of interval k-1
+    SCPP_HD void couple_prev(int k, double *RXa) const
+    {
+        constexpr int HX = NX / 2;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            double wp[HX], Cc[HX][NU];
+#pragma unroll
+            for (int i = 0; i < HX; i++) {
+                wp[i] = z[(MN + h * HX + i) * KS + k - 1] - z[(MN + NX + h * HX + i) * KS + k - 1];
+#pragma unroll
+                for (int a = 0; a < NU; a++) Cc[i][a] = T(h * HX + i, NB + a, k - 1);
+            }
+#pragma unroll
+            for (int i = 0; i < HX; i++) {
+                RXa[h * HX + i] += wp[i];
+#pragma unroll
+                for (int a = 0; a < NU; a++) RXa[NX + a] -= Cc[i][a] * wp[i];
+            }
+        }
+    }
+    // split pipeline: finishes rx (coupling, pinned variables) over ALL stages and adds its norms to nm (warp per instance)
+    SCPP_HD void residual_couple(Norms &nm)
+    {
+        double rx2 = 0, xrx = 0;
+        FOR_LANE(k, K) {
+            double R[NB], P[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++) { R[j] = rx[j * KS + k]; P[j] = prim[j * KS + k]; }
+            const uint32_t mk = fixm[k];
+            if (k > 0) couple_prev(k, R);
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                const double v = ((mk >> j) & 1u) ? 0. : R[j];
                 rx[j * KS + k] = v;
                 rx2 += v * v; xrx += P[j] * v;
             }
         }
-        acc_sig = warp_sum(acc_sig);
-        // ---- globals: lane 0
-        if (lane_id() == 0) {
-            const int r0 = RS * KS, c0 = NCN * KS, p0 = PSN * KS;
-            double s4[4], z4[4], w4[4], l4[4], r4[4];
+        nm.rx2 += warp_sum(rx2); nm.xrx += warp_sum(xrx);
+        warp_sync();
+    }
+    // the four global rows (sigma >= 0.001 and the sigma trust-region cone): every lane computes the same scalars from
+    // nm.acc_sig (already summed over the stages), lane 0 stores; the norms are added to nm
+    SCPP_HD void residual_globals(Norms &nm, bool identity)
+    {
+        const int r0 = RS * KS, c0 = NCN * KS, p0 = PSN * KS;
+        double s4[4], z4[4], w4[4], l4[4], r4[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) { s4[i] = s[r0 + i]; z4[i] = z[r0 + i]; }
-            const double dsg = prim[p0 + 1];
-            double rxs = w_time + acc_sig, cev = 1.;
-            r4[0] = s4[0] - (sg - 0.001);                           // sigma >= 0.001   (SCProblem.cpp:34)
-            rxs -= z4[0];
-            if (!(s4[0] > 0.) || !(z4[0] > 0.)) bad = 1;
-            w4[0] = identity ? 1. : z4[0] / s4[0]; l4[0] = identity ? 1. : sqrt(s4[0] * z4[0]);
-            r4[1] = s4[1] - (0.5 + 0.5 * dsg);                      // ((1+dsg)/2 ; (1-dsg)/2 ; sigma - sigbar)   (:92-96)
-            r4[2] = s4[2] - (0.5 - 0.5 * dsg);
-            r4[3] = s4[3] - (sg - sigbar);
-            rxs -= z4[3];
-            const double rxd = w_trs - 0.5 * z4[1] + 0.5 * z4[2];
-            if (identity) { for (int i = 0; i < 3; i++) { w4[1 + i] = i == 0; l4[1 + i] = i == 0; } }
-            else if (!soc::scale(s4 + 1, z4 + 1, 3, w4 + 1, cev, l4 + 1)) { bad = 1; for (int i = 0; i < 3; i++) { w4[1 + i] = i == 0; l4[1 + i] = i == 0; } }
+        for (int i = 0; i < 4; i++) { s4[i] = s[r0 + i]; z4[i] = z[r0 + i]; }
+        const double sg = prim[p0], dsg = prim[p0 + 1];
+        double rxs = w_time + nm.acc_sig, cev = 1.;
+        int bad = 0;
+        r4[0] = s4[0] - (sg - 0.001);                           // sigma >= 0.001   (SCProblem.cpp:34)
+        rxs -= z4[0];
+        if (!(s4[0] > 0.) || !(z4[0] > 0.)) bad = 1;
+        w4[0] = identity ? 1. : z4[0] / s4[0]; l4[0] = identity ? 1. : sqrt(s4[0] * z4[0]);
+        r4[1] = s4[1] - (0.5 + 0.5 * dsg);                      // ((1+dsg)/2 ; (1-dsg)/2 ; sigma - sigbar)   (:92-96)
+        r4[2] = s4[2] - (0.5 - 0.5 * dsg);
+        r4[3] = s4[3] - (sg - sigbar);
+        rxs -= z4[3];
+        const double rxd = w_trs - 0.5 * z4[1] + 0.5 * z4[2];
+        if (identity) { for (int i = 0; i < 3; i++) { w4[1 + i] = i == 0; l4[1 + i] = i == 0; } }
+        else if (!soc::scale(s4 + 1, z4 + 1, 3, w4 + 1, cev, l4 + 1)) { bad = 1; for (int i = 0; i < 3; i++) { w4[1 + i] = i == 0; l4[1 + i] = i == 0; } }
+        if (lane_id() == 0) {
 #pragma unroll
             for (int i = 0; i < 4; i++) { rz[r0 + i] = r4[i]; wb[r0 + i] = w4[i]; lam[r0 + i] = l4[i]; }
             ce[c0] = cev;
             rx[p0 + 1] = rxd; rx[p0] = rxs;
-            for (int r = 0; r < 4; r++) { gap += s4[r] * z4[r]; rz2 += r4[r] * r4[r]; zrz += z4[r] * r4[r]; }
-            pcost += w_time * sg + w_trs * dsg;
-            h2 += 0.001 * 0.001 + 0.5 + sigbar * sigbar;
-            rx2 += rxs * rxs + rxd * rxd;
-            xrx += sg * rxs + dsg * rxd;
         }
+        for (int r = 0; r < 4; r++) { nm.gap += s4[r] * z4[r]; nm.rz2 += r4[r] * r4[r]; nm.zrz += z4[r] * r4[r]; }
+        nm.pcost += w_time * sg + w_trs * dsg;
+        nm.h2 += 0.001 * 0.001 + 0.5 + sigbar * sigbar;
+        nm.rx2 += rxs * rxs + rxd * rxd;
+        nm.xrx += sg * rxs + dsg * rxd;
+        nm.bad |= bad;
         warp_sync();
-        nm.gap = warp_sum(gap); nm.rz2 = warp_sum(rz2); nm.pcost = warp_sum(pcost); nm.zrz = warp_sum(zrz);
-        nm.rx2 = warp_sum(rx2); nm.xrx = warp_sum(xrx); nm.h2 = warp_sum(h2); nm.bad = warp_or(bad);
     }
 
     // =============================================================================================================
     //  chain phase F : assemble the reduced Hessian stage by stage and factor it (block-tridiagonal Cholesky + border)
     // =============================================================================================================
-    SCPP_HD void build_model_terms(const double *WB, const double *CE, double *alpha)
+    SCPP_HD void build_model_terms(const double *WB, const double *CE, double *alpha, double *rk)
     {
-        double *rk = sm + W_RK, *dg = rk + NRK * NB;
+        double *dg = rk + NRK * NB;
         FOR_LANE(e, 2 * NRK * NB) rk[e] = 0.;
         warp_sync();
         FOR_LANE(c, NRK) {
@@ -801,10 +850,159 @@ struct Ipm {
 #endif
     }
 
+    // H_kk, O_k = H_{k+1,k} and the sigma-border b_k of stage k BEFORE the Schur update of the chain; all buffers in the shared
+    // window.  In: carry (D | D C | C' D C in Dp, border bn) of interval k-1.  Out: the same for interval k, corner += the
+    // lane-partial of s_k' D s_k.
+    SCPP_HD void assemble_body(int k, bool hasint, double *H, double *O, double *rk, const double *t, const double *WB, const double *CE,
+                               double *alpha, double *bk, double *bn, double *dsum, double *Dp, double *Dt, double &corner)
+    {
+        double *DCp = Dp + NX, *CDCp = DCp + NX * NU;
+        build_model_terms(WB, CE, alpha, rk);
+        // ---- node part of H_kk (trust region with delta eliminated) + carry from interval k-1: dense part, then the
+        //      model cones / rows, each of which touches at most 4 variables (sparse rank-1 terms, one cone at a time)
+        {
+            const double *dg = rk + NRK * NB;
+            const double *wt_ = WB + TRO;
+            const double e2i = CE[NCONE], w0 = wt_[0];
+            const double kap = e2i * (2. * w0 * w0 - 1.), c2 = 4. * e2i * e2i * w0 * w0 / kap, beta = 2. * e2i - c2;
+            FOR_LANE(i, NB) {
+                double v = e2i;
+#pragma unroll
+                for (int c = 0; c < NRK; c++) v += dg[c * NB + i];
+                dsum[i] = v;
+            }
+            warp_sync();
+#pragma unroll 2
+            FOR_LANE(e, BLK) {
+                const int i = e / NB, j = e - i * NB;
+                double v;
+                if (i < NX && j < NX) v = (i == j) ? Dp[i] : 0.;
+                else if (i < NX) v = -DCp[i * NU + (j - NX)];
+                else if (j < NX) v = -DCp[j * NU + (i - NX)];
+                else v = CDCp[(i - NX) * NU + (j - NX)];
+                if (i == j) v += dsum[i];
+                H[e] = v + beta * wt_[1 + i] * wt_[1 + j];
+            }
+            FOR_LANE(j, NB) bk[j] = bn[j];
+            warp_sync();
+#pragma unroll 1
+            for (int c = 0; c < NRK; c++) {
+                FOR_LANE(t2, 16) {
+                    const int i = sup()[4 * c + (t2 >> 2)], j = sup()[4 * c + (t2 & 3)];
+                    if (i >= 0 && j >= 0) H[i * NB + j] += alpha[c] * rk[c * NB + i] * rk[c * NB + j];
+                }
+                warp_sync();
+            }
+        }
+        warp_sync();
+        // ---- interval k: H_kk += A~' D A~ ; O = [-D A~ ; C' D A~] ; carry = (D, D C, C' D C) ; borders
+        if (hasint) {
+            FOR_LANE(i, NX) { const double dm = WB[MN + i], dp = WB[MN + NX + i]; Dt[i] = 4. * dm * dp / (dm + dp); }
+            warp_sync();
+            // O rows of the x_{k+1} block are -D A~ ; keep D A~ for the products: O[a][b], a < NX
+            FOR_LANE(e, NX * NB) { const int a = e / NB, b = e - a * NB; O[a * NB + b] = -Dt[a] * t[a * NCP + b]; }
+            FOR_LANE(e, NX * NU) { const int i = e / NU, j = e - i * NU; DCp[e] = Dt[i] * t[i * NCP + NB + j]; }
+            FOR_LANE(i, NX) Dp[i] = Dt[i];
+            warp_sync();
+            // H += A~' (D A~) = -A~' O_x   and   O_u = C' D A~ = -C' O_x   on the FP64 tensor cores (lower tiles of H suffice)
+            blk::mm<NB, NB, NX, true>([&](int m, int kk) { return (m < NB && kk < NX) ? t[kk * NCP + m] : 0.; },
+                                      [&](int kk, int n) { return (kk < NX && n < NB) ? -O[kk * NB + n] : 0.; },
+                                      [&](int m, int n, double v) { if (m < NB && n < NB) H[m * NB + n] += v; });
+            blk::mm<NU, NB, NX, false>([&](int m, int kk) { return (m < NU && kk < NX) ? t[kk * NCP + NB + m] : 0.; },
+                                       [&](int kk, int n) { return (kk < NX && n < NB) ? -O[kk * NB + n] : 0.; },
+                                       [&](int m, int n, double v) { if (m < NU && n < NB) O[(NX + m) * NB + n] = v; });
+            FOR_LANE(e, NU * NU) {
+                const int a = e / NU, b = e - a * NU;
+                double v = 0;
+#pragma unroll 2
+                for (int i = 0; i < NX; i++) v += t[i * NCP + NB + a] * DCp[i * NU + b];
+                CDCp[e] = v;
+            }
+            FOR_LANE(j, NB) {
+                double v = 0, vn;
+#pragma unroll 2
+                for (int i = 0; i < NX; i++) v += t[i * NCP + j] * Dt[i] * t[i * NCP + NB + NU];
+                bk[j] += v;
+                if (j < NX) vn = -Dt[j] * t[j * NCP + NB + NU];
+                else {
+                    vn = 0;
+#pragma unroll 2
+                    for (int i = 0; i < NX; i++) vn += t[i * NCP + NB + (j - NX)] * Dt[i] * t[i * NCP + NB + NU];
+                }
+                bn[j] = vn;
+            }
+            FOR_LANE(i, NX) { const double sv = t[i * NCP + NB + NU]; corner += Dt[i] * sv * sv; }
+        } else {
+            FOR_LANE(e, BLK) O[e] = 0.;
+        }
+        warp_sync();
+        // ---- pinned variables: identity rows/columns
+        {
+            const uint32_t mk = fixm[k], mn = hasint ? fixm[k + 1] : 0u;
+            FOR_LANE(e, BLK) {
+                const int a = e / NB, b = e - a * NB;
+                if (((mk >> a) & 1u) || ((mk >> b) & 1u)) H[e] = (a == b) ? 1. : 0.;
+                if (((mn >> a) & 1u) || ((mk >> b) & 1u)) O[e] = 0.;
+            }
+            FOR_LANE(j, NB) if ((mk >> j) & 1u) bk[j] = 0.;
+        }
+        warp_sync();
+    }
+    // one step of the block Cholesky chain on stage k: Schur update with L_{k,k-1} (in Lp), factor, Linv -> Li, L_{k+1,k} -> Ln,
+    // l_k -> lk.  H, O, bk are consumed.  Returns false when H is not positive definite.
+    SCPP_HD bool chain_step(int k, double *H, const double *O, double *bk, const double *Lp, const double *lprev, double *Li, double *Ln,
+                            double *lk, double &corner)
+    {
+        if (k > 0) {
+            blk::mm<NB, NB, NB, true>([&](int m, int kk) { return (m < NB && kk < NB) ? Lp[m * NB + kk] : 0.; },
+                                      [&](int kk, int n) { return (kk < NB && n < NB) ? Lp[n * NB + kk] : 0.; },
+                                      [&](int m, int n, double v) { if (m < NB && n < NB) H[m * NB + n] -= v; });
+            FOR_LANE(j, NB) {
+                double v = 0;
+#pragma unroll 2
+                for (int c = 0; c < NB; c++) v += Lp[j * NB + c] * lprev[c];
+                bk[j] -= v;
+            }
+        }
+        warp_sync();
+        const bool ok = chol_inv(H, Li);
+        warp_sync();
+        // ---- L_{k+1,k} = O Linv' ;  l_k = Linv bk ; corner -= l_k' l_k
+        blk::mm<NB, NB, NB, false>([&](int m, int kk) { return (m < NB && kk < NB) ? O[m * NB + kk] : 0.; },
+                                   [&](int kk, int n) { return (kk < NB && n < NB) ? Li[n * NB + kk] : 0.; },
+                                   [&](int m, int n, double v) { if (m < NB && n < NB) Ln[m * NB + n] = v; });
+        FOR_LANE(j, NB) {
+            double v = 0, v2 = 0;
+#pragma unroll
+            for (int c = 0; c < NB; c += 2) { v += Li[j * NB + c] * bk[c]; v2 += Li[j * NB + c + 1] * bk[c + 1]; }
+            v += v2;
+            lk[j] = v; corner -= v * v;
+        }
+        warp_sync();
+        return ok;
+    }
+    // corner of the sigma border: Schur complement of the chain + the global rows (sigma >= 0.001, sigma trust region with
+    // delta_sigma eliminated); sets l_ss
+    SCPP_HD bool finish_corner(double corner)
+    {
+        const int r0 = RS * KS;
+        const double d = wb[r0];
+        double w3[3] = {wb[r0 + 1], wb[r0 + 2], wb[r0 + 3]};
+        const double e2i = ce[NCN * KS];
+        double g[3] = {-0.5, 0.5, 0.}, p[3], e2[3] = {0., 0., 1.}, m2[3];
+        soc::Mv(w3, e2i, g, 3, p);
+        const double kap = g[0] * p[0] + g[1] * p[1];
+        soc::Mv(w3, e2i, e2, 3, m2);
+        corner += d + (m2[2] - p[2] * p[2] / kap);
+        l_ss = sqrt(corner > 0. ? corner : 1.);
+        return corner > 0.;
+    }
+
+    // Inline factorisation (monolithic kernel, cold start): assembly and chain interleaved stage by stage.
     SCPP_HD bool phase_factor()
     {
-        double *H = sm + W_MAT, *O = H + BLK, *Lp = sm + W_LP;
-        double *Dp = sm + W_HN, *DCp = Dp + NX, *CDCp = DCp + NX * NU;   // carry of interval k-1: D | D C | C' D C
+        double *H = sm + W_MAT, *O = H + BLK, *Lp = sm + W_LP, *rk = sm + W_RK;
+        double *Dp = sm + W_HN;             // carry of interval k-1: D | D C | C' D C
         double *F = facw();                 // Linv | Lnext | l   (the record written for this stage)
         double *Li = F, *Ln = F + OFF_LN, *lk = F + OFF_L;
         double *WB = sm + W_WB, *CE = sc() + 8, *alpha = sc();
@@ -859,146 +1057,151 @@ struct Ipm {
             warp_sync();
             tables_stage(TD);
             ld_wait(1);
-            build_model_terms(WB, CE, alpha);
-            // ---- node part of H_kk (trust region with delta eliminated) + carry from interval k-1: dense part, then the
-            //      model cones / rows, each of which touches at most 4 variables (sparse rank-1 terms, one cone at a time)
-            {
-                const double *rk = sm + W_RK, *dg = rk + NRK * NB;
-                const double *wt_ = WB + TRO;
-                const double e2i = CE[NCONE], w0 = wt_[0];
-                const double kap = e2i * (2. * w0 * w0 - 1.), c2 = 4. * e2i * e2i * w0 * w0 / kap, beta = 2. * e2i - c2;
-                double *dsum = vec(3);
-                FOR_LANE(i, NB) {
-                    double v = e2i;
-#pragma unroll
-                    for (int c = 0; c < NRK; c++) v += dg[c * NB + i];
-                    dsum[i] = v;
-                }
-                warp_sync();
-#pragma unroll 2
-                FOR_LANE(e, BLK) {
-                    const int i = e / NB, j = e - i * NB;
-                    double v;
-                    if (i < NX && j < NX) v = (i == j) ? Dp[i] : 0.;
-                    else if (i < NX) v = -DCp[i * NU + (j - NX)];
-                    else if (j < NX) v = -DCp[j * NU + (i - NX)];
-                    else v = CDCp[(i - NX) * NU + (j - NX)];
-                    if (i == j) v += dsum[i];
-                    H[e] = v + beta * wt_[1 + i] * wt_[1 + j];
-                }
-                FOR_LANE(j, NB) bk[j] = bn[j];
-                warp_sync();
-#pragma unroll 1
-                for (int c = 0; c < NRK; c++) {
-                    FOR_LANE(t, 16) {
-                        const int i = sup()[4 * c + (t >> 2)], j = sup()[4 * c + (t & 3)];
-                        if (i >= 0 && j >= 0) H[i * NB + j] += alpha[c] * rk[c * NB + i] * rk[c * NB + j];
-                    }
-                    warp_sync();
-                }
-            }
-            warp_sync();
-            // ---- interval k: H_kk += A~' D A~ ; O = [-D A~ ; C' D A~] ; carry = (D, D C, C' D C) ; borders
-            if (hasint) {
-                double *t = tile(k);
-                FOR_LANE(i, NX) { const double dm = WB[MN + i], dp = WB[MN + NX + i]; Dt[i] = 4. * dm * dp / (dm + dp); }
-                warp_sync();
-                // O rows of the x_{k+1} block are -D A~ ; keep D A~ for the products: O[a][b], a < NX
-                FOR_LANE(e, NX * NB) { const int a = e / NB, b = e - a * NB; O[a * NB + b] = -Dt[a] * t[a * NCP + b]; }
-                FOR_LANE(e, NX * NU) { const int i = e / NU, j = e - i * NU; DCp[e] = Dt[i] * t[i * NCP + NB + j]; }
-                FOR_LANE(i, NX) Dp[i] = Dt[i];
-                warp_sync();
-                // H += A~' (D A~) = -A~' O_x   and   O_u = C' D A~ = -C' O_x   on the FP64 tensor cores (lower tiles of H suffice)
-                blk::mm<NB, NB, NX, true>([&](int m, int k) { return (m < NB && k < NX) ? t[k * NCP + m] : 0.; },
-                                          [&](int k, int n) { return (k < NX && n < NB) ? -O[k * NB + n] : 0.; },
-                                          [&](int m, int n, double v) { if (m < NB && n < NB) H[m * NB + n] += v; });
-                blk::mm<NU, NB, NX, false>([&](int m, int k) { return (m < NU && k < NX) ? t[k * NCP + NB + m] : 0.; },
-                                           [&](int k, int n) { return (k < NX && n < NB) ? -O[k * NB + n] : 0.; },
-                                           [&](int m, int n, double v) { if (m < NU && n < NB) O[(NX + m) * NB + n] = v; });
-                FOR_LANE(e, NU * NU) {
-                    const int a = e / NU, b = e - a * NU;
-                    double v = 0;
-#pragma unroll 2
-                    for (int i = 0; i < NX; i++) v += t[i * NCP + NB + a] * DCp[i * NU + b];
-                    CDCp[e] = v;
-                }
-                FOR_LANE(j, NB) {
-                    double v = 0, vn;
-#pragma unroll 2
-                    for (int i = 0; i < NX; i++) v += t[i * NCP + j] * Dt[i] * t[i * NCP + NB + NU];
-                    bk[j] += v;
-                    if (j < NX) vn = -Dt[j] * t[j * NCP + NB + NU];
-                    else {
-                        vn = 0;
-#pragma unroll 2
-                        for (int i = 0; i < NX; i++) vn += t[i * NCP + NB + (j - NX)] * Dt[i] * t[i * NCP + NB + NU];
-                    }
-                    bn[j] = vn;
-                }
-                FOR_LANE(i, NX) { const double sv = t[i * NCP + NB + NU]; corner += Dt[i] * sv * sv; }
-            } else {
-                FOR_LANE(e, BLK) O[e] = 0.;
-            }
-            warp_sync();
-            // ---- pinned variables: identity rows/columns
-            {
-                const uint32_t mk = fixm[k], mn = hasint ? fixm[k + 1] : 0u;
-                FOR_LANE(e, BLK) {
-                    const int a = e / NB, b = e - a * NB;
-                    if (((mk >> a) & 1u) || ((mk >> b) & 1u)) H[e] = (a == b) ? 1. : 0.;
-                    if (((mn >> a) & 1u) || ((mk >> b) & 1u)) O[e] = 0.;
-                }
-                FOR_LANE(j, NB) if ((mk >> j) & 1u) bk[j] = 0.;
-            }
-            warp_sync();
-            // ---- Schur update with the previous off-diagonal factor: H -= Lp Lp' ; bk -= Lp lprev
-            if (k > 0) {
-                blk::mm<NB, NB, NB, true>([&](int m, int k) { return (m < NB && k < NB) ? Lp[m * NB + k] : 0.; },
-                                          [&](int k, int n) { return (k < NB && n < NB) ? Lp[n * NB + k] : 0.; },
-                                          [&](int m, int n, double v) { if (m < NB && n < NB) H[m * NB + n] -= v; });
-                FOR_LANE(j, NB) {
-                    double v = 0;
-#pragma unroll 2
-                    for (int c = 0; c < NB; c++) v += Lp[j * NB + c] * lprev[c];
-                    bk[j] -= v;
-                }
-            }
-            warp_sync();
-            // ---- Cholesky of H and Linv = L^-1
-            if (!chol_inv(H, Li)) bad = 1;
-            warp_sync();
-            // ---- L_{k+1,k} = O Linv' ;  l_k = Linv bk ; corner -= l_k' l_k
-            blk::mm<NB, NB, NB, false>([&](int m, int k) { return (m < NB && k < NB) ? O[m * NB + k] : 0.; },
-                                       [&](int k, int n) { return (k < NB && n < NB) ? Li[n * NB + k] : 0.; },
-                                       [&](int m, int n, double v) { if (m < NB && n < NB) Ln[m * NB + n] = v; });
-            FOR_LANE(j, NB) {
-                double v = 0, v2 = 0;
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) { v += Li[j * NB + c] * bk[c]; v2 += Li[j * NB + c + 1] * bk[c + 1]; }
-                v += v2;
-                lk[j] = v; corner -= v * v;
-            }
-            warp_sync();
+            assemble_body(k, hasint, H, O, rk, tile(k), WB, CE, alpha, bk, bn, vec(3), Dp, Dt, corner);
+            if (!chain_step(k, H, O, bk, Lp, lprev, Li, Ln, lk, corner)) bad = 1;
             st(fac + (size_t)k * FS, F, FS);
             FOR_LANE(e, BLK) Lp[e] = Ln[e];
             FOR_LANE(j, NB) lprev[j] = lk[j];
             warp_sync();
         }
         corner = warp_sum(corner);
-        {   // globals: sigma >= 0.001 row and the sigma trust-region cone with delta_sigma eliminated
-            const int r0 = RS * KS;
-            const double d = wb[r0];
-            double w3[3] = {wb[r0 + 1], wb[r0 + 2], wb[r0 + 3]};
-            const double e2i = ce[NCN * KS];
-            double g[3] = {-0.5, 0.5, 0.}, p[3], e2[3] = {0., 0., 1.}, m2[3];
-            soc::Mv(w3, e2i, g, 3, p);
-            const double kap = g[0] * p[0] + g[1] * p[1];
-            soc::Mv(w3, e2i, e2, 3, m2);
-            corner += d + (m2[2] - p[2] * p[2] / kap);
-        }
-        if (!(corner > 0.)) bad = 1;
-        l_ss = sqrt(corner > 0. ? corner : 1.);
+        if (!finish_corner(corner)) bad = 1;
         return !warp_or(bad);
+    }
+
+    // Split pipeline, step A (one warp per (instance, stage)): assemble H_kk | O_k | b_k of stage k into its factor record and
+    // the corner contribution of interval k into cpart[k].  Needs tables_init() on this warp's window.
+    SCPP_HD void assemble_stage(int k)
+    {
+        const bool hasint = k < K - 1;
+        double *t = sm + AW_DD, *PC = sm + AW_PC, *H = sm + AW_MAT, *O = H + BLK, *rk = sm + AW_RK;
+        double *Cp = PC, *sp = PC + NX * NU, *WBp = sp + NX;      // interval k-1: C | s column | scaling rows of its pairs
+        double *Dp = sm + W_HN, *DCp = Dp + NX, *CDCp = DCp + NX * NU;
+        double *WB = sm + W_WB, *CE = sc() + 8, *alpha = sc(), *TD = sc() + 16;
+        double *bk = vec(0), *bn = vec(1), *Dt = xv(1);
+        // ---- loads: tile k (asynchronous), then the strided pieces
+        if (hasint) {
+            const double *src = dd + (size_t)k * NX * NC;
+#if defined(__CUDA_ARCH__)
+            const unsigned d0 = (unsigned)__cvta_generic_to_shared(t);
+            for (int c = lane_id(); c < NX * (NC / 2); c += LANES) {
+                const int r = c / (NC / 2), q = c - r * (NC / 2);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0 + 8u * (r * NCP + 2 * q)), "l"(src + r * NC + 2 * q) : "memory");
+            }
+#else
+            for (int r = 0; r < NX; r++) memcpy(t + r * NCP, src + r * NC, sizeof(double) * NC);
+#endif
+        }
+        ld_commit();
+        FOR_LANE(r, RS) WB[r] = wb[r * KS + k];
+        FOR_LANE(c, NCN) CE[c] = ce[c * KS + k];
+        FOR_LANE(q, 3) TD[q] = tdir[3 * k + q];
+        if (k > 0) {
+            const double *tp = dd + (size_t)(k - 1) * NX * NC;
+            FOR_LANE(e, NX * NU) { const int i = e / NU, j = e - i * NU; Cp[e] = tp[i * NC + NB + j]; }
+            FOR_LANE(i, NX) sp[i] = tp[i * NC + NB + NU];
+            FOR_LANE(r, 2 * NX) WBp[r] = wb[(MN + r) * KS + k - 1];
+        }
+        warp_sync();
+        tables_stage(TD);
+        // ---- carry of interval k-1
+        if (k > 0) {
+            FOR_LANE(i, NX) { const double dm = WBp[i], dp = WBp[NX + i]; Dp[i] = 4. * dm * dp / (dm + dp); }
+            warp_sync();
+            FOR_LANE(e, NX * NU) DCp[e] = Dp[e / NU] * Cp[e];
+            warp_sync();
+            FOR_LANE(e, NU * NU) {
+                const int a = e / NU, b = e - a * NU;
+                double v = 0;
+#pragma unroll 2
+                for (int i = 0; i < NX; i++) v += Cp[i * NU + a] * DCp[i * NU + b];
+                CDCp[e] = v;
+            }
+            FOR_LANE(j, NB) {
+                double vn;
+                if (j < NX) vn = -Dp[j] * sp[j];
+                else {
+                    vn = 0;
+#pragma unroll 2
+                    for (int i = 0; i < NX; i++) vn += Cp[i * NU + (j - NX)] * Dp[i] * sp[i];
+                }
+                bn[j] = vn;
+            }
+        } else {
+            FOR_LANE(e, HNC) Dp[e] = 0.;
+            FOR_LANE(j, NB) bn[j] = 0.;
+        }
+        ld_wait();
+        double corner = 0.;
+        assemble_body(k, hasint, H, O, rk, t, WB, CE, alpha, bk, bn, vec(3), Dp, Dt, corner);
+        corner = warp_sum(corner);
+        double *rec = fac + (size_t)k * FS;
+        st(rec, H, BLK); st(rec + OFF_LN, O, BLK);
+        FOR_LANE(j, NB) rec[OFF_L + j] = bk[j];
+        if (lane_id() == 0) cpart[k] = corner;
+        warp_sync();
+    }
+    // Split pipeline, step F (one warp per instance): the chain over the assembled records, in place (H|O|b -> Linv|Ln|l),
+    // three records in flight.
+    SCPP_HD bool chain_factor()
+    {
+        double *Lp = sm + W_CLP, *Li = sm + W_CLI, *lprev = vec(2), *lk = vec(3);
+        double corner = 0.;
+        int bad = 0;
+        FOR_LANE(k, K) corner += cpart[k];
+        FOR_LANE(j, NB) lprev[j] = 0.;
+        ld(fbuf(0), fac, FS); ld_commit();
+        if (K > 1) ld(fbuf(1), fac + FS, FS);
+        ld_commit();
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            if (k + 2 < K) ld(fbuf((k + 2) % 3), fac + (size_t)(k + 2) * FS, FS);
+            ld_commit();
+            ld_wait(2);
+            double *F = fbuf(k % 3);
+            // L_{k+1,k} goes straight into Lp (free once the Schur update of this stage is done): it is the next stage's L_{k,k-1}
+            double *rec = fac + (size_t)k * FS;
+            if (!chain_step_inplace(k, F, F + OFF_LN, F + OFF_L, Lp, lprev, Li, lk, corner)) bad = 1;
+            st(rec, Li, BLK); st(rec + OFF_LN, Lp, BLK);
+            FOR_LANE(j, NB) { rec[OFF_L + j] = lk[j]; lprev[j] = lk[j]; }
+            warp_sync();
+        }
+        ld_wait();
+        corner = warp_sum(corner);
+        if (!finish_corner(corner)) bad = 1;
+        return !warp_or(bad);
+    }
+    // chain_step with L_{k+1,k} written over Lp: the Schur update reads Lp first, the product O Linv' is formed in registers
+    // and stored after a warp barrier
+    SCPP_HD bool chain_step_inplace(int k, double *H, const double *O, double *bk, double *Lp, const double *lprev, double *Li, double *lk,
+                                    double &corner)
+    {
+        if (k > 0) {
+            blk::mm<NB, NB, NB, true>([&](int m, int kk) { return (m < NB && kk < NB) ? Lp[m * NB + kk] : 0.; },
+                                      [&](int kk, int n) { return (kk < NB && n < NB) ? Lp[n * NB + kk] : 0.; },
+                                      [&](int m, int n, double v) { if (m < NB && n < NB) H[m * NB + n] -= v; });
+            FOR_LANE(j, NB) {
+                double v = 0;
+#pragma unroll 2
+                for (int c = 0; c < NB; c++) v += Lp[j * NB + c] * lprev[c];
+                bk[j] -= v;
+            }
+        }
+        warp_sync();
+        const bool ok = chol_inv(H, Li);
+        warp_sync();
+        blk::mm<NB, NB, NB, false>([&](int m, int kk) { return (m < NB && kk < NB) ? O[m * NB + kk] : 0.; },
+                                   [&](int kk, int n) { return (kk < NB && n < NB) ? Li[n * NB + kk] : 0.; },
+                                   [&](int m, int n, double v) { if (m < NB && n < NB) Lp[m * NB + n] = v; });
+        FOR_LANE(j, NB) {
+            double v = 0, v2 = 0;
+#pragma unroll
+            for (int c = 0; c < NB; c += 2) { v += Li[j * NB + c] * bk[c]; v2 += Li[j * NB + c + 1] * bk[c + 1]; }
+            v += v2;
+            lk[j] = v; corner -= v * v;
+        }
+        warp_sync();
+        return ok;
     }
 
     // =============================================================================================================
@@ -1038,10 +1241,10 @@ struct Ipm {
         return -csig * i2 - sqrt(1. / dv) * ((-i0 * i0 - i1 + sigmu) / i0);
     }
 
-    SCPP_HD double pass_rhs(int mode, double csig, double sigmu)   // returns the lane-partial of the sigma right-hand side
+    SCPP_HD double pass_rhs(int mode, double csig, double sigmu, bool split = false)   // returns the lane-partial of the sigma right-hand side
     {
         double gsig = 0;
-        FOR_LANE(k, K) {
+        FOR_STAGE(k) {
             const bool hasint = k < K - 1;
             double G[NB], td[3];
             // ---- block 1 (loads): rxv of xi and delta, the trust-region cone
@@ -1190,7 +1393,12 @@ struct Ipm {
             for (int j = 0; j < NB; j++) gv[j * KS + k] = G[j];
         }
         warp_sync();
-        // ---- coupling from interval k-1 and the pinned variables
+        if (!split) rhs_couple();
+        return gsig;
+    }
+    // coupling from interval k-1 and the pinned variables, over ALL stages (split pipeline: first step of the chain kernel)
+    SCPP_HD void rhs_couple()
+    {
         FOR_LANE(k, K) {
             const uint32_t mk = fixm[k];
             double g[NB];
@@ -1215,13 +1423,9 @@ struct Ipm {
             for (int j = 0; j < NB; j++) gv[j * KS + k] = ((mk >> j) & 1u) ? 0. : g[j];
         }
         warp_sync();
-        return gsig;
     }
 
     // forward substitution  f_k = Linv_k (g_k - L_{k,k-1} f_{k-1})  in place in gv ; returns the lane-partial of  sum_k l_k' f_k
-    // Both substitutions keep THREE factor records in flight (prefetch distance 2: a stage is ~300 cycles of dependent
-    // arithmetic, a DRAM round trip ~800) and read the right-hand side two stages ahead into registers.
-    // Forward: stage k needs only its own record because the coupling term L_{k+1,k} f_k is formed at the end of stage k.
     SCPP_HD void ld_col(double *dst, const double *src) const   // one stage column of a stage-minor [NB][KS] array: NB 8-byte asynchronous copies
     {
 #if defined(__CUDA_ARCH__)
@@ -1313,7 +1517,7 @@ struct Ipm {
     SCPP_HD double pass_recover(int mode, double csig, double rzs, double ysig)   // returns the lane-partial of tmax
     {
         double tmax = 0;
-        FOR_LANE(k, K) {
+        FOR_STAGE(k) {
             const bool hasint = k < K - 1;
             double yk[NB], td[3];
             // ---- block 1 (loads): the solution of the stage, the trust-region cone
@@ -1520,68 +1724,81 @@ struct Ipm {
         return tmax;
     }
 
-    SCPP_HD void phase_solve(int mode, double csig, double sigmu, double rzs, double &tmax_out)
+    // scalars of the sigma rows shared by the forward/backward halves of a solve
+    struct Glob { double rzg[4], rxg[2], kap_s, p_s[3], ysig; };
+    // globals: rhs and local elimination for the sigma rows, then y_sigma (every lane computes the same scalars)
+    SCPP_HD void globals_mid(int mode, double csig, double sigmu, double gsig, double ldot, Glob &g) const
     {
         const int r0g = RS * KS, p0g = PSN * KS;
-        double gsig = warp_sum(pass_rhs(mode, csig, sigmu));
-        const double ldot = warp_sum(chain_forward());
-        // ---- globals: rhs and local elimination for the sigma rows (every lane computes the same scalars)
-        double kap_s, p_s[3], rzg[4], rxg[2];
-        {
-            double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
-            const double e2i = ce[NCN * KS], d0 = wb[r0g];
-            if (mode == 0) { for (int i = 0; i < 4; i++) rzg[i] = ds[r0g + i]; rxg[0] = dprim[p0g]; rxg[1] = dprim[p0g + 1]; }
-            else if (mode == 1) { for (int i = 0; i < 4; i++) rzg[i] = -rz[r0g + i] + s[r0g + i]; rxg[0] = -rx[p0g]; rxg[1] = -rx[p0g + 1]; }
-            else {
-                const double l0 = lam[r0g];
-                rzg[0] = -csig * rz[r0g] - sqrt(1. / d0) * ((-l0 * l0 - cr[r0g] + sigmu) / l0);
-                double lm3[3] = {lam[r0g + 1], lam[r0g + 2], lam[r0g + 3]}, t1[3];
-                soc::jprod(lm3, lm3, 3, t1);
-                for (int i = 0; i < 3; i++) t1[i] = -t1[i] - cr[r0g + 1 + i];
-                t1[0] += sigmu;
-                soc::jdiv(lm3, t1, 3, t1);
-                soc::Wv(w3, e2i, t1, 3, t1, false);
-                for (int i = 0; i < 3; i++) rzg[1 + i] = -csig * rz[r0g + 1 + i] - t1[i];
-                rxg[0] = -csig * rx[p0g]; rxg[1] = -csig * rx[p0g + 1];
-            }
-            double g3[3] = {-0.5, 0.5, 0.}, v[3];
-            soc::Mv(w3, e2i, g3, 3, p_s);
-            kap_s = g3[0] * p_s[0] + g3[1] * p_s[1];
-            soc::Mv(w3, e2i, rzg + 1, 3, v);
-            const double prz = p_s[0] * rzg[1] + p_s[1] * rzg[2] + p_s[2] * rzg[3];
-            const double rho = (prz + rxg[1]) / kap_s;
-            gsig += rxg[0] - d0 * rzg[0] - (v[2] - p_s[2] * rho);
+        double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
+        const double e2i = ce[NCN * KS], d0 = wb[r0g];
+        if (mode == 0) { for (int i = 0; i < 4; i++) g.rzg[i] = ds[r0g + i]; g.rxg[0] = dprim[p0g]; g.rxg[1] = dprim[p0g + 1]; }
+        else if (mode == 1) { for (int i = 0; i < 4; i++) g.rzg[i] = -rz[r0g + i] + s[r0g + i]; g.rxg[0] = -rx[p0g]; g.rxg[1] = -rx[p0g + 1]; }
+        else {
+            const double l0 = lam[r0g];
+            g.rzg[0] = -csig * rz[r0g] - sqrt(1. / d0) * ((-l0 * l0 - cr[r0g] + sigmu) / l0);
+            double lm3[3] = {lam[r0g + 1], lam[r0g + 2], lam[r0g + 3]}, t1[3];
+            soc::jprod(lm3, lm3, 3, t1);
+            for (int i = 0; i < 3; i++) t1[i] = -t1[i] - cr[r0g + 1 + i];
+            t1[0] += sigmu;
+            soc::jdiv(lm3, t1, 3, t1);
+            soc::Wv(w3, e2i, t1, 3, t1, false);
+            for (int i = 0; i < 3; i++) g.rzg[1 + i] = -csig * rz[r0g + 1 + i] - t1[i];
+            g.rxg[0] = -csig * rx[p0g]; g.rxg[1] = -csig * rx[p0g + 1];
         }
+        double g3[3] = {-0.5, 0.5, 0.}, v[3];
+        soc::Mv(w3, e2i, g3, 3, g.p_s);
+        g.kap_s = g3[0] * g.p_s[0] + g3[1] * g.p_s[1];
+        soc::Mv(w3, e2i, g.rzg + 1, 3, v);
+        const double prz = g.p_s[0] * g.rzg[1] + g.p_s[1] * g.rzg[2] + g.p_s[2] * g.rzg[3];
+        const double rho = (prz + g.rxg[1]) / g.kap_s;
+        gsig += g.rxg[0] - d0 * g.rzg[0] - (v[2] - g.p_s[2] * rho);
         const double fsig = (gsig - ldot) / l_ss;
-        const double ysig = fsig / l_ss;
-        warp_sync();
-        chain_backward(ysig);
-        double tmax = pass_recover(mode, csig, rzs, ysig);
-        // ---- globals recovery (lane 0)
-        if (lane_id() == 0) {
-            double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
-            const double e2i = ce[NCN * KS], d0 = wb[r0g];
-            const double dz0 = d0 * (-ysig - rzg[0]);
-            double q[3] = {-rzg[1], -rzg[2], -ysig - rzg[3]}, mq[3], dzq[3];
-            const double pq = p_s[0] * q[0] + p_s[1] * q[1] + p_s[2] * q[2];
-            const double dds = (rxg[1] - pq) / kap_s;
-            soc::Mv(w3, e2i, q, 3, mq);
-            for (int i = 0; i < 3; i++) dzq[i] = mq[i] + p_s[i] * dds;
-            dz[r0g] = dz0; for (int i = 0; i < 3; i++) dz[r0g + 1 + i] = dzq[i];
-            dprim[p0g] = ysig; dprim[p0g + 1] = dds;
-            if (mode != 0) {
-                double dsg[4] = {rzs * rz[r0g] + ysig, rzs * rz[r0g + 1] + 0.5 * dds, rzs * rz[r0g + 2] - 0.5 * dds, rzs * rz[r0g + 3] + ysig};
-                for (int i = 0; i < 4; i++) ds[r0g + i] = dsg[i];
-                const double wv_ = sqrt(1. / d0), l0 = lam[r0g];
-                const double dzt0 = wv_ * dz0, dst0 = dsg[0] / wv_;
-                tmax = fmax(tmax, fmax(-dst0 / l0, -dzt0 / l0));
-                double lm3[3] = {lam[r0g + 1], lam[r0g + 2], lam[r0g + 3]}, dzt[3], dst[3], pr[3];
-                soc::Wv(w3, e2i, dzq, 3, dzt, false);
-                soc::Wv(w3, e2i, dsg + 1, 3, dst, true);
-                tmax = fmax(tmax, fmax(soc::step(lm3, dst, 3), soc::step(lm3, dzt, 3)));
-                if (mode == 1) { cr[r0g] = dst0 * dzt0; soc::jprod(dst, dzt, 3, pr); for (int i = 0; i < 3; i++) cr[r0g + 1 + i] = pr[i]; }
-            }
+        g.ysig = fsig / l_ss;
+    }
+    // recovery of the global rows: dz, ds, dsigma, ddelta_sigma, cr (mode 1); returns their scaled step-length bound.
+    // Call from lane 0 only (it stores).
+    SCPP_HD double globals_recover(int mode, double rzs, const Glob &g)
+    {
+        const int r0g = RS * KS, p0g = PSN * KS;
+        double tmax = 0;
+        double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
+        const double e2i = ce[NCN * KS], d0 = wb[r0g], ysig = g.ysig;
+        const double dz0 = d0 * (-ysig - g.rzg[0]);
+        double q[3] = {-g.rzg[1], -g.rzg[2], -ysig - g.rzg[3]}, mq[3], dzq[3];
+        const double pq = g.p_s[0] * q[0] + g.p_s[1] * q[1] + g.p_s[2] * q[2];
+        const double dds = (g.rxg[1] - pq) / g.kap_s;
+        soc::Mv(w3, e2i, q, 3, mq);
+        for (int i = 0; i < 3; i++) dzq[i] = mq[i] + g.p_s[i] * dds;
+        double rz4[4] = {0., 0., 0., 0.}, lm4[4] = {1., 1., 0., 0.};
+        if (mode != 0) { for (int i = 0; i < 4; i++) { rz4[i] = rz[r0g + i]; lm4[i] = lam[r0g + i]; } }
+        dz[r0g] = dz0; for (int i = 0; i < 3; i++) dz[r0g + 1 + i] = dzq[i];
+        dprim[p0g] = ysig; dprim[p0g + 1] = dds;
+        if (mode != 0) {
+            double dsg[4] = {rzs * rz4[0] + ysig, rzs * rz4[1] + 0.5 * dds, rzs * rz4[2] - 0.5 * dds, rzs * rz4[3] + ysig};
+            for (int i = 0; i < 4; i++) ds[r0g + i] = dsg[i];
+            const double wv_ = sqrt(1. / d0), l0 = lm4[0];
+            const double dzt0 = wv_ * dz0, dst0 = dsg[0] / wv_;
+            tmax = fmax(tmax, fmax(-dst0 / l0, -dzt0 / l0));
+            double lm3[3] = {lm4[1], lm4[2], lm4[3]}, dzt[3], dst[3], pr[3];
+            soc::Wv(w3, e2i, dzq, 3, dzt, false);
+            soc::Wv(w3, e2i, dsg + 1, 3, dst, true);
+            tmax = fmax(tmax, fmax(soc::step(lm3, dst, 3), soc::step(lm3, dzt, 3)));
+            if (mode == 1) { cr[r0g] = dst0 * dzt0; soc::jprod(dst, dzt, 3, pr); for (int i = 0; i < 3; i++) cr[r0g + 1 + i] = pr[i]; }
         }
+        return tmax;
+    }
+
+    SCPP_HD void phase_solve(int mode, double csig, double sigmu, double rzs, double &tmax_out)
+    {
+        const double gsig = warp_sum(pass_rhs(mode, csig, sigmu));
+        const double ldot = warp_sum(chain_forward());
+        Glob g;
+        globals_mid(mode, csig, sigmu, gsig, ldot, g);
+        warp_sync();
+        chain_backward(g.ysig);
+        double tmax = pass_recover(mode, csig, rzs, g.ysig);
+        if (lane_id() == 0) tmax = fmax(tmax, globals_recover(mode, rzs, g));
         warp_sync();
         tmax_out = warp_max(tmax);
     }
@@ -1647,27 +1864,14 @@ struct Ipm {
     // =============================================================================================================
     //  driver
     // =============================================================================================================
-    // Sliced driver.  `state` (IPM_STATE doubles, per instance, global memory) carries the solver across kernel launches:
-    // the engine runs at most `budget` interior-point iterations per launch and re-balances the batch between launches
-    // (instances need very different iteration counts; see DESIGN.md).  state[0] == 0: begin a new sub-problem.
-    // Returns with finished == false when the budget ran out; everything else lives in the workspace already.
-    static constexpr int IPM_STATE = 12;
-    SCPP_HD IpmResult solve(const IpmSettings &st_, bool have_prev, int budget, double *state, bool &finished)
+    // starting point of a sub-problem: 1 = previous interior point pulled back from the boundary, 2 = least-squares (cold) start,
+    // 0 = the cold start's factorisation failed
+    SCPP_HD int init_point(const IpmSettings &st_, bool have_prev)
     {
-        IpmResult res;
-        res.status = 1; res.iterations = 0; res.pres = res.dres = res.gap = res.relgap = res.pcost = 0.;
         const int np = n_prim(K), m = m_rows(K);
-        finished = true;
-        tables_init();
-        const bool resume = state[0] != 0.;
         Norms nm;
         double tm;
-        double best = 1e300, pending = 0.;
-        int it = 0;
-        if (resume) {
-            it = (int)state[1]; pending = state[2]; best = state[3];
-            res.pres = state[4]; res.dres = state[5]; res.gap = state[6]; res.relgap = state[7]; res.pcost = state[8]; res.iterations = (int)state[9];
-        } else if (have_prev && st_.warm > 0. && st_.warm < 1.) {
+        if (have_prev && st_.warm > 0. && st_.warm < 1.) {
             // previous interior point of this instance, pulled back from the boundary; pinned variables keep their values
             const double lw = st_.warm, lc = 1. - st_.warm;
             FOR_LANE(k, K) { for (int i = 0; i < NB; i++) if (fixed(k, i)) prim[i * KS + k] = fixv[k * NB + i]; }
@@ -1675,6 +1879,7 @@ struct Ipm {
             warp_sync();
             cone_shift(s, lc); cone_shift(z, lc);
             warp_sync();
+            return 1;
         } else {
             // ---- starting point (CVXOPT conelp / ECOS style): least-squares primal and dual points, W = I
             FOR_LANE(e, np) prim[e] = 0.;
@@ -1686,7 +1891,7 @@ struct Ipm {
             cone_shift(s, 1.); cone_shift(z, 1.);
             warp_sync();
             pass_residuals(nm, true);
-            if (!phase_factor()) { res.status = 2; if (lane_id() == 0) state[0] = 0.; warp_sync(); return res; }
+            if (!phase_factor()) return 0;
             // primal: min |G x - h|  ->  G dx - dz = slack(x0)
             eval_slack(ds);
             FOR_LANE(e, np) dprim[e] = 0.;
@@ -1715,7 +1920,33 @@ struct Ipm {
                 if (mg <= 1e-8 * fmax(1., sqrt(n2))) { cone_shift(z, 1. - mg); }
                 warp_sync();
             }
-            budget -= 1;                     // the least-squares start costs about one iteration
+            return 2;
+        }
+    }
+    // Sliced driver.  `state` (IPM_STATE doubles, per instance, global memory) carries the solver across kernel launches:
+    // the engine runs at most `budget` interior-point iterations per launch and re-balances the batch between launches
+    // (instances need very different iteration counts; see DESIGN.md).  state[0] == 0: begin a new sub-problem.
+    // Returns with finished == false when the budget ran out; everything else lives in the workspace already.
+    static constexpr int IPM_STATE = 32;
+    SCPP_HD IpmResult solve(const IpmSettings &st_, bool have_prev, int budget, double *state, bool &finished)
+    {
+        IpmResult res;
+        res.status = 1; res.iterations = 0; res.pres = res.dres = res.gap = res.relgap = res.pcost = 0.;
+        const int np = n_prim(K), m = m_rows(K);
+        finished = true;
+        tables_init();
+        const bool resume = state[0] != 0.;
+        Norms nm;
+        double tm;
+        double best = 1e300, pending = 0.;
+        int it = 0;
+        if (resume) {
+            it = (int)state[1]; pending = state[2]; best = state[3];
+            res.pres = state[4]; res.dres = state[5]; res.gap = state[6]; res.relgap = state[7]; res.pcost = state[8]; res.iterations = (int)state[9];
+        } else {
+            const int how = init_point(st_, have_prev);
+            if (how == 0) { res.status = 2; if (lane_id() == 0) state[0] = 0.; warp_sync(); return res; }
+            if (how == 2) budget -= 1;           // the least-squares start costs about one iteration
         }
         const double cnorm = sqrt(w_time * w_time + w_trs * w_trs + K * w_tr * w_tr + (K - 1) * NX * w_vc * w_vc);
         const double resx0 = fmax(1., cnorm);
@@ -1779,6 +2010,180 @@ struct Ipm {
         if (lane_id() == 0) state[0] = 0.;
         warp_sync();
         return res;
+    }
+
+    // =============================================================================================================
+    //  Split pipeline: one interior-point iteration as a SEQUENCE OF KERNELS, each with the mapping its work wants
+    //     start    (warp per new sub-problem)   starting point, residuals, first termination test
+    //     assemble (warp per (instance, stage)) H_kk | O_k | b_k of every stage, fully parallel
+    //     factor   (warp per instance)          block Cholesky chain over the assembled records
+    //     rhs / recover (warp per 32 stages)    stage-parallel passes, several warps per instance
+    //     chain    (warp per instance)          coupling, forward substitution, sigma rows, back substitution
+    //     update   (warp per 32 stages)         step + residuals of the next iterate
+    //     test     (warp per instance)          coupling + global rows of the residual, termination, bookkeeping
+    //  Scalars travel in `state` (per instance), per-warp partial sums in `part`.
+    //  state: [0] 0 idle / 1 mid-solve  [1] it  [2] pending (monolithic slices)  [3] best  [4..9] best iterate's result
+    //         [10] gap of the current iterate  [11] l_ss  [12] factorisation failed  [13..23] Glob of the running solve
+    // =============================================================================================================
+    static constexpr int ST_LSS = 11, ST_FAIL = 12, ST_GLOB = 13;
+    static constexpr int PT_ACC = 8, PT_GSIG = 9, PT_TAFF = 10, PT_TCMB = 11;
+    SCPP_HD int nparts() const { return (K + 31) / 32; }
+    SCPP_HD void set_part(int w) { k_lo = 32 * w; k_hi = (32 * w + 32 < K) ? 32 * w + 32 : K; }
+    SCPP_HD double part_sum(int slot) const { double v = 0; for (int w = 0; w < nparts(); w++) v += part[w * PSTR + slot]; return v; }
+    SCPP_HD double part_max(int slot) const { double v = 0; for (int w = 0; w < nparts(); w++) v = fmax(v, part[w * PSTR + slot]); return v; }
+    SCPP_HD int degree() const { return K * (NLP + NCN) + (K - 1) * 2 * NX + 2; }
+    // parameters of a solve: mode 1 = affine direction, mode 2 = combined direction (centering from the affine step length)
+    SCPP_HD void solve_params(int mode, const double *state, double &csig, double &sigmu, double &rzs) const
+    {
+        if (mode == 1) { csig = 1.; sigmu = 0.; rzs = -1.; return; }
+        const double tmax = part_max(PT_TAFF);
+        const double a_aff = tmax <= 1. ? 1. : 1. / tmax;
+        const double sig = (1. - a_aff) * (1. - a_aff) * (1. - a_aff), mu = state[10] / degree();
+        csig = 1. - sig; sigmu = sig * mu; rzs = -(1. - sig);
+    }
+    SCPP_HD void glob_store(double *state, const Glob &g) const
+    {
+        if (lane_id() == 0) {
+            double *q = state + ST_GLOB;
+            for (int i = 0; i < 4; i++) q[i] = g.rzg[i];
+            q[4] = g.rxg[0]; q[5] = g.rxg[1]; q[6] = g.kap_s; q[7] = g.p_s[0]; q[8] = g.p_s[1]; q[9] = g.p_s[2]; q[10] = g.ysig;
+        }
+    }
+    SCPP_HD void glob_load(const double *state, Glob &g) const
+    {
+        const double *q = state + ST_GLOB;
+        for (int i = 0; i < 4; i++) g.rzg[i] = q[i];
+        g.rxg[0] = q[4]; g.rxg[1] = q[5]; g.kap_s = q[6]; g.p_s[0] = q[7]; g.p_s[1] = q[8]; g.p_s[2] = q[9]; g.ysig = q[10];
+    }
+
+    SCPP_HD void sp_factor(double *state)
+    {
+        const bool ok = chain_factor();
+        if (lane_id() == 0) { state[ST_LSS] = l_ss; state[ST_FAIL] = ok ? 0. : 1.; }
+        warp_sync();
+    }
+    SCPP_HD void sp_rhs(int mode, const double *state, int w)
+    {
+        double csig, sigmu, rzs;
+        solve_params(mode, state, csig, sigmu, rzs);
+        set_part(w);
+        const double g = warp_sum(pass_rhs(mode, csig, sigmu, true));
+        if (lane_id() == 0) part[w * PSTR + PT_GSIG] = g;
+        warp_sync();
+    }
+    SCPP_HD void sp_chain(int mode, double *state)
+    {
+        double csig, sigmu, rzs;
+        solve_params(mode, state, csig, sigmu, rzs);
+        l_ss = state[ST_LSS];
+        rhs_couple();
+        const double gsig = part_sum(PT_GSIG);
+        const double ldot = warp_sum(chain_forward());
+        Glob g;
+        globals_mid(mode, csig, sigmu, gsig, ldot, g);
+        warp_sync();
+        chain_backward(g.ysig);
+        glob_store(state, g);
+        warp_sync();
+    }
+    SCPP_HD void sp_recover(int mode, const double *state, int w)
+    {
+        double csig, sigmu, rzs;
+        solve_params(mode, state, csig, sigmu, rzs);
+        Glob g;
+        glob_load(state, g);
+        set_part(w);
+        double tmax = pass_recover(mode, csig, rzs, g.ysig);
+        if (w == 0 && lane_id() == 0) tmax = fmax(tmax, globals_recover(mode, rzs, g));
+        tmax = warp_max(tmax);
+        if (lane_id() == 0) part[w * PSTR + (mode == 1 ? PT_TAFF : PT_TCMB)] = tmax;
+        warp_sync();
+    }
+    // step of the iterate; every warp of the instance must have finished it before sp_residuals reads its neighbours' stages
+    SCPP_HD void sp_update(int w)
+    {
+        const double tmax = part_max(PT_TCMB);
+        set_part(w);
+        pass_update(tmax <= 0.99 ? 1. : 0.99 / tmax);
+    }
+    SCPP_HD void sp_residuals(int w)
+    {
+        Norms nm;
+        set_part(w);
+        pass_residuals(nm, false, true);
+        if (lane_id() == 0) {
+            double *q = part + w * PSTR;
+            q[0] = nm.gap; q[1] = nm.rz2; q[2] = nm.pcost; q[3] = nm.zrz; q[4] = nm.rx2; q[5] = nm.xrx; q[6] = nm.h2; q[7] = nm.bad; q[PT_ACC] = nm.acc_sig;
+        }
+        warp_sync();
+    }
+    // termination test and bookkeeping of iterate `it` (the logic of the monolithic loop); returns true when the sub-problem is done
+    SCPP_HD bool test_and_book(const IpmSettings &st_, const Norms &nm, int it, bool factor_failed, double *state, IpmResult &res)
+    {
+        const int np = n_prim(K);
+        double best = (it == 0) ? 1e300 : state[3];
+        res.status = 1;
+        if (it == 0) { res.iterations = 0; res.pres = res.dres = res.gap = res.relgap = res.pcost = 0.; }
+        else { res.pres = state[4]; res.dres = state[5]; res.gap = state[6]; res.relgap = state[7]; res.pcost = state[8]; res.iterations = (int)state[9]; }
+        bool done = false;
+        double gap_cur = 0.;
+        if (factor_failed) { res.status = 2; done = true; }
+        else {
+            const double cnorm = sqrt(w_time * w_time + w_trs * w_trs + K * w_tr * w_tr + (K - 1) * NX * w_vc * w_vc);
+            const double resx0 = fmax(1., cnorm), resz0 = fmax(1., sqrt(nm.h2));
+            const double pres = sqrt(nm.rz2) / resz0, dres = sqrt(nm.rx2) / resx0, gap = nm.gap, pcost = nm.pcost;
+            const double dcost = pcost - gap + nm.zrz - nm.xrx;
+            double relgap = 1e300;
+            if (pcost < 0.) relgap = gap / -pcost; else if (dcost > 0.) relgap = gap / dcost;
+            const double score = fmax(fmax(pres, dres) / st_.feastol, fmin(gap / st_.abstol, relgap / st_.reltol));
+            if (!nm.bad && score < best) {
+                best = score;
+                res.pres = pres; res.dres = dres; res.gap = gap; res.relgap = relgap; res.pcost = pcost; res.iterations = it;
+                if (score <= 1e4) { FOR_LANE(e, np) best_[e] = prim[e]; }
+                warp_sync();
+            }
+            if (!nm.bad && pres <= st_.feastol && dres <= st_.feastol && (gap <= st_.abstol || relgap <= st_.reltol)) { res.status = 0; done = true; }
+            else if (nm.bad || it == st_.maxit || (score > 1e3 * best && best < 1e4) || (best <= 10. && score > best)) {
+                res.status = nm.bad ? 2 : (it == st_.maxit ? 1 : 2); done = true;
+            }
+            gap_cur = gap;
+        }
+        if (!done) {
+            if (lane_id() == 0) {
+                state[0] = 1.; state[1] = it; state[2] = 0.; state[3] = best;
+                state[4] = res.pres; state[5] = res.dres; state[6] = res.gap; state[7] = res.relgap; state[8] = res.pcost; state[9] = res.iterations;
+                state[10] = gap_cur; state[ST_FAIL] = 0.;
+            }
+            warp_sync();
+            return false;
+        }
+        if (res.status != 0) {
+            if (best <= 1e4) { FOR_LANE(e, np) prim[e] = best_[e]; }
+            warp_sync();
+            if (best <= 10.) res.status = 0; else if (best <= 1e4) res.status = 3;
+        } else res.iterations = it;
+        if (lane_id() == 0) state[0] = 0.;
+        warp_sync();
+        return true;
+    }
+    // start of a sub-problem (warp per instance): starting point, residuals, test of iterate 0
+    SCPP_HD bool sp_start(const IpmSettings &st_, bool have_prev, double *state, IpmResult &res)
+    {
+        tables_init();
+        Norms nm;
+        const int how = init_point(st_, have_prev);
+        if (how != 0) pass_residuals(nm, false);
+        return test_and_book(st_, nm, 0, how == 0, state, res);
+    }
+    // end of a round (warp per instance): finish the residual of the new iterate, test it
+    SCPP_HD bool sp_test(const IpmSettings &st_, double *state, IpmResult &res)
+    {
+        Norms nm;
+        nm.gap = part_sum(0); nm.rz2 = part_sum(1); nm.pcost = part_sum(2); nm.zrz = part_sum(3); nm.rx2 = part_sum(4); nm.xrx = part_sum(5);
+        nm.h2 = part_sum(6); nm.bad = part_max(7) != 0.; nm.acc_sig = part_sum(PT_ACC);
+        const bool failed = state[ST_FAIL] != 0.;
+        if (!failed) { residual_couple(nm); residual_globals(nm, false); }
+        return test_and_book(st_, nm, (int)state[1] + 1, failed, state, res);
     }
 };
 

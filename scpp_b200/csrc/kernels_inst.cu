@@ -1,0 +1,23 @@
+// scpp_b200/csrc/kernels_inst.cu — explicit instantiation of one group of kernels per translation unit.
+// Compile with -DSCPP_KERNEL_MODEL=0|1 (RocketQuat | Rocket2d) and -DSCPP_KERNEL_GROUP=0..4 (scpp_b200/build.py runs them in parallel).
+#define SCPP_KERNEL_INST 1
+#include "kernels.cuh"
+
+namespace scpp {
+#if SCPP_KERNEL_MODEL == 0
+#define SCPP_M RocketQuat
+#else
+#define SCPP_M Rocket2d
+#endif
+#if SCPP_KERNEL_GROUP == 0
+SCPP_GROUP0(, SCPP_M)
+#elif SCPP_KERNEL_GROUP == 1
+SCPP_GROUP1(, SCPP_M)
+#elif SCPP_KERNEL_GROUP == 2
+SCPP_GROUP2(, SCPP_M)
+#elif SCPP_KERNEL_GROUP == 3
+SCPP_GROUP3(, SCPP_M)
+#else
+SCPP_GROUP4(, SCPP_M)
+#endif
+} // namespace scpp

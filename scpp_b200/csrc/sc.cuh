@@ -81,32 +81,33 @@ SCPP_HD void sc_setup_instance(const ScArrays<M> &a, const ModelParamsHost &P, c
     }
 }
 
-// ---- K2 + K3: advance the sub-problem of instance n by one slice; when it is solved: readSolution and the convergence logic ----
-// SCAlgorithm::iterate, SCAlgorithm.cpp:78-131 (the defect print :85-92 is diagnostic only and not computed)
+// ---- binding of the solver object to instance n ------------------------------------------------------------------
 template <class M>
-SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n, double *smem)
+SCPP_HD void sc_bind(const ScArrays<M> &a, const ScConfig &cfg, int n, double *smem, Ipm<M> &ipm)
 {
     constexpr int NX = M::NX, NU = M::NU, NB = NX + NU, NC = NX + 2 * NU + 2;
     const int K = a.K;
-    Ipm<M> ipm;
     ipm.K = K;
     ipm.dd = a.dd + (size_t)n * (K - 1) * NX * NC;
     ipm.ddT = a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K);
-    double *X = a.X + (size_t)n * K * NX, *U = a.U + (size_t)n * K * NU;
-    ipm.Xbar = X; ipm.Ubar = U; ipm.sigbar = a.sigma[n];
+    ipm.Xbar = a.X + (size_t)n * K * NX; ipm.Ubar = a.U + (size_t)n * K * NU; ipm.sigbar = a.sigma[n];
     ipm.cst = a.cst + (size_t)n * MAX_CST;
     ipm.tdir = a.tdir + (size_t)n * K * 3;
     ipm.fixm = a.fixm + (size_t)n * K;
     ipm.fixv = a.fixv + (size_t)n * K * NB;
     ipm.w_time = cfg.weight_time; ipm.w_trs = cfg.weight_trust_region_time; ipm.w_vc = cfg.weight_virtual_control;
-    const double w_tr = a.w_tr[n];
-    ipm.w_tr = w_tr;
+    ipm.w_tr = a.w_tr[n];
     ipm.bind(a.ws + (size_t)n * a.ws_stride, smem);
-    const int it = a.iters[n];
-    bool finished;
-    const IpmResult r = ipm.solve(cfg.ipm, it > 0 && a.status[n] != 2, cfg.ipm_slice > 0 ? cfg.ipm_slice : (1 << 30),
-                                  a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE, finished);
-    if (!finished) return;                                                   // continues in the next launch
+}
+
+// ---- K3: readSolution and the convergence logic of SCAlgorithm::iterate (SCAlgorithm.cpp:100-131, 191-210) for a solved sub-problem
+template <class M>
+SCPP_HD void sc_finish_instance(const ScArrays<M> &a, const ScConfig &cfg, int n, const Ipm<M> &ipm, const IpmResult &r)
+{
+    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU;
+    const int K = a.K, it = a.iters[n];
+    double *X = a.X + (size_t)n * K * NX, *U = a.U + (size_t)n * K * NU;
+    const double w_tr = ipm.w_tr;
     double *inf = a.info + ((size_t)n * a.max_it + it) * INFO_STRIDE;
     const bool ok = (r.status == 0 || r.status == 3);
     warp_sync();
@@ -139,6 +140,55 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
         if (lane_id() == 0) h[K * NB] = ipm.sigma_val();
     }
     warp_sync();
+}
+
+// ---- K2 + K3, monolithic: advance the sub-problem of instance n by one slice; when it is solved: K3 ----
+// SCAlgorithm::iterate, SCAlgorithm.cpp:78-131 (the defect print :85-92 is diagnostic only and not computed)
+template <class M>
+SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n, double *smem)
+{
+    Ipm<M> ipm;
+    sc_bind(a, cfg, n, smem, ipm);
+    bool finished;
+    const IpmResult r = ipm.solve(cfg.ipm, a.iters[n] > 0 && a.status[n] != 2, cfg.ipm_slice > 0 ? cfg.ipm_slice : (1 << 30),
+                                  a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE, finished);
+    if (!finished) return;                                                   // continues in the next launch
+    sc_finish_instance(a, cfg, n, ipm, r);
+}
+
+// ---- K2 + K3, split pipeline (cfg.ipm_slice < 0): the steps of one interior-point iteration, each called by its own kernel ----
+enum ScStep { SP_START = 0, SP_ASSEMBLE, SP_FACTOR, SP_RHS, SP_CHAIN, SP_RECOVER, SP_UPDATE, SP_RESIDUALS, SP_TEST };
+// `sub`: stage (SP_ASSEMBLE) or 32-stage part (SP_RHS, SP_RECOVER, SP_UPDATE, SP_RESIDUALS); `mode`: 1 affine, 2 combined solve.
+// Every step except SP_START acts only on instances that are mid-solve and whose factorisation did not fail.
+template <class M, int STEP>
+SCPP_HD void sc_split_step(const ScArrays<M> &a, const ScConfig &cfg, int n, double *smem, int mode, int sub)
+{
+    double *state = a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE;
+    if (STEP == SP_START) { if (state[0] != 0.) return; }
+    else {
+        if (state[0] != 1.) return;
+        if (STEP != SP_ASSEMBLE && STEP != SP_FACTOR && STEP != SP_TEST && state[Ipm<M>::ST_FAIL] != 0.) return;
+    }
+    Ipm<M> ipm;
+    sc_bind(a, cfg, n, smem, ipm);
+    IpmResult r;
+    if (STEP == SP_START) {
+        if (ipm.sp_start(cfg.ipm, a.iters[n] > 0 && a.status[n] != 2, state, r)) sc_finish_instance(a, cfg, n, ipm, r);
+    } else if (STEP == SP_ASSEMBLE) {
+        if (sub >= a.K) return;
+        ipm.tables_init();
+        ipm.assemble_stage(sub);
+    } else if (STEP == SP_FACTOR) ipm.sp_factor(state);
+    else if (STEP == SP_CHAIN) ipm.sp_chain(mode, state);
+    else if (STEP == SP_TEST) { if (ipm.sp_test(cfg.ipm, state, r)) sc_finish_instance(a, cfg, n, ipm, r); }
+    else {
+        if (sub >= ipm.nparts()) return;
+        ipm.cst_init();
+        if (STEP == SP_RHS) ipm.sp_rhs(mode, state, sub);
+        else if (STEP == SP_RECOVER) ipm.sp_recover(mode, state, sub);
+        else if (STEP == SP_UPDATE) ipm.sp_update(sub);
+        else if (STEP == SP_RESIDUALS) ipm.sp_residuals(sub);
+    }
 }
 
 } // namespace scpp

@@ -65,9 +65,11 @@ def test_discretize_rocket2d_and_ragged_sizes(S):
             assert np.abs(got[key][0] - ref[key]).max() <= tol * max(1.0, np.abs(ref[key]).max()), (K, key)
 
 
-def _compare_run(S, name, model_o, params_list, K, max_it, tol_x=TOL_X, tol_u=TOL_U, xi=None, cfg_over=None, warm=0.0):
+def _compare_run(S, name, model_o, params_list, K, max_it, tol_x=TOL_X, tol_u=TOL_U, xi=None, cfg_over=None, warm=0.0, ipm_slice=None):
     model, params, x_init, x_final, cfg = S.load_model(name, K=K, max_iterations=max_it, keep_history=1, **(cfg_over or {}))
     cfg.ipm.warm = warm
+    if ipm_slice is not None:
+        cfg.ipm_slice = ipm_slice
     N = len(params_list)
     if xi is None:
         xi = np.array([list(p.x_init) for p in params_list])
@@ -141,6 +143,39 @@ def test_round_slicing_is_bit_identical(S):
             assert np.array_equal(a, b)
         assert np.array_equal(o[1], out[0][1])
         assert np.array_equal(o[2]["iterations"], out[0][2]["iterations"]) and np.array_equal(o[2]["flags"], out[0][2]["flags"])
+
+
+def test_split_pipeline_vs_oracle(S):
+    """the split pipeline (cfg.ipm_slice = -1: one kernel per step of the interior-point iteration, several warps per instance in the
+    stage-parallel passes) against the oracle: K=50 (two 32-stage parts), K=30 (one), K=100 (four), cold and interior warm starts"""
+    p, rpy = O.falcon9()
+    plist = [O.rq_perturb(p, rpy, 0x5C99, i) for i in range(20, 26)] + [p]
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=6, ipm_slice=-1)
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist[:4], K=50, max_it=15, warm=0.995, ipm_slice=-1)
+    _compare_run(S, "Rocket2D", O.ROCKET2D, [O.rocket2d()], K=30, max_it=15, warm=0.995, ipm_slice=-1)
+    ps, rpys = O.starship()
+    _compare_run(S, "RocketQuatStarship", O.ROCKETQUAT, [ps, O.rq_perturb(ps, rpys, 0x5C99, 1)], K=100, max_it=4, ipm_slice=-1)
+
+
+def test_split_pipeline_matches_monolithic_kernel(S):
+    """same algorithm, different decomposition over kernels and warps: identical iteration counts and decisions, iterates equal to
+    rounding (the partial sums are added in a different order)"""
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50, max_iterations=8, keep_history=1)
+    cfg.ipm.warm = 0.995
+    xi = S.perturbed_initial_states(x_init, np.deg2rad([-20.0, 20.0, 0.0]), 200)
+    out = []
+    for sl in (1, -1):
+        cfg.ipm_slice = sl
+        eng = S.SCAlgorithm(model, params, cfg, 200)
+        eng.set_boundary_states(xi, x_final)
+        eng.solve()
+        out.append((eng.get_all_solutions(), eng.get_info(), eng.get_solution()))
+        eng.close()
+    (Xa, Ua, ta), (Xb, Ub, tb) = out[0][0], out[1][0]
+    assert np.array_equal(out[0][2]["iterations"], out[1][2]["iterations"]) and np.array_equal(out[0][2]["flags"], out[1][2]["flags"])
+    assert np.abs(Xa - Xb).max() < 1e-5 and np.abs(Ua - Ub).max() < 1e-4
+    assert np.array_equal(out[0][1][:, :, 4], out[1][1][:, :, 4])                 # trust-region weights used
+    assert np.abs(out[0][1][:, :, 5] - out[1][1][:, :, 5]).max() <= 2          # interior-point iteration counts
 
 
 def test_sc_rocketquat_starship_k100(S):

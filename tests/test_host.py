@@ -130,7 +130,7 @@ def test_kernel_source_discretisation_vs_oracle():
     assert 8 < errs[0] / errs[1] < 24 and 8 < errs[1] / errs[2] < 24   # 4th-order convergence towards the RKF78 result
 
 
-@pytest.mark.parametrize("warm,ipm_slice", [(0.0, 1), (0.995, 1), (0.0, 0), (0.995, 3)])
+@pytest.mark.parametrize("warm,ipm_slice", [(0.0, 1), (0.995, 1), (0.0, 0), (0.995, 3), (0.0, -1), (0.995, -1)])
 @pytest.mark.parametrize("name,model,K,max_it", [("Rocket2D", 1, 30, 15), ("RocketQuat", 0, 20, 5)])
 def test_kernel_source_sc_loop_vs_oracle(name, model, K, max_it, warm, ipm_slice):
     """the K2/K3 source (structured IPM, one 'warp' of 1 lane) reproduces the literal ECOS-form oracle iterate by iterate"""
@@ -223,3 +223,15 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     assert a["n_act"] == b["n_act"] and a["tmax"] == b["tmax"] == 2.0
     assert a["iters"] == b["iters"] == a["local_iters"] + b["local_iters"]
     assert a["shape"] == [2, 3]
+
+
+def test_split_pipeline_two_parts_vs_monolithic_source():
+    """K = 50: the stage-parallel passes of the split pipeline run as two 32-stage parts with partial sums; same iterates as the
+    one-warp driver up to rounding, same iteration counts"""
+    p, _ = O.falcon9()
+    ocfg = O.sc_config(K=50, model=0, max_iterations=3)
+    P, xi, xf = H.params_from_oracle(0, p)
+    ref = H.sc_solve(0, P, H.sc_config(ocfg, tol=1e-8, warm=0.995, ipm_slice=1), xi, xf)
+    r = H.sc_solve(0, P, H.sc_config(ocfg, tol=1e-8, warm=0.995, ipm_slice=-1), xi, xf)
+    assert np.array_equal(r["iters"], ref["iters"]) and np.array_equal(r["info"][:, :, 5], ref["info"][:, :, 5])
+    assert np.abs(r["X_all"] - ref["X_all"]).max() < 1e-7 and np.abs(r["U_all"] - ref["U_all"]).max() < 1e-7
