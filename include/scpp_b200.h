@@ -68,7 +68,10 @@ typedef struct {
     int keep_history; /* keep every iterate for scpp_b200_get_iterate (SCAlgorithm::getAllSolutions) */
     int ipm_slice;    /* engine knob: interior-point iterations per K2 launch (default 1).  Between launches the engine re-forms
                          the batch, so an instance that needs 20 iterations does not hold back one that needs 5; 0 = run each
-                         sub-problem to the end in one launch (lock-step outer iterations).  Same arithmetic either way. */
+                         sub-problem to the end in one launch (lock-step outer iterations).  Same arithmetic either way.
+                         -1 = split pipeline (one kernel per step of the interior-point iteration, several warps per instance);
+                         -T (T > 1) = split pipeline only in rounds that advance fewer than T instances.  Same iterates up to the
+                         rounding of re-ordered sums. */
     scpp_b200_ipm_settings ipm;
 } scpp_b200_sc_config;
 

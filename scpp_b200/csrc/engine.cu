@@ -312,7 +312,10 @@ struct EngineT : scpp_b200_engine {
             CU(cudaEventRecord(ev[2], stream));
             const int n_active_round = n_active;
             const int parts = (K + 31) / 32;
-            const bool split = cfg.ipm_slice < 0 && parts <= 4;
+            // ipm_slice == -1: split pipeline in every round; ipm_slice == -T (T > 1): hybrid, split pipeline only in rounds that advance
+            // fewer than T instances (the tail of a solve, where one warp per instance leaves the GPU empty); both paths park the solver
+            // in the same state, so they can alternate round by round
+            const bool split = cfg.ipm_slice < 0 && parts <= 4 && (cfg.ipm_slice == -1 || n_active < -cfg.ipm_slice);
             if (split) {
                 // split pipeline: one interior-point iteration of every unfinished instance as a sequence of kernels (sc.cuh)
                 auto warp_launch = [&](auto kern, const int *list, int n, int mode) {

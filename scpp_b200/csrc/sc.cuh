@@ -150,7 +150,7 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
     Ipm<M> ipm;
     sc_bind(a, cfg, n, smem, ipm);
     bool finished;
-    const IpmResult r = ipm.solve(cfg.ipm, a.iters[n] > 0 && a.status[n] != 2, cfg.ipm_slice > 0 ? cfg.ipm_slice : (1 << 30),
+    const IpmResult r = ipm.solve(cfg.ipm, a.iters[n] > 0 && a.status[n] != 2, cfg.ipm_slice > 0 ? cfg.ipm_slice : (cfg.ipm_slice < 0 ? 1 : (1 << 30)),
                                   a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE, finished);
     if (!finished) return;                                                   // continues in the next launch
     sc_finish_instance(a, cfg, n, ipm, r);
