@@ -269,7 +269,7 @@ def main():
                 "config": {"workload": workload_name(args.K, n_local),
                            "batch_per_gpu": n_local, "global_batch": n_local * world, "K": args.K, "parallelism": f"instances sharded x{world}",
                            "l2": f"working set {eng.device_bytes() / 1e6:.0f} MB per GPU >> 126 MB L2 (no flush needed)",
-                           "integrator": f"RK4 x {cfg.nsub} (reference RKF78 x 5)", "ipm_tol": cfg.ipm.feastol, "ipm_warm": cfg.ipm.warm, "ipm_slice": cfg.ipm_slice},
+                           "integrator": (f"RK4 x {cfg.nsub}" if cfg.nsub > 0 else f"RK4 x {-cfg.nsub} and x {-2 * cfg.nsub}, Richardson-extrapolated") + " (reference RKF78 x 5)", "ipm_tol": cfg.ipm.feastol, "ipm_warm": cfg.ipm.warm, "ipm_slice": cfg.ipm_slice},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "ms_per_step": 1e3 * stats[1] / args.steps},
                 "gpu_launches": int(sums[2]),

@@ -64,7 +64,8 @@ typedef struct {
     double weight_time, weight_trust_region_time, weight_trust_region_trajectory, weight_virtual_control;
     double nu_tol, delta_tol;
     int max_iterations;
-    int nsub;         /* RK4 sub-steps per shooting interval (reference: RKF78 x 5, discretizationImplementation.hpp:154) */
+    int nsub;         /* RK4 sub-steps per shooting interval (reference: RKF78 x 5, discretizationImplementation.hpp:154);
+                         nsub < 0: RK4 with -nsub and with -2 nsub sub-steps, Richardson-extrapolated (default -5) */
     int keep_history; /* keep every iterate for scpp_b200_get_iterate (SCAlgorithm::getAllSolutions) */
     int ipm_slice;    /* engine knob: interior-point iterations per K2 launch (default 1).  Between launches the engine re-forms
                          the batch, so an instance that needs 20 iterations does not hold back one that needs 5; 0 = run each

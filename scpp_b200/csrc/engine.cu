@@ -475,7 +475,7 @@ void scpp_b200_default_config(int model, scpp_b200_sc_config *c)
     c->weight_trust_region_trajectory = model == SCPP_B200_MODEL_ROCKETQUAT ? 50. : 1.;
     c->weight_virtual_control = 1000.;
     c->nu_tol = 1e-5; c->delta_tol = 1e-3; c->max_iterations = 15;
-    c->nsub = 20; c->keep_history = 0; c->ipm_slice = 1;
+    c->nsub = -5; c->keep_history = 0; c->ipm_slice = 1;   // RK4 x 5 and x 10, Richardson-extrapolated: the accuracy of RK4 x 20 for 3/4 of the work
     c->ipm.feastol = 1e-8; c->ipm.abstol = 1e-8; c->ipm.reltol = 1e-8; c->ipm.maxit = 100;
 }
 
@@ -571,7 +571,7 @@ int scpp_b200_load_sc_info(const char *path, scpp_b200_sc_config *c)
 int scpp_b200_create(int model, const scpp_b200_model_params *params, const scpp_b200_sc_config *cfg, int n, int device, scpp_b200_engine **out)
 {
     if (!params || !cfg || !out || n <= 0) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: bad argument");
-    if (cfg->K < 3 || cfg->max_iterations < 1 || cfg->nsub < 1) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: K >= 3, max_iterations >= 1, nsub >= 1 required");
+    if (cfg->K < 3 || cfg->max_iterations < 1 || cfg->nsub == 0) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: K >= 3, max_iterations >= 1, nsub != 0 required");
     if (!cfg->free_final_time || !cfg->interpolate_input)
         return fail(SCPP_B200_ERR_UNSUPPORTED, "only free_final_time = true, interpolate_input = true (the shipped SC.info settings) are built");
     if (params->enable_roll_control) return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control = true is not built into this engine");
@@ -646,7 +646,7 @@ extern "C" {
 int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const double *X, const double *U, const double *sigma, const double *par,
                          double *A, double *B, double *C, double *s, double *z)
 {
-    if (K < 2 || n <= 0 || nsub < 1 || !X || !U || !sigma || !par || !A || !B || !C || !s || !z) return fail(SCPP_B200_ERR_ARG, "scpp_b200_discretize: bad argument");
+    if (K < 2 || n <= 0 || nsub == 0 || !X || !U || !sigma || !par || !A || !B || !C || !s || !z) return fail(SCPP_B200_ERR_ARG, "scpp_b200_discretize: bad argument");
     if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");
     if (model == SCPP_B200_MODEL_ROCKETQUAT) return discretize_hook<RocketQuat>(K, n, nsub, device, X, U, sigma, par, A, B, C, s, z);
     if (model == SCPP_B200_MODEL_ROCKET2D) return discretize_hook<Rocket2d>(K, n, nsub, device, X, U, sigma, par, A, B, C, s, z);

@@ -126,7 +126,9 @@ def test_kernel_source_discretisation_vs_oracle():
     for nsub in (5, 10, 20):
         got = H.discretize(0, X, U, t, par, nsub)
         errs.append(max(np.abs(got[k] - ref[k]).max() / max(1.0, np.abs(ref[k]).max()) for k in ("A", "B", "C", "s", "z")))
-    assert errs[2] < 2e-10                       # the shipped NSUB
+    assert errs[2] < 2e-10                       # RK4 x 20
+    rich = H.discretize(0, X, U, t, par, -5)     # the shipped integrator: RK4 x 5 and x 10, Richardson-extrapolated (60 instead of 80 evaluations)
+    assert max(np.abs(rich[k] - ref[k]).max() / max(1.0, np.abs(ref[k]).max()) for k in ("A", "B", "C", "s", "z")) < 2e-10
     assert 8 < errs[0] / errs[1] < 24 and 8 < errs[1] / errs[2] < 24   # 4th-order convergence towards the RKF78 result
 
 
