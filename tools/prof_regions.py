@@ -5,7 +5,10 @@ import csv, re, sys, collections, subprocess, os, tempfile
 rep, so, ksub = sys.argv[1:4]
 srcfile = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'scpp_b200', 'csrc', 'ipm.cuh')
 tmp = tempfile.mkdtemp()
-subprocess.check_call(f"cd {tmp} && cuobjdump -xelf all {os.path.abspath(so)} > /dev/null && nvdisasm -gi -c *.cubin > dis.txt", shell=True)
+# the library is linked from several objects whose embedded cubins share one name: extract each object on its own
+objs = sorted(os.path.join(os.path.dirname(os.path.abspath(so)), '_obj', f) for f in os.listdir(os.path.join(os.path.dirname(os.path.abspath(so)), '_obj')) if f.endswith('.o'))
+for i, o in enumerate(objs):
+    subprocess.check_call(f"mkdir -p {tmp}/o{i} && cd {tmp}/o{i} && cuobjdump -xelf all {o} > /dev/null && for f in *.cubin; do nvdisasm -gi -c $f; done >> {tmp}/dis.txt", shell=True)
 subprocess.check_call(f"ncu -i {rep} --page source --print-source sass --csv > {tmp}/sass.csv 2>/dev/null", shell=True)
 subprocess.check_call(f"ncu -i {rep} --page raw --csv > {tmp}/raw.csv 2>/dev/null", shell=True)
 # raw metrics
