@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128, 3) k_sp_stage(ScArrays<M> a, ScConfig cfg
 #define SCPP_ARGS_WARP(M) (ScArrays<M>, ScConfig, const int *, const int *, int, int)
 #define SCPP_ARGS_STAGE(M) (ScArrays<M>, ScConfig, const int *, int, int, int, int)
 #define SCPP_GROUP0(X, M) X template __global__ void k_solve<M, WPB_MAX, 1> SCPP_ARGS_SOLVE(M);
-#define SCPP_GROUP1(X, M) X template __global__ void k_solve<M, 4, 2> SCPP_ARGS_SOLVE(M);
+#define SCPP_GROUP1(X, M)
 #define SCPP_GROUP2(X, M) X template __global__ void k_sp_warp<M, SP_START, WPB_MAX> SCPP_ARGS_WARP(M);
 #define SCPP_GROUP3(X, M)                                                                  \
     X template __global__ void k_sp_warp<M, SP_FACTOR, WPB_MAX> SCPP_ARGS_WARP(M);          \
