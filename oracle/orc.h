@@ -127,6 +127,35 @@ int orc_sc_subproblem(int model, const void *params, const orc_sc_config *cfg, d
                       double *X, double *U, double *sigma, double *nu, double *delta,
                       double *norm1_nu, double *delta_sigma, orc_ipm_info *info);
 
+/* ---- SCvx variant (SCvx.info: SCvxAlgorithm.cpp:23-44) ---- */
+typedef struct {
+    int K;
+    int interpolate_input, nondimensionalize;
+    double rho_0, rho_1, rho_2, alpha, beta;
+    double change_threshold, weight_virtual_control, trust_region;
+    int max_iterations;
+} orc_scvx_config;
+
+/* per outer-iteration record (values of the LAST solve of the iteration) */
+typedef struct {
+    double norm1_nu, nonlinear_cost, actual_change, predicted_change, rho;
+    double trust_region_used, trust_region_next;
+    int solves;                 /* sub-problem solves in this iteration (1 + rejected steps) */
+    int pad_;
+    orc_ipm_info ipm;
+} orc_scvx_info;
+
+/* literal SCvxAlgorithm::solve() (SCvxAlgorithm.cpp:166-216) + iterate() (:61-164), cold start; same conventions as orc_sc_solve */
+int orc_scvx_solve(int model, const void *params, const orc_scvx_config *cfg,
+                   double *X_all, double *U_all, orc_scvx_info *info,
+                   double *X_out, double *U_out, double *t_out, int *converged);
+/* one SCvx sub-problem (buildSCvxProblem SCvxProblem.cpp:6-71 + addApplicationConstraints) around Ubar with trust-region radius */
+int orc_scvx_subproblem(int model, const void *params, int K, double weight_vc, double trust_region,
+                        const double *Ubar, const double *A, const double *B, const double *C, const double *z,
+                        const double *thrust_dir, double *X, double *U, double *nu, double *norm1_nu, orc_ipm_info *info);
+/* SCvxAlgorithm::getNonlinearCost (SCvxAlgorithm.cpp:262-278): sum_k |simulate(x_k; u_k, u_k+1) - x_k+1|_1 */
+double orc_scvx_nonlinear_cost(int model, int K, const double *X, const double *U, double t, const double *par);
+
 /* Export the ECOS standard form  min c'x  s.t. Ax=b, h-Gx in R+^l x Q...  of the same sub-problem
  * as COO triplets so a test can verify certificates independently (numpy).  Call with NULL arrays
  * first to get sizes.  Returns 0. */

@@ -23,7 +23,10 @@
 #define ABSTOL 1e-9
 #define RELTOL 1e-9
 #define MAXIT 100
-#define STATIC_REG 1e-13
+static double g_static_reg = 1e-13;   /* orc_set_static_reg(): the SCvx sub-problem has variables without any cone row and needs ECOS-sized regularisation */
+#define STATIC_REG g_static_reg
+void orc_set_static_reg(double v) { g_static_reg = v; }
+double orc_get_static_reg(void) { return g_static_reg; }
 #define STEP_FRAC 0.99
 #define EXPAND_THRESHOLD 48 /* LP rows with more nonzeros are kept as explicit KKT rows */
 

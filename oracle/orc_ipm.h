@@ -8,4 +8,7 @@ int orc_conic_solve_keys(int n, int p, int m, int l, int ncones, const int *q,
                          int nnzG, const int *Gi, const int *Gj, const double *Gv,
                          const double *keys_var, const double *keys_eq,
                          double *x, double *y, double *s, double *z, orc_ipm_info *info);
+/* static regularisation of the reduced KKT system (default 1e-13; not thread-safe to change while solves run) */
+void orc_set_static_reg(double v);
+double orc_get_static_reg(void);
 #endif

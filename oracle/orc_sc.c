@@ -49,6 +49,7 @@ static void dv_push(dvec_t *d, double v)
 
 typedef struct {
     int model, nx, nu, K, free_time;
+    int has_delta;              /* 1: SC (trust-region epigraph variable delta_k per stage), 0: SCvx */
     int n;                      /* variables */
     int stage_stride, stage_last_sz;
     int iN1, iSigma, iDsigma;
@@ -63,8 +64,8 @@ typedef struct {
 static int iX(const socp_t *P, int k, int i) { return k * P->stage_stride + i; }
 static int iU(const socp_t *P, int k, int i) { return k * P->stage_stride + P->nx + i; }
 static int iDelta(const socp_t *P, int k) { return k * P->stage_stride + P->nx + P->nu; }
-static int iNu(const socp_t *P, int k, int i) { return k * P->stage_stride + P->nx + P->nu + 1 + i; }
-static int iNub(const socp_t *P, int k, int i) { return k * P->stage_stride + 2 * P->nx + P->nu + 1 + i; }
+static int iNu(const socp_t *P, int k, int i) { return k * P->stage_stride + P->nx + P->nu + P->has_delta + i; }
+static int iNub(const socp_t *P, int k, int i) { return k * P->stage_stride + 2 * P->nx + P->nu + P->has_delta + i; }
 
 /* equality  sum coef*x = rhs ; key places the multiplier in the KKT ordering */
 static int eq_begin(socp_t *P, double rhs, double key) { dv_push(&P->b, rhs); dv_push(&P->keq, key); return P->b.n - 1; }
@@ -87,6 +88,7 @@ static void build_sc_problem(socp_t *P, const orc_sc_config *cfg, double weight_
                              const double *A, const double *B, const double *C, const double *s, const double *z)
 {
     const int nx = P->nx, nu = P->nu, K = P->K;
+    P->has_delta = 1;
     P->stage_stride = 2 * nx + nu + 1 + nx;
     P->n = (K - 1) * P->stage_stride + (nx + nu + 1);
     P->iN1 = P->n++;
@@ -379,6 +381,215 @@ int orc_sc_solve(int model, const void *params, const orc_sc_config *cfg,
     }
     if (converged_out) *converged_out = converged;
     free(X); free(U); free(tdir); free(A); free(B); free(C); free(s); free(z); free(delta);
+    return failed ? -iteration : iteration;
+}
+
+/* ================================================================================================================
+ * SCvx variant: buildSCvxProblem (scpp_core/src/SCvxProblem.cpp:6-71) + SCvxAlgorithm (scpp_core/src/SCvxAlgorithm.cpp)
+ * fixed final time, hard trust region on the inputs, ratio test against the nonlinear (simulated) cost
+ * ================================================================================================================ */
+double orc_scvx_static_reg = 2e-7;   /* test knob: tests/test_oracle.py varies it to show which parts of the optimum are unique */
+static void build_scvx_problem(socp_t *P, double weight_vc, double trust_region, const double *Ubar,
+                               const double *A, const double *B, const double *C, const double *z)
+{
+    const int nx = P->nx, nu = P->nu, K = P->K;
+    P->has_delta = 0;
+    P->stage_stride = nx + nu + nx + nx;                         /* x, u, nu, nu_bound  (:14-17) */
+    P->n = (K - 1) * P->stage_stride + (nx + nu);
+    P->iN1 = P->n++;                                             /* norm1_nu  :18 */
+    P->iSigma = P->iDsigma = -1;
+    P->c = (double *)calloc(P->n, sizeof(double));
+    for (int k = 0; k < K - 1; k++) {                            /* :20-40 */
+        const double *Ak = A + nx * nx * k, *Bk = B + nx * nu * k, *Ck = C + nx * nu * k, *zk = z + nx * k;
+        for (int i = 0; i < nx; i++) {
+            /* A x_k + B u_k + z + nu + C u_k+1 - x_k+1 = 0 */
+            int r = eq_begin(P, -zk[i], iNub(P, k, nx - 1) + 0.5);
+            for (int j = 0; j < nx; j++) if (Ak[i + nx * j] != 0.) coo_push(&P->A, r, iX(P, k, j), Ak[i + nx * j]);
+            for (int j = 0; j < nu; j++) if (Bk[i + nx * j] != 0.) coo_push(&P->A, r, iU(P, k, j), Bk[i + nx * j]);
+            for (int j = 0; j < nu; j++) if (Ck[i + nx * j] != 0.) coo_push(&P->A, r, iU(P, k + 1, j), Ck[i + nx * j]);
+            coo_push(&P->A, r, iNu(P, k, i), 1.);
+            coo_push(&P->A, r, iX(P, k + 1, i), -1.);
+        }
+    }
+    for (int k = 0; k < K - 1; k++)                              /* :49-50 */
+        for (int i = 0; i < nx; i++) {
+            int r = lp_begin(P, 0.); lp_coef(P, r, iNub(P, k, i), 1.); lp_coef(P, r, iNu(P, k, i), 1.);
+            r = lp_begin(P, 0.);     lp_coef(P, r, iNub(P, k, i), 1.); lp_coef(P, r, iNu(P, k, i), -1.);
+        }
+    {
+        int r = lp_begin(P, 0.);                                 /* sum(nu_bound) <= norm1_nu  :53 */
+        lp_coef(P, r, P->iN1, 1.);
+        for (int k = 0; k < K - 1; k++) for (int i = 0; i < nx; i++) lp_coef(P, r, iNub(P, k, i), -1.);
+        P->c[P->iN1] += weight_vc;                               /* :56 */
+    }
+    for (int k = 0; k < K; k++) {                                /* norm2(Ubar_k - u_k) <= trust_region  :59-68 (n_U = K with FOH) */
+        int r0 = soc_begin(P, 1 + nu);
+        soc_const(P, r0, trust_region);
+        for (int i = 0; i < nu; i++) { soc_const(P, r0 + 1 + i, Ubar[nu * k + i]); soc_coef(P, r0 + 1 + i, iU(P, k, i), -1.); }
+    }
+}
+
+int orc_scvx_subproblem(int model, const void *params, int K, double weight_vc, double trust_region,
+                        const double *Ubar, const double *A, const double *B, const double *C, const double *z,
+                        const double *thrust_dir, double *X, double *U, double *nu, double *norm1_nu, orc_ipm_info *info)
+{
+    socp_t P;
+    int np;
+    memset(&P, 0, sizeof(P));
+    P.model = model; P.K = K; P.free_time = 0;
+    orc_model_dims(model, &P.nx, &P.nu, &np);
+    build_scvx_problem(&P, weight_vc, trust_region, Ubar, A, B, C, z);
+    if (model == ORC_MODEL_ROCKETQUAT) add_rq_constraints(&P, (const orc_rq_params *)params, thrust_dir);   /* SCvxAlgorithm.cpp:56 */
+    else add_r2d_constraints(&P, (const orc_r2d_params *)params);
+    int *Gi, *Gj, nnzG, m, l; double *Gv, *h;
+    merged_G(&P, &Gi, &Gj, &Gv, &h, &nnzG, &m, &l);
+    double *x = (double *)calloc(P.n, sizeof(double)), *y = (double *)calloc(P.b.n, sizeof(double));
+    double *sv = (double *)calloc(m, sizeof(double)), *zv = (double *)calloc(m, sizeof(double));
+    double *kv = (double *)malloc(sizeof(double) * P.n);
+    for (int j = 0; j < P.n; j++) kv[j] = j;
+    /* elimination order of the quasi-definite KKT system (solver detail, not part of the problem): x_0 has no cone row in the SCvx
+     * problem, so it is eliminated AFTER the dynamics rows of interval 0, from which it inherits a positive definite block
+     * (every later x_k inherits one from the rows of interval k-1); its pinning equalities follow it */
+    {
+        const double k0 = iNub(&P, 0, P.nx - 1) + 0.5;
+        for (int r = 0; r < P.b.n; r++) {
+            const double key = P.keq.v[r];
+            if (key < P.nx && key != floor(key)) P.keq.v[r] = k0 + 0.001 * (floor(key) + 1.) + 0.0001 * (key - floor(key));
+        }
+        for (int j = 0; j < P.nx; j++) kv[j] = k0 + 0.001 * (j + 1.);
+    }
+    /* most states have no cone row here, so the KKT system is only quasi-definite through its static regularisation: use the
+     * size ECOS uses (2e-7, with iterative refinement against the unregularised system) instead of the SC path's 1e-13 */
+    const double reg_saved = orc_get_static_reg();
+    orc_set_static_reg(orc_scvx_static_reg);
+    int st = orc_conic_solve_keys(P.n, P.b.n, m, l, P.ncones, P.q, P.c, P.b.v, h, P.A.nnz, P.A.i, P.A.j, P.A.v,
+                                  nnzG, Gi, Gj, Gv, kv, P.keq.v, x, y, sv, zv, info);
+    orc_set_static_reg(reg_saved);
+    const int nx = P.nx, nuu = P.nu;
+    for (int k = 0; k < K; k++) {
+        if (X) for (int i = 0; i < nx; i++) X[nx * k + i] = x[iX(&P, k, i)];
+        if (U) for (int i = 0; i < nuu; i++) U[nuu * k + i] = x[iU(&P, k, i)];
+        if (nu && k < K - 1) for (int i = 0; i < nx; i++) nu[nx * k + i] = x[iNu(&P, k, i)];
+    }
+    if (norm1_nu) *norm1_nu = x[P.iN1];
+    free(x); free(y); free(sv); free(zv); free(kv); free(Gi); free(Gj); free(Gv); free(h);
+    socp_free(&P);
+    return st;
+}
+
+/* SCvxAlgorithm::getNonlinearCost, SCvxAlgorithm.cpp:262-278 */
+double orc_scvx_nonlinear_cost(int model, int K, const double *X, const double *U, double t, const double *par)
+{
+    int nx, nu, np;
+    orc_model_dims(model, &nx, &nu, &np);
+    double cost = 0.;
+    for (int k = 0; k < K - 1; k++) {
+        double x[ORC_MAX_NX];
+        memcpy(x, X + nx * k, sizeof(double) * nx);
+        orc_simulate(model, t / (K - 1), U + nu * k, U + nu * (k + 1), par, x);
+        for (int i = 0; i < nx; i++) cost += fabs(x[i] - X[nx * (k + 1) + i]);
+    }
+    return cost;
+}
+
+/* SCvxAlgorithm::solve (cold start) + iterate, SCvxAlgorithm.cpp:61-216.  The re-solve loop of a rejected step has no bound in the
+ * reference; the restatement stops an outer iteration after ORC_SCVX_MAX_RESOLVE solves and reports failure. */
+#define ORC_SCVX_MAX_RESOLVE 40
+int orc_scvx_solve(int model, const void *params, const orc_scvx_config *cfg,
+                   double *X_all, double *U_all, orc_scvx_info *info,
+                   double *X_out, double *U_out, double *t_out, int *converged_out)
+{
+    int nx, nu, np;
+    orc_model_dims(model, &nx, &nu, &np);
+    const int K = cfg->K;
+    orc_rq_params rq; orc_r2d_params r2;
+    const void *pp;
+    double par[ORC_MAX_NP];
+    double *X = (double *)malloc(sizeof(double) * K * nx), *U = (double *)malloc(sizeof(double) * K * nu), t;
+    double *Xo = (double *)malloc(sizeof(double) * K * nx), *Uo = (double *)malloc(sizeof(double) * K * nu);
+    double *tdir = (double *)calloc(3 * K, sizeof(double));
+    if (!cfg->interpolate_input) { fprintf(stderr, "orc: only interpolate_input=true is restated\n"); abort(); }
+    if (model == ORC_MODEL_ROCKETQUAT) {
+        rq = *(const orc_rq_params *)params;
+        if (cfg->nondimensionalize) orc_rq_nondimensionalize(&rq);                  /* :172-173 */
+        orc_rq_initial_trajectory(&rq, K, X, U, &t);                                /* :183 */
+        orc_rq_model_par(&rq, par);                                                 /* :186 */
+        for (int k = 0; k < K; k++) {                                               /* rocketQuat.cpp:162-165 */
+            const double *u = U + 4 * k; double n = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+            for (int i = 0; i < 3; i++) tdir[3 * k + i] = n > 0 ? u[i] / n : u[i];
+        }
+        pp = &rq;
+    } else {
+        r2 = *(const orc_r2d_params *)params;
+        if (cfg->nondimensionalize) orc_r2d_nondimensionalize(&r2);
+        orc_r2d_initial_trajectory(&r2, K, X, U, &t);
+        orc_r2d_model_par(&r2, par);
+        pp = &r2;
+    }
+    double trust_region = cfg->trust_region;                                        /* loadParameters() :182 */
+    double *A = (double *)malloc(sizeof(double) * (K - 1) * nx * nx), *B = (double *)malloc(sizeof(double) * (K - 1) * nx * nu);
+    double *C = (double *)malloc(sizeof(double) * (K - 1) * nx * nu), *z = (double *)malloc(sizeof(double) * (K - 1) * nx);
+    memcpy(X_all, X, sizeof(double) * K * nx); memcpy(U_all, U, sizeof(double) * K * nu);   /* :190 */
+    int iteration = 0, converged = 0, failed = 0, have_last = 0;
+    double last_nonlinear_cost = 0.;
+    while (iteration < cfg->max_iterations && !converged && !failed) {              /* :194-201 */
+        iteration++;
+        orc_scvx_info *inf = info ? info + (iteration - 1) : NULL;
+        if (inf) memset(inf, 0, sizeof(*inf));
+        orc_discretize(model, K, X, U, t, par, 1, 0, A, B, C, NULL, z);             /* :67 (fixed final time) */
+        int solves = 0;
+        for (;;) {                                                                  /* :73-146 */
+            memcpy(Xo, X, sizeof(double) * K * nx); memcpy(Uo, U, sizeof(double) * K * nu);     /* old_td :76 */
+            double norm1_nu;
+            orc_ipm_info ipm;
+            int st = orc_scvx_subproblem(model, pp, K, cfg->weight_virtual_control, trust_region, Uo, A, B, C, z,
+                                         model == ORC_MODEL_ROCKETQUAT ? tdir : NULL, X, U, NULL, &norm1_nu, &ipm);   /* :81, readSolution :94 */
+            solves++;
+            if (inf) { inf->ipm = ipm; inf->solves = solves; }
+            if (st != 0 || solves > ORC_SCVX_MAX_RESOLVE) { failed = 1; break; }    /* :87-91 (terminate) */
+            const double J = orc_scvx_nonlinear_cost(model, K, X, U, t, par);       /* :98 */
+            const double L = norm1_nu;                                              /* :100-108 */
+            if (inf) { inf->norm1_nu = norm1_nu; inf->nonlinear_cost = J; inf->trust_region_used = trust_region; }
+            if (!have_last) { last_nonlinear_cost = J; have_last = 1; break; }      /* :110-114 */
+            const double actual_change = last_nonlinear_cost - J, predicted_change = last_nonlinear_cost - L;   /* :116-117 */
+            last_nonlinear_cost = J;                                                /* :119 (also when the step is rejected below) */
+            if (inf) { inf->actual_change = actual_change; inf->predicted_change = predicted_change; }
+            if (fabs(predicted_change) < cfg->change_threshold) { converged = 1; break; }       /* :126-130 */
+            const double rho = actual_change / predicted_change;                    /* :132 */
+            if (inf) inf->rho = rho;
+            if (rho < cfg->rho_0) {                                                 /* :133-139 */
+                trust_region /= cfg->alpha;
+                memcpy(X, Xo, sizeof(double) * K * nx); memcpy(U, Uo, sizeof(double) * K * nu);
+            } else {                                                                /* :140-155 */
+                if (rho < cfg->rho_1) trust_region /= cfg->alpha;
+                else if (rho >= cfg->rho_2) trust_region *= cfg->beta;
+                break;
+            }
+        }
+        if (inf) inf->trust_region_next = trust_region;
+        memcpy(X_all + (size_t)iteration * K * nx, X, sizeof(double) * K * nx);     /* :200 */
+        memcpy(U_all + (size_t)iteration * K * nu, U, sizeof(double) * K * nu);
+    }
+    if (X_out) {                                                                    /* :214-219 */
+        memcpy(X_out, X, sizeof(double) * K * nx); memcpy(U_out, U, sizeof(double) * K * nu); *t_out = t;
+        if (cfg->nondimensionalize) {
+            if (model == ORC_MODEL_ROCKETQUAT) {
+                for (int k = 0; k < K; k++) {
+                    X_out[14 * k] *= rq.m_scale;
+                    for (int i = 1; i < 7; i++) X_out[14 * k + i] *= rq.r_scale;
+                    for (int i = 0; i < 3; i++) U_out[4 * k + i] *= rq.m_scale * rq.r_scale;
+                    U_out[4 * k + 3] *= rq.m_scale * rq.r_scale * rq.r_scale;
+                }
+            } else {
+                for (int k = 0; k < K; k++) {
+                    for (int i = 0; i < 4; i++) X_out[6 * k + i] *= r2.r_scale;
+                    U_out[2 * k + 1] *= r2.m_scale * r2.r_scale;
+                }
+            }
+        }
+    }
+    if (converged_out) *converged_out = converged;
+    free(X); free(U); free(Xo); free(Uo); free(tdir); free(A); free(B); free(C); free(z);
     return failed ? -iteration : iteration;
 }
 

@@ -237,3 +237,55 @@ def sc_config(K=50, model=ROCKETQUAT, max_iterations=15):
     c.weight_trust_region_trajectory = 50. if model == ROCKETQUAT else 1.
     c.weight_virtual_control = 1000.; c.nu_tol = 1e-5; c.delta_tol = 1e-3; c.max_iterations = max_iterations
     return c
+
+
+# ---- SCvx variant (oracle/orc_sc.c: orc_scvx_*) -----------------------------------------------------------------------
+class SCvxConfig(C.Structure):
+    _fields_ = [("K", C.c_int), ("interpolate_input", C.c_int), ("nondimensionalize", C.c_int),
+                ("rho_0", C.c_double), ("rho_1", C.c_double), ("rho_2", C.c_double), ("alpha", C.c_double), ("beta", C.c_double),
+                ("change_threshold", C.c_double), ("weight_virtual_control", C.c_double), ("trust_region", C.c_double),
+                ("max_iterations", C.c_int)]
+
+
+class SCvxInfo(C.Structure):
+    _fields_ = [("norm1_nu", C.c_double), ("nonlinear_cost", C.c_double), ("actual_change", C.c_double), ("predicted_change", C.c_double),
+                ("rho", C.c_double), ("trust_region_used", C.c_double), ("trust_region_next", C.c_double),
+                ("solves", C.c_int), ("pad_", C.c_int), ("ipm", IpmInfo)]
+
+
+def scvx_config(K=30, model=ROCKETQUAT, max_iterations=None):
+    """scpp_models/config/{RocketQuat,Rocket2D}/SCvx.info with K overridable"""
+    c = SCvxConfig()
+    c.K = K; c.interpolate_input = 1; c.nondimensionalize = 1 if model == ROCKETQUAT else 0
+    c.rho_0 = 0.0; c.rho_1 = 0.25; c.rho_2 = 0.9; c.alpha = 2.0; c.beta = 3.2
+    c.change_threshold = 1e-3 if model == ROCKETQUAT else 1e-2
+    c.weight_virtual_control = 1e3; c.trust_region = 5.
+    c.max_iterations = max_iterations if max_iterations is not None else (30 if model == ROCKETQUAT else 20)
+    return c
+
+
+def scvx_solve(model, params, cfg):
+    nx, nu, _ = DIMS[model]
+    K, M = cfg.K, cfg.max_iterations + 1
+    Xa = np.zeros((M, K, nx)); Ua = np.zeros((M, K, nu))
+    info = (SCvxInfo * cfg.max_iterations)()
+    Xo = np.zeros((K, nx)); Uo = np.zeros((K, nu)); to = C.c_double(); conv = C.c_int()
+    it = lib().orc_scvx_solve(model, C.byref(params), C.byref(cfg), _p(Xa), _p(Ua), info, _p(Xo), _p(Uo), C.byref(to), C.byref(conv))
+    n = abs(it)
+    return dict(iterations=it, converged=bool(conv.value), X_all=Xa[:n + 1], U_all=Ua[:n + 1], info=[info[i] for i in range(n)], X=Xo, U=Uo, t=to.value)
+
+
+def scvx_subproblem(model, params, K, weight_vc, trust_region, Ubar, dd, thrust_dir=None):
+    nx, nu, _ = DIMS[model]
+    A, B, Cc, s, z = dd_colmajor(dd)
+    X = np.zeros((K, nx)); U = np.zeros((K, nu)); nu_v = np.zeros((K - 1, nx)); n1 = C.c_double(); info = IpmInfo()
+    td = np.ascontiguousarray(thrust_dir, float) if thrust_dir is not None else None
+    st = lib().orc_scvx_subproblem(model, C.byref(params), K, C.c_double(weight_vc), C.c_double(trust_region), _p(np.ascontiguousarray(Ubar, float)),
+                                   _p(A), _p(B), _p(Cc), _p(z), _p(td), _p(X), _p(U), _p(nu_v), C.byref(n1), C.byref(info))
+    return dict(status=st, X=X, U=U, nu=nu_v, norm1_nu=n1.value, info=info)
+
+
+def scvx_nonlinear_cost(model, X, U, t, par):
+    lib().orc_scvx_nonlinear_cost.restype = C.c_double
+    return lib().orc_scvx_nonlinear_cost(model, X.shape[0], _p(np.ascontiguousarray(X, float)), _p(np.ascontiguousarray(U, float)), C.c_double(t),
+                                         _p(np.ascontiguousarray(par, float)))
