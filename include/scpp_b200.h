@@ -122,6 +122,14 @@ int scpp_b200_get_solution(scpp_b200_engine *e, double *X, double *U, double *t,
 int scpp_b200_get_iterate(scpp_b200_engine *e, int it, double *X, double *U, double *t);
 int scpp_b200_get_info(scpp_b200_engine *e, double *info /* [N][max_iterations][SCPP_B200_INFO_STRIDE] */);
 
+/* One step of the closed loop of scpp/src/SC_sim.cpp:47-61 for every instance (kernel K4): the first input of the current solution
+ * (u0 = U[0], u1 = interpolatedInput(U, time_step, t), scpp/src/commonFunctions.cpp:6-19) is applied to the nonlinear model for
+ * time_step seconds (scpp::simulate, scpp_core/src/simulation.cpp:31-42: RKF78, time_step/20), x_init <- simulated state ON THE DEVICE.
+ * The next scpp_b200_solve(e, 1) continues from it.  Outputs (host, optional): x_new [N][nx], u0 [N][nu] (dimensional),
+ * reached [N] = |x - x_final| < 0.02 or t < 0.25 (SC_sim.cpp:58); an instance that reached the end is frozen: later solves and
+ * steps skip it (flag 8) until scpp_b200_set_boundary_states is called again. */
+int scpp_b200_sim_step(scpp_b200_engine *e, double time_step, double *x_new, double *u0, int *reached);
+
 /* device timing of the last solve (CUDA events on the engine stream): ms in K1, ms in K2, ms total, kernel launches,
  * outer iterations executed, sum over instances of iterations executed */
 int scpp_b200_last_timing(scpp_b200_engine *e, double *ms_discretize, double *ms_socp, double *ms_total,
@@ -140,6 +148,9 @@ int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const do
 
 /* the tensor-core block products of K2 (mma.sync.m8n8k4.f64, scpp_b200/csrc/blockops.cuh) checked on the device against scalar
  * loops for the shapes the factorisation uses; returns the largest absolute deviation (no reference counterpart) */
+/* K4 alone: scpp::simulate (simulation.cpp:31-42) for n states.  x [n][nx] in/out, u0, u1 [n][nu], par [n][np] */
+int scpp_b200_simulate(int model, int n, double dt, int device, double *x, const double *u0, const double *u1, const double *par);
+
 int scpp_b200_selftest_blockops(int device, double *max_abs_err);
 
 /* ---- multi-GPU: one process (rank) per GPU, the batch is sharded by the caller ----------------------------------

@@ -115,6 +115,16 @@ int orc_sc_solve(int model, const void *params, const orc_sc_config *cfg,
                  double *X_all, double *U_all, double *t_all, orc_iter_info *info,
                  double *X_out, double *U_out, double *t_out, int *converged);
 
+/* SCAlgorithm::solve(warm_start): as orc_sc_solve, optionally warm-started from a DIMENSIONAL trajectory (X_warm != NULL) with the
+ * trust-region weight carried in *weight_tr_io (in/out; NULL = SC.info value) */
+int orc_sc_solve2(int model, const void *params, const orc_sc_config *cfg,
+                  const double *X_warm, const double *U_warm, double t_warm, double *weight_tr_io,
+                  double *X_all, double *U_all, double *t_all, orc_iter_info *info,
+                  double *X_out, double *U_out, double *t_out, int *converged);
+/* SC_sim closed loop (scpp/src/SC_sim.cpp:28-65) */
+int orc_sc_sim(int model, const void *params, const orc_sc_config *cfg, double time_step, int max_steps,
+               double *X_sim, double *U_sim, int *iters, int *reached_end);
+
 /* One SOCP sub-problem (buildSCProblem SCProblem.cpp:6-138 + addApplicationConstraints
  * rocketQuat.cpp:70-144 / rocket2d.cpp:46-84) around (Xbar,Ubar,sigmabar) with given dd.
  * params must already be in the units of Xbar (i.e. nondimensional if the trajectory is).

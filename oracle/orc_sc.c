@@ -305,6 +305,17 @@ int orc_sc_solve(int model, const void *params, const orc_sc_config *cfg,
                  double *X_all, double *U_all, double *t_all, orc_iter_info *info,
                  double *X_out, double *U_out, double *t_out, int *converged_out)
 {
+    return orc_sc_solve2(model, params, cfg, NULL, NULL, 0., NULL, X_all, U_all, t_all, info, X_out, U_out, t_out, converged_out);
+}
+
+/* SCAlgorithm::solve(warm_start) (SCAlgorithm.cpp:134-189).  X_warm != NULL: warm start from the DIMENSIONAL trajectory
+ * (X_warm, U_warm, t_warm) of a previous solve -- it is nondimensionalised with the scales of the CURRENT x_init (:141-145) and
+ * loadParameters() is not called, so the trust-region weight carries over: *weight_tr_io in/out (NULL: SC.info value, not returned). */
+int orc_sc_solve2(int model, const void *params, const orc_sc_config *cfg,
+                  const double *X_warm, const double *U_warm, double t_warm, double *weight_tr_io,
+                  double *X_all, double *U_all, double *t_all, orc_iter_info *info,
+                  double *X_out, double *U_out, double *t_out, int *converged_out)
+{
     int nx, nu, np;
     orc_model_dims(model, &nx, &nu, &np);
     const int K = cfg->K;
@@ -316,7 +327,16 @@ int orc_sc_solve(int model, const void *params, const orc_sc_config *cfg,
     if (model == ORC_MODEL_ROCKETQUAT) {
         rq = *(const orc_rq_params *)params;
         if (cfg->nondimensionalize) orc_rq_nondimensionalize(&rq);                  /* :138-139 */
-        orc_rq_initial_trajectory(&rq, K, X, U, &t);                                /* :149 */
+        if (X_warm) {                                                               /* :141-145, rocketQuat.cpp:175-186 */
+            memcpy(X, X_warm, sizeof(double) * K * nx); memcpy(U, U_warm, sizeof(double) * K * nu); t = t_warm;
+            if (cfg->nondimensionalize)
+                for (int k = 0; k < K; k++) {
+                    X[14 * k] /= rq.m_scale;
+                    for (int i = 1; i < 7; i++) X[14 * k + i] /= rq.r_scale;
+                    for (int i = 0; i < 3; i++) U[4 * k + i] /= rq.m_scale * rq.r_scale;
+                    U[4 * k + 3] /= rq.m_scale * rq.r_scale * rq.r_scale;
+                }
+        } else orc_rq_initial_trajectory(&rq, K, X, U, &t);                         /* :149 */
         orc_rq_model_par(&rq, par);                                                 /* :152 */
         for (int k = 0; k < K; k++) {                                               /* rocketQuat.cpp:162-165 */
             const double *u = U + 4 * k; double n = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
@@ -326,11 +346,18 @@ int orc_sc_solve(int model, const void *params, const orc_sc_config *cfg,
     } else {
         r2 = *(const orc_r2d_params *)params;
         if (cfg->nondimensionalize) orc_r2d_nondimensionalize(&r2);
-        orc_r2d_initial_trajectory(&r2, K, X, U, &t);
+        if (X_warm) {                                                               /* rocket2d.cpp:97-107 */
+            memcpy(X, X_warm, sizeof(double) * K * nx); memcpy(U, U_warm, sizeof(double) * K * nu); t = t_warm;
+            if (cfg->nondimensionalize)
+                for (int k = 0; k < K; k++) {
+                    for (int i = 0; i < 4; i++) X[6 * k + i] /= r2.r_scale;
+                    U[2 * k + 1] /= r2.m_scale * r2.r_scale;
+                }
+        } else orc_r2d_initial_trajectory(&r2, K, X, U, &t);
         orc_r2d_model_par(&r2, par);
         pp = &r2;
     }
-    double weight_tr = cfg->weight_trust_region_trajectory;                         /* :148 loadParameters() */
+    double weight_tr = (X_warm && weight_tr_io) ? *weight_tr_io : cfg->weight_trust_region_trajectory;   /* :148 loadParameters() only on a cold start */
     double *A = (double *)malloc(sizeof(double) * (K - 1) * nx * nx), *B = (double *)malloc(sizeof(double) * (K - 1) * nx * nu);
     double *C = (double *)malloc(sizeof(double) * (K - 1) * nx * nu), *s = (double *)malloc(sizeof(double) * (K - 1) * nx), *z = (double *)malloc(sizeof(double) * (K - 1) * nx);
     double *delta = (double *)malloc(sizeof(double) * K);
@@ -380,9 +407,64 @@ int orc_sc_solve(int model, const void *params, const orc_sc_config *cfg,
         }
     }
     if (converged_out) *converged_out = converged;
+    if (weight_tr_io) *weight_tr_io = weight_tr;
     free(X); free(U); free(tdir); free(A); free(B); free(C); free(s); free(z); free(delta);
     return failed ? -iteration : iteration;
 }
+
+/* scpp::interpolatedInput, scpp/src/commonFunctions.cpp:6-19 */
+static void interpolated_input(const double *U, int K, int nu, double t, double total_time, int foh, double *u)
+{
+    const double time_step = total_time / (K - 1);
+    size_t i = (size_t)(t / time_step);
+    if (i > (size_t)(K - 2)) i = K - 2;
+    const double *u0 = U + nu * i, *u1 = foh ? U + nu * (i + 1) : u0;
+    const double ti = fmod(t, time_step) / time_step;
+    for (int j = 0; j < nu; j++) u[j] = u0[j] + (u1[j] - u0[j]) * ti;
+}
+
+/* SC_sim (scpp/src/SC_sim.cpp:28-65): closed loop  solve(warm) -> apply the first input for time_step on the nonlinear model -> new x_init.
+ * X_sim [max_steps][nx], U_sim [max_steps][nu] (dimensional), iters [max_steps] SC iterations of each solve.  Returns the number of
+ * simulated steps written; *reached_end as in :56-61; negative on solver failure. */
+int orc_sc_sim(int model, const void *params, const orc_sc_config *cfg, double time_step, int max_steps,
+               double *X_sim, double *U_sim, int *iters, int *reached_end_out)
+{
+    int nx, nu, np;
+    orc_model_dims(model, &nx, &nu, &np);
+    const int K = cfg->K;
+    orc_rq_params rq; orc_r2d_params r2;
+    void *pp; double *x_init; const double *x_final;
+    if (model == ORC_MODEL_ROCKETQUAT) { rq = *(const orc_rq_params *)params; pp = &rq; x_init = rq.x_init; x_final = rq.x_final; }
+    else { r2 = *(const orc_r2d_params *)params; pp = &r2; x_init = r2.x_init; x_final = r2.x_final; }
+    double *X = (double *)malloc(sizeof(double) * K * nx), *U = (double *)malloc(sizeof(double) * K * nu), t = 0.;
+    double *Xa = (double *)malloc(sizeof(double) * (cfg->max_iterations + 1) * K * nx), *Ua = (double *)malloc(sizeof(double) * (cfg->max_iterations + 1) * K * nu);
+    double *ta = (double *)malloc(sizeof(double) * (cfg->max_iterations + 1));
+    double weight_tr = cfg->weight_trust_region_trajectory;
+    int sim_step = 0, written = 0, reached_end = 0, failed = 0;
+    while (sim_step < max_steps) {                                                  /* :41 */
+        const int warm = sim_step > 0;                                              /* :45 */
+        int conv;
+        int it = orc_sc_solve2(model, pp, cfg, warm ? X : NULL, warm ? U : NULL, t, &weight_tr, Xa, Ua, ta, NULL, X, U, &t, &conv);   /* :46-47 */
+        if (iters) iters[sim_step] = it;
+        if (it < 0) { failed = 1; break; }
+        double u1[ORC_MAX_NU], par[ORC_MAX_NP];
+        interpolated_input(U, K, nu, time_step, t, cfg->interpolate_input, u1);     /* :49-51 */
+        if (model == ORC_MODEL_ROCKETQUAT) orc_rq_model_par(&rq, par); else orc_r2d_model_par(&r2, par);   /* dimensional again after :182-186 */
+        orc_simulate(model, time_step, U, u1, par, x_init);                         /* :53  (x aliases model->p.x_init, :37) */
+        memcpy(X_sim + (size_t)written * nx, x_init, sizeof(double) * nx);          /* :55-56 */
+        memcpy(U_sim + (size_t)written * nu, U, sizeof(double) * nu);
+        written++;
+        double d2 = 0;
+        for (int i = 0; i < nx; i++) d2 += (x_init[i] - x_final[i]) * (x_init[i] - x_final[i]);
+        reached_end = sqrt(d2) < 0.02 || t < 0.25;                                  /* :58 */
+        if (reached_end) break;
+        sim_step++;
+    }
+    if (reached_end_out) *reached_end_out = reached_end;
+    free(X); free(U); free(Xa); free(Ua); free(ta);
+    return failed ? -written - 1 : written;
+}
+
 
 /* ================================================================================================================
  * SCvx variant: buildSCvxProblem (scpp_core/src/SCvxProblem.cpp:6-71) + SCvxAlgorithm (scpp_core/src/SCvxAlgorithm.cpp)

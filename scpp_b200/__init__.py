@@ -222,6 +222,12 @@ class SCAlgorithm:
         return dict(ms_discretize=a.value, ms_socp=b.value, ms_total=c.value, kernel_launches=l.value, outer_iterations=o.value,
                     instance_iterations=ii.value)
 
+    def sim_step(self, time_step=0.05):
+        """one closed-loop step (scpp/src/SC_sim.cpp:47-61): x_init <- simulate(x_init, u0, u1, time_step) on the device"""
+        x = np.empty((self.N, self.nx)); u = np.empty((self.N, self.nu)); r = np.empty(self.N, np.int32)
+        _check(lib().scpp_b200_sim_step(self._h, C.c_double(time_step), _p(x), _p(u), _p(r)))
+        return dict(x=x, u0=u, reached=r)
+
     def last_rounds(self):
         r, ir = C.c_int(), C.c_longlong()
         _check(lib().scpp_b200_last_rounds(self._h, C.byref(r), C.byref(ir)))
@@ -249,6 +255,14 @@ def selftest_blockops(device=0):
     err = C.c_double()
     _check(lib().scpp_b200_selftest_blockops(device, C.byref(err)))
     return err.value
+
+
+def simulate(model, x, u0, u1, par, dt, device=0):
+    """K4 alone: scpp::simulate for n states (x [n][nx], u0/u1 [n][nu], par [n][np] or one row)"""
+    x = np.ascontiguousarray(np.atleast_2d(x), float).copy(); n = x.shape[0]
+    bc = lambda a: np.ascontiguousarray(np.broadcast_to(np.atleast_2d(np.asarray(a, float)), (n, np.atleast_2d(a).shape[1])))
+    _check(lib().scpp_b200_simulate(model, n, C.c_double(dt), device, _p(x), _p(bc(u0)), _p(bc(u1)), _p(bc(par))))
+    return x
 
 
 def discretize(model, X, U, sigma, par, nsub=20, device=0):

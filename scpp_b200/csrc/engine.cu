@@ -36,34 +36,35 @@ __global__ void k_setup(ScArrays<M> a, ModelParamsHost P, ScConfig cfg)
     if (n < a.N) sc_setup_instance<M>(a, P, cfg, n);
 }
 
-// SCAlgorithm::solve(warm_start = true), SCAlgorithm.cpp:141-145,152: keep the trajectory (re-nondimensionalised with the
-// scales of the NEW x_init), keep the trust-region weight, refresh parameters and the minimum-thrust directions
 template <class M>
 __global__ void k_warm(ScArrays<M> a, ModelParamsHost P, ScConfig cfg)
 {
-    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= a.N) return;
-    const int K = a.K;
-    double *X = a.X + (size_t)n * K * NX, *U = a.U + (size_t)n * K * NU;
-    double old_scale[2] = {a.scale[2 * n], a.scale[2 * n + 1]};
-    for (int k = 0; k < K; k++) M::redim(old_scale, X + k * NX, U + k * NU);
-    double *xi = a.xi + (size_t)n * NX, *xf = a.xf + (size_t)n * NX;
-    for (int i = 0; i < NX; i++) { xi[i] = a.x_init[(size_t)n * NX + i]; xf[i] = a.x_final[(size_t)n * NX + i]; }
-    M::setup(P, cfg.nondimensionalize, xi, xf, a.par + (size_t)n * M::NP, a.cst + (size_t)n * MAX_CST, a.scale + (size_t)n * 2);
-    for (int k = 0; k < K; k++) {
-        M::nondim(a.scale + 2 * n, X + k * NX, U + k * NU);
-        a.fixm[(size_t)n * K + k] = M::fixed(P, xi, xf, K, k, a.fixv + ((size_t)n * K + k) * NB);
-        double *td = a.tdir + ((size_t)n * K + k) * 3;
-        if (P.exact_minimum_thrust) M::thrust_dir(U + k * NU, td); else { td[0] = 0.; td[1] = 0.; td[2] = 1.; }
-    }
-    a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
-    a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.;
-    if (a.hist) {
-        double *h = a.hist + (size_t)n * (a.max_it + 1) * a.hist_stride();
-        for (int k = 0; k < K; k++) { for (int i = 0; i < NX; i++) h[k * NB + i] = X[k * NX + i]; for (int i = 0; i < NU; i++) h[k * NB + NX + i] = U[k * NU + i]; }
-        h[K * NB] = a.sigma[n];
-    }
+    if (n < a.N && !(a.frozen && a.frozen[n])) sc_warm_instance<M>(a, P, cfg, n);
+}
+
+// K4: one closed-loop step per instance (thread per instance)
+template <class M>
+__global__ void k_sim_step(ScArrays<M> a, ModelParamsHost P, ScConfig cfg, double time_step, double *x_out, double *u_out, int *reached)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < a.N) sc_sim_step_instance<M>(a, P, cfg, n, time_step, x_out ? x_out + (size_t)n * M::NX : nullptr, u_out ? u_out + (size_t)n * M::NU : nullptr,
+                                         reached ? reached + n : nullptr);
+}
+// K4 test hook: plain simulate for n independent states
+template <class M>
+__global__ void k_simulate(int n, double dt, double *x, const double *u0, const double *u1, const double *par)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rkf78_simulate<M>(x + (size_t)i * M::NX, u0 + (size_t)i * M::NU, u1 + (size_t)i * M::NU, par + (size_t)i * M::NP, dt, 20);
+}
+// first active list of a solve: every instance that is not frozen
+__global__ void k_first_list(int *list, int *count, const int *frozen, int *converged, unsigned char *flags, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (frozen && frozen[i]) { converged[i] = 8; flags[i] = 8; return; }
+    list[atomicAdd(count, 1)] = i;
 }
 
 #include "kernels.cuh"
@@ -184,6 +185,7 @@ struct scpp_b200_engine {
     virtual int get_solution(double *X, double *U, double *t, int *it, int *flags) = 0;
     virtual int get_iterate(int it, double *X, double *U, double *t) = 0;
     virtual int get_info(double *info) = 0;
+    virtual int sim_step(double time_step, double *x_new, double *u0, int *reached) = 0;
     int model = 0, N = 0, device = 0;
     ModelParamsHost P;
     ScConfig cfg;
@@ -207,6 +209,8 @@ struct EngineT : scpp_b200_engine {
     unsigned long long *gcount = nullptr;
     unsigned char *flags = nullptr, *flags_all = nullptr;
     double *Xo = nullptr, *Uo = nullptr;
+    double *sim_x = nullptr, *sim_u = nullptr;   // outputs of the closed-loop step (K4)
+    int *sim_r = nullptr;
     int *h_counter = nullptr;             // pinned
     unsigned long long *h_gcount = nullptr;
     std::vector<void *> allocs;
@@ -253,7 +257,7 @@ struct EngineT : scpp_b200_engine {
         DA(a.info, (size_t)N * cfg.max_iterations * INFO_STRIDE);
         a.hist = nullptr;
         if (cfg.keep_history) DA(a.hist, (size_t)N * (cfg.max_iterations + 1) * a.hist_stride());
-        DA(active[0], N); DA(active[1], N); DA(disc, N); DA(counter, 2); DA(a.ipm_state, (size_t)N * Ipm<M>::IPM_STATE); DA(gcount, 1); DA(flags, N);
+        DA(active[0], N); DA(active[1], N); DA(disc, N); DA(counter, 2); DA(a.ipm_state, (size_t)N * Ipm<M>::IPM_STATE); DA(gcount, 1); DA(flags, N); DA(a.frozen, N); DA(sim_x, (size_t)N * NX); DA(sim_u, (size_t)N * NU); DA(sim_r, N);
         DA(Xo, (size_t)N * K * NX); DA(Uo, (size_t)N * K * NU);
 #undef DA
         CU(cudaMallocHost((void **)&h_counter, 2 * sizeof(int)));
@@ -275,6 +279,7 @@ struct EngineT : scpp_b200_engine {
         CU(cudaSetDevice(device));
         CU(cudaMemcpyAsync(a.x_init, xi, (size_t)N * NX * sizeof(double), cudaMemcpyHostToDevice, stream));
         CU(cudaMemcpyAsync(a.x_final, xf, (size_t)N * NX * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CU(cudaMemsetAsync(a.frozen, 0, (size_t)N * sizeof(int), stream));
         CU(cudaStreamSynchronize(stream));
         have_states = true;
         return 0;
@@ -288,11 +293,14 @@ struct EngineT : scpp_b200_engine {
         launches = 0; outer = 0; ms_disc = ms_socp = 0; inst_iters = 0; rounds = 0; inst_rounds = 0;
         CU(cudaEventRecord(ev[0], stream));
         if (warm) k_warm<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg);
-        else k_setup<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg);
-        k_iota<<<(N + 255) / 256, 256, 0, stream>>>(active[0], N);
-        launches += 2;
+        else { CU(cudaMemsetAsync(a.frozen, 0, (size_t)N * sizeof(int), stream)); k_setup<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg); }
         CU(cudaMemsetAsync(flags, 0, N, stream));
-        int n_active = N, n_disc = N, cur = 0;
+        CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), stream));
+        k_first_list<<<(N + 255) / 256, 256, 0, stream>>>(active[0], counter, warm ? a.frozen : nullptr, a.converged, flags, N);   // all but the frozen instances
+        launches += 2;
+        CU(cudaMemcpyAsync(h_counter, counter, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        int n_active = h_counter[0], n_disc = h_counter[0], cur = 0;
         const int *disc_list = active[0];                         // first round: every instance starts its first sub-problem
         global_active = (long long)N * nranks;
         // Rounds.  A round (1) discretises the instances that start a new sub-problem (K1), (2) advances EVERY unfinished
@@ -435,6 +443,20 @@ struct EngineT : scpp_b200_engine {
         }
         return 0;
     }
+    // one step of the closed loop of scpp/src/SC_sim.cpp for every instance: K4 advances x_init on the device; the next solve(warm) uses it
+    int sim_step(double time_step, double *x_new, double *u0, int *reached) override
+    {
+        if (!solved_once) return fail(SCPP_B200_ERR_ARG, "scpp_b200_sim_step: no solution yet");
+        if (!(time_step > 0.)) return fail(SCPP_B200_ERR_ARG, "scpp_b200_sim_step: time_step must be positive");
+        CU(cudaSetDevice(device));
+        k_sim_step<M><<<(N + 63) / 64, 64, 0, stream>>>(a, P, cfg, time_step, sim_x, sim_u, sim_r);
+        if (x_new) CU(cudaMemcpyAsync(x_new, sim_x, (size_t)N * NX * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (u0) CU(cudaMemcpyAsync(u0, sim_u, (size_t)N * NU * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (reached) CU(cudaMemcpyAsync(reached, sim_r, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        return 0;
+    }
     int get_info(double *info) override
     {
         CU(cudaSetDevice(device));
@@ -442,6 +464,22 @@ struct EngineT : scpp_b200_engine {
         return 0;
     }
 };
+
+template <class M>
+static int simulate_hook(int n, double dt, int device, double *x, const double *u0, const double *u1, const double *par)
+{
+    CU(cudaSetDevice(device));
+    double *dx = nullptr, *d0 = nullptr, *d1 = nullptr, *dp = nullptr;
+    CU(cudaMalloc((void **)&dx, sizeof(double) * n * M::NX)); CU(cudaMalloc((void **)&d0, sizeof(double) * n * M::NU));
+    CU(cudaMalloc((void **)&d1, sizeof(double) * n * M::NU)); CU(cudaMalloc((void **)&dp, sizeof(double) * n * M::NP));
+    CU(cudaMemcpy(dx, x, sizeof(double) * n * M::NX, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d0, u0, sizeof(double) * n * M::NU, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d1, u1, sizeof(double) * n * M::NU, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dp, par, sizeof(double) * n * M::NP, cudaMemcpyHostToDevice));
+    k_simulate<M><<<(n + 63) / 64, 64>>>(n, dt, dx, d0, d1, dp);
+    CU(cudaMemcpy(x, dx, sizeof(double) * n * M::NX, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(d0); cudaFree(d1); cudaFree(dp);
+    CU(cudaGetLastError());
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // C-ABI
@@ -647,6 +685,20 @@ int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const do
     if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");
     if (model == SCPP_B200_MODEL_ROCKETQUAT) return discretize_hook<RocketQuat>(K, n, nsub, device, X, U, sigma, par, A, B, C, s, z);
     if (model == SCPP_B200_MODEL_ROCKET2D) return discretize_hook<Rocket2d>(K, n, nsub, device, X, U, sigma, par, A, B, C, s, z);
+    return fail(SCPP_B200_ERR_ARG, "unknown model");
+}
+
+int scpp_b200_sim_step(scpp_b200_engine *e, double time_step, double *x_new, double *u0, int *reached)
+{
+    return e ? e->sim_step(time_step, x_new, u0, reached) : fail(SCPP_B200_ERR_ARG, "null engine");
+}
+
+int scpp_b200_simulate(int model, int n, double dt, int device, double *x, const double *u0, const double *u1, const double *par)
+{
+    if (n <= 0 || !(dt > 0.) || !x || !u0 || !u1 || !par) return fail(SCPP_B200_ERR_ARG, "scpp_b200_simulate: bad argument");
+    if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");
+    if (model == SCPP_B200_MODEL_ROCKETQUAT) return simulate_hook<RocketQuat>(n, dt, device, x, u0, u1, par);
+    if (model == SCPP_B200_MODEL_ROCKET2D) return simulate_hook<Rocket2d>(n, dt, device, x, u0, u1, par);
     return fail(SCPP_B200_ERR_ARG, "unknown model");
 }
 

@@ -24,58 +24,98 @@ extern "C" void hs_discretize(int model, int K, const double *X, const double *U
     else run_discretize<Rocket2d>(K, X, U, sigma, par, nsub, dd);
 }
 
+// host stand-in for EngineT: the per-instance arrays and the round loop of solve(); one object can run a closed loop
+template <class M>
+struct HostEngine {
+    static constexpr int NX = M::NX, NU = M::NU, NB = NX + NU, NC = NX + 2 * NU + 2;
+    ScArrays<M> a;
+    ModelParamsHost P;
+    ScConfig cfg;
+    int N, K;
+    std::vector<double> x_init, x_final, xi, xf, par, cst, scale, tdir, fixv, wtr, dd, ddT, ws, smem, ist, X, U, sigma, hist, info;
+    std::vector<uint32_t> fixm;
+    std::vector<int> iters, status, converged, frozen;
+    HostEngine(const ModelParamsHost &P_, const ScConfig &cfg_, int N_, const double *xi_in, const double *xf_in) : P(P_), cfg(cfg_), N(N_), K(cfg_.K)
+    {
+        x_init.assign(xi_in, xi_in + (size_t)N * NX); x_final.assign(xf_in, xf_in + (size_t)N * NX);
+        xi.resize(N * NX); xf.resize(N * NX); par.resize(N * M::NP); cst.resize(N * MAX_CST); scale.resize(N * 2); tdir.resize((size_t)N * K * 3);
+        fixv.resize((size_t)N * K * NB); wtr.resize(N); fixm.resize((size_t)N * K);
+        dd.resize((size_t)N * (K - 1) * NX * NC); ddT.resize((size_t)N * Ipm<M>::ddt_doubles(K));
+        a.N = N; a.K = K; a.max_it = cfg.max_iterations;
+        a.ws_stride = Ipm<M>::ws_doubles(K);
+        ws.resize((size_t)N * a.ws_stride); smem.resize(Ipm<M>::sm_doubles()); ist.resize((size_t)N * Ipm<M>::IPM_STATE);
+        X.resize((size_t)N * K * NX); U.resize((size_t)N * K * NU); sigma.resize(N);
+        hist.resize((size_t)N * (cfg.max_iterations + 1) * (K * NB + 1)); info.resize((size_t)N * cfg.max_iterations * INFO_STRIDE);
+        iters.resize(N); status.resize(N); converged.resize(N); frozen.assign(N, 0);
+        a.ipm_state = ist.data(); a.x_init = x_init.data(); a.x_final = x_final.data();
+        a.xi = xi.data(); a.xf = xf.data(); a.par = par.data(); a.cst = cst.data(); a.scale = scale.data();
+        a.X = X.data(); a.U = U.data(); a.sigma = sigma.data(); a.tdir = tdir.data(); a.fixm = fixm.data(); a.fixv = fixv.data(); a.w_tr = wtr.data();
+        a.iters = iters.data(); a.status = status.data(); a.converged = converged.data(); a.dd = dd.data(); a.ddT = ddT.data(); a.ws = ws.data();
+        a.hist = cfg.keep_history ? hist.data() : nullptr; a.info = info.data(); a.frozen = frozen.data();
+    }
+    void solve(bool warm)
+    {
+        for (int n = 0; n < N; n++) {
+            if (warm) { if (frozen[n]) { converged[n] = 8; continue; } sc_warm_instance<M>(a, P, cfg, n); }
+            else { frozen[n] = 0; sc_setup_instance<M>(a, P, cfg, n); }
+        }
+        // the engine's round structure: every round discretises the instances that start a new sub-problem and advances every
+        // unfinished instance by one slice of interior-point iterations
+        long rounds = 0;
+        for (;;) {
+            int active = 0; rounds++;
+            for (int n = 0; n < N; n++) {
+                if (converged[n] || iters[n] >= cfg.max_iterations) continue;
+                active++;
+                if (a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] == 0.)
+                    run_discretize<M>(K, a.X + (size_t)n * K * NX, a.U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg.nsub,
+                                      a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K));
+                if (cfg.ipm_slice >= 0) { sc_solve_instance<M>(a, cfg, n, smem.data()); continue; }
+                // split pipeline: the kernel sequence of one round, run here for one instance after the other
+                double *w = smem.data();
+                const int Pn = (K + 31) / 32;
+                sc_split_step<M, SP_START>(a, cfg, n, w, 0, 0);
+                for (int k = 0; k < K; k++) sc_split_step<M, SP_ASSEMBLE>(a, cfg, n, w, 0, k);
+                sc_split_step<M, SP_FACTOR>(a, cfg, n, w, 0, 0);
+                for (int mode = 1; mode <= 2; mode++) {
+                    for (int p = 0; p < Pn; p++) sc_split_step<M, SP_RHS>(a, cfg, n, w, mode, p);
+                    sc_split_step<M, SP_CHAIN>(a, cfg, n, w, mode, 0);
+                    for (int p = 0; p < Pn; p++) sc_split_step<M, SP_RECOVER>(a, cfg, n, w, mode, p);
+                }
+                for (int p = 0; p < Pn; p++) sc_split_step<M, SP_UPDATE>(a, cfg, n, w, 0, p);
+                for (int p = 0; p < Pn; p++) sc_split_step<M, SP_RESIDUALS>(a, cfg, n, w, 0, p);
+                sc_split_step<M, SP_TEST>(a, cfg, n, w, 0, 0);
+            }
+            if (!active) break;
+        }
+        if (getenv("SCPP_DEBUG_ROUNDS")) fprintf(stderr, "rounds %ld\n", rounds);
+    }
+    // redimensionalised copy of the final trajectories (SCAlgorithm.cpp:182-187)
+    void export_solution(double *Xo, double *Uo, double *so) const
+    {
+        for (int n = 0; n < N; n++) {
+            for (int k = 0; k < K; k++) {
+                double *x = Xo + ((size_t)n * K + k) * NX, *u = Uo + ((size_t)n * K + k) * NU;
+                for (int i = 0; i < NX; i++) x[i] = X[((size_t)n * K + k) * NX + i];
+                for (int i = 0; i < NU; i++) u[i] = U[((size_t)n * K + k) * NU + i];
+                M::redim(scale.data() + 2 * n, x, u);
+            }
+            so[n] = sigma[n];
+        }
+    }
+};
+
 template <class M>
 static int run_sc(const ModelParamsHost *P, const ScConfig *cfg, int N, const double *x_init, const double *x_final,
                   double *X, double *U, double *sigma, int *iters, int *status, int *converged, double *hist, double *info)
 {
-    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU, NC = NX + 2 * NU + 2;
-    const int K = cfg->K;
-    ScArrays<M> a;
-    a.N = N; a.K = K; a.max_it = cfg->max_iterations;
-    std::vector<double> xi(N * NX), xf(N * NX), par(N * M::NP), cst(N * MAX_CST), scale(N * 2), tdir((size_t)N * K * 3), fixv((size_t)N * K * NB), wtr(N);
-    std::vector<uint32_t> fixm((size_t)N * K);
-    std::vector<double> dd((size_t)N * (K - 1) * NX * NC), ddT((size_t)N * Ipm<M>::ddt_doubles(K));
-    a.ws_stride = Ipm<M>::ws_doubles(K);
-    std::vector<double> ws((size_t)N * a.ws_stride), smem(Ipm<M>::sm_doubles()), ist((size_t)N * Ipm<M>::IPM_STATE);
-    a.ipm_state = ist.data();
-    a.x_init = const_cast<double *>(x_init); a.x_final = const_cast<double *>(x_final);
-    a.xi = xi.data(); a.xf = xf.data(); a.par = par.data(); a.cst = cst.data(); a.scale = scale.data();
-    a.X = X; a.U = U; a.sigma = sigma; a.tdir = tdir.data(); a.fixm = fixm.data(); a.fixv = fixv.data(); a.w_tr = wtr.data();
-    a.iters = iters; a.status = status; a.converged = converged; a.dd = dd.data(); a.ddT = ddT.data(); a.ws = ws.data(); a.hist = hist; a.info = info;
-    for (int n = 0; n < N; n++) sc_setup_instance<M>(a, *P, *cfg, n);
-    // the engine's round structure: every round discretises the instances that start a new sub-problem and advances every
-    // unfinished instance by one slice of interior-point iterations
-    long rounds = 0;
-    for (;;) {
-        int active = 0; rounds++;
-        for (int n = 0; n < N; n++) {
-            if (converged[n] || iters[n] >= cfg->max_iterations) continue;
-            active++;
-            if (a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] == 0.)
-                run_discretize<M>(K, X + (size_t)n * K * NX, U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg->nsub,
-                                  a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K));
-            if (cfg->ipm_slice >= 0) { sc_solve_instance<M>(a, *cfg, n, smem.data()); continue; }
-            // split pipeline: the kernel sequence of one round, run here for one instance after the other
-            double *w = smem.data();
-            const int P = (K + 31) / 32;
-            sc_split_step<M, SP_START>(a, *cfg, n, w, 0, 0);
-            for (int k = 0; k < K; k++) sc_split_step<M, SP_ASSEMBLE>(a, *cfg, n, w, 0, k);
-            sc_split_step<M, SP_FACTOR>(a, *cfg, n, w, 0, 0);
-            for (int mode = 1; mode <= 2; mode++) {
-                for (int p = 0; p < P; p++) sc_split_step<M, SP_RHS>(a, *cfg, n, w, mode, p);
-                sc_split_step<M, SP_CHAIN>(a, *cfg, n, w, mode, 0);
-                for (int p = 0; p < P; p++) sc_split_step<M, SP_RECOVER>(a, *cfg, n, w, mode, p);
-            }
-            for (int p = 0; p < P; p++) sc_split_step<M, SP_UPDATE>(a, *cfg, n, w, 0, p);
-            for (int p = 0; p < P; p++) sc_split_step<M, SP_RESIDUALS>(a, *cfg, n, w, 0, p);
-            sc_split_step<M, SP_TEST>(a, *cfg, n, w, 0, 0);
-        }
-        if (!active) break;
-    }
-    if (getenv("SCPP_DEBUG_ROUNDS")) fprintf(stderr, "rounds %ld\n", rounds);
-    // redimensionalise the final trajectories (SCAlgorithm.cpp:182-187)
-    for (int n = 0; n < N; n++)
-        for (int k = 0; k < K; k++) M::redim(a.scale + 2 * n, X + ((size_t)n * K + k) * NX, U + ((size_t)n * K + k) * NU);
+    ScConfig c = *cfg; c.keep_history = 1;
+    HostEngine<M> e(*P, c, N, x_init, x_final);
+    e.solve(false);
+    e.export_solution(X, U, sigma);
+    memcpy(iters, e.iters.data(), sizeof(int) * N); memcpy(status, e.status.data(), sizeof(int) * N); memcpy(converged, e.converged.data(), sizeof(int) * N);
+    if (hist) memcpy(hist, e.hist.data(), sizeof(double) * e.hist.size());
+    if (info) memcpy(info, e.info.data(), sizeof(double) * e.info.size());
     return 0;
 }
 
@@ -84,6 +124,35 @@ extern "C" int hs_sc_solve(int model, const ModelParamsHost *P, const ScConfig *
 {
     if (model == 0) return run_sc<RocketQuat>(P, cfg, N, x_init, x_final, X, U, sigma, iters, status, converged, hist, info);
     return run_sc<Rocket2d>(P, cfg, N, x_init, x_final, X, U, sigma, iters, status, converged, hist, info);
+}
+
+// closed loop of scpp/src/SC_sim.cpp for N instances: X_sim [steps][N][nx], U_sim [steps][N][nu], iters [steps][N], reached [N]
+template <class M>
+static int run_sim(const ModelParamsHost *P, const ScConfig *cfg, int N, const double *x_init, const double *x_final, double time_step, int steps,
+                   double *X_sim, double *U_sim, int *iters, int *reached)
+{
+    HostEngine<M> e(*P, *cfg, N, x_init, x_final);
+    for (int n = 0; n < N; n++) reached[n] = 0;
+    for (int s = 0; s < steps; s++) {
+        e.solve(s > 0);
+        for (int n = 0; n < N; n++) {
+            iters[(size_t)s * N + n] = e.frozen[n] ? 0 : e.iters[n];
+            int r = 0;
+            sc_sim_step_instance<M>(e.a, e.P, e.cfg, n, time_step, X_sim + ((size_t)s * N + n) * M::NX, U_sim + ((size_t)s * N + n) * M::NU, &r);
+            reached[n] = r;
+        }
+    }
+    return 0;
+}
+extern "C" int hs_sc_sim(int model, const ModelParamsHost *P, const ScConfig *cfg, int N, const double *x_init, const double *x_final, double time_step,
+                         int steps, double *X_sim, double *U_sim, int *iters, int *reached)
+{
+    if (model == 0) return run_sim<RocketQuat>(P, cfg, N, x_init, x_final, time_step, steps, X_sim, U_sim, iters, reached);
+    return run_sim<Rocket2d>(P, cfg, N, x_init, x_final, time_step, steps, X_sim, U_sim, iters, reached);
+}
+extern "C" void hs_simulate(int model, double dt, double *x, const double *u0, const double *u1, const double *par)
+{
+    if (model == 0) rkf78_simulate<RocketQuat>(x, u0, u1, par, dt, 20); else rkf78_simulate<Rocket2d>(x, u0, u1, par, dt, 20);
 }
 
 // forward-mode dual number: instantiates the generic-scalar flow map (the plugin surface, systemFlowMap) to obtain the exact

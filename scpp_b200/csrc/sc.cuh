@@ -5,6 +5,7 @@
 #pragma once
 #include "ipm.cuh"
 #include "discretize.cuh"
+#include "simulate.cuh"
 
 namespace scpp {
 
@@ -44,6 +45,7 @@ struct ScArrays {
     double *ddT;                   // [N][NX*NC][KS]  the same tiles, stage-minor
     double *ws;                    // [N][ws_doubles]
     double *ipm_state;             // [N][Ipm::IPM_STATE]  solver state parked between K2 launches ([0] != 0: mid-solve)
+    int *frozen;                   // [N] or null: instances whose closed loop has reached the end (skipped by solve and sim_step)
     double *hist;                  // [N][max_it+1][K*NB+1] or null
     double *info;                  // [N][max_it][INFO_STRIDE]
     size_t ws_stride;
@@ -79,6 +81,76 @@ SCPP_HD void sc_setup_instance(const ScArrays<M> &a, const ModelParamsHost &P, c
         for (int k = 0; k < K; k++) { for (int i = 0; i < NX; i++) h[k * NB + i] = X[k * NX + i]; for (int i = 0; i < NU; i++) h[k * NB + NX + i] = U[k * NU + i]; }
         h[K * NB] = a.sigma[n];
     }
+}
+
+// ---- K0 (warm): SCAlgorithm::solve(warm_start = true), SCAlgorithm.cpp:141-145,152: keep the trajectory (re-nondimensionalised with
+// the scales of the NEW x_init), keep the trust-region weight and sigma, refresh parameters and the minimum-thrust directions
+template <class M>
+SCPP_HD void sc_warm_instance(const ScArrays<M> &a, const ModelParamsHost &P, const ScConfig &cfg, int n)
+{
+    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU;
+    const int K = a.K;
+    double *X = a.X + (size_t)n * K * NX, *U = a.U + (size_t)n * K * NU;
+    double old_scale[2] = {a.scale[2 * n], a.scale[2 * n + 1]};
+    for (int k = 0; k < K; k++) M::redim(old_scale, X + k * NX, U + k * NU);
+    double *xi = a.xi + (size_t)n * NX, *xf = a.xf + (size_t)n * NX;
+    for (int i = 0; i < NX; i++) { xi[i] = a.x_init[(size_t)n * NX + i]; xf[i] = a.x_final[(size_t)n * NX + i]; }
+    M::setup(P, cfg.nondimensionalize, xi, xf, a.par + (size_t)n * M::NP, a.cst + (size_t)n * MAX_CST, a.scale + (size_t)n * 2);
+    for (int k = 0; k < K; k++) {
+        M::nondim(a.scale + 2 * n, X + k * NX, U + k * NU);
+        a.fixm[(size_t)n * K + k] = M::fixed(P, xi, xf, K, k, a.fixv + ((size_t)n * K + k) * NB);
+        double *td = a.tdir + ((size_t)n * K + k) * 3;
+        if (P.exact_minimum_thrust) M::thrust_dir(U + k * NU, td); else { td[0] = 0.; td[1] = 0.; td[2] = 1.; }
+    }
+    a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
+    a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.;
+    if (a.hist) {
+        double *h = a.hist + (size_t)n * (a.max_it + 1) * a.hist_stride();
+        for (int k = 0; k < K; k++) { for (int i = 0; i < NX; i++) h[k * NB + i] = X[k * NX + i]; for (int i = 0; i < NU; i++) h[k * NB + NX + i] = U[k * NU + i]; }
+        h[K * NB] = a.sigma[n];
+    }
+}
+
+// ---- K4: one step of the closed loop of scpp/src/SC_sim.cpp:47-61 for instance n: apply the first input of the current solution to
+// the nonlinear model for time_step (dimensional units, model parameters redimensionalised as after SCAlgorithm.cpp:182-186),
+// x_init <- simulated state.  u1 = scpp::interpolatedInput(td.U, time_step, td.t, foh) (scpp/src/commonFunctions.cpp:6-19).
+template <class M>
+SCPP_HD void sc_sim_step_instance(const ScArrays<M> &a, const ModelParamsHost &P, const ScConfig &cfg, int n, double time_step,
+                                  double *x_out /* [NX] or null */, double *u_out /* [NU] or null */, int *reached /* or null */)
+{
+    constexpr int NX = M::NX, NU = M::NU;
+    const int K = a.K;
+    if (a.frozen && a.frozen[n]) {
+        if (x_out) for (int i = 0; i < NX; i++) x_out[i] = a.x_init[(size_t)n * NX + i];
+        if (u_out) for (int j = 0; j < NU; j++) u_out[j] = 0.;
+        if (reached) *reached = 1;
+        return;
+    }
+    const double *U = a.U + (size_t)n * K * NU, *scale = a.scale + 2 * n;
+    const double t = a.sigma[n];
+    const double node_dt = t / (K - 1);
+    long long i = (long long)(time_step / node_dt);
+    if (i > K - 2) i = K - 2;
+    const double ti = fmod(time_step, node_dt) / node_dt;
+    double xd[NX], u0[NU], ua[NU], ub[NU], u1[NU];
+    for (int j = 0; j < NU; j++) { u0[j] = U[j]; ua[j] = U[NU * i + j]; ub[j] = cfg.interpolate_input ? U[NU * (i + 1) + j] : U[NU * i + j]; }
+    for (int e = 0; e < NX; e++) xd[e] = 0.;
+    M::redim(scale, xd, u0); M::redim(scale, xd, ua); M::redim(scale, xd, ub);      // redimensionalizeTrajectory (SCAlgorithm.cpp:186)
+    for (int j = 0; j < NU; j++) u1[j] = ua[j] + (ub[j] - ua[j]) * ti;
+    // dimensional model parameters (model->redimensionalize(); updateModelParameters(), :184-185)
+    double xi[NX], xf[NX], par[M::NP], cst[MAX_CST], sc2[2];
+    for (int e = 0; e < NX; e++) { xi[e] = a.x_init[(size_t)n * NX + e]; xf[e] = a.x_final[(size_t)n * NX + e]; }
+    M::setup(P, 0, xi, xf, par, cst, sc2);
+    double x[NX];
+    for (int e = 0; e < NX; e++) x[e] = a.x_init[(size_t)n * NX + e];
+    rkf78_simulate<M>(x, u0, u1, par, time_step, 20);                               // simulate(model, time_step, u0, u1, x)  SC_sim.cpp:53
+    double d2 = 0.;
+    for (int e = 0; e < NX; e++) { a.x_init[(size_t)n * NX + e] = x[e]; const double d = x[e] - a.x_final[(size_t)n * NX + e]; d2 += d * d; }
+    const int end = (sqrt(d2) < 0.02) || (t < 0.25);                                // :58
+    if (a.frozen && end) a.frozen[n] = 1;
+    if (x_out) for (int e = 0; e < NX; e++) x_out[e] = x[e];
+    if (u_out) for (int j = 0; j < NU; j++) u_out[j] = u0[j];
+    if (reached) *reached = end;
 }
 
 // ---- binding of the solver object to instance n ------------------------------------------------------------------

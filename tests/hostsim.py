@@ -94,6 +94,23 @@ def sc_solve(model, P, cfg, x_init, x_final):
     return dict(X=X, U=U, t=sg, iters=iters, status=status, converged=conv, X_all=H[..., :nx], U_all=H[..., nx:], t_all=hist[:, :, -1], info=info)
 
 
+def sc_sim(model, P, cfg, x_init, x_final, time_step, steps):
+    nx, nu = DIMS[model]
+    x_init = np.ascontiguousarray(np.atleast_2d(x_init), float); N = x_init.shape[0]
+    x_final = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(x_final), (N, nx)), float)
+    Xs = np.zeros((steps, N, nx)); Us = np.zeros((steps, N, nu)); iters = np.zeros((steps, N), np.int32); reached = np.zeros(N, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().hs_sc_sim(model, C.byref(P), C.byref(cfg), N, p(x_init), p(x_final), C.c_double(time_step), steps, p(Xs), p(Us), p(iters), p(reached))
+    return dict(X_sim=Xs, U_sim=Us, iters=iters, reached=reached)
+
+
+def simulate(model, dt, u0, u1, par, x):
+    x = np.array(x, float)
+    p = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(C.c_void_p)
+    lib().hs_simulate(model, C.c_double(dt), x.ctypes.data_as(C.c_void_p), p(u0), p(u1), p(par))
+    return x
+
+
 def discretize(model, X, U, sigma, par, nsub):
     nx, nu = DIMS[model]
     K = X.shape[0]

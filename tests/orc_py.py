@@ -289,3 +289,12 @@ def scvx_nonlinear_cost(model, X, U, t, par):
     lib().orc_scvx_nonlinear_cost.restype = C.c_double
     return lib().orc_scvx_nonlinear_cost(model, X.shape[0], _p(np.ascontiguousarray(X, float)), _p(np.ascontiguousarray(U, float)), C.c_double(t),
                                          _p(np.ascontiguousarray(par, float)))
+
+
+# ---- closed loop (scpp/src/SC_sim.cpp) ----------------------------------------------------------------------------------
+def sc_sim(model, params, cfg, time_step=0.05, max_steps=100):
+    nx, nu, _ = DIMS[model]
+    Xs = np.zeros((max_steps, nx)); Us = np.zeros((max_steps, nu)); iters = np.zeros(max_steps, np.int32); reached = C.c_int()
+    n = lib().orc_sc_sim(model, C.byref(params), C.byref(cfg), C.c_double(time_step), max_steps, _p(Xs), _p(Us), _p(iters), C.byref(reached))
+    m = n if n >= 0 else -n - 1
+    return dict(steps=n, X_sim=Xs[:m], U_sim=Us[:m], iters=iters[:max(m, 1)], reached_end=bool(reached.value))

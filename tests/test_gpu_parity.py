@@ -271,3 +271,42 @@ def test_warm_start_and_errors(S):
     bad = S.default_config(model); bad.free_final_time = 0
     with pytest.raises(S.ScppError):
         S.SCAlgorithm(model, params, bad, 1)
+
+
+def test_k4_simulate_vs_oracle(S):
+    """K4 alone through the C-ABI: scpp::simulate for a batch of states"""
+    p, _ = O.falcon9()
+    par = np.zeros(10); O.lib().orc_rq_model_par(C.byref(p), par.ctypes.data_as(C.c_void_p))
+    rng = np.random.default_rng(7)
+    n = 64
+    x = np.tile(np.array(p.x_init), (n, 1)); x[:, 1:7] *= 1 + 0.1 * rng.standard_normal((n, 6))
+    u0 = np.tile([1e4, -2e4, 3e5, 0.], (n, 1)) * (1 + 0.1 * rng.standard_normal((n, 4))); u1 = u0 * 1.05
+    got = S.simulate(S.ROCKETQUAT, x, u0, u1, par, 0.05)
+    for i in range(n):
+        ref = O.simulate(O.ROCKETQUAT, 0.05, u0[i], u1[i], par, x[i])
+        assert np.abs(got[i] - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def test_closed_loop_vs_oracle(S):
+    """scpp/src/SC_sim.cpp on the device: solve, K4 step (x_init advanced on the device), warm-started solve ... against the oracle's
+    literal loop, for a small Monte-Carlo batch; instances that reach the end are frozen"""
+    for name, model_o, K, steps, plist in (("Rocket2D", O.ROCKET2D, 30, 4, [O.rocket2d()]),
+                                          ("RocketQuat", O.ROCKETQUAT, 20, 2, [O.falcon9()[0]] + [O.rq_perturb(*O.falcon9(), 0x5C99, i) for i in range(3)])):
+        model, params, x_init, x_final, cfg = S.load_model(name, K=K, max_iterations=15)
+        xi = np.array([list(p.x_init) for p in plist])
+        eng = S.SCAlgorithm(model, params, cfg, len(plist))
+        eng.set_boundary_states(xi, x_final)
+        Xs, Us, its = [], [], []
+        for s in range(steps):
+            eng.solve(warm_start=s > 0)
+            its.append(eng.get_solution()["iterations"].copy())
+            r = eng.sim_step(0.05)
+            Xs.append(r["x"]); Us.append(r["u0"])
+        eng.close()
+        Xs, Us, its = np.array(Xs), np.array(Us), np.array(its)
+        ocfg = O.sc_config(K=K, model=model_o, max_iterations=15)
+        for i, p in enumerate(plist):
+            ro = O.sc_sim(model_o, p, ocfg, 0.05, steps)
+            assert ro["steps"] == steps and np.array_equal(its[:, i], ro["iters"][:steps])
+            sx, su = np.abs(ro["X_sim"]).max(), np.abs(ro["U_sim"]).max()
+            assert np.abs(Xs[:, i] - ro["X_sim"]).max() < 1e-6 * sx and np.abs(Us[:, i] - ro["U_sim"]).max() < 1e-4 * su

@@ -237,3 +237,33 @@ def test_split_pipeline_two_parts_vs_monolithic_source():
     r = H.sc_solve(0, P, H.sc_config(ocfg, tol=1e-8, warm=0.995, ipm_slice=-1), xi, xf)
     assert np.array_equal(r["iters"], ref["iters"]) and np.array_equal(r["info"][:, :, 5], ref["info"][:, :, 5])
     assert np.abs(r["X_all"] - ref["X_all"]).max() < 1e-7 and np.abs(r["U_all"] - ref["U_all"]).max() < 1e-7
+
+
+def test_k4_simulate_source_is_the_oracle_integrator():
+    """K4 body (RKF78, 20 steps, first-order-hold input) vs the oracle's restatement of scpp::simulate: same arithmetic"""
+    p, _ = O.falcon9()
+    par = np.zeros(10); O.lib().orc_rq_model_par(C.byref(p), par.ctypes.data_as(C.c_void_p))
+    x = np.array(p.x_init); u0 = np.array([1e4, -2e4, 3e5, 0.]); u1 = np.array([-1e4, 1e4, 3.5e5, 0.])
+    a = H.simulate(0, 0.05, u0, u1, par, x); b = O.simulate(0, 0.05, u0, u1, par, x)
+    assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max() and np.abs(a - x).max() > 1e-3
+    p2 = O.rocket2d()
+    par2 = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(p2), par2.ctypes.data_as(C.c_void_p))
+    x2 = np.array(p2.x_init)
+    a2 = H.simulate(1, 0.05, [0.01, 3e5], [0.02, 3.2e5], par2, x2); b2 = O.simulate(1, 0.05, [0.01, 3e5], [0.02, 3.2e5], par2, x2)
+    assert np.abs(a2 - b2).max() <= 1e-12 * np.abs(b2).max()
+
+
+@pytest.mark.parametrize("name,model,K,steps", [("Rocket2D", 1, 30, 4), ("RocketQuat", 0, 20, 2)])
+def test_closed_loop_source_vs_oracle(name, model, K, steps):
+    """SC_sim closed loop (scpp/src/SC_sim.cpp:41-65): cold solve, then warm-started solves from the simulated state; the kernel source
+    (warm-start re-scaling, interpolated input, K4, carried trust-region weight) against the oracle's literal loop"""
+    p = O.falcon9()[0] if model == 0 else O.rocket2d()
+    ocfg = O.sc_config(K=K, model=model, max_iterations=15)
+    ro = O.sc_sim(model, p, ocfg, 0.05, steps)
+    assert ro["steps"] == steps
+    P, xi, xf = H.params_from_oracle(model, p)
+    rh = H.sc_sim(model, P, H.sc_config(ocfg, tol=1e-8, warm=0.0, ipm_slice=1, history=False), xi, xf, 0.05, steps)
+    assert np.array_equal(rh["iters"][:, 0], ro["iters"][:steps])
+    sx, su = np.abs(ro["X_sim"]).max(), np.abs(ro["U_sim"]).max()
+    assert np.abs(rh["X_sim"][:, 0] - ro["X_sim"]).max() < 1e-7 * sx
+    assert np.abs(rh["U_sim"][:, 0] - ro["U_sim"]).max() < 1e-5 * su
