@@ -372,8 +372,11 @@ struct EngineT : scpp_b200_engine {
                 launches++;
             }
             CU(cudaMemcpyAsync(h_counter, counter, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-            if (comm) {
-                // the one data-path collective: every rank learns every instance's flag
+            // the one data-path collective: every rank learns every instance's flag.  With one interior-point iteration per round an outer
+            // iteration spans ~10 rounds, so the flags are exchanged every 10th round (once per round in lock-step mode): about one
+            // all-gather per outer iteration; a rank that runs out of work idles through at most 9 empty rounds before everyone agrees to stop
+            const bool exchange = comm && (slice_eff == 0 || (round + 1) % 10 == 0);
+            if (exchange) {
                 int rc = g_nccl.AllGather(flags, flags_all, (size_t)N, /*ncclUint8*/ 1, comm, stream);
                 if (rc != 0) return fail(SCPP_B200_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
                 CU(cudaMemsetAsync(gcount, 0, sizeof(unsigned long long), stream));
@@ -391,7 +394,8 @@ struct EngineT : scpp_b200_engine {
             disc_list = disc;
             cur ^= 1;
             rounds++; inst_rounds += n_active_round;
-            global_active = comm ? (long long)*h_gcount : (long long)n_active;
+            if (!comm) global_active = (long long)n_active;
+            else if (exchange) global_active = (long long)*h_gcount;
         }
         // SC iterations done: per instance (reported as instance-iterations) and the largest count (outer iterations)
         h_iters.resize(N);
