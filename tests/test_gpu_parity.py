@@ -4,12 +4,14 @@ PARITY UNPINNED: the reference has no golden vectors; the oracle (oracle/*.c) is
 residuals (tests/test_oracle.py).  Tolerances are north_star's: 1e-5 on the state, 1e-4 on the control, in the units the
 algorithm iterates on (nondimensional; thrusts are ~1e-2 there, SURVEY §7 "parity definition")."""
 import ctypes as C
+import os
 import numpy as np
 import pytest
 
 import orc_py as O
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 TOL_X, TOL_U = 1e-5, 1e-4
 RPY_F9 = np.deg2rad([-20.0, 20.0, 0.0])
@@ -310,3 +312,22 @@ def test_closed_loop_vs_oracle(S):
             assert ro["steps"] == steps and np.array_equal(its[:, i], ro["iters"][:steps])
             sx, su = np.abs(ro["X_sim"]).max(), np.abs(ro["U_sim"]).max()
             assert np.abs(Xs[:, i] - ro["X_sim"]).max() < 1e-6 * sx and np.abs(Us[:, i] - ro["U_sim"]).max() < 1e-4 * su
+
+
+def test_sc_oneshot_output_layout(S, tmp_path):
+    """tools/sc_oneshot.py writes what scpp/src/SC_oneshot.cpp:29-63 writes: output/<Model>/SC/<time>/<k>/{X,U,t}.txt, redimensionalised,
+    comma-separated, 6 significant digits -- readable by the reference's plotting scripts (np.loadtxt(..., delimiter=','))"""
+    import subprocess, sys, glob
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "sc_oneshot.py"), "--model", "RocketQuat", "--K", "20", "--out", str(tmp_path)], text=True)
+    root = out.strip().splitlines()[-1]
+    its = sorted(int(os.path.basename(d)) for d in glob.glob(os.path.join(root, "*")))
+    p, _ = O.falcon9()
+    ro = O.sc_solve(O.ROCKETQUAT, p, O.sc_config(K=20, max_iterations=15))
+    assert its == list(range(ro["iterations"] + 1))
+    X = np.loadtxt(os.path.join(root, str(its[-1]), "X.txt"), delimiter=","); U = np.loadtxt(os.path.join(root, str(its[-1]), "U.txt"), delimiter=",")
+    t = float(open(os.path.join(root, str(its[-1]), "t.txt")).read())
+    assert X.shape == (20, 14) and U.shape == (20, 4)
+    assert np.allclose(X, ro["X"], rtol=2e-5, atol=2e-5 * np.abs(ro["X"]).max()) and np.allclose(U, ro["U"], rtol=2e-4, atol=2e-5 * np.abs(ro["U"]).max())
+    assert abs(t - ro["t"]) < 1e-4 * ro["t"]
+    X0 = np.loadtxt(os.path.join(root, "0", "X.txt"), delimiter=",")           # iterate 0 = the initial guess, redimensionalised
+    assert np.allclose(X0[0], np.array(p.x_init), rtol=1e-5) and np.allclose(X0[-1, 1:7], np.array(p.x_final)[1:7], rtol=1e-5, atol=1e-3)
