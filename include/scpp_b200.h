@@ -130,6 +130,12 @@ int scpp_b200_get_info(scpp_b200_engine *e, double *info /* [N][max_iterations][
  * steps skip it (flag 8) until scpp_b200_set_boundary_states is called again. */
 int scpp_b200_sim_step(scpp_b200_engine *e, double time_step, double *x_new, double *u0, int *reached);
 
+/* LQR tracking gains along the current solution of every instance (kernel K5): LQRTracker::LQRTracker scpp_core/src/LQRTracker.cpp:6-28 with
+ * ComputeLQR / careSolve / solveSchurIterative scpp_core/src/LQR.cpp:7-109 (matrix sign iteration on the Hamiltonian, eps 1e-8, <= 100
+ * steps; FullPivLU solve).  q_diag [nx], r_diag [nu] = state_weights / input_weights of LQR.info (LQRTracker.cpp:30-40).
+ * gains [N][K][nu][nx] (row-major, dimensional units), ok [N][K] (optional) = success flag of careSolve. */
+int scpp_b200_lqr_gains(scpp_b200_engine *e, const double *q_diag, const double *r_diag, double *gains, int *ok);
+
 /* device timing of the last solve (CUDA events on the engine stream): ms in K1, ms in K2, ms total, kernel launches,
  * outer iterations executed, sum over instances of iterations executed */
 int scpp_b200_last_timing(scpp_b200_engine *e, double *ms_discretize, double *ms_socp, double *ms_total,

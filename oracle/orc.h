@@ -137,6 +137,11 @@ int orc_sc_subproblem(int model, const void *params, const orc_sc_config *cfg, d
                       double *X, double *U, double *sigma, double *nu, double *delta,
                       double *norm1_nu, double *delta_sigma, orc_ipm_info *info);
 
+/* ---- LQR tracking gains (scpp_core/src/LQR.cpp, LQRTracker.cpp:6-28); matrices row-major */
+int orc_lqr_gain(int nx, int nu, const double *q_diag, const double *r_diag, const double *A, const double *B, double *K);
+void orc_lqr_tracker_gains(int model, int K, const double *X, const double *U, const double *par,
+                           const double *q_diag, const double *r_diag, double *gains, int *ok);
+
 /* ---- SCvx variant (SCvx.info: SCvxAlgorithm.cpp:23-44) ---- */
 typedef struct {
     int K;

@@ -228,6 +228,15 @@ class SCAlgorithm:
         _check(lib().scpp_b200_sim_step(self._h, C.c_double(time_step), _p(x), _p(u), _p(r)))
         return dict(x=x, u0=u, reached=r)
 
+    def lqr_gains(self, q_diag, r_diag):
+        """LQRTracker gains for every node of every instance's current solution: (gains [N][K][nu][nx], ok [N][K])"""
+        K = self.config.K
+        g = np.empty((self.N, K, self.nu, self.nx)); ok = np.empty((self.N, K), np.int32)
+        q = np.ascontiguousarray(q_diag, float); r = np.ascontiguousarray(r_diag, float)
+        assert q.shape == (self.nx,) and r.shape == (self.nu,)
+        _check(lib().scpp_b200_lqr_gains(self._h, _p(q), _p(r), _p(g), _p(ok)))
+        return g, ok
+
     def last_rounds(self):
         r, ir = C.c_int(), C.c_longlong()
         _check(lib().scpp_b200_last_rounds(self._h, C.byref(r), C.byref(ir)))
@@ -255,6 +264,22 @@ def selftest_blockops(device=0):
     err = C.c_double()
     _check(lib().scpp_b200_selftest_blockops(device, C.byref(err)))
     return err.value
+
+
+def lqr_input(t, x, X, U, t_total, gains):
+    """LQRTracker::getInput (scpp_core/src/LQRTracker.cpp:41-65) with TrajectoryData::inputAtTime / approxStateAtTime
+    (trajectoryData.hpp:41-78), first-order hold: u = -K(t) (x - x_target(t)) + u_target(t)"""
+    Kn = X.shape[0]
+    t = min(max(t, 0.0), t_total)
+    dt = t_total / (Kn - 1)
+    if t == t_total:
+        xt, ut = X[-1], U[-1]
+    else:
+        i = int(t / dt); a = np.fmod(t, dt) / dt
+        xt = X[i] + a * (X[i + 1] - X[i]); ut = U[i] + a * (U[i + 1] - U[i])
+    i = int(t / dt); a = np.fmod(t, dt) / dt
+    K0 = gains[min(i, Kn - 1)]; K1 = gains[min(Kn - 1, i + 1)]
+    return -(K0 + a * (K1 - K0)) @ (np.asarray(x, float) - xt) + ut
 
 
 def simulate(model, x, u0, u1, par, dt, device=0):

@@ -2,6 +2,7 @@
 // Built for sm_100a only; there is no CPU execution path in this library.
 #include "../../include/scpp_b200.h"
 #include "sc.cuh"
+#include "lqr.cuh"
 #include "info_parser.hpp"
 
 #include <cuda_runtime.h>
@@ -58,6 +59,25 @@ __global__ void k_simulate(int n, double dt, double *x, const double *u0, const 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) rkf78_simulate<M>(x + (size_t)i * M::NX, u0 + (size_t)i * M::NU, u1 + (size_t)i * M::NU, par + (size_t)i * M::NP, dt, 20);
 }
+// K5: LQR tracking gains, one warp per (instance, node); Jacobians at the redimensionalised solution node with dimensional parameters
+template <class M>
+__global__ void __launch_bounds__(128) k_lqr(ScArrays<M> a, ModelParamsHost P, const double *qd, const double *rd, double *gains, int *ok)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int NX = M::NX, NU = M::NU;
+    const int warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * 4 + warp;
+    if (gw >= (long long)a.N * a.K) return;
+    const int n = int(gw / a.K), k = int(gw - (long long)n * a.K);
+    double x[NX], u[NU], xi[NX], xf[NX], par[M::NP], cst[MAX_CST], sc2[2];
+    for (int i = 0; i < NX; i++) { x[i] = a.X[((size_t)n * a.K + k) * NX + i]; xi[i] = a.x_init[(size_t)n * NX + i]; xf[i] = a.x_final[(size_t)n * NX + i]; }
+    for (int j = 0; j < NU; j++) u[j] = a.U[((size_t)n * a.K + k) * NU + j];
+    M::redim(a.scale + 2 * n, x, u);
+    M::setup(P, 0, xi, xf, par, cst, sc2);
+    const bool good = Lqr<M>::gain(x, u, par, qd, rd, gains + (size_t)gw * NU * NX, smem + (size_t)warp * Lqr<M>::sm_doubles());
+    if ((threadIdx.x & 31) == 0) ok[gw] = good;
+}
+
 // first active list of a solve: every instance that is not frozen
 __global__ void k_first_list(int *list, int *count, const int *frozen, int *converged, unsigned char *flags, int n)
 {
@@ -186,6 +206,7 @@ struct scpp_b200_engine {
     virtual int get_iterate(int it, double *X, double *U, double *t) = 0;
     virtual int get_info(double *info) = 0;
     virtual int sim_step(double time_step, double *x_new, double *u0, int *reached) = 0;
+    virtual int lqr_gains(const double *q_diag, const double *r_diag, double *gains, int *ok) = 0;
     int model = 0, N = 0, device = 0;
     ModelParamsHost P;
     ScConfig cfg;
@@ -461,6 +482,29 @@ struct EngineT : scpp_b200_engine {
         CU(cudaGetLastError());
         return 0;
     }
+    // LQRTracker::LQRTracker (scpp_core/src/LQRTracker.cpp:6-28) for every instance: one gain per node of the current solution
+    int lqr_gains(const double *q_diag, const double *r_diag, double *gains, int *ok) override
+    {
+        if (!solved_once) return fail(SCPP_B200_ERR_ARG, "scpp_b200_lqr_gains: no solution yet");
+        if (!q_diag || !r_diag || !gains) return fail(SCPP_B200_ERR_ARG, "scpp_b200_lqr_gains: null argument");
+        CU(cudaSetDevice(device));
+        const int K = cfg.K;
+        const size_t ng = (size_t)N * K * NU * NX;
+        double *dq = nullptr, *dg = nullptr; int *dok = nullptr;
+        CU(cudaMalloc((void **)&dq, sizeof(double) * (NX + NU))); CU(cudaMalloc((void **)&dg, sizeof(double) * ng)); CU(cudaMalloc((void **)&dok, sizeof(int) * N * K));
+        CU(cudaMemcpyAsync(dq, q_diag, sizeof(double) * NX, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(dq + NX, r_diag, sizeof(double) * NU, cudaMemcpyHostToDevice, stream));
+        const int smem = int(4 * Lqr<M>::sm_doubles() * sizeof(double));
+        CU(cudaFuncSetAttribute(k_lqr<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const long long warps = (long long)N * K;
+        k_lqr<M><<<(unsigned)((warps + 3) / 4), 128, smem, stream>>>(a, P, dq, dq + NX, dg, dok);
+        CU(cudaMemcpyAsync(gains, dg, sizeof(double) * ng, cudaMemcpyDeviceToHost, stream));
+        if (ok) CU(cudaMemcpyAsync(ok, dok, sizeof(int) * N * K, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        cudaFree(dq); cudaFree(dg); cudaFree(dok);
+        CU(cudaGetLastError());
+        return 0;
+    }
     int get_info(double *info) override
     {
         CU(cudaSetDevice(device));
@@ -692,6 +736,10 @@ int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const do
     return fail(SCPP_B200_ERR_ARG, "unknown model");
 }
 
+int scpp_b200_lqr_gains(scpp_b200_engine *e, const double *q_diag, const double *r_diag, double *gains, int *ok)
+{
+    return e ? e->lqr_gains(q_diag, r_diag, gains, ok) : fail(SCPP_B200_ERR_ARG, "null engine");
+}
 int scpp_b200_sim_step(scpp_b200_engine *e, double time_step, double *x_new, double *u0, int *reached)
 {
     return e ? e->sim_step(time_step, x_new, u0, reached) : fail(SCPP_B200_ERR_ARG, "null engine");

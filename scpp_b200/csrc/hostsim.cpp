@@ -2,6 +2,7 @@
 // Built into tests/_hostsim/libhostsim.so by tests/hostsim.py; never part of libscpp_b200.so and never
 // loaded by the scpp_b200 package: the product has no CPU execution path.
 #include "sc.cuh"
+#include "lqr.cuh"
 #include <vector>
 #include <cstring>
 #include <cstdlib>
@@ -191,6 +192,18 @@ static void run_jac(const double *x, const double *u, const double *par, double 
 extern "C" void hs_jacobians(int model, const double *x, const double *u, const double *par, double *f, double *A_ad, double *B_ad, double *A_lin, double *B_lin)
 {
     if (model == 0) run_jac<RocketQuat>(x, u, par, f, A_ad, B_ad, A_lin, B_lin); else run_jac<Rocket2d>(x, u, par, f, A_ad, B_ad, A_lin, B_lin);
+}
+
+// K5 body on the host: gains [K][nu][nx], ok [K]
+template <class M>
+static void run_lqr(int K, const double *X, const double *U, const double *par, const double *qd, const double *rd, double *gains, int *ok)
+{
+    std::vector<double> sm(Lqr<M>::sm_doubles());
+    for (int k = 0; k < K; k++) ok[k] = Lqr<M>::gain(X + (size_t)k * M::NX, U + (size_t)k * M::NU, par, qd, rd, gains + (size_t)k * M::NU * M::NX, sm.data());
+}
+extern "C" void hs_lqr_gains(int model, int K, const double *X, const double *U, const double *par, const double *qd, const double *rd, double *gains, int *ok)
+{
+    if (model == 0) run_lqr<RocketQuat>(K, X, U, par, qd, rd, gains, ok); else run_lqr<Rocket2d>(K, X, U, par, qd, rd, gains, ok);
 }
 
 extern "C" int hs_sizes(int which) { return which == 0 ? (int)sizeof(ModelParamsHost) : (int)sizeof(ScConfig); }

@@ -43,6 +43,12 @@ SCPP_D void warp_sum3(double &a, double &b, double &c)   // three interleaved bu
     }
 }
 SCPP_D int warp_or(int v) { return __any_sync(0xffffffffu, v); }
+SCPP_D int warp_min_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 SCPP_D double warp_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 #else
 constexpr int LANES = 1;
@@ -52,6 +58,7 @@ inline double warp_sum(double v) { return v; }
 inline double warp_max(double v) { return v; }
 inline void warp_sum3(double &, double &, double &) {}
 inline int warp_or(int v) { return v; }
+inline int warp_min_i(int v) { return v; }
 inline double warp_bcast(double v, int) { return v; }
 #endif
 

@@ -331,3 +331,27 @@ def test_sc_oneshot_output_layout(S, tmp_path):
     assert abs(t - ro["t"]) < 1e-4 * ro["t"]
     X0 = np.loadtxt(os.path.join(root, "0", "X.txt"), delimiter=",")           # iterate 0 = the initial guess, redimensionalised
     assert np.allclose(X0[0], np.array(p.x_init), rtol=1e-5) and np.allclose(X0[-1, 1:7], np.array(p.x_final)[1:7], rtol=1e-5, atol=1e-3)
+
+
+def test_k5_lqr_gains_vs_oracle(S):
+    """LQRTracker gains through the C-ABI (one warp per (instance, node)) vs the oracle, Rocket2D K=30 with the reference's LQR.info
+    weights; getInput's interpolation is the host helper lqr_input"""
+    model, params, x_init, x_final, cfg = S.load_model("Rocket2D", K=30, max_iterations=15)
+    eng = S.SCAlgorithm(model, params, cfg, 3)
+    eng.set_boundary_states(x_init, x_final)
+    eng.solve()
+    sol = eng.get_solution()
+    q, r = np.ones(6), np.array([2.0, 2.0])
+    G, ok = eng.lqr_gains(q, r)
+    eng.close()
+    p2 = O.rocket2d()
+    par = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(p2), par.ctypes.data_as(C.c_void_p))
+    pp = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(C.c_void_p)
+    Gr = np.zeros((30, 2, 6)); okr = np.zeros(30, np.int32)
+    O.lib().orc_lqr_tracker_gains(1, 30, pp(sol["X"][0]), pp(sol["U"][0]), pp(par), pp(q), pp(r), Gr.ctypes.data_as(C.c_void_p), okr.ctypes.data_as(C.c_void_p))
+    assert ok.all() and okr.all()
+    for i in range(3):
+        rel = np.abs(G[i] - Gr).max(axis=(1, 2)) / np.abs(Gr).max(axis=(1, 2))
+        assert rel.max() < 1e-4
+    u = S.lqr_input(0.37 * sol["t"][0], sol["X"][0][3] * 1.01, sol["X"][0], sol["U"][0], sol["t"][0], G[0])
+    assert u.shape == (2,) and np.isfinite(u).all()

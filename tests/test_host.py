@@ -267,3 +267,25 @@ def test_closed_loop_source_vs_oracle(name, model, K, steps):
     sx, su = np.abs(ro["X_sim"]).max(), np.abs(ro["U_sim"]).max()
     assert np.abs(rh["X_sim"][:, 0] - ro["X_sim"]).max() < 1e-7 * sx
     assert np.abs(rh["U_sim"][:, 0] - ro["U_sim"]).max() < 1e-5 * su
+
+
+def test_k5_lqr_gain_source_vs_oracle():
+    """K5 body (Gauss-Jordan inverse inside the sign iteration, complete-pivoting solve) vs the oracle's restatement of LQR.cpp along a
+    solved Rocket2D trajectory with the reference's LQR.info weights.  The Hamiltonians of this model are ill-conditioned (double
+    integrators): two correct implementations of the same iteration agree to ~1e-6 relative, which is the bar here."""
+    p2 = O.rocket2d()
+    rs = O.sc_solve(1, p2, O.sc_config(K=30, model=1, max_iterations=6))
+    par = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(p2), par.ctypes.data_as(C.c_void_p))
+    X, U = rs["X"], rs["U"]
+    q, r = np.ones(6), np.array([2.0, 2.0])
+    pp = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(C.c_void_p)
+    G = np.zeros((30, 2, 6)); ok = np.zeros(30, np.int32); G2 = np.zeros((30, 2, 6)); ok2 = np.zeros(30, np.int32)
+    O.lib().orc_lqr_tracker_gains(1, 30, pp(X), pp(U), pp(par), pp(q), pp(r), G.ctypes.data_as(C.c_void_p), ok.ctypes.data_as(C.c_void_p))
+    H.lib().hs_lqr_gains(1, 30, pp(X), pp(U), pp(par), pp(q), pp(r), G2.ctypes.data_as(C.c_void_p), ok2.ctypes.data_as(C.c_void_p))
+    assert ok.all() and ok2.all()
+    rel = np.abs(G - G2).max(axis=(1, 2)) / np.abs(G).max(axis=(1, 2))
+    assert rel.max() < 1e-4
+    # the gains stabilise the linearised dynamics at every node
+    for k in (0, 10, 29):
+        A, B = O.jac(1, X[k], U[k], par)
+        assert np.linalg.eigvals(A - B @ G2[k]).real.max() < 0

@@ -305,3 +305,18 @@ def test_scvx_subproblem_optimum_is_not_unique_in_the_states():
     assert abs(a["info"][0].norm1_nu - b["info"][0].norm1_nu) < 1e-8 * a["info"][0].norm1_nu
     assert np.abs(a["U_all"][1] - b["U_all"][1]).max() < 1e-5
     assert np.abs(a["X_all"][1] - b["X_all"][1]).max() > 1e-2
+
+
+def test_lqr_restatement_against_scipy_care():
+    """solveSchurIterative + FullPivLU restatement (LQR.cpp:7-109) reproduces the stabilising CARE solution on well-conditioned systems"""
+    import scipy.linalg as sl
+    rng = np.random.default_rng(0)
+    p = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(C.c_void_p)
+    for nx, nu in ((6, 2), (14, 4)):
+        A = rng.standard_normal((nx, nx)); B = rng.standard_normal((nx, nu)); q = 0.5 + rng.random(nx); r = 1.0 + rng.random(nu)
+        K = np.zeros((nu, nx))
+        assert O.lib().orc_lqr_gain(nx, nu, p(q), p(r), p(A), p(B), K.ctypes.data_as(C.c_void_p)) == 1
+        P = sl.solve_continuous_are(A, B, np.diag(q), np.diag(r))
+        Kref = np.linalg.solve(np.diag(r), B.T @ P)
+        assert np.abs(K - Kref).max() < 1e-10 * np.abs(Kref).max()
+        assert np.linalg.eigvals(A - B @ K).real.max() < 0          # stabilising
