@@ -330,7 +330,10 @@ def test_sc_oneshot_output_layout(S, tmp_path):
     assert np.allclose(X, ro["X"], rtol=2e-5, atol=2e-5 * np.abs(ro["X"]).max()) and np.allclose(U, ro["U"], rtol=2e-4, atol=2e-5 * np.abs(ro["U"]).max())
     assert abs(t - ro["t"]) < 1e-4 * ro["t"]
     X0 = np.loadtxt(os.path.join(root, "0", "X.txt"), delimiter=",")           # iterate 0 = the initial guess, redimensionalised
-    assert np.allclose(X0[0], np.array(p.x_init), rtol=1e-5) and np.allclose(X0[-1, 1:7], np.array(p.x_final)[1:7], rtol=1e-5, atol=1e-3)
+    xi_, xf_ = np.array(p.x_init), np.array(p.x_final)
+    assert np.allclose(X0[0], xi_, rtol=1e-5)
+    # last node of the initial guess: alpha2 = (K-1)/K, the reference's denominator is K (rocketQuat.cpp:45-46)
+    assert np.allclose(X0[-1, 1:7], (xi_[1:7] + 19 * xf_[1:7]) / 20, rtol=1e-5, atol=1e-3)
 
 
 def test_k5_lqr_gains_vs_oracle(S):
