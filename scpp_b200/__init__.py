@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscpp_b200.so")
+LIB_PATH = os.environ.get("SCPP_B200_LIB", os.path.join(_HERE, "libscpp_b200.so"))   # the override is for A/B experiments with kernel variants
 CONFIG_DIR = os.path.join(os.path.dirname(_HERE), "configs")
 
 ROCKETQUAT, ROCKET2D = 0, 1

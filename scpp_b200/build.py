@@ -9,7 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "libscpp_b200.so")
-ARCH = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+# -static-global-template-stub=false: the kernels are explicit instantiations DEFINED in other translation units (kernels_inst.cu) and only
+# declared (extern template) where they are launched
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-static-global-template-stub=false"]
 GROUPS = [(m, g) for m in (0, 1) for g in range(5)]
 
 
