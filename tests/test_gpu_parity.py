@@ -358,3 +358,36 @@ def test_k5_lqr_gains_vs_oracle(S):
         assert rel.max() < 1e-4
     u = S.lqr_input(0.37 * sol["t"][0], sol["X"][0][3] * 1.01, sol["X"][0], sol["U"][0], sol["t"][0], G[0])
     assert u.shape == (2,) and np.isfinite(u).all()
+
+
+def test_ragged_batch_sizes_and_a_failing_instance(S):
+    """batch sizes that do not fill the launch shape (1, 149 = one more than the SMs, a K with few stages), and an instance whose
+    sub-problem is infeasible (initial mass below the dry mass): the reference would std::terminate (SCAlgorithm.cpp:94-98); here it is
+    flagged (flags == 2) and every other instance is bit-identical to its solo solve"""
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=10, max_iterations=4)
+    N = 149
+    xi = S.perturbed_initial_states(x_init, RPY_F9, N)
+    xi[5, 0] = 0.9 * x_final[0]                          # below m_dry: m_k >= m_dry cannot hold at k = 0
+    eng = S.SCAlgorithm(model, params, cfg, N)
+    eng.set_boundary_states(xi, x_final)
+    eng.solve()
+    a = eng.get_solution()
+    eng.close()
+    assert a["flags"][5] == 2 and (np.delete(a["flags"], 5) != 2).all()
+    for i in (0, 6, 148):
+        e1 = S.SCAlgorithm(model, params, cfg, 1)
+        e1.set_boundary_states(xi[i:i + 1], x_final)
+        e1.solve()
+        c = e1.get_solution()
+        e1.close()
+        assert np.array_equal(c["X"][0], a["X"][i]) and np.array_equal(c["U"][0], a["U"][i]) and c["iterations"][0] == a["iterations"][i]
+    # smallest horizon the engine accepts
+    m3, p3, xi3, xf3, c3 = S.load_model("Rocket2D", K=3, max_iterations=3)
+    e3 = S.SCAlgorithm(m3, p3, c3, 2)
+    e3.set_boundary_states(xi3, xf3)
+    e3.solve()
+    s3 = e3.get_solution()
+    e3.close()
+    assert np.isfinite(s3["X"]).all() and np.array_equal(s3["X"][0], s3["X"][1])
+    with pytest.raises(S.ScppError):
+        S.load_model("Rocket2D", K=2) and S.SCAlgorithm(*S.load_model("Rocket2D", K=2)[:2], S.load_model("Rocket2D", K=2)[4], 1)
