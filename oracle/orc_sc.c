@@ -511,6 +511,49 @@ static void build_scvx_problem(socp_t *P, double weight_vc, double trust_region,
     }
 }
 
+/* Ruiz equilibration of the problem data as ECOS does before it factors (its set_equilibration: a few sweeps of square-rooted
+ * row / column infinity norms, one common factor per second-order cone), solve, then scale the solution back.  Used for the SCvx
+ * sub-problem, whose KKT system has no trust-region block to hide the 1/J_z ~ 2.5e5 entries of the nondimensional B matrices. */
+static int conic_solve_equilibrated(int n, int p, int m, int l, int ncones, const int *q, const double *c, const double *b, const double *h,
+                                    int nnzA, const int *Ai, const int *Aj, const double *Av, int nnzG, const int *Gi, const int *Gj, const double *Gv,
+                                    const double *kv, const double *keq, double *x, double *y, double *sv, double *zv, orc_ipm_info *info)
+{
+    double *xe = (double *)malloc(sizeof(double) * n), *ae = (double *)malloc(sizeof(double) * (p + 1)), *ge = (double *)malloc(sizeof(double) * m);
+    double *xt = (double *)malloc(sizeof(double) * n), *at = (double *)malloc(sizeof(double) * (p + 1)), *gt = (double *)malloc(sizeof(double) * m);
+    double *As = (double *)malloc(sizeof(double) * (nnzA + 1)), *Gs = (double *)malloc(sizeof(double) * (nnzG + 1));
+    double *cs = (double *)malloc(sizeof(double) * n), *bs = (double *)malloc(sizeof(double) * (p + 1)), *hs = (double *)malloc(sizeof(double) * m);
+    memcpy(As, Av, sizeof(double) * nnzA); memcpy(Gs, Gv, sizeof(double) * nnzG);
+    for (int j = 0; j < n; j++) xe[j] = 1.;
+    for (int i = 0; i < p; i++) ae[i] = 1.;
+    for (int i = 0; i < m; i++) ge[i] = 1.;
+    for (int sweep = 0; sweep < 3; sweep++) {
+        for (int j = 0; j < n; j++) xt[j] = 0.;
+        for (int i = 0; i < p; i++) at[i] = 0.;
+        for (int i = 0; i < m; i++) gt[i] = 0.;
+        for (int e = 0; e < nnzA; e++) { const double a = fabs(As[e]); if (a > xt[Aj[e]]) xt[Aj[e]] = a; if (a > at[Ai[e]]) at[Ai[e]] = a; }
+        for (int e = 0; e < nnzG; e++) { const double a = fabs(Gs[e]); if (a > xt[Gj[e]]) xt[Gj[e]] = a; if (a > gt[Gi[e]]) gt[Gi[e]] = a; }
+        int o = l;
+        for (int k = 0; k < ncones; k++) { double sum = 0.; for (int r = 0; r < q[k]; r++) sum += gt[o + r]; for (int r = 0; r < q[k]; r++) gt[o + r] = sum / q[k]; o += q[k]; }
+        for (int j = 0; j < n; j++) xt[j] = xt[j] < 1e-6 ? 1. : sqrt(xt[j]);
+        for (int i = 0; i < p; i++) at[i] = at[i] < 1e-6 ? 1. : sqrt(at[i]);
+        for (int i = 0; i < m; i++) gt[i] = gt[i] < 1e-6 ? 1. : sqrt(gt[i]);
+        for (int e = 0; e < nnzA; e++) As[e] /= at[Ai[e]] * xt[Aj[e]];
+        for (int e = 0; e < nnzG; e++) Gs[e] /= gt[Gi[e]] * xt[Gj[e]];
+        for (int j = 0; j < n; j++) xe[j] *= xt[j];
+        for (int i = 0; i < p; i++) ae[i] *= at[i];
+        for (int i = 0; i < m; i++) ge[i] *= gt[i];
+    }
+    for (int j = 0; j < n; j++) cs[j] = c[j] / xe[j];
+    for (int i = 0; i < p; i++) bs[i] = b[i] / ae[i];
+    for (int i = 0; i < m; i++) hs[i] = h[i] / ge[i];
+    const int st = orc_conic_solve_keys(n, p, m, l, ncones, q, cs, bs, hs, nnzA, Ai, Aj, As, nnzG, Gi, Gj, Gs, kv, keq, x, y, sv, zv, info);
+    for (int j = 0; j < n; j++) x[j] /= xe[j];
+    for (int i = 0; i < p; i++) y[i] /= ae[i];
+    for (int i = 0; i < m; i++) { zv[i] /= ge[i]; sv[i] *= ge[i]; }
+    free(xe); free(ae); free(ge); free(xt); free(at); free(gt); free(As); free(Gs); free(cs); free(bs); free(hs);
+    return st;
+}
+
 int orc_scvx_subproblem(int model, const void *params, int K, double weight_vc, double trust_region,
                         const double *Ubar, const double *A, const double *B, const double *C, const double *z,
                         const double *thrust_dir, double *X, double *U, double *nu, double *norm1_nu, orc_ipm_info *info)
@@ -544,8 +587,8 @@ int orc_scvx_subproblem(int model, const void *params, int K, double weight_vc, 
      * size ECOS uses (2e-7, with iterative refinement against the unregularised system) instead of the SC path's 1e-13 */
     const double reg_saved = orc_get_static_reg();
     orc_set_static_reg(orc_scvx_static_reg);
-    int st = orc_conic_solve_keys(P.n, P.b.n, m, l, P.ncones, P.q, P.c, P.b.v, h, P.A.nnz, P.A.i, P.A.j, P.A.v,
-                                  nnzG, Gi, Gj, Gv, kv, P.keq.v, x, y, sv, zv, info);
+    int st = conic_solve_equilibrated(P.n, P.b.n, m, l, P.ncones, P.q, P.c, P.b.v, h, P.A.nnz, P.A.i, P.A.j, P.A.v,
+                                      nnzG, Gi, Gj, Gv, kv, P.keq.v, x, y, sv, zv, info);
     orc_set_static_reg(reg_saved);
     const int nx = P.nx, nuu = P.nu;
     for (int k = 0; k < K; k++) {
