@@ -74,6 +74,14 @@ typedef struct {
                          -T (T > 1) = split pipeline only in rounds that advance fewer than T instances.  Same iterates up to the
                          rounding of re-ordered sums. */
     scpp_b200_ipm_settings ipm;
+    /* SCvx variant (scpp_core/src/SCvxAlgorithm.cpp, SCvxProblem.cpp; parameters of SCvx.info, SCvxAlgorithm.cpp:23-44).
+     * algorithm = 0: SC (the fields above), 1: SCvx -- fixed final time, hard trust region of radius scvx_trust_region on the inputs,
+     * ratio test (rho_0/1/2, alpha, beta) against the simulated nonlinear cost, converged when |predicted change| < change_threshold.
+     * For SCvx, scpp_b200_get_info returns per outer iteration: norm1_nu, nonlinear cost, rho, trust region used, sub-problem solves,
+     * ipm_iterations, ipm_status, pres, dres, relgap. */
+    int algorithm;
+    int pad2_;
+    double scvx_rho_0, scvx_rho_1, scvx_rho_2, scvx_alpha, scvx_beta, scvx_change_threshold, scvx_trust_region;
 } scpp_b200_sc_config;
 
 typedef struct scpp_b200_engine scpp_b200_engine;
@@ -94,6 +102,7 @@ void scpp_b200_default_config(int model, scpp_b200_sc_config *cfg); /* values of
  * x_init / x_final receive the boundary states built there (nx doubles each). */
 int scpp_b200_load_model_info(const char *path, int model, scpp_b200_model_params *params, double *x_init, double *x_final);
 int scpp_b200_load_sc_info(const char *path, scpp_b200_sc_config *cfg); /* SCAlgorithm::loadParameters */
+int scpp_b200_load_scvx_info(const char *path, scpp_b200_sc_config *cfg); /* SCvxAlgorithm::loadParameters (SCvxAlgorithm.cpp:23-44); sets algorithm = 1 */
 
 /* ---- engine life cycle ------------------------------------------------------------------------------------------
  * replaces SCAlgorithm::SCAlgorithm(Model::ptr_t) + SCAlgorithm::initialize() (SCAlgorithm.cpp:14-20,48-64):

@@ -38,7 +38,9 @@ class SCConfig(C.Structure):
                 ("weight_time", C.c_double), ("weight_trust_region_time", C.c_double),
                 ("weight_trust_region_trajectory", C.c_double), ("weight_virtual_control", C.c_double),
                 ("nu_tol", C.c_double), ("delta_tol", C.c_double), ("max_iterations", C.c_int), ("nsub", C.c_int),
-                ("keep_history", C.c_int), ("ipm_slice", C.c_int), ("ipm", IpmSettings)]
+                ("keep_history", C.c_int), ("ipm_slice", C.c_int), ("ipm", IpmSettings),
+                ("algorithm", C.c_int), ("pad2_", C.c_int), ("scvx_rho_0", C.c_double), ("scvx_rho_1", C.c_double), ("scvx_rho_2", C.c_double),
+                ("scvx_alpha", C.c_double), ("scvx_beta", C.c_double), ("scvx_change_threshold", C.c_double), ("scvx_trust_region", C.c_double)]
 
 
 class ScppError(RuntimeError):
@@ -108,12 +110,19 @@ def load_sc_info(path, model):
     return cfg
 
 
-def load_model(name, K=None, **overrides):
-    """convenience: configs/<name>/{model,SC}.info -> (model id, ModelParams, x_init, x_final, SCConfig)"""
+def load_scvx_info(path, model):
+    """SCvxAlgorithm::loadParameters (SCvxAlgorithm.cpp:23-44): SCConfig with algorithm = 1"""
+    cfg = default_config(model)
+    _check(lib().scpp_b200_load_scvx_info(path.encode(), C.byref(cfg)))
+    return cfg
+
+
+def load_model(name, K=None, algorithm="SC", **overrides):
+    """convenience: configs/<name>/{model,SC|SCvx}.info -> (model id, ModelParams, x_init, x_final, SCConfig)"""
     model = ROCKET2D if name == "Rocket2D" else ROCKETQUAT
     folder = os.path.join(CONFIG_DIR, name)
     p, xi, xf = load_model_info(os.path.join(folder, "model.info"), model)
-    cfg = load_sc_info(os.path.join(folder, "SC.info"), model)
+    cfg = load_scvx_info(os.path.join(folder, "SCvx.info"), model) if algorithm == "SCvx" else load_sc_info(os.path.join(folder, "SC.info"), model)
     if K is not None:
         cfg.K = K
     for k, v in overrides.items():

@@ -78,6 +78,23 @@ __global__ void __launch_bounds__(128) k_lqr(ScArrays<M> a, ModelParamsHost P, c
     if ((threadIdx.x & 31) == 0) ok[gw] = good;
 }
 
+// SCvx: nonlinear cost of the candidates (thread per (listed instance, interval)) and the ratio test (thread per listed instance)
+template <class M>
+__global__ void k_scvx_cost(ScArrays<M> a, ScConfig cfg, const int *__restrict__ list, int n_list)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = a.K - 1;
+    if (idx >= (long long)n_list * per) return;
+    const int li = int(idx / per), k = int(idx - (long long)li * per);
+    sc_scvx_cost<M>(a, cfg, list[li], k);
+}
+template <class M>
+__global__ void k_scvx_decide(ScArrays<M> a, ScConfig cfg, const int *__restrict__ list, int n_list)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_list) sc_scvx_decide<M>(a, cfg, list[i]);
+}
+
 // first active list of a solve: every instance that is not frozen
 __global__ void k_first_list(int *list, int *count, const int *frozen, int *converged, unsigned char *flags, int n)
 {
@@ -278,7 +295,12 @@ struct EngineT : scpp_b200_engine {
         DA(a.info, (size_t)N * cfg.max_iterations * INFO_STRIDE);
         a.hist = nullptr;
         if (cfg.keep_history) DA(a.hist, (size_t)N * (cfg.max_iterations + 1) * a.hist_stride());
-        DA(active[0], N); DA(active[1], N); DA(disc, N); DA(counter, 2); DA(a.ipm_state, (size_t)N * Ipm<M>::IPM_STATE); DA(gcount, 1); DA(flags, N); DA(a.frozen, N); DA(sim_x, (size_t)N * NX); DA(sim_u, (size_t)N * NU); DA(sim_r, N);
+        DA(active[0], N); DA(active[1], N); DA(disc, N); DA(counter, 2); DA(a.ipm_state, (size_t)N * Ipm<M>::IPM_STATE); DA(gcount, 1); DA(flags, N); DA(a.frozen, N);
+        a.trust = a.last_cost = a.n1c = a.Xc = a.Uc = a.costp = nullptr; a.have_last = a.solves = a.phase = nullptr;
+        if (cfg.algorithm == 1) {
+            DA(a.trust, N); DA(a.last_cost, N); DA(a.n1c, N); DA(a.Xc, (size_t)N * K * NX); DA(a.Uc, (size_t)N * K * NU); DA(a.costp, (size_t)N * K);
+            DA(a.have_last, N); DA(a.solves, N); DA(a.phase, N);
+        } DA(sim_x, (size_t)N * NX); DA(sim_u, (size_t)N * NU); DA(sim_r, N);
         DA(Xo, (size_t)N * K * NX); DA(Uo, (size_t)N * K * NU);
 #undef DA
         CU(cudaMallocHost((void **)&h_counter, 2 * sizeof(int)));
@@ -329,7 +351,7 @@ struct EngineT : scpp_b200_engine {
         // solved), (3) re-forms the lists and exchanges the flag bytes.  With ipm_slice == 0 a slice is a whole sub-problem and
         // the rounds are the reference's outer iterations in lock-step.
         const int slice_eff = cfg.ipm_slice < 0 ? 1 : cfg.ipm_slice;
-        const long long max_rounds = (long long)cfg.max_iterations * (slice_eff > 0 ? (cfg.ipm.maxit + 3) / slice_eff + 2 : 1) + 1;
+        const long long max_rounds = (long long)cfg.max_iterations * (cfg.algorithm == 1 ? SCVX_MAX_RESOLVE + 1 : 1) * (slice_eff > 0 ? (cfg.ipm.maxit + 3) / slice_eff + 2 : 1) + 1;
         for (long long round = 0; round < max_rounds && global_active > 0; round++) {
             CU(cudaEventRecord(ev[1], stream));
             if (n_disc > 0) {
@@ -384,6 +406,12 @@ struct EngineT : scpp_b200_engine {
                 const size_t smem = (size_t)wpb * Ipm<M>::sm_doubles() * sizeof(double);
                 k_solve<M, WPB_MAX, 1><<<(n_active + wpb - 1) / wpb, wpb * 32, smem, stream>>>(a, cfg, active[cur], n_active);
                 launches++;
+            }
+            if (cfg.algorithm == 1 && n_active > 0) {      // SCvx: simulate the candidates of the sub-problems that ended in this round, ratio test
+                const long long thr = (long long)n_active * (K - 1);
+                k_scvx_cost<M><<<(unsigned)((thr + 127) / 128), 128, 0, stream>>>(a, cfg, active[cur], n_active);
+                k_scvx_decide<M><<<(n_active + 127) / 128, 128, 0, stream>>>(a, cfg, active[cur], n_active);
+                launches += 2;
             }
             CU(cudaEventRecord(ev[3], stream));
             CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), stream));
@@ -560,6 +588,9 @@ void scpp_b200_default_config(int model, scpp_b200_sc_config *c)
     c->nu_tol = 1e-5; c->delta_tol = 1e-3; c->max_iterations = 15;
     c->nsub = -5; c->keep_history = 0; c->ipm_slice = 1;   // RK4 x 5 and x 10, Richardson-extrapolated: the accuracy of RK4 x 20 for 3/4 of the work
     c->ipm.feastol = 1e-8; c->ipm.abstol = 1e-8; c->ipm.reltol = 1e-8; c->ipm.maxit = 100;
+    c->algorithm = 0;   // SCvx.info values, used when algorithm is set to 1
+    c->scvx_rho_0 = 0.; c->scvx_rho_1 = 0.25; c->scvx_rho_2 = 0.9; c->scvx_alpha = 2.; c->scvx_beta = 3.2;
+    c->scvx_change_threshold = model == SCPP_B200_MODEL_ROCKETQUAT ? 1e-3 : 1e-2; c->scvx_trust_region = 5.;
 }
 
 static void deg2rad(double &v) { v *= M_PI / 180.; }
@@ -651,8 +682,31 @@ int scpp_b200_load_sc_info(const char *path, scpp_b200_sc_config *c)
     return 0;
 }
 
+int scpp_b200_load_scvx_info(const char *path, scpp_b200_sc_config *c)
+{
+    try {   // SCvxAlgorithm::loadParameters, SCvxAlgorithm.cpp:23-44
+        ParameterServer ps(path);
+        bool nd, ii;
+        ps.loadScalar("K", c->K);
+        ps.loadScalar("nondimensionalize", nd);
+        ps.loadScalar("max_iterations", c->max_iterations);
+        ps.loadScalar("alpha", c->scvx_alpha); ps.loadScalar("beta", c->scvx_beta);
+        ps.loadScalar("rho_0", c->scvx_rho_0); ps.loadScalar("rho_1", c->scvx_rho_1); ps.loadScalar("rho_2", c->scvx_rho_2);
+        ps.loadScalar("change_threshold", c->scvx_change_threshold);
+        ps.loadScalar("weight_virtual_control", c->weight_virtual_control);
+        ps.loadScalar("trust_region", c->scvx_trust_region);
+        ps.loadScalar("interpolate_input", ii);
+        c->nondimensionalize = nd; c->interpolate_input = ii; c->algorithm = 1;
+        c->free_final_time = 1;   // engine-internal: the time column exists and sigma is pinned to final_time (SCvx has a fixed final time)
+    } catch (const std::exception &ex) { return fail(SCPP_B200_ERR_IO, ex.what()); }
+    return 0;
+}
+
 int scpp_b200_create(int model, const scpp_b200_model_params *params, const scpp_b200_sc_config *cfg, int n, int device, scpp_b200_engine **out)
 {
+    if (cfg && cfg->algorithm != 0 && cfg->algorithm != 1) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: algorithm must be 0 (SC) or 1 (SCvx)");
+    if (cfg && cfg->algorithm == 1 && !(cfg->scvx_trust_region > 0. && cfg->scvx_alpha > 1. && cfg->scvx_beta > 1.))
+        return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: SCvx needs trust_region > 0, alpha > 1, beta > 1");
     if (!params || !cfg || !out || n <= 0) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: bad argument");
     if (cfg->K < 3 || cfg->max_iterations < 1 || cfg->nsub == 0) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: K >= 3, max_iterations >= 1, nsub != 0 required");
     if (!cfg->free_final_time || !cfg->interpolate_input)

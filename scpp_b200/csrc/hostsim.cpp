@@ -35,7 +35,8 @@ struct HostEngine {
     int N, K;
     std::vector<double> x_init, x_final, xi, xf, par, cst, scale, tdir, fixv, wtr, dd, ddT, ws, smem, ist, X, U, sigma, hist, info;
     std::vector<uint32_t> fixm;
-    std::vector<int> iters, status, converged, frozen;
+    std::vector<int> iters, status, converged, frozen, have_last, solves, phase;
+    std::vector<double> trust, last_cost, n1c, Xc, Uc, costp;
     HostEngine(const ModelParamsHost &P_, const ScConfig &cfg_, int N_, const double *xi_in, const double *xf_in) : P(P_), cfg(cfg_), N(N_), K(cfg_.K)
     {
         x_init.assign(xi_in, xi_in + (size_t)N * NX); x_final.assign(xf_in, xf_in + (size_t)N * NX);
@@ -53,6 +54,10 @@ struct HostEngine {
         a.X = X.data(); a.U = U.data(); a.sigma = sigma.data(); a.tdir = tdir.data(); a.fixm = fixm.data(); a.fixv = fixv.data(); a.w_tr = wtr.data();
         a.iters = iters.data(); a.status = status.data(); a.converged = converged.data(); a.dd = dd.data(); a.ddT = ddT.data(); a.ws = ws.data();
         a.hist = cfg.keep_history ? hist.data() : nullptr; a.info = info.data(); a.frozen = frozen.data();
+        trust.resize(N); last_cost.resize(N); n1c.resize(N); Xc.resize((size_t)N * K * NX); Uc.resize((size_t)N * K * NU); costp.resize((size_t)N * K);
+        have_last.resize(N); solves.resize(N); phase.resize(N);
+        a.trust = trust.data(); a.last_cost = last_cost.data(); a.n1c = n1c.data(); a.Xc = Xc.data(); a.Uc = Uc.data(); a.costp = costp.data();
+        a.have_last = have_last.data(); a.solves = solves.data(); a.phase = phase.data();
     }
     void solve(bool warm)
     {
@@ -71,7 +76,11 @@ struct HostEngine {
                 if (a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] == 0.)
                     run_discretize<M>(K, a.X + (size_t)n * K * NX, a.U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg.nsub,
                                       a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K));
-                if (cfg.ipm_slice >= 0) { sc_solve_instance<M>(a, cfg, n, smem.data()); continue; }
+                if (cfg.ipm_slice >= 0) {
+                    sc_solve_instance<M>(a, cfg, n, smem.data());
+                    if (cfg.algorithm == 1) { for (int k = 0; k < K - 1; k++) sc_scvx_cost<M>(a, cfg, n, k); sc_scvx_decide<M>(a, cfg, n); }   // the cost / decide kernels
+                    continue;
+                }
                 // split pipeline: the kernel sequence of one round, run here for one instance after the other
                 double *w = smem.data();
                 const int Pn = (K + 31) / 32;
@@ -86,6 +95,7 @@ struct HostEngine {
                 for (int p = 0; p < Pn; p++) sc_split_step<M, SP_UPDATE>(a, cfg, n, w, 0, p);
                 for (int p = 0; p < Pn; p++) sc_split_step<M, SP_RESIDUALS>(a, cfg, n, w, 0, p);
                 sc_split_step<M, SP_TEST>(a, cfg, n, w, 0, 0);
+                if (cfg.algorithm == 1) { for (int k = 0; k < K - 1; k++) sc_scvx_cost<M>(a, cfg, n, k); sc_scvx_decide<M>(a, cfg, n); }
             }
             if (!active) break;
         }

@@ -207,6 +207,11 @@ struct Ipm {
     const uint32_t *fixm;  // [K]
     const double *fixv;    // [K][NB]
     double w_time, w_trs, w_tr, w_vc;
+    // SCvx variant (buildSCvxProblem, scpp_core/src/SCvxProblem.cpp:6-71): fixed final time (sigma pinned: the global rows are skipped),
+    // hard trust region |ubar_k - u_k| <= tr_rad on the INPUT rows of the node cone only (delta_k pinned to tr_rad, state rows inactive:
+    // their s, z, w, lambda stay exactly zero), cost w_vc |nu|_1 alone (caller sets w_time = w_trs = w_tr = 0)
+    bool scvx = false;
+    double tr_rad = 0.;
     // ---- workspace (global memory, per instance) -------------------------------------------------------------------
     double *prim, *dprim, *rx, *best_;
     double *s, *z, *wb, *lam, *rz, *cr, *dz, *ds;
@@ -242,6 +247,7 @@ struct Ipm {
     SCPP_HD double dsigma_val() const { return prim[PSN * KS + 1]; }
 
     SCPP_HD bool fixed(int k, int i) const { return (fixm[k] >> i) & 1u; }
+    SCPP_HD bool tr_row(int i) const { return !scvx || i > NX; }      // is tail row i (1..NB) of the node cone active?
     SCPP_HD double xibar(int k, int i) const { return i < NX ? Xbar[k * NX + i] : Ubar[k * NU + (i - NX)]; }
     SCPP_HD double T(int i, int j, int k) const { return ddT[(i * NC + j) * KS + k]; }     // tile element, stage-minor
 
@@ -438,7 +444,7 @@ struct Ipm {
                 }
             }
         }
-        if (lane_id() == 0 && k_lo == 0) {
+        if (lane_id() == 0 && k_lo == 0 && !scvx) {
             const int r0 = RS * KS, p0 = PSN * KS;
             double s4[4], z4[4], d4[4], e4[4];
 #pragma unroll
@@ -514,12 +520,14 @@ struct Ipm {
 #pragma unroll
                 for (int i = 1; i < D; i++) {
                     const double xb = XB[i - 1];
-                    const double rv = S[i] - (xb - P[i - 1]);
+                    const double rv = tr_row(i) ? S[i] - (xb - P[i - 1]) : 0.;
                     RZ[i] = rv;
-                    h2 += xb * xb; rz2 += rv * rv; zrz += Z[i] * rv;
+                    if (tr_row(i)) h2 += xb * xb;
+                    rz2 += rv * rv; zrz += Z[i] * rv;
                     a += S[i] * S[i]; b += Z[i] * Z[i]; c += S[i] * Z[i];
                     RXa[i - 1] += Z[i];                                    // G'z of the trust-region rows
                 }
+                if (scvx) h2 += delta * delta;                             // the head row's h is the radius
                 gap += c; pcost += w_tr * delta;
                 double cev = 1.;
                 const double ss = S[0] * S[0] - a, zz = Z[0] * Z[0] - b;
@@ -545,8 +553,9 @@ struct Ipm {
 #pragma unroll
                 for (int i = 0; i < D; i++) { rz[(TRO + i) * KS + k] = RZ[i]; wb[(TRO + i) * KS + k] = S[i]; lam[(TRO + i) * KS + k] = Z[i]; }
                 ce[NCONE * KS + k] = cev;
-                rx[NB * KS + k] = w_tr - z0;
-                rx2 += (w_tr - z0) * (w_tr - z0); xrx += delta * (w_tr - z0);
+                const double rxdl = scvx ? 0. : w_tr - z0;                 // delta is not a variable of the SCvx problem
+                rx[NB * KS + k] = rxdl;
+                rx2 += rxdl * rxdl; xrx += delta * rxdl;
             }
             // ---- block 2: model rows (LP rows, model cones):  S2 <- wb, Z2 <- lam, RZ2
             {
@@ -671,7 +680,7 @@ struct Ipm {
         nm.gap = warp_sum(gap); nm.rz2 = warp_sum(rz2); nm.pcost = warp_sum(pcost); nm.zrz = warp_sum(zrz);
         nm.rx2 = warp_sum(rx2); nm.xrx = warp_sum(xrx); nm.h2 = warp_sum(h2); nm.bad = warp_or(bad);
         nm.acc_sig = warp_sum(acc_sig);
-        if (!split) residual_globals(nm, identity);
+        if (!split && !scvx) residual_globals(nm, identity);
     }
     // RXa += [w ; -C' w] of interval k-1
     SCPP_HD void couple_prev(int k, double *RXa) const
@@ -864,9 +873,9 @@ struct Ipm {
             const double *dg = rk + NRK * NB;
             const double *wt_ = WB + TRO;
             const double e2i = CE[NCONE], w0 = wt_[0];
-            const double kap = e2i * (2. * w0 * w0 - 1.), c2 = 4. * e2i * e2i * w0 * w0 / kap, beta = 2. * e2i - c2;
+            const double kap = e2i * (2. * w0 * w0 - 1.), c2 = scvx ? 0. : 4. * e2i * e2i * w0 * w0 / kap, beta = 2. * e2i - c2;
             FOR_LANE(i, NB) {
-                double v = e2i;
+                double v = tr_row(i + 1) ? e2i : 0.;
 #pragma unroll
                 for (int c = 0; c < NRK; c++) v += dg[c * NB + i];
                 dsum[i] = v;
@@ -985,6 +994,7 @@ struct Ipm {
     // delta_sigma eliminated); sets l_ss
     SCPP_HD bool finish_corner(double corner)
     {
+        if (scvx) { l_ss = 1.; return true; }                  // sigma is pinned: no border
         const int r0 = RS * KS;
         const double d = wb[r0];
         double w3[3] = {wb[r0 + 1], wb[r0 + 2], wb[r0 + 3]};
@@ -1290,7 +1300,7 @@ struct Ipm {
                 double dot = w0 * q[0], prz = -kap * q[0];
 #pragma unroll
                 for (int i = 1; i < D; i++) { dot -= w[i] * q[i]; prz += 2. * e2i * w0 * w[i] * q[i]; }
-                const double rho = (prz + rxd) / kap;
+                const double rho = scvx ? 0. : (prz + rxd) / kap;
 #pragma unroll
                 for (int i = 1; i < D; i++) G[i - 1] += e2i * (-2. * dot * w[i] + q[i]) - 2. * e2i * w0 * w[i] * rho;
             }
@@ -1542,8 +1552,8 @@ struct Ipm {
                 q[0] = -q[0];
                 double pq = -kap * q[0], dot = w0 * q[0];
 #pragma unroll
-                for (int i = 1; i < D; i++) { q[i] = yk[i - 1] - q[i]; pq += 2. * e2i * w0 * w[i] * q[i]; dot -= w[i] * q[i]; }
-                const double ddl = (rxd - pq) / kap;
+                for (int i = 1; i < D; i++) { q[i] = tr_row(i) ? yk[i - 1] - q[i] : 0.; pq += 2. * e2i * w0 * w[i] * q[i]; dot -= w[i] * q[i]; }
+                const double ddl = scvx ? 0. : (rxd - pq) / kap;
                 dprim[NB * KS + k] = ddl;
                 // dz = M q + p ddl   (in q)
                 q[0] = e2i * (2. * dot * w0 - q[0]) - kap * ddl;
@@ -1556,7 +1566,7 @@ struct Ipm {
                     dsv[0] = rzs * RZ[0] + ddl;
                     double w1z = 0, w1s = 0;
 #pragma unroll
-                    for (int i = 1; i < D; i++) { dsv[i] = rzs * RZ[i] - yk[i - 1]; w1z += w[i] * q[i]; w1s += w[i] * dsv[i]; }
+                    for (int i = 1; i < D; i++) { dsv[i] = tr_row(i) ? rzs * RZ[i] - yk[i - 1] : 0.; w1z += w[i] * q[i]; w1s += w[i] * dsv[i]; }
 #pragma unroll
                     for (int i = 0; i < D; i++) ds[(TRO + i) * KS + k] = dsv[i];
                     // scaled directions  dz~ = W dz (in q),  ds~ = W^-1 ds (in dsv)
@@ -1729,6 +1739,7 @@ struct Ipm {
     // globals: rhs and local elimination for the sigma rows, then y_sigma (every lane computes the same scalars)
     SCPP_HD void globals_mid(int mode, double csig, double sigmu, double gsig, double ldot, Glob &g) const
     {
+        if (scvx) { for (int i = 0; i < 4; i++) g.rzg[i] = 0.; g.rxg[0] = g.rxg[1] = 0.; g.kap_s = 1.; g.p_s[0] = g.p_s[1] = g.p_s[2] = 0.; g.ysig = 0.; return; }
         const int r0g = RS * KS, p0g = PSN * KS;
         double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
         const double e2i = ce[NCN * KS], d0 = wb[r0g];
@@ -1760,6 +1771,7 @@ struct Ipm {
     // Call from lane 0 only (it stores).
     SCPP_HD double globals_recover(int mode, double rzs, const Glob &g)
     {
+        if (scvx) return 0.;
         const int r0g = RS * KS, p0g = PSN * KS;
         double tmax = 0;
         double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
@@ -1815,7 +1827,7 @@ struct Ipm {
             for (int r = 0; r < NROW; r++) { const RowDesc rd = M::crow(r); out[r * KS + k] = row_h(rd) - row_dot(r, k, prim); }
             out[TRO * KS + k] = prim[NB * KS + k];
 #pragma unroll
-            for (int j = 0; j < NB; j++) out[(TRO + 1 + j) * KS + k] = xibar(k, j) - prim[j * KS + k];
+            for (int j = 0; j < NB; j++) out[(TRO + 1 + j) * KS + k] = tr_row(j + 1) ? xibar(k, j) - prim[j * KS + k] : 0.;
 #pragma unroll 2
             for (int i = 0; i < NX; i++) {
                 double tm = 0., tp = 0.;
@@ -1832,7 +1844,7 @@ struct Ipm {
                 out[(MN + i) * KS + k] = tm; out[(MN + NX + i) * KS + k] = tp;
             }
         }
-        if (lane_id() == 0) { const int r0 = RS * KS; out[r0] = sg - 0.001; out[r0 + 1] = 0.5 + 0.5 * dsg; out[r0 + 2] = 0.5 - 0.5 * dsg; out[r0 + 3] = sg - sigbar; }
+        if (lane_id() == 0 && !scvx) { const int r0 = RS * KS; out[r0] = sg - 0.001; out[r0 + 1] = 0.5 + 0.5 * dsg; out[r0 + 2] = 0.5 - 0.5 * dsg; out[r0 + 3] = sg - sigbar; }
         warp_sync();
     }
     // visit every cone of a row array: f(first index, stride, dimension)
@@ -1845,7 +1857,7 @@ struct Ipm {
             f(TRO * KS + k, KS, D);
             if (k < K - 1) for (int r = MN; r < RS; r++) f(r * KS + k, KS, 1);
         }
-        if (lane_id() == 0) { f(RS * KS, 1, 1); f(RS * KS + 1, 1, 3); }
+        if (lane_id() == 0 && !scvx) { f(RS * KS, 1, 1); f(RS * KS + 1, 1, 3); }
     }
     SCPP_HD void cone_margin(const double *u, double &mn, double &nrm2) const
     {
@@ -1874,7 +1886,8 @@ struct Ipm {
         if (have_prev && st_.warm > 0. && st_.warm < 1.) {
             // previous interior point of this instance, pulled back from the boundary; pinned variables keep their values
             const double lw = st_.warm, lc = 1. - st_.warm;
-            FOR_LANE(k, K) { for (int i = 0; i < NB; i++) if (fixed(k, i)) prim[i * KS + k] = fixv[k * NB + i]; }
+            FOR_LANE(k, K) { for (int i = 0; i < NB; i++) if (fixed(k, i)) prim[i * KS + k] = fixv[k * NB + i]; if (scvx) prim[NB * KS + k] = tr_rad; }
+            if (scvx && lane_id() == 0) { prim[PSN * KS] = sigbar; prim[PSN * KS + 1] = 0.; }
             FOR_LANE(e, m) { s[e] *= lw; z[e] *= lw; }
             warp_sync();
             cone_shift(s, lc); cone_shift(z, lc);
@@ -1885,7 +1898,7 @@ struct Ipm {
             FOR_LANE(e, np) prim[e] = 0.;
             FOR_LANE(e, m) { s[e] = 0.; z[e] = 0.; }
             warp_sync();
-            FOR_LANE(k, K) { for (int i = 0; i < NB; i++) prim[i * KS + k] = fixed(k, i) ? fixv[k * NB + i] : xibar(k, i); }
+            FOR_LANE(k, K) { for (int i = 0; i < NB; i++) prim[i * KS + k] = fixed(k, i) ? fixv[k * NB + i] : xibar(k, i); if (scvx) prim[NB * KS + k] = tr_rad; }
             if (lane_id() == 0) { prim[PSN * KS] = sigbar; prim[PSN * KS + 1] = 0.; }
             warp_sync();
             cone_shift(s, 1.); cone_shift(z, 1.);
@@ -1950,7 +1963,7 @@ struct Ipm {
         }
         const double cnorm = sqrt(w_time * w_time + w_trs * w_trs + K * w_tr * w_tr + (K - 1) * NX * w_vc * w_vc);
         const double resx0 = fmax(1., cnorm);
-        const int degree = K * (NLP + NCN) + (K - 1) * 2 * NX + 2;
+        const int degree = K * (NLP + NCN) + (K - 1) * 2 * NX + (scvx ? 0 : 2);
         // One slice = factorisation + the two solves of iteration `it`, then update + residuals + termination test of `it+1`,
         // so that the cheap final test never occupies a launch of its own.  A resumed solver re-enters after the test.
         bool past_test = resume;
@@ -2031,7 +2044,7 @@ struct Ipm {
     SCPP_HD void set_part(int w) { k_lo = 32 * w; k_hi = (32 * w + 32 < K) ? 32 * w + 32 : K; }
     SCPP_HD double part_sum(int slot) const { double v = 0; for (int w = 0; w < nparts(); w++) v += part[w * PSTR + slot]; return v; }
     SCPP_HD double part_max(int slot) const { double v = 0; for (int w = 0; w < nparts(); w++) v = fmax(v, part[w * PSTR + slot]); return v; }
-    SCPP_HD int degree() const { return K * (NLP + NCN) + (K - 1) * 2 * NX + 2; }
+    SCPP_HD int degree() const { return K * (NLP + NCN) + (K - 1) * 2 * NX + (scvx ? 0 : 2); }
     // parameters of a solve: mode 1 = affine direction, mode 2 = combined direction (centering from the affine step length)
     SCPP_HD void solve_params(int mode, const double *state, double &csig, double &sigmu, double &rzs) const
     {

@@ -20,7 +20,12 @@ struct ScConfig {
     int keep_history;         // store every iterate (getAllSolutions)
     int ipm_slice;            // interior-point iterations per K2 launch (0: run every sub-problem to the end in one launch)
     IpmSettings ipm;
+    // SCvx variant (SCvx.info, scpp_core/src/SCvxAlgorithm.cpp:23-44); algorithm == 0: SC (everything above), 1: SCvx
+    int algorithm;
+    int pad2_;
+    double scvx_rho_0, scvx_rho_1, scvx_rho_2, scvx_alpha, scvx_beta, scvx_change_threshold, scvx_trust_region;
 };
+constexpr int SCVX_MAX_RESOLVE = 40;   // the reference's re-solve loop of a rejected step has no bound; the engine fails the instance after this many
 
 constexpr int INFO_STRIDE = 10;   // per (instance, iteration): norm1_nu, sum_delta, delta_sigma, sigma, w_tr_used,
                                   //                            ipm_iterations, ipm_status, pres, dres, relgap
@@ -46,6 +51,10 @@ struct ScArrays {
     double *ws;                    // [N][ws_doubles]
     double *ipm_state;             // [N][Ipm::IPM_STATE]  solver state parked between K2 launches ([0] != 0: mid-solve)
     int *frozen;                   // [N] or null: instances whose closed loop has reached the end (skipped by solve and sim_step)
+    // SCvx state (null for SC): trust-region radius, last nonlinear cost (+ flag), solves of the running outer iteration, 1 = a solved
+    // sub-problem waits for its nonlinear cost and the ratio test, candidate iterate, its norm1_nu, per-interval simulated defects
+    double *trust, *last_cost, *n1c, *Xc, *Uc, *costp;
+    int *have_last, *solves, *phase;
     double *hist;                  // [N][max_it+1][K*NB+1] or null
     double *info;                  // [N][max_it][INFO_STRIDE]
     size_t ws_stride;
@@ -76,6 +85,7 @@ SCPP_HD void sc_setup_instance(const ScArrays<M> &a, const ModelParamsHost &P, c
     a.w_tr[n] = cfg.weight_trust_region_trajectory;                            // loadParameters(), SCAlgorithm.cpp:148
     a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
     a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.;
+    if (cfg.algorithm == 1) { a.trust[n] = cfg.scvx_trust_region; a.have_last[n] = 0; a.last_cost[n] = 0.; a.solves[n] = 0; a.phase[n] = 0; }   // loadParameters(), SCvxAlgorithm.cpp:182
     if (a.hist) {
         double *h = a.hist + (size_t)n * (a.max_it + 1) * a.hist_stride();
         for (int k = 0; k < K; k++) { for (int i = 0; i < NX; i++) h[k * NB + i] = X[k * NX + i]; for (int i = 0; i < NU; i++) h[k * NB + NX + i] = U[k * NU + i]; }
@@ -169,6 +179,7 @@ SCPP_HD void sc_bind(const ScArrays<M> &a, const ScConfig &cfg, int n, double *s
     ipm.fixv = a.fixv + (size_t)n * K * NB;
     ipm.w_time = cfg.weight_time; ipm.w_trs = cfg.weight_trust_region_time; ipm.w_vc = cfg.weight_virtual_control;
     ipm.w_tr = a.w_tr[n];
+    if (cfg.algorithm == 1) { ipm.scvx = true; ipm.tr_rad = a.trust[n]; ipm.w_time = 0.; ipm.w_trs = 0.; ipm.w_tr = 0.; }
     ipm.bind(a.ws + (size_t)n * a.ws_stride, smem);
 }
 
@@ -214,6 +225,90 @@ SCPP_HD void sc_finish_instance(const ScArrays<M> &a, const ScConfig &cfg, int n
     warp_sync();
 }
 
+// ---- SCvx, stage 1 of an outer iteration's end (warp, K2 epilogue): readSolution into the CANDIDATE iterate (SCvxAlgorithm.cpp:94,
+// :218-232) and norm1_nu; the nonlinear cost needs a simulation of every interval and runs as its own kernel (sc_scvx_cost), the ratio
+// test after it (sc_scvx_decide)
+template <class M>
+SCPP_HD void sc_scvx_candidate(const ScArrays<M> &a, const ScConfig &cfg, int n, const Ipm<M> &ipm, const IpmResult &r)
+{
+    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU;
+    const int K = a.K;
+    double *Xc = a.Xc + (size_t)n * K * NX, *Uc = a.Uc + (size_t)n * K * NU;
+    const bool ok = (r.status == 0 || r.status == 3);
+    warp_sync();
+    double n1 = 0;
+    if (ok) {
+        FOR_LANE(e, K * NB) { const int k = e / NB, i = e - k * NB; const double v = ipm.xi_at(k, i); if (i < NX) Xc[k * NX + i] = v; else Uc[k * NU + (i - NX)] = v; }
+        FOR_LANE(e, (K - 1) * NX) n1 += ipm.t_at(e / NX, e % NX);            // norm1_nu (:100-101)
+    }
+    n1 = warp_sum(n1);
+    if (lane_id() == 0) {
+        double *inf = a.info + ((size_t)n * a.max_it + a.iters[n]) * INFO_STRIDE;
+        inf[5] = r.iterations; inf[6] = r.status; inf[7] = r.pres; inf[8] = r.dres; inf[9] = r.relgap;
+        a.solves[n] += 1;
+        if (!ok || a.solves[n] > SCVX_MAX_RESOLVE) { a.status[n] = ok ? 1 : r.status; a.converged[n] = 2; a.iters[n] += 1; }   // :87-91 (terminate)
+        else { a.n1c[n] = n1; a.phase[n] = 1; if (r.status == 3) a.status[n] = 3; }
+    }
+    warp_sync();
+}
+// ---- SCvx, stage 2 (thread per (instance, interval)): one term of getNonlinearCost (SCvxAlgorithm.cpp:262-278) for the candidate, in the
+// units the algorithm iterates on
+template <class M>
+SCPP_HD void sc_scvx_cost(const ScArrays<M> &a, const ScConfig &cfg, int n, int k)
+{
+    constexpr int NX = M::NX, NU = M::NU;
+    const int K = a.K;
+    if (a.phase[n] != 1 || k >= K - 1) return;
+    const double *Xc = a.Xc + (size_t)n * K * NX, *Uc = a.Uc + (size_t)n * K * NU;
+    double x[NX];
+    for (int i = 0; i < NX; i++) x[i] = Xc[k * NX + i];
+    rkf78_simulate<M>(x, Uc + k * NU, Uc + (k + 1) * NU, a.par + (size_t)n * M::NP, a.sigma[n] / (K - 1), 20);
+    double c = 0.;
+    for (int i = 0; i < NX; i++) c += fabs(x[i] - Xc[(k + 1) * NX + i]);
+    a.costp[(size_t)n * K + k] = c;
+}
+// ---- SCvx, stage 3 (thread per instance): the ratio test and trust-region update of SCvxAlgorithm::iterate (:96-155)
+template <class M>
+SCPP_HD void sc_scvx_decide(const ScArrays<M> &a, const ScConfig &cfg, int n)
+{
+    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU;
+    const int K = a.K;
+    if (a.phase[n] != 1) return;
+    a.phase[n] = 0;
+    double J = 0.;
+    for (int k = 0; k < K - 1; k++) J += a.costp[(size_t)n * K + k];               // nonlinear_cost (:98)
+    const double L = a.n1c[n];                                                    // linear_cost   (:107-108)
+    const int it = a.iters[n];
+    double *inf = a.info + ((size_t)n * a.max_it + it) * INFO_STRIDE;
+    inf[0] = L; inf[1] = J; inf[2] = 0.; inf[3] = a.trust[n]; inf[4] = a.solves[n];
+    bool accept = true, converged = false;
+    if (!a.have_last[n]) { a.last_cost[n] = J; a.have_last[n] = 1; }              // :110-114
+    else {
+        const double actual = a.last_cost[n] - J, predicted = a.last_cost[n] - L;   // :116-117
+        a.last_cost[n] = J;                                                       // :119 (also when the step is rejected below)
+        if (fabs(predicted) < cfg.scvx_change_threshold) converged = true;        // :126-130
+        else {
+            const double rho = actual / predicted;                                // :132
+            inf[2] = rho;
+            if (rho < cfg.scvx_rho_0) { a.trust[n] /= cfg.scvx_alpha; accept = false; }            // :133-139  td = old_td
+            else if (rho < cfg.scvx_rho_1) a.trust[n] /= cfg.scvx_alpha;          // :144-148
+            else if (rho >= cfg.scvx_rho_2) a.trust[n] *= cfg.scvx_beta;          // :149-153
+        }
+    }
+    if (!accept) return;                                                          // same outer iteration: solve again with the smaller radius
+    double *X = a.X + (size_t)n * K * NX, *U = a.U + (size_t)n * K * NU;
+    const double *Xc = a.Xc + (size_t)n * K * NX, *Uc = a.Uc + (size_t)n * K * NU;
+    for (int e = 0; e < K * NX; e++) X[e] = Xc[e];
+    for (int e = 0; e < K * NU; e++) U[e] = Uc[e];
+    a.iters[n] = it + 1; a.solves[n] = 0;
+    if (converged) a.converged[n] = 1;
+    if (a.hist) {
+        double *h = a.hist + ((size_t)n * (a.max_it + 1) + it + 1) * a.hist_stride();
+        for (int k = 0; k < K; k++) { for (int i = 0; i < NX; i++) h[k * NB + i] = X[k * NX + i]; for (int i = 0; i < NU; i++) h[k * NB + NX + i] = U[k * NU + i]; }
+        h[K * NB] = a.sigma[n];
+    }
+}
+
 // ---- K2 + K3, monolithic: advance the sub-problem of instance n by one slice; when it is solved: K3 ----
 // SCAlgorithm::iterate, SCAlgorithm.cpp:78-131 (the defect print :85-92 is diagnostic only and not computed)
 template <class M>
@@ -222,10 +317,11 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
     Ipm<M> ipm;
     sc_bind(a, cfg, n, smem, ipm);
     bool finished;
-    const IpmResult r = ipm.solve(cfg.ipm, a.iters[n] > 0 && a.status[n] != 2, cfg.ipm_slice > 0 ? cfg.ipm_slice : (cfg.ipm_slice < 0 ? 1 : (1 << 30)),
+    const bool have_prev = (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2;
+    const IpmResult r = ipm.solve(cfg.ipm, have_prev, cfg.ipm_slice > 0 ? cfg.ipm_slice : (cfg.ipm_slice < 0 ? 1 : (1 << 30)),
                                   a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE, finished);
     if (!finished) return;                                                   // continues in the next launch
-    sc_finish_instance(a, cfg, n, ipm, r);
+    if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r);
 }
 
 // ---- K2 + K3, split pipeline (cfg.ipm_slice < 0): the steps of one interior-point iteration, each called by its own kernel ----
@@ -245,14 +341,14 @@ SCPP_HD void sc_split_step(const ScArrays<M> &a, const ScConfig &cfg, int n, dou
     sc_bind(a, cfg, n, smem, ipm);
     IpmResult r;
     if (STEP == SP_START) {
-        if (ipm.sp_start(cfg.ipm, a.iters[n] > 0 && a.status[n] != 2, state, r)) sc_finish_instance(a, cfg, n, ipm, r);
+        if (ipm.sp_start(cfg.ipm, (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2, state, r)) { if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r); }
     } else if (STEP == SP_ASSEMBLE) {
         if (sub >= a.K) return;
         ipm.tables_init();
         ipm.assemble_stage(sub);
     } else if (STEP == SP_FACTOR) ipm.sp_factor(state);
     else if (STEP == SP_CHAIN) ipm.sp_chain(mode, state);
-    else if (STEP == SP_TEST) { if (ipm.sp_test(cfg.ipm, state, r)) sc_finish_instance(a, cfg, n, ipm, r); }
+    else if (STEP == SP_TEST) { if (ipm.sp_test(cfg.ipm, state, r)) { if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r); } }
     else {
         if (sub >= ipm.nparts()) return;
         ipm.cst_init();

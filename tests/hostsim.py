@@ -26,7 +26,9 @@ class ScConfig(C.Structure):
                 ("weight_time", C.c_double), ("weight_trust_region_time", C.c_double),
                 ("weight_trust_region_trajectory", C.c_double), ("weight_virtual_control", C.c_double),
                 ("nu_tol", C.c_double), ("delta_tol", C.c_double), ("max_iterations", C.c_int), ("nsub", C.c_int),
-                ("keep_history", C.c_int), ("ipm_slice", C.c_int), ("ipm", IpmSettings)]
+                ("keep_history", C.c_int), ("ipm_slice", C.c_int), ("ipm", IpmSettings),
+                ("algorithm", C.c_int), ("pad2_", C.c_int), ("scvx_rho_0", C.c_double), ("scvx_rho_1", C.c_double), ("scvx_rho_2", C.c_double),
+                ("scvx_alpha", C.c_double), ("scvx_beta", C.c_double), ("scvx_change_threshold", C.c_double), ("scvx_trust_region", C.c_double)]
 
 
 def build():
@@ -73,6 +75,20 @@ def sc_config(ocfg, nsub=20, tol=1e-9, maxit=100, history=True, warm=0.0, ipm_sl
         setattr(c, f, getattr(ocfg, f))
     c.nsub = nsub; c.keep_history = int(history); c.ipm_slice = ipm_slice
     c.ipm.feastol = tol; c.ipm.abstol = tol; c.ipm.reltol = tol; c.ipm.maxit = maxit; c.ipm.warm = warm
+    return c
+
+
+def scvx_config(ov, final_time_free=False, nsub=20, tol=1e-8, maxit=100, history=True, warm=0.0, ipm_slice=1):
+    """orc_py.SCvxConfig -> ScConfig with algorithm = 1 (SCvx)"""
+    c = ScConfig()
+    c.K = ov.K; c.free_final_time = 1; c.interpolate_input = ov.interpolate_input; c.nondimensionalize = ov.nondimensionalize
+    c.weight_time = 0.; c.weight_trust_region_time = 0.; c.weight_trust_region_trajectory = 0.; c.weight_virtual_control = ov.weight_virtual_control
+    c.nu_tol = 0.; c.delta_tol = 0.; c.max_iterations = ov.max_iterations
+    c.nsub = nsub; c.keep_history = int(history); c.ipm_slice = ipm_slice
+    c.ipm.feastol = tol; c.ipm.abstol = tol; c.ipm.reltol = tol; c.ipm.maxit = maxit; c.ipm.warm = warm
+    c.algorithm = 1
+    c.scvx_rho_0 = ov.rho_0; c.scvx_rho_1 = ov.rho_1; c.scvx_rho_2 = ov.rho_2; c.scvx_alpha = ov.alpha; c.scvx_beta = ov.beta
+    c.scvx_change_threshold = ov.change_threshold; c.scvx_trust_region = ov.trust_region
     return c
 
 

@@ -391,3 +391,40 @@ def test_ragged_batch_sizes_and_a_failing_instance(S):
     assert np.isfinite(s3["X"]).all() and np.array_equal(s3["X"][0], s3["X"][1])
     with pytest.raises(S.ScppError):
         S.load_model("Rocket2D", K=2) and S.SCAlgorithm(*S.load_model("Rocket2D", K=2)[:2], S.load_model("Rocket2D", K=2)[4], 1)
+
+
+def test_scvx_vs_oracle(S):
+    """SCvx on the device (algorithm = 1): nominal Falcon-9 instance and perturbed ones, K = 30, the reference's SCvx.info.  Parity on the
+    common prefix of identical accept/reject decisions (the ratio test branches on the sign of rho, see tests/test_host.py); every
+    instance the oracle solves converges here too"""
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", algorithm="SCvx", keep_history=1)
+    assert cfg.algorithm == 1 and cfg.K == 30 and cfg.max_iterations == 30
+    cfg.ipm.warm = 0.995
+    p, rpy = O.falcon9()
+    plist = [p] + [O.rq_perturb(p, rpy, 0x5C99, i) for i in (0, 2, 3)]
+    xi = np.array([list(q.x_init) for q in plist])
+    eng = S.SCAlgorithm(model, params, cfg, len(plist))
+    eng.set_boundary_states(xi, x_final)
+    eng.solve()
+    sol = eng.get_solution(); info = eng.get_info(); Xh, Uh, th = eng.get_all_solutions()
+    eng.close()
+    ocfg = O.scvx_config(K=30, model=O.ROCKETQUAT)
+    for i, q in enumerate(plist):
+        ro = O.scvx_solve(O.ROCKETQUAT, q, ocfg)
+        assert ro["converged"] and sol["flags"][i] == 1 and abs(int(sol["iterations"][i]) - ro["iterations"]) <= 6
+        m = 0
+        for it in range(min(ro["iterations"], int(sol["iterations"][i]))):
+            a = ro["info"][it]
+            if a.solves != int(info[i, it, 4]) or abs(a.trust_region_used - info[i, it, 3]) > 1e-12 * a.trust_region_used:
+                break
+            m += 1
+        assert m >= 3
+        for it in range(m + 1):
+            assert np.abs(Xh[i, it] - ro["X_all"][it]).max() < 5e-5 and np.abs(Uh[i, it] - ro["U_all"][it]).max() < 5e-6
+        for it in range(m):
+            assert abs(ro["info"][it].norm1_nu - info[i, it, 0]) < 1e-5 * ro["info"][it].norm1_nu
+            assert abs(ro["info"][it].nonlinear_cost - info[i, it, 1]) < 2e-4 * ro["info"][it].nonlinear_cost
+    # the nominal instance takes the oracle's decisions to the end
+    ro = O.scvx_solve(O.ROCKETQUAT, p, ocfg)
+    assert int(sol["iterations"][0]) == ro["iterations"]
+    assert np.allclose(sol["X"][0], ro["X"], rtol=1e-4, atol=1e-4 * np.abs(ro["X"]).max())

@@ -289,3 +289,52 @@ def test_k5_lqr_gain_source_vs_oracle():
     for k in (0, 10, 29):
         A, B = O.jac(1, X[k], U[k], par)
         assert np.linalg.eigvals(A - B @ G2[k]).real.max() < 0
+
+
+def _scvx_common_prefix(ro, info_h, n_h):
+    """number of leading outer iterations in which both runs took the same decisions (solves per iteration, trust region used)"""
+    m = 0
+    for it in range(min(abs(ro["iterations"]), n_h)):
+        a = ro["info"][it]
+        if a.solves != int(info_h[it, 4]) or abs(a.trust_region_used - info_h[it, 3]) > 1e-12 * a.trust_region_used:
+            break
+        m += 1
+    return m
+
+
+@pytest.mark.parametrize("warm", [0.0, 0.995])
+def test_scvx_source_vs_oracle_nominal(warm):
+    """SCvx variant (SCvxProblem.cpp:6-71, SCvxAlgorithm.cpp:61-164) in the kernel source -- trust-region cone on the input rows with a
+    pinned radius, pinned sigma, K4 cost, ratio test -- against the oracle's literal loop on the reference's RocketQuat SCvx.info:
+    same decisions, same radii, converged in the same iteration; iterates to 5e-5 / 5e-6 (the sub-problem minimises only |nu|_1, its
+    states are weakly determined, so the SC bar of 1e-5 is not reachable between two interior-point codes)"""
+    p = O.falcon9()[0]
+    ocfg = O.scvx_config(K=30, model=0)
+    ro = O.scvx_solve(0, p, ocfg)
+    P, xi, xf = H.params_from_oracle(0, p)
+    rh = H.sc_solve(0, P, H.scvx_config(ocfg, tol=1e-8, warm=warm), xi, xf)
+    n = ro["iterations"]
+    assert n > 5 and ro["converged"] and rh["iters"][0] == n and rh["converged"][0] == 1
+    for it in range(n + 1):
+        assert np.abs(rh["X_all"][0, it] - ro["X_all"][it]).max() < 5e-5 and np.abs(rh["U_all"][0, it] - ro["U_all"][it]).max() < 5e-6
+    for it in range(n):
+        a, h = ro["info"][it], rh["info"][0, it]
+        assert abs(a.norm1_nu - h[0]) < 1e-5 * a.norm1_nu and abs(a.nonlinear_cost - h[1]) < 2e-4 * a.nonlinear_cost
+        assert abs(a.rho - h[2]) < 2e-3 * max(1.0, abs(a.rho))
+    assert abs(ro["info"][n - 1].trust_region_used - rh["info"][0, n - 1, 3]) < 1e-12
+
+
+def test_scvx_source_vs_oracle_perturbed_prefix():
+    """SCvx branches on the sign of rho (rho_0 = 0): when the actual change is ~0 the accept/reject decision flips on rounding noise
+    and the two runs part ways (both still converge).  Parity is therefore asserted on the common prefix of identical decisions."""
+    p, rpy = O.falcon9()
+    pp = O.rq_perturb(p, rpy, 0x5C99, 0)
+    ocfg = O.scvx_config(K=30, model=0)
+    ro = O.scvx_solve(0, pp, ocfg)
+    P, xi, xf = H.params_from_oracle(0, pp)
+    rh = H.sc_solve(0, P, H.scvx_config(ocfg, tol=1e-8, warm=0.995), xi, xf)
+    assert ro["converged"] and rh["converged"][0] == 1 and abs(rh["iters"][0] - ro["iterations"]) <= 6
+    m = _scvx_common_prefix(ro, rh["info"][0], rh["iters"][0])
+    assert m >= 3
+    for it in range(m + 1):
+        assert np.abs(rh["X_all"][0, it] - ro["X_all"][it]).max() < 5e-5 and np.abs(rh["U_all"][0, it] - ro["U_all"][it]).max() < 5e-6
