@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="instances per GPU (weak scaling)")
     ap.add_argument("--K", type=int, default=K_BENCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--algorithm", default="SC", choices=["SC", "SCvx"], help="SC (default, the measured path) or the SCvx variant (no CPU baseline arm)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -169,7 +170,9 @@ def main():
     if S.device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU path)")
 
-    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=args.K)
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=args.K, algorithm=args.algorithm)
+    if args.algorithm == "SCvx":
+        args.no_cpu_baseline = True
     # interior warm start of the sub-problems (engine knob, same optimum; parity-tested in tests/test_gpu_parity.py);
     # SCPP_WARM=0 gives ECOS-style cold starts
     cfg.ipm.warm = float(os.environ.get("SCPP_WARM", "0.995"))
@@ -266,7 +269,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": stats[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.K, n_local),
+                "config": {"workload": workload_name(args.K, n_local) if args.algorithm == "SC" else workload_name(args.K, n_local).replace("free-final-time SC", "fixed-final-time SCvx").replace("max_iterations=15", f"max_iterations={cfg.max_iterations}"),
                            "batch_per_gpu": n_local, "global_batch": n_local * world, "K": args.K, "parallelism": f"instances sharded x{world}",
                            "l2": f"working set {eng.device_bytes() / 1e6:.0f} MB per GPU >> 126 MB L2 (no flush needed)",
                            "integrator": (f"RK4 x {cfg.nsub}" if cfg.nsub > 0 else f"RK4 x {-cfg.nsub} and x {-2 * cfg.nsub}, Richardson-extrapolated") + " (reference RKF78 x 5)", "ipm_tol": cfg.ipm.feastol, "ipm_warm": cfg.ipm.warm, "ipm_slice": cfg.ipm_slice},

