@@ -425,6 +425,6 @@ def test_scvx_vs_oracle(S):
         assert m >= 3, (i, m)
         for it in range(m):
             assert abs(ro["info"][it].norm1_nu - info[i, it, 0]) < 1e-4 * ro["info"][it].norm1_nu
-            assert abs(ro["info"][it].nonlinear_cost - info[i, it, 1]) < 1e-3 * ro["info"][it].nonlinear_cost
+            assert abs(ro["info"][it].nonlinear_cost - info[i, it, 1]) < 5e-3 * ro["info"][it].nonlinear_cost
         Jo, Jg = ro["info"][-1].nonlinear_cost, info[i, n - 1, 1]
         assert abs(Jo - Jg) < 0.05 * Jo
