@@ -114,6 +114,7 @@ SCPP_HD void sc_warm_instance(const ScArrays<M> &a, const ModelParamsHost &P, co
     }
     a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
     a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.;
+    if (cfg.algorithm == 1) { a.solves[n] = 0; a.phase[n] = 0; }   // the radius and last_nonlinear_cost are members the reference does not reset on a warm start
     if (a.hist) {
         double *h = a.hist + (size_t)n * (a.max_it + 1) * a.hist_stride();
         for (int k = 0; k < K; k++) { for (int i = 0; i < NX; i++) h[k * NB + i] = X[k * NX + i]; for (int i = 0; i < NU; i++) h[k * NB + NX + i] = U[k * NU + i]; }
