@@ -24,10 +24,20 @@ def run(model, p, K, max_it):
                 iterations=np.array(r["iterations"]), converged=np.array(int(r["converged"])), info=info)
 
 
+def run_scvx(model, p, K):
+    cfg = O.scvx_config(K=K, model=model)
+    r = O.scvx_solve(model, p, cfg)
+    info = np.array([[i.norm1_nu, i.nonlinear_cost, i.rho, i.trust_region_used, i.solves, i.ipm.iterations, i.ipm.status, i.ipm.pres, i.ipm.dres, i.ipm.relgap]
+                     for i in r["info"]])
+    return dict(X_all=r["X_all"], U_all=r["U_all"], X=r["X"], U=r["U"], t=np.array(r["t"]), iterations=np.array(r["iterations"]),
+                converged=np.array(int(r["converged"])), info=info)
+
+
 if __name__ == "__main__":
     O.build()
     np.savez_compressed(os.path.join(HERE, "rocket2d_K30.npz"), **run(O.ROCKET2D, O.rocket2d(), 30, 15))
     p, rpy = O.falcon9()
     np.savez_compressed(os.path.join(HERE, "rocketquat_K20_nominal.npz"), **run(O.ROCKETQUAT, p, 20, 5))
     np.savez_compressed(os.path.join(HERE, "rocketquat_K50_inst7.npz"), **run(O.ROCKETQUAT, O.rq_perturb(p, rpy, 0x5C99, 7), 50, 4))
+    np.savez_compressed(os.path.join(HERE, "rocketquat_scvx_K30_nominal.npz"), **run_scvx(O.ROCKETQUAT, p, 30))
     print("written", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))

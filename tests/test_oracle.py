@@ -320,3 +320,17 @@ def test_lqr_restatement_against_scipy_care():
         Kref = np.linalg.solve(np.diag(r), B.T @ P)
         assert np.abs(K - Kref).max() < 1e-10 * np.abs(Kref).max()
         assert np.linalg.eigvals(A - B @ K).real.max() < 0          # stabilising
+
+
+def test_scvx_oracle_reproduces_committed_fixture():
+    """tests/golden/rocketquat_scvx_K30_nominal.npz (oracle-generated): the SCvx restatement on the reference's RocketQuat SCvx.info --
+    16 outer iterations, converged; pins the oracle (equilibration, regularisation, ratio-test loop) against drift"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rocketquat_scvx_K30_nominal.npz"))
+    p, _ = O.falcon9()
+    r = O.scvx_solve(O.ROCKETQUAT, p, O.scvx_config(K=30, model=O.ROCKETQUAT))
+    assert r["iterations"] == int(g["iterations"]) == 16 and int(r["converged"]) == int(g["converged"]) == 1
+    assert np.allclose(r["X_all"], g["X_all"], atol=1e-9) and np.allclose(r["U_all"], g["U_all"], atol=1e-9)
+    assert np.array_equal(np.array([i.solves for i in r["info"]]), g["info"][:, 4].astype(int))
+    J = g["info"][:, 1]
+    assert J[-1] < 0.15 * J[0]                                 # the nonlinear defect falls by an order of magnitude
