@@ -346,3 +346,19 @@ def test_scvx_source_vs_oracle_perturbed_prefix():
     assert m >= 3
     Jo, Jh = ro["info"][-1].nonlinear_cost, rh["info"][0, n - 1, 1]
     assert abs(Jo - Jh) < 0.05 * Jo
+
+
+def test_scvx_info_loader(S, tmp_path):
+    """scpp_b200_load_scvx_info == SCvxAlgorithm::loadParameters (SCvxAlgorithm.cpp:23-44) on the shipped SCvx.info values; a missing
+    key raises like the reference's ParameterServer"""
+    for name, K, thr, nd, mit in (("RocketQuat", 30, 1e-3, 1, 30), ("Rocket2D", 30, 1e-2, 0, 20)):
+        model, params, xi, xf, cfg = S.load_model(name, algorithm="SCvx")
+        assert cfg.algorithm == 1 and cfg.K == K and cfg.max_iterations == mit and cfg.nondimensionalize == nd and cfg.interpolate_input == 1
+        assert (cfg.scvx_rho_0, cfg.scvx_rho_1, cfg.scvx_rho_2, cfg.scvx_alpha, cfg.scvx_beta) == (0.0, 0.25, 0.9, 2.0, 3.2)
+        assert cfg.scvx_change_threshold == thr and cfg.weight_virtual_control == 1e3 and cfg.scvx_trust_region == 5.0
+    bad = tmp_path / "SCvx.info"
+    bad.write_text("K 30\nnondimensionalize true\nmax_iterations 5\n")
+    with pytest.raises(S.ScppError):
+        S.load_scvx_info(str(bad), S.ROCKETQUAT)
+    cfg = S.default_config(S.ROCKETQUAT)
+    assert cfg.algorithm == 0
