@@ -2195,7 +2195,7 @@ struct Ipm {
         nm.gap = part_sum(0); nm.rz2 = part_sum(1); nm.pcost = part_sum(2); nm.zrz = part_sum(3); nm.rx2 = part_sum(4); nm.xrx = part_sum(5);
         nm.h2 = part_sum(6); nm.bad = part_max(7) != 0.; nm.acc_sig = part_sum(PT_ACC);
         const bool failed = state[ST_FAIL] != 0.;
-        if (!failed) { residual_couple(nm); residual_globals(nm, false); }
+        if (!failed) { residual_couple(nm); if (!scvx) residual_globals(nm, false); }
         return test_and_book(st_, nm, (int)state[1] + 1, failed, state, res);
     }
 };

@@ -362,3 +362,13 @@ def test_scvx_info_loader(S, tmp_path):
         S.load_scvx_info(str(bad), S.ROCKETQUAT)
     cfg = S.default_config(S.ROCKETQUAT)
     assert cfg.algorithm == 0
+
+
+def test_scvx_in_the_split_pipeline_source():
+    """SCvx mode of every step of the split pipeline (K = 30: one 32-stage part, so the sums are the monolithic kernel's): identical iterates"""
+    p = O.falcon9()[0]
+    ocfg = O.scvx_config(K=30, model=0, max_iterations=8)
+    P, xi, xf = H.params_from_oracle(0, p)
+    a = H.sc_solve(0, P, H.scvx_config(ocfg, tol=1e-8, warm=0.995, ipm_slice=1), xi, xf)
+    b = H.sc_solve(0, P, H.scvx_config(ocfg, tol=1e-8, warm=0.995, ipm_slice=-1), xi, xf)
+    assert a["iters"][0] == b["iters"][0] == 8 and np.array_equal(a["X_all"], b["X_all"]) and np.array_equal(a["U_all"], b["U_all"])
