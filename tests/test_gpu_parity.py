@@ -428,3 +428,13 @@ def test_scvx_vs_oracle(S):
             assert abs(ro["info"][it].nonlinear_cost - info[i, it, 1]) < 5e-3 * ro["info"][it].nonlinear_cost
         Jo, Jg = ro["info"][-1].nonlinear_cost, info[i, n - 1, 1]
         assert abs(Jo - Jg) < 0.05 * Jo
+
+
+def test_cpp_host_mirror_runs_sc_and_scvx(S, tmp_path):
+    """the C++ host mirror (include/scpp_b200.hpp) end to end on the device: SC and SCvx for the nominal RocketQuat instance"""
+    import subprocess
+    exe = str(tmp_path / "cpp_mirror")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp_mirror.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "scpp_b200"), "-lscpp_b200", "-Wl,-rpath," + os.path.join(ROOT, "scpp_b200")])
+    out = subprocess.run([exe, os.path.join(ROOT, "configs"), "gpu"], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok (GPU)" in out.stdout and "flag=1" in out.stdout, out.stdout + out.stderr

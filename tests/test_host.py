@@ -372,3 +372,21 @@ def test_scvx_in_the_split_pipeline_source():
     a = H.sc_solve(0, P, H.scvx_config(ocfg, tol=1e-8, warm=0.995, ipm_slice=1), xi, xf)
     b = H.sc_solve(0, P, H.scvx_config(ocfg, tol=1e-8, warm=0.995, ipm_slice=-1), xi, xf)
     assert a["iters"][0] == b["iters"][0] == 8 and np.array_equal(a["X_all"], b["X_all"]) and np.array_equal(a["U_all"], b["U_all"])
+
+
+def _build_cpp_mirror(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "cpp_mirror")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp_mirror.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "scpp_b200"), "-lscpp_b200", "-Wl,-rpath," + os.path.join(ROOT, "scpp_b200")])
+    return exe
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_a_gpu(S, tmp_path):
+    """include/scpp_b200.hpp (SCAlgorithm / SCvxAlgorithm with the reference's method names) builds against the C-ABI library; parameter
+    loading and the error behaviour work on the host; with no CUDA device initialize() throws 'no CUDA device' (no fallback)"""
+    import subprocess
+    if S.device_count() > 0:
+        pytest.skip("a GPU is present (covered by the gpu-marked test)")
+    out = subprocess.run([_build_cpp_mirror(tmp_path), os.path.join(ROOT, "configs")], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok (no GPU)" in out.stdout, out.stdout + out.stderr
