@@ -169,7 +169,9 @@ int scpp_b200_simulate(int model, int n, double dt, int device, double *x, const
 int scpp_b200_selftest_blockops(int device, double *max_abs_err);
 
 /* ---- multi-GPU: one process (rank) per GPU, the batch is sharded by the caller ----------------------------------
- * the only data-path collective is one ncclAllGather of the per-instance convergence flags per outer iteration. */
+ * the only data-path collective is one ncclAllGather of the per-instance convergence flags per outer iteration.
+ * Shards may differ in size (N_total % nranks != 0): comm_init all-gathers the shard sizes and every rank contributes max(N) flag bytes,
+ * its padding marked 'done'.  comm_init is collective: every rank must call it. */
 int scpp_b200_comm_unique_id(char id[128]);
 int scpp_b200_comm_init(scpp_b200_engine *e, int nranks, int rank, const char id[128]);
 long long scpp_b200_global_active(scpp_b200_engine *e); /* instances still iterating over all ranks after the last solve */

@@ -375,7 +375,9 @@ int orc_sc_solve2(int model, const void *params, const orc_sc_config *cfg,
                                    model == ORC_MODEL_ROCKETQUAT ? tdir : NULL,
                                    X, U, &sigma, NULL, delta, &norm1_nu, &delta_sigma, &ipm);  /* :78, readSolution :100 */
         double t2 = now_ms();
-        if (st != 0) { failed = 1; if (inf) { memset(inf, 0, sizeof(*inf)); inf->ipm = ipm; } break; } /* :94-98 (terminate) */
+        /* status 3 = reduced accuracy (ECOS: ECOS_OPTIMAL + ECOS_INACC_OFFSET, "close to optimal"): the iteration continues, as in the engine;
+         * how Epigraph's ECOSSolver::solve maps that exit code to its bool result cannot be checked here (submodule absent) */
+        if (st != 0 && st != 3) { failed = 1; if (inf) { memset(inf, 0, sizeof(*inf)); inf->ipm = ipm; } break; } /* :94-98 (terminate) */
         t = cfg->free_final_time ? sigma : t;                                       /* :193-196 */
         double sum_delta = 0;
         for (int k = 0; k < K; k++) sum_delta += delta[k];                          /* :105-107 */
@@ -671,7 +673,7 @@ int orc_scvx_solve(int model, const void *params, const orc_scvx_config *cfg,
                                          model == ORC_MODEL_ROCKETQUAT ? tdir : NULL, X, U, NULL, &norm1_nu, &ipm);   /* :81, readSolution :94 */
             solves++;
             if (inf) { inf->ipm = ipm; inf->solves = solves; }
-            if (st != 0 || solves > ORC_SCVX_MAX_RESOLVE) { failed = 1; break; }    /* :87-91 (terminate) */
+            if ((st != 0 && st != 3) || solves > ORC_SCVX_MAX_RESOLVE) { failed = 1; break; }    /* :87-91 (terminate) */
             const double J = orc_scvx_nonlinear_cost(model, K, X, U, t, par);       /* :98 */
             const double L = norm1_nu;                                              /* :100-108 */
             if (inf) { inf->norm1_nu = norm1_nu; inf->nonlinear_cost = J; inf->trust_region_used = trust_region; }

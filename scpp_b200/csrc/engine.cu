@@ -224,6 +224,7 @@ struct scpp_b200_engine {
     virtual int get_info(double *info) = 0;
     virtual int sim_step(double time_step, double *x_new, double *u0, int *reached) = 0;
     virtual int lqr_gains(const double *q_diag, const double *r_diag, double *gains, int *ok) = 0;
+    virtual int comm_buffers() = 0;
     int model = 0, N = 0, device = 0;
     ModelParamsHost P;
     ScConfig cfg;
@@ -244,16 +245,20 @@ struct EngineT : scpp_b200_engine {
     int *active[2] = {nullptr, nullptr}, *disc = nullptr;
     int *counter = nullptr;               // [0] next active count, [1] instances starting a new sub-problem
     std::vector<int> h_iters;
+    std::vector<unsigned char> h_flags;
     unsigned long long *gcount = nullptr;
     unsigned char *flags = nullptr, *flags_all = nullptr;
     double *Xo = nullptr, *Uo = nullptr;
     double *sim_x = nullptr, *sim_u = nullptr;   // outputs of the closed-loop step (K4)
     int *sim_r = nullptr;
+    double *lqr_q = nullptr, *lqr_g = nullptr;   // K5 buffers (first use)
+    int *lqr_ok = nullptr;
     int *h_counter = nullptr;             // pinned
     unsigned long long *h_gcount = nullptr;
     std::vector<void *> allocs;
     bool have_states = false, solved_once = false;
     int n_sm = 148;
+    int N_pad = 0;                         // multi-GPU: flag bytes every rank contributes (max shard size)
 
     template <class T>
     int dalloc(T **p, size_t n)
@@ -351,7 +356,7 @@ struct EngineT : scpp_b200_engine {
         // solved), (3) re-forms the lists and exchanges the flag bytes.  With ipm_slice == 0 a slice is a whole sub-problem and
         // the rounds are the reference's outer iterations in lock-step.
         const int slice_eff = cfg.ipm_slice < 0 ? 1 : cfg.ipm_slice;
-        const long long max_rounds = (long long)cfg.max_iterations * (cfg.algorithm == 1 ? SCVX_MAX_RESOLVE + 1 : 1) * (slice_eff > 0 ? (cfg.ipm.maxit + 3) / slice_eff + 2 : 1) + 1;
+        const long long max_rounds = (long long)cfg.max_iterations * (cfg.algorithm == 1 ? SCVX_MAX_RESOLVE + 1 : 1) * (slice_eff > 0 ? (cfg.ipm.maxit + 3 + 8) / slice_eff + 2 : 1) + 1;   // + 8: rounds repeated after a regularised re-factorisation
         for (long long round = 0; round < max_rounds && global_active > 0; round++) {
             CU(cudaEventRecord(ev[1], stream));
             if (n_disc > 0) {
@@ -426,10 +431,10 @@ struct EngineT : scpp_b200_engine {
             // all-gather per outer iteration; a rank that runs out of work idles through at most 9 empty rounds before everyone agrees to stop
             const bool exchange = comm && (slice_eff == 0 || (round + 1) % 10 == 0);
             if (exchange) {
-                int rc = g_nccl.AllGather(flags, flags_all, (size_t)N, /*ncclUint8*/ 1, comm, stream);
+                int rc = g_nccl.AllGather(flags, flags_all, (size_t)N_pad, /*ncclUint8*/ 1, comm, stream);
                 if (rc != 0) return fail(SCPP_B200_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
                 CU(cudaMemsetAsync(gcount, 0, sizeof(unsigned long long), stream));
-                const long long tot = (long long)N * nranks;
+                const long long tot = (long long)N_pad * nranks;
                 k_count_zero<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(flags_all, tot, gcount);
                 launches++;
                 CU(cudaMemcpyAsync(h_gcount, gcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -447,10 +452,14 @@ struct EngineT : scpp_b200_engine {
             else if (exchange) global_active = (long long)*h_gcount;
         }
         // SC iterations done: per instance (reported as instance-iterations) and the largest count (outer iterations)
-        h_iters.resize(N);
+        h_iters.resize(N); h_flags.resize(N);
         CU(cudaMemcpyAsync(h_iters.data(), a.iters, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(h_flags.data(), flags, (size_t)N, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
-        for (int n = 0; n < N; n++) { inst_iters += h_iters[n]; if (h_iters[n] > outer) outer = h_iters[n]; }
+        for (int n = 0; n < N; n++) {
+            if (h_flags[n] == 8) continue;                          // frozen in the closed loop: not solved, a.iters is the count of an earlier solve
+            inst_iters += h_iters[n]; if (h_iters[n] > outer) outer = h_iters[n];
+        }
         CU(cudaEventRecord(ev[4], stream));
         CU(cudaStreamSynchronize(stream));
         float mt = 0;
@@ -518,8 +527,12 @@ struct EngineT : scpp_b200_engine {
         CU(cudaSetDevice(device));
         const int K = cfg.K;
         const size_t ng = (size_t)N * K * NU * NX;
-        double *dq = nullptr, *dg = nullptr; int *dok = nullptr;
-        CU(cudaMalloc((void **)&dq, sizeof(double) * (NX + NU))); CU(cudaMalloc((void **)&dg, sizeof(double) * ng)); CU(cudaMalloc((void **)&dok, sizeof(int) * N * K));
+        if (!lqr_g) {                                            // engine-owned buffers, allocated on first use, freed with the engine
+            int rc;
+            if ((rc = dalloc(&lqr_q, (size_t)(NX + NU))) || (rc = dalloc(&lqr_g, ng)) || (rc = dalloc(&lqr_ok, (size_t)N * K))) return rc;
+        }
+        double *dq = lqr_q, *dg = lqr_g; int *dok = lqr_ok;
+        CU(cudaMemsetAsync(dg, 0xff, sizeof(double) * ng, stream));       // NaN: a gain Lqr::gain does not write (sign iteration not converged, ok = 0) is never garbage
         CU(cudaMemcpyAsync(dq, q_diag, sizeof(double) * NX, cudaMemcpyHostToDevice, stream));
         CU(cudaMemcpyAsync(dq + NX, r_diag, sizeof(double) * NU, cudaMemcpyHostToDevice, stream));
         const int smem = int(4 * Lqr<M>::sm_doubles() * sizeof(double));
@@ -529,8 +542,30 @@ struct EngineT : scpp_b200_engine {
         CU(cudaMemcpyAsync(gains, dg, sizeof(double) * ng, cudaMemcpyDeviceToHost, stream));
         if (ok) CU(cudaMemcpyAsync(ok, dok, sizeof(int) * N * K, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
-        cudaFree(dq); cudaFree(dg); cudaFree(dok);
         CU(cudaGetLastError());
+        return 0;
+    }
+    // flag exchange buffers.  Shards may have different sizes (N_total % nranks != 0): every rank sends N_pad = max over ranks of N bytes,
+    // the bytes beyond its own N are a constant non-zero 'done' flag, so ncclAllGather sees equal counts and the padding never counts as active.
+    int comm_buffers() override
+    {
+        int *dn = nullptr;
+        std::vector<int> hn(nranks, 0);
+        CU(cudaMalloc((void **)&dn, sizeof(int) * (nranks + 1)));
+        CU(cudaMemcpyAsync(dn + nranks, &N, sizeof(int), cudaMemcpyHostToDevice, stream));
+        int rc = g_nccl.AllGather(dn + nranks, dn, 1, /*ncclInt32*/ 2, comm, stream);
+        if (rc != 0) { cudaFree(dn); return fail(SCPP_B200_ERR_NCCL, std::string("ncclAllGather(N): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); }
+        CU(cudaMemcpyAsync(hn.data(), dn, sizeof(int) * nranks, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        cudaFree(dn);
+        N_pad = N;
+        for (int r = 0; r < nranks; r++) if (hn[r] > N_pad) N_pad = hn[r];
+        unsigned char *fp = nullptr, *fa = nullptr;
+        CU(cudaMalloc((void **)&fp, (size_t)N_pad)); allocs.push_back(fp);
+        CU(cudaMalloc((void **)&fa, (size_t)N_pad * nranks)); allocs.push_back(fa);
+        CU(cudaMemsetAsync(fp, 1, (size_t)N_pad, stream));
+        CU(cudaStreamSynchronize(stream));
+        flags = fp; flags_all = fa;
         return 0;
     }
     int get_info(double *info) override
@@ -839,12 +874,7 @@ int scpp_b200_comm_init(scpp_b200_engine *e, int nranks, int rank, const char id
     int rc = g_nccl.CommInitRank(&e->comm, nranks, uid, rank);
     if (rc) return fail(SCPP_B200_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     e->nranks = nranks; e->rank = rank;
-    // flags of all ranks
-    unsigned char *fa = nullptr;
-    CU(cudaMalloc((void **)&fa, (size_t)e->N * nranks));
-    if (e->model == SCPP_B200_MODEL_ROCKETQUAT) { auto *t = static_cast<EngineT<RocketQuat> *>(e); t->flags_all = fa; t->allocs.push_back(fa); }
-    else { auto *t = static_cast<EngineT<Rocket2d> *>(e); t->flags_all = fa; t->allocs.push_back(fa); }
-    return 0;
+    return e->comm_buffers();
 }
 
 } // extern "C"

@@ -797,6 +797,20 @@ struct Ipm {
         warp_sync();
     }
 
+    // Adaptive cap on the scalings z/s of the virtual-control pairs where they enter the MATRIX of the condensed Newton system (assembly and
+    // the elimination / recovery of t).  Near a sub-problem optimum every pair with nu_ki = 0 is active on both sides and z/s grows like
+    // 1/mu.  When the optimal cost is zero (SCvx: the linearised dynamics can be met exactly, scpp_core/src/SCvxProblem.cpp:27) nothing else
+    // bounds the reduced Hessian from below in the input directions and the block-tridiagonal Schur complements have to cancel
+    // D a'a ~ 1e13 down to the O(1) curvature of the node terms: a pivot turns non-positive.  ECOS survives this case because it factors
+    // the un-condensed quasi-definite KKT matrix with static regularisation delta: W^2 -> W^2 + delta, i.e. z/s -> 1/(s/z + delta).  The
+    // same modification is applied here ON DEMAND: a failed factorisation is repeated with z/s capped at dcap = 1e10, 1e9, ... (DCAP_MIN),
+    // and the cap stays for the rest of that sub-problem.  Right-hand sides, the primal step ds (taken from the primal Newton equation)
+    // and the step lengths keep the true scalings, so the iterate stays interior and the residuals stay exact; only dz of the capped rows
+    // is damped.  (Capping unconditionally doubles the iteration count of ordinary sub-problems: measured, DESIGN.md.)
+    static constexpr double DCAP_FIRST = 1e10, DCAP_MIN = 1e7;
+    double dcap = 0.;        // 0: no cap
+    SCPP_HD double capd(double d) const { return (dcap > 0. && d > dcap) ? dcap : d; }
+    SCPP_HD bool tighten_cap() { dcap = (dcap == 0.) ? DCAP_FIRST : dcap * 0.1; return dcap >= DCAP_MIN; }
     // Cholesky factor of the NB x NB block H (lower triangle valid, row-major in the shared window) and its inverse Li = L^-1.
     // Device: lane i keeps row i of H in registers; column j is scaled by rsqrt of the pivot (broadcast by shuffle) and the
     // trailing update takes L[c][j] from lane c by shuffle, fully unrolled (153 DFMA).  L goes back to the window, then lane c
@@ -906,7 +920,7 @@ struct Ipm {
         warp_sync();
         // ---- interval k: H_kk += A~' D A~ ; O = [-D A~ ; C' D A~] ; carry = (D, D C, C' D C) ; borders
         if (hasint) {
-            FOR_LANE(i, NX) { const double dm = WB[MN + i], dp = WB[MN + NX + i]; Dt[i] = 4. * dm * dp / (dm + dp); }
+            FOR_LANE(i, NX) { const double dm = capd(WB[MN + i]), dp = capd(WB[MN + NX + i]); Dt[i] = 4. * dm * dp / (dm + dp); }
             warp_sync();
             // O rows of the x_{k+1} block are -D A~ ; keep D A~ for the products: O[a][b], a < NX
             FOR_LANE(e, NX * NB) { const int a = e / NB, b = e - a * NB; O[a * NB + b] = -Dt[a] * t[a * NCP + b]; }
@@ -1116,7 +1130,7 @@ struct Ipm {
         tables_stage(TD);
         // ---- carry of interval k-1
         if (k > 0) {
-            FOR_LANE(i, NX) { const double dm = WBp[i], dp = WBp[NX + i]; Dp[i] = 4. * dm * dp / (dm + dp); }
+            FOR_LANE(i, NX) { const double dm = capd(WBp[i]), dp = capd(WBp[NX + i]); Dp[i] = 4. * dm * dp / (dm + dp); }
             warp_sync();
             FOR_LANE(e, NX * NU) DCp[e] = Dp[e / NU] * Cp[e];
             warp_sync();
@@ -1376,9 +1390,9 @@ struct Ipm {
                 };
                 auto do_row = [&](int i, const double *cur) {
                     const int o = MN + i;
-                    const double dm = cur[NB + 1], dp = cur[NB + 2];
-                    const double rm = lp_rzv(mode, csig, sigmu, dm, cur[NB + 4], cur[NB + 6], cur[NB + 8]);
-                    const double rp = lp_rzv(mode, csig, sigmu, dp, cur[NB + 5], cur[NB + 7], cur[NB + 9]);
+                    const double rm = lp_rzv(mode, csig, sigmu, cur[NB + 1], cur[NB + 4], cur[NB + 6], cur[NB + 8]);
+                    const double rp = lp_rzv(mode, csig, sigmu, cur[NB + 2], cur[NB + 5], cur[NB + 7], cur[NB + 9]);
+                    const double dm = capd(cur[NB + 1]), dp = capd(cur[NB + 2]);      // matrix side: capped (see dcap)
                     if (mode != 0) { ds[o * KS + k] = rm; ds[(o + NX) * KS + k] = rp; }
                     const double rho = (-(dm * rm + dp * rp) + cur[NB + 3]) / (dm + dp);
                     const double wi = dm * (rm + rho) - dp * (rp + rho);
@@ -1691,7 +1705,7 @@ struct Ipm {
 #pragma unroll
                     for (int a = 0; a < NU; a++) acc2 -= cur[NB + a] * XNu[a];
                     const double ady = acc + acc2 - cur[NB + NU] * ysig;
-                    const double dm = cur[NT + 1], dp = cur[NT + 2];
+                    const double dm = capd(cur[NT + 1]), dp = capd(cur[NT + 2]);
                     const double qm = ady - cur[NT + 3], qp = -ady - cur[NT + 4];
                     const double dt = (cur[NT + 5] + dm * qm + dp * qp) / (dm + dp);
                     const double dzm = dm * (qm - dt), dzp = dp * (qp - dt);
@@ -1701,13 +1715,13 @@ struct Ipm {
                         const double dsm = rzs * cur[NT + 6] - (ady - dt), dsp = rzs * cur[NT + 7] - (-ady - dt);
                         ds[o * KS + k] = dsm; ds[(o + NX) * KS + k] = dsp;
                         {
-                            const double iw = sqrt(dm), il = 1. / cur[NT + 8];
+                            const double iw = sqrt(cur[NT + 1]), il = 1. / cur[NT + 8];
                             const double dzt = dzm / iw, dst = dsm * iw;
                             tmax = fmax(tmax, fmax(-dst, -dzt) * il);
                             if (mode == 1) cr[o * KS + k] = dst * dzt;
                         }
                         {
-                            const double iw = sqrt(dp), il = 1. / cur[NT + 9];
+                            const double iw = sqrt(cur[NT + 2]), il = 1. / cur[NT + 9];
                             const double dzt = dzp / iw, dst = dsp * iw;
                             tmax = fmax(tmax, fmax(-dst, -dzt) * il);
                             if (mode == 1) cr[(o + NX) * KS + k] = dst * dzt;
@@ -1954,7 +1968,7 @@ struct Ipm {
         double best = 1e300, pending = 0.;
         int it = 0;
         if (resume) {
-            it = (int)state[1]; pending = state[2]; best = state[3];
+            it = (int)state[1]; pending = state[2]; best = state[3]; dcap = state[ST_DCAP];
             res.pres = state[4]; res.dres = state[5]; res.gap = state[6]; res.relgap = state[7]; res.pcost = state[8]; res.iterations = (int)state[9];
         } else {
             const int how = init_point(st_, have_prev);
@@ -1998,7 +2012,7 @@ struct Ipm {
                     if (lane_id() == 0) {
                         state[0] = 1.; state[1] = it; state[2] = pending; state[3] = best;
                         state[4] = res.pres; state[5] = res.dres; state[6] = res.gap; state[7] = res.relgap; state[8] = res.pcost; state[9] = res.iterations;
-                        state[10] = gap_cur;
+                        state[10] = gap_cur; state[ST_DCAP] = dcap;
                     }
                     warp_sync();
                     finished = false;
@@ -2007,7 +2021,9 @@ struct Ipm {
             }
             past_test = false;
             budget--;
-            if (!phase_factor()) { res.status = 2; break; }
+            bool factored = phase_factor();
+            while (!factored && tighten_cap()) factored = phase_factor();        // numerically indefinite: regularise (see dcap) and repeat
+            if (!factored) { res.status = 2; break; }
             double tmax;
             phase_solve(1, 1., 0., -1., tmax);                               // affine direction
             const double a_aff = tmax <= 1. ? 1. : 1. / tmax;
@@ -2018,7 +2034,7 @@ struct Ipm {
         if (res.status != 0) {
             if (best <= 1e4) { FOR_LANE(e, np) prim[e] = best_[e]; }
             warp_sync();
-            if (best <= 10.) res.status = 0; else if (best <= 1e4) res.status = 3;
+            if (best <= 1e4) res.status = 3;      // best iterate inside the accuracy band but short of the tolerances: reduced accuracy
         } else res.iterations = it;
         if (lane_id() == 0) state[0] = 0.;
         warp_sync();
@@ -2038,7 +2054,7 @@ struct Ipm {
     //  state: [0] 0 idle / 1 mid-solve  [1] it  [2] pending (monolithic slices)  [3] best  [4..9] best iterate's result
     //         [10] gap of the current iterate  [11] l_ss  [12] factorisation failed  [13..23] Glob of the running solve
     // =============================================================================================================
-    static constexpr int ST_LSS = 11, ST_FAIL = 12, ST_GLOB = 13;
+    static constexpr int ST_LSS = 11, ST_FAIL = 12, ST_GLOB = 13, ST_DCAP = 24;
     static constexpr int PT_ACC = 8, PT_GSIG = 9, PT_TAFF = 10, PT_TCMB = 11;
     SCPP_HD int nparts() const { return (K + 31) / 32; }
     SCPP_HD void set_part(int w) { k_lo = 32 * w; k_hi = (32 * w + 32 < K) ? 32 * w + 32 : K; }
@@ -2072,7 +2088,9 @@ struct Ipm {
     SCPP_HD void sp_factor(double *state)
     {
         const bool ok = chain_factor();
-        if (lane_id() == 0) { state[ST_LSS] = l_ss; state[ST_FAIL] = ok ? 0. : 1.; }
+        // numerically indefinite: tighten the cap (see dcap); 2 = the rest of this round is skipped and the next round repeats the iteration
+        const bool retry = !ok && tighten_cap();
+        if (lane_id() == 0) { state[ST_LSS] = l_ss; state[ST_FAIL] = ok ? 0. : (retry ? 2. : 1.); state[ST_DCAP] = dcap; }
         warp_sync();
     }
     SCPP_HD void sp_rhs(int mode, const double *state, int w)
@@ -2166,6 +2184,7 @@ struct Ipm {
                 state[0] = 1.; state[1] = it; state[2] = 0.; state[3] = best;
                 state[4] = res.pres; state[5] = res.dres; state[6] = res.gap; state[7] = res.relgap; state[8] = res.pcost; state[9] = res.iterations;
                 state[10] = gap_cur; state[ST_FAIL] = 0.;
+                if (it == 0) state[ST_DCAP] = 0.;
             }
             warp_sync();
             return false;
@@ -2173,7 +2192,7 @@ struct Ipm {
         if (res.status != 0) {
             if (best <= 1e4) { FOR_LANE(e, np) prim[e] = best_[e]; }
             warp_sync();
-            if (best <= 10.) res.status = 0; else if (best <= 1e4) res.status = 3;
+            if (best <= 1e4) res.status = 3;      // best iterate inside the accuracy band but short of the tolerances: reduced accuracy
         } else res.iterations = it;
         if (lane_id() == 0) state[0] = 0.;
         warp_sync();
@@ -2194,6 +2213,7 @@ struct Ipm {
         Norms nm;
         nm.gap = part_sum(0); nm.rz2 = part_sum(1); nm.pcost = part_sum(2); nm.zrz = part_sum(3); nm.rx2 = part_sum(4); nm.xrx = part_sum(5);
         nm.h2 = part_sum(6); nm.bad = part_max(7) != 0.; nm.acc_sig = part_sum(PT_ACC);
+        if (state[ST_FAIL] == 2.) { if (lane_id() == 0) state[ST_FAIL] = 0.; warp_sync(); return false; }
         const bool failed = state[ST_FAIL] != 0.;
         if (!failed) { residual_couple(nm); if (!scvx) residual_globals(nm, false); }
         return test_and_book(st_, nm, (int)state[1] + 1, failed, state, res);

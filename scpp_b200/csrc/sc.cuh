@@ -340,6 +340,7 @@ SCPP_HD void sc_split_step(const ScArrays<M> &a, const ScConfig &cfg, int n, dou
     }
     Ipm<M> ipm;
     sc_bind(a, cfg, n, smem, ipm);
+    if (STEP != SP_START) ipm.dcap = state[Ipm<M>::ST_DCAP];
     IpmResult r;
     if (STEP == SP_START) {
         if (ipm.sp_start(cfg.ipm, (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2, state, r)) { if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r); }

@@ -438,3 +438,167 @@ def test_cpp_host_mirror_runs_sc_and_scvx(S, tmp_path):
                            "-L" + os.path.join(ROOT, "scpp_b200"), "-lscpp_b200", "-Wl,-rpath," + os.path.join(ROOT, "scpp_b200")])
     out = subprocess.run([exe, os.path.join(ROOT, "configs"), "gpu"], capture_output=True, text=True)
     assert out.returncode == 0 and "ok (GPU)" in out.stdout and "flag=1" in out.stdout, out.stdout + out.stderr
+
+
+# ---- round 2: parity at the shapes that are measured ------------------------------------------------------------------------
+def _oracle_many(fn, items, threads=None):
+    """the oracle on several instances at once (ctypes releases the GIL; one instance per host thread)"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 4)) as ex:
+        return list(ex.map(fn, items))
+
+
+def _status_fractions(info, iters):
+    """fractions of the solved sub-problems by exit status: 0 = tolerances met, 3 = reduced accuracy (best iterate inside the band)"""
+    st = np.concatenate([info[i, :n, 6] for i, n in enumerate(iters)]).astype(int)
+    sc = np.concatenate([np.maximum(info[i, :n, 7], info[i, :n, 8]) for i, n in enumerate(iters)])
+    return {s: float((st == s).mean()) for s in (0, 1, 2, 3)}, float(sc.max())
+
+
+def test_bench_shape_sample_from_the_full_batch(S):
+    """BASELINE.json configs[1] exactly as bench.py runs it (1024 perturbed RocketQuat instances, K = 50, interior warm start, one
+    interior-point iteration per launch, Richardson RK4): 64 randomly indexed instances OF THAT BATCH against the oracle, all 15 iterates,
+    plus the exit-status census of the 15 360 sub-problems"""
+    N = 1024
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50, keep_history=1)
+    cfg.ipm.warm = 0.995
+    xi = S.perturbed_initial_states(x_init, RPY_F9, N)
+    eng = S.SCAlgorithm(model, params, cfg, N)
+    eng.set_boundary_states(xi, x_final)
+    eng.solve()
+    sol = eng.get_solution(); info = eng.get_info(); Xh, Uh, th = eng.get_all_solutions()
+    eng.close()
+    idx = np.sort(np.random.default_rng(2024).choice(N, 64, replace=False))
+    p, rpy = O.falcon9()
+    ocfg = O.sc_config(K=50, max_iterations=cfg.max_iterations)
+    ros = _oracle_many(lambda i: O.sc_solve(O.ROCKETQUAT, O.rq_perturb(p, rpy, 0x5C99, int(i)), ocfg), idx)
+    worst = (0.0, 0.0)
+    for i, ro in zip(idx, ros):
+        n = abs(ro["iterations"])
+        assert ro["iterations"] > 0 and sol["iterations"][i] == n and (sol["flags"][i] == 1) == ro["converged"]
+        assert np.allclose(Xh[i, 0], ro["X_all"][0], atol=1e-12)          # the batch generator and the oracle's perturbation are the same instance
+        for it in range(n + 1):
+            dX = np.abs(Xh[i, it] - ro["X_all"][it]).max(); dU = np.abs(Uh[i, it] - ro["U_all"][it]).max()
+            assert dX < TOL_X and dU < TOL_U, f"instance {i} iterate {it}: dX {dX:.2e} dU {dU:.2e}"
+            worst = (max(worst[0], dX), max(worst[1], dU))
+        for it in range(n):
+            assert info[i, it, 4] == ro["info"][it].weight_tr_used
+    frac, resid = _status_fractions(info, sol["iterations"])
+    print(f"\n[bench shape] worst |dX| {worst[0]:.2e} |dU| {worst[1]:.2e}; sub-problem exits: {frac}; worst residual {resid:.2e}")
+    # every sub-problem ends with its tolerances met (0) or, at the accuracy floor of the condensed system, inside the 10x band (3)
+    assert frac[1] == 0.0 and frac[2] == 0.0 and frac[3] <= 0.35 and resid < 1e-6
+
+
+def test_converging_rocketquat_workload(S):
+    """NON-REFERENCE weights (w_tr = 2, w_vc = 1e4, nu_tol = 1e-3, delta_tol = 1e-2 instead of SC.info's 50 / 1e3 / 1e-5 / 1e-3), found by
+    experiment: with the shipped weights no RocketQuat instance converges.  Here some instances converge after 6-7
+    iterations and others run to the limit, so convergence (SCAlgorithm.cpp:131), weight doubling (:112-115), early exit and the
+    compaction of an unevenly finishing batch run on nx = 14.  Same decisions as the oracle, iterates to 1e-5 / 1e-4 over the first
+    iterations and for every instance that converges (a stalled loop re-solves a weakly determined problem: late iterates of the
+    non-converging instances drift to ~1e-4)."""
+    over = dict(weight_trust_region_trajectory=2.0, weight_virtual_control=1e4, nu_tol=1e-3, delta_tol=1e-2)
+    ids = [8, 20, 22, 0, 4, 5, 12, 15, 17, 19]
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50, max_iterations=20, keep_history=1, **over)
+    p, rpy = O.falcon9()
+    plist = [p] + [O.rq_perturb(p, rpy, 0x5C99, i) for i in ids]
+    xi = np.array([list(q.x_init) for q in plist])
+    eng = S.SCAlgorithm(model, params, cfg, len(plist))
+    eng.set_boundary_states(xi, x_final)
+    eng.solve()
+    sol = eng.get_solution(); info = eng.get_info(); Xh, Uh, th = eng.get_all_solutions()
+    eng.close()
+    ocfg = O.sc_config(K=50, max_iterations=20)
+    for k, v in over.items():
+        setattr(ocfg, k, v)
+    ros = _oracle_many(lambda q: O.sc_solve(O.ROCKETQUAT, q, ocfg), plist)
+    n_conv = 0
+    for i, ro in enumerate(ros):
+        n = abs(ro["iterations"])
+        assert ro["iterations"] > 0 and sol["iterations"][i] == n and (sol["flags"][i] == 1) == ro["converged"], (i, sol["iterations"][i], ro["iterations"])
+        n_conv += int(ro["converged"])
+        upto = n if ro["converged"] else 6
+        for it in range(upto + 1):
+            dX = np.abs(Xh[i, it] - ro["X_all"][it]).max(); dU = np.abs(Uh[i, it] - ro["U_all"][it]).max()
+            assert dX < TOL_X and dU < TOL_U, f"instance {i} iterate {it}: dX {dX:.2e} dU {dU:.2e}"
+        for it in range(n):
+            assert info[i, it, 4] == ro["info"][it].weight_tr_used
+    assert n_conv >= 4 and n_conv < len(plist)            # a mixed batch: early exits next to instances that use every iteration
+    assert len(set(int(v) for v in sol["iterations"])) >= 3
+
+
+def test_starship_k100_batch(S):
+    """BASELINE.json configs[4]: Starship parameters, K = 100, 32 perturbed instances, all 15 iterations against the oracle"""
+    ps, rpys = O.starship()
+    plist = [ps] + [O.rq_perturb(ps, rpys, 0x5C99, i) for i in range(31)]
+    _compare_run_threaded(S, "RocketQuatStarship", plist, K=100, max_it=15, warm=0.995)
+
+
+def _compare_run_threaded(S, name, plist, K, max_it, warm=0.0):
+    model, params, x_init, x_final, cfg = S.load_model(name, K=K, max_iterations=max_it, keep_history=1)
+    cfg.ipm.warm = warm
+    xi = np.array([list(q.x_init) for q in plist])
+    eng = S.SCAlgorithm(model, params, cfg, len(plist))
+    eng.set_boundary_states(xi, x_final)
+    eng.solve()
+    sol = eng.get_solution(); info = eng.get_info(); Xh, Uh, th = eng.get_all_solutions()
+    eng.close()
+    ocfg = O.sc_config(K=K, max_iterations=max_it)
+    ros = _oracle_many(lambda q: O.sc_solve(O.ROCKETQUAT, q, ocfg), plist)
+    for i, ro in enumerate(ros):
+        n = abs(ro["iterations"])
+        assert ro["iterations"] > 0 and sol["iterations"][i] == n and (sol["flags"][i] == 1) == ro["converged"]
+        for it in range(n + 1):
+            dX = np.abs(Xh[i, it] - ro["X_all"][it]).max(); dU = np.abs(Uh[i, it] - ro["U_all"][it]).max()
+            assert dX < TOL_X and dU < TOL_U, f"instance {i} iterate {it}: dX {dX:.2e} dU {dU:.2e}"
+        for it in range(n):
+            assert info[i, it, 4] == ro["info"][it].weight_tr_used
+
+
+def test_scvx_k50_full_batch_no_failures_and_oracle_sample(S):
+    """the metric's own shape for the SCvx variant: K = 50, 1024 perturbed instances.  (1) no instance ends flagged: sub-problems whose
+    optimal cost is zero used to lose positive definiteness (2.7 % of the batch in round 1); the on-demand regularisation (ipm.cuh: dcap)
+    carries them through.  (2) a sample of the batch against the oracle: same convergence, the leading accepted iterates to north_star's
+    1e-5 / 1e-4 (the loop is not reproducible decision by decision once rounding decides a ratio test, see test_scvx_vs_oracle)."""
+    N = 1024
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", algorithm="SCvx", K=50, keep_history=1)
+    cfg.ipm.warm = 0.995
+    xi = S.perturbed_initial_states(x_init, RPY_F9, N)
+    eng = S.SCAlgorithm(model, params, cfg, N)
+    eng.set_boundary_states(xi, x_final)
+    eng.solve()
+    sol = eng.get_solution(); info = eng.get_info(); Xh, Uh, th = eng.get_all_solutions()
+    eng.close()
+    failed = float((sol["flags"] == 2).mean())
+    print(f"\n[SCvx K=50 x {N}] failed fraction {failed}, converged fraction {(sol['flags'] == 1).mean():.3f}, mean outer iterations {sol['iterations'].mean():.1f}")
+    assert failed == 0.0
+    assert (sol["flags"] == 1).mean() > 0.95
+    idx = [24, 29, 93, 7, 100, 513, 777, 1000]              # 24, 29, 93: zero-cost second sub-problem (failed in round 1)
+    p, rpy = O.falcon9()
+    ocfg = O.scvx_config(K=50, model=O.ROCKETQUAT)
+    ros = _oracle_many(lambda i: O.scvx_solve(O.ROCKETQUAT, O.rq_perturb(p, rpy, 0x5C99, int(i)), ocfg), idx)
+    lead, xs = [], []
+    for i, ro in zip(idx, ros):
+        n = int(sol["iterations"][i])
+        if ro["iterations"] <= 0:
+            continue                                        # the oracle's own solver gave up on this instance (zero-cost sub-problem)
+        assert ro["converged"] and sol["flags"][i] == 1
+        # The sub-problem minimises |nu|_1 alone: U and the costs are unique, X is only weakly determined (states trade against virtual
+        # control at equal cost; DESIGN.md).  Leading iterates are counted on U, norm1_nu and the nonlinear cost; X is recorded beside them.
+        m, zero_cost = 0, False
+        for it in range(1, min(ro["iterations"], n) + 1):
+            a = ro["info"][it - 1]
+            if a.norm1_nu < 1e-8:      # optimal cost zero: the optimal set is a face, U is not unique either; the two loops part here and both converge
+                zero_cost = True
+                break
+            if (np.abs(Uh[i, it] - ro["U_all"][it]).max() < TOL_U and abs(a.norm1_nu - info[i, it - 1, 0]) < 1e-4 * max(a.norm1_nu, 1e-6)
+                    and abs(a.nonlinear_cost - info[i, it - 1, 1]) < 5e-3 * a.nonlinear_cost):
+                m = it
+                xs.append(np.abs(Xh[i, it] - ro["X_all"][it]).max() < TOL_X)
+            else:
+                break
+        if not zero_cost:
+            lead.append(m)
+        Jo, Jg = ro["info"][-1].nonlinear_cost, info[i, n - 1, 1]
+        assert abs(Jo - Jg) < 0.05 * max(Jo, 1e-3), (i, Jo, Jg)
+    print(f"[SCvx K=50] leading iterates equal to the oracle's (U to 1e-4, costs): {lead}; of those with X to 1e-5: {np.mean(xs):.2f}")
+    assert len(lead) >= 4 and min(lead) >= 3 and np.mean(xs) >= 0.6
