@@ -176,6 +176,7 @@ def main():
     # interior warm start of the sub-problems (engine knob, same optimum; parity-tested in tests/test_gpu_parity.py);
     # SCPP_WARM=0 gives ECOS-style cold starts
     cfg.ipm.warm = float(os.environ.get("SCPP_WARM", "0.995"))
+    cfg.solver = int(os.environ.get("SCPP_SOLVER", "1"))      # 1: CTA-per-instance solver (round 2); 0: warp-per-instance rounds (round 1)
     cfg.ipm_slice = int(os.environ.get("SCPP_SLICE", "1"))    # interior-point iterations per K2 launch (0: lock-step outer iterations)
     rpy = np.deg2rad([-20.0, 20.0, 0.0])      # rpy_init of configs/RocketQuat/model.info
     n_local = args.batch

@@ -80,7 +80,7 @@ typedef struct {
      * For SCvx, scpp_b200_get_info returns per outer iteration: norm1_nu, nonlinear cost, rho, trust region used, sub-problem solves,
      * ipm_iterations, ipm_status, pres, dres, relgap. */
     int algorithm;
-    int pad2_;
+    int solver;
     double scvx_rho_0, scvx_rho_1, scvx_rho_2, scvx_alpha, scvx_beta, scvx_change_threshold, scvx_trust_region;
 } scpp_b200_sc_config;
 

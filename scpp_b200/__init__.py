@@ -39,7 +39,7 @@ class SCConfig(C.Structure):
                 ("weight_trust_region_trajectory", C.c_double), ("weight_virtual_control", C.c_double),
                 ("nu_tol", C.c_double), ("delta_tol", C.c_double), ("max_iterations", C.c_int), ("nsub", C.c_int),
                 ("keep_history", C.c_int), ("ipm_slice", C.c_int), ("ipm", IpmSettings),
-                ("algorithm", C.c_int), ("pad2_", C.c_int), ("scvx_rho_0", C.c_double), ("scvx_rho_1", C.c_double), ("scvx_rho_2", C.c_double),
+                ("algorithm", C.c_int), ("solver", C.c_int), ("scvx_rho_0", C.c_double), ("scvx_rho_1", C.c_double), ("scvx_rho_2", C.c_double),
                 ("scvx_alpha", C.c_double), ("scvx_beta", C.c_double), ("scvx_change_threshold", C.c_double), ("scvx_trust_region", C.c_double)]
 
 

@@ -56,5 +56,26 @@ SCPP_HD void mm(FA fa, FB fb, FC fc)
 #endif
 }
 
+// One 8 x 8 output tile (mi, ni) of the same product (Kd = 4 KT): the unit of work when several warps share a block product.
+template <int KT, class FA, class FB, class FC>
+SCPP_HD void mm_tile(int mi, int ni, FA fa, FB fb, FC fc)
+{
+#if defined(__CUDA_ARCH__)
+    const int lane = lane_id(), g = lane >> 2, t = lane & 3;
+    double c0 = 0., c1 = 0.;
+#pragma unroll
+    for (int kk = 0; kk < KT; kk++) dmma(c0, c1, fa(mi * 8 + g, kk * 4 + t), fb(kk * 4 + t, ni * 8 + g));
+    fc(mi * 8 + g, ni * 8 + 2 * t, c0);
+    fc(mi * 8 + g, ni * 8 + 2 * t + 1, c1);
+#else
+    for (int m = mi * 8; m < mi * 8 + 8; m++)
+        for (int n = ni * 8; n < ni * 8 + 8; n++) {
+            double v = 0.;
+            for (int k = 0; k < 4 * KT; k++) v += fa(m, k) * fb(k, n);
+            fc(m, n, v);
+        }
+#endif
+}
+
 } // namespace blk
 } // namespace scpp

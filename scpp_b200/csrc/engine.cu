@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -125,6 +126,27 @@ __global__ void k_compact(const int *__restrict__ active, int n_active, const in
         if (ipm_state[(size_t)n * state_stride] == 0.) disc[atomicAdd(counters + 1, 1)] = n;
     }
 }
+// longest-processing-time-first order of the work queue of the CTA-per-instance solver: the instances whose previous sub-problem took the
+// most interior-point iterations are handed out first, so the last CTAs to finish a round hold short sub-problems (counting sort by that
+// iteration count, descending; one block; the order inside a bucket does not matter: instances are independent)
+__global__ void __launch_bounds__(1024) k_lpt_order(const int *__restrict__ in, int *__restrict__ out, int n, const int *__restrict__ iters,
+                                                    const double *__restrict__ info, int max_it)
+{
+    __shared__ int hist[128], base[128];
+    for (int b = threadIdx.x; b < 128; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    auto key = [&](int inst) {
+        const int it = iters[inst];
+        int kx = it > 0 ? (int)info[((size_t)inst * max_it + (it - 1)) * INFO_STRIDE + 5] : 127;
+        return kx < 0 ? 0 : (kx > 127 ? 127 : kx);
+    };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[key(in[i])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { int acc = 0; for (int b = 127; b >= 0; b--) { base[b] = acc; acc += hist[b]; } }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const int inst = in[i]; out[atomicAdd(&base[key(inst)], 1)] = inst; }
+}
+
 __global__ void k_count_zero(const unsigned char *__restrict__ flags, long long n, unsigned long long *__restrict__ out)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,6 +280,8 @@ struct EngineT : scpp_b200_engine {
     std::vector<void *> allocs;
     bool have_states = false, solved_once = false;
     int n_sm = 148;
+    size_t cta_smem = 0;
+    int cta_per_sm = 1, *queue = nullptr, *lpt = nullptr;   // CTA-per-instance solver: shared-memory image, residency, device-side work queue
     int N_pad = 0;                         // multi-GPU: flag bytes every rank contributes (max shard size)
 
     template <class T>
@@ -318,6 +342,17 @@ struct EngineT : scpp_b200_engine {
             CU(cudaFuncSetAttribute(k_sp_warp<M, SP_CHAIN, WPB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsm));
             CU(cudaFuncSetAttribute(k_sp_assemble<M, WPB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WPB_MAX * Ipm<M>::asm_doubles() * sizeof(double))));
         }
+        // CTA-per-instance solver: two CTAs per SM when two shared-memory images fit (K <= ~55), otherwise one
+        cta_smem = (size_t)Ipm<M>::cta_sm_doubles(K) * sizeof(double);
+        cta_per_sm = (2 * (cta_smem + 1024) <= 227 * 1024) ? 2 : 1;
+        if (getenv("SCPP_CTA_PER_SM")) cta_per_sm = atoi(getenv("SCPP_CTA_PER_SM")) == 1 ? 1 : cta_per_sm;      // experiments
+        if (cfg.solver == 1) {
+            if (cta_smem > 227 * 1024) return fail(SCPP_B200_ERR_UNSUPPORTED, "solver = 1 keeps the block factor in shared memory: K too large (use solver = 0)");
+            CU(cudaFuncSetAttribute(k_solve_cta<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cta_smem)));
+            CU(cudaFuncSetAttribute(k_solve_cta<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cta_smem)));
+            int rc2;
+            if ((rc2 = dalloc(&queue, 1)) || (rc2 = dalloc(&lpt, N))) return rc2;
+        }
         CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
         CU(cudaStreamSynchronize(stream));
         return 0;
@@ -355,7 +390,7 @@ struct EngineT : scpp_b200_engine {
         // instance by one slice of cfg.ipm_slice interior-point iterations (K2; K3 runs in its epilogue when a sub-problem is
         // solved), (3) re-forms the lists and exchanges the flag bytes.  With ipm_slice == 0 a slice is a whole sub-problem and
         // the rounds are the reference's outer iterations in lock-step.
-        const int slice_eff = cfg.ipm_slice < 0 ? 1 : cfg.ipm_slice;
+        const int slice_eff = cfg.solver == 1 ? 0 : (cfg.ipm_slice < 0 ? 1 : cfg.ipm_slice);      // solver 1: a round is an outer iteration
         const long long max_rounds = (long long)cfg.max_iterations * (cfg.algorithm == 1 ? SCVX_MAX_RESOLVE + 1 : 1) * (slice_eff > 0 ? (cfg.ipm.maxit + 3 + 8) / slice_eff + 2 : 1) + 1;   // + 8: rounds repeated after a regularised re-factorisation
         for (long long round = 0; round < max_rounds && global_active > 0; round++) {
             CU(cudaEventRecord(ev[1], stream));
@@ -370,8 +405,21 @@ struct EngineT : scpp_b200_engine {
             // ipm_slice == -1: split pipeline in every round; ipm_slice == -T (T > 1): hybrid, split pipeline only in rounds that advance
             // fewer than T instances (the tail of a solve, where one warp per instance leaves the GPU empty); both paths park the solver
             // in the same state, so they can alternate round by round
-            const bool split = cfg.ipm_slice < 0 && parts <= 4 && (cfg.ipm_slice == -1 || n_active < -cfg.ipm_slice);
-            if (split) {
+            const bool split = cfg.solver == 0 && cfg.ipm_slice < 0 && parts <= 4 && (cfg.ipm_slice == -1 || n_active < -cfg.ipm_slice);
+            if (cfg.solver == 1) {
+                if (n_active > 0) {
+                    CU(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+                    const int grid = n_active < n_sm * cta_per_sm ? n_active : n_sm * cta_per_sm;
+                    const int *order = active[cur];
+                    if (n_active > grid && round > 0) {       // more instances than resident CTAs: hand out the long sub-problems first
+                        k_lpt_order<<<1, 1024, 0, stream>>>(active[cur], lpt, n_active, a.iters, a.info, cfg.max_iterations);
+                        order = lpt; launches++;
+                    }
+                    if (cta_per_sm == 2) k_solve_cta<M, 2><<<grid, cta_threads_for(2), cta_smem, stream>>>(a, cfg, order, n_active, queue);
+                    else k_solve_cta<M, 1><<<grid, cta_threads_for(1), cta_smem, stream>>>(a, cfg, order, n_active, queue);
+                    launches++;
+                }
+            } else if (split) {
                 // split pipeline: one interior-point iteration of every unfinished instance as a sequence of kernels (sc.cuh)
                 auto warp_launch = [&](auto kern, const int *list, int n, int mode) {
                     int wpb = (n + n_sm - 1) / n_sm;

@@ -45,7 +45,7 @@ struct HostEngine {
         dd.resize((size_t)N * (K - 1) * NX * NC); ddT.resize((size_t)N * Ipm<M>::ddt_doubles(K));
         a.N = N; a.K = K; a.max_it = cfg.max_iterations;
         a.ws_stride = Ipm<M>::ws_doubles(K);
-        ws.resize((size_t)N * a.ws_stride); smem.resize(Ipm<M>::sm_doubles()); ist.resize((size_t)N * Ipm<M>::IPM_STATE);
+        ws.resize((size_t)N * a.ws_stride); smem.resize(Ipm<M>::sm_doubles() + Ipm<M>::cta_sm_doubles(K)); ist.resize((size_t)N * Ipm<M>::IPM_STATE);
         X.resize((size_t)N * K * NX); U.resize((size_t)N * K * NU); sigma.resize(N);
         hist.resize((size_t)N * (cfg.max_iterations + 1) * (K * NB + 1)); info.resize((size_t)N * cfg.max_iterations * INFO_STRIDE);
         iters.resize(N); status.resize(N); converged.resize(N); frozen.assign(N, 0);
@@ -76,6 +76,11 @@ struct HostEngine {
                 if (a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] == 0.)
                     run_discretize<M>(K, a.X + (size_t)n * K * NX, a.U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg.nsub,
                                       a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K));
+                if (cfg.solver == 1) {
+                    sc_solve_instance_cta<M>(a, cfg, n, smem.data());
+                    if (cfg.algorithm == 1) { for (int k = 0; k < K - 1; k++) sc_scvx_cost<M>(a, cfg, n, k); sc_scvx_decide<M>(a, cfg, n); }
+                    continue;
+                }
                 if (cfg.ipm_slice >= 0) {
                     sc_solve_instance<M>(a, cfg, n, smem.data());
                     if (cfg.algorithm == 1) { for (int k = 0; k < K - 1; k++) sc_scvx_cost<M>(a, cfg, n, k); sc_scvx_decide<M>(a, cfg, n); }   // the cost / decide kernels

@@ -54,6 +54,8 @@ struct IpmResult {
     int status;      // 0 optimal, 1 max iterations, 2 numerical failure, 3 reduced accuracy
     int iterations;
     double pres, dres, gap, relgap, pcost;
+    int point_ok;    // the (s, z) left in the workspace are a valid interior point (false when the last iterate left the cones: no warm start from it)
+    int pad_;
 };
 
 // ---- second-order-cone primitives on small local arrays (dimension <= 4: the model cones) ------------------------------
@@ -174,7 +176,7 @@ struct Ipm {
     SCPP_HD static int n_prim(int K) { return PSN * ks(K) + 2; }
     SCPP_HD static int n_ce(int K) { return NCN * ks(K) + 2; }
     static constexpr int PARTS = 8, PSTR = 16;   // split pipeline: per-warp partial sums of the stage-parallel passes (K <= 32 * PARTS)
-    SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 8 * m_rows(K) + n_ce(K) + (NB + NX + 1) * ks(K) + PARTS * PSTR + K * FS + 16; }
+    SCPP_HD static int ws_doubles(int K) { return 4 * n_prim(K) + 8 * m_rows(K) + n_ce(K) + (NB + 2 * NX + 1) * ks(K) + PARTS * PSTR + K * FS + 16; }
     SCPP_HD static int ddt_doubles(int K) { return NX * NC * ks(K); }
     // Shared window of a warp.  Front: per-solve tables and small vectors (every kernel).  Then a union:
     //   inline factorisation (monolithic kernel):  two tile buffers | record out | L_{k,k-1} | H | O | model terms
@@ -219,6 +221,7 @@ struct Ipm {
     double *gv;            // [NB][KS]  right-hand side g -> forward solution f -> solution y
     double *wv;            // [NX][KS]  w of interval k (coupling to node k+1)
     double *cpart;         // [KS]      corner contribution of interval k (assembly kernel)
+    double *dtv;           // [NX][KS]  D of interval k (CTA-per-instance solver)
     double *part;          // [PARTS][PSTR] partial sums of the split stage-parallel passes
     double *fac;           // [K][FS]
     double *sm;            // per-warp shared window
@@ -235,6 +238,7 @@ struct Ipm {
         gv = p; p += NB * KS;
         wv = p; p += NX * KS;
         cpart = p; p += KS;
+        dtv = p; p += NX * KS;
         part = p; p += PARTS * PSTR;
         fac = p;
         sm = smem;
@@ -1958,7 +1962,7 @@ struct Ipm {
     SCPP_HD IpmResult solve(const IpmSettings &st_, bool have_prev, int budget, double *state, bool &finished)
     {
         IpmResult res;
-        res.status = 1; res.iterations = 0; res.pres = res.dres = res.gap = res.relgap = res.pcost = 0.;
+        res.status = 1; res.iterations = 0; res.pres = res.dres = res.gap = res.relgap = res.pcost = 0.; res.point_ok = 1; res.pad_ = 0;
         const int np = n_prim(K), m = m_rows(K);
         finished = true;
         tables_init();
@@ -2006,7 +2010,7 @@ struct Ipm {
                 // stop on failure, on the iteration limit, on divergence, or at the accuracy floor of the condensed system: once an
                 // iterate within 10x of the tolerances exists and the next one is worse (the dual residual grows with the
                 // conditioning as the gap closes), later iterates only get worse; the best iterate is returned below
-                if (nm.bad || it == st_.maxit || (score > 1e3 * best && best < 1e4) || (best <= 10. && score > best)) { res.status = nm.bad ? 2 : (it == st_.maxit ? 1 : 2); break; }
+                if (nm.bad || it == st_.maxit || (score > 1e3 * best && best < 1e4) || (best <= 10. && score > best)) { res.status = nm.bad ? 2 : (it == st_.maxit ? 1 : 2); res.point_ok = !nm.bad; break; }
                 gap_cur = gap;
                 if (budget <= 0) {                       // out of budget: park the solver state, continue in the next launch
                     if (lane_id() == 0) {
@@ -2054,7 +2058,7 @@ struct Ipm {
     //  state: [0] 0 idle / 1 mid-solve  [1] it  [2] pending (monolithic slices)  [3] best  [4..9] best iterate's result
     //         [10] gap of the current iterate  [11] l_ss  [12] factorisation failed  [13..23] Glob of the running solve
     // =============================================================================================================
-    static constexpr int ST_LSS = 11, ST_FAIL = 12, ST_GLOB = 13, ST_DCAP = 24;
+    static constexpr int ST_LSS = 11, ST_FAIL = 12, ST_GLOB = 13, ST_DCAP = 24, ST_NOPOINT = 25;
     static constexpr int PT_ACC = 8, PT_GSIG = 9, PT_TAFF = 10, PT_TCMB = 11;
     SCPP_HD int nparts() const { return (K + 31) / 32; }
     SCPP_HD void set_part(int w) { k_lo = 32 * w; k_hi = (32 * w + 32 < K) ? 32 * w + 32 : K; }
@@ -2153,7 +2157,7 @@ struct Ipm {
     {
         const int np = n_prim(K);
         double best = (it == 0) ? 1e300 : state[3];
-        res.status = 1;
+        res.status = 1; res.point_ok = 1; res.pad_ = 0;
         if (it == 0) { res.iterations = 0; res.pres = res.dres = res.gap = res.relgap = res.pcost = 0.; }
         else { res.pres = state[4]; res.dres = state[5]; res.gap = state[6]; res.relgap = state[7]; res.pcost = state[8]; res.iterations = (int)state[9]; }
         bool done = false;
@@ -2175,7 +2179,7 @@ struct Ipm {
             }
             if (!nm.bad && pres <= st_.feastol && dres <= st_.feastol && (gap <= st_.abstol || relgap <= st_.reltol)) { res.status = 0; done = true; }
             else if (nm.bad || it == st_.maxit || (score > 1e3 * best && best < 1e4) || (best <= 10. && score > best)) {
-                res.status = nm.bad ? 2 : (it == st_.maxit ? 1 : 2); done = true;
+                res.status = nm.bad ? 2 : (it == st_.maxit ? 1 : 2); res.point_ok = !nm.bad; done = true;
             }
             gap_cur = gap;
         }
@@ -2218,6 +2222,8 @@ struct Ipm {
         if (!failed) { residual_couple(nm); if (!scvx) residual_globals(nm, false); }
         return test_and_book(st_, nm, (int)state[1] + 1, failed, state, res);
     }
+
+#include "ipm_cta.inl"
 };
 
 } // namespace scpp

@@ -36,6 +36,26 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) k_solve(ScArrays<M> a, ScConf
     sc_solve_instance<M>(a, cfg, active[gw], smem + (size_t)warp * Ipm<M>::sm_doubles());
 }
 
+// K2 (+K3), round 2 (cfg.solver == 1): one CTA per instance, persistent CTAs pulling instances from a device-side queue; a CTA keeps its
+// instance for the whole sub-problem (ipm_cta.inl), so an instance that needs 25 interior-point iterations never holds back one that needs 5
+// two CTAs of 4 warps per SM when two shared-memory images fit (K <= ~55), one CTA of 8 warps otherwise: 255 registers per thread either way
+// (the cone arithmetic of a stage needs them: at 128 registers the kernel spills 10 KB per thread and runs 2x slower)
+constexpr int cta_threads_for(int minb) { return minb == 2 ? 128 : 256; }
+template <class M, int MINB>
+__global__ void __launch_bounds__(cta_threads_for(MINB), MINB) k_solve_cta(ScArrays<M> a, ScConfig cfg, const int *__restrict__ active, int n_active, int *__restrict__ queue)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_idx;
+    for (;;) {
+        if (threadIdx.x == 0) s_idx = atomicAdd(queue, 1);
+        __syncthreads();
+        const int idx = s_idx;
+        __syncthreads();
+        if (idx >= n_active) return;
+        sc_solve_instance_cta<M>(a, cfg, active[idx], smem);
+    }
+}
+
 // ---- split pipeline (cfg.ipm_slice < 0): one kernel per step of the interior-point iteration (sc.cuh: sc_split_step) ----
 // warp per instance, full shared window: start of a sub-problem / chain factorisation / substitutions
 template <class M, int STEP, int MAXW>
@@ -94,7 +114,9 @@ __global__ void __launch_bounds__(128, 3) k_sp_stage(ScArrays<M> a, ScConfig cfg
 #define SCPP_ARGS_WARP(M) (ScArrays<M>, ScConfig, const int *, const int *, int, int)
 #define SCPP_ARGS_STAGE(M) (ScArrays<M>, ScConfig, const int *, int, int, int, int)
 #define SCPP_GROUP0(X, M) X template __global__ void k_solve<M, WPB_MAX, 1> SCPP_ARGS_SOLVE(M);
-#define SCPP_GROUP1(X, M)
+#define SCPP_GROUP1(X, M)                                                                  \
+    X template __global__ void k_solve_cta<M, 2>(ScArrays<M>, ScConfig, const int *, int, int *);  \
+    X template __global__ void k_solve_cta<M, 1>(ScArrays<M>, ScConfig, const int *, int, int *);
 #define SCPP_GROUP2(X, M) X template __global__ void k_sp_warp<M, SP_START, WPB_MAX> SCPP_ARGS_WARP(M);
 #define SCPP_GROUP3(X, M)                                                                  \
     X template __global__ void k_sp_warp<M, SP_FACTOR, WPB_MAX> SCPP_ARGS_WARP(M);          \

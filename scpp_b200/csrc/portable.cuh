@@ -65,4 +65,21 @@ inline double warp_bcast(double v, int) { return v; }
 // lanes stride over [0,n)
 #define FOR_LANE(i, n) for (int i = lane_id(); i < (n); i += LANES)
 
+// ---- CTA-wide cooperation (the CTA-per-instance solver, cta_ipm.cuh); the host-simulation build is one thread ----
+#if defined(__CUDA_ARCH__)
+SCPP_D int cta_tid() { return threadIdx.x; }
+SCPP_D int cta_threads() { return blockDim.x; }
+SCPP_D int cta_warp() { return threadIdx.x >> 5; }
+SCPP_D int cta_warps() { return blockDim.x >> 5; }
+SCPP_D void cta_sync() { __syncthreads(); }
+#else
+inline int cta_tid() { return 0; }
+inline int cta_threads() { return 1; }
+inline int cta_warp() { return 0; }
+inline int cta_warps() { return 1; }
+inline void cta_sync() {}
+#endif
+// threads of the CTA stride over [0,n)
+#define FOR_CTA(i, n) for (int i = cta_tid(); i < (n); i += cta_threads())
+
 } // namespace scpp

@@ -22,7 +22,8 @@ struct ScConfig {
     IpmSettings ipm;
     // SCvx variant (SCvx.info, scpp_core/src/SCvxAlgorithm.cpp:23-44); algorithm == 0: SC (everything above), 1: SCvx
     int algorithm;
-    int pad2_;
+    int solver;               // K2 mapping.  0: one warp per instance, one interior-point slice per launch (round 1).  1: one CTA per instance,
+                              // whole sub-problem per launch, factor in shared memory, persistent CTAs pulling from a queue (round 2, ipm_cta.inl)
     double scvx_rho_0, scvx_rho_1, scvx_rho_2, scvx_alpha, scvx_beta, scvx_change_threshold, scvx_trust_region;
 };
 constexpr int SCVX_MAX_RESOLVE = 40;   // the reference's re-solve loop of a rejected step has no bound; the engine fails the instance after this many
@@ -84,7 +85,7 @@ SCPP_HD void sc_setup_instance(const ScArrays<M> &a, const ModelParamsHost &P, c
     a.sigma[n] = P.final_time;
     a.w_tr[n] = cfg.weight_trust_region_trajectory;                            // loadParameters(), SCAlgorithm.cpp:148
     a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
-    a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.;
+    a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.; a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE + Ipm<M>::ST_NOPOINT] = 0.;
     if (cfg.algorithm == 1) { a.trust[n] = cfg.scvx_trust_region; a.have_last[n] = 0; a.last_cost[n] = 0.; a.solves[n] = 0; a.phase[n] = 0; }   // loadParameters(), SCvxAlgorithm.cpp:182
     if (a.hist) {
         double *h = a.hist + (size_t)n * (a.max_it + 1) * a.hist_stride();
@@ -113,7 +114,7 @@ SCPP_HD void sc_warm_instance(const ScArrays<M> &a, const ModelParamsHost &P, co
         if (P.exact_minimum_thrust) M::thrust_dir(U + k * NU, td); else { td[0] = 0.; td[1] = 0.; td[2] = 1.; }
     }
     a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
-    a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.;
+    a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.; a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE + Ipm<M>::ST_NOPOINT] = 0.;
     if (cfg.algorithm == 1) { a.solves[n] = 0; a.phase[n] = 0; }   // the radius and last_nonlinear_cost are members the reference does not reset on a warm start
     if (a.hist) {
         double *h = a.hist + (size_t)n * (a.max_it + 1) * a.hist_stride();
@@ -166,7 +167,7 @@ SCPP_HD void sc_sim_step_instance(const ScArrays<M> &a, const ModelParamsHost &P
 
 // ---- binding of the solver object to instance n ------------------------------------------------------------------
 template <class M>
-SCPP_HD void sc_bind(const ScArrays<M> &a, const ScConfig &cfg, int n, double *smem, Ipm<M> &ipm)
+SCPP_HD void sc_bind(const ScArrays<M> &a, const ScConfig &cfg, int n, double *smem, Ipm<M> &ipm, bool cta = false)
 {
     constexpr int NX = M::NX, NU = M::NU, NB = NX + NU, NC = NX + 2 * NU + 2;
     const int K = a.K;
@@ -181,7 +182,7 @@ SCPP_HD void sc_bind(const ScArrays<M> &a, const ScConfig &cfg, int n, double *s
     ipm.w_time = cfg.weight_time; ipm.w_trs = cfg.weight_trust_region_time; ipm.w_vc = cfg.weight_virtual_control;
     ipm.w_tr = a.w_tr[n];
     if (cfg.algorithm == 1) { ipm.scvx = true; ipm.tr_rad = a.trust[n]; ipm.w_time = 0.; ipm.w_trs = 0.; ipm.w_tr = 0.; }
-    ipm.bind(a.ws + (size_t)n * a.ws_stride, smem);
+    if (cta) ipm.bind_cta(a.ws + (size_t)n * a.ws_stride, smem); else ipm.bind(a.ws + (size_t)n * a.ws_stride, smem);
 }
 
 // ---- K3: readSolution and the convergence logic of SCAlgorithm::iterate (SCAlgorithm.cpp:100-131, 191-210) for a solved sub-problem
@@ -318,11 +319,29 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
     Ipm<M> ipm;
     sc_bind(a, cfg, n, smem, ipm);
     bool finished;
-    const bool have_prev = (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2;
-    const IpmResult r = ipm.solve(cfg.ipm, have_prev, cfg.ipm_slice > 0 ? cfg.ipm_slice : (cfg.ipm_slice < 0 ? 1 : (1 << 30)),
-                                  a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE, finished);
+    double *state = a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE;
+    const bool have_prev = (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2 && state[Ipm<M>::ST_NOPOINT] == 0.;
+    const IpmResult r = ipm.solve(cfg.ipm, have_prev, cfg.ipm_slice > 0 ? cfg.ipm_slice : (cfg.ipm_slice < 0 ? 1 : (1 << 30)), state, finished);
     if (!finished) return;                                                   // continues in the next launch
+    if (lane_id() == 0) state[Ipm<M>::ST_NOPOINT] = r.point_ok ? 0. : 1.;
     if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r);
+}
+
+// ---- K2 + K3, one CTA per instance (cfg.solver == 1): the whole sub-problem of instance n, then K3 on warp 0 ----
+template <class M>
+SCPP_HD void sc_solve_instance_cta(const ScArrays<M> &a, const ScConfig &cfg, int n, double *smem)
+{
+    Ipm<M> ipm;
+    sc_bind(a, cfg, n, smem, ipm, true);
+    double *state = a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE;
+    const bool have_prev = (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2 && state[Ipm<M>::ST_NOPOINT] == 0.;
+    cta_sync();                                                              // every thread has read the flags before warp 0 updates them below
+    const IpmResult r = ipm.cp_solve_subproblem(cfg.ipm, have_prev);
+    if (cta_tid() < LANES) {
+        if (lane_id() == 0) state[Ipm<M>::ST_NOPOINT] = r.point_ok ? 0. : 1.;
+        if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r);
+    }
+    cta_sync();
 }
 
 // ---- K2 + K3, split pipeline (cfg.ipm_slice < 0): the steps of one interior-point iteration, each called by its own kernel ----
@@ -343,7 +362,7 @@ SCPP_HD void sc_split_step(const ScArrays<M> &a, const ScConfig &cfg, int n, dou
     if (STEP != SP_START) ipm.dcap = state[Ipm<M>::ST_DCAP];
     IpmResult r;
     if (STEP == SP_START) {
-        if (ipm.sp_start(cfg.ipm, (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2, state, r)) { if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r); }
+        if (ipm.sp_start(cfg.ipm, (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2 && state[Ipm<M>::ST_NOPOINT] == 0., state, r)) { if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r); }
     } else if (STEP == SP_ASSEMBLE) {
         if (sub >= a.K) return;
         ipm.tables_init();

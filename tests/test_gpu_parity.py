@@ -602,3 +602,45 @@ def test_scvx_k50_full_batch_no_failures_and_oracle_sample(S):
         assert abs(Jo - Jg) < 0.05 * max(Jo, 1e-3), (i, Jo, Jg)
     print(f"[SCvx K=50] leading iterates equal to the oracle's (U to 1e-4, costs): {lead}; of those with X to 1e-5: {np.mean(xs):.2f}")
     assert len(lead) >= 4 and min(lead) >= 3 and np.mean(xs) >= 0.6
+
+
+# ---- round 2: the CTA-per-instance solver (cfg.solver = 1) -------------------------------------------------------------------------------
+def _solve_batch(S, name, xi, x_final_override=None, N=None, **over):
+    solver = over.pop("solver", 1); warm = over.pop("warm", 0.0)
+    model, params, x_init, x_final, cfg = S.load_model(name, keep_history=1, **over)
+    cfg.solver = solver; cfg.ipm.warm = warm
+    eng = S.SCAlgorithm(model, params, cfg, len(xi))
+    eng.set_boundary_states(xi, x_final)
+    eng.solve()
+    out = (eng.get_solution(), eng.get_info(), eng.get_all_solutions(), eng.last_timing())
+    eng.close()
+    return out
+
+
+def test_cta_solver_vs_oracle(S):
+    """cfg.solver = 1 (one CTA per instance, factor in shared memory, whole sub-problem per launch) against the oracle: RocketQuat K = 50
+    cold and with the interior warm start, Rocket2D K = 30 (converges), Starship K = 100 (one CTA per SM)"""
+    p, rpy = O.falcon9()
+    plist = [O.rq_perturb(p, rpy, 0x5C99, i) for i in range(60, 66)] + [p]
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=6, cfg_over=dict(solver=1))
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist[:4], K=50, max_it=15, warm=0.995, cfg_over=dict(solver=1))
+    _compare_run(S, "Rocket2D", O.ROCKET2D, [O.rocket2d()], K=30, max_it=15, cfg_over=dict(solver=1))
+    _compare_run(S, "Rocket2D", O.ROCKET2D, [O.rocket2d()], K=30, max_it=15, warm=0.995, cfg_over=dict(solver=1))
+    ps, rpys = O.starship()
+    _compare_run(S, "RocketQuatStarship", O.ROCKETQUAT, [ps, O.rq_perturb(ps, rpys, 0x5C99, 1)], K=100, max_it=4, cfg_over=dict(solver=1))
+
+
+def test_cta_solver_matches_warp_solver_on_a_batch(S):
+    """same method, different mapping (sums in a different order): identical decisions and iteration counts on 300 instances (more than
+    the 296 resident CTAs: the queue hands out a second instance to some), iterates equal far inside the parity bar; and the batch result
+    does not depend on which CTA solved which instance (two runs are bit-identical)"""
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50, max_iterations=8)
+    xi = S.perturbed_initial_states(x_init, RPY_F9, 300)
+    a = _solve_batch(S, "RocketQuat", xi, K=50, max_iterations=8, solver=0, warm=0.995)
+    b = _solve_batch(S, "RocketQuat", xi, K=50, max_iterations=8, solver=1, warm=0.995)
+    c = _solve_batch(S, "RocketQuat", xi, K=50, max_iterations=8, solver=1, warm=0.995)
+    assert np.array_equal(a[0]["iterations"], b[0]["iterations"]) and np.array_equal(a[0]["flags"], b[0]["flags"])
+    (Xa, Ua, ta), (Xb, Ub, tb) = a[2], b[2]
+    assert np.abs(Xa - Xb).max() < TOL_X and np.abs(Ua - Ub).max() < TOL_U
+    assert np.array_equal(a[1][:, :, 4], b[1][:, :, 4])
+    assert np.array_equal(b[2][0], c[2][0]) and np.array_equal(b[2][1], c[2][1]) and np.array_equal(b[1], c[1])

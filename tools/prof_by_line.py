@@ -40,7 +40,7 @@ src = open(srcfile).read().split('\n')
 fname = srcfile.split('/')[-1]
 funcs = []
 for i, l in enumerate(src, 1):
-    m = re.match(r'\s+(?:template <[^>]*>\s*)?SCPP_HD\s+(?:static\s+)?(?:constexpr\s+)?[\w:<>\*& ]+?\s+\*?(\w+)\(', l)
+    m = re.match(r'\s*(?:template <[^>]*>\s*)?SCPP_HD\s+(?:static\s+)?(?:constexpr\s+)?[\w:<>\*& ]+?\s+\*?(\w+)\(', l)
     if m and not l.strip().startswith('//'): funcs.append((i, m.group(1)))
 def region(loc):
     f, n = loc
