@@ -122,6 +122,7 @@ __global__ void k_compact(const int *__restrict__ active, int n_active, const in
     const int f = c ? c : (iters[n] >= max_it ? 4 : 0);
     flags[n] = (unsigned char)f;
     if (!f) {
+        atomicMin(counters + 2, iters[n]);
         next[atomicAdd(counters, 1)] = n;
         if (ipm_state[(size_t)n * state_stride] == 0.) disc[atomicAdd(counters + 1, 1)] = n;
     }
@@ -265,7 +266,7 @@ struct EngineT : scpp_b200_engine {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int *active[2] = {nullptr, nullptr}, *disc = nullptr;
-    int *counter = nullptr;               // [0] next active count, [1] instances starting a new sub-problem
+    int *counter = nullptr;               // [0] next active count, [1] instances starting a new sub-problem, [2] fewest outer iterations among the active
     std::vector<int> h_iters;
     std::vector<unsigned char> h_flags;
     unsigned long long *gcount = nullptr;
@@ -282,6 +283,11 @@ struct EngineT : scpp_b200_engine {
     int n_sm = 148;
     size_t cta_smem = 0;
     int cta_per_sm = 1, *queue = nullptr, *lpt = nullptr;   // CTA-per-instance solver: shared-memory image, residency, device-side work queue
+    cudaStream_t cstream = nullptr;        // communication stream (flag exchanges)
+    cudaEvent_t ev_flags = nullptr;
+    unsigned char *flags_tx = nullptr;
+    int exchanges = 0;
+    bool exchange_pending = false;
     int N_pad = 0;                         // multi-GPU: flag bytes every rank contributes (max shard size)
 
     template <class T>
@@ -301,6 +307,8 @@ struct EngineT : scpp_b200_engine {
         if (h_counter) cudaFreeHost(h_counter);
         if (h_gcount) cudaFreeHost(h_gcount);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
+        if (ev_flags) cudaEventDestroy(ev_flags);
+        if (cstream) cudaStreamDestroy(cstream);
         if (stream) cudaStreamDestroy(stream);
     }
     int init() override
@@ -324,7 +332,7 @@ struct EngineT : scpp_b200_engine {
         DA(a.info, (size_t)N * cfg.max_iterations * INFO_STRIDE);
         a.hist = nullptr;
         if (cfg.keep_history) DA(a.hist, (size_t)N * (cfg.max_iterations + 1) * a.hist_stride());
-        DA(active[0], N); DA(active[1], N); DA(disc, N); DA(counter, 2); DA(a.ipm_state, (size_t)N * Ipm<M>::IPM_STATE); DA(gcount, 1); DA(flags, N); DA(a.frozen, N);
+        DA(active[0], N); DA(active[1], N); DA(disc, N); DA(counter, 4); DA(a.ipm_state, (size_t)N * Ipm<M>::IPM_STATE); DA(gcount, 1); DA(flags, N); DA(a.frozen, N);
         a.trust = a.last_cost = a.n1c = a.Xc = a.Uc = a.costp = nullptr; a.have_last = a.solves = a.phase = nullptr;
         if (cfg.algorithm == 1) {
             DA(a.trust, N); DA(a.last_cost, N); DA(a.n1c, N); DA(a.Xc, (size_t)N * K * NX); DA(a.Uc, (size_t)N * K * NU); DA(a.costp, (size_t)N * K);
@@ -332,7 +340,7 @@ struct EngineT : scpp_b200_engine {
         } DA(sim_x, (size_t)N * NX); DA(sim_u, (size_t)N * NU); DA(sim_r, N);
         DA(Xo, (size_t)N * K * NX); DA(Uo, (size_t)N * K * NU);
 #undef DA
-        CU(cudaMallocHost((void **)&h_counter, 2 * sizeof(int)));
+        CU(cudaMallocHost((void **)&h_counter, 4 * sizeof(int)));
         CU(cudaMallocHost((void **)&h_gcount, sizeof(unsigned long long)));
         CU(cudaFuncSetAttribute(k_solve<M, WPB_MAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WPB_MAX * Ipm<M>::sm_doubles() * sizeof(double))));
         {
@@ -378,7 +386,7 @@ struct EngineT : scpp_b200_engine {
         if (warm) k_warm<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg);
         else { CU(cudaMemsetAsync(a.frozen, 0, (size_t)N * sizeof(int), stream)); k_setup<M><<<(N + T - 1) / T, T, 0, stream>>>(a, P, cfg); }
         CU(cudaMemsetAsync(flags, 0, N, stream));
-        CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), stream));
+        CU(cudaMemsetAsync(counter, 0, 4 * sizeof(int), stream));
         k_first_list<<<(N + 255) / 256, 256, 0, stream>>>(active[0], counter, warm ? a.frozen : nullptr, a.converged, flags, N);   // all but the frozen instances
         launches += 2;
         CU(cudaMemcpyAsync(h_counter, counter, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -392,7 +400,8 @@ struct EngineT : scpp_b200_engine {
         // the rounds are the reference's outer iterations in lock-step.
         const int slice_eff = cfg.solver == 1 ? 0 : (cfg.ipm_slice < 0 ? 1 : cfg.ipm_slice);      // solver 1: a round is an outer iteration
         const long long max_rounds = (long long)cfg.max_iterations * (cfg.algorithm == 1 ? SCVX_MAX_RESOLVE + 1 : 1) * (slice_eff > 0 ? (cfg.ipm.maxit + 3 + 8) / slice_eff + 2 : 1) + 1;   // + 8: rounds repeated after a regularised re-factorisation
-        for (long long round = 0; round < max_rounds && global_active > 0; round++) {
+        exchanges = 0; exchange_pending = false;
+        for (long long round = 0; round < max_rounds && n_active > 0; round++) {
             CU(cudaEventRecord(ev[1], stream));
             if (n_disc > 0) {
                 const long long thr = (long long)n_disc * (K - 1) * NC;
@@ -468,24 +477,21 @@ struct EngineT : scpp_b200_engine {
             }
             CU(cudaEventRecord(ev[3], stream));
             CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), stream));
+            CU(cudaMemsetAsync(counter + 2, 0x7f, sizeof(int), stream));
             if (n_active > 0) {
                 k_compact<<<(n_active + 255) / 256, 256, 0, stream>>>(active[cur], n_active, a.converged, a.iters, cfg.max_iterations, a.ipm_state,
                                                                      Ipm<M>::IPM_STATE, active[cur ^ 1], disc, counter, flags);
                 launches++;
             }
-            CU(cudaMemcpyAsync(h_counter, counter, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-            // the one data-path collective: every rank learns every instance's flag.  With one interior-point iteration per round an outer
-            // iteration spans ~10 rounds, so the flags are exchanged every 10th round (once per round in lock-step mode): about one
-            // all-gather per outer iteration; a rank that runs out of work idles through at most 9 empty rounds before everyone agrees to stop
-            const bool exchange = comm && (slice_eff == 0 || (round + 1) % 10 == 0);
-            if (exchange) {
-                int rc = g_nccl.AllGather(flags, flags_all, (size_t)N_pad, /*ncclUint8*/ 1, comm, stream);
-                if (rc != 0) return fail(SCPP_B200_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
-                CU(cudaMemsetAsync(gcount, 0, sizeof(unsigned long long), stream));
-                const long long tot = (long long)N_pad * nranks;
-                k_count_zero<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(flags_all, tot, gcount);
-                launches++;
-                CU(cudaMemcpyAsync(h_gcount, gcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+            CU(cudaMemcpyAsync(h_counter, counter, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            // The one data-path collective: ncclAllGather of the per-instance flag bytes, ONE PER OUTER ITERATION, and never waited for inside
+            // the loop.  Instances are independent, so a rank stops on the completion of its own shard; the exchange only reports the global
+            // state.  Every rank issues exactly max_iterations exchanges per solve (a collective needs matching calls): the i-th is enqueued
+            // on the communication stream once every running instance of this rank has passed outer iteration i; what is left when the rank
+            // runs out of work is enqueued after the loop.
+            if (comm) {
+                CU(cudaEventRecord(ev_flags, stream));
+                exchange_pending = true;
             }
             CU(cudaStreamSynchronize(stream));
             float m1 = 0, m2 = 0;
@@ -493,11 +499,24 @@ struct EngineT : scpp_b200_engine {
             CU(cudaEventElapsedTime(&m2, ev[2], ev[3]));
             ms_disc += m1; ms_socp += m2;
             n_active = h_counter[0]; n_disc = h_counter[1];
+            if (comm) {
+                const int passed = n_active > 0 ? h_counter[2] : cfg.max_iterations;
+                while (exchanges < passed && exchanges < cfg.max_iterations) { int rc = exchange_flags(); if (rc) return rc; }
+            }
             disc_list = disc;
             cur ^= 1;
             rounds++; inst_rounds += n_active_round;
-            if (!comm) global_active = (long long)n_active;
-            else if (exchange) global_active = (long long)*h_gcount;
+            global_active = (long long)n_active;           // this rank's shard; the global count follows after the loop
+        }
+        if (comm) {
+            while (exchanges < cfg.max_iterations) { int rc = exchange_flags(); if (rc) return rc; }
+            CU(cudaMemsetAsync(gcount, 0, sizeof(unsigned long long), cstream));
+            const long long tot = (long long)N_pad * nranks;
+            k_count_zero<<<(unsigned)((tot + 255) / 256), 256, 0, cstream>>>(flags_all, tot, gcount);
+            CU(cudaMemcpyAsync(h_gcount, gcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cstream));
+            CU(cudaStreamSynchronize(cstream));
+            global_active = (long long)*h_gcount;
+            launches++;
         }
         // SC iterations done: per instance (reported as instance-iterations) and the largest count (outer iterations)
         h_iters.resize(N); h_flags.resize(N);
@@ -614,6 +633,19 @@ struct EngineT : scpp_b200_engine {
         CU(cudaMemsetAsync(fp, 1, (size_t)N_pad, stream));
         CU(cudaStreamSynchronize(stream));
         flags = fp; flags_all = fa;
+        CU(cudaMalloc((void **)&flags_tx, (size_t)N_pad)); allocs.push_back(flags_tx);
+        CU(cudaEventCreateWithFlags(&ev_flags, cudaEventDisableTiming));
+        return 0;
+    }
+    // one flag exchange on the communication stream, ordered after the last flag update of the compute stream; not waited for
+    int exchange_flags()
+    {
+        if (!cstream) { CU(cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking)); }
+        if (exchange_pending) CU(cudaStreamWaitEvent(cstream, ev_flags, 0));
+        CU(cudaMemcpyAsync(flags_tx, flags, (size_t)N_pad, cudaMemcpyDeviceToDevice, cstream));      // snapshot: the compute stream keeps updating flags
+        int rc = g_nccl.AllGather(flags_tx, flags_all, (size_t)N_pad, /*ncclUint8*/ 1, comm, cstream);
+        if (rc != 0) return fail(SCPP_B200_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+        exchanges++;
         return 0;
     }
     int get_info(double *info) override

