@@ -82,6 +82,10 @@ typedef struct {
     int algorithm;
     int solver;
     double scvx_rho_0, scvx_rho_1, scvx_rho_2, scvx_alpha, scvx_beta, scvx_change_threshold, scvx_trust_region;
+    int jacobian;     /* how K1 obtains the Jacobian products (computeJacobians, systemDynamics.hpp:206-235): 1 (default) forward-mode dual
+                         numbers over the model's generic-scalar flow map -- what CppAD gives the reference, nothing model-specific beyond
+                         systemFlowMap; 0 the hand-derived sparse Jacobian of models.cuh (optional fast path, tested equal) */
+    int pad3_;
 } scpp_b200_sc_config;
 
 typedef struct scpp_b200_engine scpp_b200_engine;
@@ -160,6 +164,9 @@ size_t scpp_b200_device_bytes(scpp_b200_engine *e);
  * scpp_core/include/discretizationData.hpp:8-20): A [n][K-1][nx*nx], B,C [n][K-1][nx*nu], s,z [n][K-1][nx]. */
 int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const double *X, const double *U, const double *sigma,
                          const double *par, double *A, double *B, double *C, double *s, double *z);
+/* the same with the Jacobian path chosen explicitly (scpp_b200_sc_config.jacobian: 1 dual numbers over the flow map, 0 hand-derived) */
+int scpp_b200_discretize2(int model, int K, int n, int nsub, int jacobian, int device, const double *X, const double *U, const double *sigma,
+                          const double *par, double *A, double *B, double *C, double *s, double *z);
 
 /* the tensor-core block products of K2 (mma.sync.m8n8k4.f64, scpp_b200/csrc/blockops.cuh) checked on the device against scalar
  * loops for the shapes the factorisation uses; returns the largest absolute deviation (no reference counterpart) */

@@ -40,7 +40,8 @@ class SCConfig(C.Structure):
                 ("nu_tol", C.c_double), ("delta_tol", C.c_double), ("max_iterations", C.c_int), ("nsub", C.c_int),
                 ("keep_history", C.c_int), ("ipm_slice", C.c_int), ("ipm", IpmSettings),
                 ("algorithm", C.c_int), ("solver", C.c_int), ("scvx_rho_0", C.c_double), ("scvx_rho_1", C.c_double), ("scvx_rho_2", C.c_double),
-                ("scvx_alpha", C.c_double), ("scvx_beta", C.c_double), ("scvx_change_threshold", C.c_double), ("scvx_trust_region", C.c_double)]
+                ("scvx_alpha", C.c_double), ("scvx_beta", C.c_double), ("scvx_change_threshold", C.c_double), ("scvx_trust_region", C.c_double),
+                ("jacobian", C.c_int), ("pad3_", C.c_int)]
 
 
 class ScppError(RuntimeError):
@@ -299,7 +300,7 @@ def simulate(model, x, u0, u1, par, dt, device=0):
     return x
 
 
-def discretize(model, X, U, sigma, par, nsub=20, device=0):
+def discretize(model, X, U, sigma, par, nsub=20, device=0, jacobian=1):
     """test hook on hot path 1 (discretization::multipleShooting): returns dict of [n][K-1][row][col] arrays"""
     nx, nu, npar = model_dims(model)
     X = np.ascontiguousarray(X, float); U = np.ascontiguousarray(U, float)
@@ -310,5 +311,5 @@ def discretize(model, X, U, sigma, par, nsub=20, device=0):
     par = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(np.asarray(par, float)), (n, npar)))
     A = np.empty((n, K - 1, nx, nx)); B = np.empty((n, K - 1, nu, nx)); Cc = np.empty((n, K - 1, nu, nx))
     s = np.empty((n, K - 1, nx)); z = np.empty((n, K - 1, nx))
-    _check(lib().scpp_b200_discretize(model, K, n, nsub, device, _p(X), _p(U), _p(sigma), _p(par), _p(A), _p(B), _p(Cc), _p(s), _p(z)))
+    _check(lib().scpp_b200_discretize2(model, K, n, nsub, jacobian, device, _p(X), _p(U), _p(sigma), _p(par), _p(A), _p(B), _p(Cc), _p(s), _p(z)))
     return dict(A=A.transpose(0, 1, 3, 2), B=B.transpose(0, 1, 3, 2), C=Cc.transpose(0, 1, 3, 2), s=s, z=z)

@@ -52,8 +52,34 @@ SCPP_HD void discretize_rhs(const double *x, const double *col, const double *u,
     }
 }
 
-// X:[K][NX] U:[K][NU] of one instance; writes column `c` of interval `k` into dd_k (row-major [NX][NC])
+// The same right-hand side through forward-mode AD of the model's generic-scalar flow map (cfg.jacobian = 1, the default): every column's
+// derivative is sigma J (dx, du) [+ f for the s column] with ONE tangent direction,
+//      A column:  (col, 0)      B / C column:  (col, alpha e_j) / (col, beta e_j)      s column:  (col, 0)      z column:  (col - x, -u)
+// so one dual-number pass of flow_map gives f and the product; no Jacobian entries, no hand-derived code (what CppAD gives the reference,
+// scpp_core/include/systemDynamics.hpp:206-235).
 template <class M>
+SCPP_HD void discretize_rhs_ad(const double *x, const double *col, const double *u, const double *par, double sigma,
+                               int ctype, int cidx, double alpha, double beta, double *dx, double *dcol)
+{
+    constexpr int NX = M::NX, NU = M::NU;
+    Dual xd[NX], ud[NU], fd[NX];
+#pragma unroll
+    for (int i = 0; i < NX; i++) xd[i] = Dual(x[i], ctype == 4 ? col[i] - x[i] : col[i]);
+#pragma unroll
+    for (int j = 0; j < NU; j++) {
+        double t = 0.;
+        if (ctype == 1 && j == cidx) t = alpha;
+        if (ctype == 2 && j == cidx) t = beta;
+        if (ctype == 4) t = -u[j];
+        ud[j] = Dual(u[j], t);
+    }
+    M::template flow_map<Dual>(xd, ud, par, fd);
+#pragma unroll
+    for (int i = 0; i < NX; i++) { dx[i] = sigma * fd[i].v; dcol[i] = sigma * fd[i].d + (ctype == 3 ? fd[i].v : 0.); }
+}
+
+// X:[K][NX] U:[K][NU] of one instance; writes column `c` of interval `k` into dd_k (row-major [NX][NC])
+template <class M, bool AD = false>
 SCPP_HD void discretize_column(const double *X, const double *U, double sigma, const double *par, int K, int k, int c,
                                int nsub, int free_time, double *ddk, double *ddT = nullptr, int KS = 0)
 {
@@ -94,7 +120,8 @@ SCPP_HD void discretize_column(const double *X, const double *U, double sigma, c
                 const double beta = tau / dtau, alpha = (dtau - tau) / dtau;
 #pragma unroll
                 for (int j = 0; j < NU; j++) u[j] = u0[j] + beta * du[j];
-                discretize_rhs<M>(xt, ct, u, du, par, sigma, ctype, cidx, alpha, beta, kx, kc);
+                if (AD) discretize_rhs_ad<M>(xt, ct, u, par, sigma, ctype, cidx, alpha, beta, kx, kc);
+                else discretize_rhs<M>(xt, ct, u, du, par, sigma, ctype, cidx, alpha, beta, kx, kc);
                 const double wgt = (sgi == 0 || sgi == 3) ? h / 6. : h / 3.;
                 const double nxt = (sgi == 2) ? h : 0.5 * h;
 #pragma unroll

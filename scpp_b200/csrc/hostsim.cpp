@@ -11,12 +11,19 @@
 using namespace scpp;
 
 template <class M>
-static void run_discretize(int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd, double *ddT = nullptr)
+static void run_discretize(int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd, double *ddT = nullptr, int jacobian = 0)
 {
     constexpr int NC = M::NX + 2 * M::NU + 2;
     for (int k = 0; k < K - 1; k++)
-        for (int c = 0; c < NC; c++)
-            discretize_column<M>(X, U, sigma, par, K, k, c, nsub, 1, dd + (size_t)k * M::NX * NC, ddT, Ipm<M>::ks(K));
+        for (int c = 0; c < NC; c++) {
+            if (jacobian) discretize_column<M, true>(X, U, sigma, par, K, k, c, nsub, 1, dd + (size_t)k * M::NX * NC, ddT, Ipm<M>::ks(K));
+            else discretize_column<M, false>(X, U, sigma, par, K, k, c, nsub, 1, dd + (size_t)k * M::NX * NC, ddT, Ipm<M>::ks(K));
+        }
+}
+extern "C" void hs_discretize2(int model, int K, const double *X, const double *U, double sigma, const double *par, int nsub, int jacobian, double *dd)
+{
+    if (model == 0) run_discretize<RocketQuat>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian);
+    else run_discretize<Rocket2d>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian);
 }
 
 extern "C" void hs_discretize(int model, int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd)
@@ -75,7 +82,7 @@ struct HostEngine {
                 active++;
                 if (a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] == 0.)
                     run_discretize<M>(K, a.X + (size_t)n * K * NX, a.U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg.nsub,
-                                      a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K));
+                                      a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K), cfg.jacobian);
                 if (cfg.solver == 1) {
                     sc_solve_instance_cta<M>(a, cfg, n, smem.data());
                     if (cfg.algorithm == 1) { for (int k = 0; k < K - 1; k++) sc_scvx_cost<M>(a, cfg, n, k); sc_scvx_decide<M>(a, cfg, n); }
@@ -173,18 +180,18 @@ extern "C" void hs_simulate(int model, double dt, double *x, const double *u0, c
 
 // forward-mode dual number: instantiates the generic-scalar flow map (the plugin surface, systemFlowMap) to obtain the exact
 // Jacobian the reference gets from CppAD (systemDynamics.hpp:206-235); compared in tests with the hand-derived sparse one
-struct Dual {
+struct HDual {
     double v, d;
-    Dual(double v_ = 0., double d_ = 0.) : v(v_), d(d_) {}
+    HDual(double v_ = 0., double d_ = 0.) : v(v_), d(d_) {}
 };
-static inline Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
-static inline Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
-static inline Dual operator-(Dual a) { return {-a.v, -a.d}; }
-static inline Dual operator*(Dual a, Dual b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
-static inline Dual operator/(Dual a, Dual b) { return {a.v / b.v, (a.d * b.v - a.v * b.d) / (b.v * b.v)}; }
-static inline Dual sqrt(Dual a) { double r = std::sqrt(a.v); return {r, a.d / (2. * r)}; }
-static inline Dual sin(Dual a) { return {std::sin(a.v), std::cos(a.v) * a.d}; }
-static inline Dual cos(Dual a) { return {std::cos(a.v), -std::sin(a.v) * a.d}; }
+static inline HDual operator+(HDual a, HDual b) { return {a.v + b.v, a.d + b.d}; }
+static inline HDual operator-(HDual a, HDual b) { return {a.v - b.v, a.d - b.d}; }
+static inline HDual operator-(HDual a) { return {-a.v, -a.d}; }
+static inline HDual operator*(HDual a, HDual b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
+static inline HDual operator/(HDual a, HDual b) { return {a.v / b.v, (a.d * b.v - a.v * b.d) / (b.v * b.v)}; }
+static inline HDual sqrt(HDual a) { double r = std::sqrt(a.v); return {r, a.d / (2. * r)}; }
+static inline HDual sin(HDual a) { return {std::sin(a.v), std::cos(a.v) * a.d}; }
+static inline HDual cos(HDual a) { return {std::cos(a.v), -std::sin(a.v) * a.d}; }
 
 template <class M>
 static void run_jac(const double *x, const double *u, const double *par, double *f, double *A_ad, double *B_ad, double *A_lin, double *B_lin)
@@ -192,10 +199,10 @@ static void run_jac(const double *x, const double *u, const double *par, double 
     constexpr int NX = M::NX, NU = M::NU;
     M::template flow_map<double>(x, u, par, f);
     for (int j = 0; j < NX + NU; j++) {
-        Dual xd[NX], ud[NU], fd[NX];
-        for (int i = 0; i < NX; i++) xd[i] = Dual(x[i], i == j ? 1. : 0.);
-        for (int i = 0; i < NU; i++) ud[i] = Dual(u[i], NX + i == j ? 1. : 0.);
-        M::template flow_map<Dual>(xd, ud, par, fd);
+        HDual xd[NX], ud[NU], fd[NX];
+        for (int i = 0; i < NX; i++) xd[i] = HDual(x[i], i == j ? 1. : 0.);
+        for (int i = 0; i < NU; i++) ud[i] = HDual(u[i], NX + i == j ? 1. : 0.);
+        M::template flow_map<HDual>(xd, ud, par, fd);
         for (int i = 0; i < NX; i++) { if (j < NX) A_ad[i * NX + j] = fd[i].d; else B_ad[i * NU + (j - NX)] = fd[i].d; }
     }
     typename M::Lin L;

@@ -10,7 +10,7 @@ namespace scpp {
 constexpr int WPB_MAX = 7;   // warps (= problem instances) per CTA of the SOCP kernels (chosen per launch, see EngineT::solve())
 
 // K1: one thread per (active instance, interval, column)
-template <class M>
+template <class M, bool AD>
 __global__ void __launch_bounds__(128) k_discretize(ScArrays<M> a, int nsub, int free_time, const int *__restrict__ active, int n_active)
 {
     constexpr int NX = M::NX, NU = M::NU, NC = NX + 2 * NU + 2;
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(128) k_discretize(ScArrays<M> a, int nsub, int
     const int ai = int(idx / per), rem = int(idx - (long long)ai * per);
     const int k = rem / NC, c = rem - k * NC;
     const int n = active ? active[ai] : ai;
-    discretize_column<M>(a.X + (size_t)n * a.K * NX, a.U + (size_t)n * a.K * NU, a.sigma[n], a.par + (size_t)n * M::NP,
+    discretize_column<M, AD>(a.X + (size_t)n * a.K * NX, a.U + (size_t)n * a.K * NU, a.sigma[n], a.par + (size_t)n * M::NP,
                          a.K, k, c, nsub, free_time, a.dd + ((size_t)n * (a.K - 1) + k) * NX * NC,
                          a.ddT ? a.ddT + (size_t)n * Ipm<M>::ddt_doubles(a.K) : nullptr, Ipm<M>::ks(a.K));
 }
@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(128, 3) k_sp_stage(ScArrays<M> a, ScConfig cfg
     X template __global__ void k_sp_warp<M, SP_CHAIN, WPB_MAX> SCPP_ARGS_WARP(M);           \
     X template __global__ void k_sp_assemble<M, WPB_MAX> SCPP_ARGS_SOLVE(M);                \
     X template __global__ void k_sp_test<M> SCPP_ARGS_SOLVE(M);                             \
-    X template __global__ void k_discretize<M>(ScArrays<M>, int, int, const int *, int);
+    X template __global__ void k_discretize<M, false>(ScArrays<M>, int, int, const int *, int);   \
+    X template __global__ void k_discretize<M, true>(ScArrays<M>, int, int, const int *, int);
 #define SCPP_GROUP4(X, M)                                                                  \
     X template __global__ void k_sp_stage<M, SP_RHS> SCPP_ARGS_STAGE(M);                    \
     X template __global__ void k_sp_stage<M, SP_RECOVER> SCPP_ARGS_STAGE(M);                \

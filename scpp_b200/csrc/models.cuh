@@ -12,6 +12,40 @@
 namespace scpp {
 
 // ------------------------------------------------------------------------------------------------
+// Forward-mode dual number (value + ONE tangent): the device counterpart of the reference's AD scalar
+// (CppAD::AD<CppAD::cg::CG<double>>, scpp_core/include/systemDynamics.hpp:34-39).  Instantiating a model's generic-scalar flow map
+// (systemFlowMap, :69-73) with it gives f(x,u) and the directional derivative J (dx, du) in one pass; the multiple-shooting kernel needs
+// exactly one such product per right-hand-side evaluation and column (discretize.cuh), so no Jacobian is ever formed and a model
+// plugs in with nothing but its flow map.
+// ------------------------------------------------------------------------------------------------
+struct Dual {
+    double v, d;
+    SCPP_HD Dual() : v(0.), d(0.) {}
+    SCPP_HD explicit Dual(double v_) : v(v_), d(0.) {}
+    SCPP_HD Dual(double v_, double d_) : v(v_), d(d_) {}
+};
+SCPP_HD Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
+SCPP_HD Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
+SCPP_HD Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
+SCPP_HD Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
+SCPP_HD Dual operator/(Dual a, Dual b) { const double q = a.v / b.v; return Dual(q, (a.d - q * b.d) / b.v); }
+SCPP_HD Dual operator+(double a, Dual b) { return Dual(a + b.v, b.d); }
+SCPP_HD Dual operator+(Dual a, double b) { return Dual(a.v + b, a.d); }
+SCPP_HD Dual operator-(double a, Dual b) { return Dual(a - b.v, -b.d); }
+SCPP_HD Dual operator-(Dual a, double b) { return Dual(a.v - b, a.d); }
+SCPP_HD Dual operator*(double a, Dual b) { return Dual(a * b.v, a * b.d); }
+SCPP_HD Dual operator*(Dual a, double b) { return Dual(a.v * b, a.d * b); }
+SCPP_HD Dual operator/(Dual a, double b) { return Dual(a.v / b, a.d / b); }
+SCPP_HD Dual operator/(double a, Dual b) { const double q = a / b.v; return Dual(q, -q * b.d / b.v); }
+// (the overloads below hide ::sqrt / ::sin / ::cos for unqualified calls inside this namespace: forward the double versions)
+SCPP_HD double sqrt(double a) { return ::sqrt(a); }
+SCPP_HD double sin(double a) { return ::sin(a); }
+SCPP_HD double cos(double a) { return ::cos(a); }
+SCPP_HD Dual sqrt(Dual a) { const double r = ::sqrt(a.v); return Dual(r, a.d / (2. * r)); }
+SCPP_HD Dual sin(Dual a) { return Dual(::sin(a.v), ::cos(a.v) * a.d); }
+SCPP_HD Dual cos(Dual a) { return Dual(::cos(a.v), -::sin(a.v) * a.d); }
+
+// ------------------------------------------------------------------------------------------------
 // per-instance problem description as uploaded by the host (dimensional, angles in rad)
 // mirrors RocketQuat::Parameters (scpp_models/include/rocketQuat.hpp:50-85) /
 //         Rocket2d::Parameters  (scpp_models/include/rocket2d.hpp:51-84)

@@ -28,7 +28,8 @@ class ScConfig(C.Structure):
                 ("nu_tol", C.c_double), ("delta_tol", C.c_double), ("max_iterations", C.c_int), ("nsub", C.c_int),
                 ("keep_history", C.c_int), ("ipm_slice", C.c_int), ("ipm", IpmSettings),
                 ("algorithm", C.c_int), ("solver", C.c_int), ("scvx_rho_0", C.c_double), ("scvx_rho_1", C.c_double), ("scvx_rho_2", C.c_double),
-                ("scvx_alpha", C.c_double), ("scvx_beta", C.c_double), ("scvx_change_threshold", C.c_double), ("scvx_trust_region", C.c_double)]
+                ("scvx_alpha", C.c_double), ("scvx_beta", C.c_double), ("scvx_change_threshold", C.c_double), ("scvx_trust_region", C.c_double),
+                ("jacobian", C.c_int), ("pad3_", C.c_int)]
 
 
 def build():
@@ -127,10 +128,10 @@ def simulate(model, dt, u0, u1, par, x):
     return x
 
 
-def discretize(model, X, U, sigma, par, nsub):
+def discretize(model, X, U, sigma, par, nsub, jacobian=0):
     nx, nu = DIMS[model]
     K = X.shape[0]
     out = np.zeros((K - 1, nx, nx + 2 * nu + 2))
     p = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(C.c_void_p)
-    lib().hs_discretize(model, K, p(X), p(U), C.c_double(sigma), p(par), nsub, out.ctypes.data_as(C.c_void_p))
+    lib().hs_discretize2(model, K, p(X), p(U), C.c_double(sigma), p(par), nsub, jacobian, out.ctypes.data_as(C.c_void_p))
     return dict(A=out[:, :, :nx], B=out[:, :, nx:nx + nu], C=out[:, :, nx + nu:nx + 2 * nu], s=out[:, :, nx + 2 * nu], z=out[:, :, nx + 2 * nu + 1])

@@ -644,3 +644,15 @@ def test_cta_solver_matches_warp_solver_on_a_batch(S):
     assert np.abs(Xa - Xb).max() < TOL_X and np.abs(Ua - Ub).max() < TOL_U
     assert np.array_equal(a[1][:, :, 4], b[1][:, :, 4])
     assert np.array_equal(b[2][0], c[2][0]) and np.array_equal(b[2][1], c[2][1]) and np.array_equal(b[1], c[1])
+
+
+def test_two_gpu_sharded_solve_is_bit_identical(S):
+    """multi-GPU (needs >= 2 devices, skipped on a one-GPU box; run with gpurun --gpus 2): an unevenly sharded batch of the converging workload
+    == the single-GPU solve, bit for bit, with the asynchronous per-outer-iteration flag exchange (tools/multi_gpu_check.py)"""
+    import subprocess, sys
+    if S.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29517",
+                          os.path.join(ROOT, "tools", "multi_gpu_check.py"), "300"], capture_output=True, text=True, timeout=900)
+    print(out.stdout[-2000:])
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
