@@ -123,6 +123,11 @@ int scpp_b200_set_boundary_states(scpp_b200_engine *e, const double *x_init, con
  * per iteration K1 multiple shooting (discretization::multipleShooting, discretization.cpp:42-55),
  * K2 SOCP solve (ECOSSolver::solve, SCAlgorithm.cpp:78) fused with readSolution and the convergence logic
  * (SCAlgorithm.cpp:100-131).  A failed instance is flagged, never aborts the batch (reference: std::terminate, :94-98). */
+/* per-instance model parameters (optional): Pn [N] in the layout of scpp_b200_model_params, i.e. one RocketQuat::Parameters /
+ * Rocket2d::Parameters (scpp_models/include/rocketQuat.hpp:50-85) per instance, so a Monte-Carlo batch can vary the vehicle (inertia, I_sp,
+ * thrust limits, constraint angles ...) and not only the boundary states.  NULL: every instance uses the parameters given at creation.
+ * Takes effect at the next scpp_b200_solve. */
+int scpp_b200_set_instance_params(scpp_b200_engine *e, const scpp_b200_model_params *Pn);
 int scpp_b200_solve(scpp_b200_engine *e, int warm_start);
 
 /* SCAlgorithm::getSolution (SCAlgorithm.cpp:212-215): final trajectories REDIMENSIONALISED (:182-187).

@@ -225,6 +225,15 @@ class SCAlgorithm:
         _check(lib().scpp_b200_get_info(self._h, _p(info)))
         return info
 
+    def set_instance_params(self, params_list):
+        """one ModelParams per instance (Monte-Carlo over the vehicle); None: back to the shared parameters"""
+        if params_list is None:
+            _check(lib().scpp_b200_set_instance_params(self._h, None))
+            return
+        assert len(params_list) == self.N
+        arr = (ModelParams * self.N)(*params_list)
+        _check(lib().scpp_b200_set_instance_params(self._h, C.byref(arr)))
+
     def last_timing(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         l, o, ii = C.c_int(), C.c_int(), C.c_longlong()

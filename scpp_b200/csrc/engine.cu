@@ -35,14 +35,14 @@ template <class M>
 __global__ void k_setup(ScArrays<M> a, ModelParamsHost P, ScConfig cfg)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < a.N) sc_setup_instance<M>(a, P, cfg, n);
+    if (n < a.N) sc_setup_instance<M>(a, a.Pn ? a.Pn[n] : P, cfg, n);
 }
 
 template <class M>
 __global__ void k_warm(ScArrays<M> a, ModelParamsHost P, ScConfig cfg)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < a.N && !(a.frozen && a.frozen[n])) sc_warm_instance<M>(a, P, cfg, n);
+    if (n < a.N && !(a.frozen && a.frozen[n])) sc_warm_instance<M>(a, a.Pn ? a.Pn[n] : P, cfg, n);
 }
 
 // K4: one closed-loop step per instance (thread per instance)
@@ -50,7 +50,7 @@ template <class M>
 __global__ void k_sim_step(ScArrays<M> a, ModelParamsHost P, ScConfig cfg, double time_step, double *x_out, double *u_out, int *reached)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < a.N) sc_sim_step_instance<M>(a, P, cfg, n, time_step, x_out ? x_out + (size_t)n * M::NX : nullptr, u_out ? u_out + (size_t)n * M::NU : nullptr,
+    if (n < a.N) sc_sim_step_instance<M>(a, a.Pn ? a.Pn[n] : P, cfg, n, time_step, x_out ? x_out + (size_t)n * M::NX : nullptr, u_out ? u_out + (size_t)n * M::NU : nullptr,
                                          reached ? reached + n : nullptr);
 }
 // K4 test hook: plain simulate for n independent states
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128) k_lqr(ScArrays<M> a, ModelParamsHost P, c
     for (int i = 0; i < NX; i++) { x[i] = a.X[((size_t)n * a.K + k) * NX + i]; xi[i] = a.x_init[(size_t)n * NX + i]; xf[i] = a.x_final[(size_t)n * NX + i]; }
     for (int j = 0; j < NU; j++) u[j] = a.U[((size_t)n * a.K + k) * NU + j];
     M::redim(a.scale + 2 * n, x, u);
-    M::setup(P, 0, xi, xf, par, cst, sc2);
+    M::setup(a.Pn ? a.Pn[n] : P, 0, xi, xf, par, cst, sc2);
     const bool good = Lqr<M>::gain(x, u, par, qd, rd, gains + (size_t)gw * NU * NX, smem + (size_t)warp * Lqr<M>::sm_doubles());
     if ((threadIdx.x & 31) == 0) ok[gw] = good;
 }
@@ -248,6 +248,7 @@ struct scpp_b200_engine {
     virtual int sim_step(double time_step, double *x_new, double *u0, int *reached) = 0;
     virtual int lqr_gains(const double *q_diag, const double *r_diag, double *gains, int *ok) = 0;
     virtual int comm_buffers() = 0;
+    virtual int set_instance_params(const scpp_b200_model_params *Pn) = 0;
     int model = 0, N = 0, device = 0;
     ModelParamsHost P;
     ScConfig cfg;
@@ -281,6 +282,7 @@ struct EngineT : scpp_b200_engine {
     std::vector<void *> allocs;
     bool have_states = false, solved_once = false;
     int n_sm = 148;
+    ModelParamsHost *d_Pn = nullptr;       // per-instance model parameters (optional)
     size_t cta_smem = 0;
     int cta_per_sm = 1, *queue = nullptr, *lpt = nullptr;   // CTA-per-instance solver: shared-memory image, residency, device-side work queue
     cudaStream_t cstream = nullptr;        // communication stream (flag exchanges)
@@ -317,7 +319,7 @@ struct EngineT : scpp_b200_engine {
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto &e : ev) CU(cudaEventCreate(&e));
         const int K = cfg.K;
-        a.N = N; a.K = K; a.max_it = cfg.max_iterations;
+        a.N = N; a.K = K; a.max_it = cfg.max_iterations; a.Pn = nullptr;
         a.ws_stride = Ipm<M>::ws_doubles(K);
         int rc;
 #define DA(ptr, n) if ((rc = dalloc(&(ptr), (size_t)(n)))) return rc
@@ -659,6 +661,18 @@ struct EngineT : scpp_b200_engine {
         exchanges++;
         return 0;
     }
+    // RocketQuat::Parameters per instance (rocketQuat.hpp:50-85): a Monte-Carlo batch may vary the vehicle, not only the boundary states
+    int set_instance_params(const scpp_b200_model_params *Pn) override
+    {
+        CU(cudaSetDevice(device));
+        if (!Pn) { a.Pn = nullptr; return 0; }
+        for (int n = 0; n < N; n++) if (Pn[n].enable_roll_control) return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control = true is not built into this engine");
+        if (!d_Pn) { int rc; if ((rc = dalloc(&d_Pn, (size_t)N))) return rc; }
+        CU(cudaMemcpyAsync(d_Pn, Pn, (size_t)N * sizeof(ModelParamsHost), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        a.Pn = d_Pn;
+        return 0;
+    }
     static int chunk_size()
     {
         const char *e = getenv("SCPP_CHUNK");
@@ -860,6 +874,7 @@ int scpp_b200_create(int model, const scpp_b200_model_params *params, const scpp
 }
 void scpp_b200_destroy(scpp_b200_engine *e) { delete e; }
 int scpp_b200_set_boundary_states(scpp_b200_engine *e, const double *xi, const double *xf) { return (e && xi && xf) ? e->set_boundary(xi, xf) : fail(SCPP_B200_ERR_ARG, "null argument"); }
+int scpp_b200_set_instance_params(scpp_b200_engine *e, const scpp_b200_model_params *Pn) { return e ? e->set_instance_params(Pn) : fail(SCPP_B200_ERR_ARG, "null engine"); }
 int scpp_b200_solve(scpp_b200_engine *e, int warm) { return e ? e->solve(warm) : fail(SCPP_B200_ERR_ARG, "null engine"); }
 int scpp_b200_get_solution(scpp_b200_engine *e, double *X, double *U, double *t, int *it, int *fl) { return e ? e->get_solution(X, U, t, it, fl) : fail(SCPP_B200_ERR_ARG, "null engine"); }
 int scpp_b200_get_iterate(scpp_b200_engine *e, int it, double *X, double *U, double *t) { return e ? e->get_iterate(it, X, U, t) : fail(SCPP_B200_ERR_ARG, "null engine"); }

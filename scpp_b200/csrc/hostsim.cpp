@@ -50,7 +50,7 @@ struct HostEngine {
         xi.resize(N * NX); xf.resize(N * NX); par.resize(N * M::NP); cst.resize(N * MAX_CST); scale.resize(N * 2); tdir.resize((size_t)N * K * 3);
         fixv.resize((size_t)N * K * NB); wtr.resize(N); fixm.resize((size_t)N * K);
         dd.resize((size_t)N * (K - 1) * NX * NC); ddT.resize((size_t)N * Ipm<M>::ddt_doubles(K));
-        a.N = N; a.K = K; a.max_it = cfg.max_iterations;
+        a.N = N; a.K = K; a.max_it = cfg.max_iterations; a.Pn = nullptr;
         a.ws_stride = Ipm<M>::ws_doubles(K);
         ws.resize((size_t)N * a.ws_stride); smem.resize(Ipm<M>::sm_doubles() + Ipm<M>::cta_sm_doubles(K)); ist.resize((size_t)N * Ipm<M>::IPM_STATE);
         X.resize((size_t)N * K * NX); U.resize((size_t)N * K * NU); sigma.resize(N);

@@ -28,19 +28,19 @@ SCPP_HD Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
 SCPP_HD Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
 SCPP_HD Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
 SCPP_HD Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
-SCPP_HD Dual operator/(Dual a, Dual b) { const double q = a.v / b.v; return Dual(q, (a.d - q * b.d) / b.v); }
+SCPP_HD Dual operator/(Dual a, Dual b) { const double ib = 1. / b.v, q = a.v * ib; return Dual(q, (a.d - q * b.d) * ib); }   // one division
 SCPP_HD Dual operator+(double a, Dual b) { return Dual(a + b.v, b.d); }
 SCPP_HD Dual operator+(Dual a, double b) { return Dual(a.v + b, a.d); }
 SCPP_HD Dual operator-(double a, Dual b) { return Dual(a - b.v, -b.d); }
 SCPP_HD Dual operator-(Dual a, double b) { return Dual(a.v - b, a.d); }
 SCPP_HD Dual operator*(double a, Dual b) { return Dual(a * b.v, a * b.d); }
 SCPP_HD Dual operator*(Dual a, double b) { return Dual(a.v * b, a.d * b); }
-SCPP_HD Dual operator/(Dual a, double b) { return Dual(a.v / b, a.d / b); }
-SCPP_HD Dual operator/(double a, Dual b) { const double q = a / b.v; return Dual(q, -q * b.d / b.v); }
-// (the overloads below hide ::sqrt / ::sin / ::cos for unqualified calls inside this namespace: forward the double versions)
-SCPP_HD double sqrt(double a) { return ::sqrt(a); }
-SCPP_HD double sin(double a) { return ::sin(a); }
-SCPP_HD double cos(double a) { return ::cos(a); }
+SCPP_HD Dual operator/(Dual a, double b) { const double ib = 1. / b; return Dual(a.v * ib, a.d * ib); }
+SCPP_HD Dual operator/(double a, Dual b) { const double ib = 1. / b.v, q = a * ib; return Dual(q, -q * b.d * ib); }
+// (the overloads below would hide ::sqrt / ::sin / ::cos for unqualified calls inside this namespace: re-declare the double versions here)
+using ::sqrt;
+using ::sin;
+using ::cos;
 SCPP_HD Dual sqrt(Dual a) { const double r = ::sqrt(a.v); return Dual(r, a.d / (2. * r)); }
 SCPP_HD Dual sin(Dual a) { return Dual(::sin(a.v), ::cos(a.v) * a.d); }
 SCPP_HD Dual cos(Dual a) { return Dual(::cos(a.v), -::sin(a.v) * a.d); }

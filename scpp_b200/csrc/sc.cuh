@@ -40,6 +40,7 @@ struct ScArrays {
     int N, K, max_it;
     double *x_init, *x_final;      // [N][NX] as uploaded (dimensional)
     double *xi, *xf;               // [N][NX] scaled
+    const ModelParamsHost *Pn;     // [N] per-instance model parameters (Monte-Carlo over the vehicle), or null: every instance uses the engine's
     double *par;                   // [N][NP]
     double *cst;                   // [N][MAX_CST]
     double *scale;                 // [N][2]

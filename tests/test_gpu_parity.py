@@ -656,3 +656,65 @@ def test_two_gpu_sharded_solve_is_bit_identical(S):
                           os.path.join(ROOT, "tools", "multi_gpu_check.py"), "300"], capture_output=True, text=True, timeout=900)
     print(out.stdout[-2000:])
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_dual_number_jacobians_equal_the_hand_derived_ones(S):
+    """K1 with cfg.jacobian = 1 (forward-mode dual numbers over the model's generic-scalar flow map: nothing model-specific beyond
+    systemFlowMap, the role CppAD plays in the reference, systemDynamics.hpp:110-235) against jacobian = 0 (hand-derived sparse Jacobian):
+    equal to rounding on both models; a whole SC solve on the optional fast path still matches the oracle"""
+    p, rpy = O.falcon9()
+    r = O.sc_solve(O.ROCKETQUAT, p, O.sc_config(K=50, max_iterations=2))
+    pn, par = _oracle_nondim_par(p)
+    X, U, t = r["X_all"][2], r["U_all"][2], r["t_all"][2]
+    a = S.discretize(S.ROCKETQUAT, X, U, t, par, nsub=-5, jacobian=1); b = S.discretize(S.ROCKETQUAT, X, U, t, par, nsub=-5, jacobian=0)
+    for key in ("A", "B", "C", "s", "z"):
+        assert np.abs(a[key] - b[key]).max() <= 1e-13 * max(1.0, np.abs(b[key]).max()), key
+    p2 = O.rocket2d()
+    pn2 = O.R2DParams.from_buffer_copy(p2); O.lib().orc_r2d_nondimensionalize(C.byref(pn2))
+    par2 = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(pn2), par2.ctypes.data_as(C.c_void_p))
+    X2 = np.zeros((30, 6)); U2 = np.zeros((30, 2)); t2 = C.c_double()
+    O.lib().orc_r2d_initial_trajectory(C.byref(pn2), 30, X2.ctypes.data_as(C.c_void_p), U2.ctypes.data_as(C.c_void_p), C.byref(t2))
+    a = S.discretize(S.ROCKET2D, X2, U2, t2.value, par2, nsub=20, jacobian=1); b = S.discretize(S.ROCKET2D, X2, U2, t2.value, par2, nsub=20, jacobian=0)
+    for key in ("A", "B", "C", "s", "z"):
+        assert np.abs(a[key] - b[key]).max() <= 1e-13 * max(1.0, np.abs(b[key]).max()), key
+    assert S.default_config(S.ROCKETQUAT).jacobian == 1
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, [p, O.rq_perturb(p, rpy, 0x5C99, 3)], K=50, max_it=4, cfg_over=dict(jacobian=0))
+
+
+def test_per_instance_model_parameters(S):
+    """scpp_b200_set_instance_params: every instance of the batch has its own vehicle (inertia, specific impulse, thrust limits, glide
+    slope); each one against the oracle run with that instance's parameters"""
+    import copy
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=30, max_iterations=5, keep_history=1)
+    p, rpy = O.falcon9()
+    plist, mlist = [], []
+    for i, (isp, jscale, tmax, gs) in enumerate([(275., 1.0, 420000., 30.), (300., 1.2, 400000., 35.), (260., 0.8, 450000., 25.), (290., 1.1, 430000., 40.)]):
+        q = O.rq_perturb(p, rpy, 0x5C99, 200 + i)
+        q.alpha_m = 1. / (isp * 9.81); q.T_max = tmax; q.gamma_gs = np.deg2rad(gs)
+        for a in range(3):
+            q.J_B[a] = p.J_B[a] * jscale
+        plist.append(q)
+        m = S.ModelParams.from_buffer_copy(params)
+        m.alpha_m = q.alpha_m; m.T_max = q.T_max; m.gamma_gs = q.gamma_gs
+        for a in range(3):
+            m.J_B[a] = q.J_B[a]
+        mlist.append(m)
+    xi = np.array([list(q.x_init) for q in plist])
+    eng = S.SCAlgorithm(model, params, cfg, len(plist))
+    eng.set_instance_params(mlist)
+    eng.set_boundary_states(xi, x_final)
+    eng.solve()
+    sol = eng.get_solution(); Xh, Uh, th = eng.get_all_solutions()
+    ocfg = O.sc_config(K=30, max_iterations=5)
+    for i, q in enumerate(plist):
+        ro = O.sc_solve(O.ROCKETQUAT, q, ocfg)
+        n = abs(ro["iterations"])
+        assert ro["iterations"] > 0 and sol["iterations"][i] == n
+        for it in range(n + 1):
+            assert np.abs(Xh[i, it] - ro["X_all"][it]).max() < TOL_X and np.abs(Uh[i, it] - ro["U_all"][it]).max() < TOL_U, (i, it)
+    # back to the shared parameters: instance 0 (whose vehicle is the nominal one) is unchanged, the others are not
+    eng.set_instance_params(None)
+    eng.solve()
+    sol2 = eng.get_solution()
+    eng.close()
+    assert np.array_equal(sol2["X"][0], sol["X"][0]) and not np.array_equal(sol2["X"][1], sol["X"][1])
