@@ -138,6 +138,9 @@ int scpp_b200_get_solution(scpp_b200_engine *e, double *X, double *U, double *t,
 /* SCAlgorithm::getAllSolutions (SCAlgorithm.cpp:217-232): iterate `it` (0 = initial guess) of every instance in the
  * units the algorithm iterates on (nondimensional when cfg.nondimensionalize).  Needs cfg.keep_history. */
 int scpp_b200_get_iterate(scpp_b200_engine *e, int it, double *X, double *U, double *t);
+/* the same iterate redimensionalised, as SCAlgorithm::getAllSolutions returns it (SCAlgorithm.cpp:217-232: model->redimensionalizeTrajectory
+ * on a copy of every iterate); scpp_b200_get_iterate returns the units the algorithm iterates on (what the parity tests compare) */
+int scpp_b200_get_iterate_dimensional(scpp_b200_engine *e, int it, double *X, double *U, double *t);
 int scpp_b200_get_info(scpp_b200_engine *e, double *info /* [N][max_iterations][SCPP_B200_INFO_STRIDE] */);
 
 /* One step of the closed loop of scpp/src/SC_sim.cpp:47-61 for every instance (kernel K4): the first input of the current solution

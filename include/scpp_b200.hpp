@@ -83,8 +83,8 @@ public:
         check(scpp_b200_get_solution(engine, X.data(), U.data(), t.data(), nullptr, nullptr));
         fill(td, X.data() + size_t(instance) * K * nx, U.data() + size_t(instance) * K * nu, t[instance]);
     }
-    // every iterate of one instance, in the units the algorithm iterates on (the reference redimensionalises them with
-    // model->redimensionalizeTrajectory, SCAlgorithm.cpp:217-232)
+    // every iterate of one instance, redimensionalised like the reference's (model->redimensionalizeTrajectory on a copy of every iterate,
+    // SCAlgorithm.cpp:217-232)
     void getAllSolutions(std::vector<trajectory_data_t> &all, int instance = 0) const
     {
         require_solved(instance);
@@ -94,7 +94,7 @@ public:
         std::vector<double> X(size_t(N) * K * nx), U(size_t(N) * K * nu), t(N);
         all.clear();
         for (int it = 0; it <= its[instance]; it++) {
-            check(scpp_b200_get_iterate(engine, it, X.data(), U.data(), t.data()));
+            check(scpp_b200_get_iterate_dimensional(engine, it, X.data(), U.data(), t.data()));
             all.emplace_back();
             fill(all.back(), X.data() + size_t(instance) * K * nx, U.data() + size_t(instance) * K * nu, t[instance]);
         }

@@ -210,6 +210,12 @@ class SCAlgorithm:
         _check(lib().scpp_b200_get_solution(self._h, _p(out["X"]), _p(out["U"]), _p(out["t"]), _p(out["iterations"]), _p(out["flags"])))
         return out
 
+    def get_iterate_dimensional(self, it):
+        """one iterate, redimensionalised like SCAlgorithm::getAllSolutions (SCAlgorithm.cpp:217-232)"""
+        X = np.empty((self.N, self.config.K, self.nx)); U = np.empty((self.N, self.config.K, self.nu)); t = np.empty(self.N)
+        _check(lib().scpp_b200_get_iterate_dimensional(self._h, it, _p(X), _p(U), _p(t)))
+        return X, U, t
+
     def get_iterate(self, it):
         K = self.config.K
         X = np.empty((self.N, K, self.nx)); U = np.empty((self.N, K, self.nu)); t = np.empty(self.N)

@@ -243,7 +243,7 @@ struct scpp_b200_engine {
     virtual int set_boundary(const double *xi, const double *xf) = 0;
     virtual int solve(int warm) = 0;
     virtual int get_solution(double *X, double *U, double *t, int *it, int *flags) = 0;
-    virtual int get_iterate(int it, double *X, double *U, double *t) = 0;
+    virtual int get_iterate(int it, double *X, double *U, double *t, int redim = 0) = 0;
     virtual int get_info(double *info) = 0;
     virtual int sim_step(double time_step, double *x_new, double *u0, int *reached) = 0;
     virtual int lqr_gains(const double *q_diag, const double *r_diag, double *gains, int *ok) = 0;
@@ -564,7 +564,7 @@ struct EngineT : scpp_b200_engine {
         CU(cudaGetLastError());
         return 0;
     }
-    int get_iterate(int it, double *X, double *U, double *t) override
+    int get_iterate(int it, double *X, double *U, double *t, int redim = 0) override
     {
         if (!a.hist) return fail(SCPP_B200_ERR_ARG, "scpp_b200_get_iterate: engine created without keep_history");
         if (it < 0 || it > cfg.max_iterations) return fail(SCPP_B200_ERR_ARG, "scpp_b200_get_iterate: iteration out of range");
@@ -575,11 +575,20 @@ struct EngineT : scpp_b200_engine {
         CU(cudaMemcpy2DAsync(buf.data(), hs * sizeof(double), a.hist + (size_t)it * hs, (size_t)(cfg.max_iterations + 1) * hs * sizeof(double),
                              hs * sizeof(double), N, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
+        std::vector<double> sc;
+        if (redim) {      // SCAlgorithm::getAllSolutions redimensionalises every iterate (SCAlgorithm.cpp:217-232, model->redimensionalizeTrajectory)
+            sc.resize((size_t)N * 2);
+            CU(cudaMemcpy(sc.data(), a.scale, sc.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        }
         for (int n = 0; n < N; n++) {
             const double *h = buf.data() + (size_t)n * hs;
             for (int k = 0; k < K; k++) {
-                if (X) for (int i = 0; i < NX; i++) X[((size_t)n * K + k) * NX + i] = h[k * NB + i];
-                if (U) for (int i = 0; i < NU; i++) U[((size_t)n * K + k) * NU + i] = h[k * NB + NX + i];
+                double x[NX], u[NU];
+                for (int i = 0; i < NX; i++) x[i] = h[k * NB + i];
+                for (int i = 0; i < NU; i++) u[i] = h[k * NB + NX + i];
+                if (redim) M::redim(sc.data() + 2 * n, x, u);
+                if (X) for (int i = 0; i < NX; i++) X[((size_t)n * K + k) * NX + i] = x[i];
+                if (U) for (int i = 0; i < NU; i++) U[((size_t)n * K + k) * NU + i] = u[i];
             }
             if (t) t[n] = h[K * NB];
         }
@@ -878,6 +887,7 @@ int scpp_b200_set_instance_params(scpp_b200_engine *e, const scpp_b200_model_par
 int scpp_b200_solve(scpp_b200_engine *e, int warm) { return e ? e->solve(warm) : fail(SCPP_B200_ERR_ARG, "null engine"); }
 int scpp_b200_get_solution(scpp_b200_engine *e, double *X, double *U, double *t, int *it, int *fl) { return e ? e->get_solution(X, U, t, it, fl) : fail(SCPP_B200_ERR_ARG, "null engine"); }
 int scpp_b200_get_iterate(scpp_b200_engine *e, int it, double *X, double *U, double *t) { return e ? e->get_iterate(it, X, U, t) : fail(SCPP_B200_ERR_ARG, "null engine"); }
+int scpp_b200_get_iterate_dimensional(scpp_b200_engine *e, int it, double *X, double *U, double *t) { return e ? e->get_iterate(it, X, U, t, 1) : fail(SCPP_B200_ERR_ARG, "null engine"); }
 int scpp_b200_get_info(scpp_b200_engine *e, double *info) { return (e && info) ? e->get_info(info) : fail(SCPP_B200_ERR_ARG, "null argument"); }
 int scpp_b200_last_timing(scpp_b200_engine *e, double *a, double *b, double *c, int *l, int *o, long long *ii)
 {

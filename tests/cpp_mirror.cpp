@@ -2,6 +2,7 @@
 // exercised without a GPU: parameter loading, the reference's error behaviour, and the loud failure when there is no CUDA device.
 // With a GPU (argv[2] == "gpu") it runs SC and SCvx for one instance.
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include "scpp_b200.hpp"
 
@@ -29,6 +30,9 @@ int main(int argc, char **argv)
         a.initialize(); a.cfg.K = 15; a.solve();
         scpp_b200::trajectory_data_t td; a.getSolution(td);
         std::vector<scpp_b200::trajectory_data_t> all; a.getAllSolutions(all);
+        // getAllSolutions redimensionalises every iterate (SCAlgorithm.cpp:217-232): the last one equals getSolution, the first starts at x_init
+        for (size_t k = 0; k < td.n_X(); k++) for (int i = 0; i < a.state_dim(); i++) if (all.back().X[k][i] != td.X[k][i]) { printf("FAIL: last iterate != solution\n"); return 1; }
+        if (std::fabs(all.front().X[0][0] - 24000.) > 1e-6) { printf("FAIL: iterates are not redimensionalised (m0 = %g)\n", all.front().X[0][0]); return 1; }
         v.initialize(); v.solve();
         std::vector<int> it, fl; v.getStatus(it, fl);
         printf("ok (GPU): SC K=%zu iterates=%zu t=%.3f ; SCvx iterations=%d flag=%d\n", td.n_X(), all.size(), td.t, it[0], fl[0]);
