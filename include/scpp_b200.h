@@ -191,6 +191,35 @@ int scpp_b200_comm_unique_id(char id[128]);
 int scpp_b200_comm_init(scpp_b200_engine *e, int nranks, int rank, const char id[128]);
 long long scpp_b200_global_active(scpp_b200_engine *e); /* instances still iterating over all ranks after the last solve */
 
+/* ---- receding-horizon MPC ------------------------------------------------------------------------------------
+ * replaces MPCAlgorithm (scpp_core/include/MPCAlgorithm.hpp:9-98, src/MPCAlgorithm.cpp:11-140), buildMPCProblem (src/MPCProblem.cpp:6-87)
+ * and exactLinearDiscretization (src/discretization.cpp:9-40) for a Monte-Carlo batch: N instances that share the model, the operating
+ * point and the weights and differ in x_init / x_final.  The linear time-invariant dynamics are eliminated once on the host; kernel K6
+ * solves the dense conic program of every instance (one thread each).  Models: Rocket2D (the only reference model with getOperatingPoint
+ * and an MPC.info).  Not built: intermediate_cost_active, constant_dynamics = false, nondimensionalize (UNSUPPORTED); the state rows of
+ * addApplicationConstraints act on nodes 1..K-1 (node 0 is the given state). */
+typedef struct {
+    int K;
+    int nondimensionalize, constant_dynamics, intermediate_cost_active;
+    double time_horizon;
+    double state_weights_intermediate[16], state_weights_terminal[16], input_weights[8];
+    scpp_b200_ipm_settings ipm;
+} scpp_b200_mpc_config;
+typedef struct scpp_b200_mpc scpp_b200_mpc;
+int scpp_b200_load_mpc_info(const char *path, int model, scpp_b200_mpc_config *cfg);                  /* MPCAlgorithm::loadParameters */
+int scpp_b200_mpc_create(int model, const scpp_b200_model_params *params, const scpp_b200_mpc_config *cfg, int n_instances, int device,
+                         scpp_b200_mpc **out);                                                         /* MPCAlgorithm ctor + initialize() */
+void scpp_b200_mpc_destroy(scpp_b200_mpc *m);
+int scpp_b200_mpc_set_states(scpp_b200_mpc *m, const double *x_init, const double *x_final);           /* setInitialState / setFinalState; [N][nx], NULL keeps */
+int scpp_b200_mpc_solve(scpp_b200_mpc *m);                                                             /* MPCAlgorithm::solve for every instance */
+/* getSolution: X [N][K][nx], U [N][K-1][nu]; status [N]: 0 optimal, 3 reduced accuracy, 1/2 failed; iters [N] interior-point iterations */
+int scpp_b200_mpc_get_solution(scpp_b200_mpc *m, double *X, double *U, int *status, int *iters);
+/* one step of scpp/src/MPC_sim.cpp:64-70 on the device: simulate(model, dt, u, u, x) with u = U[0], x_init <- x; x_new [N][nx] or NULL */
+int scpp_b200_mpc_sim_step(scpp_b200_mpc *m, double dt, double *x_new);
+/* test hook: A [nx][nx], B [nx][nu] (row-major), z [nx] of exactLinearDiscretization at the operating point */
+int scpp_b200_mpc_get_discretization(scpp_b200_mpc *m, double *A, double *B, double *z);
+double scpp_b200_mpc_last_ms(scpp_b200_mpc *m);                                                        /* device time of the last solve */
+
 #ifdef __cplusplus
 }
 #endif

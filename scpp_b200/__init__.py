@@ -278,6 +278,71 @@ class SCAlgorithm:
         return lib().scpp_b200_global_active(self._h)
 
 
+class MPCConfig(C.Structure):
+    """scpp_b200_mpc_config == MPC.info (MPCAlgorithm.cpp:17-32)"""
+    _fields_ = [("K", C.c_int), ("nondimensionalize", C.c_int), ("constant_dynamics", C.c_int), ("intermediate_cost_active", C.c_int),
+                ("time_horizon", C.c_double), ("state_weights_intermediate", C.c_double * 16), ("state_weights_terminal", C.c_double * 16),
+                ("input_weights", C.c_double * 8), ("ipm", IpmSettings)]
+
+
+def load_mpc_info(path, model):
+    cfg = MPCConfig()
+    _check(lib().scpp_b200_load_mpc_info(path.encode(), model, C.byref(cfg)))
+    return cfg
+
+
+class MPCAlgorithm:
+    """Batched counterpart of scpp::MPCAlgorithm (scpp_core/include/MPCAlgorithm.hpp:9-98): one linear receding-horizon problem per
+    instance, all sharing the model, the operating point and the weights"""
+
+    def __init__(self, model, params, config, n_instances, device=0):
+        self.model, self.params, self.config, self.N = model, params, config, int(n_instances)
+        self.nx, self.nu, _ = model_dims(model)
+        self._h = C.c_void_p()
+        _check(lib().scpp_b200_mpc_create(model, C.byref(params), C.byref(config), self.N, device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().scpp_b200_mpc_destroy.argtypes = [C.c_void_p]
+            lib().scpp_b200_mpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_states(self, x_init=None, x_final=None):
+        """setInitialState / setFinalState for every instance"""
+        b = lambda a: None if a is None else np.ascontiguousarray(np.broadcast_to(np.atleast_2d(np.asarray(a, float)), (self.N, self.nx)))
+        xi, xf = b(x_init), b(x_final)
+        _check(lib().scpp_b200_mpc_set_states(self._h, _p(xi), _p(xf)))
+
+    def solve(self):
+        _check(lib().scpp_b200_mpc_solve(self._h))
+
+    def get_solution(self):
+        K = self.config.K
+        X = np.empty((self.N, K, self.nx)); U = np.empty((self.N, K - 1, self.nu)); st = np.empty(self.N, np.int32); it = np.empty(self.N, np.int32)
+        _check(lib().scpp_b200_mpc_get_solution(self._h, _p(X), _p(U), _p(st), _p(it)))
+        return dict(X=X, U=U, status=st, iterations=it)
+
+    def sim_step(self, dt):
+        x = np.empty((self.N, self.nx))
+        _check(lib().scpp_b200_mpc_sim_step(self._h, C.c_double(dt), _p(x)))
+        return x
+
+    def discretization(self):
+        A = np.empty((self.nx, self.nx)); B = np.empty((self.nx, self.nu)); z = np.empty(self.nx)
+        _check(lib().scpp_b200_mpc_get_discretization(self._h, _p(A), _p(B), _p(z)))
+        return A, B, z
+
+    def last_ms(self):
+        lib().scpp_b200_mpc_last_ms.restype = C.c_double
+        return lib().scpp_b200_mpc_last_ms(self._h)
+
+
 def comm_unique_id():
     buf = C.create_string_buffer(128)
     _check(lib().scpp_b200_comm_unique_id(buf))

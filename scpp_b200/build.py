@@ -29,7 +29,8 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
-    jobs = [([nvcc] + ARCH + extra + ["-c", os.path.join(SRC, "engine.cu"), "-o", os.path.join(OBJ, "engine.o")], "engine")]
+    jobs = [([nvcc] + ARCH + extra + ["-c", os.path.join(SRC, "engine.cu"), "-o", os.path.join(OBJ, "engine.o")], "engine"),
+            ([nvcc] + ARCH + extra + ["-c", os.path.join(SRC, "mpc.cu"), "-o", os.path.join(OBJ, "mpc.o")], "mpc")]
     for m, g in GROUPS:
         jobs.append(([nvcc] + ARCH + extra + [f"-DSCPP_KERNEL_MODEL={m}", f"-DSCPP_KERNEL_GROUP={g}", "-c", os.path.join(SRC, "kernels_inst.cu"),
                                               "-o", os.path.join(OBJ, f"k_{m}_{g}.o")], f"kernels model {m} group {g}"))
@@ -44,7 +45,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         list(ex.map(run, jobs))
-    objs = [os.path.join(OBJ, "engine.o")] + [os.path.join(OBJ, f"k_{m}_{g}.o") for m, g in GROUPS]
+    objs = [os.path.join(OBJ, "engine.o"), os.path.join(OBJ, "mpc.o")] + [os.path.join(OBJ, f"k_{m}_{g}.o") for m, g in GROUPS]
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + ["-ldl"])
     return OUT
 

@@ -21,6 +21,7 @@ static_assert(SCPP_B200_INFO_STRIDE == INFO_STRIDE, "ABI constant mismatch");
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+int scpp_b200_fail(int code, const std::string &msg) { return fail(code, msg); }      // for the other translation units of the library (mpc.cu)
 #define CU(call)                                                                                                  \
     do {                                                                                                          \
         cudaError_t e_ = (call);                                                                                  \

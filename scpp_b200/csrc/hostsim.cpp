@@ -228,4 +228,20 @@ extern "C" void hs_lqr_gains(int model, int K, const double *X, const double *U,
     if (model == 0) run_lqr<RocketQuat>(K, X, U, par, qd, rd, gains, ok); else run_lqr<Rocket2d>(K, X, U, par, qd, rd, gains, ok);
 }
 
+// K6 body on the host: the dense conic solver of mpc.cuh on a problem given in full (G row-major [nr][nv])
+#include "mpc.cuh"
+extern "C" int hs_dense_conic(int nv, int nl, int ncones, const int *cdim, const double *G, const double *c, const double *h, double tol, double *y, int *iters)
+{
+    static DenseConic<48, 320, 48> S;
+    int nr = nl;
+    for (int k = 0; k < ncones; k++) nr += cdim[k];
+    if (nv > 48 || nr > 320 || ncones > 48) return -1;
+    S.nv = nv; S.nl = nl; S.ncones = ncones; S.nr = nr; S.cdim = cdim; S.G = G; S.c = c;
+    IpmSettings st; st.feastol = st.abstol = st.reltol = tol; st.maxit = 100; st.pad_ = 0; st.warm = 0.;
+    const IpmResult r = S.solve(h, st);
+    for (int i = 0; i < nv; i++) y[i] = S.y[i];
+    *iters = r.iterations;
+    return r.status;
+}
+
 extern "C" int hs_sizes(int which) { return which == 0 ? (int)sizeof(ModelParamsHost) : (int)sizeof(ScConfig); }

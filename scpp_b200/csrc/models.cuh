@@ -299,6 +299,8 @@ struct RocketQuat {
         for (int i = 0; i < 3; i++) u[i] /= scale[0] * scale[1];
         u[3] /= scale[0] * scale[1] * scale[1];
     }
+    // getOperatingPoint is not overridden by RocketQuat: the base class throws (scpp_core/include/systemModel.hpp:119)
+    SCPP_HD static bool operating_point(const ModelParamsHost &, double *, double *) { return false; }
     // linearised minimum-thrust direction: U0.head<3>().normalized() (rocketQuat.cpp:162-165)
     SCPP_HD static void thrust_dir(const double *u, double *d)
     {
@@ -408,6 +410,13 @@ struct Rocket2d {
         u[1] /= scale[0] * scale[1];
     }
     SCPP_HD static void thrust_dir(const double *, double *d) { d[0] = 0.; d[1] = 0.; d[2] = 1.; }
+    // Rocket2d::getOperatingPoint (rocket2d.cpp:40-44): hover, x = 0, u = (gimbal 0, thrust |g| m)
+    SCPP_HD static bool operating_point(const ModelParamsHost &P, double *x, double *u)
+    {
+        for (int i = 0; i < NX; i++) x[i] = 0.;
+        u[0] = 0.; u[1] = -P.g_I[1] * P.m;
+        return true;
+    }
 };
 
 static const RowDesc rq_rows_host[RocketQuat::NLP + RocketQuat::NCR] = SCPP_RQ_ROWS;

@@ -718,3 +718,48 @@ def test_per_instance_model_parameters(S):
     sol2 = eng.get_solution()
     eng.close()
     assert np.array_equal(sol2["X"][0], sol["X"][0]) and not np.array_equal(sol2["X"][1], sol["X"][1])
+
+
+def test_mpc_vs_oracle(S):
+    """MPCAlgorithm on the device (kernel K6, one thread per instance) for a Monte-Carlo batch of Rocket2D states against the
+    oracle's conic solver on the full problem of buildMPCProblem + addApplicationConstraints (tests/mpc_ref.py); exactLinearDiscretization
+    against scipy's matrix exponential; K = 7 (the shipped MPC.info) and K = 21 (a 20-step horizon, BASELINE configs[3])"""
+    import mpc_ref as R
+    model, params, x_init, x_final, _ = S.load_model("Rocket2D")
+    params.constrain_initial_final = 0
+    p = O.rocket2d()
+    rng = np.random.default_rng(11)
+    for K, horizon in ((7, 1.5), (21, 4.0)):
+        cfg = S.load_mpc_info(os.path.join(S.CONFIG_DIR, "Rocket2D", "MPC.info"), S.ROCKET2D)
+        cfg.K = K; cfg.time_horizon = horizon
+        N = 64
+        x0 = np.array([-20., 100., 2., -10., 0.05, 0.0]) * (1 + 0.1 * rng.standard_normal((N, 6)))
+        xf = np.array([0., 0, 0, -1, 0, 0.])
+        mpc = S.MPCAlgorithm(model, params, cfg, N)
+        A, B, z = mpc.discretization()
+        Ar, Br, zr = R.discretize(p, horizon / (K - 1))
+        assert np.abs(A - Ar).max() < 1e-8 and np.abs(B - Br).max() < 1e-8 * max(1., np.abs(Br).max()) and np.abs(z - zr).max() < 1e-8
+        mpc.set_states(x0, xf)
+        mpc.solve()
+        sol = mpc.get_solution()
+        assert (np.isin(sol["status"], (0, 3))).mean() > 0.9 and sol["iterations"].max() < 60
+        w_term = np.array(list(cfg.state_weights_terminal)[:6]); w_in = np.array(list(cfg.input_weights)[:2])
+        for i in range(0, N, 8):
+            P = R.full_socp(p, K, A, B, z, x0[i], xf, w_term, w_in)
+            r = R.solve_with_oracle(O, P)
+            if r["status"] != 0:
+                continue
+            assert sol["status"][i] in (0, 3)
+            Xo = np.array([[r["x"][P["iX"](k, j)] for j in range(6)] for k in range(K)]); Uo = np.array([[r["x"][P["iU"](k, j)] for j in range(2)] for k in range(K - 1)])
+            assert np.abs(sol["U"][i][:, 0] - Uo[:, 0]).max() < 1e-4 and np.abs(sol["U"][i][:, 1] - Uo[:, 1]).max() < 1e-5 * np.abs(Uo[:, 1]).max(), (K, i)
+            assert np.abs(sol["X"][i] - Xo).max() < 1e-5 * max(1., np.abs(Xo).max()), (K, i)
+        # closed loop (MPC_sim.cpp:64-70): the simulated state is the next initial state; the oracle's RKF78 gives the same step
+        x1 = mpc.sim_step(0.05)
+        par = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(p), par.ctypes.data_as(C.c_void_p))
+        ref = O.simulate(O.ROCKET2D, 0.05, sol["U"][0][0], sol["U"][0][0], par, x0[0])
+        assert np.abs(x1[0] - ref).max() < 1e-9 * max(1., np.abs(ref).max())
+        mpc.solve()
+        assert (np.isin(mpc.get_solution()["status"], (0, 3))).mean() > 0.9
+        mpc.close()
+    with pytest.raises(S.ScppError):
+        S.MPCAlgorithm(S.ROCKETQUAT, S.load_model("RocketQuat")[1], cfg, 1)          # no operating point: the reference throws too

@@ -390,3 +390,44 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_a_gpu(S, tmp_path):
         pytest.skip("a GPU is present (covered by the gpu-marked test)")
     out = subprocess.run([_build_cpp_mirror(tmp_path), os.path.join(ROOT, "configs")], capture_output=True, text=True)
     assert out.returncode == 0 and "ok (no GPU)" in out.stdout, out.stdout + out.stderr
+
+
+def test_mpc_dense_conic_source_vs_oracle():
+    """K6 body on the host (mpc.cuh: dense Mehrotra / Nesterov-Todd solver, one problem per thread on the device) on the CONDENSED MPC problem
+    against the oracle's generic conic solver on the FULL problem of buildMPCProblem (MPCProblem.cpp:6-87: X, U, equality-constrained
+    dynamics), both built in tests/mpc_ref.py from the same exact discretisation; several states, K = 7 (MPC.info) and K = 21"""
+    import ctypes as C
+    import mpc_ref as R
+    p = O.rocket2d()
+    w_term = np.array([5., 5, 5, 1, 1, 1]); w_in = np.array([0.1, 0.1])
+    x_final = np.array([0., 0, 0, -1, 0, 0.])
+    pp = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(3)
+    for K, horizon in ((7, 1.5), (21, 4.0)):
+        A, B, z = R.discretize(p, horizon / (K - 1))
+        compared = 0
+        for trial in range(4):
+            x_init = np.array([-20., 100., 2., -10., 0.05, 0.0]) * (1 + 0.15 * rng.standard_normal(6))
+            P = R.full_socp(p, K, A, B, z, x_init, x_final, w_term, w_in)
+            r = R.solve_with_oracle(O, P)
+            if r["status"] != 0:
+                continue                      # an instance the oracle cannot solve to tolerance (glide slope / minimum thrust make it infeasible)
+            compared += 1
+            Uo = np.array([[r["x"][P["iU"](k, i)] for i in range(2)] for k in range(K - 1)])
+            nv, nl, cdim, G, c, h, _ = R.condensed(p, K, A, B, z, x_init, x_final, w_term, w_in)
+            y = np.zeros(nv); it = C.c_int()
+            st = H.lib().hs_dense_conic(nv, nl, len(cdim), pp(np.array(cdim, np.int32)), pp(G), pp(c), pp(h), C.c_double(1e-8), pp(y), C.byref(it))
+            assert st in (0, 3) and it.value < 40
+            assert abs(y[-2] + y[-1] - r["info"].pcost) < 1e-7 * abs(r["info"].pcost)
+            U = y[:-2].reshape(K - 1, 2)
+            assert np.abs(U[:, 0] - Uo[:, 0]).max() < 1e-4 and np.abs(U[:, 1] - Uo[:, 1]).max() < 1e-5 * np.abs(Uo[:, 1]).max()      # north_star: 1e-4 on the control
+        assert compared >= 2
+
+
+def test_mpc_info_loader(S):
+    """scpp_b200_load_mpc_info == MPCAlgorithm::loadParameters (MPCAlgorithm.cpp:17-32) on the shipped Rocket2D MPC.info"""
+    c = S.load_mpc_info(os.path.join(S.CONFIG_DIR, "Rocket2D", "MPC.info"), S.ROCKET2D)
+    assert (c.K, c.time_horizon, c.nondimensionalize, c.constant_dynamics, c.intermediate_cost_active) == (7, 1.5, 0, 1, 0)
+    assert list(c.state_weights_terminal)[:6] == [5., 5., 5., 1., 1., 1.] and np.allclose(list(c.input_weights)[:2], [0.1, 0.1])
+    with pytest.raises(S.ScppError):
+        S.load_mpc_info(os.path.join(S.CONFIG_DIR, "Rocket2D", "SC.info"), S.ROCKET2D)
