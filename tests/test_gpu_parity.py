@@ -729,7 +729,7 @@ def test_mpc_vs_oracle(S):
     params.constrain_initial_final = 0
     p = O.rocket2d()
     rng = np.random.default_rng(11)
-    for K, horizon in ((7, 1.5), (21, 4.0)):
+    for K, horizon, gimbal_bar in ((7, 1.5, 1e-4), (21, 2.5, 5e-3)):     # bars: see tests/test_host.py::test_mpc_dense_conic_source_vs_oracle
         cfg = S.load_mpc_info(os.path.join(S.CONFIG_DIR, "Rocket2D", "MPC.info"), S.ROCKET2D)
         cfg.K = K; cfg.time_horizon = horizon
         N = 64
@@ -744,15 +744,18 @@ def test_mpc_vs_oracle(S):
         sol = mpc.get_solution()
         assert (np.isin(sol["status"], (0, 3))).mean() > 0.9 and sol["iterations"].max() < 60
         w_term = np.array(list(cfg.state_weights_terminal)[:6]); w_in = np.array(list(cfg.input_weights)[:2])
+        compared = 0
         for i in range(0, N, 8):
             P = R.full_socp(p, K, A, B, z, x0[i], xf, w_term, w_in)
             r = R.solve_with_oracle(O, P)
             if r["status"] != 0:
                 continue
+            compared += 1
             assert sol["status"][i] in (0, 3)
             Xo = np.array([[r["x"][P["iX"](k, j)] for j in range(6)] for k in range(K)]); Uo = np.array([[r["x"][P["iU"](k, j)] for j in range(2)] for k in range(K - 1)])
-            assert np.abs(sol["U"][i][:, 0] - Uo[:, 0]).max() < 1e-4 and np.abs(sol["U"][i][:, 1] - Uo[:, 1]).max() < 1e-5 * np.abs(Uo[:, 1]).max(), (K, i)
+            assert np.abs(sol["U"][i][:, 0] - Uo[:, 0]).max() < gimbal_bar and np.abs(sol["U"][i][:, 1] - Uo[:, 1]).max() < 1e-5 * np.abs(Uo[:, 1]).max(), (K, i)
             assert np.abs(sol["X"][i] - Xo).max() < 1e-5 * max(1., np.abs(Xo).max()), (K, i)
+        assert compared >= 5
         # closed loop (MPC_sim.cpp:64-70): the simulated state is the next initial state; the oracle's RKF78 gives the same step
         x1 = mpc.sim_step(0.05)
         par = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(p), par.ctypes.data_as(C.c_void_p))
