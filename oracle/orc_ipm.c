@@ -23,7 +23,7 @@
 #define ABSTOL 1e-9
 #define RELTOL 1e-9
 #define MAXIT 100
-static double g_static_reg = 1e-13;   /* orc_set_static_reg(): the SCvx sub-problem has variables without any cone row and needs ECOS-sized regularisation */
+static __thread double g_static_reg = 1e-13;   /* per thread: the tests run the oracle on several host threads and the SCvx solve sets and restores it (a shared global raced and leaked 2e-7 into later SC solves).  orc_set_static_reg(): the SCvx sub-problem has variables without any cone row and needs ECOS-sized regularisation */
 #define STATIC_REG g_static_reg
 void orc_set_static_reg(double v) { g_static_reg = v; }
 double orc_get_static_reg(void) { return g_static_reg; }

@@ -23,12 +23,16 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant: A/B experiments -- builds libscpp_b200_<variant>.so with extra -D defines (selected at run time with SCPP_B200_LIB)"""
+    global OBJ, OUT
+    if variant:
+        OBJ = os.path.join(HERE, "_obj_" + variant); OUT = os.path.join(HERE, f"libscpp_b200_{variant}.so"); force = True
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + list(defines)
     jobs = [([nvcc] + ARCH + extra + ["-c", os.path.join(SRC, "engine.cu"), "-o", os.path.join(OBJ, "engine.o")], "engine"),
             ([nvcc] + ARCH + extra + ["-c", os.path.join(SRC, "mpc.cu"), "-o", os.path.join(OBJ, "mpc.o")], "mpc")]
     for m, g in GROUPS:
@@ -51,4 +55,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:      # python scpp_b200/build.py --variant w8 -DSCPP_WPB_MAX=8
+        i = sys.argv.index("--variant")
+        print(build(variant=sys.argv[i + 1], defines=[a for a in sys.argv[i + 2:] if a.startswith("-")], verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

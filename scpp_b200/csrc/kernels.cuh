@@ -7,7 +7,10 @@
 
 namespace scpp {
 
-constexpr int WPB_MAX = 7;   // warps (= problem instances) per CTA of the SOCP kernels (chosen per launch, see EngineT::solve())
+#ifndef SCPP_WPB_MAX
+#define SCPP_WPB_MAX 7
+#endif
+constexpr int WPB_MAX = SCPP_WPB_MAX;   // warps (= problem instances) per CTA of the SOCP kernels (chosen per launch, see EngineT::solve())
 
 // K1: one thread per (active instance, interval, column)
 template <class M, bool AD>
