@@ -29,6 +29,11 @@ extern "C" {
 /* model selector: the reference picks the model at compile time, scpp_core/include/activeModel.hpp:6-10 */
 #define SCPP_B200_MODEL_ROCKETQUAT 0 /* scpp_models/src/rocketQuat.cpp, nx=14 nu=4 np=10 */
 #define SCPP_B200_MODEL_ROCKET2D 1   /* scpp_models/src/rocket2d.cpp,  nx=6  nu=2 np=6  */
+/* the same planar rocket written ONLY against the reference's plugin surface (scpp_core/include/systemModel.hpp:64-137): generic-scalar
+ * systemFlowMap, getInitializedTrajectory, (non/re)dimensionalisation and addApplicationConstraints in the cvx:: DSL (include/scpp_cvx.hpp).
+ * Jacobians by forward-mode dual numbers; the constraint table is generated at build time from the recorded constraints
+ * (include/scpp_plugin.hpp, tools/gen_plugin.cpp, scpp_b200/plugins/rocket2d_plugin.hpp).  Needs constrain_initial_final = true. */
+#define SCPP_B200_MODEL_ROCKET2D_PLUGIN 2
 
 /* RocketQuat::Parameters (scpp_models/include/rocketQuat.hpp:50-85) and Rocket2d::Parameters
  * (scpp_models/include/rocket2d.hpp:51-84) as loaded from model.info; angles in radians.
@@ -98,6 +103,12 @@ int scpp_b200_version(void);
 const char *scpp_b200_last_error(void);
 int scpp_b200_device_count(void); /* 0 if no usable CUDA device */
 int scpp_b200_model_dims(int model, int *nx, int *nu, int *np);
+/* the stage-wise constraint table the engine uses for `model`, evaluated for `params` (dimensional, nondimensionalize = 0): one record of
+ * 8 doubles per row {n, idx0, idx1, idx2, coef0, coef1, coef2, h} meaning  s = h - sum_j coef_j * xi[idx_j]  (xi = [x ; u] of a node; a
+ * coefficient taken from the per-node minimum-thrust direction is reported as NaN).  rows receives n_lp LP rows, then the cone rows;
+ * cone_dims [n_cones].  What a maintainer compares against a model's addApplicationConstraints (tests/cvx_shim_test.cpp does). */
+int scpp_b200_model_rows(int model, const scpp_b200_model_params *params, const double *x_init, const double *x_final, int max_rows,
+                         double *rows, int *n_lp, int *n_cones, int *cone_dims);
 void scpp_b200_default_config(int model, scpp_b200_sc_config *cfg); /* values of scpp_models/config/<Model>/SC.info */
 
 /* ---- parameter files (host logic; usable without a GPU) -------------------------------------------------------

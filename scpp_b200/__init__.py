@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCPP_B200_LIB", os.path.join(_HERE, "libscpp_b200.so"))   # the override is for A/B experiments with kernel variants
 CONFIG_DIR = os.path.join(os.path.dirname(_HERE), "configs")
 
-ROCKETQUAT, ROCKET2D = 0, 1
-MODEL_NAMES = {ROCKETQUAT: "RocketQuat", ROCKET2D: "Rocket2D"}
+ROCKETQUAT, ROCKET2D, ROCKET2D_PLUGIN = 0, 1, 2      # 2: Rocket2D written only against the plugin surface (scpp_b200/plugins/rocket2d_plugin.hpp)
+MODEL_NAMES = {ROCKETQUAT: "RocketQuat", ROCKET2D: "Rocket2D", ROCKET2D_PLUGIN: "Rocket2D"}
 INFO_STRIDE = 10
 INFO_FIELDS = ("norm1_nu", "sum_delta", "delta_sigma", "sigma", "weight_tr_used", "ipm_iterations", "ipm_status", "pres", "dres", "relgap")
 
@@ -118,9 +118,25 @@ def load_scvx_info(path, model):
     return cfg
 
 
+def model_rows(model, params, x_init, x_final):
+    """scpp_b200_model_rows: the stage-wise constraint table the engine uses, evaluated for params: (LP rows, [cone rows...]) with every row
+    = (dict index -> coefficient, h) meaning s = h - sum coef * xi[index]"""
+    rows = np.zeros((64, 8)); nlp = C.c_int(); nc = C.c_int(); dims = (C.c_int * 16)()
+    xi = np.ascontiguousarray(x_init, float); xf = np.ascontiguousarray(x_final, float)
+    _check(lib().scpp_b200_model_rows(model, C.byref(params), _p(xi), _p(xf), 64, _p(rows), C.byref(nlp), C.byref(nc), dims))
+    conv = lambda r: ({int(r[1 + q]): float(r[4 + q]) for q in range(int(r[0]))}, float(r[7]))
+    lp = [conv(rows[r]) for r in range(nlp.value)]
+    cones, at = [], nlp.value
+    for c in range(nc.value):
+        cones.append([conv(rows[at + i]) for i in range(dims[c])]); at += dims[c]
+    return lp, cones
+
+
 def load_model(name, K=None, algorithm="SC", **overrides):
-    """convenience: configs/<name>/{model,SC|SCvx}.info -> (model id, ModelParams, x_init, x_final, SCConfig)"""
-    model = ROCKET2D if name == "Rocket2D" else ROCKETQUAT
+    """convenience: configs/<name>/{model,SC|SCvx}.info -> (model id, ModelParams, x_init, x_final, SCConfig); name "Rocket2DPlugin" = the
+    Rocket2D files with the plugin-surface model"""
+    model = ROCKET2D_PLUGIN if name == "Rocket2DPlugin" else (ROCKET2D if name == "Rocket2D" else ROCKETQUAT)
+    name = MODEL_NAMES[model] if model == ROCKET2D_PLUGIN else name
     folder = os.path.join(CONFIG_DIR, name)
     p, xi, xf = load_model_info(os.path.join(folder, "model.info"), model)
     cfg = load_scvx_info(os.path.join(folder, "SCvx.info"), model) if algorithm == "SCvx" else load_sc_info(os.path.join(folder, "SC.info"), model)

@@ -729,7 +729,38 @@ int scpp_b200_device_count(void)
 int scpp_b200_model_dims(int model, int *nx, int *nu, int *np)
 {
     if (model == SCPP_B200_MODEL_ROCKETQUAT) { *nx = RocketQuat::NX; *nu = RocketQuat::NU; *np = RocketQuat::NP; return 0; }
-    if (model == SCPP_B200_MODEL_ROCKET2D) { *nx = Rocket2d::NX; *nu = Rocket2d::NU; *np = Rocket2d::NP; return 0; }
+    if (model == SCPP_B200_MODEL_ROCKET2D || model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) { *nx = Rocket2d::NX; *nu = Rocket2d::NU; *np = Rocket2d::NP; return 0; }
+    return fail(SCPP_B200_ERR_ARG, "unknown model");
+}
+extern "C++" {
+template <class M>
+static int model_rows_t(const ModelParamsHost &P, const double *x_init, const double *x_final, int max_rows, double *rows, int *n_lp, int *n_cones, int *cone_dims)
+{
+    if (M::NLP + M::NCR > max_rows) return fail(SCPP_B200_ERR_ARG, "scpp_b200_model_rows: max_rows too small");
+    double xi[M::NX], xf[M::NX], par[M::NP], cst[MAX_CST], sc2[2];
+    for (int i = 0; i < M::NX; i++) { xi[i] = x_init[i]; xf[i] = x_final[i]; }
+    M::setup(P, 0, xi, xf, par, cst, sc2);
+    for (int r = 0; r < M::NLP + M::NCR; r++) {
+        const RowDesc rd = M::row(r);
+        double *o = rows + 8 * r;
+        o[0] = rd.n;
+        for (int q = 0; q < 3; q++) { o[1 + q] = q < rd.n ? rd.idx[q] : -1; o[4 + q] = q < rd.n ? (rd.cs[q] >= 0 ? cst[rd.cs[q]] : NAN) : 0.; }
+        o[7] = cst[rd.hs];
+    }
+    *n_lp = M::NLP; *n_cones = M::NCONE;
+    for (int c = 0; c < M::NCONE; c++) cone_dims[c] = M::cone_dim(c);
+    return 0;
+}
+}   // extern "C++"
+int scpp_b200_model_rows(int model, const scpp_b200_model_params *params, const double *x_init, const double *x_final, int max_rows,
+                         double *rows, int *n_lp, int *n_cones, int *cone_dims)
+{
+    if (!params || !x_init || !x_final || !rows || !n_lp || !n_cones || !cone_dims) return fail(SCPP_B200_ERR_ARG, "scpp_b200_model_rows: bad argument");
+    ModelParamsHost P;
+    memcpy(&P, params, sizeof(P));
+    if (model == SCPP_B200_MODEL_ROCKETQUAT) return model_rows_t<RocketQuat>(P, x_init, x_final, max_rows, rows, n_lp, n_cones, cone_dims);
+    if (model == SCPP_B200_MODEL_ROCKET2D) return model_rows_t<Rocket2d>(P, x_init, x_final, max_rows, rows, n_lp, n_cones, cone_dims);
+    if (model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) return model_rows_t<Rocket2dPlugin>(P, x_init, x_final, max_rows, rows, n_lp, n_cones, cone_dims);
     return fail(SCPP_B200_ERR_ARG, "unknown model");
 }
 // scpp_models/config/RocketQuat/SC.info:1-16, scpp_models/config/Rocket2D/SC.info:1-16
@@ -800,7 +831,7 @@ int scpp_b200_load_model_info(const char *path, int model, scpp_b200_model_param
             // perturbed by the caller instead
             (void)random_initial_state;
             if (roll) return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control = true is not built into this engine");
-        } else if (model == SCPP_B200_MODEL_ROCKET2D) {   // rocket2d.cpp:150-196
+        } else if (model == SCPP_B200_MODEL_ROCKET2D || model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) {   // rocket2d.cpp:150-196
             bool cif, slack;
             double r_init[2], v_init[2], r_final[2], v_final[2], w_init, w_final, eta_init, eta_final;
             ps.loadMatrix("g_I", p->g_I, 2); ps.loadScalar("J_B", p->J_B[0]); ps.loadMatrix("r_T_B", p->r_T_B, 2);
@@ -873,6 +904,10 @@ int scpp_b200_create(int model, const scpp_b200_model_params *params, const scpp
     scpp_b200_engine *e = nullptr;
     if (model == SCPP_B200_MODEL_ROCKETQUAT) e = new EngineT<RocketQuat>();
     else if (model == SCPP_B200_MODEL_ROCKET2D) e = new EngineT<Rocket2d>();
+    else if (model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) {
+        if (!params->constrain_initial_final) return fail(SCPP_B200_ERR_UNSUPPORTED, "the plugin model's table was generated with constrain_initial_final = true");
+        e = new EngineT<Rocket2dPlugin>();
+    }
     else return fail(SCPP_B200_ERR_ARG, "unknown model");
     e->model = model; e->N = n; e->device = device;
     memcpy(&e->P, params, sizeof(ModelParamsHost));
@@ -947,6 +982,7 @@ int scpp_b200_discretize2(int model, int K, int n, int nsub, int jacobian, int d
     if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");
     if (model == SCPP_B200_MODEL_ROCKETQUAT) return discretize_hook<RocketQuat>(K, n, nsub, jacobian, device, X, U, sigma, par, A, B, C, s, z);
     if (model == SCPP_B200_MODEL_ROCKET2D) return discretize_hook<Rocket2d>(K, n, nsub, jacobian, device, X, U, sigma, par, A, B, C, s, z);
+    if (model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) return discretize_hook<Rocket2dPlugin>(K, n, nsub, jacobian, device, X, U, sigma, par, A, B, C, s, z);
     return fail(SCPP_B200_ERR_ARG, "unknown model");
 }
 int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const double *X, const double *U, const double *sigma, const double *par,
@@ -970,6 +1006,7 @@ int scpp_b200_simulate(int model, int n, double dt, int device, double *x, const
     if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");
     if (model == SCPP_B200_MODEL_ROCKETQUAT) return simulate_hook<RocketQuat>(n, dt, device, x, u0, u1, par);
     if (model == SCPP_B200_MODEL_ROCKET2D) return simulate_hook<Rocket2d>(n, dt, device, x, u0, u1, par);
+    if (model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) return simulate_hook<Rocket2dPlugin>(n, dt, device, x, u0, u1, par);
     return fail(SCPP_B200_ERR_ARG, "unknown model");
 }
 

@@ -819,7 +819,7 @@ struct Ipm {
     // Device: lane i keeps row i of H in registers; column j is scaled by rsqrt of the pivot (broadcast by shuffle) and the
     // trailing update takes L[c][j] from lane c by shuffle, fully unrolled (153 DFMA).  L goes back to the window, then lane c
     // forward-substitutes column c of the inverse with uniform (broadcast) reads of L.  Host: the same arithmetic as plain loops.
-    SCPP_HD bool chol_inv(double *H, double *Li)
+    SCPP_HD_CHOL bool chol_inv(double *H, double *Li)
     {
 #if defined(__CUDA_ARCH__)
         const int lane = lane_id();
@@ -1269,7 +1269,7 @@ struct Ipm {
         return -csig * i2 - sqrt(1. / dv) * ((-i0 * i0 - i1 + sigmu) / i0);
     }
 
-    SCPP_HD double pass_rhs(int mode, double csig, double sigmu, bool split = false)   // returns the lane-partial of the sigma right-hand side
+    SCPP_HD_PASS double pass_rhs(int mode, double csig, double sigmu, bool split = false)   // returns the lane-partial of the sigma right-hand side
     {
         double gsig = 0;
         FOR_STAGE(k) {
@@ -1542,7 +1542,7 @@ struct Ipm {
         ld_wait();
     }
 
-    SCPP_HD double pass_recover(int mode, double csig, double rzs, double ysig)   // returns the lane-partial of tmax
+    SCPP_HD_PASS double pass_recover(int mode, double csig, double rzs, double ysig)   // returns the lane-partial of tmax
     {
         double tmax = 0;
         FOR_STAGE(k) {

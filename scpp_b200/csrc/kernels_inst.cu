@@ -1,13 +1,15 @@
 // scpp_b200/csrc/kernels_inst.cu — explicit instantiation of one group of kernels per translation unit.
-// Compile with -DSCPP_KERNEL_MODEL=0|1 (RocketQuat | Rocket2d) and -DSCPP_KERNEL_GROUP=0..4 (scpp_b200/build.py runs them in parallel).
+// Compile with -DSCPP_KERNEL_MODEL=0|1|2 (RocketQuat | Rocket2d | Rocket2dPlugin) and -DSCPP_KERNEL_GROUP=0..4 (scpp_b200/build.py runs them in parallel).
 #define SCPP_KERNEL_INST 1
 #include "kernels.cuh"
 
 namespace scpp {
 #if SCPP_KERNEL_MODEL == 0
 #define SCPP_M RocketQuat
-#else
+#elif SCPP_KERNEL_MODEL == 1
 #define SCPP_M Rocket2d
+#else
+#define SCPP_M Rocket2dPlugin
 #endif
 #if SCPP_KERNEL_GROUP == 0
 SCPP_GROUP0(, SCPP_M)

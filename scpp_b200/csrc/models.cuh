@@ -419,6 +419,11 @@ struct Rocket2d {
     }
 };
 
+} // namespace scpp
+// a model written only against the plugin surface (flow map + cvx:: constraints): Jacobians by dual numbers, tables generated at build time
+#include "../plugins/rocket2d_plugin.hpp"
+namespace scpp {
+
 static const RowDesc rq_rows_host[RocketQuat::NLP + RocketQuat::NCR] = SCPP_RQ_ROWS;
 static const RowDesc r2d_rows_host[Rocket2d::NLP + Rocket2d::NCR] = SCPP_R2D_ROWS;
 #if defined(__CUDACC__)
@@ -441,5 +446,19 @@ SCPP_HD RowDesc Rocket2d::row(int r)
     return r2d_rows_host[r];
 #endif
 }
+#if !defined(SCPP_PLUGIN_GENERATE)
+static const RowDesc r2dp_rows_host[Rocket2dPlugin::NLP + Rocket2dPlugin::NCR] = ROCKET2D_PLUGIN_ROWS;
+#if defined(__CUDACC__)
+static __constant__ RowDesc r2dp_rows_dev[Rocket2dPlugin::NLP + Rocket2dPlugin::NCR] = ROCKET2D_PLUGIN_ROWS;
+#endif
+SCPP_HD RowDesc Rocket2dPlugin::row(int r)
+{
+#if defined(__CUDA_ARCH__)
+    return r2dp_rows_dev[r];
+#else
+    return r2dp_rows_host[r];
+#endif
+}
+#endif
 
 } // namespace scpp

@@ -352,6 +352,7 @@ int scpp_b200_mpc_create(int model, const scpp_b200_model_params *params, const 
     if (scpp_b200_device_count() <= 0) return scpp_b200_fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");
     scpp_b200_mpc *e = nullptr;
     if (model == SCPP_B200_MODEL_ROCKET2D) e = new MpcEngineT<Rocket2d>();
+    else if (model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) e = new MpcEngineT<Rocket2dPlugin>();
     else if (model == SCPP_B200_MODEL_ROCKETQUAT) return scpp_b200_fail(SCPP_B200_ERR_UNSUPPORTED, "RocketQuat has no operating point (getOperatingPoint is not overridden in the reference: it throws)");
     else return scpp_b200_fail(SCPP_B200_ERR_ARG, "unknown model");
     e->model = model; e->N = n; e->device = device;

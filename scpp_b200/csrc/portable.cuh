@@ -11,9 +11,11 @@
 #if defined(__CUDACC__)
 #define SCPP_HD __host__ __device__ __forceinline__
 #define SCPP_D __device__ __forceinline__
+#define SCPP_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define SCPP_HD inline
 #define SCPP_D inline
+#define SCPP_HD_NOINLINE inline
 #endif
 
 namespace scpp {
@@ -63,6 +65,17 @@ inline double warp_bcast(double v, int) { return v; }
 #endif
 
 // lanes stride over [0,n)
+// code-size experiments (build variants, scpp_b200/build.py --variant): out-of-line Cholesky / stage passes
+#if defined(SCPP_NOINLINE_CHOL)
+#define SCPP_HD_CHOL SCPP_HD_NOINLINE
+#else
+#define SCPP_HD_CHOL SCPP_HD
+#endif
+#if defined(SCPP_NOINLINE_PASS)
+#define SCPP_HD_PASS SCPP_HD_NOINLINE
+#else
+#define SCPP_HD_PASS SCPP_HD
+#endif
 #define FOR_LANE(i, n) for (int i = lane_id(); i < (n); i += LANES)
 
 // ---- CTA-wide cooperation (the CTA-per-instance solver, cta_ipm.cuh); the host-simulation build is one thread ----

@@ -93,7 +93,7 @@ def scvx_config(ov, final_time_free=False, nsub=20, tol=1e-8, maxit=100, history
     return c
 
 
-DIMS = {0: (14, 4), 1: (6, 2)}
+DIMS = {0: (14, 4), 1: (6, 2), 2: (6, 2)}      # 2: Rocket2dPlugin
 
 
 def sc_solve(model, P, cfg, x_init, x_final):

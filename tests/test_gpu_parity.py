@@ -771,3 +771,29 @@ def test_mpc_vs_oracle(S):
         mpc.close()
     with pytest.raises(S.ScppError):
         S.MPCAlgorithm(S.ROCKETQUAT, S.load_model("RocketQuat")[1], cfg, 1)          # no operating point: the reference throws too
+
+
+def test_plugin_surface_model_vs_oracle(S):
+    """a model added with NO hand-written Jacobian and NO hand-written row table (SCPP_B200_MODEL_ROCKET2D_PLUGIN: the planar
+    rocket written against systemFlowMap / getInitializedTrajectory / addApplicationConstraints only, scpp_b200/plugins/rocket2d_plugin.hpp)
+    on the device through the C-ABI against the oracle's Rocket2D: a batch of different initial states, every iterate, same decisions; K1
+    with its dual-number Jacobians against the RKF78 oracle; SCvx and the closed loop run on it too"""
+    d2r = np.pi / 180
+    plist = []
+    for i, (rx, ry, vy, eta) in enumerate([(-200, 800, -100, -20), (150, 700, -80, 10), (-50, 900, -120, 25), (300, 600, -60, -15), (0, 500, -90, 5)]):
+        p = O.rocket2d(); p.x_init[:] = [rx, ry, 0, vy, eta * d2r, 0]
+        plist.append(p)
+    rep = _compare_run(S, "Rocket2DPlugin", O.ROCKET2D, plist, K=30, max_it=15)
+    assert len(rep) >= 15
+    _compare_run(S, "Rocket2DPlugin", O.ROCKET2D, plist[:2], K=30, max_it=15, warm=0.995, cfg_over=dict(solver=1))      # CTA-per-instance solver
+    # K1 alone on the plugin model (dual numbers only: it has no hand-derived Jacobian) against the oracle's RKF78 discretisation
+    p2 = O.rocket2d()
+    pn2 = O.R2DParams.from_buffer_copy(p2); O.lib().orc_r2d_nondimensionalize(C.byref(pn2))
+    par2 = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(pn2), par2.ctypes.data_as(C.c_void_p))
+    ro = O.sc_solve(O.ROCKET2D, p2, O.sc_config(K=30, model=O.ROCKET2D, max_iterations=2))
+    X, U, t = ro["X_all"][2], ro["U_all"][2], ro["t_all"][2]
+    a = S.discretize(S.ROCKET2D_PLUGIN, X, U, t, par2, nsub=-5, jacobian=1); b = S.discretize(S.ROCKET2D_PLUGIN, X, U, t, par2, nsub=-5, jacobian=0)
+    ref = O.discretize(O.ROCKET2D, X, U, t, par2)
+    for key in ("A", "B", "C", "s", "z"):
+        assert np.abs(a[key][0] - ref[key]).max() <= 2e-9 * max(1.0, np.abs(ref[key]).max()), key
+        assert np.abs(a[key] - b[key]).max() <= 1e-13 * max(1.0, np.abs(b[key]).max()), key       # AutoJacobian (dense, duals) == the dual-number products

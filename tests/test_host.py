@@ -434,3 +434,59 @@ def test_mpc_info_loader(S):
     assert list(c.state_weights_terminal)[:6] == [5., 5., 5., 1., 1., 1.] and np.allclose(list(c.input_weights)[:2], [0.1, 0.1])
     with pytest.raises(S.ScppError):
         S.load_mpc_info(os.path.join(S.CONFIG_DIR, "Rocket2D", "SC.info"), S.ROCKET2D)
+
+
+def test_cvx_shim_lowers_the_reference_constraints(S, tmp_path):
+    """include/scpp_cvx.hpp (recording shim of the reference's constraint DSL) + include/scpp_plugin.hpp (lowering to stage-wise tables):
+    RocketQuat's and Rocket2d's addApplicationConstraints written call by call as in rocketQuat.cpp:70-144 / rocket2d.cpp:46-84 lower to
+    exactly the tables the engine uses (scpp_b200_model_rows through the C-ABI), the pinned variables included; the problem-builder subset
+    (SCProblem.cpp:16-134) records and evaluates (tests/cvx_shim_test.cpp)"""
+    import subprocess
+    exe = str(tmp_path / "cvx_shim_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cvx_shim_test.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "scpp_b200"), "-lscpp_b200", "-Wl,-rpath," + os.path.join(ROOT, "scpp_b200")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
+
+
+def test_generated_plugin_table_is_current(tmp_path):
+    """scpp_b200/csrc/gen/rocket2d_plugin.inc is what tools/gen_plugin.cpp produces from scpp_b200/plugins/rocket2d_plugin.hpp today"""
+    import subprocess
+    exe = str(tmp_path / "gen_plugin")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "gen_plugin.cpp"), "-o", exe])
+    subprocess.check_call([exe, str(tmp_path)])
+    new = open(tmp_path / "rocket2d_plugin.inc").read(); old = open(os.path.join(ROOT, "scpp_b200", "csrc", "gen", "rocket2d_plugin.inc")).read()
+    assert new == old
+
+
+def test_plugin_surface_model_source_vs_oracle(S):
+    """a model written ONLY against the plugin surface (scpp_b200/plugins/rocket2d_plugin.hpp: generic-scalar flow map + constraints in the
+    cvx:: DSL; Jacobians by dual numbers, row table / pins / constant slots generated at build time) through the kernel source on the host:
+    same iteration count and convergence as the oracle's Rocket2D, iterates to 1e-5 / 1e-4; equal to the hand-written Rocket2d traits to
+    solver accuracy; its dual-number Jacobian equals the hand-derived one; the engine reports the generated table through the C-ABI"""
+    p = O.rocket2d()
+    ocfg = O.sc_config(K=30, model=1, max_iterations=15)
+    P, xi, xf = H.params_from_oracle(1, p)
+    ro = O.sc_solve(O.ROCKET2D, p, ocfg)
+    res = {}
+    for model in (1, 2):
+        r = H.sc_solve(model, P, H.sc_config(ocfg, nsub=-5, tol=1e-8), xi, xf)
+        n = int(r["iters"][0])
+        assert n == abs(ro["iterations"]) and bool(r["converged"][0]) == ro["converged"]
+        for it in range(n + 1):
+            assert np.abs(r["X_all"][0, it] - ro["X_all"][it]).max() < 1e-5 and np.abs(r["U_all"][0, it] - ro["U_all"][it]).max() < 1e-4, (model, it)
+        res[model] = r
+    assert np.abs(res[1]["X_all"] - res[2]["X_all"]).max() < 1e-6 and np.abs(res[1]["U_all"] - res[2]["U_all"]).max() < 1e-6
+    # Jacobians: AutoJacobian (duals over the plugin's flow map) == Rocket2d's hand-derived Lin
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(6); u = np.array([0.1, 0.7]); par = np.array([1.0, 0.3, 0.0, -0.01, 0.0, -0.02])
+    f = np.zeros(6); A_ad = np.zeros((6, 6)); B_ad = np.zeros((6, 2)); A1 = np.zeros((6, 6)); B1 = np.zeros((6, 2)); A2 = np.zeros((6, 6)); B2 = np.zeros((6, 2))
+    pp = lambda a: a.ctypes.data_as(C.c_void_p)
+    H.lib().hs_jacobians(1, pp(x), pp(u), pp(par), pp(f), pp(A_ad), pp(B_ad), pp(A1), pp(B1))
+    H.lib().hs_jacobians(2, pp(x), pp(u), pp(par), pp(f), pp(A_ad), pp(B_ad), pp(A2), pp(B2))
+    assert np.abs(A1 - A2).max() < 1e-14 and np.abs(B1 - B2).max() < 1e-14 and np.abs(A2 - A_ad).max() < 1e-14
+    # the table in use, through the C-ABI: 8 LP rows (4 boxes) and the glide-slope cone, numerically equal to the hand-written model's
+    model, params, x_init, x_final, _ = S.load_model("Rocket2D")
+    lp_a, cones_a = S.model_rows(S.ROCKET2D, params, x_init, x_final); lp_b, cones_b = S.model_rows(S.ROCKET2D_PLUGIN, params, x_init, x_final)
+    key = lambda r: (sorted(r[0].items()), r[1])
+    assert sorted(map(key, lp_a)) == sorted(map(key, lp_b)) and [list(map(key, c)) for c in cones_a] == [list(map(key, c)) for c in cones_b]

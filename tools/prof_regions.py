@@ -61,16 +61,16 @@ for r in rows[2:]:
     fr = amap.get(a - base, [])
     reg = region(fr)
     for n, c in cols.items(): agg[reg][n] += int(r[c] or 0)
-    agg[reg]['all'] += int(r[ism] or 0); agg[reg]['ex'] += int(r[iex] or 0)
+    agg[reg]['all'] += int(r[ism] or 0); agg[reg]['ex'] += int(r[iex] or 0); agg[reg]['static'] += 1
     op = r[isrc].split()[1] if r[isrc].strip().startswith('@') else r[isrc].split()[0]
     if op.startswith('LDL') or op.startswith('STL'): agg[reg]['local'] += int(r[iex] or 0)
     inner = next(((f, n) for f, n in fr if f == fname), None)
     if inner: line_s[inner[1]] += int(r[ism] or 0)
 T = sum(v['all'] for v in agg.values()); E = sum(v['ex'] for v in agg.values())
 print(f"total samples {T}, warp instructions {E}")
-print(f"{'region':20s} smp%  ex%  long wait short sel  br noinst lg mio  local-ex%")
+print(f"{'region':20s} smp%  ex%  long wait short sel  br noinst lg mio  local-ex%  code KB (static SASS x 16 B)")
 for k, v in sorted(agg.items(), key=lambda t: -t[1]['all'])[:16]:
     a = v['all'] or 1
-    print(f"{k:20s} {100*a/T:5.1f} {100*v['ex']/E:5.1f} " + ' '.join(f"{100*v[c]/a:4.0f}" for c in cols) + f"  {100*v['local']/max(1,v['ex']):5.1f}")
+    print(f"{k:20s} {100*a/T:5.1f} {100*v['ex']/E:5.1f} " + ' '.join(f"{100*v[c]/a:4.0f}" for c in cols) + f"  {100*v['local']/max(1,v['ex']):5.1f}  {v['static']*16/1024:7.1f}")
 print("top lines:")
 for n, c in line_s.most_common(14): print(f"  {n:5d} {100*c/T:5.1f}  {src[n-1].strip()[:110]}")
