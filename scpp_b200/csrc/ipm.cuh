@@ -2025,8 +2025,9 @@ struct Ipm {
             }
             past_test = false;
             budget--;
-            bool factored = phase_factor();
-            while (!factored && tighten_cap()) factored = phase_factor();        // numerically indefinite: regularise (see dcap) and repeat
+            bool factored;                                                       // ONE call site: the factorisation is inlined once (code size)
+#pragma unroll 1
+            do { factored = phase_factor(); } while (!factored && tighten_cap());        // numerically indefinite: regularise (see dcap) and repeat
             if (!factored) { res.status = 2; break; }
             double tmax;
             phase_solve(1, 1., 0., -1., tmax);                               // affine direction

@@ -14,8 +14,12 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group(backend="gloo")
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-over = dict(weight_trust_region_trajectory=2.0, weight_virtual_control=1e4, nu_tol=1e-3, delta_tol=1e-2)
-model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50, max_iterations=20, **over)
+algorithm = sys.argv[2] if len(sys.argv) > 2 else "SC"      # "SCvx": BASELINE.json configs[2] (free-final-time SCvx, K = 50, sharded), shipped SCvx.info
+if algorithm == "SCvx":
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50, algorithm="SCvx")
+else:
+    over = dict(weight_trust_region_trajectory=2.0, weight_virtual_control=1e4, nu_tol=1e-3, delta_tol=1e-2)
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50, max_iterations=20, **over)
 cfg.ipm.warm = 0.995
 xi_all = S.perturbed_initial_states(x_init, np.deg2rad([-20.0, 20.0, 0.0]), N)
 w = np.arange(1, world + 1, dtype=float); cuts = np.concatenate([[0], np.round(np.cumsum(w) / w.sum() * N).astype(int)])
