@@ -34,6 +34,9 @@ extern "C" {
  * Jacobians by forward-mode dual numbers; the constraint table is generated at build time from the recorded constraints
  * (include/scpp_plugin.hpp, tools/gen_plugin.cpp, scpp_b200/plugins/rocket2d_plugin.hpp).  Needs constrain_initial_final = true. */
 #define SCPP_B200_MODEL_ROCKET2D_PLUGIN 2
+/* RocketQuat written the same way WITH roll control (enable_roll_control = true, rocketQuat.cpp:135-138: |roll torque| <= t_max, w_z and the
+ * torque free): scpp_b200/plugins/rocketquat_plugin.hpp.  Requires params.enable_roll_control = 1; models 0 requires it to be 0. */
+#define SCPP_B200_MODEL_ROCKETQUAT_ROLL 3
 
 /* RocketQuat::Parameters (scpp_models/include/rocketQuat.hpp:50-85) and Rocket2d::Parameters
  * (scpp_models/include/rocket2d.hpp:51-84) as loaded from model.info; angles in radians.

@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCPP_B200_LIB", os.path.join(_HERE, "libscpp_b200.so"))   # the override is for A/B experiments with kernel variants
 CONFIG_DIR = os.path.join(os.path.dirname(_HERE), "configs")
 
-ROCKETQUAT, ROCKET2D, ROCKET2D_PLUGIN = 0, 1, 2      # 2: Rocket2D written only against the plugin surface (scpp_b200/plugins/rocket2d_plugin.hpp)
-MODEL_NAMES = {ROCKETQUAT: "RocketQuat", ROCKET2D: "Rocket2D", ROCKET2D_PLUGIN: "Rocket2D"}
+ROCKETQUAT, ROCKET2D, ROCKET2D_PLUGIN, ROCKETQUAT_ROLL = 0, 1, 2, 3      # 2, 3: models written only against the plugin surface (scpp_b200/plugins/)
+MODEL_NAMES = {ROCKETQUAT: "RocketQuat", ROCKET2D: "Rocket2D", ROCKET2D_PLUGIN: "Rocket2D", ROCKETQUAT_ROLL: "RocketQuatRoll"}
 INFO_STRIDE = 10
 INFO_FIELDS = ("norm1_nu", "sum_delta", "delta_sigma", "sigma", "weight_tr_used", "ipm_iterations", "ipm_status", "pres", "dres", "relgap")
 
@@ -135,8 +135,8 @@ def model_rows(model, params, x_init, x_final):
 def load_model(name, K=None, algorithm="SC", **overrides):
     """convenience: configs/<name>/{model,SC|SCvx}.info -> (model id, ModelParams, x_init, x_final, SCConfig); name "Rocket2DPlugin" = the
     Rocket2D files with the plugin-surface model"""
-    model = ROCKET2D_PLUGIN if name == "Rocket2DPlugin" else (ROCKET2D if name == "Rocket2D" else ROCKETQUAT)
-    name = MODEL_NAMES[model] if model == ROCKET2D_PLUGIN else name
+    model = {"Rocket2DPlugin": ROCKET2D_PLUGIN, "Rocket2D": ROCKET2D, "RocketQuatRoll": ROCKETQUAT_ROLL}.get(name, ROCKETQUAT)
+    name = MODEL_NAMES[model] if model in (ROCKET2D_PLUGIN, ROCKETQUAT_ROLL) else name
     folder = os.path.join(CONFIG_DIR, name)
     p, xi, xf = load_model_info(os.path.join(folder, "model.info"), model)
     cfg = load_scvx_info(os.path.join(folder, "SCvx.info"), model) if algorithm == "SCvx" else load_sc_info(os.path.join(folder, "SC.info"), model)

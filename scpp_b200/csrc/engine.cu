@@ -676,7 +676,7 @@ struct EngineT : scpp_b200_engine {
     {
         CU(cudaSetDevice(device));
         if (!Pn) { a.Pn = nullptr; return 0; }
-        for (int n = 0; n < N; n++) if (Pn[n].enable_roll_control) return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control = true is not built into this engine");
+        for (int n = 0; n < N; n++) if ((Pn[n].enable_roll_control != 0) != (model == SCPP_B200_MODEL_ROCKETQUAT_ROLL)) return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control: use model SCPP_B200_MODEL_ROCKETQUAT_ROLL for true, SCPP_B200_MODEL_ROCKETQUAT for false");
         if (!d_Pn) { int rc; if ((rc = dalloc(&d_Pn, (size_t)N))) return rc; }
         CU(cudaMemcpyAsync(d_Pn, Pn, (size_t)N * sizeof(ModelParamsHost), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));
@@ -728,7 +728,7 @@ int scpp_b200_device_count(void)
 }
 int scpp_b200_model_dims(int model, int *nx, int *nu, int *np)
 {
-    if (model == SCPP_B200_MODEL_ROCKETQUAT) { *nx = RocketQuat::NX; *nu = RocketQuat::NU; *np = RocketQuat::NP; return 0; }
+    if (model == SCPP_B200_MODEL_ROCKETQUAT || model == SCPP_B200_MODEL_ROCKETQUAT_ROLL) { *nx = RocketQuat::NX; *nu = RocketQuat::NU; *np = RocketQuat::NP; return 0; }
     if (model == SCPP_B200_MODEL_ROCKET2D || model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) { *nx = Rocket2d::NX; *nu = Rocket2d::NU; *np = Rocket2d::NP; return 0; }
     return fail(SCPP_B200_ERR_ARG, "unknown model");
 }
@@ -761,6 +761,7 @@ int scpp_b200_model_rows(int model, const scpp_b200_model_params *params, const 
     if (model == SCPP_B200_MODEL_ROCKETQUAT) return model_rows_t<RocketQuat>(P, x_init, x_final, max_rows, rows, n_lp, n_cones, cone_dims);
     if (model == SCPP_B200_MODEL_ROCKET2D) return model_rows_t<Rocket2d>(P, x_init, x_final, max_rows, rows, n_lp, n_cones, cone_dims);
     if (model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) return model_rows_t<Rocket2dPlugin>(P, x_init, x_final, max_rows, rows, n_lp, n_cones, cone_dims);
+    if (model == SCPP_B200_MODEL_ROCKETQUAT_ROLL) return model_rows_t<RocketQuatRollPlugin>(P, x_init, x_final, max_rows, rows, n_lp, n_cones, cone_dims);
     return fail(SCPP_B200_ERR_ARG, "unknown model");
 }
 // scpp_models/config/RocketQuat/SC.info:1-16, scpp_models/config/Rocket2D/SC.info:1-16
@@ -768,16 +769,17 @@ void scpp_b200_default_config(int model, scpp_b200_sc_config *c)
 {
     memset(c, 0, sizeof(*c));
     c->free_final_time = 1; c->interpolate_input = 1; c->nondimensionalize = 1;
-    c->K = model == SCPP_B200_MODEL_ROCKETQUAT ? 15 : 25;
+    const bool rq = model == SCPP_B200_MODEL_ROCKETQUAT || model == SCPP_B200_MODEL_ROCKETQUAT_ROLL;
+    c->K = rq ? 15 : 25;
     c->weight_time = 1.; c->weight_trust_region_time = 1.;
-    c->weight_trust_region_trajectory = model == SCPP_B200_MODEL_ROCKETQUAT ? 50. : 1.;
+    c->weight_trust_region_trajectory = rq ? 50. : 1.;
     c->weight_virtual_control = 1000.;
     c->nu_tol = 1e-5; c->delta_tol = 1e-3; c->max_iterations = 15;
     c->nsub = -5; c->keep_history = 0; c->ipm_slice = 1;   // RK4 x 5 and x 10, Richardson-extrapolated: the accuracy of RK4 x 20 for 3/4 of the work
     c->ipm.feastol = 1e-8; c->ipm.abstol = 1e-8; c->ipm.reltol = 1e-8; c->ipm.maxit = 100;
     c->algorithm = 0;   // SCvx.info values, used when algorithm is set to 1
     c->scvx_rho_0 = 0.; c->scvx_rho_1 = 0.25; c->scvx_rho_2 = 0.9; c->scvx_alpha = 2.; c->scvx_beta = 3.2;
-    c->scvx_change_threshold = model == SCPP_B200_MODEL_ROCKETQUAT ? 1e-3 : 1e-2; c->scvx_trust_region = 5.;
+    c->scvx_change_threshold = rq ? 1e-3 : 1e-2; c->scvx_trust_region = 5.;
     c->jacobian = 1;
 }
 
@@ -802,7 +804,7 @@ int scpp_b200_load_model_info(const char *path, int model, scpp_b200_model_param
     try {
         ParameterServer ps(path);
         memset(p, 0, sizeof(*p));
-        if (model == SCPP_B200_MODEL_ROCKETQUAT) {   // rocketQuat.cpp:234-289
+        if (model == SCPP_B200_MODEL_ROCKETQUAT || model == SCPP_B200_MODEL_ROCKETQUAT_ROLL) {   // rocketQuat.cpp:234-289
             bool random_initial_state, exact, roll;
             double I_sp, m_init, m_dry, r_init[3], v_init[3], rpy_init[3], w_init[3], r_final[3], v_final[3], rpy_final[3], w_final[3];
             ps.loadMatrix("g_I", p->g_I, 3); ps.loadMatrix("J_B", p->J_B, 3); ps.loadMatrix("r_T_B", p->r_T_B, 3);
@@ -830,7 +832,7 @@ int scpp_b200_load_model_info(const char *path, int model, scpp_b200_model_param
             // random_initial_state: randomizeInitialState() is commented out in the reference (rocketQuat.cpp:203-227); batches are
             // perturbed by the caller instead
             (void)random_initial_state;
-            if (roll) return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control = true is not built into this engine");
+            if (roll != (model == SCPP_B200_MODEL_ROCKETQUAT_ROLL)) return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control: use model SCPP_B200_MODEL_ROCKETQUAT_ROLL for true, SCPP_B200_MODEL_ROCKETQUAT for false");
         } else if (model == SCPP_B200_MODEL_ROCKET2D || model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) {   // rocket2d.cpp:150-196
             bool cif, slack;
             double r_init[2], v_init[2], r_final[2], v_final[2], w_init, w_final, eta_init, eta_final;
@@ -899,7 +901,8 @@ int scpp_b200_create(int model, const scpp_b200_model_params *params, const scpp
     if (cfg->K < 3 || cfg->max_iterations < 1 || cfg->nsub == 0) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: K >= 3, max_iterations >= 1, nsub != 0 required");
     if (!cfg->free_final_time || !cfg->interpolate_input)
         return fail(SCPP_B200_ERR_UNSUPPORTED, "only free_final_time = true, interpolate_input = true (the shipped SC.info settings) are built");
-    if (params->enable_roll_control) return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control = true is not built into this engine");
+    if ((params->enable_roll_control != 0) != (model == SCPP_B200_MODEL_ROCKETQUAT_ROLL))
+        return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control: use model SCPP_B200_MODEL_ROCKETQUAT_ROLL for true, SCPP_B200_MODEL_ROCKETQUAT for false");
     if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");
     scpp_b200_engine *e = nullptr;
     if (model == SCPP_B200_MODEL_ROCKETQUAT) e = new EngineT<RocketQuat>();
@@ -908,6 +911,7 @@ int scpp_b200_create(int model, const scpp_b200_model_params *params, const scpp
         if (!params->constrain_initial_final) return fail(SCPP_B200_ERR_UNSUPPORTED, "the plugin model's table was generated with constrain_initial_final = true");
         e = new EngineT<Rocket2dPlugin>();
     }
+    else if (model == SCPP_B200_MODEL_ROCKETQUAT_ROLL) e = new EngineT<RocketQuatRollPlugin>();
     else return fail(SCPP_B200_ERR_ARG, "unknown model");
     e->model = model; e->N = n; e->device = device;
     memcpy(&e->P, params, sizeof(ModelParamsHost));
@@ -983,6 +987,7 @@ int scpp_b200_discretize2(int model, int K, int n, int nsub, int jacobian, int d
     if (model == SCPP_B200_MODEL_ROCKETQUAT) return discretize_hook<RocketQuat>(K, n, nsub, jacobian, device, X, U, sigma, par, A, B, C, s, z);
     if (model == SCPP_B200_MODEL_ROCKET2D) return discretize_hook<Rocket2d>(K, n, nsub, jacobian, device, X, U, sigma, par, A, B, C, s, z);
     if (model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) return discretize_hook<Rocket2dPlugin>(K, n, nsub, jacobian, device, X, U, sigma, par, A, B, C, s, z);
+    if (model == SCPP_B200_MODEL_ROCKETQUAT_ROLL) return discretize_hook<RocketQuatRollPlugin>(K, n, nsub, jacobian, device, X, U, sigma, par, A, B, C, s, z);
     return fail(SCPP_B200_ERR_ARG, "unknown model");
 }
 int scpp_b200_discretize(int model, int K, int n, int nsub, int device, const double *X, const double *U, const double *sigma, const double *par,
@@ -1007,6 +1012,7 @@ int scpp_b200_simulate(int model, int n, double dt, int device, double *x, const
     if (model == SCPP_B200_MODEL_ROCKETQUAT) return simulate_hook<RocketQuat>(n, dt, device, x, u0, u1, par);
     if (model == SCPP_B200_MODEL_ROCKET2D) return simulate_hook<Rocket2d>(n, dt, device, x, u0, u1, par);
     if (model == SCPP_B200_MODEL_ROCKET2D_PLUGIN) return simulate_hook<Rocket2dPlugin>(n, dt, device, x, u0, u1, par);
+    if (model == SCPP_B200_MODEL_ROCKETQUAT_ROLL) return simulate_hook<RocketQuatRollPlugin>(n, dt, device, x, u0, u1, par);
     return fail(SCPP_B200_ERR_ARG, "unknown model");
 }
 

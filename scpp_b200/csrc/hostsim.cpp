@@ -24,6 +24,7 @@ extern "C" void hs_discretize2(int model, int K, const double *X, const double *
 {
     if (model == 0) run_discretize<RocketQuat>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian);
     else if (model == 2) run_discretize<Rocket2dPlugin>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian);
+    else if (model == 3) run_discretize<RocketQuatRollPlugin>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian);
     else run_discretize<Rocket2d>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian);
 }
 
@@ -148,6 +149,7 @@ extern "C" int hs_sc_solve(int model, const ModelParamsHost *P, const ScConfig *
 {
     if (model == 0) return run_sc<RocketQuat>(P, cfg, N, x_init, x_final, X, U, sigma, iters, status, converged, hist, info);
     if (model == 2) return run_sc<Rocket2dPlugin>(P, cfg, N, x_init, x_final, X, U, sigma, iters, status, converged, hist, info);
+    if (model == 3) return run_sc<RocketQuatRollPlugin>(P, cfg, N, x_init, x_final, X, U, sigma, iters, status, converged, hist, info);
     return run_sc<Rocket2d>(P, cfg, N, x_init, x_final, X, U, sigma, iters, status, converged, hist, info);
 }
 
@@ -215,7 +217,7 @@ static void run_jac(const double *x, const double *u, const double *par, double 
 }
 extern "C" void hs_jacobians(int model, const double *x, const double *u, const double *par, double *f, double *A_ad, double *B_ad, double *A_lin, double *B_lin)
 {
-    if (model == 0) run_jac<RocketQuat>(x, u, par, f, A_ad, B_ad, A_lin, B_lin); else if (model == 2) run_jac<Rocket2dPlugin>(x, u, par, f, A_ad, B_ad, A_lin, B_lin); else run_jac<Rocket2d>(x, u, par, f, A_ad, B_ad, A_lin, B_lin);
+    if (model == 0) run_jac<RocketQuat>(x, u, par, f, A_ad, B_ad, A_lin, B_lin); else if (model == 2) run_jac<Rocket2dPlugin>(x, u, par, f, A_ad, B_ad, A_lin, B_lin); else if (model == 3) run_jac<RocketQuatRollPlugin>(x, u, par, f, A_ad, B_ad, A_lin, B_lin); else run_jac<Rocket2d>(x, u, par, f, A_ad, B_ad, A_lin, B_lin);
 }
 
 // K5 body on the host: gains [K][nu][nx], ok [K]

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(128, 3) k_sp_stage(ScArrays<M> a, ScConfig cfg
 SCPP_ALL_GROUPS(extern, RocketQuat)
 SCPP_ALL_GROUPS(extern, Rocket2d)
 SCPP_ALL_GROUPS(extern, Rocket2dPlugin)
+SCPP_ALL_GROUPS(extern, RocketQuatRollPlugin)
 #endif
 
 } // namespace scpp

@@ -1,5 +1,5 @@
 // scpp_b200/csrc/kernels_inst.cu — explicit instantiation of one group of kernels per translation unit.
-// Compile with -DSCPP_KERNEL_MODEL=0|1|2 (RocketQuat | Rocket2d | Rocket2dPlugin) and -DSCPP_KERNEL_GROUP=0..4 (scpp_b200/build.py runs them in parallel).
+// Compile with -DSCPP_KERNEL_MODEL=0|1|2|3 (RocketQuat | Rocket2d | Rocket2dPlugin | RocketQuatRollPlugin) and -DSCPP_KERNEL_GROUP=0..4 (scpp_b200/build.py runs them in parallel).
 #define SCPP_KERNEL_INST 1
 #include "kernels.cuh"
 
@@ -8,8 +8,10 @@ namespace scpp {
 #define SCPP_M RocketQuat
 #elif SCPP_KERNEL_MODEL == 1
 #define SCPP_M Rocket2d
-#else
+#elif SCPP_KERNEL_MODEL == 2
 #define SCPP_M Rocket2dPlugin
+#else
+#define SCPP_M RocketQuatRollPlugin
 #endif
 #if SCPP_KERNEL_GROUP == 0
 SCPP_GROUP0(, SCPP_M)

@@ -422,6 +422,7 @@ struct Rocket2d {
 } // namespace scpp
 // a model written only against the plugin surface (flow map + cvx:: constraints): Jacobians by dual numbers, tables generated at build time
 #include "../plugins/rocket2d_plugin.hpp"
+#include "../plugins/rocketquat_plugin.hpp"
 namespace scpp {
 
 static const RowDesc rq_rows_host[RocketQuat::NLP + RocketQuat::NCR] = SCPP_RQ_ROWS;
@@ -457,6 +458,18 @@ SCPP_HD RowDesc Rocket2dPlugin::row(int r)
     return r2dp_rows_dev[r];
 #else
     return r2dp_rows_host[r];
+#endif
+}
+static const RowDesc rqrp_rows_host[RocketQuatRollPlugin::NLP + RocketQuatRollPlugin::NCR] = ROCKETQUAT_ROLL_PLUGIN_ROWS;
+#if defined(__CUDACC__)
+static __constant__ RowDesc rqrp_rows_dev[RocketQuatRollPlugin::NLP + RocketQuatRollPlugin::NCR] = ROCKETQUAT_ROLL_PLUGIN_ROWS;
+#endif
+SCPP_HD RowDesc RocketQuatRollPlugin::row(int r)
+{
+#if defined(__CUDA_ARCH__)
+    return rqrp_rows_dev[r];
+#else
+    return rqrp_rows_host[r];
 #endif
 }
 #endif

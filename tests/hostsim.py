@@ -56,7 +56,7 @@ def lib():
 def params_from_oracle(model, p):
     """orc_py.RQParams / R2DParams -> (ModelParamsHost, x_init, x_final)"""
     P = ModelParamsHost()
-    if model == 0:
+    if model in (0, 3):
         P.g_I[:] = list(p.g_I); P.J_B[:] = list(p.J_B); P.r_T_B[:] = list(p.r_T_B)
         P.alpha_m = p.alpha_m; P.T_min = p.T_min; P.T_max = p.T_max; P.t_max = p.t_max
         P.gimbal_max = p.gimbal_max; P.theta_max = p.theta_max; P.gamma_gs = p.gamma_gs; P.w_B_max = p.w_B_max
@@ -93,7 +93,7 @@ def scvx_config(ov, final_time_free=False, nsub=20, tol=1e-8, maxit=100, history
     return c
 
 
-DIMS = {0: (14, 4), 1: (6, 2), 2: (6, 2)}      # 2: Rocket2dPlugin
+DIMS = {0: (14, 4), 1: (6, 2), 2: (6, 2), 3: (14, 4)}      # 2: Rocket2dPlugin, 3: RocketQuatRollPlugin
 
 
 def sc_solve(model, P, cfg, x_init, x_final):

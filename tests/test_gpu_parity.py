@@ -797,3 +797,23 @@ def test_plugin_surface_model_vs_oracle(S):
     for key in ("A", "B", "C", "s", "z"):
         assert np.abs(a[key][0] - ref[key]).max() <= 2e-9 * max(1.0, np.abs(ref[key]).max()), key
         assert np.abs(a[key] - b[key]).max() <= 1e-13 * max(1.0, np.abs(b[key]).max()), key       # AutoJacobian (dense, duals) == the dual-number products
+
+
+def test_rocketquat_roll_control_vs_oracle(S):
+    """RocketQuat with enable_roll_control = true (model id 3, written against the plugin surface only: scpp_b200/plugins/rocketquat_plugin.hpp)
+    on the device against the oracle's RocketQuat with enable_roll_control = 1: K = 50, a perturbed batch with initial roll rates, every
+    iterate to 1e-5 / 1e-4, same decisions; both K2 mappings"""
+    p, rpy = O.falcon9()
+    plist = []
+    for i in range(5):
+        q = O.rq_perturb(p, rpy, 0x5C99, 40 + i)
+        q.enable_roll_control = 1
+        q.x_init[13] = 0.01 * (i - 2)
+        plist.append(q)
+    over = dict()
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuatRoll", K=50, max_iterations=6, keep_history=1)
+    assert params.enable_roll_control == 1
+    _compare_run(S, "RocketQuatRoll", O.ROCKETQUAT, plist, K=50, max_it=6)
+    _compare_run(S, "RocketQuatRoll", O.ROCKETQUAT, plist[:3], K=50, max_it=6, warm=0.995, cfg_over=dict(solver=1))
+    with pytest.raises(S.ScppError):
+        S.SCAlgorithm(S.ROCKETQUAT, params, cfg, 1)             # the hand-written model refuses roll control and names model 3

@@ -450,13 +450,13 @@ def test_cvx_shim_lowers_the_reference_constraints(S, tmp_path):
 
 
 def test_generated_plugin_table_is_current(tmp_path):
-    """scpp_b200/csrc/gen/rocket2d_plugin.inc is what tools/gen_plugin.cpp produces from scpp_b200/plugins/rocket2d_plugin.hpp today"""
+    """scpp_b200/csrc/gen/*.inc are what tools/gen_plugin.cpp produces from scpp_b200/plugins/*.hpp today"""
     import subprocess
     exe = str(tmp_path / "gen_plugin")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "gen_plugin.cpp"), "-o", exe])
     subprocess.check_call([exe, str(tmp_path)])
-    new = open(tmp_path / "rocket2d_plugin.inc").read(); old = open(os.path.join(ROOT, "scpp_b200", "csrc", "gen", "rocket2d_plugin.inc")).read()
-    assert new == old
+    for f in ("rocket2d_plugin.inc", "rocketquat_roll_plugin.inc"):
+        assert open(tmp_path / f).read() == open(os.path.join(ROOT, "scpp_b200", "csrc", "gen", f)).read(), f
 
 
 def test_plugin_surface_model_source_vs_oracle(S):
@@ -490,3 +490,33 @@ def test_plugin_surface_model_source_vs_oracle(S):
     lp_a, cones_a = S.model_rows(S.ROCKET2D, params, x_init, x_final); lp_b, cones_b = S.model_rows(S.ROCKET2D_PLUGIN, params, x_init, x_final)
     key = lambda r: (sorted(r[0].items()), r[1])
     assert sorted(map(key, lp_a)) == sorted(map(key, lp_b)) and [list(map(key, c)) for c in cones_a] == [list(map(key, c)) for c in cones_b]
+
+
+def test_rocketquat_with_roll_control_through_the_plugin_surface(S):
+    """enable_roll_control = true (rocketQuat.cpp:135-138: |roll torque| <= t_max, w_z and the torque free) is built as a model written against
+    the plugin surface only (scpp_b200/plugins/rocketquat_plugin.hpp, model id 3: RocketQuat's flow map, dual-number Jacobians, generated
+    table with 4 LP rows): kernel source on the host against the oracle with enable_roll_control = 1, the torque really used; the
+    hand-written model refuses the setting and points at model 3"""
+    p, rpy = O.falcon9()
+    for inst in (None, 3):
+        q = p if inst is None else O.rq_perturb(p, rpy, 0x5C99, inst)
+        q.enable_roll_control = 1
+        q.x_init[13] = 0.02                       # an initial roll rate: the roll torque has something to do
+        ocfg = O.sc_config(K=20, max_iterations=5)
+        ro = O.sc_solve(O.ROCKETQUAT, q, ocfg)
+        P, xi, xf = H.params_from_oracle(3, q)
+        r = H.sc_solve(3, P, H.sc_config(ocfg, nsub=-5, tol=1e-8), xi, xf)
+        n = int(r["iters"][0])
+        assert n == abs(ro["iterations"]) == 5
+        for it in range(n + 1):
+            assert np.abs(r["X_all"][0, it] - ro["X_all"][it]).max() < 1e-5 and np.abs(r["U_all"][0, it] - ro["U_all"][it]).max() < 1e-4, (inst, it)
+        t_max = q.t_max / (q.x_init[0] * np.linalg.norm(q.x_init[1:4]) ** 2)
+        tq = r["U_all"][0, n, :, 3]
+        assert np.abs(tq).max() > 0.5 * t_max and np.abs(tq).max() <= t_max * (1 + 1e-6)          # active and inside its box
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuatRoll")
+    assert model == S.ROCKETQUAT_ROLL and params.enable_roll_control == 1
+    lp, cones = S.model_rows(model, params, x_init, x_final)
+    assert len(lp) == 4 and [len(c) for c in cones] == [3, 3, 4, 4, 3]
+    assert sorted(r[1] for r in lp if list(r[0]) == [17]) == [params.t_max, params.t_max] and sorted(list(r[0].values())[0] for r in lp if list(r[0]) == [17]) == [-1., 1.]
+    with pytest.raises(S.ScppError):
+        S.load_model_info(os.path.join(S.CONFIG_DIR, "RocketQuatRoll", "model.info"), S.ROCKETQUAT)      # the hand-written table has no roll rows

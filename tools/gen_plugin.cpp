@@ -19,8 +19,13 @@ static int generate(const std::string &dir, const std::string &file, const std::
     cvx::OptimizationProblem socp;
     socp.addVariable("X", M::NX, K);
     socp.addVariable("U", M::NU, K);
-    M::addApplicationConstraints(socp, constants, x_init, x_final);
+    std::vector<double> node_array(3 * K, 0.);
     scpp_plugin::Lowering L;
+    if constexpr (M::uses_node_array) {
+        M::addApplicationConstraints(socp, constants, x_init, x_final, node_array.data());
+        L.node_array = {node_array.data(), 3 * K}; L.node_rows = 3;
+    } else
+        M::addApplicationConstraints(socp, constants, x_init, x_final);
     L.constants = {constants, M::NCONST}; L.x_init = {x_init, M::NX}; L.x_final = {x_final, M::NX};
     const scpp_plugin::StageTable t = L.lower(socp);
     const scpp_plugin::Emitted e = scpp_plugin::emit_inc(t, NAME, scpp::MAX_CST);
@@ -36,7 +41,9 @@ int main(int argc, char **argv)
 {
     const std::string dir = argc > 1 ? argv[1] : ".";
     try {
-        return generate<scpp::Rocket2dPlugin>(dir, "rocket2d_plugin.inc", "ROCKET2D_PLUGIN");
+        int rc = generate<scpp::Rocket2dPlugin>(dir, "rocket2d_plugin.inc", "ROCKET2D_PLUGIN");
+        if (!rc) rc = generate<scpp::RocketQuatRollPlugin>(dir, "rocketquat_roll_plugin.inc", "ROCKETQUAT_ROLL_PLUGIN");
+        return rc;
     } catch (const std::exception &ex) {
         std::cerr << "gen_plugin: " << ex.what() << "\n";
         return 2;
