@@ -68,7 +68,8 @@ typedef struct {
 /* SC.info as read by SCAlgorithm::loadParameters (scpp_core/src/SCAlgorithm.cpp:22-46) + engine knobs */
 typedef struct {
     int K;
-    int free_final_time, interpolate_input, nondimensionalize;
+    int free_final_time, interpolate_input, nondimensionalize;   /* free_final_time = 0: sigma is not a variable (SCProblem.cpp:27-35), the final time stays
+                                                                     model.info's final_time; interpolate_input = 0 (zero-order hold) returns UNSUPPORTED */
     double weight_time, weight_trust_region_time, weight_trust_region_trajectory, weight_virtual_control;
     double nu_tol, delta_tol;
     int max_iterations;

@@ -899,8 +899,8 @@ int scpp_b200_create(int model, const scpp_b200_model_params *params, const scpp
         return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: SCvx needs trust_region > 0, alpha > 1, beta > 1");
     if (!params || !cfg || !out || n <= 0) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: bad argument");
     if (cfg->K < 3 || cfg->max_iterations < 1 || cfg->nsub == 0) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: K >= 3, max_iterations >= 1, nsub != 0 required");
-    if (!cfg->free_final_time || !cfg->interpolate_input)
-        return fail(SCPP_B200_ERR_UNSUPPORTED, "only free_final_time = true, interpolate_input = true (the shipped SC.info settings) are built");
+    if (!cfg->interpolate_input)
+        return fail(SCPP_B200_ERR_UNSUPPORTED, "only interpolate_input = true (first-order hold, the shipped SC.info setting) is built");
     if ((params->enable_roll_control != 0) != (model == SCPP_B200_MODEL_ROCKETQUAT_ROLL))
         return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control: use model SCPP_B200_MODEL_ROCKETQUAT_ROLL for true, SCPP_B200_MODEL_ROCKETQUAT for false");
     if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");

@@ -214,6 +214,10 @@ struct Ipm {
     // their s, z, w, lambda stay exactly zero), cost w_vc |nu|_1 alone (caller sets w_time = w_trs = w_tr = 0)
     bool scvx = false;
     double tr_rad = 0.;
+    // sigma pinned to sigbar, the global rows (sigma >= 0.001, the sigma trust region) and the border of the Newton system skipped: SCvx, and SC
+    // with free_final_time = false (SCProblem.cpp:27-35,49-56,82-100: no sigma / delta_sigma variables; the fixed-time z_k of
+    // discretizationImplementation.hpp:111-116 equals z_k + s_k sigbar of the free-time tile, so K1 is unchanged).  scvx implies sig_fixed.
+    bool sig_fixed = false;
     // ---- workspace (global memory, per instance) -------------------------------------------------------------------
     double *prim, *dprim, *rx, *best_;
     double *s, *z, *wb, *lam, *rz, *cr, *dz, *ds;
@@ -448,7 +452,7 @@ struct Ipm {
                 }
             }
         }
-        if (lane_id() == 0 && k_lo == 0 && !scvx) {
+        if (lane_id() == 0 && k_lo == 0 && !sig_fixed) {
             const int r0 = RS * KS, p0 = PSN * KS;
             double s4[4], z4[4], d4[4], e4[4];
 #pragma unroll
@@ -684,7 +688,7 @@ struct Ipm {
         nm.gap = warp_sum(gap); nm.rz2 = warp_sum(rz2); nm.pcost = warp_sum(pcost); nm.zrz = warp_sum(zrz);
         nm.rx2 = warp_sum(rx2); nm.xrx = warp_sum(xrx); nm.h2 = warp_sum(h2); nm.bad = warp_or(bad);
         nm.acc_sig = warp_sum(acc_sig);
-        if (!split && !scvx) residual_globals(nm, identity);
+        if (!split && !sig_fixed) residual_globals(nm, identity);
     }
     // RXa += [w ; -C' w] of interval k-1
     SCPP_HD void couple_prev(int k, double *RXa) const
@@ -813,8 +817,22 @@ struct Ipm {
     // is damped.  (Capping unconditionally doubles the iteration count of ordinary sub-problems: measured, DESIGN.md.)
     static constexpr double DCAP_FIRST = 1e10, DCAP_MIN = 1e7;
     double dcap = 0.;        // 0: no cap
+#if defined(SCPP_NO_DCAP)      // A/B experiment: what the cap costs in the stage passes
+    SCPP_HD double capd(double d) const { return d; }
+#elif defined(SCPP_DCAP_SMEM) && defined(__CUDA_ARCH__)      // A/B experiment: the cap re-read from the shared window at every use (no long-lived register)
+    SCPP_HD double capd(double d) const { const double c = sc()[24]; return (c > 0. && d > c) ? c : d; }
+#else
     SCPP_HD double capd(double d) const { return (dcap > 0. && d > dcap) ? dcap : d; }
-    SCPP_HD bool tighten_cap() { dcap = (dcap == 0.) ? DCAP_FIRST : dcap * 0.1; return dcap >= DCAP_MIN; }
+#endif
+    SCPP_HD bool tighten_cap()
+    {
+        dcap = (dcap == 0.) ? DCAP_FIRST : dcap * 0.1;
+#if defined(SCPP_DCAP_SMEM) && defined(__CUDA_ARCH__)
+        if (lane_id() == 0) sc()[24] = dcap;
+        warp_sync();
+#endif
+        return dcap >= DCAP_MIN;
+    }
     // Cholesky factor of the NB x NB block H (lower triangle valid, row-major in the shared window) and its inverse Li = L^-1.
     // Device: lane i keeps row i of H in registers; column j is scaled by rsqrt of the pivot (broadcast by shuffle) and the
     // trailing update takes L[c][j] from lane c by shuffle, fully unrolled (153 DFMA).  L goes back to the window, then lane c
@@ -1012,7 +1030,7 @@ struct Ipm {
     // delta_sigma eliminated); sets l_ss
     SCPP_HD bool finish_corner(double corner)
     {
-        if (scvx) { l_ss = 1.; return true; }                  // sigma is pinned: no border
+        if (sig_fixed) { l_ss = 1.; return true; }             // sigma is pinned: no border
         const int r0 = RS * KS;
         const double d = wb[r0];
         double w3[3] = {wb[r0 + 1], wb[r0 + 2], wb[r0 + 3]};
@@ -1757,7 +1775,7 @@ struct Ipm {
     // globals: rhs and local elimination for the sigma rows, then y_sigma (every lane computes the same scalars)
     SCPP_HD void globals_mid(int mode, double csig, double sigmu, double gsig, double ldot, Glob &g) const
     {
-        if (scvx) { for (int i = 0; i < 4; i++) g.rzg[i] = 0.; g.rxg[0] = g.rxg[1] = 0.; g.kap_s = 1.; g.p_s[0] = g.p_s[1] = g.p_s[2] = 0.; g.ysig = 0.; return; }
+        if (sig_fixed) { for (int i = 0; i < 4; i++) g.rzg[i] = 0.; g.rxg[0] = g.rxg[1] = 0.; g.kap_s = 1.; g.p_s[0] = g.p_s[1] = g.p_s[2] = 0.; g.ysig = 0.; return; }
         const int r0g = RS * KS, p0g = PSN * KS;
         double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
         const double e2i = ce[NCN * KS], d0 = wb[r0g];
@@ -1789,7 +1807,7 @@ struct Ipm {
     // Call from lane 0 only (it stores).
     SCPP_HD double globals_recover(int mode, double rzs, const Glob &g)
     {
-        if (scvx) return 0.;
+        if (sig_fixed) return 0.;
         const int r0g = RS * KS, p0g = PSN * KS;
         double tmax = 0;
         double w3[3] = {wb[r0g + 1], wb[r0g + 2], wb[r0g + 3]};
@@ -1862,7 +1880,7 @@ struct Ipm {
                 out[(MN + i) * KS + k] = tm; out[(MN + NX + i) * KS + k] = tp;
             }
         }
-        if (lane_id() == 0 && !scvx) { const int r0 = RS * KS; out[r0] = sg - 0.001; out[r0 + 1] = 0.5 + 0.5 * dsg; out[r0 + 2] = 0.5 - 0.5 * dsg; out[r0 + 3] = sg - sigbar; }
+        if (lane_id() == 0 && !sig_fixed) { const int r0 = RS * KS; out[r0] = sg - 0.001; out[r0 + 1] = 0.5 + 0.5 * dsg; out[r0 + 2] = 0.5 - 0.5 * dsg; out[r0 + 3] = sg - sigbar; }
         warp_sync();
     }
     // visit every cone of a row array: f(first index, stride, dimension)
@@ -1875,7 +1893,7 @@ struct Ipm {
             f(TRO * KS + k, KS, D);
             if (k < K - 1) for (int r = MN; r < RS; r++) f(r * KS + k, KS, 1);
         }
-        if (lane_id() == 0 && !scvx) { f(RS * KS, 1, 1); f(RS * KS + 1, 1, 3); }
+        if (lane_id() == 0 && !sig_fixed) { f(RS * KS, 1, 1); f(RS * KS + 1, 1, 3); }
     }
     SCPP_HD void cone_margin(const double *u, double &mn, double &nrm2) const
     {
@@ -1905,7 +1923,7 @@ struct Ipm {
             // previous interior point of this instance, pulled back from the boundary; pinned variables keep their values
             const double lw = st_.warm, lc = 1. - st_.warm;
             FOR_LANE(k, K) { for (int i = 0; i < NB; i++) if (fixed(k, i)) prim[i * KS + k] = fixv[k * NB + i]; if (scvx) prim[NB * KS + k] = tr_rad; }
-            if (scvx && lane_id() == 0) { prim[PSN * KS] = sigbar; prim[PSN * KS + 1] = 0.; }
+            if (sig_fixed && lane_id() == 0) { prim[PSN * KS] = sigbar; prim[PSN * KS + 1] = 0.; }
             FOR_LANE(e, m) { s[e] *= lw; z[e] *= lw; }
             warp_sync();
             cone_shift(s, lc); cone_shift(z, lc);
@@ -1967,12 +1985,19 @@ struct Ipm {
         finished = true;
         tables_init();
         const bool resume = state[0] != 0.;
+#if defined(SCPP_DCAP_SMEM) && defined(__CUDA_ARCH__)
+        if (lane_id() == 0) sc()[24] = resume ? state[ST_DCAP] : 0.;
+        warp_sync();
+#endif
         Norms nm;
         double tm;
         double best = 1e300, pending = 0.;
         int it = 0;
         if (resume) {
-            it = (int)state[1]; pending = state[2]; best = state[3]; dcap = state[ST_DCAP];
+            it = (int)state[1]; pending = state[2]; best = state[3];
+#if !defined(SCPP_R01_SOLVE)
+            dcap = state[ST_DCAP];
+#endif
             res.pres = state[4]; res.dres = state[5]; res.gap = state[6]; res.relgap = state[7]; res.pcost = state[8]; res.iterations = (int)state[9];
         } else {
             const int how = init_point(st_, have_prev);
@@ -1981,7 +2006,7 @@ struct Ipm {
         }
         const double cnorm = sqrt(w_time * w_time + w_trs * w_trs + K * w_tr * w_tr + (K - 1) * NX * w_vc * w_vc);
         const double resx0 = fmax(1., cnorm);
-        const int degree = K * (NLP + NCN) + (K - 1) * 2 * NX + (scvx ? 0 : 2);
+        const int degree = K * (NLP + NCN) + (K - 1) * 2 * NX + (sig_fixed ? 0 : 2);
         // One slice = factorisation + the two solves of iteration `it`, then update + residuals + termination test of `it+1`,
         // so that the cheap final test never occupies a launch of its own.  A resumed solver re-enters after the test.
         bool past_test = resume;
@@ -2016,7 +2041,10 @@ struct Ipm {
                     if (lane_id() == 0) {
                         state[0] = 1.; state[1] = it; state[2] = pending; state[3] = best;
                         state[4] = res.pres; state[5] = res.dres; state[6] = res.gap; state[7] = res.relgap; state[8] = res.pcost; state[9] = res.iterations;
-                        state[10] = gap_cur; state[ST_DCAP] = dcap;
+                        state[10] = gap_cur;
+#if !defined(SCPP_R01_SOLVE)
+                        state[ST_DCAP] = dcap;
+#endif
                     }
                     warp_sync();
                     finished = false;
@@ -2025,10 +2053,14 @@ struct Ipm {
             }
             past_test = false;
             budget--;
+#if defined(SCPP_R01_SOLVE)      // A/B experiment: the round-1 driver (no retry with a tightened cap)
+            if (!phase_factor()) { res.status = 2; break; }
+#else
             bool factored;                                                       // ONE call site: the factorisation is inlined once (code size)
 #pragma unroll 1
             do { factored = phase_factor(); } while (!factored && tighten_cap());        // numerically indefinite: regularise (see dcap) and repeat
             if (!factored) { res.status = 2; break; }
+#endif
             double tmax;
             phase_solve(1, 1., 0., -1., tmax);                               // affine direction
             const double a_aff = tmax <= 1. ? 1. : 1. / tmax;
@@ -2065,7 +2097,7 @@ struct Ipm {
     SCPP_HD void set_part(int w) { k_lo = 32 * w; k_hi = (32 * w + 32 < K) ? 32 * w + 32 : K; }
     SCPP_HD double part_sum(int slot) const { double v = 0; for (int w = 0; w < nparts(); w++) v += part[w * PSTR + slot]; return v; }
     SCPP_HD double part_max(int slot) const { double v = 0; for (int w = 0; w < nparts(); w++) v = fmax(v, part[w * PSTR + slot]); return v; }
-    SCPP_HD int degree() const { return K * (NLP + NCN) + (K - 1) * 2 * NX + (scvx ? 0 : 2); }
+    SCPP_HD int degree() const { return K * (NLP + NCN) + (K - 1) * 2 * NX + (sig_fixed ? 0 : 2); }
     // parameters of a solve: mode 1 = affine direction, mode 2 = combined direction (centering from the affine step length)
     SCPP_HD void solve_params(int mode, const double *state, double &csig, double &sigmu, double &rzs) const
     {
@@ -2220,7 +2252,7 @@ struct Ipm {
         nm.h2 = part_sum(6); nm.bad = part_max(7) != 0.; nm.acc_sig = part_sum(PT_ACC);
         if (state[ST_FAIL] == 2.) { if (lane_id() == 0) state[ST_FAIL] = 0.; warp_sync(); return false; }
         const bool failed = state[ST_FAIL] != 0.;
-        if (!failed) { residual_couple(nm); if (!scvx) residual_globals(nm, false); }
+        if (!failed) { residual_couple(nm); if (!sig_fixed) residual_globals(nm, false); }
         return test_and_book(st_, nm, (int)state[1] + 1, failed, state, res);
     }
 

@@ -160,7 +160,7 @@ SCPP_HD void cp_update(double a)
             if (h == 0) put_rows<MN, NX>(k, S, Z); else put_rows<MN + NX, NX>(k, S, Z);
         }
     }
-    if (cta_tid() == 0 && !scvx) {
+    if (cta_tid() == 0 && !sig_fixed) {
         const int r0 = RS * KS, p0 = PSN * KS;
         double s4[4], z4[4];
         for (int i = 0; i < 4; i++) { s4[i] = s[r0 + i] + a * ds[r0 + i]; z4[i] = z[r0 + i] + a * dz[r0 + i]; }
@@ -344,7 +344,7 @@ SCPP_HD void cp_residuals(Norms &nm, bool identity)
     double r[9] = {gap, rz2, pcost, zrz, rx2, xrx, h2, acc_sig, bad};
     cta_sum(r);
     nm.gap = r[0]; nm.rz2 = r[1]; nm.pcost = r[2]; nm.zrz = r[3]; nm.rx2 = r[4]; nm.xrx = r[5]; nm.h2 = r[6]; nm.acc_sig = r[7]; nm.bad = r[8] != 0.;
-    if (!scvx) {
+    if (!sig_fixed) {
         // the four global rows: every thread computes the same scalars, one thread stores
         Norms g = nm;
         if (cta_tid() < LANES) residual_globals(g, identity);          // warp 0 (its lane 0 stores)
@@ -1175,7 +1175,7 @@ SCPP_HD void cp_eval_slack(double *out)
             out[(MN + i) * KS + k] = tm; out[(MN + NX + i) * KS + k] = tp;
         }
     }
-    if (cta_tid() == 0 && !scvx) { const int r0 = RS * KS; out[r0] = sg - 0.001; out[r0 + 1] = 0.5 + 0.5 * dsg; out[r0 + 2] = 0.5 - 0.5 * dsg; out[r0 + 3] = sg - sigbar; }
+    if (cta_tid() == 0 && !sig_fixed) { const int r0 = RS * KS; out[r0] = sg - 0.001; out[r0 + 1] = 0.5 + 0.5 * dsg; out[r0 + 2] = 0.5 - 0.5 * dsg; out[r0 + 3] = sg - sigbar; }
     cta_sync();
 }
 template <class F>
@@ -1187,7 +1187,7 @@ SCPP_HD void cp_for_cones(F &&f) const
         f(TRO * KS + k, KS, D);
         if (k < K - 1) for (int r = MN; r < RS; r++) f(r * KS + k, KS, 1);
     }
-    if (cta_tid() == 0 && !scvx) { f(RS * KS, 1, 1); f(RS * KS + 1, 1, 3); }
+    if (cta_tid() == 0 && !sig_fixed) { f(RS * KS, 1, 1); f(RS * KS + 1, 1, 3); }
 }
 SCPP_HD void cp_cone_margin(const double *u, double &mn, double &nrm2)
 {
@@ -1215,7 +1215,7 @@ SCPP_HD int cp_init_point(const IpmSettings &st_, bool have_prev)
     if (have_prev && st_.warm > 0. && st_.warm < 1.) {
         const double lw = st_.warm, lc = 1. - st_.warm;
         FOR_CTA(k, K) { for (int i = 0; i < NB; i++) if (fixed(k, i)) prim[i * KS + k] = fixv[k * NB + i]; if (scvx) prim[NB * KS + k] = tr_rad; }
-        if (scvx && cta_tid() == 0) { prim[PSN * KS] = sigbar; prim[PSN * KS + 1] = 0.; }
+        if (sig_fixed && cta_tid() == 0) { prim[PSN * KS] = sigbar; prim[PSN * KS + 1] = 0.; }
         FOR_CTA(e, m) { s[e] *= lw; z[e] *= lw; }
         cta_sync();
         cp_cone_shift(s, lc); cp_cone_shift(z, lc);

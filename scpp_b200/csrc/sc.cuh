@@ -184,7 +184,8 @@ SCPP_HD void sc_bind(const ScArrays<M> &a, const ScConfig &cfg, int n, double *s
     ipm.fixv = a.fixv + (size_t)n * K * NB;
     ipm.w_time = cfg.weight_time; ipm.w_trs = cfg.weight_trust_region_time; ipm.w_vc = cfg.weight_virtual_control;
     ipm.w_tr = a.w_tr[n];
-    if (cfg.algorithm == 1) { ipm.scvx = true; ipm.tr_rad = a.trust[n]; ipm.w_time = 0.; ipm.w_trs = 0.; ipm.w_tr = 0.; }
+    if (cfg.algorithm == 1) { ipm.scvx = true; ipm.sig_fixed = true; ipm.tr_rad = a.trust[n]; ipm.w_time = 0.; ipm.w_trs = 0.; ipm.w_tr = 0.; }
+    else if (!cfg.free_final_time) { ipm.sig_fixed = true; ipm.w_time = 0.; ipm.w_trs = 0.; }      // SC with a fixed final time: no sigma / delta_sigma (SCProblem.cpp:27-35,82-100)
     if (cta) ipm.bind_cta(a.ws + (size_t)n * a.ws_stride, smem); else ipm.bind(a.ws + (size_t)n * a.ws_stride, smem);
 }
 

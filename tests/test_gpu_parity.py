@@ -270,7 +270,7 @@ def test_warm_start_and_errors(S):
     assert (warm["flags"] == 1).all() and (warm["iterations"] <= cold["iterations"]).all()
     assert np.allclose(warm["X"], cold["X"], atol=1e-3 * np.abs(cold["X"]).max())
     eng.close()
-    bad = S.default_config(model); bad.free_final_time = 0
+    bad = S.default_config(model); bad.interpolate_input = 0      # zero-order-hold inputs are not built: reported, not ignored
     with pytest.raises(S.ScppError):
         S.SCAlgorithm(model, params, bad, 1)
 
@@ -817,3 +817,20 @@ def test_rocketquat_roll_control_vs_oracle(S):
     _compare_run(S, "RocketQuatRoll", O.ROCKETQUAT, plist[:3], K=50, max_it=6, warm=0.995, cfg_over=dict(solver=1))
     with pytest.raises(S.ScppError):
         S.SCAlgorithm(S.ROCKETQUAT, params, cfg, 1)             # the hand-written model refuses roll control and names model 3
+
+
+def test_fixed_final_time_sc_vs_oracle(S):
+    """SC with free_final_time = false (a setting the reference dispatches on, SCProblem.cpp:27-35 / discretization.cpp:42-55; not used by the
+    shipped SC.info): RocketQuat K = 50 perturbed batch and Rocket2D K = 30 on the device against the oracle with free_final_time = 0, both K2
+    mappings; the final time of every instance stays at final_time"""
+    p, rpy = O.falcon9()
+    plist = [O.rq_perturb(p, rpy, 0x5C99, i) for i in range(70, 74)] + [p]
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=6, cfg_over=dict(free_final_time=0))
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist[:2], K=50, max_it=6, warm=0.995, cfg_over=dict(free_final_time=0, solver=1))
+    _compare_run(S, "Rocket2D", O.ROCKET2D, [O.rocket2d()], K=30, max_it=8, cfg_over=dict(free_final_time=0))
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=20, max_iterations=3, free_final_time=0)
+    eng = S.SCAlgorithm(model, params, cfg, 2)
+    eng.set_boundary_states(np.tile(x_init, (2, 1)), x_final)
+    eng.solve()
+    assert np.all(eng.get_solution()["t"] == params.final_time)
+    eng.close()

@@ -520,3 +520,22 @@ def test_rocketquat_with_roll_control_through_the_plugin_surface(S):
     assert sorted(r[1] for r in lp if list(r[0]) == [17]) == [params.t_max, params.t_max] and sorted(list(r[0].values())[0] for r in lp if list(r[0]) == [17]) == [-1., 1.]
     with pytest.raises(S.ScppError):
         S.load_model_info(os.path.join(S.CONFIG_DIR, "RocketQuatRoll", "model.info"), S.ROCKETQUAT)      # the hand-written table has no roll rows
+
+
+def test_fixed_final_time_sc_source_vs_oracle():
+    """SC with free_final_time = false (SCProblem.cpp:27-35,49-56,82-100: no sigma / delta_sigma variables; fixed-time discretisation
+    discretizationImplementation.hpp:111-116): the interior-point solver pins sigma (the global rows and the border of the Newton system are
+    skipped, z_fixed = z + s sigma falls out of the free-time tile) -- kernel source on the host, monolithic and split pipeline, against the
+    oracle with free_final_time = 0; the final time stays at model.info's final_time"""
+    for model, p, K in ((1, O.rocket2d(), 30), (0, O.falcon9()[0], 20)):
+        ocfg = O.sc_config(K=K, model=model, max_iterations=6)
+        ocfg.free_final_time = 0
+        ro = O.sc_solve(model, p, ocfg)
+        P, xi, xf = H.params_from_oracle(model, p)
+        for sl in (1, -1):
+            r = H.sc_solve(model, P, H.sc_config(ocfg, nsub=-5, tol=1e-8, ipm_slice=sl), xi, xf)
+            n = int(r["iters"][0])
+            assert n == abs(ro["iterations"]) and bool(r["converged"][0]) == ro["converged"]
+            assert r["t"][0] == p.final_time and np.all(ro["t_all"] == p.final_time)
+            for it in range(n + 1):
+                assert np.abs(r["X_all"][0, it] - ro["X_all"][it]).max() < 1e-5 and np.abs(r["U_all"][0, it] - ro["U_all"][it]).max() < 1e-4, (model, sl, it)
