@@ -207,9 +207,8 @@ def main():
     eng, cfg, xi, x_final = make_engine(S, args, rank, local, world, warm, args.solver)
     n_local = args.batch
     if world > 1:
-        obj = [S.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        eng.comm_init(world, rank, obj[0])
+        from scpp_b200.sharding import broadcast_unique_id
+        eng.comm_init(world, rank, broadcast_unique_id(dist, S.comm_unique_id, rank))
 
     def sync_all():
         if dist is not None:
@@ -270,10 +269,8 @@ def main():
     stats = np.array([dev_total_ms, wall_e2e, wall_dev] + [extras.get(k, {}).get("ms", 0.0) for k in ("cold", "other_solver")], dtype=np.float64)
     sums = np.array([inst_iters, e2e_iters, launches] + [extras.get(k, {}).get("inst_iters", 0) for k in ("cold", "other_solver")], dtype=np.float64)
     if dist is not None:
-        import torch
-        tmax = torch.tensor(stats, device="cuda"); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = torch.tensor(sums, device="cuda"); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        stats, sums = tmax.cpu().numpy(), tsum.cpu().numpy()
+        from scpp_b200.sharding import reduce_timing
+        stats, sums = reduce_timing(dist, stats, sums, device="cuda")      # max over ranks of the times, sum over ranks of the counts
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         value = sums[0] / (stats[0] * 1e-3)

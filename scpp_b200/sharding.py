@@ -1,7 +1,8 @@
 """Host-side plumbing for multi-GPU runs: one process (rank) per GPU, the batch of problem instances is partitioned
 contiguously; no trajectory or Jacobian data ever crosses GPUs.  The only exchange on the data path is the per-instance
 convergence flags once per outer iteration (ncclAllGather inside libscpp_b200; the same protocol is expressed here over
-torch.distributed so it can be exercised with the gloo backend on CPU)."""
+torch.distributed so it can be exercised with the gloo backend on CPU).  bench.py and tools/multi_gpu_check.py bootstrap their ranks with
+these helpers (unique-id broadcast, max / sum aggregation of the timings); tests/test_host.py runs them over gloo with world_size 2."""
 import numpy as np
 
 
@@ -31,11 +32,11 @@ def global_active(dist, local_flags, pad_to):
     return int((allf == 0).sum()), allf.numpy()
 
 
-def reduce_timing(dist, seconds, counts):
-    """max over ranks of the timed seconds, sum over ranks of the work counts (bench.py's aggregation)"""
+def reduce_timing(dist, seconds, counts, device=None):
+    """max over ranks of the timed seconds, sum over ranks of the work counts (bench.py's aggregation); device: "cuda" under the nccl backend"""
     import torch
-    t = torch.tensor(list(seconds), dtype=torch.float64)
-    c = torch.tensor(list(counts), dtype=torch.float64)
+    t = torch.tensor(list(seconds), dtype=torch.float64, device=device)
+    c = torch.tensor(list(counts), dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    return t.numpy(), c.numpy()
+    return t.cpu().numpy(), c.cpu().numpy()

@@ -25,9 +25,8 @@ xi_all = S.perturbed_initial_states(x_init, np.deg2rad([-20.0, 20.0, 0.0]), N)
 w = np.arange(1, world + 1, dtype=float); cuts = np.concatenate([[0], np.round(np.cumsum(w) / w.sum() * N).astype(int)])
 lo, hi = int(cuts[rank]), int(cuts[rank + 1])
 eng = S.SCAlgorithm(model, params, cfg, hi - lo, device=local)
-obj = [S.comm_unique_id() if rank == 0 else None]
-dist.broadcast_object_list(obj, src=0)
-eng.comm_init(world, rank, obj[0])
+from scpp_b200.sharding import broadcast_unique_id
+eng.comm_init(world, rank, broadcast_unique_id(dist, S.comm_unique_id, rank))
 eng.set_boundary_states(xi_all[lo:hi], x_final)
 eng.solve()
 sol = eng.get_solution(); ga = eng.global_active(); r = eng.last_rounds()
