@@ -412,7 +412,7 @@ struct EngineT : scpp_b200_engine {
         // solved), (3) re-forms the lists and exchanges the flag bytes.  With ipm_slice == 0 a slice is a whole sub-problem and
         // the rounds are the reference's outer iterations in lock-step.
         const int slice_eff = cfg.solver == 1 ? 0 : (cfg.ipm_slice < 0 ? 1 : cfg.ipm_slice);      // solver 1: a round is an outer iteration
-        const long long max_rounds = (long long)cfg.max_iterations * (cfg.algorithm == 1 ? SCVX_MAX_RESOLVE + 1 : 1) * (slice_eff > 0 ? (cfg.ipm.maxit + 3 + 8) / slice_eff + 2 : 1) + 1;   // + 8: rounds repeated after a regularised re-factorisation
+        const long long max_rounds = (long long)cfg.max_iterations * (cfg.algorithm == 1 ? SCVX_MAX_RESOLVE + 1 : 1) * (slice_eff > 0 ? (cfg.ipm.maxit + 3 + 8) / slice_eff + 2 : 1) + 9;   // + 8: rounds repeated after a regularised re-factorisation
         for (long long round = 0; round < max_rounds && n_active > 0; round++) {
             CU(cudaEventRecord(ev[1], stream));
             if (n_disc > 0) {

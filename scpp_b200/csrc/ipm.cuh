@@ -1472,46 +1472,55 @@ struct Ipm {
     }
 
     // forward substitution  f_k = Linv_k (g_k - L_{k,k-1} f_{k-1})  in place in gv ; returns the lane-partial of  sum_k l_k' f_k
-    SCPP_HD void ld_col(double *dst, const double *src) const   // one stage column of a stage-minor [NB][KS] array: NB 8-byte asynchronous copies
+    SCPP_HD void ld_col(double *dst, const double *src, int ks) const   // one stage column of a stage-minor [NB][KS] array: NB 8-byte asynchronous copies
     {
 #if defined(__CUDA_ARCH__)
         const int j = lane_id();
-        if (j < NB) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + j)), "l"(src + (size_t)j * KS) : "memory");
+        if (j < NB) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + j)), "l"(src + (size_t)j * ks) : "memory");
 #else
-        for (int j = 0; j < NB; j++) dst[j] = src[(size_t)j * KS];
+        for (int j = 0; j < NB; j++) dst[j] = src[(size_t)j * ks];
 #endif
     }
     SCPP_HD double chain_forward()
     {
+        // the solver object lives in local memory and every asynchronous copy is a compiler memory barrier: members read inside the loop
+        // are re-loaded from the stack in every stage (ncu r02i: 10 % of the kernel's stall samples waited for `fac` to come back before
+        // the copy addresses could be formed) -> loop-invariant members are taken into registers here
+        const double *const fac_ = fac;
+        double *const gv_ = gv;
+        const int K_ = K, KS_ = KS;
         double *fcur = vec(0), *tmp = vec(1);
+        double *const v0 = vec(2), *const v1 = vec(3), *const v2 = vec(4), *const fb0 = fbuf(0), *const fb1 = fbuf(1), *const fb2 = fbuf(2);
+        auto vecr = [&](int i) { return i == 0 ? v0 : (i == 1 ? v1 : v2); };
+        auto fbr = [&](int i) { return i == 0 ? fb0 : (i == 1 ? fb1 : fb2); };
         double ldot = 0;
         // group of record r carries the right-hand side of stage r+1 (needed at the end of stage r)
-        ld(fbuf(0), fac, FS); if (K > 1) ld_col(vec(2 + 1 % 3), gv + 1); ld_commit();
-        if (K > 1) { ld(fbuf(1), fac + FS, FS); if (K > 2) ld_col(vec(2 + 2 % 3), gv + 2); }
+        ld(fb0, fac_, FS); if (K_ > 1) ld_col(vecr(1 % 3), gv_ + 1, KS_); ld_commit();
+        if (K_ > 1) { ld(fb1, fac_ + FS, FS); if (K_ > 2) ld_col(vecr(2 % 3), gv_ + 2, KS_); }
         ld_commit();
-        FOR_LANE(jj, NB) tmp[jj] = gv[jj * KS];
+        FOR_LANE(jj, NB) tmp[jj] = gv_[jj * KS_];
 #pragma unroll 1
-        for (int k = 0; k < K; k++) {
-            if (k + 2 < K) { ld(fbuf((k + 2) % 3), fac + (size_t)(k + 2) * FS, FS); if (k + 3 < K) ld_col(vec(2 + (k + 3) % 3), gv + k + 3); }
+        for (int k = 0; k < K_; k++) {
+            if (k + 2 < K_) { ld(fbr((k + 2) % 3), fac_ + (size_t)(k + 2) * FS, FS); if (k + 3 < K_) ld_col(vecr((k + 3) % 3), gv_ + k + 3, KS_); }
             ld_commit();
             ld_wait(2);
-            const double *F = fbuf(k % 3), *Ln = F + OFF_LN, *gn = vec(2 + (k + 1) % 3);
+            const double *F = fbr(k % 3), *Ln = F + OFF_LN, *gn = vecr((k + 1) % 3);
             FOR_LANE(jj, NB) {
-                double v = 0, v2 = 0;
+                double v = 0, v2_ = 0;
 #pragma unroll
-                for (int c = 0; c < NB; c += 2) { v += F[jj * NB + c] * tmp[c]; v2 += F[jj * NB + c + 1] * tmp[c + 1]; }
-                v += v2;
+                for (int c = 0; c < NB; c += 2) { v += F[jj * NB + c] * tmp[c]; v2_ += F[jj * NB + c + 1] * tmp[c + 1]; }
+                v += v2_;
                 fcur[jj] = v;
-                gv[jj * KS + k] = v;
+                gv_[jj * KS_ + k] = v;
                 ldot += F[OFF_L + jj] * v;
             }
             warp_sync();
-            if (k + 1 < K) {
+            if (k + 1 < K_) {
                 FOR_LANE(jj, NB) {
-                    double v = gn[jj], v2 = 0;
+                    double v = gn[jj], v2_ = 0;
 #pragma unroll
-                    for (int c = 0; c < NB; c += 2) { v -= Ln[jj * NB + c] * fcur[c]; v2 -= Ln[jj * NB + c + 1] * fcur[c + 1]; }
-                    v += v2;
+                    for (int c = 0; c < NB; c += 2) { v -= Ln[jj * NB + c] * fcur[c]; v2_ -= Ln[jj * NB + c + 1] * fcur[c + 1]; }
+                    v += v2_;
                     tmp[jj] = v;
                 }
             }
@@ -1523,37 +1532,48 @@ struct Ipm {
     // back substitution  y_k = Linv_k' (f_k - L_{k+1,k}' y_{k+1} - l_k y_sigma)  in place in gv
     SCPP_HD void chain_backward(double ysig)
     {
+        // loop-invariant members in registers (see chain_forward); the pinned-variable mask of the NEXT stage is loaded one stage ahead
+        // (ncu r02i: 4 % of the stall samples waited for fixm[k] at its first use)
+        const double *const fac_ = fac;
+        double *const gv_ = gv;
+        const uint32_t *const fixm_ = fixm;
+        const int K_ = K, KS_ = KS;
         double *ynext = vec(0), *tmp = vec(1);
-        ld(fbuf((K - 1) % 3), fac + (size_t)(K - 1) * FS, FS); ld_col(vec(2 + (K - 1) % 3), gv + K - 1); ld_commit();
-        if (K > 1) { ld(fbuf((K - 2) % 3), fac + (size_t)(K - 2) * FS, FS); ld_col(vec(2 + (K - 2) % 3), gv + K - 2); }
+        double *const v0 = vec(2), *const v1 = vec(3), *const v2 = vec(4), *const fb0 = fbuf(0), *const fb1 = fbuf(1), *const fb2 = fbuf(2);
+        auto vecr = [&](int i) { return i == 0 ? v0 : (i == 1 ? v1 : v2); };
+        auto fbr = [&](int i) { return i == 0 ? fb0 : (i == 1 ? fb1 : fb2); };
+        ld(fbr((K_ - 1) % 3), fac_ + (size_t)(K_ - 1) * FS, FS); ld_col(vecr((K_ - 1) % 3), gv_ + K_ - 1, KS_); ld_commit();
+        if (K_ > 1) { ld(fbr((K_ - 2) % 3), fac_ + (size_t)(K_ - 2) * FS, FS); ld_col(vecr((K_ - 2) % 3), gv_ + K_ - 2, KS_); }
         ld_commit();
+        uint32_t mk_next = fixm_[K_ - 1];
 #pragma unroll 1
-        for (int k = K - 1; k >= 0; k--) {
-            const bool hasint = k < K - 1;
-            if (k >= 2) { ld(fbuf((k - 2) % 3), fac + (size_t)(k - 2) * FS, FS); ld_col(vec(2 + (k - 2) % 3), gv + k - 2); }
+        for (int k = K_ - 1; k >= 0; k--) {
+            const bool hasint = k < K_ - 1;
+            if (k >= 2) { ld(fbr((k - 2) % 3), fac_ + (size_t)(k - 2) * FS, FS); ld_col(vecr((k - 2) % 3), gv_ + k - 2, KS_); }
             ld_commit();
-            const uint32_t mk = fixm[k];
+            const uint32_t mk = mk_next;
+            if (k > 0) mk_next = fixm_[k - 1];
             ld_wait(2);
-            const double *F = fbuf(k % 3), *fk = vec(2 + k % 3);
+            const double *F = fbr(k % 3), *fk = vecr(k % 3);
             FOR_LANE(jj, NB) {
                 double v = fk[jj] - F[OFF_L + jj] * ysig;
                 if (hasint) {
-                    double v2 = 0;
+                    double v2_ = 0;
 #pragma unroll
-                    for (int c = 0; c < NB; c += 2) { v -= F[OFF_LN + c * NB + jj] * ynext[c]; v2 -= F[OFF_LN + (c + 1) * NB + jj] * ynext[c + 1]; }
-                    v += v2;
+                    for (int c = 0; c < NB; c += 2) { v -= F[OFF_LN + c * NB + jj] * ynext[c]; v2_ -= F[OFF_LN + (c + 1) * NB + jj] * ynext[c + 1]; }
+                    v += v2_;
                 }
                 tmp[jj] = v;
             }
             warp_sync();
             FOR_LANE(jj, NB) {
-                double v = 0, v2 = 0;
+                double v = 0, v2_ = 0;
 #pragma unroll
-                for (int c = 0; c < NB; c += 2) { v += F[c * NB + jj] * tmp[c]; v2 += F[(c + 1) * NB + jj] * tmp[c + 1]; }
-                v += v2;
+                for (int c = 0; c < NB; c += 2) { v += F[c * NB + jj] * tmp[c]; v2_ += F[(c + 1) * NB + jj] * tmp[c + 1]; }
+                v += v2_;
                 if ((mk >> jj) & 1u) v = 0.;
                 ynext[jj] = v;
-                gv[jj * KS + k] = v;
+                gv_[jj * KS_ + k] = v;
             }
             warp_sync();
         }
@@ -2056,10 +2076,24 @@ struct Ipm {
 #if defined(SCPP_R01_SOLVE)      // A/B experiment: the round-1 driver (no retry with a tightened cap)
             if (!phase_factor()) { res.status = 2; break; }
 #else
-            bool factored;                                                       // ONE call site: the factorisation is inlined once (code size)
-#pragma unroll 1
-            do { factored = phase_factor(); } while (!factored && tighten_cap());        // numerically indefinite: regularise (see dcap) and repeat
-            if (!factored) { res.status = 2; break; }
+            // numerically indefinite: regularise (see dcap) and repeat THIS iteration in the next launch.  No loop around the factorisation and
+            // no branch back into the main loop: with either the compiler schedules the whole inlined iteration 8-11 % slower (43.3 k vs
+            // 39.5-40.1 k instance-iterations/s, profiles/r02o_*, r02p_*).
+            if (!phase_factor()) {
+                if (tighten_cap()) {
+                    // park exactly as when the budget runs out (the state is that of "after the test of iterate `it`"): the NEXT launch re-enters
+                    // at the factorisation with the tightened cap.  An exit, not a branch back into the loop: dcap stays loop-invariant.
+                    if (lane_id() == 0) {
+                        state[0] = 1.; state[1] = it; state[2] = pending; state[3] = best;
+                        state[4] = res.pres; state[5] = res.dres; state[6] = res.gap; state[7] = res.relgap; state[8] = res.pcost; state[9] = res.iterations;
+                        state[10] = gap_cur; state[ST_DCAP] = dcap;
+                    }
+                    warp_sync();
+                    finished = false;
+                    return res;
+                }
+                res.status = 2; break;
+            }
 #endif
             double tmax;
             phase_solve(1, 1., 0., -1., tmax);                               // affine direction
