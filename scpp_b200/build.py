@@ -79,6 +79,6 @@ if __name__ == "__main__":
     if "--variant" in sys.argv:      # python scpp_b200/build.py --variant w8 -DSCPP_WPB_MAX=8
         i = sys.argv.index("--variant")
         only = [(0, 0)] if "--k2-only" in sys.argv else None      # only k_solve<RocketQuat> (kernel group 0 of model 0)
-        print(build(variant=sys.argv[i + 1], defines=[a for a in sys.argv[i + 2:] if a.startswith("-D")], verbose="-v" in sys.argv, only=only))
+        print(build(variant=sys.argv[i + 1], defines=[a for a in sys.argv[i + 2:] if a.startswith("-D")] + [f for a in sys.argv[i + 2:] if a.startswith("--nvcc=") for f in a[7:].split(",")], verbose="-v" in sys.argv, only=only))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

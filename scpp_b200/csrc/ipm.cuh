@@ -300,6 +300,15 @@ struct Ipm {
         warp_sync();
     }
     SCPP_HD void st(double *dst, const double *src, int n) const { FOR_LANE(e, n) dst[e] = src[e]; }
+    SCPP_HD void copy4(double *dst, const double *src, int n) const      // global -> global, four independent loads in flight per lane
+    {
+        int e = lane_id();
+        for (; e + 3 * LANES < n; e += 4 * LANES) {
+            const double a = src[e], b = src[e + LANES], c = src[e + 2 * LANES], d = src[e + 3 * LANES];
+            dst[e] = a; dst[e + LANES] = b; dst[e + 2 * LANES] = c; dst[e + 3 * LANES] = d;
+        }
+        for (; e < n; e += LANES) dst[e] = src[e];
+    }
 
     SCPP_HD double *vec(int i) const { return sm + W_VEC + i * NB; }
     SCPP_HD double *xv(int i) const { return sm + W_X + i * pad2(NX); }
@@ -342,15 +351,25 @@ struct Ipm {
             }
         }
         warp_sync();
+        if (lane_id() == 0) {      // entries of the coefficient table that take the stage's minimum-thrust direction (tables_stage)
+            int n = 0, *tl = sup() + TDL;
+            for (int r = 0; r < NROW; r++) {
+                const RowDesc rd = M::row(r);
+                for (int q = 0; q < 3; q++) if (q < rd.n && rd.cs[q] < 0 && n < TDL_MAX) { tl[1 + 2 * n] = r * 4 + q; tl[2 + 2 * n] = -rd.cs[q] - 1; n++; }
+            }
+            tl[0] = n;
+        }
+        warp_sync();
     }
     // once per stage of the chain: only the linearised minimum-thrust row depends on k (coefficient slots < 0 take -tdir[k])
+    // (the list of those entries is built once by tables_init: walking the row table here cost 1.6 % of the kernel in local-memory copies
+    // of RowDesc, ncu r02q)
+    static constexpr int TDL = 4 * NRK, TDL_MAX = (2 * pad2(2 * NB) - TDL - 1) / 2;      // list behind sup(): count, then (rcq entry, direction component) pairs
     SCPP_HD void tables_stage(const double *td) const   // td: the stage's direction in the shared window
     {
-        FOR_LANE(e, NROW * 3) {
-            const int r = e / 3, q = e - 3 * r;
-            const RowDesc rd = M::row(r);
-            if (q < rd.n && rd.cs[q] < 0) rcq()[r * 4 + q] = -td[-rd.cs[q] - 1];
-        }
+        const int *tl = sup() + TDL;
+        const int n = tl[0];
+        FOR_LANE(e, n) rcq()[tl[1 + 2 * e]] = -td[tl[2 + 2 * e]];
     }
     // ---- model rows in the stage-parallel passes: the row index is a compile-time constant after unrolling, so the row table
     //      folds into immediates and the scatter targets are registers
@@ -2048,7 +2067,7 @@ struct Ipm {
                 if (!nm.bad && score < best) {
                     best = score;
                     res.pres = pres; res.dres = dres; res.gap = gap; res.relgap = relgap; res.pcost = pcost; res.iterations = it;
-                    if (score <= 1e4) { FOR_LANE(e, np) best_[e] = prim[e]; }      // a fallback iterate only matters inside the accuracy band
+                    if (score <= 1e4) copy4(best_, prim, np);      // a fallback iterate only matters inside the accuracy band
                     warp_sync();
                 }
                 if (!nm.bad && pres <= st_.feastol && dres <= st_.feastol && (gap <= st_.abstol || relgap <= st_.reltol)) { res.status = 0; break; }
@@ -2103,7 +2122,7 @@ struct Ipm {
             pending = tmax <= 0.99 ? 1. : 0.99 / tmax;
         }
         if (res.status != 0) {
-            if (best <= 1e4) { FOR_LANE(e, np) prim[e] = best_[e]; }
+            if (best <= 1e4) copy4(prim, best_, np);
             warp_sync();
             if (best <= 1e4) res.status = 3;      // best iterate inside the accuracy band but short of the tolerances: reduced accuracy
         } else res.iterations = it;
@@ -2241,7 +2260,7 @@ struct Ipm {
             if (!nm.bad && score < best) {
                 best = score;
                 res.pres = pres; res.dres = dres; res.gap = gap; res.relgap = relgap; res.pcost = pcost; res.iterations = it;
-                if (score <= 1e4) { FOR_LANE(e, np) best_[e] = prim[e]; }
+                if (score <= 1e4) copy4(best_, prim, np);
                 warp_sync();
             }
             if (!nm.bad && pres <= st_.feastol && dres <= st_.feastol && (gap <= st_.abstol || relgap <= st_.reltol)) { res.status = 0; done = true; }
@@ -2261,7 +2280,7 @@ struct Ipm {
             return false;
         }
         if (res.status != 0) {
-            if (best <= 1e4) { FOR_LANE(e, np) prim[e] = best_[e]; }
+            if (best <= 1e4) copy4(prim, best_, np);
             warp_sync();
             if (best <= 1e4) res.status = 3;      // best iterate inside the accuracy band but short of the tolerances: reduced accuracy
         } else res.iterations = it;

@@ -33,7 +33,7 @@ for ln in open(f"{tmp}/dis.txt"):
 src = open(srcfile).read().split('\n'); fname = os.path.basename(srcfile)
 funcs = []
 for i, l in enumerate(src, 1):
-    m = re.match(r'\s+(?:template <[^>]*>\s*)?SCPP_HD\s+(?:static\s+)?(?:constexpr\s+)?[\w:<>\*& ]+?\s+\*?(\w+)\(', l)
+    m = re.match(r'\s+(?:template <[^>]*>\s*)?SCPP_HD(?:_PASS|_CHOL)?\s+(?:static\s+)?(?:constexpr\s+)?[\w:<>\*& ]+?\s+\*?(\w+)\(', l)
     if m and not l.strip().startswith('//'): funcs.append((i, m.group(1)))
 def fn_of(n):
     name = '?'
