@@ -62,7 +62,8 @@ typedef struct {
     int pad_;
     double warm;                    /* 0 = cold start of every sub-problem (what ECOS does); 0<warm<1: from the second outer iteration on,
                                        start from the instance's previous interior solution pulled back from the cone boundary,
-                                       (s,z) <- warm*(s,z) + (1-warm)*e (same optimum, ~2.8x fewer interior-point iterations) */
+                                       (s,z) <- warm*(s,z) + (1-warm)*e (same optimum, ~2.8x fewer interior-point iterations); the sub-problem after
+                                       a stalled outer iteration (sum of the trust-region radii <= delta_tol) starts 50x closer, 1-w' = (1-warm)/50 */
 } scpp_b200_ipm_settings;
 
 /* SC.info as read by SCAlgorithm::loadParameters (scpp_core/src/SCAlgorithm.cpp:22-46) + engine knobs */

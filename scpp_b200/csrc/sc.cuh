@@ -315,6 +315,24 @@ SCPP_HD void sc_scvx_decide(const ScArrays<M> &a, const ScConfig &cfg, int n)
     }
 }
 
+// Interior warm start (ipm.warm in (0,1), an engine knob: ECOS has none).  The sub-problem that follows a STALLED outer iteration -- the sum of
+// the trust-region radii of the previous solution is below delta_tol, the trajectory did not move -- is almost the sub-problem just solved, so
+// it starts 50x closer to that solution: (s,z) <- w'(s,z) + (1-w')e with 1-w' = (1-warm)/50.  Measured on the kernel source (4 instances x 15
+// iterations): 4 instead of 5 interior-point iterations per stalled sub-problem, while a uniformly closer start costs the moving sub-problems
+// 30 % more iterations.  Same optimum, same tolerances; only the starting point changes.
+constexpr double WARM_STALLED_GAIN = 0.02;
+template <class M>
+SCPP_HD IpmSettings sc_ipm_settings(const ScArrays<M> &a, const ScConfig &cfg, int n)
+{
+    IpmSettings st = cfg.ipm;
+    const int it = a.iters[n];
+    if (cfg.algorithm == 0 && st.warm > 0. && st.warm < 1. && it > 0) {
+        const double sum_delta = a.info[((size_t)n * a.max_it + it - 1) * INFO_STRIDE + 1];
+        if (sum_delta <= cfg.delta_tol) st.warm = 1. - (1. - st.warm) * WARM_STALLED_GAIN;
+    }
+    return st;
+}
+
 // ---- K2 + K3, monolithic: advance the sub-problem of instance n by one slice; when it is solved: K3 ----
 // SCAlgorithm::iterate, SCAlgorithm.cpp:78-131 (the defect print :85-92 is diagnostic only and not computed)
 template <class M>
@@ -325,7 +343,7 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
     bool finished;
     double *state = a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE;
     const bool have_prev = (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2 && state[Ipm<M>::ST_NOPOINT] == 0.;
-    const IpmResult r = ipm.solve(cfg.ipm, have_prev, cfg.ipm_slice > 0 ? cfg.ipm_slice : (cfg.ipm_slice < 0 ? 1 : (1 << 30)), state, finished);
+    const IpmResult r = ipm.solve(sc_ipm_settings(a, cfg, n), have_prev, cfg.ipm_slice > 0 ? cfg.ipm_slice : (cfg.ipm_slice < 0 ? 1 : (1 << 30)), state, finished);
     if (!finished) return;                                                   // continues in the next launch
     if (lane_id() == 0) state[Ipm<M>::ST_NOPOINT] = r.point_ok ? 0. : 1.;
     if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r);
@@ -340,7 +358,7 @@ SCPP_HD void sc_solve_instance_cta(const ScArrays<M> &a, const ScConfig &cfg, in
     double *state = a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE;
     const bool have_prev = (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2 && state[Ipm<M>::ST_NOPOINT] == 0.;
     cta_sync();                                                              // every thread has read the flags before warp 0 updates them below
-    const IpmResult r = ipm.cp_solve_subproblem(cfg.ipm, have_prev);
+    const IpmResult r = ipm.cp_solve_subproblem(sc_ipm_settings(a, cfg, n), have_prev);
     if (cta_tid() < LANES) {
         if (lane_id() == 0) state[Ipm<M>::ST_NOPOINT] = r.point_ok ? 0. : 1.;
         if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r);
@@ -366,7 +384,7 @@ SCPP_HD void sc_split_step(const ScArrays<M> &a, const ScConfig &cfg, int n, dou
     if (STEP != SP_START) ipm.dcap = state[Ipm<M>::ST_DCAP];
     IpmResult r;
     if (STEP == SP_START) {
-        if (ipm.sp_start(cfg.ipm, (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2 && state[Ipm<M>::ST_NOPOINT] == 0., state, r)) { if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r); }
+        if (ipm.sp_start(sc_ipm_settings(a, cfg, n), (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2 && state[Ipm<M>::ST_NOPOINT] == 0., state, r)) { if (cfg.algorithm == 1) sc_scvx_candidate(a, cfg, n, ipm, r); else sc_finish_instance(a, cfg, n, ipm, r); }
     } else if (STEP == SP_ASSEMBLE) {
         if (sub >= a.K) return;
         ipm.tables_init();
