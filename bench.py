@@ -148,6 +148,7 @@ def make_engine(S, args, rank, local, world, warm, solver):
     name = args.config
     model, params, x_init, x_final, cfg = S.load_model(name, K=args.K, algorithm=args.algorithm)
     cfg.ipm.warm = warm
+    cfg.ipm.stalled_step = int(os.environ.get("SCPP_STALLED_STEP", "0"))      # experiment knob (scpp_b200.h): default off
     cfg.solver = solver
     cfg.ipm_slice = int(os.environ.get("SCPP_SLICE", "1"))    # solver 0: interior-point iterations per K2 launch (0: lock-step outer iterations)
     rpy = np.deg2rad([70.0, 0.0, 0.0]) if name == "RocketQuatStarship" else np.deg2rad([-20.0, 20.0, 0.0])      # rpy_init of configs/<name>/model.info

@@ -59,7 +59,9 @@ typedef struct {
 typedef struct {
     double feastol, abstol, reltol; /* ECOS defaults: 1e-8 */
     int maxit;                      /* ECOS default: 100 */
-    int pad_;
+    int stalled_step;               /* engine knob, with warm > 0 only: the sub-problem after a stalled outer iteration steps 1 - 10^-stalled_step of the way
+                                       to the cone boundary instead of 0.99 (0 = 0.99 everywhere, the default).  3 was measured to shorten the AVERAGE
+                                       solve and to lengthen the slowest one of a batch, which is what a round waits for (profiles/README.md) */
     double warm;                    /* 0 = cold start of every sub-problem (what ECOS does); 0<warm<1: from the second outer iteration on,
                                        start from the instance's previous interior solution pulled back from the cone boundary,
                                        (s,z) <- warm*(s,z) + (1-warm)*e (same optimum, ~2.8x fewer interior-point iterations); the sub-problem after

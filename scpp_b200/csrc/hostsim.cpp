@@ -241,7 +241,7 @@ extern "C" int hs_dense_conic(int nv, int nl, int ncones, const int *cdim, const
     for (int k = 0; k < ncones; k++) nr += cdim[k];
     if (nv > 48 || nr > 320 || ncones > 48) return -1;
     S.nv = nv; S.nl = nl; S.ncones = ncones; S.nr = nr; S.cdim = cdim; S.G = G; S.c = c;
-    IpmSettings st; st.feastol = st.abstol = st.reltol = tol; st.maxit = 100; st.pad_ = 0; st.warm = 0.;
+    IpmSettings st; st.feastol = st.abstol = st.reltol = tol; st.maxit = 100; st.stalled_step = 0; st.warm = 0.;
     const IpmResult r = S.solve(h, st);
     for (int i = 0; i < nv; i++) y[i] = S.y[i];
     *iters = r.iterations;

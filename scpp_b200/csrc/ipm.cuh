@@ -44,7 +44,7 @@ namespace scpp {
 struct IpmSettings {
     double feastol, abstol, reltol;
     int maxit;
-    int pad_;
+    int stalled_step;   // see sc.cuh: sc_step_fraction
     double warm;     // 0: cold start of every sub-problem (what ECOS does).  0 < warm < 1: when the instance has a previous sub-problem
                      // solution, start from that interior point pulled back from the boundary, (s,z) <- warm*(s,z) + (1-warm)*e,
                      // and skip the least-squares start.  Same optimum (parity-tested), ~2.8x fewer interior-point iterations.
@@ -218,6 +218,9 @@ struct Ipm {
     // with free_final_time = false (SCProblem.cpp:27-35,49-56,82-100: no sigma / delta_sigma variables; the fixed-time z_k of
     // discretizationImplementation.hpp:111-116 equals z_k + s_k sigbar of the free-time tile, so K1 is unchanged).  scvx implies sig_fixed.
     bool sig_fixed = false;
+    // fraction of the step to the cone boundary taken by an iterate (ECOS / CVXOPT: 0.99); sc.cuh: sc_step_fraction may raise it for the
+    // sub-problem after a stalled outer iteration (experiment knob ipm.stalled_step, default off)
+    double step_frac = 0.99;
     // ---- workspace (global memory, per instance) -------------------------------------------------------------------
     double *prim, *dprim, *rx, *best_;
     double *s, *z, *wb, *lam, *rz, *cr, *dz, *ds;
@@ -2119,7 +2122,7 @@ struct Ipm {
             const double a_aff = tmax <= 1. ? 1. : 1. / tmax;
             const double sig = (1. - a_aff) * (1. - a_aff) * (1. - a_aff), mu = gap_cur / degree;
             phase_solve(2, 1. - sig, sig * mu, -(1. - sig), tmax);           // combined direction
-            pending = tmax <= 0.99 ? 1. : 0.99 / tmax;
+            pending = tmax <= step_frac ? 1. : step_frac / tmax;
         }
         if (res.status != 0) {
             if (best <= 1e4) copy4(prim, best_, np);
@@ -2225,7 +2228,7 @@ struct Ipm {
     {
         const double tmax = part_max(PT_TCMB);
         set_part(w);
-        pass_update(tmax <= 0.99 ? 1. : 0.99 / tmax);
+        pass_update(tmax <= step_frac ? 1. : step_frac / tmax);
     }
     SCPP_HD void sp_residuals(int w)
     {

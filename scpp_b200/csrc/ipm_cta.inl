@@ -1301,7 +1301,7 @@ SCPP_HD IpmResult cp_solve_subproblem(const IpmSettings &st_, bool have_prev)
         const double a_aff = tmax <= 1. ? 1. : 1. / tmax;
         const double sig = (1. - a_aff) * (1. - a_aff) * (1. - a_aff), mu = gap / deg;
         cp_solve(2, 1. - sig, sig * mu, -(1. - sig), tmax);
-        pending = tmax <= 0.99 ? 1. : 0.99 / tmax;
+        pending = tmax <= step_frac ? 1. : step_frac / tmax;
     }
     if (res.status != 0) {
         if (best <= 1e4) { FOR_CTA(e, np) prim[e] = best_[e]; }

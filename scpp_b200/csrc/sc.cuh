@@ -332,6 +332,18 @@ SCPP_HD IpmSettings sc_ipm_settings(const ScArrays<M> &a, const ScConfig &cfg, i
     }
     return st;
 }
+// the step fraction that goes with the starting point (Ipm::step_frac): 0.99 (ECOS / CVXOPT), or, as an experiment knob (ipm.stalled_step = d > 0),
+// 1 - 10^-d for the close start after a stalled iteration.  Measured at batch 1024 (profiles/README.md): d = 4 takes the stalled sub-problems from
+// 4 to 2 interior-point iterations on average (7.8 instead of 8.45 per instance-iteration) but a few instances per sub-problem then need 20-40, and
+// a round waits for the slowest instance: 383 instead of 157 rounds per step, 26.6 k instead of 46.2 k instance-iterations/s.  Default 0.
+template <class M>
+SCPP_HD double sc_step_fraction(const ScArrays<M> &a, const ScConfig &cfg, int n)
+{
+    if (cfg.ipm.stalled_step <= 0 || !(cfg.ipm.warm > 0.) || sc_ipm_settings(a, cfg, n).warm == cfg.ipm.warm) return 0.99;
+    double f = 1.;
+    for (int d = 0; d < cfg.ipm.stalled_step && d < 8; d++) f *= 0.1;
+    return 1. - f;
+}
 
 // ---- K2 + K3, monolithic: advance the sub-problem of instance n by one slice; when it is solved: K3 ----
 // SCAlgorithm::iterate, SCAlgorithm.cpp:78-131 (the defect print :85-92 is diagnostic only and not computed)
@@ -340,6 +352,7 @@ SCPP_HD void sc_solve_instance(const ScArrays<M> &a, const ScConfig &cfg, int n,
 {
     Ipm<M> ipm;
     sc_bind(a, cfg, n, smem, ipm);
+    ipm.step_frac = sc_step_fraction(a, cfg, n);
     bool finished;
     double *state = a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE;
     const bool have_prev = (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2 && state[Ipm<M>::ST_NOPOINT] == 0.;
@@ -355,6 +368,7 @@ SCPP_HD void sc_solve_instance_cta(const ScArrays<M> &a, const ScConfig &cfg, in
 {
     Ipm<M> ipm;
     sc_bind(a, cfg, n, smem, ipm, true);
+    ipm.step_frac = sc_step_fraction(a, cfg, n);
     double *state = a.ipm_state + (size_t)n * Ipm<M>::IPM_STATE;
     const bool have_prev = (a.iters[n] > 0 || (cfg.algorithm == 1 && a.solves[n] > 0)) && a.status[n] != 2 && state[Ipm<M>::ST_NOPOINT] == 0.;
     cta_sync();                                                              // every thread has read the flags before warp 0 updates them below
@@ -381,6 +395,7 @@ SCPP_HD void sc_split_step(const ScArrays<M> &a, const ScConfig &cfg, int n, dou
     }
     Ipm<M> ipm;
     sc_bind(a, cfg, n, smem, ipm);
+    ipm.step_frac = sc_step_fraction(a, cfg, n);
     if (STEP != SP_START) ipm.dcap = state[Ipm<M>::ST_DCAP];
     IpmResult r;
     if (STEP == SP_START) {

@@ -18,7 +18,7 @@ class ModelParamsHost(C.Structure):
 
 
 class IpmSettings(C.Structure):
-    _fields_ = [("feastol", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("maxit", C.c_int), ("pad_", C.c_int), ("warm", C.c_double)]
+    _fields_ = [("feastol", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("maxit", C.c_int), ("stalled_step", C.c_int), ("warm", C.c_double)]
 
 
 class ScConfig(C.Structure):
