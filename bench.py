@@ -178,8 +178,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="instances per GPU (weak scaling)")
     ap.add_argument("--K", type=int, default=K_BENCH)
     ap.add_argument("--config", default="RocketQuat", choices=["RocketQuat", "RocketQuatStarship"], help="parameter set under configs/ (Starship: BASELINE configs[4], use --K 100 --batch 4096)")
-    ap.add_argument("--solver", type=int, default=int(os.environ.get("SCPP_SOLVER", "0")), choices=[0, 1],
-                    help="K2 mapping: 0 warp per instance in rounds (fastest today), 1 CTA per instance with the factor in shared memory")
+    ap.add_argument("--solver", type=int, default=int(os.environ.get("SCPP_SOLVER", "0")), choices=[0, 1, 2],
+                    help="K2 mapping: 0 warp per instance in rounds, 1 CTA per instance with the factor in shared memory, 2 = 0 with the tail of a solve on 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the cold-start and other-solver measurements (sweeps)")
     ap.add_argument("--algorithm", default="SC", choices=["SC", "SCvx"], help="SC (default, the measured path) or the SCvx variant (no CPU baseline arm)")
@@ -252,7 +252,7 @@ def main():
     # ---- the same workload with cold-started sub-problems, and with the other K2 mapping (single-GPU figures, rank 0's shard on every rank)
     extras = {}
     if not args.no_extras:
-        for key, w, sv in (("cold", 0.0, args.solver), ("other_solver", warm, 1 - args.solver)):
+        for key, w, sv in (("cold", 0.0, args.solver), ("other_solver", warm, 1 if args.solver != 1 else 0)):
             try:
                 e2, c2, _, _ = make_engine(S, args, rank, local, world, w, sv)
             except S.ScppError as ex:
@@ -348,7 +348,7 @@ def main():
             line["value_cold"] = sums[3] / (stats[3] * 1e-3)
             line["warm_start_gain"] = value / line["value_cold"]
         if "other_solver" in extras:
-            line["value_other_solver"] = {"k2_solver": 1 - args.solver, "value": (sums[4] / (stats[4] * 1e-3)) if "ms" in extras["other_solver"] else None,
+            line["value_other_solver"] = {"k2_solver": 1 if args.solver != 1 else 0, "value": (sums[4] / (stats[4] * 1e-3)) if "ms" in extras["other_solver"] else None,
                                           "note": extras["other_solver"].get("unavailable", "same workload and warm start, the other K2 mapping")}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

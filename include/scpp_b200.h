@@ -92,7 +92,10 @@ typedef struct {
      * For SCvx, scpp_b200_get_info returns per outer iteration: norm1_nu, nonlinear cost, rho, trust region used, sub-problem solves,
      * ipm_iterations, ipm_status, pres, dres, relgap. */
     int algorithm;
-    int solver;
+    int solver;       /* K2 mapping.  0 (default): one warp per instance, one interior-point iteration per launch, the batch re-formed in between.
+                         1: one CTA per instance, whole sub-problem per launch, factor in shared memory (K <= ~120).  2: as 0, and in the TAIL of a
+                         solve (fewer unfinished instances than resident CTAs) the sub-problems that start run on mapping 1 -- results then agree
+                         with mapping 0 to solver accuracy, not bit for bit, and depend on the batch composition */
     double scvx_rho_0, scvx_rho_1, scvx_rho_2, scvx_alpha, scvx_beta, scvx_change_threshold, scvx_trust_region;
     int jacobian;     /* how K1 obtains the Jacobian products (computeJacobians, systemDynamics.hpp:206-235): 1 (default) forward-mode dual
                          numbers over the model's generic-scalar flow map -- what CppAD gives the reference, nothing model-specific beyond

@@ -114,7 +114,7 @@ __global__ void k_iota(int *v, int n) { const int i = blockIdx.x * blockDim.x + 
 // per-instance flag bytes the ranks exchange (0 running, 1 converged, 2 failed, 4 iteration limit reached)
 __global__ void k_compact(const int *__restrict__ active, int n_active, const int *__restrict__ converged, const int *__restrict__ iters, int max_it,
                           const double *__restrict__ ipm_state, int state_stride, int *__restrict__ next, int *__restrict__ disc,
-                          int *__restrict__ counters, unsigned char *__restrict__ flags)
+                          int *__restrict__ counters, unsigned char *__restrict__ flags, int *__restrict__ cont = nullptr)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_active) return;
@@ -126,6 +126,7 @@ __global__ void k_compact(const int *__restrict__ active, int n_active, const in
         atomicMin(counters + 2, iters[n]);
         next[atomicAdd(counters, 1)] = n;
         if (ipm_state[(size_t)n * state_stride] == 0.) disc[atomicAdd(counters + 1, 1)] = n;
+        else if (cont) cont[atomicAdd(counters + 3, 1)] = n;               // in the middle of a sub-problem (solver 2: tail rounds)
     }
 }
 // longest-processing-time-first order of the work queue of the CTA-per-instance solver: the instances whose previous sub-problem took the
@@ -267,7 +268,7 @@ struct EngineT : scpp_b200_engine {
     ScArrays<M> a;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    int *active[2] = {nullptr, nullptr}, *disc = nullptr;
+    int *active[2] = {nullptr, nullptr}, *disc = nullptr, *cont = nullptr;
     int *counter = nullptr;               // [0] next active count, [1] instances starting a new sub-problem, [2] fewest outer iterations among the active
     std::vector<int> h_iters;
     std::vector<unsigned char> h_flags;
@@ -285,6 +286,7 @@ struct EngineT : scpp_b200_engine {
     int n_sm = 148;
     ModelParamsHost *d_Pn = nullptr;       // per-instance model parameters (optional)
     size_t cta_smem = 0;
+    bool cta_ok = false;                                    // the shared-memory image of the CTA solver fits (K small enough)
     int cta_per_sm = 1, *queue = nullptr, *lpt = nullptr;   // CTA-per-instance solver: shared-memory image, residency, device-side work queue
     cudaStream_t cstream = nullptr;        // communication stream (flag exchanges)
     cudaEvent_t ev_flags = nullptr;
@@ -335,7 +337,7 @@ struct EngineT : scpp_b200_engine {
         DA(a.info, (size_t)N * cfg.max_iterations * INFO_STRIDE);
         a.hist = nullptr;
         if (cfg.keep_history) DA(a.hist, (size_t)N * (cfg.max_iterations + 1) * a.hist_stride());
-        DA(active[0], N); DA(active[1], N); DA(disc, N); DA(counter, 4); DA(a.ipm_state, (size_t)N * Ipm<M>::IPM_STATE); DA(gcount, 1); DA(flags, N); DA(a.frozen, N);
+        DA(active[0], N); DA(active[1], N); DA(disc, N); DA(cont, N); DA(counter, 4); DA(a.ipm_state, (size_t)N * Ipm<M>::IPM_STATE); DA(gcount, 1); DA(flags, N); DA(a.frozen, N);
         a.trust = a.last_cost = a.n1c = a.Xc = a.Uc = a.costp = nullptr; a.have_last = a.solves = a.phase = nullptr;
         if (cfg.algorithm == 1) {
             DA(a.trust, N); DA(a.last_cost, N); DA(a.n1c, N); DA(a.Xc, (size_t)N * K * NX); DA(a.Uc, (size_t)N * K * NU); DA(a.costp, (size_t)N * K);
@@ -357,8 +359,9 @@ struct EngineT : scpp_b200_engine {
         cta_smem = (size_t)Ipm<M>::cta_sm_doubles(K) * sizeof(double);
         cta_per_sm = (2 * (cta_smem + 1024) <= 227 * 1024) ? 2 : 1;
         if (getenv("SCPP_CTA_PER_SM")) cta_per_sm = atoi(getenv("SCPP_CTA_PER_SM")) == 1 ? 1 : cta_per_sm;      // experiments
-        if (cfg.solver == 1) {
-            if (cta_smem > 227 * 1024) return fail(SCPP_B200_ERR_UNSUPPORTED, "solver = 1 keeps the block factor in shared memory: K too large (use solver = 0)");
+        cta_ok = cta_smem <= 227 * 1024;
+        if (cfg.solver == 1 || (cfg.solver == 2 && cta_ok)) {
+            if (!cta_ok) return fail(SCPP_B200_ERR_UNSUPPORTED, "solver = 1 keeps the block factor in shared memory: K too large (use solver = 0)");
             CU(cudaFuncSetAttribute(k_solve_cta<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cta_smem)));
             CU(cudaFuncSetAttribute(k_solve_cta<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cta_smem)));
             int rc2;
@@ -405,7 +408,7 @@ struct EngineT : scpp_b200_engine {
         launches += 1;
         CU(cudaMemcpyAsync(h_counter, counter, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
-        int n_active = h_counter[0], n_disc = h_counter[0], cur = 0;
+        int n_active = h_counter[0], n_disc = h_counter[0], n_cont = 0, cur = 0;
         const int *disc_list = active[0];                         // first round: every instance starts its first sub-problem
         // Rounds.  A round (1) discretises the instances that start a new sub-problem (K1), (2) advances EVERY unfinished
         // instance by one slice of cfg.ipm_slice interior-point iterations (K2; K3 runs in its epilogue when a sub-problem is
@@ -469,6 +472,26 @@ struct EngineT : scpp_b200_engine {
                     k_sp_test<M><<<(n_active + 3) / 4, 128, 0, stream>>>(a, cfg, lst, n_active);
                     launches += 2;
                 }
+            } else if (cfg.solver == 2 && cta_ok && n_active > 0 && n_active <= n_sm * cta_per_sm) {
+                // solver 2, TAIL of a solve: fewer unfinished instances than CTAs the GPU holds.  A round of the warp solver lasts as long as one
+                // warp needs for one interior-point iteration however few instances it advances, and the last 15 % of the rounds of a 1024-batch
+                // advance a few dozen stragglers.  Here a sub-problem that STARTS in such a round runs on the CTA-per-instance solver (8 warps per
+                // instance, whole sub-problem in this launch); instances in the middle of a sub-problem finish it on the warp solver.  The two
+                // mappings sum in different orders: results agree to solver accuracy, not bit for bit, and which mapping an instance sees depends
+                // on the batch -- hence a knob (cfg.solver = 2), not the default.
+                if (n_disc > 0) {
+                    CU(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+                    const int grid = n_disc < n_sm * cta_per_sm ? n_disc : n_sm * cta_per_sm;
+                    if (cta_per_sm == 2) k_solve_cta<M, 2><<<grid, cta_threads_for(2), cta_smem, stream>>>(a, cfg, disc_list, n_disc, queue);
+                    else k_solve_cta<M, 1><<<grid, cta_threads_for(1), cta_smem, stream>>>(a, cfg, disc_list, n_disc, queue);
+                    launches++;
+                }
+                if (n_cont > 0) {
+                    int wpb = (n_cont + n_sm - 1) / n_sm;
+                    if (wpb > WPB_MAX) wpb = WPB_MAX;
+                    k_solve<M, WPB_MAX, 1><<<(n_cont + wpb - 1) / wpb, wpb * 32, (size_t)wpb * Ipm<M>::sm_doubles() * sizeof(double), stream>>>(a, cfg, cont, n_cont);
+                    launches++;
+                }
             } else
             if (n_active > 0) {
                 // one warp per instance.  Small batches: spread the warps evenly, one CTA per SM (a batch of 1024 on 148 SMs is
@@ -491,12 +514,13 @@ struct EngineT : scpp_b200_engine {
             CU(cudaEventRecord(ev[3], stream));
             CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), stream));
             CU(cudaMemsetAsync(counter + 2, 0x7f, sizeof(int), stream));
+            CU(cudaMemsetAsync(counter + 3, 0, sizeof(int), stream));
             if (n_active > 0) {
                 k_compact<<<(n_active + 255) / 256, 256, 0, stream>>>(active[cur], n_active, a.converged, a.iters, cfg.max_iterations, a.ipm_state,
-                                                                     Ipm<M>::IPM_STATE, active[cur ^ 1], disc, counter, flags);
+                                                                     Ipm<M>::IPM_STATE, active[cur ^ 1], disc, counter, flags, cont);
                 launches++;
             }
-            CU(cudaMemcpyAsync(h_counter, counter, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CU(cudaMemcpyAsync(h_counter, counter, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             // The one data-path collective: ncclAllGather of the per-instance flag bytes, ONE PER OUTER ITERATION, and never waited for inside
             // the loop.  Instances are independent, so a rank stops on the completion of its own shard; the exchange only reports the global
             // state.  Every rank issues exactly max_iterations exchanges per solve (a collective needs matching calls): the i-th is enqueued
@@ -511,7 +535,7 @@ struct EngineT : scpp_b200_engine {
             CU(cudaEventElapsedTime(&m1, ev[1], ev[2]));
             CU(cudaEventElapsedTime(&m2, ev[2], ev[3]));
             ms_disc += m1; ms_socp += m2;
-            n_active = h_counter[0]; n_disc = h_counter[1];
+            n_active = h_counter[0]; n_disc = h_counter[1]; n_cont = h_counter[3];
             if (comm && last_chunk) {
                 const int passed = n_active > 0 ? h_counter[2] : cfg.max_iterations;
                 while (exchanges < passed && exchanges < cfg.max_iterations) { int rc = exchange_flags(); if (rc) return rc; }

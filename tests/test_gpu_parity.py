@@ -834,3 +834,21 @@ def test_fixed_final_time_sc_vs_oracle(S):
     eng.solve()
     assert np.all(eng.get_solution()["t"] == params.final_time)
     eng.close()
+
+
+def test_hybrid_tail_solver_vs_oracle_and_warp_solver(S):
+    """cfg.solver = 2: the warp solver, with the sub-problems that start in the TAIL of a solve (fewer unfinished instances than resident CTAs)
+    on the CTA-per-instance solver.  A batch of 200 is a tail from the first round on (every sub-problem on the CTA solver), 1024 switches near
+    the end: same decisions and iteration counts as the warp solver alone, iterates far inside the parity bar; a sample against the oracle"""
+    p, rpy = O.falcon9()
+    plist = [O.rq_perturb(p, rpy, 0x5C99, i) for i in range(90, 94)]
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=6, warm=0.995, cfg_over=dict(solver=2))
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50, max_iterations=15)
+    for N in (200, 1024):
+        xi = S.perturbed_initial_states(x_init, RPY_F9, N)
+        a = _solve_batch(S, "RocketQuat", xi, K=50, max_iterations=15, solver=0, warm=0.995)
+        b = _solve_batch(S, "RocketQuat", xi, K=50, max_iterations=15, solver=2, warm=0.995)
+        assert np.array_equal(a[0]["iterations"], b[0]["iterations"]) and np.array_equal(a[0]["flags"], b[0]["flags"])
+        (Xa, Ua, ta), (Xb, Ub, tb) = a[2], b[2]
+        assert np.abs(Xa - Xb).max() < TOL_X and np.abs(Ua - Ub).max() < TOL_U
+        assert np.array_equal(a[1][:, :, 4], b[1][:, :, 4])                      # same weight-doubling decisions
