@@ -1205,6 +1205,16 @@ SCPP_HD void cp_cone_margin(const double *u, double &mn, double &nrm2)
     nrm2 = r[0];
 }
 SCPP_HD void cp_cone_shift(double *u, double a) { cp_for_cones([&](int o, int, int) { u[o] += a; }); cta_sync(); }
+SCPP_HD void cp_cone_shift_each(double *u, double target)      // see cone_shift_each
+{
+    cp_for_cones([&](int o, int st_, int d) {
+        double t = 0;
+        for (int i = 1; i < d; i++) t += u[o + i * st_] * u[o + i * st_];
+        const double mg = u[o] - sqrt(t);
+        if (mg < target) u[o] += target - mg;
+    });
+    cta_sync();
+}
 
 // starting point (see init_point): 1 = previous interior point pulled back, 2 = least-squares start, 0 = its factorisation failed
 SCPP_HD int cp_init_point(const IpmSettings &st_, bool have_prev)
@@ -1239,7 +1249,7 @@ SCPP_HD int cp_init_point(const IpmSettings &st_, bool have_prev)
     cp_eval_slack(s);
     {
         double mg, n2; cp_cone_margin(s, mg, n2);
-        if (mg <= 1e-8 * fmax(1., sqrt(n2))) cp_cone_shift(s, 1. - mg);
+        if (mg <= 1e-8 * fmax(1., sqrt(n2))) cp_cone_shift_each(s, INIT_MARGIN);
     }
     FOR_CTA(e, m) ds[e] = 0.;
     FOR_CTA(e, np) dprim[e] = 0.;
@@ -1252,7 +1262,7 @@ SCPP_HD int cp_init_point(const IpmSettings &st_, bool have_prev)
     cta_sync();
     {
         double mg, n2; cp_cone_margin(z, mg, n2);
-        if (mg <= 1e-8 * fmax(1., sqrt(n2))) cp_cone_shift(z, 1. - mg);
+        if (mg <= 1e-8 * fmax(1., sqrt(n2))) cp_cone_shift_each(z, INIT_MARGIN);
     }
     return 2;
 }
