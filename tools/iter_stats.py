@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, scpp_b200 as S
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=50)
-cfg.ipm.warm = float(os.environ.get("SCPP_WARM", "0.995"))
+cfg.ipm.warm = float(os.environ.get("SCPP_WARM", "0.995")); cfg.ipm.stalled_step = int(os.environ.get("SCPP_STALLED_STEP", "0"))
 rpy = np.deg2rad([-20.0, 20.0, 0.0])
 xi = S.perturbed_initial_states(x_init, rpy, batch)
 eng = S.SCAlgorithm(model, params, cfg, batch)
