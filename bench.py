@@ -144,12 +144,16 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+K1_JACOBIAN = 2
+
+
 def make_engine(S, args, rank, local, world, warm, solver):
     name = args.config
     model, params, x_init, x_final, cfg = S.load_model(name, K=args.K, algorithm=args.algorithm)
     cfg.ipm.warm = warm
     cfg.ipm.stalled_step = int(os.environ.get("SCPP_STALLED_STEP", "0"))      # experiment knob (scpp_b200.h): default off
     cfg.solver = solver
+    cfg.jacobian = int(os.environ.get("SCPP_JACOBIAN", str(K1_JACOBIAN)))      # K1 path (scpp_b200.h): 2 = hand-derived Jacobian shared by the columns of an interval
     cfg.ipm_slice = int(os.environ.get("SCPP_SLICE", "1"))    # solver 0: interior-point iterations per K2 launch (0: lock-step outer iterations)
     rpy = np.deg2rad([70.0, 0.0, 0.0]) if name == "RocketQuatStarship" else np.deg2rad([-20.0, 20.0, 0.0])      # rpy_init of configs/<name>/model.info
     xi = S.perturbed_initial_states(x_init, rpy, args.batch, first=rank * args.batch)
@@ -330,6 +334,8 @@ def main():
                 "config": {"workload": workload_name(args.K, n_local, args.config) if args.algorithm == "SC" else workload_name(args.K, n_local, args.config).replace("free-final-time SC", "fixed-final-time SCvx").replace("max_iterations=15", f"max_iterations={cfg.max_iterations}"),
                            "batch_per_gpu": n_local, "global_batch": n_local * world, "K": args.K, "parallelism": f"instances sharded x{world}",
                            "l2": f"working set {dev_bytes / 1e6:.0f} MB per GPU >> 126 MB L2 (no flush needed)",
+                           "k1_jacobian": {0: "hand-derived, one thread per column", 1: "dual numbers over the flow map, one thread per column (library default)",
+                                           2: "hand-derived, linearisation shared by the columns of an interval (k_discretize_shared; parity-tested against 0 and 1)"}[cfg.jacobian],
                            "integrator": (f"RK4 x {cfg.nsub}" if cfg.nsub > 0 else f"RK4 x {-cfg.nsub} and x {-2 * cfg.nsub}, Richardson-extrapolated") + " (reference RKF78 x 5)",
                            "ipm_tol": cfg.ipm.feastol, "ipm_warm": warm, "ipm_slice": cfg.ipm_slice, "k2_solver": args.solver,
                            "note": "value: sub-problems warm-started from the previous interior point (engine knob, same optimum); value_cold: every sub-problem "

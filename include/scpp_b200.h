@@ -99,7 +99,9 @@ typedef struct {
     double scvx_rho_0, scvx_rho_1, scvx_rho_2, scvx_alpha, scvx_beta, scvx_change_threshold, scvx_trust_region;
     int jacobian;     /* how K1 obtains the Jacobian products (computeJacobians, systemDynamics.hpp:206-235): 1 (default) forward-mode dual
                          numbers over the model's generic-scalar flow map -- what CppAD gives the reference, nothing model-specific beyond
-                         systemFlowMap; 0 the hand-derived sparse Jacobian of models.cuh (optional fast path, tested equal) */
+                         systemFlowMap; 0 the hand-derived sparse Jacobian of models.cuh (optional fast path, tested equal); 2 the hand-derived
+                         Jacobian evaluated once per right-hand side and shared by the columns of an interval (discretize_shared.cuh: the
+                         fastest K1; models without a hand-derived Jacobian take path 1) */
     int pad3_;
 } scpp_b200_sc_config;
 

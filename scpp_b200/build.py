@@ -12,7 +12,7 @@ OUT = os.path.join(HERE, "libscpp_b200.so")
 # -static-global-template-stub=false: the kernels are explicit instantiations DEFINED in other translation units (kernels_inst.cu) and only
 # declared (extern template) where they are launched
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-static-global-template-stub=false"]
-GROUPS = [(m, g) for m in (0, 3, 1, 2) for g in range(5)]      # models: RocketQuat, RocketQuatRollPlugin (the slow ones first), Rocket2d, Rocket2dPlugin
+GROUPS = [(m, g) for m in (0, 3, 1, 2) for g in range(6)]      # models: RocketQuat, RocketQuatRollPlugin (the slow ones first), Rocket2d, Rocket2dPlugin
 
 
 def needs_build():

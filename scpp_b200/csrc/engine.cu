@@ -108,6 +108,35 @@ __global__ void k_first_list(int *list, int *count, const int *frozen, int *conv
 
 #include "kernels.cuh"
 
+// K1 launch.  jacobian: 1 dual numbers over the flow map (one thread per column), 0 hand-derived Jacobian (same mapping),
+// 2 hand-derived Jacobian with the linearisation shared by the columns of an interval (discretize_shared.cuh; models whose Lin record is
+// a dense generated matrix do not fit its shared-memory stash and take path 1)
+template <class M>
+static cudaError_t launch_discretize(const ScArrays<M> &a, int nsub, int jacobian, int free_time, const int *list, int n, cudaStream_t stream)
+{
+    constexpr int NC = M::NX + 2 * M::NU + 2;
+    if (jacobian == 2 && !k1s_fits<M>()) jacobian = 1;
+    if (jacobian == 2) {
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 64 && !attr_set[dev]) {
+            e = cudaFuncSetAttribute(k_discretize_shared<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k1s_smem_bytes<M>()));
+            if (e != cudaSuccess) return e;
+            attr_set[dev] = true;
+        }
+        const long long pairs = (long long)n * (a.K - 1);
+        k_discretize_shared<M><<<(unsigned)((pairs + K1S_IPB - 1) / K1S_IPB), K1S_THREADS, k1s_smem_bytes<M>(), stream>>>(a, nsub, list, n);
+    } else {
+        const long long thr = (long long)n * (a.K - 1) * NC;
+        if (jacobian) k_discretize<M, true><<<(unsigned)((thr + 127) / 128), 128, 0, stream>>>(a, nsub, free_time, list, n);
+        else k_discretize<M, false><<<(unsigned)((thr + 127) / 128), 128, 0, stream>>>(a, nsub, free_time, list, n);
+    }
+    return cudaGetLastError();
+}
+
+
 __global__ void k_iota(int *v, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) v[i] = i; }
 
 // after a round: the next active list, the instances among them that start a new sub-problem (to be discretised) and the
@@ -419,9 +448,7 @@ struct EngineT : scpp_b200_engine {
         for (long long round = 0; round < max_rounds && n_active > 0; round++) {
             CU(cudaEventRecord(ev[1], stream));
             if (n_disc > 0) {
-                const long long thr = (long long)n_disc * (K - 1) * NC;
-                if (cfg.jacobian) k_discretize<M, true><<<(unsigned)((thr + 127) / 128), 128, 0, stream>>>(a, cfg.nsub, cfg.free_final_time, disc_list, n_disc);
-                else k_discretize<M, false><<<(unsigned)((thr + 127) / 128), 128, 0, stream>>>(a, cfg.nsub, cfg.free_final_time, disc_list, n_disc);
+                CU(launch_discretize<M>(a, cfg.nsub, cfg.jacobian, cfg.free_final_time, disc_list, n_disc, stream));
                 launches++;
             }
             CU(cudaEventRecord(ev[2], stream));
@@ -984,9 +1011,7 @@ static int discretize_hook(int K, int n, int nsub, int jacobian, int device, con
     CU(cudaMalloc((void **)&a.sigma, (size_t)n * 8)); CU(cudaMalloc((void **)&a.par, (size_t)n * M::NP * 8)); CU(cudaMalloc((void **)&a.dd, nd * 8));
     CU(cudaMemcpy(a.X, X, (size_t)n * K * NX * 8, cudaMemcpyHostToDevice)); CU(cudaMemcpy(a.U, U, (size_t)n * K * NU * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(a.sigma, sigma, (size_t)n * 8, cudaMemcpyHostToDevice)); CU(cudaMemcpy(a.par, par, (size_t)n * M::NP * 8, cudaMemcpyHostToDevice));
-    const long long thr = (long long)n * (K - 1) * NC;
-    if (jacobian) k_discretize<M, true><<<(unsigned)((thr + 127) / 128), 128>>>(a, nsub, 1, nullptr, n);
-    else k_discretize<M, false><<<(unsigned)((thr + 127) / 128), 128>>>(a, nsub, 1, nullptr, n);
+    CU(launch_discretize<M>(a, nsub, jacobian, 1, nullptr, n, 0));
     CU(cudaGetLastError());
     std::vector<double> dd(nd);
     CU(cudaMemcpy(dd.data(), a.dd, nd * 8, cudaMemcpyDeviceToHost));

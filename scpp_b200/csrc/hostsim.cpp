@@ -2,7 +2,9 @@
 // Built into tests/_hostsim/libhostsim.so by tests/hostsim.py; never part of libscpp_b200.so and never
 // loaded by the scpp_b200 package: the product has no CPU execution path.
 #include "sc.cuh"
+#include "discretize_shared.cuh"
 #include "lqr.cuh"
+#include <cstddef>
 #include <vector>
 #include <cstring>
 #include <cstdlib>
@@ -14,6 +16,33 @@ template <class M>
 static void run_discretize(int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd, double *ddT = nullptr, int jacobian = 0)
 {
     constexpr int NC = M::NX + 2 * M::NU + 2;
+    if (jacobian == 2) {      // the roles of k_discretize_shared run one after the other, step by step
+        constexpr int NX = M::NX, NU = M::NU;
+        const int S = k1s_steps(nsub);
+        double h0, h1, rdtau;
+        k1s_step_sizes(nsub, K, h0, h1, rdtau);
+        for (int k = 0; k < K - 1; k++) {
+            std::vector<double> stash(k1s_stride<M>()), xs(k1s_xstride<M>()), cols(NC * NX, 0.), colc(NC * NX, 0.);
+            double x[NX], x0[NX], u0[NU], du[NU];
+            for (int i = 0; i < NX; i++) x0[i] = X[NX * k + i];
+            for (int j = 0; j < NU; j++) { u0[j] = U[NU * k + j]; du[j] = U[NU * (k + 1) + j] - u0[j]; }
+            StageLin<M> *rec = reinterpret_cast<StageLin<M> *>(stash.data());
+            for (int s = 0; s < S; s++) {
+                int ns, st;
+                k1s_schedule(nsub, s, ns, st);
+                k1s_chain<M>(x, x0, u0, du, par, sigma, (nsub < 0 && s >= -nsub) ? h1 : h0, rdtau, st, xs.data());
+                for (int sgi = 0; sgi < 4; sgi++) k1s_linearize<M>(xs.data() + sgi * (NX + NU), par, rec[sgi]);
+                for (int c = 0; c < NC; c++) {
+                    int ctype, cidx;
+                    k1s_column_type(NX, NU, c, ctype, cidx);
+                    k1s_consumer_step<M>(&cols[c * NX], &colc[c * NX], 1, ctype, cidx, sigma, h0, h1, rdtau, nsub, s, rec);
+                }
+            }
+            for (int c = 0; c < NC; c++)
+                for (int i = 0; i < NX; i++) dd[(size_t)k * NX * NC + i * NC + c] = cols[c * NX + i];
+        }
+        return;
+    }
     for (int k = 0; k < K - 1; k++)
         for (int c = 0; c < NC; c++) {
             if (jacobian) discretize_column<M, true>(X, U, sigma, par, K, k, c, nsub, 1, dd + (size_t)k * M::NX * NC, ddT, Ipm<M>::ks(K));

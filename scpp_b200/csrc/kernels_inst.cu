@@ -1,5 +1,5 @@
 // scpp_b200/csrc/kernels_inst.cu — explicit instantiation of one group of kernels per translation unit.
-// Compile with -DSCPP_KERNEL_MODEL=0|1|2|3 (RocketQuat | Rocket2d | Rocket2dPlugin | RocketQuatRollPlugin) and -DSCPP_KERNEL_GROUP=0..4 (scpp_b200/build.py runs them in parallel).
+// Compile with -DSCPP_KERNEL_MODEL=0|1|2|3 (RocketQuat | Rocket2d | Rocket2dPlugin | RocketQuatRollPlugin) and -DSCPP_KERNEL_GROUP=0..5 (scpp_b200/build.py runs them in parallel).
 #define SCPP_KERNEL_INST 1
 #include "kernels.cuh"
 
@@ -21,7 +21,9 @@ SCPP_GROUP1(, SCPP_M)
 SCPP_GROUP2(, SCPP_M)
 #elif SCPP_KERNEL_GROUP == 3
 SCPP_GROUP3(, SCPP_M)
-#else
+#elif SCPP_KERNEL_GROUP == 4
 SCPP_GROUP4(, SCPP_M)
+#else
+SCPP_GROUP5(, SCPP_M)
 #endif
 } // namespace scpp

@@ -25,7 +25,8 @@ struct ScConfig {
     int solver;               // K2 mapping.  0: one warp per instance, one interior-point slice per launch (round 1).  1: one CTA per instance,
                               // whole sub-problem per launch, factor in shared memory, persistent CTAs pulling from a queue (round 2, ipm_cta.inl)
     double scvx_rho_0, scvx_rho_1, scvx_rho_2, scvx_alpha, scvx_beta, scvx_change_threshold, scvx_trust_region;
-    int jacobian;             // K1: 1 = forward-mode dual numbers over the model's flow map (default), 0 = the hand-derived sparse Jacobian (models.cuh)
+    int jacobian;             // K1: 1 = forward-mode dual numbers over the model's flow map (default), 0 = the hand-derived sparse Jacobian (models.cuh),
+                              // 2 = hand-derived, linearisation shared by the columns of an interval (discretize_shared.cuh)
     int pad3_;
 };
 constexpr int SCVX_MAX_RESOLVE = 40;   // the reference's re-solve loop of a rejected step has no bound; the engine fails the instance after this many

@@ -683,6 +683,48 @@ def test_dual_number_jacobians_equal_the_hand_derived_ones(S):
     _compare_run(S, "RocketQuat", O.ROCKETQUAT, [p, O.rq_perturb(p, rpy, 0x5C99, 3)], K=50, max_it=4, cfg_over=dict(jacobian=0))
 
 
+def test_shared_linearisation_k1_equals_the_column_kernels(S):
+    """K1 with cfg.jacobian = 2 (discretize_shared.cuh: one producer warp linearises x(tau) a step ahead, 13 consumer warps integrate the
+    columns of 13 intervals out of shared memory) against the column kernels (0: same hand-derived Jacobian; 1: dual numbers) and the
+    RKF78 oracle; batch sizes that leave the last CTA partly empty; a whole SC solve on this path against the oracle"""
+    p, rpy = O.falcon9()
+    r = O.sc_solve(O.ROCKETQUAT, p, O.sc_config(K=50, max_iterations=2))
+    pn, par = _oracle_nondim_par(p)
+    X, U, t = r["X_all"][2], r["U_all"][2], r["t_all"][2]
+    ref = O.discretize(O.ROCKETQUAT, X, U, t, par)
+    rng = np.random.default_rng(11)
+    for n in (1, 3, 37):      # 49, 147, 1813 intervals: none a multiple of 13
+        Xb = X[None] * (1.0 + 1e-3 * rng.standard_normal((n,) + X.shape)); Ub = U[None] * (1.0 + 1e-3 * rng.standard_normal((n,) + U.shape))
+        Xb[0], Ub[0] = X, U
+        tb = t * (1.0 + 0.01 * rng.standard_normal(n)); tb[0] = t
+        for nsub in (-5, 20):
+            a = S.discretize(S.ROCKETQUAT, Xb, Ub, tb, par, nsub=nsub, jacobian=2)
+            b = S.discretize(S.ROCKETQUAT, Xb, Ub, tb, par, nsub=nsub, jacobian=0)
+            c = S.discretize(S.ROCKETQUAT, Xb, Ub, tb, par, nsub=nsub, jacobian=1)
+            for key in ("A", "B", "C", "s", "z"):
+                sc = max(1.0, np.abs(b[key]).max())
+                assert np.abs(a[key] - b[key]).max() <= 1e-13 * sc, (n, nsub, key)
+                assert np.abs(a[key] - c[key]).max() <= 1e-13 * sc, (n, nsub, key)
+                assert np.abs(a[key][0] - ref[key]).max() <= 2e-10 * max(1.0, np.abs(ref[key]).max()), (n, nsub, key)
+    p2 = O.rocket2d()
+    pn2 = O.R2DParams.from_buffer_copy(p2); O.lib().orc_r2d_nondimensionalize(C.byref(pn2))
+    par2 = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(pn2), par2.ctypes.data_as(C.c_void_p))
+    for K in (3, 30):
+        X2 = np.zeros((K, 6)); U2 = np.zeros((K, 2)); t2 = C.c_double()
+        O.lib().orc_r2d_initial_trajectory(C.byref(pn2), K, X2.ctypes.data_as(C.c_void_p), U2.ctypes.data_as(C.c_void_p), C.byref(t2))
+        a = S.discretize(S.ROCKET2D, X2, U2, t2.value, par2, nsub=-5, jacobian=2); b = S.discretize(S.ROCKET2D, X2, U2, t2.value, par2, nsub=-5, jacobian=0)
+        for key in ("A", "B", "C", "s", "z"):
+            assert np.abs(a[key] - b[key]).max() <= 1e-13 * max(1.0, np.abs(b[key]).max()), (K, key)
+    # plugin models (Lin generated by dual numbers, dense): the small one fits the stash, the 14-state one does not and takes path 1
+    a = S.discretize(S.ROCKET2D_PLUGIN, X2, U2, t2.value, par2, nsub=-5, jacobian=2); b = S.discretize(S.ROCKET2D_PLUGIN, X2, U2, t2.value, par2, nsub=-5, jacobian=1)
+    for key in ("A", "B", "C", "s", "z"):
+        assert np.abs(a[key] - b[key]).max() <= 1e-13 * max(1.0, np.abs(b[key]).max()), key
+    a = S.discretize(S.ROCKETQUAT_ROLL, X, U, t, par, nsub=-5, jacobian=2); b = S.discretize(S.ROCKETQUAT_ROLL, X, U, t, par, nsub=-5, jacobian=1)
+    assert all(np.array_equal(a[key], b[key]) for key in a)
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, [p, O.rq_perturb(p, rpy, 0x5C99, 3), O.rq_perturb(p, rpy, 0x5C99, 4)], K=50, max_it=4, cfg_over=dict(jacobian=2))
+    _compare_run(S, "Rocket2D", O.ROCKET2D, [p2], K=30, max_it=15, cfg_over=dict(jacobian=2))
+
+
 def test_per_instance_model_parameters(S):
     """scpp_b200_set_instance_params: every instance of the batch has its own vehicle (inertia, specific impulse, thrust limits, glide
     slope); each one against the oracle run with that instance's parameters"""

@@ -130,6 +130,17 @@ def test_kernel_source_discretisation_vs_oracle():
     rich = H.discretize(0, X, U, t, par, -5)     # the shipped integrator: RK4 x 5 and x 10, Richardson-extrapolated (60 instead of 80 evaluations)
     assert max(np.abs(rich[k] - ref[k]).max() / max(1.0, np.abs(ref[k]).max()) for k in ("A", "B", "C", "s", "z")) < 2e-10
     assert 8 < errs[0] / errs[1] < 24 and 8 < errs[1] / errs[2] < 24   # 4th-order convergence towards the RKF78 result
+    # the shared-linearisation mapping (cfg.jacobian = 2, discretize_shared.cuh): producer one RK4 step ahead, two stash buffers, the
+    # Richardson pair as one 15-step schedule -- same arithmetic as the column kernel with the hand-derived Jacobian
+    for nsub in (-5, 20, 3):
+        shared = H.discretize(0, X, U, t, par, nsub, jacobian=2); column = H.discretize(0, X, U, t, par, nsub, jacobian=0)
+        for k in ("A", "B", "C", "s", "z"):
+            assert np.abs(shared[k] - column[k]).max() <= 1e-13 * max(1.0, np.abs(column[k]).max()), (nsub, k)
+    rng = np.random.default_rng(3)               # Rocket2D (12 columns, dense B record)
+    X2 = rng.normal(size=(9, 6)) * 0.3; U2 = np.column_stack([rng.normal(size=9) * 0.1, 1.0 + rng.random(9)]); par2 = np.array([1.0, 0.02, 0.0, -0.1, 0.0, -0.05])
+    shared = H.discretize(1, X2, U2, 3.0, par2, -5, jacobian=2); column = H.discretize(1, X2, U2, 3.0, par2, -5, jacobian=0)
+    for k in ("A", "B", "C", "s", "z"):
+        assert np.abs(shared[k] - column[k]).max() <= 1e-13 * max(1.0, np.abs(column[k]).max()), k
 
 
 @pytest.mark.parametrize("warm,ipm_slice", [(0.0, 1), (0.995, 1), (0.0, 0), (0.995, 3), (0.0, -1), (0.995, -1)])
