@@ -83,11 +83,13 @@ SCPP_HD void k1s_chain(double *x, const double *x0, const double *u0, const doub
         for (int i = 0; i < NX; i++) x[i] = x0[i];
     }
     const double t0 = st * h, h6 = h * (1. / 6.);
-    double xa[NX], xt[NX], u[NU];
+    // x at the start of the step is the stage-0 point in xs: it is read back from there instead of being held in registers (the chain
+    // keeps the accumulator x[] and the stage point xt[] only)
+    double xt[NX], u[NU];
 #pragma unroll
-    for (int i = 0; i < NX; i++) { xa[i] = x[i]; xt[i] = x[i]; }
-#pragma unroll 1
-    for (int sgi = 0; sgi < 4; sgi++) {
+    for (int i = 0; i < NX; i++) xt[i] = x[i];
+#pragma unroll
+    for (int sgi = 0; sgi < 4; sgi++) {      // unrolled: stage times and weights are immediates
         const double tau = t0 + (sgi == 0 ? 0. : (sgi == 3 ? h : 0.5 * h));
         const double beta = tau * rdtau;
 #pragma unroll
@@ -104,12 +106,10 @@ SCPP_HD void k1s_chain(double *x, const double *x0, const double *u0, const doub
 #pragma unroll
         for (int i = 0; i < NX; i++) {
             const double kx = sigma * L.f[i];
-            xa[i] += wgt * kx;
-            xt[i] = x[i] + nxt * kx;
+            x[i] += wgt * kx;
+            if (sgi < 3) xt[i] = xs[i] + nxt * kx;
         }
     }
-#pragma unroll
-    for (int i = 0; i < NX; i++) x[i] = xa[i];
 }
 
 // LINEARISER: the record of one stage point
