@@ -150,13 +150,14 @@ SCPP_HD int k1s_forcing_offset(int ctype, int cidx)
     return int(offsetof(R, g) / 8);
 }
 
-// CONSUMER: RK4 step `st` (of ns) of one column out of the four stage records
+// CONSUMER: RK4 step `st` of one column out of the four stage records.  sigma is folded into the step:  sigma (A v + w V) h  =  (A v + w V) (sigma h),
+// so a stage costs three fused multiply-adds per element on top of the sparse A v  (w: alpha | beta | 1 / sigma | -1 | 0 by column type)
 template <class M>
-SCPP_HD void k1s_consume(double *col, int ctype, int voff, double sigma, double h, double rdtau, int st, const StageLin<M> *rec)
+SCPP_HD void k1s_consume(double *col, int ctype, int voff, double sigma, double rsigma, double h, double rdtau, int st, const StageLin<M> *rec)
 {
     constexpr int NX = M::NX;
-    const double t0 = st * h, h6 = h * (1. / 6.);
-    const double wa = ctype == 1 ? sigma : 0., wb = ctype == 2 ? sigma : 0., wc = ctype == 3 ? 1. : (ctype == 4 ? -sigma : 0.);
+    const double t0 = st * h, hs = sigma * h, h6 = hs * (1. / 6.);
+    const double wa = ctype == 1 ? 1. : 0., wb = ctype == 2 ? 1. : 0., wc = ctype == 3 ? rsigma : (ctype == 4 ? -1. : 0.);
     double ca[NX], ct[NX];
 #pragma unroll
     for (int i = 0; i < NX; i++) { ca[i] = col[i]; ct[i] = col[i]; }
@@ -164,16 +165,16 @@ SCPP_HD void k1s_consume(double *col, int ctype, int voff, double sigma, double 
     for (int sgi = 0; sgi < 4; sgi++) {      // unrolled: stage weights, record offsets and hold weights fold into immediates
         const double tau = t0 + (sgi == 0 ? 0. : (sgi == 3 ? h : 0.5 * h));
         const double beta = tau * rdtau, alpha = 1. - beta;
-        const double w = wa * alpha + (wb * beta + wc);      // sigma alpha | sigma beta | 1 | -sigma | 0, without a branch on the column type
+        const double w = wa * alpha + (wb * beta + wc);      // without a branch on the column type
         const StageLin<M> &R = rec[sgi];
         const double *V = reinterpret_cast<const double *>(&R) + voff;
         double kc[NX];
         M::A_apply(R.L, ct, kc);
         const double wgt = (sgi == 0 || sgi == 3) ? h6 : 2. * h6;
-        const double nxt = (sgi == 2) ? h : 0.5 * h;
+        const double nxt = (sgi == 2) ? hs : 0.5 * hs;
 #pragma unroll
         for (int i = 0; i < NX; i++) {
-            const double k = sigma * kc[i] + w * V[i];
+            const double k = kc[i] + w * V[i];
             ca[i] += wgt * k;
             kc[i] = col[i] + nxt * k;
         }
@@ -196,7 +197,7 @@ SCPP_HD void k1s_column_type(int NX, int NU, int c, int &ctype, int &cidx)
 // what a consumer does around step s: start of a pass (unit column), the step, and after the last step the Richardson combination.
 // The result of the first pass is parked in colc[i * cstride] (on the GPU: the column's own slot of the output tile, so it holds no registers).
 template <class M>
-SCPP_HD void k1s_consumer_step(double *col, double *colc, int cstride, int ctype, int cidx, double sigma, double h0, double h1, double rdtau, int nsub, int s,
+SCPP_HD void k1s_consumer_step(double *col, double *colc, int cstride, int ctype, int cidx, double sigma, double rsigma, double h0, double h1, double rdtau, int nsub, int s,
                                const StageLin<M> *rec)
 {
     constexpr int NX = M::NX;
@@ -210,7 +211,7 @@ SCPP_HD void k1s_consumer_step(double *col, double *colc, int cstride, int ctype
 #pragma unroll
         for (int i = 0; i < NX; i++) col[i] = (ctype == 0 && i == cidx) ? 1. : 0.;
     }
-    k1s_consume<M>(col, ctype, k1s_forcing_offset<M>(ctype, cidx), sigma, (nsub < 0 && s >= -nsub) ? h1 : h0, rdtau, st, rec);
+    k1s_consume<M>(col, ctype, k1s_forcing_offset<M>(ctype, cidx), sigma, rsigma, (nsub < 0 && s >= -nsub) ? h1 : h0, rdtau, st, rec);
     if (nsub < 0 && s == k1s_steps(nsub) - 1) {      // y = y_2n + (y_2n - y_n) / 15 removes the h^4 term (discretize.cuh)
 #pragma unroll
         for (int i = 0; i < NX; i++) col[i] += (col[i] - colc[i * cstride]) * (1. / 15.);
@@ -285,10 +286,11 @@ __global__ void __launch_bounds__(K1S_THREADS, 1) k_discretize_shared(ScArrays<M
             for (int i = 0; i < NX; i++) col[i] = 0.;
             const int c = lane;
             double *ddk = a.dd + ((size_t)n * (K - 1) + k) * NX * NC;
+            const double rsigma = 1. / sigma;
 #pragma unroll 1
             for (int t = 0; t < S + 2; t++) {
                 if (on && t >= 2)
-                    k1s_consumer_step<M>(col, ddk + c, NC, ctype, cidx, sigma, h0, h1, rdtau, nsub, t - 2,
+                    k1s_consumer_step<M>(col, ddk + c, NC, ctype, cidx, sigma, rsigma, h0, h1, rdtau, nsub, t - 2,
                                          reinterpret_cast<const StageLin<M> *>(LS + ((size_t)(t & 1) * IPB + slot) * STRIDE));
                 __syncthreads();
             }

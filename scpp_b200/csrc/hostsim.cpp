@@ -35,7 +35,7 @@ static void run_discretize(int K, const double *X, const double *U, double sigma
                 for (int c = 0; c < NC; c++) {
                     int ctype, cidx;
                     k1s_column_type(NX, NU, c, ctype, cidx);
-                    k1s_consumer_step<M>(&cols[c * NX], &colc[c * NX], 1, ctype, cidx, sigma, h0, h1, rdtau, nsub, s, rec);
+                    k1s_consumer_step<M>(&cols[c * NX], &colc[c * NX], 1, ctype, cidx, sigma, 1. / sigma, h0, h1, rdtau, nsub, s, rec);
                 }
             }
             for (int c = 0; c < NC; c++)
