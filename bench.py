@@ -317,7 +317,7 @@ def main():
         roof_fp64 = None
         fl = prof.get("r02_fp64_flops.json")
         if fl and fp64 and fl.get("K") == args.K and kname in fl:
-            flops_step = fl[kname]["flop_per_instance_ipm_iteration"] * ipm_iters + fl["k_discretize"]["flop_per_instance_discretization"] * (inst_iters / args.steps)
+            flops_step = fl[kname]["flop_per_instance_ipm_iteration"] * ipm_iters + fl["k_discretize_shared" if cfg.jacobian == 2 and "k_discretize_shared" in fl else "k_discretize"]["flop_per_instance_discretization"] * (inst_iters / args.steps)
             tf = flops_step / (float(np.mean(dev_ms)) * 1e-3) / 1e12
             roof_fp64 = {"bound": "fp64", "achieved": tf, "peak": fp64["dfma_tflops"], "unit": "TFLOP/s", "frac": tf / fp64["dfma_tflops"],
                          "flop_per_instance_iteration": flops_step / max(1.0, inst_iters / args.steps),
