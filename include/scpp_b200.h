@@ -72,7 +72,10 @@ typedef struct {
 typedef struct {
     int K;
     int free_final_time, interpolate_input, nondimensionalize;   /* free_final_time = 0: sigma is not a variable (SCProblem.cpp:27-35), the final time stays
-                                                                     model.info's final_time; interpolate_input = 0 (zero-order hold) returns UNSUPPORTED */
+                                                                     model.info's final_time; interpolate_input = 0 (zero-order hold, discretizationImplementation.hpp:41-50,
+                                                                     SCProblem.cpp:49-56,114-121): SC on RocketQuat / Rocket2D; the reference's U then has K - 1 columns, here
+                                                                     column K - 1 of every returned U is a pinned placeholder that is in no dynamics row (sc.cuh: sc_zoh_pins);
+                                                                     SCvx or a plugin model with it returns UNSUPPORTED */
     double weight_time, weight_trust_region_time, weight_trust_region_trajectory, weight_virtual_control;
     double nu_tol, delta_tol;
     int max_iterations;

@@ -134,8 +134,10 @@ protected:
     void fill(trajectory_data_t &td, const double *X, const double *U, double t) const
     {
         const int K = cfg.K;
-        td.X.assign(K, std::vector<double>(nx)); td.U.assign(K, std::vector<double>(nu));
-        for (int k = 0; k < K; k++) { for (int i = 0; i < nx; i++) td.X[k][i] = X[size_t(k) * nx + i]; for (int i = 0; i < nu; i++) td.U[k][i] = U[size_t(k) * nu + i]; }
+        const int KU = cfg.interpolate_input ? K : K - 1;      // trajectoryData.hpp:27-32: zero-order hold has K - 1 input columns (the engine's column K - 1 is a placeholder)
+        td.X.assign(K, std::vector<double>(nx)); td.U.assign(KU, std::vector<double>(nu));
+        for (int k = 0; k < K; k++) for (int i = 0; i < nx; i++) td.X[k][i] = X[size_t(k) * nx + i];
+        for (int k = 0; k < KU; k++) for (int i = 0; i < nu; i++) td.U[k][i] = U[size_t(k) * nu + i];
         td.t = t;
     }
     int model, nx = 0, nu = 0, np = 0;

@@ -49,6 +49,7 @@ static void dv_push(dvec_t *d, double v)
 
 typedef struct {
     int model, nx, nu, K, free_time;
+    int KU;                     /* input columns: K (first-order hold) or K - 1 (zero-order hold, trajectoryData.hpp:27-32) */
     int has_delta;              /* 1: SC (trust-region epigraph variable delta_k per stage), 0: SCvx */
     int n;                      /* variables */
     int stage_stride, stage_last_sz;
@@ -82,7 +83,9 @@ static void socp_free(socp_t *P)
     free(P->b.v); free(P->hL.v); free(P->hQ.v); free(P->keq.v); free(P->c);
 }
 
-/* ---- buildSCProblem, SCProblem.cpp:6-138 (interpolate_input == true) ---- */
+/* ---- buildSCProblem, SCProblem.cpp:6-138.  Zero-order hold (dd.interpolatedInput() false): no C_k term (:49-52), the trust region of the
+ * last node has no input part (:116-121); the variable layout keeps a column U(:, K-1), which then appears in no row but the equalities that
+ * pin it to zero in build_full (a variable the reference does not have == a variable fixed to a constant that enters nothing) ---- */
 static void build_sc_problem(socp_t *P, const orc_sc_config *cfg, double weight_tr,
                              const double *Xbar, const double *Ubar, double sigmabar,
                              const double *A, const double *B, const double *C, const double *s, const double *z)
@@ -105,7 +108,7 @@ static void build_sc_problem(socp_t *P, const orc_sc_config *cfg, double weight_
             int r = eq_begin(P, -zk[i], iNub(P, k, nx - 1) + 0.5);
             for (int j = 0; j < nx; j++) if (Ak[i + nx * j] != 0.) coo_push(&P->A, r, iX(P, k, j), Ak[i + nx * j]);
             for (int j = 0; j < nu; j++) if (Bk[i + nx * j] != 0.) coo_push(&P->A, r, iU(P, k, j), Bk[i + nx * j]);
-            for (int j = 0; j < nu; j++) if (Ck[i + nx * j] != 0.) coo_push(&P->A, r, iU(P, k + 1, j), Ck[i + nx * j]);
+            if (P->KU == K) for (int j = 0; j < nu; j++) if (Ck[i + nx * j] != 0.) coo_push(&P->A, r, iU(P, k + 1, j), Ck[i + nx * j]);
             if (P->free_time && s[nx * k + i] != 0.) coo_push(&P->A, r, P->iSigma, s[nx * k + i]);
             coo_push(&P->A, r, iNu(P, k, i), 1.);
             coo_push(&P->A, r, iX(P, k + 1, i), -1.);
@@ -131,10 +134,11 @@ static void build_sc_problem(socp_t *P, const orc_sc_config *cfg, double weight_
         P->c[P->iDsigma] += cfg->weight_trust_region_time;       /* :99 */
     }
     for (int k = 0; k < K; k++) {                                /* :102-126 */
-        int r0 = soc_begin(P, 1 + nx + nu);
+        const int with_u = k < P->KU;                            /* :116 */
+        int r0 = soc_begin(P, 1 + nx + (with_u ? nu : 0));
         soc_coef(P, r0, iDelta(P, k), 1.);
         for (int i = 0; i < nx; i++) { soc_const(P, r0 + 1 + i, Xbar[nx * k + i]); soc_coef(P, r0 + 1 + i, iX(P, k, i), -1.); }
-        for (int i = 0; i < nu; i++) { soc_const(P, r0 + 1 + nx + i, Ubar[nu * k + i]); soc_coef(P, r0 + 1 + nx + i, iU(P, k, i), -1.); }
+        if (with_u) for (int i = 0; i < nu; i++) { soc_const(P, r0 + 1 + nx + i, Ubar[nu * k + i]); soc_coef(P, r0 + 1 + nx + i, iU(P, k, i), -1.); }
         P->c[iDelta(P, k)] += weight_tr;                         /* :134 */
     }
 }
@@ -144,7 +148,7 @@ static void fix_var(socp_t *P, int col, double val) { int r = eq_begin(P, val, c
 /* ---- RocketQuat::addApplicationConstraints, rocketQuat.cpp:70-144 ---- */
 static void add_rq_constraints(socp_t *P, const orc_rq_params *p, const double *thrust_dir)
 {
-    const int K = P->K;
+    const int K = P->K, KU = P->KU;      /* KU = v_U.cols() */
     const double gimbal_const = tan(p->gimbal_max), gs_const = tan(p->gamma_gs);      /* :158-160 */
     const double tilt_const = sqrt((1. - cos(p->theta_max)) / 2.);
     for (int i = 0; i < 14; i++) fix_var(P, iX(P, 0, i), p->x_init[i]);              /* :79 */
@@ -164,44 +168,44 @@ static void add_rq_constraints(socp_t *P, const orc_rq_params *p, const double *
         soc_const(P, r0, p->w_B_max);
         for (int i = 0; i < 3; i++) soc_coef(P, r0 + 1 + i, iX(P, k, 11 + i), 1.);
     }
-    fix_var(P, iU(P, K - 1, 0), 0.); fix_var(P, iU(P, K - 1, 1), 0.); fix_var(P, iU(P, K - 1, 3), 0.); /* :109-111 */
+    fix_var(P, iU(P, KU - 1, 0), 0.); fix_var(P, iU(P, KU - 1, 1), 0.); fix_var(P, iU(P, KU - 1, 3), 0.); /* :109-111 */
     if (p->exact_minimum_thrust) {                                                    /* :113-121 */
-        for (int k = 0; k < K; k++) {
+        for (int k = 0; k < KU; k++) {
             int r = lp_begin(P, -p->T_min);
             for (int i = 0; i < 3; i++) { double d = thrust_dir ? thrust_dir[3 * k + i] : (i == 2 ? 1. : 0.); lp_coef(P, r, iU(P, k, i), d); }
         }
     } else {
-        for (int k = 0; k < K; k++) { int r = lp_begin(P, -p->T_min); lp_coef(P, r, iU(P, k, 2), 1.); } /* :125 */
+        for (int k = 0; k < KU; k++) { int r = lp_begin(P, -p->T_min); lp_coef(P, r, iU(P, k, 2), 1.); } /* :125 */
     }
-    for (int k = 0; k < K; k++) {                                                     /* max thrust :129 */
+    for (int k = 0; k < KU; k++) {                                                     /* max thrust :129 */
         int r0 = soc_begin(P, 4);
         soc_const(P, r0, p->T_max);
         for (int i = 0; i < 3; i++) soc_coef(P, r0 + 1 + i, iU(P, k, i), 1.);
     }
-    for (int k = 0; k < K; k++) {                                                     /* gimbal :132-133 */
+    for (int k = 0; k < KU; k++) {                                                     /* gimbal :132-133 */
         int r0 = soc_begin(P, 3);
         soc_coef(P, r0, iU(P, k, 2), gimbal_const); soc_coef(P, r0 + 1, iU(P, k, 0), 1.); soc_coef(P, r0 + 2, iU(P, k, 1), 1.);
     }
     if (p->enable_roll_control) {                                                     /* :135-138 */
-        for (int k = 0; k < K; k++) {
+        for (int k = 0; k < KU; k++) {
             int r = lp_begin(P, p->t_max); lp_coef(P, r, iU(P, k, 3), 1.);
             r = lp_begin(P, p->t_max);     lp_coef(P, r, iU(P, k, 3), -1.);
         }
     } else {                                                                          /* :139-143 */
         for (int k = 0; k < K; k++) fix_var(P, iX(P, k, 13), 0.);
-        for (int k = 0; k < K; k++) fix_var(P, iU(P, k, 3), 0.);
+        for (int k = 0; k < KU; k++) fix_var(P, iU(P, k, 3), 0.);
     }
 }
 
 /* ---- Rocket2d::addApplicationConstraints, rocket2d.cpp:46-84 ---- */
 static void add_r2d_constraints(socp_t *P, const orc_r2d_params *p)
 {
-    const int K = P->K;
+    const int K = P->K, KU = P->KU;
     const double tan_gs = tan(p->gamma_gs);                                           /* :147 */
     if (p->constrain_initial_final) {                                                 /* :53-59 */
         for (int i = 0; i < 6; i++) fix_var(P, iX(P, 0, i), p->x_init[i]);
         for (int i = 0; i < 6; i++) fix_var(P, iX(P, K - 1, i), p->x_final[i]);
-        fix_var(P, iU(P, K - 1, 0), 0.);
+        fix_var(P, iU(P, KU - 1, 0), 0.);
     }
     for (int k = 0; k < K; k++) {                                                     /* glideslope :63-64 (norm of a 1-vector) */
         int r0 = soc_begin(P, 2);
@@ -210,8 +214,8 @@ static void add_r2d_constraints(socp_t *P, const orc_r2d_params *p)
 #define BOX(col, lo, hi) { int r = lp_begin(P, -(lo)); lp_coef(P, r, (col), 1.); r = lp_begin(P, (hi)); lp_coef(P, r, (col), -1.); }
     for (int k = 0; k < K; k++) BOX(iX(P, k, 4), -p->theta_max, p->theta_max)        /* :66-68 */
     for (int k = 0; k < K; k++) BOX(iX(P, k, 5), -p->w_B_max, p->w_B_max)            /* :70-72 */
-    for (int k = 0; k < K; k++) BOX(iU(P, k, 0), -p->gimbal_max, p->gimbal_max)      /* :76-78 */
-    for (int k = 0; k < K; k++) BOX(iU(P, k, 1), p->T_min, p->T_max)                 /* :80-82 */
+    for (int k = 0; k < KU; k++) BOX(iU(P, k, 0), -p->gimbal_max, p->gimbal_max)      /* :76-78 */
+    for (int k = 0; k < KU; k++) BOX(iU(P, k, 1), p->T_min, p->T_max)                 /* :80-82 */
 #undef BOX
 }
 
@@ -224,10 +228,11 @@ static void build_full(socp_t *P, int model, const void *params, const orc_sc_co
     memset(P, 0, sizeof(*P));
     P->model = model; P->K = cfg->K; P->free_time = cfg->free_final_time;
     orc_model_dims(model, &P->nx, &P->nu, &np);
-    if (!cfg->interpolate_input) { fprintf(stderr, "orc: only interpolate_input=true is restated\n"); abort(); }
+    P->KU = cfg->interpolate_input ? P->K : P->K - 1;
     build_sc_problem(P, cfg, weight_tr, Xbar, Ubar, sigmabar, A, B, C, s, z);
     if (model == ORC_MODEL_ROCKETQUAT) add_rq_constraints(P, (const orc_rq_params *)params, thrust_dir);
     else add_r2d_constraints(P, (const orc_r2d_params *)params);
+    for (int k = P->KU; k < P->K; k++) for (int j = 0; j < P->nu; j++) fix_var(P, iU(P, k, j), 0.);   /* the column the reference does not have */
 }
 
 /* merge LP + SOC rows into one G/h */
@@ -563,7 +568,7 @@ int orc_scvx_subproblem(int model, const void *params, int K, double weight_vc, 
     socp_t P;
     int np;
     memset(&P, 0, sizeof(P));
-    P.model = model; P.K = K; P.free_time = 0;
+    P.model = model; P.K = K; P.KU = K; P.free_time = 0;
     orc_model_dims(model, &P.nx, &P.nu, &np);
     build_scvx_problem(&P, weight_vc, trust_region, Ubar, A, B, C, z);
     if (model == ORC_MODEL_ROCKETQUAT) add_rq_constraints(&P, (const orc_rq_params *)params, thrust_dir);   /* SCvxAlgorithm.cpp:56 */

@@ -81,7 +81,7 @@ SCPP_HD void discretize_rhs_ad(const double *x, const double *col, const double 
 // X:[K][NX] U:[K][NU] of one instance; writes column `c` of interval `k` into dd_k (row-major [NX][NC])
 template <class M, bool AD = false>
 SCPP_HD void discretize_column(const double *X, const double *U, double sigma, const double *par, int K, int k, int c,
-                               int nsub, int free_time, double *ddk, double *ddT = nullptr, int KS = 0)
+                               int nsub, int free_time /* bit 0: free final time (unused here), bit 1: zero-order hold */, double *ddk, double *ddT = nullptr, int KS = 0)
 {
     constexpr int NX = M::NX, NU = M::NU, NC = NX + 2 * NU + 2;
     int ctype, cidx;
@@ -94,7 +94,10 @@ SCPP_HD void discretize_column(const double *X, const double *U, double sigma, c
 #pragma unroll
     for (int i = 0; i < NX; i++) x0[i] = X[NX * k + i];
 #pragma unroll
-    for (int j = 0; j < NU; j++) { u0[j] = U[NU * k + j]; du[j] = U[NU * (k + 1) + j] - u0[j]; }
+    // zero-order hold (flags bit 1; discretizationImplementation.hpp:41-50,96-101): the input stays u_k over the interval, the B columns
+    // integrate the whole input matrix (alpha = 1) and the C columns nothing (beta = 0: C_k == 0 exactly)
+    const bool zoh = (free_time & 2) != 0;
+    for (int j = 0; j < NU; j++) { u0[j] = U[NU * k + j]; du[j] = zoh ? 0. : U[NU * (k + 1) + j] - u0[j]; }
     const double dtau = 1. / double(K - 1);
     // nsub > 0: classical RK4 with nsub sub-steps.  nsub < 0: RK4 with n = -nsub and with 2n sub-steps, Richardson-extrapolated
     // (y = y_2n + (y_2n - y_n) / 15 removes the h^4 term): 3n sub-steps for an error below RK4 x 5n (tests/test_host.py).
@@ -117,7 +120,7 @@ SCPP_HD void discretize_column(const double *X, const double *U, double sigma, c
 #pragma unroll 1
             for (int sgi = 0; sgi < 4; sgi++) {
                 const double tau = t0 + (sgi == 0 ? 0. : (sgi == 3 ? h : 0.5 * h));
-                const double beta = tau / dtau, alpha = (dtau - tau) / dtau;
+                const double beta = zoh ? 0. : tau / dtau, alpha = zoh ? 1. : (dtau - tau) / dtau;
 #pragma unroll
                 for (int j = 0; j < NU; j++) u[j] = u0[j] + beta * du[j];
                 if (AD) discretize_rhs_ad<M>(xt, ct, u, par, sigma, ctype, cidx, alpha, beta, kx, kc);
@@ -143,7 +146,6 @@ SCPP_HD void discretize_column(const double *X, const double *U, double sigma, c
             }
         }
     }
-    (void)free_time;
 #pragma unroll
     for (int i = 0; i < NX; i++) ddk[i * NC + c] = col[i];
     if (ddT) {   // the same tile, stage-minor: element (i, c) of interval k at (i*NC + c)*KS + k   (stage-parallel passes of K2)

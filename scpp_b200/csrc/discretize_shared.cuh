@@ -153,7 +153,7 @@ SCPP_HD int k1s_forcing_offset(int ctype, int cidx)
 // CONSUMER: RK4 step `st` of one column out of the four stage records.  sigma is folded into the step:  sigma (A v + w V) h  =  (A v + w V) (sigma h),
 // so a stage costs three fused multiply-adds per element on top of the sparse A v  (w: alpha | beta | 1 / sigma | -1 | 0 by column type)
 template <class M>
-SCPP_HD void k1s_consume(double *col, int ctype, int voff, double sigma, double rsigma, double h, double rdtau, int st, const StageLin<M> *rec)
+SCPP_HD void k1s_consume(double *col, int ctype, int voff, double sigma, double rsigma, double h, double rdtau, int st, const StageLin<M> *rec, bool zoh = false)
 {
     constexpr int NX = M::NX;
     const double t0 = st * h, hs = sigma * h, h6 = hs * (1. / 6.);
@@ -164,7 +164,7 @@ SCPP_HD void k1s_consume(double *col, int ctype, int voff, double sigma, double 
 #pragma unroll
     for (int sgi = 0; sgi < 4; sgi++) {      // unrolled: stage weights, record offsets and hold weights fold into immediates
         const double tau = t0 + (sgi == 0 ? 0. : (sgi == 3 ? h : 0.5 * h));
-        const double beta = tau * rdtau, alpha = 1. - beta;
+        const double beta = zoh ? 0. : tau * rdtau, alpha = 1. - beta;      // zero-order hold: B integrates the whole input matrix, C nothing
         const double w = wa * alpha + (wb * beta + wc);      // without a branch on the column type
         const StageLin<M> &R = rec[sgi];
         const double *V = reinterpret_cast<const double *>(&R) + voff;
@@ -198,7 +198,7 @@ SCPP_HD void k1s_column_type(int NX, int NU, int c, int &ctype, int &cidx)
 // The result of the first pass is parked in colc[i * cstride] (on the GPU: the column's own slot of the output tile, so it holds no registers).
 template <class M>
 SCPP_HD void k1s_consumer_step(double *col, double *colc, int cstride, int ctype, int cidx, double sigma, double rsigma, double h0, double h1, double rdtau, int nsub, int s,
-                               const StageLin<M> *rec)
+                               const StageLin<M> *rec, bool zoh = false)
 {
     constexpr int NX = M::NX;
     int ns, st;
@@ -211,7 +211,7 @@ SCPP_HD void k1s_consumer_step(double *col, double *colc, int cstride, int ctype
 #pragma unroll
         for (int i = 0; i < NX; i++) col[i] = (ctype == 0 && i == cidx) ? 1. : 0.;
     }
-    k1s_consume<M>(col, ctype, k1s_forcing_offset<M>(ctype, cidx), sigma, rsigma, (nsub < 0 && s >= -nsub) ? h1 : h0, rdtau, st, rec);
+    k1s_consume<M>(col, ctype, k1s_forcing_offset<M>(ctype, cidx), sigma, rsigma, (nsub < 0 && s >= -nsub) ? h1 : h0, rdtau, st, rec, zoh);
     if (nsub < 0 && s == k1s_steps(nsub) - 1) {      // y = y_2n + (y_2n - y_n) / 15 removes the h^4 term (discretize.cuh)
 #pragma unroll
         for (int i = 0; i < NX; i++) col[i] += (col[i] - colc[i * cstride]) * (1. / 15.);
@@ -228,7 +228,7 @@ template <class M>
 __host__ __device__ constexpr bool k1s_fits() { return k1s_smem_bytes<M>() <= 160 * 1024; }      // models with a dense generated Lin keep the column kernel
 
 template <class M>
-__global__ void __launch_bounds__(K1S_THREADS, 1) k_discretize_shared(ScArrays<M> a, int nsub, const int *__restrict__ active, int n_active)
+__global__ void __launch_bounds__(K1S_THREADS, 1) k_discretize_shared(ScArrays<M> a, int nsub, int zoh, const int *__restrict__ active, int n_active)
 {
     constexpr int NX = M::NX, NU = M::NU, NC = NX + 2 * NU + 2, IPB = K1S_IPB, STRIDE = k1s_stride<M>(), XSTRIDE = k1s_xstride<M>();
     static_assert(NC <= 32 && IPB <= 16, "one lane per column; a lineariser warp holds two stages of every interval");
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(K1S_THREADS, 1) k_discretize_shared(ScArrays<M
             double x[NX], u0[NU], du[NU];
             const double *X = a.X + (size_t)n * K * NX, *U = a.U + (size_t)n * K * NU;
 #pragma unroll
-            for (int j = 0; j < NU; j++) { u0[j] = U[NU * k + j]; du[j] = U[NU * (k + 1) + j] - u0[j]; }
+            for (int j = 0; j < NU; j++) { u0[j] = U[NU * k + j]; du[j] = zoh ? 0. : U[NU * (k + 1) + j] - u0[j]; }      // zero-order hold: u_k over the interval
 #pragma unroll 1
             for (int t = 0; t < S + 2; t++) {
                 if (on && t < S) {
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(K1S_THREADS, 1) k_discretize_shared(ScArrays<M
             for (int t = 0; t < S + 2; t++) {
                 if (on && t >= 2)
                     k1s_consumer_step<M>(col, ddk + c, NC, ctype, cidx, sigma, rsigma, h0, h1, rdtau, nsub, t - 2,
-                                         reinterpret_cast<const StageLin<M> *>(LS + ((size_t)(t & 1) * IPB + slot) * STRIDE));
+                                         reinterpret_cast<const StageLin<M> *>(LS + ((size_t)(t & 1) * IPB + slot) * STRIDE), zoh != 0);
                 __syncthreads();
             }
             if (on) {

@@ -112,7 +112,7 @@ __global__ void k_first_list(int *list, int *count, const int *frozen, int *conv
 // 2 hand-derived Jacobian with the linearisation shared by the columns of an interval (discretize_shared.cuh; models whose Lin record is
 // a dense generated matrix do not fit its shared-memory stash and take path 1)
 template <class M>
-static cudaError_t launch_discretize(const ScArrays<M> &a, int nsub, int jacobian, int free_time, const int *list, int n, cudaStream_t stream)
+static cudaError_t launch_discretize(const ScArrays<M> &a, int nsub, int jacobian, int free_time /* bit 0: free final time, bit 1: zero-order hold */, const int *list, int n, cudaStream_t stream)
 {
     constexpr int NC = M::NX + 2 * M::NU + 2;
     if (jacobian == 2 && !k1s_fits<M>()) jacobian = 1;
@@ -127,7 +127,7 @@ static cudaError_t launch_discretize(const ScArrays<M> &a, int nsub, int jacobia
             attr_set[dev] = true;
         }
         const long long pairs = (long long)n * (a.K - 1);
-        k_discretize_shared<M><<<(unsigned)((pairs + K1S_IPB - 1) / K1S_IPB), K1S_THREADS, k1s_smem_bytes<M>(), stream>>>(a, nsub, list, n);
+        k_discretize_shared<M><<<(unsigned)((pairs + K1S_IPB - 1) / K1S_IPB), K1S_THREADS, k1s_smem_bytes<M>(), stream>>>(a, nsub, (free_time & 2) != 0, list, n);
     } else {
         const long long thr = (long long)n * (a.K - 1) * NC;
         if (jacobian) k_discretize<M, true><<<(unsigned)((thr + 127) / 128), 128, 0, stream>>>(a, nsub, free_time, list, n);
@@ -448,7 +448,7 @@ struct EngineT : scpp_b200_engine {
         for (long long round = 0; round < max_rounds && n_active > 0; round++) {
             CU(cudaEventRecord(ev[1], stream));
             if (n_disc > 0) {
-                CU(launch_discretize<M>(a, cfg.nsub, cfg.jacobian, cfg.free_final_time, disc_list, n_disc, stream));
+                CU(launch_discretize<M>(a, cfg.nsub, cfg.jacobian, (cfg.free_final_time ? 1 : 0) | (cfg.interpolate_input ? 0 : 2), disc_list, n_disc, stream));
                 launches++;
             }
             CU(cudaEventRecord(ev[2], stream));
@@ -950,8 +950,8 @@ int scpp_b200_create(int model, const scpp_b200_model_params *params, const scpp
         return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: SCvx needs trust_region > 0, alpha > 1, beta > 1");
     if (!params || !cfg || !out || n <= 0) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: bad argument");
     if (cfg->K < 3 || cfg->max_iterations < 1 || cfg->nsub == 0) return fail(SCPP_B200_ERR_ARG, "scpp_b200_create: K >= 3, max_iterations >= 1, nsub != 0 required");
-    if (!cfg->interpolate_input)
-        return fail(SCPP_B200_ERR_UNSUPPORTED, "only interpolate_input = true (first-order hold, the shipped SC.info setting) is built");
+    if (!cfg->interpolate_input && (cfg->algorithm != 0 || (model != SCPP_B200_MODEL_ROCKETQUAT && model != SCPP_B200_MODEL_ROCKET2D)))
+        return fail(SCPP_B200_ERR_UNSUPPORTED, "interpolate_input = false (zero-order hold) is built for the SC algorithm on RocketQuat and Rocket2D (models with a placeholder input, models.cuh)");
     if ((params->enable_roll_control != 0) != (model == SCPP_B200_MODEL_ROCKETQUAT_ROLL))
         return fail(SCPP_B200_ERR_UNSUPPORTED, "enable_roll_control: use model SCPP_B200_MODEL_ROCKETQUAT_ROLL for true, SCPP_B200_MODEL_ROCKETQUAT for false");
     if (scpp_b200_device_count() <= 0) return fail(SCPP_B200_ERR_CUDA, "no CUDA device: libscpp_b200 has no CPU execution path");

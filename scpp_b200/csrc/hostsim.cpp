@@ -13,7 +13,7 @@
 using namespace scpp;
 
 template <class M>
-static void run_discretize(int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd, double *ddT = nullptr, int jacobian = 0)
+static void run_discretize(int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd, double *ddT = nullptr, int jacobian = 0, bool zoh = false)
 {
     constexpr int NC = M::NX + 2 * M::NU + 2;
     if (jacobian == 2) {      // the roles of k_discretize_shared run one after the other, step by step
@@ -25,7 +25,7 @@ static void run_discretize(int K, const double *X, const double *U, double sigma
             std::vector<double> stash(k1s_stride<M>()), xs(k1s_xstride<M>()), cols(NC * NX, 0.), colc(NC * NX, 0.);
             double x[NX], x0[NX], u0[NU], du[NU];
             for (int i = 0; i < NX; i++) x0[i] = X[NX * k + i];
-            for (int j = 0; j < NU; j++) { u0[j] = U[NU * k + j]; du[j] = U[NU * (k + 1) + j] - u0[j]; }
+            for (int j = 0; j < NU; j++) { u0[j] = U[NU * k + j]; du[j] = zoh ? 0. : U[NU * (k + 1) + j] - u0[j]; }
             StageLin<M> *rec = reinterpret_cast<StageLin<M> *>(stash.data());
             for (int s = 0; s < S; s++) {
                 int ns, st;
@@ -35,18 +35,21 @@ static void run_discretize(int K, const double *X, const double *U, double sigma
                 for (int c = 0; c < NC; c++) {
                     int ctype, cidx;
                     k1s_column_type(NX, NU, c, ctype, cidx);
-                    k1s_consumer_step<M>(&cols[c * NX], &colc[c * NX], 1, ctype, cidx, sigma, 1. / sigma, h0, h1, rdtau, nsub, s, rec);
+                    k1s_consumer_step<M>(&cols[c * NX], &colc[c * NX], 1, ctype, cidx, sigma, 1. / sigma, h0, h1, rdtau, nsub, s, rec, zoh);
                 }
             }
             for (int c = 0; c < NC; c++)
-                for (int i = 0; i < NX; i++) dd[(size_t)k * NX * NC + i * NC + c] = cols[c * NX + i];
+                for (int i = 0; i < NX; i++) {
+                    dd[(size_t)k * NX * NC + i * NC + c] = cols[c * NX + i];
+                    if (ddT) ddT[(size_t)(i * NC + c) * Ipm<M>::ks(K) + k] = cols[c * NX + i];
+                }
         }
         return;
     }
     for (int k = 0; k < K - 1; k++)
         for (int c = 0; c < NC; c++) {
-            if (jacobian) discretize_column<M, true>(X, U, sigma, par, K, k, c, nsub, 1, dd + (size_t)k * M::NX * NC, ddT, Ipm<M>::ks(K));
-            else discretize_column<M, false>(X, U, sigma, par, K, k, c, nsub, 1, dd + (size_t)k * M::NX * NC, ddT, Ipm<M>::ks(K));
+            if (jacobian) discretize_column<M, true>(X, U, sigma, par, K, k, c, nsub, zoh ? 3 : 1, dd + (size_t)k * M::NX * NC, ddT, Ipm<M>::ks(K));
+            else discretize_column<M, false>(X, U, sigma, par, K, k, c, nsub, zoh ? 3 : 1, dd + (size_t)k * M::NX * NC, ddT, Ipm<M>::ks(K));
         }
 }
 extern "C" void hs_discretize2(int model, int K, const double *X, const double *U, double sigma, const double *par, int nsub, int jacobian, double *dd)
@@ -55,6 +58,12 @@ extern "C" void hs_discretize2(int model, int K, const double *X, const double *
     else if (model == 2) run_discretize<Rocket2dPlugin>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian);
     else if (model == 3) run_discretize<RocketQuatRollPlugin>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian);
     else run_discretize<Rocket2d>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian);
+}
+
+extern "C" void hs_discretize_zoh(int model, int K, const double *X, const double *U, double sigma, const double *par, int nsub, int jacobian, double *dd)
+{
+    if (model == 0) run_discretize<RocketQuat>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian, true);
+    else run_discretize<Rocket2d>(K, X, U, sigma, par, nsub, dd, nullptr, jacobian, true);
 }
 
 extern "C" void hs_discretize(int model, int K, const double *X, const double *U, double sigma, const double *par, int nsub, double *dd)
@@ -113,7 +122,7 @@ struct HostEngine {
                 active++;
                 if (a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] == 0.)
                     run_discretize<M>(K, a.X + (size_t)n * K * NX, a.U + (size_t)n * K * NU, sigma[n], a.par + (size_t)n * M::NP, cfg.nsub,
-                                      a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K), cfg.jacobian);
+                                      a.dd + (size_t)n * (K - 1) * NX * NC, a.ddT + (size_t)n * Ipm<M>::ddt_doubles(K), cfg.jacobian, !cfg.interpolate_input);
                 if (cfg.solver == 1) {
                     sc_solve_instance_cta<M>(a, cfg, n, smem.data());
                     if (cfg.algorithm == 1) { for (int k = 0; k < K - 1; k++) sc_scvx_cost<M>(a, cfg, n, k); sc_scvx_decide<M>(a, cfg, n); }

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128, 3) k_sp_stage(ScArrays<M> a, ScConfig cfg
     X template __global__ void k_sp_stage<M, SP_RHS> SCPP_ARGS_STAGE(M);                    \
     X template __global__ void k_sp_stage<M, SP_RECOVER> SCPP_ARGS_STAGE(M);                \
     X template __global__ void k_sp_stage<M, SP_UPDATE> SCPP_ARGS_STAGE(M);
-#define SCPP_GROUP5(X, M) X template __global__ void k_discretize_shared<M>(ScArrays<M>, int, const int *, int);
+#define SCPP_GROUP5(X, M) X template __global__ void k_discretize_shared<M>(ScArrays<M>, int, int, const int *, int);
 #define SCPP_ALL_GROUPS(X, M) SCPP_GROUP0(X, M) SCPP_GROUP1(X, M) SCPP_GROUP2(X, M) SCPP_GROUP3(X, M) SCPP_GROUP4(X, M) SCPP_GROUP5(X, M)
 
 #if !defined(SCPP_KERNEL_INST)

@@ -269,6 +269,10 @@ struct RocketQuat {
         for (int i = 11; i < 14; i++) x[i] = a1 * xi[i] + a2 * xf[i];
         u[0] = 0.; u[1] = 0.; u[2] = (cst[8] - cst[11]) / 2.; u[3] = 0.;   // (T_max - T_min)/2  :64
     }
+    // zero-order hold (interpolate_input = false): the reference's U has K - 1 columns; the engine keeps K and pins column K - 1 to this
+    // strictly feasible placeholder, which appears in no dynamics row (sc.cuh: sc_zoh_pins)
+    static constexpr bool ZOH = true;
+    SCPP_HD static void zoh_placeholder_input(const double *cst, double *u) { u[0] = 0.; u[1] = 0.; u[2] = 0.5 * (cst[8] + cst[11]); u[3] = 0.; }
     // fixed variables of node k: bit i set => xi[i] is pinned to val[i]  (rocketQuat.cpp:79,83-89,109-111,141-142)
     SCPP_HD static uint32_t fixed(const ModelParamsHost &, const double *xi, const double *xf, int K, int k, double *val)
     {
@@ -389,6 +393,8 @@ struct Rocket2d {
         for (int i = 0; i < NX; i++) x[i] = a1 * xi[i] + a2 * xf[i];
         u[0] = 0.; u[1] = (cst[7] + (-cst[6])) / 2.;
     }
+    static constexpr bool ZOH = true;
+    SCPP_HD static void zoh_placeholder_input(const double *cst, double *u) { u[0] = 0.; u[1] = 0.5 * (cst[7] - cst[6]); }
     SCPP_HD static uint32_t fixed(const ModelParamsHost &P, const double *xi, const double *xf, int K, int k, double *val)
     {
         uint32_t mask = 0;

@@ -67,6 +67,29 @@ struct ScArrays {
     SCPP_HD size_t hist_stride() const { return (size_t)K * NB + 1; }
 };
 
+// ---- zero-order-hold inputs (interpolate_input = false; discretizationImplementation.hpp:41-50, SCProblem.cpp:49-56,114-121) --------
+// The reference then has K - 1 input columns: u_k acts on interval k alone (no C_k), the model's "final input" constraints bind column
+// K - 2 (v_U.col(v_U.cols() - 1), rocketQuat.cpp:109-111) and the trust region of node K - 1 has no input part.  The engine keeps its K-column
+// layout: K1 holds the input over the interval (C_k == 0 exactly, B_k is the whole input matrix), the final-input pins of the model move to
+// node K - 2, and column K - 1 becomes a placeholder -- pinned to a strictly feasible constant, so it is no variable, its constraint rows are
+// constants and its trust-region term is identically zero.  What remains is the reference's problem.
+template <class M>
+SCPP_HD void sc_zoh_pins(const ScArrays<M> &a, const ScConfig &cfg, int n)
+{
+    constexpr int NX = M::NX, NU = M::NU, NB = NX + NU;
+    if (cfg.interpolate_input) return;
+    const int K = a.K;
+    uint32_t *fm = a.fixm + (size_t)n * K;
+    double *fv = a.fixv + (size_t)n * K * NB, *U = a.U + (size_t)n * K * NU;
+    const uint32_t in_bits = ((1u << NU) - 1u) << NX;
+    fm[K - 2] |= fm[K - 1] & in_bits;
+    for (int j = 0; j < NU; j++) if (fm[K - 1] >> (NX + j) & 1u) fv[(K - 2) * NB + NX + j] = fv[(K - 1) * NB + NX + j];
+    double ph[NU];
+    M::zoh_placeholder_input(a.cst + (size_t)n * MAX_CST, ph);
+    fm[K - 1] |= in_bits;
+    for (int j = 0; j < NU; j++) { fv[(K - 1) * NB + NX + j] = ph[j]; U[(K - 1) * NU + j] = ph[j]; }
+}
+
 // ---- K0: nondimensionalise, model parameters, constraint constants, pinned variables, initial guess -------------
 // SCAlgorithm::solve cold start, SCAlgorithm.cpp:138-159
 template <class M>
@@ -86,6 +109,8 @@ SCPP_HD void sc_setup_instance(const ScArrays<M> &a, const ModelParamsHost &P, c
         if (P.exact_minimum_thrust) M::thrust_dir(U + k * NU, td);            // rocketQuat.cpp:162-165
         else { td[0] = 0.; td[1] = 0.; td[2] = 1.; }
     }
+    sc_zoh_pins<M>(a, cfg, n);
+    if (!cfg.interpolate_input && P.exact_minimum_thrust) M::thrust_dir(U + (K - 1) * NU, a.tdir + ((size_t)n * K + K - 1) * 3);
     a.sigma[n] = P.final_time;
     a.w_tr[n] = cfg.weight_trust_region_trajectory;                            // loadParameters(), SCAlgorithm.cpp:148
     a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
@@ -117,6 +142,8 @@ SCPP_HD void sc_warm_instance(const ScArrays<M> &a, const ModelParamsHost &P, co
         double *td = a.tdir + ((size_t)n * K + k) * 3;
         if (P.exact_minimum_thrust) M::thrust_dir(U + k * NU, td); else { td[0] = 0.; td[1] = 0.; td[2] = 1.; }
     }
+    sc_zoh_pins<M>(a, cfg, n);
+    if (!cfg.interpolate_input && P.exact_minimum_thrust) M::thrust_dir(U + (K - 1) * NU, a.tdir + ((size_t)n * K + K - 1) * 3);
     a.iters[n] = 0; a.status[n] = 0; a.converged[n] = 0;
     a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE] = 0.; a.ipm_state[(size_t)n * Ipm<M>::IPM_STATE + Ipm<M>::ST_NOPOINT] = 0.;
     if (cfg.algorithm == 1) { a.solves[n] = 0; a.phase[n] = 0; }   // the radius and last_nonlinear_cost are members the reference does not reset on a warm start

@@ -8,6 +8,9 @@ namespace scpp {
 template <class Derived, int NX_, int NU_>
 struct AutoJacobian {
     struct Lin { double f[NX_]; double A[NX_][NX_]; double B[NX_][NU_]; };
+    // zero-order-hold inputs need a strictly feasible placeholder for the unused last input column: not part of the plugin surface
+    static constexpr bool ZOH = false;
+    SCPP_HD static void zoh_placeholder_input(const double *, double *u) { for (int j = 0; j < NU_; j++) u[j] = 0.; }
     SCPP_HD static void linearize(const double *x, const double *u, const double *par, Lin &L)
     {
         Dual xd[NX_], ud[NU_], fd[NX_];

@@ -128,10 +128,10 @@ def simulate(model, dt, u0, u1, par, x):
     return x
 
 
-def discretize(model, X, U, sigma, par, nsub, jacobian=0):
+def discretize(model, X, U, sigma, par, nsub, jacobian=0, zoh=False):
     nx, nu = DIMS[model]
     K = X.shape[0]
     out = np.zeros((K - 1, nx, nx + 2 * nu + 2))
     p = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(C.c_void_p)
-    lib().hs_discretize2(model, K, p(X), p(U), C.c_double(sigma), p(par), nsub, jacobian, out.ctypes.data_as(C.c_void_p))
+    (lib().hs_discretize_zoh if zoh else lib().hs_discretize2)(model, K, p(X), p(U), C.c_double(sigma), p(par), nsub, jacobian, out.ctypes.data_as(C.c_void_p))
     return dict(A=out[:, :, :nx], B=out[:, :, nx:nx + nu], C=out[:, :, nx + nu:nx + 2 * nu], s=out[:, :, nx + 2 * nu], z=out[:, :, nx + 2 * nu + 1])

@@ -92,7 +92,8 @@ def _compare_run(S, name, model_o, params_list, K, max_it, tol_x=TOL_X, tol_u=TO
         assert sol["iterations"][i] == n, f"instance {i}: iteration count {sol['iterations'][i]} vs oracle {n}"
         assert (sol["flags"][i] == 1) == ro["converged"]
         for it in range(n + 1):
-            dX = np.abs(Xh[i, it] - ro["X_all"][it]).max(); dU = np.abs(Uh[i, it] - ro["U_all"][it]).max()
+            ku = K if ocfg.interpolate_input else K - 1      # zero-order hold: the reference has no input column K - 1 (a pinned placeholder here)
+            dX = np.abs(Xh[i, it] - ro["X_all"][it]).max(); dU = np.abs(Uh[i, it, :ku] - ro["U_all"][it][:ku]).max()
             assert dX < tol_x and dU < tol_u, f"instance {i} iterate {it}: dX {dX:.2e} dU {dU:.2e}"
             report.append((dX, dU))
         # same discrete decisions: weight doubling (SCAlgorithm.cpp:112-115) and convergence test (:131)
@@ -270,8 +271,9 @@ def test_warm_start_and_errors(S):
     assert (warm["flags"] == 1).all() and (warm["iterations"] <= cold["iterations"]).all()
     assert np.allclose(warm["X"], cold["X"], atol=1e-3 * np.abs(cold["X"]).max())
     eng.close()
-    bad = S.default_config(model); bad.interpolate_input = 0      # zero-order-hold inputs are not built: reported, not ignored
-    with pytest.raises(S.ScppError):
+    bad = S.default_config(model); bad.interpolate_input = 0; bad.algorithm = 1      # zero-order-hold inputs are built for SC only: SCvx with them is reported, not ignored
+    bad.scvx_trust_region = 1.0; bad.scvx_alpha = 2.0; bad.scvx_beta = 3.2
+    with pytest.raises(S.ScppError, match="zero-order hold"):
         S.SCAlgorithm(model, params, bad, 1)
 
 
@@ -723,6 +725,25 @@ def test_shared_linearisation_k1_equals_the_column_kernels(S):
     assert all(np.array_equal(a[key], b[key]) for key in a)
     _compare_run(S, "RocketQuat", O.ROCKETQUAT, [p, O.rq_perturb(p, rpy, 0x5C99, 3), O.rq_perturb(p, rpy, 0x5C99, 4)], K=50, max_it=4, cfg_over=dict(jacobian=2))
     _compare_run(S, "Rocket2D", O.ROCKET2D, [p2], K=30, max_it=15, cfg_over=dict(jacobian=2))
+
+
+def test_zero_order_hold_inputs(S):
+    """interpolate_input = false (discretizationImplementation.hpp:41-50,96-101; SCProblem.cpp:49-56,114-121; final-input constraints on
+    column K - 2, rocketQuat.cpp:109-111): every iterate against the oracle's literal K - 1 input columns, on both K1 paths and both models"""
+    _compare_run(S, "Rocket2D", O.ROCKET2D, [O.rocket2d()], K=30, max_it=15, cfg_over=dict(interpolate_input=0))
+    p, rpy = O.falcon9()
+    plist = [p, O.rq_perturb(p, rpy, 0x5C99, 3), O.rq_perturb(p, rpy, 0x5C99, 5)]
+    for jac in (1, 2):
+        _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist, K=50, max_it=5, cfg_over=dict(interpolate_input=0, jacobian=jac))
+    _compare_run(S, "RocketQuat", O.ROCKETQUAT, plist[:2], K=50, max_it=5, cfg_over=dict(interpolate_input=0, jacobian=2), warm=0.995)
+    model, params, x_init, x_final, cfg = S.load_model("RocketQuat", K=20, max_iterations=3, keep_history=1, interpolate_input=0)
+    eng = S.SCAlgorithm(model, params, cfg, 2)
+    eng.set_boundary_states(np.array([list(q.x_init) for q in plist[:2]]), x_final)
+    eng.solve()
+    Xh, Uh, th = eng.get_all_solutions(); sol = eng.get_solution()
+    assert np.array_equal(Uh[:, 1:, 19], Uh[:, :-1, 19]) and (Uh[:, :, 19, 2] > 0).all()      # the placeholder column never moves
+    assert np.abs(sol["U"][:, 18, [0, 1, 3]]).max() < 1e-9                                  # u_x = u_y = torque = 0 on the last real column
+    eng.close()
 
 
 def test_per_instance_model_parameters(S):

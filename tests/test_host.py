@@ -166,6 +166,46 @@ def test_kernel_source_sc_loop_vs_oracle(name, model, K, max_it, warm, ipm_slice
     assert np.allclose(rh["X"][0], ro["X"], rtol=1e-6, atol=1e-4 * np.abs(ro["X"]).max())
 
 
+@pytest.mark.parametrize("name,model,K,max_it", [("Rocket2D", 1, 30, 15), ("RocketQuat", 0, 20, 5)])
+def test_kernel_source_zero_order_hold_vs_oracle(name, model, K, max_it):
+    """interpolate_input = false (discretizationImplementation.hpp:41-50,96-101; SCProblem.cpp:49-56,114-121; the model's final-input
+    constraints on column K - 2): the engine's K-column layout with a pinned placeholder column against the oracle's literal K - 1 columns,
+    iterate by iterate; the discretisation alone against the oracle's zero-order-hold RKF78"""
+    p = O.falcon9()[0] if model == 0 else O.rocket2d()
+    ocfg = O.sc_config(K=K, model=model, max_iterations=max_it)
+    foh = O.sc_solve(model, p, ocfg)
+    ocfg.interpolate_input = 0
+    ro = O.sc_solve(model, p, ocfg)
+    if model == 0:
+        pn = O.RQParams.from_buffer_copy(p); O.lib().orc_rq_nondimensionalize(C.byref(pn))
+        par = np.zeros(10); O.lib().orc_rq_model_par(C.byref(pn), par.ctypes.data_as(C.c_void_p))
+    else:
+        pn = O.R2DParams.from_buffer_copy(p); O.lib().orc_r2d_nondimensionalize(C.byref(pn))
+        par = np.zeros(6); O.lib().orc_r2d_model_par(C.byref(pn), par.ctypes.data_as(C.c_void_p))
+    Xm, Um, tm = ro["X_all"][2], ro["U_all"][2], ro["t_all"][2]
+    ref = O.discretize(model, Xm, Um, tm, par, foh=False)
+    for jac in (0, 1, 2):          # all three K1 paths hold the input: B is the whole input matrix, C is exactly zero
+        got = H.discretize(model, Xm, Um, tm, par, -5, jacobian=jac, zoh=True)
+        for key in ("A", "B", "s", "z"):
+            assert np.abs(got[key] - ref[key]).max() <= 2e-10 * max(1.0, np.abs(ref[key]).max()), (jac, key)
+        assert not got["C"].any()
+    k = K // 2                   # linear model == nonlinear propagation with the input held, at the linearisation point
+    lin = ref["A"][k] @ Xm[k] + ref["B"][k] @ Um[k] + ref["s"][k] * tm + ref["z"][k]
+    assert np.allclose(lin, O.simulate(model, tm / (K - 1), Um[k], Um[k], par, Xm[k]), atol=1e-9)
+    P, xi, xf = H.params_from_oracle(model, p)
+    rh = H.sc_solve(model, P, H.sc_config(ocfg, tol=1e-8, warm=0.0, ipm_slice=1), xi, xf)
+    n = ro["iterations"]
+    assert n > 0 and rh["iters"][0] == n and bool(rh["converged"][0] == 1) == ro["converged"]
+    assert np.abs(ro["X_all"][n] - foh["X_all"][min(n, foh["iterations"])]).max() > 1e-4          # the two holds are different problems
+    for it in range(1, n + 1):
+        assert np.abs(rh["X_all"][0, it] - ro["X_all"][it]).max() < 1e-5, it
+        assert np.abs(rh["U_all"][0, it, :K - 1] - ro["U_all"][it][:K - 1]).max() < 1e-4, it     # column K - 1: placeholder here, absent in the reference
+    for it in range(n):
+        assert rh["info"][0, it, 4] == ro["info"][it].weight_tr_used
+        assert int(rh["info"][0, it, 6]) in (0, 3)
+        assert abs(rh["info"][0, it, 0] - ro["info"][it].norm1_nu) < 1e-6 and abs(rh["info"][0, it, 1] - ro["info"][it].sum_delta) < 1e-5 * max(1.0, ro["info"][it].sum_delta)
+
+
 def test_sliced_solver_is_bit_identical_to_unsliced():
     """parking the interior-point state between launches (cfg.ipm_slice) must not change a single bit of the iterates"""
     p, _ = O.falcon9()
