@@ -180,16 +180,21 @@ struct Ipm {
     SCPP_HD static int ddt_doubles(int K) { return NX * NC * ks(K); }
     // Shared window of a warp.  Front: per-solve tables and small vectors (every kernel).  Then a union:
     //   inline factorisation (monolithic kernel):  two tile buffers | record out | L_{k,k-1} | H | O | model terms
-    //   substitutions / chain factorisation:       ring of three records | L_{k,k-1} | Linv scratch
+    //   substitutions / chain factorisation:       ring of RING records | L_{k,k-1} | Linv scratch
     //   assembly kernel (one warp per stage):      tile | carry data of interval k-1 | H | O | model terms
     static constexpr int HNC = pad2(NX + NX * NU + NU * NU);      // D | D C | C' D C  of the previous interval
+#ifndef SCPP_RING
+#define SCPP_RING 3
+#endif
+    static constexpr int RING = SCPP_RING;      // factor records in flight in the substitutions (3 or 4).  4 was measured (profiles/README, r03h): no faster by itself, and the
+                                                // 213 KB of shared memory it needs per CTA leave 28 KB of L1 instead of 60 KB: K2 11 % slower
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
     static constexpr int W_CST = 0, W_RCQ = W_CST + pad2(MAX_CST + 4), W_RIDX = W_RCQ + 4 * NROW, W_REV = W_RIDX + pad2(2 * NROW),
                          W_SC = W_REV + pad2(2 * NB), W_VEC = W_SC + 32, W_X = W_VEC + 6 * NB, W_WB = W_X + 2 * pad2(NX), W_HN = W_WB + pad2(RS),
                          W_U = W_HN + HNC,
                          W_DD = W_U, W_FAC = W_DD + 2 * pad2(NX * NCP), W_LP = W_FAC + FS, W_MAT = W_LP + BLK, W_RK = W_MAT + 2 * BLK,
                          W_F_END = W_RK + 2 * NRK * NB,
-                         W_RING = W_U, W_CLP = W_RING + 3 * FS, W_CLI = W_CLP + BLK, W_C_END = W_CLI + BLK,
+                         W_RING = W_U, W_CLP = W_RING + RING * FS, W_CLI = W_CLP + BLK, W_C_END = W_CLI + BLK,
                          AW_DD = W_U, AW_PC = AW_DD + pad2(NX * NCP), AW_MAT = AW_PC + pad2(NX * NU + 3 * NX), AW_RK = AW_MAT + 2 * BLK,
                          AW_END = AW_RK + 2 * NRK * NB,
                          W_END = cmax(W_F_END, W_C_END);
@@ -296,7 +301,8 @@ struct Ipm {
     SCPP_HD void ld_wait(int pending = 0) const   // all but the `pending` most recent groups have landed
     {
 #if defined(__CUDA_ARCH__)
-        if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        if (pending == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
         else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
@@ -1512,21 +1518,26 @@ struct Ipm {
         double *const gv_ = gv;
         const int K_ = K, KS_ = KS;
         double *fcur = vec(0), *tmp = vec(1);
-        double *const v0 = vec(2), *const v1 = vec(3), *const v2 = vec(4), *const fb0 = fbuf(0), *const fb1 = fbuf(1), *const fb2 = fbuf(2);
-        auto vecr = [&](int i) { return i == 0 ? v0 : (i == 1 ? v1 : v2); };
-        auto fbr = [&](int i) { return i == 0 ? fb0 : (i == 1 ? fb1 : fb2); };
+        static_assert(RING == 3 || RING == 4, "ring of three or four records");
+        constexpr int R = RING, AH = RING - 1;      // AH records ahead of the stage being processed
+        double *const v0 = vec(2), *const v1 = vec(3), *const v2 = vec(4), *const v3 = vec(5);
+        double *const fb0 = fbuf(0), *const fb1 = fbuf(1), *const fb2 = fbuf(2), *const fb3 = fbuf(R - 1);
+        auto vecr = [&](int i) { return i == 0 ? v0 : (i == 1 ? v1 : (i == 2 ? v2 : v3)); };
+        auto fbr = [&](int i) { return i == 0 ? fb0 : (i == 1 ? fb1 : (i == 2 ? fb2 : fb3)); };
         double ldot = 0;
         // group of record r carries the right-hand side of stage r+1 (needed at the end of stage r)
-        ld(fb0, fac_, FS); if (K_ > 1) ld_col(vecr(1 % 3), gv_ + 1, KS_); ld_commit();
-        if (K_ > 1) { ld(fb1, fac_ + FS, FS); if (K_ > 2) ld_col(vecr(2 % 3), gv_ + 2, KS_); }
-        ld_commit();
+#pragma unroll
+        for (int r = 0; r < AH; r++) {
+            if (r < K_) { ld(fbr(r), fac_ + (size_t)r * FS, FS); if (r + 1 < K_) ld_col(vecr((r + 1) % R), gv_ + r + 1, KS_); }
+            ld_commit();
+        }
         FOR_LANE(jj, NB) tmp[jj] = gv_[jj * KS_];
 #pragma unroll 1
         for (int k = 0; k < K_; k++) {
-            if (k + 2 < K_) { ld(fbr((k + 2) % 3), fac_ + (size_t)(k + 2) * FS, FS); if (k + 3 < K_) ld_col(vecr((k + 3) % 3), gv_ + k + 3, KS_); }
+            if (k + AH < K_) { ld(fbr((k + AH) % R), fac_ + (size_t)(k + AH) * FS, FS); if (k + AH + 1 < K_) ld_col(vecr((k + AH + 1) % R), gv_ + k + AH + 1, KS_); }
             ld_commit();
-            ld_wait(2);
-            const double *F = fbr(k % 3), *Ln = F + OFF_LN, *gn = vecr((k + 1) % 3);
+            ld_wait(AH);
+            const double *F = fbr(k % R), *Ln = F + OFF_LN, *gn = vecr((k + 1) % R);
             FOR_LANE(jj, NB) {
                 double v = 0, v2_ = 0;
 #pragma unroll
@@ -1561,22 +1572,26 @@ struct Ipm {
         const uint32_t *const fixm_ = fixm;
         const int K_ = K, KS_ = KS;
         double *ynext = vec(0), *tmp = vec(1);
-        double *const v0 = vec(2), *const v1 = vec(3), *const v2 = vec(4), *const fb0 = fbuf(0), *const fb1 = fbuf(1), *const fb2 = fbuf(2);
-        auto vecr = [&](int i) { return i == 0 ? v0 : (i == 1 ? v1 : v2); };
-        auto fbr = [&](int i) { return i == 0 ? fb0 : (i == 1 ? fb1 : fb2); };
-        ld(fbr((K_ - 1) % 3), fac_ + (size_t)(K_ - 1) * FS, FS); ld_col(vecr((K_ - 1) % 3), gv_ + K_ - 1, KS_); ld_commit();
-        if (K_ > 1) { ld(fbr((K_ - 2) % 3), fac_ + (size_t)(K_ - 2) * FS, FS); ld_col(vecr((K_ - 2) % 3), gv_ + K_ - 2, KS_); }
-        ld_commit();
+        constexpr int R = RING, AH = RING - 1;
+        double *const v0 = vec(2), *const v1 = vec(3), *const v2 = vec(4), *const v3 = vec(5);
+        double *const fb0 = fbuf(0), *const fb1 = fbuf(1), *const fb2 = fbuf(2), *const fb3 = fbuf(R - 1);
+        auto vecr = [&](int i) { return i == 0 ? v0 : (i == 1 ? v1 : (i == 2 ? v2 : v3)); };
+        auto fbr = [&](int i) { return i == 0 ? fb0 : (i == 1 ? fb1 : (i == 2 ? fb2 : fb3)); };
+#pragma unroll
+        for (int r = 1; r <= AH; r++) {
+            if (K_ - r >= 0) { ld(fbr((K_ - r) % R), fac_ + (size_t)(K_ - r) * FS, FS); ld_col(vecr((K_ - r) % R), gv_ + K_ - r, KS_); }
+            ld_commit();
+        }
         uint32_t mk_next = fixm_[K_ - 1];
 #pragma unroll 1
         for (int k = K_ - 1; k >= 0; k--) {
             const bool hasint = k < K_ - 1;
-            if (k >= 2) { ld(fbr((k - 2) % 3), fac_ + (size_t)(k - 2) * FS, FS); ld_col(vecr((k - 2) % 3), gv_ + k - 2, KS_); }
+            if (k >= AH) { ld(fbr((k - AH) % R), fac_ + (size_t)(k - AH) * FS, FS); ld_col(vecr((k - AH) % R), gv_ + k - AH, KS_); }
             ld_commit();
             const uint32_t mk = mk_next;
             if (k > 0) mk_next = fixm_[k - 1];
-            ld_wait(2);
-            const double *F = fbr(k % 3), *fk = vecr(k % 3);
+            ld_wait(AH);
+            const double *F = fbr(k % R), *fk = vecr(k % R);
             FOR_LANE(jj, NB) {
                 double v = fk[jj] - F[OFF_L + jj] * ysig;
                 if (hasint) {
