@@ -377,6 +377,8 @@ struct EngineT : scpp_b200_engine {
         CU(cudaMallocHost((void **)&h_counter, 4 * sizeof(int)));
         CU(cudaMallocHost((void **)&h_gcount, sizeof(unsigned long long)));
         CU(cudaFuncSetAttribute(k_solve<M, WPB_MAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WPB_MAX * Ipm<M>::sm_doubles() * sizeof(double))));
+        if (const char *cv = getenv("SCPP_CARVEOUT"))      // experiment knob: shared-memory share of the 256 KB L1 / shared array in percent (the rest is L1)
+            CU(cudaFuncSetAttribute(k_solve<M, WPB_MAX, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
         {
             const int wsm = int(WPB_MAX * Ipm<M>::sm_doubles() * sizeof(double));
             CU(cudaFuncSetAttribute(k_sp_warp<M, SP_START, WPB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsm));
