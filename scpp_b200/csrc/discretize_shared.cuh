@@ -8,9 +8,9 @@
 // Here a CTA owns IPB intervals and splits the ROLES between warps:
 //   * one CHAIN warp, lane i <-> interval i: integrates x(tau) alone (f only), TWO RK4 steps ahead of the columns, and leaves the four
 //     stage points (x, u) of a step in shared memory;
-//   * two LINEARISER warps, lane <-> (interval, stage), ONE step ahead: per stage point a record { Lin (f, sparse A, B), columns of B,
+//   * a LINEARISER warp (two in the large shape), lane <-> (interval, stage), ONE step ahead: per stage point a record { Lin (f, sparse A, B), columns of B,
 //     g = A x + B u } in shared memory (the Jacobian work is off the sequential chain x_s -> f -> x_s+1 and parallel over the stages);
-//   * IPB CONSUMER warps, warp w <-> interval w, lane c <-> column c (coalesced tile stores as before): per stage only their own
+//   * IPB CONSUMER warps (6; 13 in the one-CTA-per-SM shape), warp w <-> interval w, lane c <-> column c (coalesced tile stores as before): per stage only their own
 //     sigma A v + w_c V_c out of the record (A entries by broadcast loads; the forcing vector V_c -- a column of B, f or g -- by lane,
 //     so all column types run the same instructions), and the RK4 update of one 14-vector.
 // Both stashes are double-buffered by step parity; one __syncthreads() per RK4 step hands the buffers on.  The step bodies are SCPP_HD functions, so the host-simulation build
@@ -219,27 +219,38 @@ SCPP_HD void k1s_consumer_step(double *col, double *colc, int cstride, int ctype
 }
 
 #if defined(__CUDACC__)
-constexpr int K1S_IPB = 13;        // intervals per CTA: 13 consumer warps + chain warp + 2 lineariser warps = 512 threads x 128 registers, the register file of an SM
-constexpr int K1S_THREADS = (K1S_IPB + 3) * 32;
+#ifndef SCPP_K1S_SMALL
+#define SCPP_K1S_SMALL 1
+#endif
+// CTA shape.  0: 13 consumer warps + chain warp + 2 lineariser warps (two stages per warp) = 512 threads x 128 registers, one CTA per SM.
+//            1 (default): 6 consumer warps + chain warp + 1 lineariser warp (four stages) = 256 threads, two CTAs per SM: while one CTA
+//               waits at its step barrier for its chain warp the other one runs (measured: 22.1 against 23.9 ms of K1 per bench step)
+constexpr int K1S_LIN = SCPP_K1S_SMALL ? 1 : 2;                // lineariser warps
+constexpr int K1S_IPB = SCPP_K1S_SMALL ? 6 : 13;               // intervals per CTA
+constexpr int K1S_LSH = SCPP_K1S_SMALL ? 3 : 4;                // a lineariser lane: interval = lane & (2^LSH - 1), stage slot = lane >> LSH
+constexpr int K1S_THREADS = (K1S_IPB + 1 + K1S_LIN) * 32;
 
 template <class M>
 __host__ __device__ constexpr size_t k1s_smem_bytes() { return (size_t)2 * K1S_IPB * (k1s_stride<M>() + k1s_xstride<M>()) * sizeof(double); }
 template <class M>
-__host__ __device__ constexpr bool k1s_fits() { return k1s_smem_bytes<M>() <= 160 * 1024; }      // models with a dense generated Lin keep the column kernel
+__host__ __device__ constexpr bool k1s_fits()      // models with a dense generated Lin keep the column kernel (their linearize is NX + NU dual-number passes: too much for one lineariser lane)
+{
+    return k1s_smem_bytes<M>() * (SCPP_K1S_SMALL ? 2 : 1) <= 200 * 1024 && sizeof(typename M::Lin) / 8 <= 128;
+}
 
 template <class M>
-__global__ void __launch_bounds__(K1S_THREADS, 1) k_discretize_shared(ScArrays<M> a, int nsub, int zoh, const int *__restrict__ active, int n_active)
+__global__ void __launch_bounds__(K1S_THREADS, SCPP_K1S_SMALL ? 2 : 1) k_discretize_shared(ScArrays<M> a, int nsub, int zoh, const int *__restrict__ active, int n_active)
 {
     constexpr int NX = M::NX, NU = M::NU, NC = NX + 2 * NU + 2, IPB = K1S_IPB, STRIDE = k1s_stride<M>(), XSTRIDE = k1s_xstride<M>();
-    static_assert(NC <= 32 && IPB <= 16, "one lane per column; a lineariser warp holds two stages of every interval");
+    static_assert(NC <= 32 && IPB <= (1 << K1S_LSH) && K1S_LIN * (32 >> K1S_LSH) == 4, "one lane per column; the lineariser lanes cover four stages of every interval");
     extern __shared__ __align__(16) double stash[];
     if constexpr (k1s_fits<M>()) {
         double *LS = stash;                                   // [2][IPB][STRIDE]   stage records
         double *XS = stash + (size_t)2 * IPB * STRIDE;        // [2][IPB][XSTRIDE]  stage points
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int role = warp < IPB ? 0 : (warp == IPB ? 1 : 2);                 // consumer | chain | lineariser
-        const int slot = role == 0 ? warp : (role == 1 ? lane : (lane & 15));   // interval of this CTA the thread works for
-        const int lstage = 2 * (warp - IPB - 1) + (lane >> 4);                  // lineariser: its stage of the step
+        const int slot = role == 0 ? warp : (role == 1 ? lane : (lane & ((1 << K1S_LSH) - 1)));   // interval of this CTA the thread works for
+        const int lstage = (32 >> K1S_LSH) * (warp - IPB - 1) + (lane >> K1S_LSH);                // lineariser: its stage of the step
         const long long total = (long long)n_active * (a.K - 1);
         const long long p = (long long)blockIdx.x * IPB + slot;
         const bool on = slot < IPB && p < total && (role != 0 || lane < NC);

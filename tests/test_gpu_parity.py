@@ -686,8 +686,8 @@ def test_dual_number_jacobians_equal_the_hand_derived_ones(S):
 
 
 def test_shared_linearisation_k1_equals_the_column_kernels(S):
-    """K1 with cfg.jacobian = 2 (discretize_shared.cuh: one producer warp linearises x(tau) a step ahead, 13 consumer warps integrate the
-    columns of 13 intervals out of shared memory) against the column kernels (0: same hand-derived Jacobian; 1: dual numbers) and the
+    """K1 with cfg.jacobian = 2 (discretize_shared.cuh: per CTA a chain warp integrates x(tau) two steps ahead, a lineariser warp leaves the stage records
+    in shared memory one step ahead, and one column warp per interval integrates the 24 columns out of them) against the column kernels (0: same hand-derived Jacobian; 1: dual numbers) and the
     RKF78 oracle; batch sizes that leave the last CTA partly empty; a whole SC solve on this path against the oracle"""
     p, rpy = O.falcon9()
     r = O.sc_solve(O.ROCKETQUAT, p, O.sc_config(K=50, max_iterations=2))
@@ -695,7 +695,7 @@ def test_shared_linearisation_k1_equals_the_column_kernels(S):
     X, U, t = r["X_all"][2], r["U_all"][2], r["t_all"][2]
     ref = O.discretize(O.ROCKETQUAT, X, U, t, par)
     rng = np.random.default_rng(11)
-    for n in (1, 3, 37):      # 49, 147, 1813 intervals: none a multiple of 13
+    for n in (1, 3, 37):      # 49, 147, 1813 intervals: none a multiple of the 6 (or 13) intervals of a CTA
         Xb = X[None] * (1.0 + 1e-3 * rng.standard_normal((n,) + X.shape)); Ub = U[None] * (1.0 + 1e-3 * rng.standard_normal((n,) + U.shape))
         Xb[0], Ub[0] = X, U
         tb = t * (1.0 + 0.01 * rng.standard_normal(n)); tb[0] = t
