@@ -82,7 +82,7 @@ SCPP_HD void k1s_chain(double *x, const double *x0, const double *u0, const doub
 #pragma unroll
         for (int i = 0; i < NX; i++) x[i] = x0[i];
     }
-    const double t0 = st * h, h6 = h * (1. / 6.);
+    const double t0 = st * h, hs = sigma * h, h6 = hs * (1. / 6.);
     // x at the start of the step is the stage-0 point in xs: it is read back from there instead of being held in registers (the chain
     // keeps the accumulator x[] and the stage point xt[] only)
     double xt[NX], u[NU];
@@ -101,13 +101,12 @@ SCPP_HD void k1s_chain(double *x, const double *x0, const double *u0, const doub
         for (int j = 0; j < NU; j++) o[NX + j] = u[j];
         typename M::Lin L;
         M::linearize(xt, u, par, L);
-        const double wgt = (sgi == 0 || sgi == 3) ? h6 : 2. * h6;
-        const double nxt = (sgi == 2) ? h : 0.5 * h;
+        const double wgt = (sgi == 0 || sgi == 3) ? h6 : 2. * h6;      // sigma folded into the step: h6 = sigma h / 6, hs = sigma h
+        const double nxt = (sgi == 2) ? hs : 0.5 * hs;
 #pragma unroll
         for (int i = 0; i < NX; i++) {
-            const double kx = sigma * L.f[i];
-            x[i] += wgt * kx;
-            if (sgi < 3) xt[i] = xs[i] + nxt * kx;
+            x[i] += wgt * L.f[i];
+            if (sgi < 3) xt[i] = xs[i] + nxt * L.f[i];
         }
     }
 }
