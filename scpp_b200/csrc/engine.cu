@@ -530,6 +530,8 @@ struct EngineT : scpp_b200_engine {
                 int wpb = (n_active + n_sm - 1) / n_sm;
                 if (wpb < 1) wpb = 1;
                 if (wpb > WPB_MAX) wpb = WPB_MAX;
+                // experiment knob SCPP_WPB_BIG: warps per CTA once the instances exceed one wave (fewer warps leave more of the 256 KB array to the L1)
+                if (n_active > n_sm * WPB_MAX) { static const int big = getenv("SCPP_WPB_BIG") ? atoi(getenv("SCPP_WPB_BIG")) : WPB_MAX; if (big >= 1 && big < wpb) wpb = big; }
                 const size_t smem = (size_t)wpb * Ipm<M>::sm_doubles() * sizeof(double);
                 k_solve<M, WPB_MAX, 1><<<(n_active + wpb - 1) / wpb, wpb * 32, smem, stream>>>(a, cfg, active[cur], n_active);
                 launches++;
